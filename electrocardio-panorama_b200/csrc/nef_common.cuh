@@ -1,0 +1,72 @@
+// Shared definitions for the Nef-Net B200 hot path (sm_100a only).
+//
+// Internal activation layout "CBL4" (channel-chunk major, zero halo):
+//   a tensor with C channels (C % 4 == 0), B segments and L samples is an array of float4 rows
+//       T[c4][b * Lp + P + l]   (c4 = channel / 4, lane = channel % 4),  Lp = L + 2 * P, P = NEF_HALO
+//   the P halo rows on each side of every segment are kept zero for the life of the tensor: kernels
+//   never store to them, so a k-tap "same" convolution over the flattened row axis needs no boundary
+//   logic and a tile of rows is one contiguous run of 16-byte rows per channel chunk (bulk-copyable,
+//   and directly a tcgen05 no-swizzle operand: K-major when K = channels, MN-major when K = rows).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define NEF_HALO 3
+#define NEF_GUARD_ROWS 272   // readable rows after (and before) every CBL4 tensor: tiles may overrun
+#define NEF_NROI 7
+#define NEF_ROI_SIZE 16
+
+extern "C" void nef_set_error(const char* fmt, ...);
+
+#define NEF_CHECK_LAUNCH(name)                                                        \
+  do {                                                                                \
+    cudaError_t e__ = cudaGetLastError();                                             \
+    if (e__ != cudaSuccess) {                                                         \
+      nef_set_error("%s: launch failed: %s", name, cudaGetErrorString(e__));          \
+      return 1;                                                                       \
+    }                                                                                 \
+  } while (0)
+
+#define NEF_REQUIRE(cond, ...)          \
+  do {                                  \
+    if (!(cond)) {                      \
+      nef_set_error(__VA_ARGS__);       \
+      return 2;                         \
+    }                                   \
+  } while (0)
+
+namespace nef {
+
+__device__ __forceinline__ float tf32_rn(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
+__device__ __forceinline__ float4 tf32_rn4(float4 v) {
+  return make_float4(tf32_rn(v.x), tf32_rn(v.y), tf32_rn(v.z), tf32_rn(v.w));
+}
+
+__device__ __forceinline__ uint64_t mix64(uint64_t z) {  // splitmix64 finaliser
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+// four 16-bit uniforms for the float4 at (row, chunk) of a tensor; keep lane i iff u_i >= p * 65536
+__device__ __forceinline__ uint64_t drop_bits(uint64_t seed, long row, int c4) {
+  return mix64(seed ^ (uint64_t(row) * 0x9E3779B97F4A7C15ull) ^ (uint64_t(c4) << 40) ^ (uint64_t(c4) * 0xD1B54A32D192ED03ull));
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ float4 operator+(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+__device__ __forceinline__ float4 operator*(float4 a, float4 b) { return make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w); }
+__device__ __forceinline__ float4 operator*(float4 a, float s) { return make_float4(a.x * s, a.y * s, a.z * s, a.w * s); }
+__device__ __forceinline__ float4 f4zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+__device__ __forceinline__ float& f4at(float4& v, int i) { return reinterpret_cast<float*>(&v)[i]; }
+__device__ __forceinline__ float f4get(const float4& v, int i) { return reinterpret_cast<const float*>(&v)[i]; }
+
+}  // namespace nef

@@ -1,0 +1,1059 @@
+// Non-GEMM kernels of the Nef-Net hot path: stem, angular encoding, ROI resampling, latent mixing,
+// BatchNorm passes, the 64->1 output convolution, losses and the optimiser step.
+// Reference lines are cited per kernel (paths relative to the reference's codes/).
+#include "nef_elem.cuh"
+
+namespace nef {
+
+static inline int grid_for(long total, int block, int cap = 148 * 32) {
+  long g = (total + block - 1) / block;
+  if (g < 1) g = 1;
+  if (g > cap) g = cap;
+  return (int)g;
+}
+
+// ===========================================================================================
+// Encoder stem: Conv1d(G -> 128G, k15, s2, p7, groups=G, no bias) -> ReLU -> MaxPool1d(3,2,1)
+// network/encoder/resnet_1d.py:102-105, network/encoder/encoder.py:35-38
+// ===========================================================================================
+constexpr int STEM_TJ = 128;
+
+__global__ void __launch_bounds__(256) stem_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, T4 y,
+                                                       int G, int L) {
+  __shared__ float xs[4 * STEM_TJ + 24];
+  __shared__ float4 ws[15][32];
+  const int tid = threadIdx.x;
+  const int g = blockIdx.y, b = blockIdx.z;
+  const int j0 = blockIdx.x * STEM_TJ;
+  const int L2 = L / 2, L4 = L / 4;
+  const float* xb = x + ((long)b * G + g) * L;
+  for (int i = tid; i < 4 * STEM_TJ + 19; i += 256) {
+    int p = 4 * j0 - 9 + i;
+    xs[i] = (p >= 0 && p < L) ? xb[p] : 0.f;
+  }
+  for (int i = tid; i < 15 * 32; i += 256) {
+    int t = i / 32, c4 = i % 32;
+    const float* wp = w + ((long)g * 128 + c4 * 4) * 15 + t;
+    ws[t][c4] = make_float4(wp[0], wp[15], wp[30], wp[45]);
+  }
+  __syncthreads();
+  const int jl = tid & (STEM_TJ - 1), chalf = tid / STEM_TJ;
+  const int j = j0 + jl;
+  if (j >= L4) return;
+  float xr[19];
+#pragma unroll
+  for (int k = 0; k < 19; ++k) xr[k] = xs[4 * jl + k];
+  const bool v0 = (2 * j - 1) >= 0, v2 = (2 * j + 1) < L2;
+  for (int cc = 0; cc < 16; ++cc) {
+    const int c4 = chalf * 16 + cc;
+    float4 a0 = f4zero(), a1 = f4zero(), a2 = f4zero();
+#pragma unroll
+    for (int t = 0; t < 15; ++t) {
+      const float4 wv = ws[t][c4];
+      a0 = a0 + wv * xr[t];
+      a1 = a1 + wv * xr[2 + t];
+      a2 = a2 + wv * xr[4 + t];
+    }
+    float4 m = a1;
+    if (v0) m = make_float4(fmaxf(m.x, a0.x), fmaxf(m.y, a0.y), fmaxf(m.z, a0.z), fmaxf(m.w, a0.w));
+    if (v2) m = make_float4(fmaxf(m.x, a2.x), fmaxf(m.y, a2.y), fmaxf(m.z, a2.z), fmaxf(m.w, a2.w));
+    m = make_float4(fmaxf(m.x, 0.f), fmaxf(m.y, 0.f), fmaxf(m.z, 0.f), fmaxf(m.w, 0.f));
+    *y.at(g * 32 + c4, b, j) = tf32_rn4(m);
+  }
+}
+
+constexpr int STEMB_TJ = 256;
+
+// weight gradient of the stem (the input needs none): recompute the three conv taps of every pooled
+// output, route the gradient to the first maximum (MaxPool1d) if it is positive (ReLU).
+__global__ void __launch_bounds__(256) stem_bwd_kernel(const float* __restrict__ x, const float* __restrict__ w, T4 dy,
+                                                       float* __restrict__ dw, int G, int L) {
+  __shared__ float xs[4 * STEMB_TJ + 24];
+  __shared__ float sdw[15][128];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = blockIdx.y, b = blockIdx.z;
+  const int j0 = blockIdx.x * STEMB_TJ;
+  const int L2 = L / 2, L4 = L / 4;
+  const float* xb = x + ((long)b * G + g) * L;
+  for (int i = tid; i < 4 * STEMB_TJ + 19; i += 256) {
+    int p = 4 * j0 - 9 + i;
+    xs[i] = (p >= 0 && p < L) ? xb[p] : 0.f;
+  }
+  for (int i = tid; i < 15 * 128; i += 256) (&sdw[0][0])[i] = 0.f;
+  float4 wv[15], acc[15];
+#pragma unroll
+  for (int t = 0; t < 15; ++t) {
+    const float* wp = w + ((long)g * 128 + lane * 4) * 15 + t;
+    wv[t] = make_float4(wp[0], wp[15], wp[30], wp[45]);
+    acc[t] = f4zero();
+  }
+  __syncthreads();
+  for (int jj = 0; jj < 32; ++jj) {
+    const int jl = warp * 32 + jj;
+    const int j = j0 + jl;
+    if (j >= L4) break;
+    const float4 gy = *dy.at(g * 32 + lane, b, j);
+    float xr[19];
+#pragma unroll
+    for (int k = 0; k < 19; ++k) xr[k] = xs[4 * jl + k];
+    float4 a0 = f4zero(), a1 = f4zero(), a2 = f4zero();
+#pragma unroll
+    for (int t = 0; t < 15; ++t) {
+      a0 = a0 + wv[t] * xr[t];
+      a1 = a1 + wv[t] * xr[2 + t];
+      a2 = a2 + wv[t] * xr[4 + t];
+    }
+    const bool v0 = (2 * j - 1) >= 0, v2 = (2 * j + 1) < L2;
+    float4 s0 = f4zero(), s1 = f4zero(), s2 = f4zero();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float c0 = f4get(a0, k), c1 = f4get(a1, k), c2 = f4get(a2, k);
+      int best = 1;
+      float bv = c1;
+      if (v0 && c0 >= c1) { best = 0; bv = c0; }   // first maximum wins (window order 2j-1, 2j, 2j+1)
+      if (v2 && c2 > bv) { best = 2; bv = c2; }
+      const float gk = bv > 0.f ? f4get(gy, k) : 0.f;
+      f4at(s0, k) = best == 0 ? gk : 0.f;
+      f4at(s1, k) = best == 1 ? gk : 0.f;
+      f4at(s2, k) = best == 2 ? gk : 0.f;
+    }
+#pragma unroll
+    for (int t = 0; t < 15; ++t) acc[t] = acc[t] + s0 * xr[t] + s1 * xr[2 + t] + s2 * xr[4 + t];
+  }
+#pragma unroll
+  for (int t = 0; t < 15; ++t) {
+    atomicAdd(&sdw[t][lane * 4 + 0], acc[t].x);
+    atomicAdd(&sdw[t][lane * 4 + 1], acc[t].y);
+    atomicAdd(&sdw[t][lane * 4 + 2], acc[t].z);
+    atomicAdd(&sdw[t][lane * 4 + 3], acc[t].w);
+  }
+  __syncthreads();
+  for (int i = tid; i < 15 * 128; i += 256) {
+    const int t = i / 128, c = i % 128;
+    const float v = sdw[t][c];
+    if (v != 0.f) atomicAdd(dw + ((long)g * 128 + c) * 15 + t, v);
+  }
+}
+
+int stem_fwd(const float* x, const float* w, T4 y, int G, cudaStream_t s) {
+  const int L = y.L * 4;
+  dim3 grid((y.L + STEM_TJ - 1) / STEM_TJ, G, y.B);
+  stem_fwd_kernel<<<grid, 256, 0, s>>>(x, w, y, G, L);
+  NEF_CHECK_LAUNCH("stem_fwd_kernel");
+  return 0;
+}
+int stem_bwd(const float* x, const float* w, T4 dy, float* dw, int G, cudaStream_t s) {
+  const int L = dy.L * 4;
+  dim3 grid((dy.L + STEMB_TJ - 1) / STEMB_TJ, G, dy.B);
+  stem_bwd_kernel<<<grid, 256, 0, s>>>(x, w, dy, dw, G, L);
+  NEF_CHECK_LAUNCH("stem_bwd_kernel");
+  return 0;
+}
+
+// ===========================================================================================
+// Angular encoding + Linear: network/utils/theta_encoder.py:13-29, model_nefnet.py:76-77
+// ===========================================================================================
+__device__ __forceinline__ void theta_feat(const float* th, float* f) {
+  const float a[4] = {th[0], th[1], th[0] + th[1], th[0] - th[1]};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    f[3 * i] = a[i];
+    f[3 * i + 1] = sinf(a[i]);
+    f[3 * i + 2] = cosf(a[i]);
+  }
+}
+
+__global__ void angular_fwd_kernel(const float* __restrict__ theta, const float* __restrict__ w,
+                                   const float* __restrict__ bias, float* __restrict__ out, int n, int D) {
+  const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (i >= (long)n * D) return;
+  const int d = i % D;
+  const long r = i / D;
+  float f[12];
+  theta_feat(theta + r * 2, f);
+  float acc = 0.f;
+#pragma unroll
+  for (int k = 0; k < 12; ++k) acc += f[k] * w[d * 12 + k];
+  out[i] = acc + bias[d];
+}
+
+// one block per output feature d: dw[d][k] += sum_r dout[r][d] feat[r][k], db[d] += sum_r dout[r][d]
+__global__ void __launch_bounds__(128) angular_bwd_kernel(const float* __restrict__ theta, const float* __restrict__ dout,
+                                                          float* __restrict__ dw, float* __restrict__ db, int n, int D) {
+  __shared__ float red[13][4];
+  const int d = blockIdx.x;
+  float acc[13];
+#pragma unroll
+  for (int k = 0; k < 13; ++k) acc[k] = 0.f;
+  for (int r = threadIdx.x; r < n; r += blockDim.x) {
+    float f[12];
+    theta_feat(theta + (long)r * 2, f);
+    const float g = dout[(long)r * D + d];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) acc[k] += g * f[k];
+    acc[12] += g;
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < 13; ++k) {
+    const float v = warp_sum(acc[k]);
+    if (lane == 0) red[k][warp] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 13) {
+    const float v = red[threadIdx.x][0] + red[threadIdx.x][1] + red[threadIdx.x][2] + red[threadIdx.x][3];
+    if (threadIdx.x < 12) dw[d * 12 + threadIdx.x] += v;
+    else db[d] += v;
+  }
+}
+
+int angular_fwd(const float* theta, const float* w, const float* b, float* out, int n, int D, cudaStream_t s) {
+  const long total = (long)n * D;
+  angular_fwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(theta, w, b, out, n, D);
+  NEF_CHECK_LAUNCH("angular_fwd_kernel");
+  return 0;
+}
+int angular_bwd(const float* theta, const float* dout, float* dw, float* db, int n, int D, cudaStream_t s) {
+  angular_bwd_kernel<<<D, 128, 0, s>>>(theta, dout, dw, db, n, D);
+  NEF_CHECK_LAUNCH("angular_bwd_kernel");
+  return 0;
+}
+
+// ===========================================================================================
+// roi_algin (network/utils/roi_pooling_1d.py:38-69).  What it computes: every output is
+// the bilinear read at the CENTRE of the sequence times the tent weight max(0, 1 - |gx| / 2) of the
+// projected roi linspace.  Only the centre columns of z2_conv1's output are live, so that block is
+// evaluated on a window around them (window_extract / window_scatter).
+// ===========================================================================================
+Window centre_window(int L4) {
+  Window w;
+  const float iy = (L4 - 1) * 0.5f;
+  w.y0 = (int)floorf(iy);
+  w.wy1 = iy - w.y0;
+  int lo = w.y0 - 2, hi = w.y0 + 4;
+  if (lo < 0) lo = 0;
+  if (hi > L4) hi = L4;
+  w.w0 = lo;
+  w.Lw = hi - lo;
+  return w;
+}
+
+__global__ void window_extract_kernel(T4 w, T4 xw, int G, Window win) {
+  // xw chunk g*16 + c  <-  w chunk g*32 + 16 + c
+  const long total = (long)G * 16 * xw.B * win.Lw;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int l = i % win.Lw;
+    long r = i / win.Lw;
+    const int b = r % xw.B;
+    const int c = r / xw.B;
+    const int g = c / 16, cc = c % 16;
+    *xw.at(c, b, l) = *w.at(g * 32 + 16 + cc, b, win.w0 + l);
+  }
+}
+
+__global__ void window_scatter_kernel(T4 gxw, T4 gw, int G, Window win) {
+  const long total = (long)G * 16 * gw.B * gw.L;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int l = i % gw.L;
+    long r = i / gw.L;
+    const int b = r % gw.B;
+    const int c = r / gw.B;
+    const int g = c / 16, cc = c % 16;
+    const int lw = l - win.w0;
+    float4 v = f4zero();
+    if (lw >= 0 && lw < win.Lw) v = *gxw.at(c, b, lw);
+    *gw.at(g * 32 + 16 + cc, b, l) = v;
+  }
+}
+
+int window_extract(T4 w, T4 xw, int G, Window win, cudaStream_t s) {
+  const long total = (long)G * 16 * xw.B * win.Lw;
+  window_extract_kernel<<<grid_for(total, 256), 256, 0, s>>>(w, xw, G, win);
+  NEF_CHECK_LAUNCH("window_extract_kernel");
+  return 0;
+}
+int window_scatter(T4 gxw, T4 gw, int G, Window win, cudaStream_t s) {
+  const long total = (long)G * 16 * gw.B * gw.L;
+  window_scatter_kernel<<<grid_for(total, 256), 256, 0, s>>>(gxw, gw, G, win);
+  NEF_CHECK_LAUNCH("window_scatter_kernel");
+  return 0;
+}
+
+// tent weight of sample s of roi j of segment b (roi_pooling_1d.py:50-58 + grid_sample's x interpolation
+// over a width-1 axis)
+__device__ __forceinline__ float roi_wx(const int64_t* rois, int b, int j, int s, int L4) {
+  float r0 = (float)rois[((long)b * NEF_NROI + j) * 2 + 0] * 0.25f;
+  float r1 = (float)rois[((long)b * NEF_NROI + j) * 2 + 1] * 0.25f;
+  const float sc = 2.0f / (float)L4;
+  r0 = r0 * sc - 1.0f;
+  r1 = r1 * sc - 1.0f;
+  const float step = (r1 - r0) / (float)(NEF_ROI_SIZE - 1);
+  const float gx = s < NEF_ROI_SIZE / 2 ? r0 + step * (float)s : r1 - step * (float)(NEF_ROI_SIZE - 1 - s);
+  return fmaxf(1.0f - fabsf(gx) * 0.5f, 0.f);
+}
+
+__global__ void roi_align_fwd_kernel(T4 z2c, const int64_t* __restrict__ rois, T4 ra, Window win, int L4) {
+  // ra channel ch = c * 7 + j  (model_nefnet.py:137 view)
+  const long total = (long)(ra.C / 4) * ra.B * NEF_ROI_SIZE;
+  const int c0 = win.y0 - win.w0;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int s = i % NEF_ROI_SIZE;
+    long r = i / NEF_ROI_SIZE;
+    const int b = r % ra.B;
+    const int ch4 = r / ra.B;
+    float4 v;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int ch = ch4 * 4 + k;
+      const int c = ch / NEF_NROI, j = ch % NEF_NROI;
+      const float4* zp = z2c.at(c >> 2, b, c0);
+      float centre = f4get(zp[0], c & 3) * (1.0f - win.wy1);
+      if (win.wy1 > 0.f && c0 + 1 < win.Lw) centre += f4get(zp[1], c & 3) * win.wy1;
+      f4at(v, k) = centre * roi_wx(rois, b, j, s, L4);
+    }
+    *ra.at(ch4, b, s) = tf32_rn4(v);
+  }
+}
+
+__global__ void roi_align_bwd_kernel(T4 dra, const int64_t* __restrict__ rois, T4 z2c, T4 gz2c, Window win, int L4) {
+  const long total = (long)(z2c.C / 4) * z2c.B;
+  const int c0 = win.y0 - win.w0;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int b = i % z2c.B;
+    const int c4 = i / z2c.B;
+    float4 dc = f4zero();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int c = c4 * 4 + k;
+      float acc = 0.f;
+      for (int j = 0; j < NEF_NROI; ++j) {
+        const int ch = c * NEF_NROI + j;
+        const float4* dp = dra.at(ch >> 2, b, 0);
+        for (int s = 0; s < NEF_ROI_SIZE; ++s) acc += f4get(dp[s], ch & 3) * roi_wx(rois, b, j, s, L4);
+      }
+      f4at(dc, k) = acc;
+    }
+    for (int l = 0; l < win.Lw; ++l) {
+      float wgt = 0.f;
+      if (l == c0) wgt = 1.0f - win.wy1;
+      else if (l == c0 + 1 && win.wy1 > 0.f) wgt = win.wy1;
+      const float4 z = *z2c.at(c4, b, l);
+      float4 g = make_float4(z.x > 0.f ? dc.x * wgt : 0.f, z.y > 0.f ? dc.y * wgt : 0.f, z.z > 0.f ? dc.z * wgt : 0.f,
+                             z.w > 0.f ? dc.w * wgt : 0.f);
+      *gz2c.at(c4, b, l) = tf32_rn4(g);
+    }
+  }
+}
+
+int roi_align_fwd(T4 z2c, const int64_t* rois, T4 ra, Window win, int L4, cudaStream_t s) {
+  const long total = (long)(ra.C / 4) * ra.B * NEF_ROI_SIZE;
+  roi_align_fwd_kernel<<<grid_for(total, 256), 256, 0, s>>>(z2c, rois, ra, win, L4);
+  NEF_CHECK_LAUNCH("roi_align_fwd_kernel");
+  return 0;
+}
+int roi_align_bwd(T4 dra, const int64_t* rois, T4 z2c, T4 gz2c, Window win, int L4, cudaStream_t s) {
+  const long total = (long)(z2c.C / 4) * z2c.B;
+  roi_align_bwd_kernel<<<grid_for(total, 128), 128, 0, s>>>(dra, rois, z2c, gz2c, win, L4);
+  NEF_CHECK_LAUNCH("roi_align_bwd_kernel");
+  return 0;
+}
+
+__global__ void deinterleave2_kernel(T4 src, T4 even, T4 odd) {
+  const long total = (long)(src.C / 4) * src.B * even.L;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int l = i % even.L;
+    long r = i / even.L;
+    const int b = r % src.B;
+    const int c4 = r / src.B;
+    const float4* sp = src.at(c4, b, 2 * l);
+    *even.at(c4, b, l) = sp[0];
+    *odd.at(c4, b, l) = sp[1];
+  }
+}
+int deinterleave2(T4 src, T4 even, T4 odd, cudaStream_t s) {
+  const long total = (long)(src.C / 4) * src.B * even.L;
+  deinterleave2_kernel<<<grid_for(total, 256), 256, 0, s>>>(src, even, odd);
+  NEF_CHECK_LAUNCH("deinterleave2_kernel");
+  return 0;
+}
+
+// ===========================================================================================
+// Latent mixing: roi_pooling_reverse (roi_pooling_1d.py:72-99), lead mean and lead shuffle
+// (model_nefnet.py:143-160), query scaling (:163-166) and the decoder's first Upsample (:102).
+// One block per (segment b, 4-channel chunk cc of the 128 latent channels, half: z1 | z2).
+// ===========================================================================================
+struct RoiTab {            // per-segment resampling table
+  int start[NEF_NROI + 1]; // prefix sums of the truncated roi lengths (concatenation order)
+};
+
+__device__ __forceinline__ void roi_table(const int64_t* rois, int b, RoiTab& t) {
+  int acc = 0;
+  for (int j = 0; j < NEF_NROI; ++j) {
+    t.start[j] = acc;
+    const long a0 = (long)((float)rois[((long)b * NEF_NROI + j) * 2 + 0] * 0.25f);  // .long() truncation (:83-85)
+    const long a1 = (long)((float)rois[((long)b * NEF_NROI + j) * 2 + 1] * 0.25f);
+    const int n = (int)(a1 - a0);
+    acc += n > 0 ? n : 0;
+  }
+  t.start[NEF_NROI] = acc;
+}
+
+// F.interpolate(mode='linear', align_corners=False) source coordinates for output i of n from 32 samples
+__device__ __forceinline__ void interp_src(int i, int n, int& i0, int& i1, float& lam) {
+  const float scale = 32.0f / (float)n;
+  float src = scale * ((float)i + 0.5f) - 0.5f;
+  if (src < 0.f) src = 0.f;
+  i0 = (int)src;
+  if (i0 > 31) i0 = 31;
+  i1 = i0 < 31 ? i0 + 1 : 31;
+  lam = src - (float)i0;
+}
+
+constexpr int LAT_TL = 256;  // latent positions per inner tile
+
+__global__ void __launch_bounds__(256) latent_fwd_kernel(const LatentArgs a) {
+  extern __shared__ float4 sm[];
+  const int L4 = a.z1.L;
+  const int b = blockIdx.x, cc = blockIdx.y, half = blockIdx.z;
+  const int tid = threadIdx.x;
+  float4* z2s = sm;                                   // [G][7 chunks][32]   (z2 half only)
+  float4* mt = sm + (half ? a.G * 7 * 32 : 0);        // [LAT_TL + 2] mean
+  float4* pt = mt + (LAT_TL + 2);                     // [LAT_TL + 2] pick
+  __shared__ RoiTab tab;
+  if (half == 1) {
+    if (tid == 0) roi_table(a.rois, b, tab);
+    if (a.write_lat) {
+      for (int i = tid; i < a.G * 7 * 32; i += 256) {
+        const int pos = i & 31, r = i >> 5;
+        const int g = r / 7, m = r % 7;
+        z2s[i] = *a.z2o.at(g * 224 + cc * 7 + m, b, pos);
+      }
+    }
+  }
+  __syncthreads();
+  const int latc = half * 32 + cc;  // chunk in the 256-channel latent
+  const float4 qv = *reinterpret_cast<const float4*>(a.q + (long)b * a.q_stride + latc * 4);
+  const float invG = 1.0f / (float)a.G;
+
+  for (int t0 = 0; t0 < L4; t0 += LAT_TL) {
+    // ---- stage 1: lat values for positions t0-1 .. t0+LAT_TL (clamped) into smem
+    for (int i = tid; i < LAT_TL + 2; i += 256) {
+      int l = t0 - 1 + i;
+      l = l < 0 ? 0 : (l > L4 - 1 ? L4 - 1 : l);
+      float4 m, p;
+      if (!a.write_lat) {
+        m = *a.lat[0].at(latc, b, l);
+        p = m;
+      } else if (half == 0) {
+        m = f4zero();
+        p = f4zero();
+        for (int g = 0; g < a.G; ++g) {
+          const float4 v = *a.z1.at(g * 32 + cc, b, l);
+          m = m + v;
+          if (g == a.c1) p = v;
+        }
+        m = m * invG;
+      } else {
+        int j = 0;
+        while (j < NEF_NROI - 1 && l >= tab.start[j + 1]) ++j;
+        const int n = tab.start[j + 1] - tab.start[j];
+        int i0, i1;
+        float lam;
+        interp_src(l - tab.start[j], n > 0 ? n : 1, i0, i1, lam);
+        m = f4zero();
+        p = f4zero();
+        for (int g = 0; g < a.G; ++g) {
+          float4 v;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int chl = k * 7 + j;  // local channel among the 28 of this (g, cc)
+            const float4* zp = z2s + (g * 7 + (chl >> 2)) * 32;
+            const float x0 = f4get(zp[i0], chl & 3), x1 = f4get(zp[i1], chl & 3);
+            f4at(v, k) = (1.0f - lam) * x0 + lam * x1;
+          }
+          m = m + v;
+          if (g == a.c2) p = v;
+        }
+        m = m * invG;
+      }
+      mt[i] = m;
+      pt[i] = p;
+    }
+    __syncthreads();
+    // ---- stage 2: write the latents and their query-scaled x2 upsamples
+    const int nl = min(LAT_TL, L4 - t0);
+    for (int k3 = 0; k3 < a.n_lat; ++k3) {
+      // lat_all = [z1m, z2m], lat_p = [z1[c1], z2m], lat_l = [z1m, z2[c2]]
+      const bool use_pick = (k3 == 1 && half == 0) || (k3 == 2 && half == 1);
+      const float4* src = use_pick ? pt : mt;
+      if (a.write_lat) {
+        for (int i = tid; i < nl; i += 256) *a.lat[k3].at(latc, b, t0 + i) = src[i + 1];
+      }
+      for (int i = tid; i < 2 * nl; i += 256) {
+        const int li = i >> 1;  // latent position t0 + li ; smem index li + 1
+        float4 v;
+        if ((i & 1) == 0) v = src[li] * 0.25f + src[li + 1] * 0.75f;
+        else v = src[li + 1] * 0.75f + src[li + 2] * 0.25f;
+        *a.u0[k3].at(latc, b, 2 * t0 + i) = tf32_rn4(v * qv);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+int latent_fwd(const LatentArgs& a, cudaStream_t s) {
+  const size_t smem = ((size_t)a.G * 7 * 32 + 2 * (LAT_TL + 2)) * sizeof(float4);
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    cudaFuncSetAttribute(latent_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    configured = smem;
+  }
+  dim3 grid(a.z1.B, 32, 2);
+  latent_fwd_kernel<<<grid, 256, smem, s>>>(a);
+  NEF_CHECK_LAUNCH("latent_fwd_kernel");
+  return 0;
+}
+
+// Backward of the above.  d lat_k = q * up^T(d u0_k);  d q += sum lat_k * up^T(d u0_k)
+__global__ void __launch_bounds__(256) latent_bwd_kernel(const LatentBwdArgs a) {
+  extern __shared__ float4 sm[];
+  const int L4 = a.z1.L;
+  const int b = blockIdx.x, cc = blockIdx.y, half = blockIdx.z;
+  const int tid = threadIdx.x, lane = tid & 31;
+  float* Tm = reinterpret_cast<float*>(sm);  // [4][7][32] adjoint-resampled d(mean) / d(pick)   (z2 half)
+  float* Tp = Tm + 4 * 7 * 32;
+  __shared__ RoiTab tab;
+  __shared__ float dq_s[4];
+  if (tid < 4) dq_s[tid] = 0.f;
+  if (half == 1) {
+    if (tid == 0) roi_table(a.rois, b, tab);
+    for (int i = tid; i < 2 * 4 * 7 * 32; i += 256) Tm[i] = 0.f;
+  }
+  __syncthreads();
+  const int latc = half * 32 + cc;
+  const float4 qv = *reinterpret_cast<const float4*>(a.q + (long)b * a.q_stride + latc * 4);
+  const float invG = 1.0f / (float)a.G;
+  float4 dq = f4zero();
+  const int L2 = 2 * L4;
+  for (int l = tid; l < L4; l += 256) {
+    float4 dm = f4zero(), dp = f4zero();
+#pragma unroll
+    for (int k3 = 0; k3 < 3; ++k3) {
+      const float4* du = a.du0[k3].at(latc, b, 0);
+      float4 d = du[2 * l] * 0.75f + du[2 * l + 1] * 0.75f;
+      if (l + 1 < L4) d = d + du[2 * l + 2] * 0.25f;
+      if (l >= 1) d = d + du[2 * l - 1] * 0.25f;
+      if (l == 0) d = d + du[0] * 0.25f;
+      if (l == L4 - 1) d = d + du[L2 - 1] * 0.25f;
+      dq = dq + d * (*a.lat[k3].at(latc, b, l));
+      d = d * qv;
+      const bool use_pick = (k3 == 1 && half == 0) || (k3 == 2 && half == 1);
+      if (use_pick) dp = dp + d;
+      else dm = dm + d;
+    }
+    if (half == 0) {
+      for (int g = 0; g < a.G; ++g) {
+        const float4 z = *a.z1.at(g * 32 + cc, b, l);
+        float4 gsum = dm * invG;
+        if (g == a.c1) gsum = gsum + dp;
+        gsum = make_float4(z.x > 0.f ? gsum.x : 0.f, z.y > 0.f ? gsum.y : 0.f, z.z > 0.f ? gsum.z : 0.f,
+                           z.w > 0.f ? gsum.w : 0.f);
+        *a.gz1.at(g * 32 + cc, b, l) = tf32_rn4(gsum);
+      }
+    } else {
+      int j = 0;
+      while (j < NEF_NROI - 1 && l >= tab.start[j + 1]) ++j;
+      const int n = tab.start[j + 1] - tab.start[j];
+      int i0, i1;
+      float lam;
+      interp_src(l - tab.start[j], n > 0 ? n : 1, i0, i1, lam);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float vm = f4get(dm, k), vp = f4get(dp, k);
+        atomicAdd(&Tm[(k * 7 + j) * 32 + i0], (1.0f - lam) * vm);
+        atomicAdd(&Tm[(k * 7 + j) * 32 + i1], lam * vm);
+        atomicAdd(&Tp[(k * 7 + j) * 32 + i0], (1.0f - lam) * vp);
+        atomicAdd(&Tp[(k * 7 + j) * 32 + i1], lam * vp);
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float v = warp_sum(f4get(dq, k));
+    if (lane == 0) atomicAdd(&dq_s[k], v);
+  }
+  __syncthreads();
+  if (tid < 4) a.dq[(long)b * 256 + latc * 4 + tid] = dq_s[tid];
+  if (half == 1) {
+    // g z2o[(g*128 + 4cc + k)*7 + j][pos] = (Tm/G + [g == c2] Tp) * (z2o > 0)
+    for (int i = tid; i < a.G * 7 * 32; i += 256) {
+      const int pos = i & 31, r = i >> 5;
+      const int g = r / 7, m = r % 7;
+      const float4 z = *a.z2o.at(g * 224 + cc * 7 + m, b, pos);
+      float4 o;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int chl = m * 4 + e;  // = k * 7 + j
+        float v = Tm[chl * 32 + pos] * invG;
+        if (g == a.c2) v += Tp[chl * 32 + pos];
+        f4at(o, e) = f4get(z, e) > 0.f ? v : 0.f;
+      }
+      *a.gz2o.at(g * 224 + cc * 7 + m, b, pos) = tf32_rn4(o);
+    }
+  }
+}
+
+int latent_bwd(const LatentBwdArgs& a, cudaStream_t s) {
+  const size_t smem = (size_t)2 * 4 * 7 * 32 * sizeof(float);
+  dim3 grid(a.z1.B, 32, 2);
+  latent_bwd_kernel<<<grid, 256, smem, s>>>(a);
+  NEF_CHECK_LAUNCH("latent_bwd_kernel");
+  return 0;
+}
+
+// ===========================================================================================
+// Decoder BatchNorm1d (train: batch statistics, eps 1e-5, momentum 0.1), model_nefnet.py:17-24
+// ===========================================================================================
+__global__ void bn_finalize_kernel(BnLayer bn, int C, double count, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float* rmean, float* rvar, int64_t* nbt,
+                                   int training) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) {
+    float mean, invstd;
+    if (training) {
+      const double m = bn.sum[c] / count;
+      double var = bn.sq[c] / count - m * m;
+      if (var < 0.0) var = 0.0;
+      mean = (float)m;
+      invstd = (float)(1.0 / sqrt(var + 1e-5));
+      const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+      rmean[c] = 0.9f * rmean[c] + 0.1f * mean;
+      rvar[c] = 0.9f * rvar[c] + 0.1f * (float)unbiased;
+    } else {
+      mean = rmean[c];
+      invstd = 1.0f / sqrtf(rvar[c] + 1e-5f);
+    }
+    bn.mean[c] = mean;
+    bn.invstd[c] = invstd;
+    const float sc = gamma[c] * invstd;
+    bn.scale[c] = sc;
+    bn.shift[c] = beta[c] - mean * sc;
+  }
+  if (training && c == 0) nbt[0] += 1;
+}
+int bn_finalize(const BnLayer& bn, int C, double count, const float* gamma, const float* beta, float* rmean,
+                float* rvar, int64_t* nbt, int training, cudaStream_t s) {
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(bn, C, count, gamma, beta, rmean, rvar, nbt, training);
+  NEF_CHECK_LAUNCH("bn_finalize_kernel");
+  return 0;
+}
+
+__device__ __forceinline__ float4 bn_relu4(float4 c, float4 sc, float4 sh) {
+  return make_float4(fmaxf(c.x * sc.x + sh.x, 0.f), fmaxf(c.y * sc.y + sh.y, 0.f), fmaxf(c.z * sc.z + sh.z, 0.f),
+                     fmaxf(c.w * sc.w + sh.w, 0.f));
+}
+
+// out = relu(bn(c)) ; with upsample: out = Upsample(x2, linear, align_corners=False)(relu(bn(c)))
+__global__ void bn_relu_kernel(T4 c, const float* __restrict__ scale, const float* __restrict__ shift, T4 out,
+                               int upsample) {
+  const long total = (long)(c.C / 4) * c.B * out.L;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int l = i % out.L;
+    long r = i / out.L;
+    const int b = r % c.B;
+    const int c4 = r / c.B;
+    const float4 sc = reinterpret_cast<const float4*>(scale)[c4], sh = reinterpret_cast<const float4*>(shift)[c4];
+    float4 v;
+    if (!upsample) {
+      v = bn_relu4(*c.at(c4, b, l), sc, sh);
+    } else {
+      const int li = l >> 1;
+      const float4 a1 = bn_relu4(*c.at(c4, b, li), sc, sh);
+      if ((l & 1) == 0) {
+        const float4 a0 = li > 0 ? bn_relu4(*c.at(c4, b, li - 1), sc, sh) : a1;
+        v = a0 * 0.25f + a1 * 0.75f;
+      } else {
+        const float4 a2 = li + 1 < c.L ? bn_relu4(*c.at(c4, b, li + 1), sc, sh) : a1;
+        v = a1 * 0.75f + a2 * 0.25f;
+      }
+    }
+    *out.at(c4, b, l) = tf32_rn4(v);
+  }
+}
+int bn_relu(T4 c, const float* scale, const float* shift, T4 out, int upsample, cudaStream_t s) {
+  const long total = (long)(c.C / 4) * c.B * out.L;
+  bn_relu_kernel<<<grid_for(total, 256), 256, 0, s>>>(c, scale, shift, out, upsample);
+  NEF_CHECK_LAUNCH("bn_relu_kernel");
+  return 0;
+}
+
+// adjoint of Upsample(x2, linear, align_corners=False): (C, 2n) -> (C, n)
+__global__ void up_adjoint_kernel(T4 du, T4 da) {
+  const long total = (long)(da.C / 4) * da.B * da.L;
+  const int n = da.L;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int l = i % n;
+    long r = i / n;
+    const int b = r % da.B;
+    const int c4 = r / da.B;
+    const float4* p = du.at(c4, b, 0);
+    float4 d = p[2 * l] * 0.75f + p[2 * l + 1] * 0.75f;
+    if (l + 1 < n) d = d + p[2 * l + 2] * 0.25f;
+    if (l >= 1) d = d + p[2 * l - 1] * 0.25f;
+    if (l == 0) d = d + p[0] * 0.25f;
+    if (l == n - 1) d = d + p[2 * n - 1] * 0.25f;
+    *da.at(c4, b, l) = d;
+  }
+}
+int up_adjoint(T4 du, T4 da, cudaStream_t s) {
+  const long total = (long)(da.C / 4) * da.B * da.L;
+  up_adjoint_kernel<<<grid_for(total, 256), 256, 0, s>>>(du, da);
+  NEF_CHECK_LAUNCH("up_adjoint_kernel");
+  return 0;
+}
+
+// BatchNorm backward, pass 1: g = da * (bn(c) > 0);  s1 += sum g ; s2 += sum g * xhat      (per channel)
+// grid (row tiles, C/4); block 256
+__global__ void __launch_bounds__(256) bnbwd_stats_kernel(T4 da, T4 c, BnLayer bn) {
+  __shared__ float red[8][8];
+  const int c4 = blockIdx.y;
+  const float4 sc = reinterpret_cast<const float4*>(bn.scale)[c4], sh = reinterpret_cast<const float4*>(bn.shift)[c4];
+  const float4 mu = reinterpret_cast<const float4*>(bn.mean)[c4], is = reinterpret_cast<const float4*>(bn.invstd)[c4];
+  float4 s1 = f4zero(), s2 = f4zero();
+  const long total = (long)c.B * c.L;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int l = i % c.L;
+    const int b = i / c.L;
+    const float4 cv = *c.at(c4, b, l), dv = *da.at(c4, b, l);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float x = f4get(cv, k);
+      const float g = (x * f4get(sc, k) + f4get(sh, k)) > 0.f ? f4get(dv, k) : 0.f;
+      f4at(s1, k) += g;
+      f4at(s2, k) += g * (x - f4get(mu, k)) * f4get(is, k);
+    }
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float a = warp_sum(f4get(s1, k)), b2 = warp_sum(f4get(s2, k));
+    if (lane == 0) {
+      red[warp][k] = a;
+      red[warp][4 + k] = b2;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    float v = 0.f;
+    for (int w = 0; w < 8; ++w) v += red[w][threadIdx.x];
+    if (threadIdx.x < 4) atomicAdd(bn.s1 + c4 * 4 + threadIdx.x, (double)v);
+    else atomicAdd(bn.s2 + c4 * 4 + threadIdx.x - 4, (double)v);
+  }
+}
+int bnbwd_stats(T4 da, T4 c, const BnLayer& bn, cudaStream_t s) {
+  const long total = (long)c.B * c.L;
+  int gx = (int)((total + 256 * 8 - 1) / (256 * 8));
+  if (gx < 1) gx = 1;
+  if (gx > 148 * 4) gx = 148 * 4;
+  dim3 grid(gx, c.C / 4);
+  bnbwd_stats_kernel<<<grid, 256, 0, s>>>(da, c, bn);
+  NEF_CHECK_LAUNCH("bnbwd_stats_kernel");
+  return 0;
+}
+
+// pass 2: dc = gamma * invstd * (g - s1/N - xhat * s2/N) ; dgamma += s2 ; dbeta += s1
+__global__ void bnbwd_apply_kernel(T4 da, T4 c, BnLayer bn, const float* __restrict__ gamma, double count, T4 dc,
+                                   float* dgamma, float* dbeta) {
+  const long total = (long)(c.C / 4) * c.B * c.L;
+  const float invn = (float)(1.0 / count);
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int l = i % c.L;
+    long r = i / c.L;
+    const int b = r % c.B;
+    const int c4 = r / c.B;
+    const float4 cv = *c.at(c4, b, l), dv = *da.at(c4, b, l);
+    float4 o;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int ch = c4 * 4 + k;
+      const float x = f4get(cv, k);
+      const float g = (x * bn.scale[ch] + bn.shift[ch]) > 0.f ? f4get(dv, k) : 0.f;
+      const float xhat = (x - bn.mean[ch]) * bn.invstd[ch];
+      f4at(o, k) = gamma[ch] * bn.invstd[ch] * (g - (float)bn.s1[ch] * invn - xhat * (float)bn.s2[ch] * invn);
+    }
+    *dc.at(c4, b, l) = tf32_rn4(o);
+  }
+  if (blockIdx.x == 0) {
+    for (int ch = threadIdx.x; ch < c.C; ch += blockDim.x) {
+      if (dgamma) dgamma[ch] += (float)bn.s2[ch];
+      if (dbeta) dbeta[ch] += (float)bn.s1[ch];
+    }
+  }
+}
+int bnbwd_apply(T4 da, T4 c, const BnLayer& bn, const float* gamma, double count, T4 dc, float* dgamma, float* dbeta,
+                cudaStream_t s) {
+  const long total = (long)(c.C / 4) * c.B * c.L;
+  bnbwd_apply_kernel<<<grid_for(total, 256), 256, 0, s>>>(da, c, bn, gamma, count, dc, dgamma, dbeta);
+  NEF_CHECK_LAUNCH("bnbwd_apply_kernel");
+  return 0;
+}
+
+// ===========================================================================================
+// Output layer: relu(bn4(c4)) -> Conv1d(64 -> 1, k3, p1) -> sigmoid(x / 3)    model_nefnet.py:106,168
+// ===========================================================================================
+__global__ void __launch_bounds__(128) dec_out_fwd_kernel(T4 c4t, const float* __restrict__ scale,
+                                                          const float* __restrict__ shift, const float* __restrict__ w,
+                                                          const float* __restrict__ bias, float* __restrict__ out,
+                                                          int out_bstride) {
+  __shared__ float4 ws[3][16], scs[16], shs[16];
+  const int tid = threadIdx.x;
+  if (tid < 48) {
+    const int t = tid / 16, c = tid % 16;
+    ws[t][c] = make_float4(w[(c * 4 + 0) * 3 + t], w[(c * 4 + 1) * 3 + t], w[(c * 4 + 2) * 3 + t], w[(c * 4 + 3) * 3 + t]);
+  } else if (tid < 64) {
+    scs[tid - 48] = reinterpret_cast<const float4*>(scale)[tid - 48];
+    shs[tid - 48] = reinterpret_cast<const float4*>(shift)[tid - 48];
+  }
+  __syncthreads();
+  const int L = c4t.L;
+  const long total = (long)c4t.B * L;
+  for (long i = blockIdx.x * (long)blockDim.x + tid; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int l = i % L;
+    const int b = i / L;
+    float acc = bias[0];
+#pragma unroll 4
+    for (int c = 0; c < 16; ++c) {
+      const float4* p = c4t.at(c, b, l);
+      const float4 a1 = bn_relu4(p[0], scs[c], shs[c]);
+      float4 s = a1 * ws[1][c];
+      if (l > 0) s = s + bn_relu4(p[-1], scs[c], shs[c]) * ws[0][c];
+      if (l + 1 < L) s = s + bn_relu4(p[1], scs[c], shs[c]) * ws[2][c];
+      acc += (s.x + s.y) + (s.z + s.w);
+    }
+    out[(long)b * out_bstride + l] = 1.0f / (1.0f + expf(-acc * (1.0f / 3.0f)));
+  }
+}
+int dec_out_fwd(T4 c4, const float* scale, const float* shift, const float* w, const float* b, float* out,
+                int out_bstride, cudaStream_t s) {
+  const long total = (long)c4.B * c4.L;
+  dec_out_fwd_kernel<<<grid_for(total, 128), 128, 0, s>>>(c4, scale, shift, w, b, out, out_bstride);
+  NEF_CHECK_LAUNCH("dec_out_fwd_kernel");
+  return 0;
+}
+
+// backward of the output layer fused with pass 1 of bn4's backward:
+//   dy = dout * out (1 - out) / 3 ; dw[ci][t] += sum dy[l] a4[l+t-1][ci] ; db += sum dy
+//   g4[l][ci] = (sum_t dy[l-t+1] w[ci][t]) * (a4 > 0) ; s1 += g4 ; s2 += g4 * xhat
+__global__ void __launch_bounds__(128) dec_out_bwd_kernel(T4 c4t, BnLayer bn, const float* __restrict__ w,
+                                                          const float* __restrict__ out, const float* __restrict__ dout,
+                                                          T4 g4, float* __restrict__ dw, float* __restrict__ db) {
+  __shared__ float4 ws[3][16], scs[16], shs[16], mus[16], iss[16];
+  __shared__ float acc_s[16][20];  // per chunk: s1[4], s2[4], dw[3][4]
+  __shared__ float db_s;
+  const int tid = threadIdx.x, lane = tid & 31;
+  if (tid < 48) {
+    const int t = tid / 16, c = tid % 16;
+    ws[t][c] = make_float4(w[(c * 4 + 0) * 3 + t], w[(c * 4 + 1) * 3 + t], w[(c * 4 + 2) * 3 + t], w[(c * 4 + 3) * 3 + t]);
+  } else if (tid < 64) {
+    const int c = tid - 48;
+    scs[c] = reinterpret_cast<const float4*>(bn.scale)[c];
+    shs[c] = reinterpret_cast<const float4*>(bn.shift)[c];
+    mus[c] = reinterpret_cast<const float4*>(bn.mean)[c];
+    iss[c] = reinterpret_cast<const float4*>(bn.invstd)[c];
+  }
+  for (int i = tid; i < 16 * 20; i += 128) (&acc_s[0][0])[i] = 0.f;
+  if (tid == 0) db_s = 0.f;
+  __syncthreads();
+  const int L = c4t.L;
+  const long total = (long)c4t.B * L;
+  const long span = (long)gridDim.x * blockDim.x;
+  const long iters = (total + span - 1) / span;
+  float dbl = 0.f;
+  for (long it = 0; it < iters; ++it) {
+    const long i = it * span + blockIdx.x * (long)blockDim.x + tid;
+    const bool ok = i < total;
+    const int l = ok ? (int)(i % L) : 0;
+    const int b = ok ? (int)(i / L) : 0;
+    float dym = 0.f, dy0 = 0.f, dyp = 0.f;  // dy at l-1, l, l+1
+    if (ok) {
+      const float* op = out + (long)b * L + l;
+      const float* dp = dout + (long)b * L + l;
+      dy0 = dp[0] * op[0] * (1.0f - op[0]) * (1.0f / 3.0f);
+      if (l > 0) dym = dp[-1] * op[-1] * (1.0f - op[-1]) * (1.0f / 3.0f);
+      if (l + 1 < L) dyp = dp[1] * op[1] * (1.0f - op[1]) * (1.0f / 3.0f);
+    }
+    dbl += dy0;
+    for (int c = 0; c < 16; ++c) {
+      float4 gv = f4zero(), xh = f4zero(), a0 = f4zero(), am = f4zero(), ap = f4zero();
+      if (ok) {
+        const float4* p = c4t.at(c, b, l);
+        const float4 cv = p[0];
+        a0 = bn_relu4(cv, scs[c], shs[c]);
+        if (l > 0) am = bn_relu4(p[-1], scs[c], shs[c]);
+        if (l + 1 < L) ap = bn_relu4(p[1], scs[c], shs[c]);
+        // da4[l] = dy[l+1] w[.,0] + dy[l] w[.,1] + dy[l-1] w[.,2]
+        float4 d = ws[0][c] * dyp + ws[1][c] * dy0 + ws[2][c] * dym;
+        gv = make_float4(a0.x > 0.f ? d.x : 0.f, a0.y > 0.f ? d.y : 0.f, a0.z > 0.f ? d.z : 0.f, a0.w > 0.f ? d.w : 0.f);
+        xh = make_float4((cv.x - mus[c].x) * iss[c].x, (cv.y - mus[c].y) * iss[c].y, (cv.z - mus[c].z) * iss[c].z,
+                         (cv.w - mus[c].w) * iss[c].w);
+        *g4.at(c, b, l) = gv;
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float g = f4get(gv, k);
+        const float r1 = warp_sum(g), r2 = warp_sum(g * f4get(xh, k));
+        const float w0 = warp_sum(dy0 * f4get(am, k)), w1 = warp_sum(dy0 * f4get(a0, k)), w2 = warp_sum(dy0 * f4get(ap, k));
+        if (lane == 0) {
+          atomicAdd(&acc_s[c][k], r1);
+          atomicAdd(&acc_s[c][4 + k], r2);
+          atomicAdd(&acc_s[c][8 + k], w0);
+          atomicAdd(&acc_s[c][12 + k], w1);
+          atomicAdd(&acc_s[c][16 + k], w2);
+        }
+      }
+    }
+  }
+  dbl = warp_sum(dbl);
+  if (lane == 0) atomicAdd(&db_s, dbl);
+  __syncthreads();
+  for (int i = tid; i < 16 * 20; i += 128) {
+    const int c = i / 20, e = i % 20;
+    const float v = acc_s[c][e];
+    if (e < 4) atomicAdd(bn.s1 + c * 4 + e, (double)v);
+    else if (e < 8) atomicAdd(bn.s2 + c * 4 + e - 4, (double)v);
+    else {
+      const int t = (e - 8) / 4, k = (e - 8) % 4;
+      atomicAdd(dw + (c * 4 + k) * 3 + t, v);
+    }
+  }
+  if (tid == 0) atomicAdd(db, db_s);
+}
+int dec_out_bwd(T4 c4, const BnLayer& bn, const float* w, const float* out, const float* dout, T4 g4, float* dw,
+                float* db, cudaStream_t s) {
+  const long total = (long)c4.B * c4.L;
+  int g = (int)((total + 128 * 8 - 1) / (128 * 8));
+  if (g < 1) g = 1;
+  if (g > 148 * 8) g = 148 * 8;
+  dec_out_bwd_kernel<<<g, 128, 0, s>>>(c4, bn, w, out, dout, g4, dw, db);
+  NEF_CHECK_LAUNCH("dec_out_bwd_kernel");
+  return 0;
+}
+
+// ===========================================================================================
+// Standin-Learning loss, network/loss/losses.py:21-50 ; SGD, solver/optim_scheduler.py:10
+// ===========================================================================================
+__global__ void __launch_bounds__(256) loss_fwd_kernel(const float* __restrict__ o, const float* __restrict__ op,
+                                                       const float* __restrict__ ol, const float* __restrict__ tg, long n,
+                                                       int use_mse, double* sums) {
+  __shared__ float red[3][8];
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const float v = o[i];
+    if (op) s0 += fabsf(v - op[i]);
+    if (ol) s1 += fabsf(v - ol[i]);
+    if (tg) {
+      const float d = v - tg[i];
+      s2 += use_mse ? d * d : fabsf(d);
+    }
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2);
+  if (lane == 0) { red[0][warp] = s0; red[1][warp] = s1; red[2][warp] = s2; }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    float v = 0.f;
+    for (int w = 0; w < 8; ++w) v += red[threadIdx.x][w];
+    atomicAdd(sums + threadIdx.x, (double)v);
+  }
+}
+__global__ void loss_finish_kernel(const double* sums, long n, float f0, float f1, float f2, float* losses) {
+  const float l1 = (float)(sums[0] / (double)n) * f0, l2 = (float)(sums[1] / (double)n) * f1,
+              l3 = (float)(sums[2] / (double)n) * f2;
+  losses[0] = l1 + l2 + l3;
+  losses[1] = l1;
+  losses[2] = l2;
+  losses[3] = l3;
+}
+__device__ __forceinline__ float sgnf(float x) { return x > 0.f ? 1.f : (x < 0.f ? -1.f : 0.f); }
+__global__ void loss_bwd_kernel(const float* __restrict__ o, const float* __restrict__ op, const float* __restrict__ ol,
+                                const float* __restrict__ tg, long n, int use_mse, float f0, float f1, float f2,
+                                const float* __restrict__ dloss, float* __restrict__ d_o, float* __restrict__ d_op,
+                                float* __restrict__ d_ol) {
+  // dloss = upstream gradient of the 4 returned values (total, l1*f0, l2*f1, l3*f2); total = sum of the parts
+  const float inv = 1.0f / (float)n;
+  const float u0 = (dloss ? dloss[0] + dloss[1] : 1.0f) * inv, u1 = (dloss ? dloss[0] + dloss[2] : 1.0f) * inv,
+              u2 = (dloss ? dloss[0] + dloss[3] : 1.0f) * inv;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const float v = o[i];
+    if (d_op) d_op[i] = f0 != 0.f ? f0 * u0 * sgnf(op[i] - v) : 0.f;
+    if (d_ol) d_ol[i] = f1 != 0.f ? f1 * u1 * sgnf(ol[i] - v) : 0.f;
+    if (d_o) {
+      const float d = v - tg[i];
+      d_o[i] = f2 != 0.f ? f2 * u2 * (use_mse ? 2.0f * d : sgnf(d)) : 0.f;
+    }
+  }
+}
+__global__ void pair_finish_kernel(const double* sum, long n, float* result) { result[0] = (float)(sum[2] / (double)n); }
+
+__global__ void sgd_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, long n, float lr,
+                           float momentum, float gscale) {
+  const long n4 = n >> 2;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
+    float4 gv = reinterpret_cast<const float4*>(g)[i] * gscale;
+    float4 mv = reinterpret_cast<float4*>(m)[i] * momentum + gv;
+    float4 pv = reinterpret_cast<float4*>(p)[i];
+    pv = pv + mv * (-lr);
+    reinterpret_cast<float4*>(m)[i] = mv;
+    reinterpret_cast<float4*>(p)[i] = pv;
+  }
+  for (long i = (n4 << 2) + blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const float mv = m[i] * momentum + g[i] * gscale;
+    m[i] = mv;
+    p[i] -= lr * mv;
+  }
+}
+
+}  // namespace nef
+
+using namespace nef;
+
+extern "C" int nef_loss_fwd(const float* out, const float* out_p, const float* out_l, const float* target, int64_t n,
+                            int use_mse, const float* f, int using_mask, double* sums, float* losses, nef_stream_t s) {
+  cudaStream_t st = (cudaStream_t)s;
+  cudaMemsetAsync(sums, 0, 3 * sizeof(double), st);
+  loss_fwd_kernel<<<grid_for(n, 256, 148 * 8), 256, 0, st>>>(out, (using_mask & 1) ? out_p : nullptr,
+                                                              (using_mask & 2) ? out_l : nullptr,
+                                                              (using_mask & 4) ? target : nullptr, n, use_mse, sums);
+  NEF_CHECK_LAUNCH("loss_fwd_kernel");
+  loss_finish_kernel<<<1, 1, 0, st>>>(sums, n, f[0], f[1], f[2], losses);
+  NEF_CHECK_LAUNCH("loss_finish_kernel");
+  return 0;
+}
+
+extern "C" int nef_loss_bwd(const float* out, const float* out_p, const float* out_l, const float* target, int64_t n,
+                            int use_mse, const float* f, int using_mask, const float* dloss, float* dout, float* dout_p,
+                            float* dout_l, nef_stream_t s) {
+  const float f0 = (using_mask & 1) ? f[0] : 0.f, f1 = (using_mask & 2) ? f[1] : 0.f, f2 = (using_mask & 4) ? f[2] : 0.f;
+  loss_bwd_kernel<<<grid_for(n, 256, 148 * 8), 256, 0, (cudaStream_t)s>>>(out, out_p, out_l, target, n, use_mse, f0, f1,
+                                                                          f2, dloss, dout, dout_p, dout_l);
+  NEF_CHECK_LAUNCH("loss_bwd_kernel");
+  return 0;
+}
+
+extern "C" int nef_pair_loss(const float* a, const float* b, int64_t n, int use_mse, double* sum, float* result,
+                             nef_stream_t s) {
+  cudaStream_t st = (cudaStream_t)s;
+  cudaMemsetAsync(sum, 0, 3 * sizeof(double), st);
+  loss_fwd_kernel<<<grid_for(n, 256, 148 * 8), 256, 0, st>>>(a, nullptr, nullptr, b, n, use_mse, sum);
+  NEF_CHECK_LAUNCH("loss_fwd_kernel");
+  pair_finish_kernel<<<1, 1, 0, st>>>(sum, n, result);
+  NEF_CHECK_LAUNCH("pair_finish_kernel");
+  return 0;
+}
+
+extern "C" int nef_sgd_step(float* p, const float* g, float* m, int64_t n, float lr, float momentum, float gscale,
+                            nef_stream_t s) {
+  sgd_kernel<<<grid_for(n / 4 + 1, 256, 148 * 8), 256, 0, (cudaStream_t)s>>>(p, g, m, n, lr, momentum, gscale);
+  NEF_CHECK_LAUNCH("sgd_kernel");
+  return 0;
+}

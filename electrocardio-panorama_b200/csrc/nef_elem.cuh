@@ -1,0 +1,74 @@
+// Host-callable launchers of the non-GEMM kernels (nef_elem.cu), used by the plan (nef_plan.cu).
+#pragma once
+#include "nef_common.cuh"
+#include "../../include/nefnet_b200.h"
+
+namespace nef {
+
+// A CBL4 tensor view: p = row 0 of chunk 0, cs = rows per chunk (= B * Lp), Lp = L + 2 * HALO.
+struct T4 {
+  float4* p;
+  long cs;
+  int C, B, L, Lp;
+  __host__ __device__ long row(int b, int l) const { return (long)b * Lp + NEF_HALO + l; }
+  __host__ __device__ float4* at(int c4, int b, int l) const { return p + (long)c4 * cs + row(b, l); }
+};
+
+struct BnLayer {          // one BatchNorm1d of the decoder for one decoder call
+  double* sum;            // [C] batch sum of the conv output   (zeroed before the conv)
+  double* sq;             // [C]
+  float* scale;           // [C] gamma * invstd
+  float* shift;           // [C] beta - mean * scale
+  float* mean;            // [C] saved for backward
+  float* invstd;          // [C]
+  double* s1;             // [C] backward: sum g
+  double* s2;             // [C] backward: sum g * xhat
+};
+
+int stem_fwd(const float* x, const float* w, T4 y, int G, cudaStream_t s);
+int stem_bwd(const float* x, const float* w, T4 dy, float* dw, int G, cudaStream_t s);
+int angular_fwd(const float* theta, const float* w, const float* b, float* out, int n, int D, cudaStream_t s);
+int angular_bwd(const float* theta, const float* dout, float* dw, float* db, int n, int D, cudaStream_t s);
+
+// z2_conv1 only matters at the centre columns (roi_algin samples nothing else)
+struct Window { int w0, Lw, y0; float wy1; };
+Window centre_window(int L4);
+int window_extract(T4 w, T4 xw, int G, Window win, cudaStream_t s);                  // w z2-half -> (64G, Lw)
+int window_scatter(T4 gxw, T4 gw, int G, Window win, cudaStream_t s);                // -> z2 half of g_w, zeros elsewhere
+int roi_align_fwd(T4 z2c, const int64_t* rois, T4 ra, Window win, int L4, cudaStream_t s);
+int roi_align_bwd(T4 dra, const int64_t* rois, T4 z2c, T4 gz2c, Window win, int L4, cudaStream_t s);
+int deinterleave2(T4 src, T4 even, T4 odd, cudaStream_t s);                          // (C, 2n) -> 2 x (C, n)
+
+struct LatentArgs {
+  T4 z1, z2o;             // (128G, L4), (896G, 32)
+  const int64_t* rois;
+  const float* q;         // (B, 256) query scale (mlp2 output), or (B, V, 256) with view index
+  int q_stride;           // floats between segments in q
+  int G, c1, c2;
+  T4 lat[3];              // unscaled latents (256, L4): all, patient-shuffled, lead-shuffled
+  T4 u0[3];               // upsample2(q * lat) (256, L/2)
+  int n_lat;              // 3 (train) or 1 (extra views: only lat[0] / u0[0])
+  int write_lat;          // 0: lat already built, only (re)build u0 from it with another q
+};
+int latent_fwd(const LatentArgs& a, cudaStream_t s);
+struct LatentBwdArgs {
+  T4 du0[3]; T4 lat[3]; T4 z1, z2o; const int64_t* rois; const float* q; int q_stride; int G, c1, c2;
+  T4 gz1;                 // out: grad wrt pre-ReLU z1 (128G, L4)
+  T4 gz2o;                // out: grad wrt pre-ReLU z2o (896G, 32)
+  float* dq;              // out (B, 256), overwritten
+};
+int latent_bwd(const LatentBwdArgs& a, cudaStream_t s);
+
+int bn_finalize(const BnLayer& bn, int C, double count, const float* gamma, const float* beta, float* rmean,
+                float* rvar, int64_t* nbt, int training, cudaStream_t s);
+int bn_relu(T4 c, const float* scale, const float* shift, T4 out, int upsample, cudaStream_t s);
+int up_adjoint(T4 du, T4 da, cudaStream_t s);
+int bnbwd_stats(T4 da, T4 c, const BnLayer& bn, cudaStream_t s);
+int bnbwd_apply(T4 da, T4 c, const BnLayer& bn, const float* gamma, double count, T4 dc, float* dgamma, float* dbeta,
+                cudaStream_t s);
+int dec_out_fwd(T4 c4, const float* scale, const float* shift, const float* w, const float* b, float* out,
+                int out_bstride, cudaStream_t s);
+int dec_out_bwd(T4 c4, const BnLayer& bn, const float* w, const float* out, const float* dout, T4 g4, float* dw,
+                float* db, cudaStream_t s);
+
+}  // namespace nef

@@ -1,0 +1,774 @@
+// Host-side orchestration of the Nef-Net hot path and the C ABI around it (include/nefnet_b200.h).
+// Follows Model_nefnet.forward (network/model_nefnet.py:109-194) and its autograd backward kernel by
+// kernel; every launch goes to the caller's stream, all memory comes from the caller's workspace.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "nef_elem.cuh"
+
+using namespace nef;
+
+// ---------------------------------------------------------------------------------------------
+// errors / library state
+// ---------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+extern "C" void nef_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+extern "C" const char* nef_last_error(void) { return g_err; }
+extern "C" int nef_version(void) { return NEF_ABI_VERSION; }
+
+extern "C" int nef_gconv_fwd_simt(const NefConvDesc* d, nef_stream_t s);
+extern "C" int nef_gconv_wgrad_simt(const NefWgradDesc* d, nef_stream_t s);
+extern "C" int nef_gconv_fwd_tc(const NefConvDesc* d, nef_stream_t s);
+extern "C" int nef_gconv_wgrad_tc(const NefWgradDesc* d, nef_stream_t s);
+extern "C" int nef_tc_init(void);
+
+static int g_conv_impl = 1;
+extern "C" int nef_set_conv_impl(int impl) {
+  g_conv_impl = impl;
+  return 0;
+}
+extern "C" int nef_get_conv_impl(void) { return g_conv_impl; }
+
+extern "C" int nef_init(int device) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  NEF_REQUIRE(e == cudaSuccess && n > 0, "nef_init: no CUDA device (%s); this library has no CPU path",
+              cudaGetErrorString(e));
+  NEF_REQUIRE(device >= 0 && device < n, "nef_init: device %d out of range (%d devices)", device, n);
+  cudaDeviceProp p;
+  cudaGetDeviceProperties(&p, device);
+  NEF_REQUIRE(p.major == 10, "nef_init: device %d is sm_%d%d; this library is built for sm_100a (B200) only", device,
+              p.major, p.minor);
+  cudaSetDevice(device);
+  return nef_tc_init();
+}
+
+extern "C" int nef_gconv_fwd(const NefConvDesc* d, nef_stream_t s) {
+  NEF_REQUIRE(d->N == 64 || d->N == 128, "nef_gconv_fwd: N must be 64 or 128 (got %d)", d->N);
+  for (int i = 0; i < d->n_terms; ++i)
+    NEF_REQUIRE(d->term[i].cin_g % 32 == 0 && d->term[i].taps >= 1 && d->term[i].taps <= 7,
+                "nef_gconv_fwd: term %d: cin_g %% 32 and taps in [1,7] required", i);
+  return g_conv_impl == 1 ? nef_gconv_fwd_tc(d, s) : nef_gconv_fwd_simt(d, s);
+}
+extern "C" int nef_gconv_wgrad(const NefWgradDesc* d, nef_stream_t s) {
+  NEF_REQUIRE(d->cout_g % 64 == 0 && d->cin_g % 64 == 0, "nef_gconv_wgrad: cout_g, cin_g must be multiples of 64");
+  return g_conv_impl == 1 ? nef_gconv_wgrad_tc(d, s) : nef_gconv_wgrad_simt(d, s);
+}
+
+// ---------------------------------------------------------------------------------------------
+// parameter table (state_dict order of the reference)
+// ---------------------------------------------------------------------------------------------
+enum ParamIdx {
+  P_STEM = 0,
+  P_ENC = 1,  // + 2*i + {0: conv1, 1: conv2}
+  P_MLP1_W = 7, P_MLP1_B, P_MLP2_W, P_MLP2_B, P_WFE_W, P_WFE_B,
+  P_WCONV = 13,   // + {0 conv1, 1 conv2, 2 res.w, 3 res.b}
+  P_Z1 = 17, P_Z2C1 = 21, P_Z2A = 25,
+  P_CT_W = 29, P_CT_B = 30,
+  P_Z2B = 31,
+  P_DEC1 = 35,    // + {0 c0.w,1 c0.b,2 bn1.w,3 bn1.b,4 rm,5 rv,6 nbt,7 c3.w,8 c3.b,9 bn4.w,10 bn4.b,11 rm,12 rv,13 nbt}
+  P_DEC3 = 49,
+  P_OUT_W = 63, P_OUT_B = 64,
+  P_COUNT = 65
+};
+
+struct ParamInfo { std::string name; int64_t numel; };
+static std::vector<ParamInfo> param_table(int G) {
+  std::vector<ParamInfo> t;
+  auto add = [&](const std::string& n, int64_t e) { t.push_back({n, e}); };
+  add("W_encoder.conv1.weight", 128LL * G * 15);
+  for (int i = 0; i < 3; ++i) {
+    add("W_encoder.layer1." + std::to_string(i) + ".conv1.weight", 128LL * G * 128 * 7);
+    add("W_encoder.layer1." + std::to_string(i) + ".conv2.weight", 128LL * G * 128 * 7);
+  }
+  add("mlp1.weight", 128 * 12); add("mlp1.bias", 128);
+  add("mlp2.weight", 256 * 12); add("mlp2.bias", 256);
+  add("w_feature_extractor.0.weight", 128 * 128 * 3); add("w_feature_extractor.0.bias", 128);
+  auto block = [&](const std::string& p, int cin_g, int groups) {
+    add(p + ".conv1.weight", 128LL * groups * cin_g * 3);
+    add(p + ".conv2.weight", 128LL * groups * 128 * 3);
+    add(p + ".residual_conv.weight", 128LL * groups * cin_g);
+    add(p + ".residual_conv.bias", 128LL * groups);
+  };
+  block("w_conv.0", 128, G);
+  block("z1_conv.0", 64, G);
+  block("z2_conv1.0", 64, G);
+  block("z2_conv2.0", 128, 7 * G);
+  add("z2_conv2.1.weight", 896LL * G * 64 * 2);
+  add("z2_conv2.1.bias", 448LL * G);
+  block("z2_conv2.2", 64, 7 * G);
+  const int cin[2] = {256, 128}, cout[2] = {128, 64};
+  const char* st[2] = {"decoder.1", "decoder.3"};
+  for (int s = 0; s < 2; ++s) {
+    const std::string p = std::string(st[s]) + ".double_conv.";
+    add(p + "0.weight", (int64_t)cout[s] * cin[s] * 3); add(p + "0.bias", cout[s]);
+    add(p + "1.weight", cout[s]); add(p + "1.bias", cout[s]);
+    add(p + "1.running_mean", cout[s]); add(p + "1.running_var", cout[s]); add(p + "1.num_batches_tracked", 1);
+    add(p + "3.weight", (int64_t)cout[s] * cout[s] * 3); add(p + "3.bias", cout[s]);
+    add(p + "4.weight", cout[s]); add(p + "4.bias", cout[s]);
+    add(p + "4.running_mean", cout[s]); add(p + "4.running_var", cout[s]); add(p + "4.num_batches_tracked", 1);
+  }
+  add("decoder.4.weight", 64 * 3); add("decoder.4.bias", 1);
+  return t;
+}
+static thread_local std::string g_name_tmp;
+extern "C" int nef_param_count(int G) { (void)G; return P_COUNT; }
+extern "C" const char* nef_param_name(int G, int i) {
+  auto t = param_table(G);
+  if (i < 0 || i >= (int)t.size()) return "";
+  g_name_tmp = t[i].name;
+  return g_name_tmp.c_str();
+}
+extern "C" int64_t nef_param_numel(int G, int i) {
+  auto t = param_table(G);
+  if (i < 0 || i >= (int)t.size()) return -1;
+  return t[i].numel;
+}
+
+// ---------------------------------------------------------------------------------------------
+// plan
+// ---------------------------------------------------------------------------------------------
+struct ConvW {            // one convolution's weights: reference tensor + packed copies
+  int pidx;               // index in the parameter table
+  int groups, cout_g, cin_g, taps;
+  float* pk_f;            // forward packing  [g][t][cin_g/32][8][cout_g][4]
+  float* pk_d;            // data-gradient packing (flipped taps, transposed); N = min(cin_g, 128)
+};
+
+struct DecBufs {          // one decoder call
+  T4 c1, a1, c2, u1, c3, a3, c4;
+  BnLayer bn[4];
+  float* out;             // (B, L) saved sigmoid output
+};
+
+struct NefPlan {
+  int B, G, L, V, L2, L4, C1;
+  Window win;
+  size_t ws_bytes;
+  char* base;
+  bool bound;
+  // bump allocator state (offsets in bytes, relative to base)
+  size_t cursor;
+  // activations
+  T4 s0, eh[3], ey[3], hw, w, h1, z1, xw, hz, z2c, ra, h20, y20, t21, h22, z2o;
+  T4 lat[3], u0[3];
+  DecBufs dec[3];
+  float *s_in, *q, *rq;
+  // gradients
+  T4 GA[3];
+  T4 gz2o, gh22, dt21, dte, dto, gy20, gh20, dra, gz2c, ghz, gxw;
+  T4 dg4, dg3, du1, dg2, dg1, du0[3];
+  float *ds_in, *dq;
+  double* bn_stats;       // all BnLayer doubles, contiguous (zeroed per step)
+  size_t bn_stats_count;
+  // weights
+  ConvW enc[6], wc[2], z1c[3], z2c1[3], z2a[2], z2b[3], decw[4];
+  float *ct_f[2], *ct_d[2];
+  // saved forward state
+  const float* x_in; const float* thetas_in; const float* query_in; const int64_t* rois_in;
+  int c1, c2; float drop_p; int bn_training; bool have_fwd;
+};
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct Carver {
+  NefPlan* p;
+  bool dry;
+  size_t cur;
+  void* take(size_t bytes) {
+    cur = align_up(cur, 256);
+    void* r = dry ? nullptr : (void*)(p->base + cur);
+    cur += bytes;
+    return r;
+  }
+  T4 t4(int C, int L) {
+    T4 t;
+    t.C = C; t.B = p->B; t.L = L; t.Lp = L + 2 * NEF_HALO;
+    t.cs = (long)p->B * t.Lp;
+    const size_t bytes = ((size_t)(C / 4) * t.cs + NEF_GUARD_ROWS) * sizeof(float4);
+    t.p = reinterpret_cast<float4*>(take(bytes));
+    return t;
+  }
+  float* f32(size_t n) { return reinterpret_cast<float*>(take(n * sizeof(float))); }
+};
+
+static void carve_convw(Carver& c, ConvW& w, int pidx, int groups, int cout_g, int cin_g, int taps) {
+  w.pidx = pidx; w.groups = groups; w.cout_g = cout_g; w.cin_g = cin_g; w.taps = taps;
+  const size_t n = (size_t)groups * cout_g * cin_g * taps;
+  w.pk_f = c.f32(n);
+  w.pk_d = c.f32(n);
+}
+
+static void carve(NefPlan* p, bool dry) {
+  Carver c{p, dry, 0};
+  c.take(NEF_GUARD_ROWS * sizeof(float4));  // front guard
+  const int G = p->G, C1 = p->C1, L4 = p->L4, L2 = p->L2, L = p->L, B = p->B;
+  p->s0 = c.t4(C1, L4);
+  for (int i = 0; i < 3; ++i) { p->eh[i] = c.t4(C1, L4); p->ey[i] = c.t4(C1, L4); }
+  p->hw = c.t4(C1, L4); p->w = c.t4(C1, L4); p->h1 = c.t4(C1, L4); p->z1 = c.t4(C1, L4);
+  p->xw = c.t4(64 * G, p->win.Lw); p->hz = c.t4(C1, p->win.Lw); p->z2c = c.t4(C1, p->win.Lw);
+  p->ra = c.t4(896 * G, 16); p->h20 = c.t4(896 * G, 16); p->y20 = c.t4(896 * G, 16);
+  p->t21 = c.t4(448 * G, 32); p->h22 = c.t4(896 * G, 32); p->z2o = c.t4(896 * G, 32);
+  for (int k = 0; k < 3; ++k) { p->lat[k] = c.t4(256, L4); p->u0[k] = c.t4(256, L2); }
+  for (int k = 0; k < 3; ++k) {
+    DecBufs& d = p->dec[k];
+    d.c1 = c.t4(128, L2); d.a1 = c.t4(128, L2); d.c2 = c.t4(128, L2); d.u1 = c.t4(128, L);
+    d.c3 = c.t4(64, L); d.a3 = c.t4(64, L); d.c4 = c.t4(64, L);
+    d.out = c.f32((size_t)B * L);
+    const int ch[4] = {128, 128, 64, 64};
+    for (int i = 0; i < 4; ++i) {
+      d.bn[i].scale = c.f32(ch[i]); d.bn[i].shift = c.f32(ch[i]);
+      d.bn[i].mean = c.f32(ch[i]); d.bn[i].invstd = c.f32(ch[i]);
+    }
+  }
+  // BatchNorm double accumulators: 3 calls x 4 layers x 4 arrays x 128
+  p->bn_stats_count = 3 * 4 * 4 * 128;
+  p->bn_stats = reinterpret_cast<double*>(c.take(p->bn_stats_count * sizeof(double)));
+  if (!dry) {
+    double* q = p->bn_stats;
+    for (int k = 0; k < 3; ++k)
+      for (int i = 0; i < 4; ++i) {
+        p->dec[k].bn[i].sum = q; q += 128;
+        p->dec[k].bn[i].sq = q; q += 128;
+        p->dec[k].bn[i].s1 = q; q += 128;
+        p->dec[k].bn[i].s2 = q; q += 128;
+      }
+  }
+  p->s_in = c.f32((size_t)B * C1); p->ds_in = c.f32((size_t)B * C1);
+  p->q = c.f32((size_t)B * 256); p->dq = c.f32((size_t)B * 256);
+  p->rq = c.f32((size_t)B * (p->V > 0 ? p->V : 1) * 256);
+  for (int i = 0; i < 3; ++i) p->GA[i] = c.t4(C1, L4);
+  p->gz2o = c.t4(896 * G, 32); p->gh22 = c.t4(896 * G, 32); p->dt21 = c.t4(448 * G, 32);
+  p->dte = c.t4(448 * G, 16); p->dto = c.t4(448 * G, 16);
+  p->gy20 = c.t4(896 * G, 16); p->gh20 = c.t4(896 * G, 16); p->dra = c.t4(896 * G, 16);
+  p->gz2c = c.t4(C1, p->win.Lw); p->ghz = c.t4(C1, p->win.Lw); p->gxw = c.t4(64 * G, p->win.Lw);
+  p->dg4 = c.t4(64, L); p->dg3 = c.t4(64, L); p->du1 = c.t4(128, L); p->dg2 = c.t4(128, L2); p->dg1 = c.t4(128, L2);
+  for (int k = 0; k < 3; ++k) p->du0[k] = c.t4(256, L2);
+  // weights
+  for (int i = 0; i < 6; ++i) carve_convw(c, p->enc[i], P_ENC + i, G, 128, 128, 7);
+  carve_convw(c, p->wc[0], P_WCONV + 0, G, 128, 128, 3);
+  carve_convw(c, p->wc[1], P_WCONV + 1, G, 128, 128, 3);
+  carve_convw(c, p->z1c[0], P_Z1 + 0, G, 128, 64, 3);
+  carve_convw(c, p->z1c[1], P_Z1 + 1, G, 128, 128, 3);
+  carve_convw(c, p->z1c[2], P_Z1 + 2, G, 128, 64, 1);
+  carve_convw(c, p->z2c1[0], P_Z2C1 + 0, G, 128, 64, 3);
+  carve_convw(c, p->z2c1[1], P_Z2C1 + 1, G, 128, 128, 3);
+  carve_convw(c, p->z2c1[2], P_Z2C1 + 2, G, 128, 64, 1);
+  carve_convw(c, p->z2a[0], P_Z2A + 0, 7 * G, 128, 128, 3);
+  carve_convw(c, p->z2a[1], P_Z2A + 1, 7 * G, 128, 128, 3);
+  carve_convw(c, p->z2b[0], P_Z2B + 0, 7 * G, 128, 64, 3);
+  carve_convw(c, p->z2b[1], P_Z2B + 1, 7 * G, 128, 128, 3);
+  carve_convw(c, p->z2b[2], P_Z2B + 2, 7 * G, 128, 64, 1);
+  carve_convw(c, p->decw[0], P_DEC1 + 0, 1, 128, 256, 3);
+  carve_convw(c, p->decw[1], P_DEC1 + 7, 1, 128, 128, 3);
+  carve_convw(c, p->decw[2], P_DEC3 + 0, 1, 64, 128, 3);
+  carve_convw(c, p->decw[3], P_DEC3 + 7, 1, 64, 64, 3);
+  for (int t = 0; t < 2; ++t) {
+    p->ct_f[t] = c.f32((size_t)7 * G * 128 * 64);
+    p->ct_d[t] = c.f32((size_t)7 * G * 128 * 64);
+  }
+  c.take(NEF_GUARD_ROWS * sizeof(float4));
+  p->ws_bytes = align_up(c.cur, 256);
+}
+
+extern "C" int nef_plan_create(int B, int G, int L, int V, NefPlan** out) {
+  NEF_REQUIRE(B >= 1 && G >= 1 && L >= 16 && L % 4 == 0, "nef_plan_create: need B>=1, G>=1, L>=16, L %% 4 == 0 (B=%d G=%d L=%d)",
+              B, G, L);
+  NefPlan* p = new NefPlan();
+  memset(p, 0, sizeof(NefPlan));
+  p->B = B; p->G = G; p->L = L; p->V = V; p->L2 = L / 2; p->L4 = L / 4; p->C1 = 128 * G;
+  p->win = centre_window(p->L4);
+  carve(p, true);
+  *out = p;
+  return 0;
+}
+extern "C" void nef_plan_destroy(NefPlan* p) { delete p; }
+extern "C" size_t nef_plan_workspace_bytes(const NefPlan* p) { return p->ws_bytes; }
+extern "C" int nef_plan_bind(NefPlan* p, void* ws, size_t bytes, nef_stream_t s) {
+  NEF_REQUIRE(bytes >= p->ws_bytes, "nef_plan_bind: workspace too small (%zu < %zu)", bytes, p->ws_bytes);
+  NEF_REQUIRE(((uintptr_t)ws & 255) == 0, "nef_plan_bind: workspace must be 256-byte aligned");
+  p->base = (char*)ws;
+  carve(p, false);
+  cudaError_t e = cudaMemsetAsync(ws, 0, p->ws_bytes, (cudaStream_t)s);
+  NEF_REQUIRE(e == cudaSuccess, "nef_plan_bind: memset failed: %s", cudaGetErrorString(e));
+  p->bound = true;
+  p->have_fwd = false;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// descriptor builders
+// ---------------------------------------------------------------------------------------------
+struct CD {
+  NefConvDesc d;
+  CD(int groups, int N, const T4& space) {
+    memset(&d, 0, sizeof(d));
+    d.groups = groups; d.N = N; d.rows = space.cs; d.Lp = space.Lp; d.L = space.L;
+    d.mask_scale = 1.f;
+  }
+  CD& term(const T4& x, int off, int gs, int cin_g, int taps, const float* w) {
+    NefConvTerm& t = d.term[d.n_terms++];
+    t.x = reinterpret_cast<const float*>(x.p); t.x_cstride = x.cs; t.x_c4_off = off; t.x_c4_gstride = gs;
+    t.cin_g = cin_g; t.taps = taps; t.tap_off = -(taps / 2); t.w = w;
+    return *this;
+  }
+  CD& out(const T4& y, int off, int gs, int lmul = 1, int ladd = 0) {
+    d.y = reinterpret_cast<float*>(y.p); d.y_cstride = y.cs; d.y_c4_off = off; d.y_c4_gstride = gs;
+    d.y_Lp = y.Lp; d.y_lmul = lmul; d.y_ladd = ladd;
+    return *this;
+  }
+  CD& bias(const float* b) { d.bias = b; return *this; }
+  CD& res(const T4& r, int off, int gs) {
+    d.res = reinterpret_cast<const float*>(r.p); d.res_cstride = r.cs; d.res_c4_off = off; d.res_c4_gstride = gs;
+    return *this;
+  }
+  CD& relu() { d.relu = 1; return *this; }
+  CD& drop(float p, uint64_t seed) { d.drop_p = p; d.drop_seed = seed; return *this; }
+  CD& bscale(const float* s) { d.bscale = s; return *this; }
+  CD& bsgrad(float* g) { d.bscale_grad = g; return *this; }
+  CD& mask(const T4& m, int off, int gs, int mode, float scale) {
+    d.mask = reinterpret_cast<const float*>(m.p); d.mask_cstride = m.cs; d.mask_c4_off = off; d.mask_c4_gstride = gs;
+    d.mask_mode = mode; d.mask_scale = scale;
+    return *this;
+  }
+  CD& stats(double* s1, double* s2) { d.stat_sum = s1; d.stat_sq = s2; return *this; }
+  CD& round() { d.round_tf32 = 1; return *this; }
+  int run(cudaStream_t s) { return nef_gconv_fwd(&d, (nef_stream_t)s); }
+};
+
+static int wgrad(const T4& dy, int dy_off, int dy_gs, int cout_g, const T4& x, int x_off, int x_gs, int cin_g,
+                 int groups, int taps, float* dw, int64_t sg, int64_t sm, int64_t sn, int64_t st, float* db,
+                 cudaStream_t s) {
+  if (!dw) return 0;
+  NefWgradDesc d;
+  memset(&d, 0, sizeof(d));
+  d.dy = reinterpret_cast<const float*>(dy.p); d.dy_cstride = dy.cs; d.dy_c4_off = dy_off; d.dy_c4_gstride = dy_gs;
+  d.x = reinterpret_cast<const float*>(x.p); d.x_cstride = x.cs; d.x_c4_off = x_off; d.x_c4_gstride = x_gs;
+  d.cout_g = cout_g; d.cin_g = cin_g; d.groups = groups; d.taps = taps; d.tap_off = -(taps / 2);
+  d.rows = dy.cs; d.dw = dw; d.sg = sg; d.sm = sm; d.sn = sn; d.st = st; d.db = db;
+  return nef_gconv_wgrad(&d, (nef_stream_t)s);
+}
+// standard Conv1d weight (groups*cout_g, cin_g, taps)
+static int wgrad_std(const T4& dy, int dy_off, int dy_gs, const T4& x, int x_off, int x_gs, const ConvW& w, float* dw,
+                     float* db, cudaStream_t s) {
+  return wgrad(dy, dy_off, dy_gs, w.cout_g, x, x_off, x_gs, w.cin_g, w.groups, w.taps, dw,
+               (int64_t)w.cout_g * w.cin_g * w.taps, (int64_t)w.cin_g * w.taps, w.taps, 1, db, s);
+}
+
+#define RUN(x)            \
+  do {                    \
+    int rc__ = (x);       \
+    if (rc__) return rc__; \
+  } while (0)
+
+static int pack_fwd(const ConvW& w, const float* const* P, cudaStream_t s) {
+  return nef_pack_weights(P[w.pidx], w.pk_f, w.groups, w.cout_g, w.cin_g, w.taps, (int64_t)w.cout_g * w.cin_g * w.taps,
+                          (int64_t)w.cin_g * w.taps, w.taps, 1, 0, (nef_stream_t)s);
+}
+// dgrad: N' = cin_g (split into sub-groups of 128 when larger; only for groups == 1), K' = cout_g, flipped taps
+static int pack_dgrad(const ConvW& w, const float* const* P, cudaStream_t s) {
+  if (w.cin_g > 128) {
+    const int sub = w.cin_g / 128;
+    return nef_pack_weights(P[w.pidx], w.pk_d, sub, 128, w.cout_g, w.taps, (int64_t)128 * w.taps, w.taps,
+                            (int64_t)w.cin_g * w.taps, 1, 1, (nef_stream_t)s);
+  }
+  return nef_pack_weights(P[w.pidx], w.pk_d, w.groups, w.cin_g, w.cout_g, w.taps, (int64_t)w.cout_g * w.cin_g * w.taps,
+                          w.taps, (int64_t)w.cin_g * w.taps, 1, 1, (nef_stream_t)s);
+}
+
+template <class F>
+static int for_all_convw(NefPlan* p, F f) {
+  for (int i = 0; i < 6; ++i) RUN(f(p->enc[i]));
+  for (int i = 0; i < 2; ++i) RUN(f(p->wc[i]));
+  for (int i = 0; i < 3; ++i) RUN(f(p->z1c[i]));
+  for (int i = 0; i < 3; ++i) RUN(f(p->z2c1[i]));
+  for (int i = 0; i < 2; ++i) RUN(f(p->z2a[i]));
+  for (int i = 0; i < 3; ++i) RUN(f(p->z2b[i]));
+  for (int i = 0; i < 4; ++i) RUN(f(p->decw[i]));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------------------------
+// residual block: h = drop(relu(conv1(x))) ; y = relu(conv2(h) + r(x))   (resnet_1d.py:39-53, model_nefnet.py:48-60)
+struct BlockIO {
+  T4 x; int x_off, x_gs;   // input view
+  T4 h, y;
+  const ConvW* c1; const ConvW* c2; const ConvW* cr;  // cr == nullptr: identity residual
+  const float* res_bias;
+  int groups;
+};
+
+static int block_fwd(const BlockIO& io, float drop_p, uint64_t seed, const float* bscale, cudaStream_t s) {
+  CD a(io.groups, 128, io.x);
+  a.term(io.x, io.x_off, io.x_gs, io.c1->cin_g, io.c1->taps, io.c1->pk_f).out(io.h, 0, 32).relu().round();
+  if (drop_p > 0.f) a.drop(drop_p, seed);
+  RUN(a.run(s));
+  CD b(io.groups, 128, io.x);
+  b.term(io.h, 0, 32, 128, io.c2->taps, io.c2->pk_f).out(io.y, 0, 32).relu().round();
+  if (io.cr) b.term(io.x, io.x_off, io.x_gs, io.cr->cin_g, 1, io.cr->pk_f).bias(io.res_bias);
+  else b.res(io.x, io.x_off, io.x_gs);
+  if (bscale) b.bscale(bscale);
+  RUN(b.run(s));
+  return 0;
+}
+
+static int decoder_fwd(NefPlan* p, const float* const* P, int slot, const T4& u0, int training, float* out_user,
+                       int out_bstride, cudaStream_t s) {
+  DecBufs& d = p->dec[slot];
+  const int B = p->B;
+  struct Lay { const ConvW* w; int pb; T4 in; T4 c; int bnp; double count; };
+  const Lay lay[4] = {{&p->decw[0], P_DEC1 + 1, u0, d.c1, P_DEC1 + 2, (double)B * p->L2},
+                      {&p->decw[1], P_DEC1 + 8, d.a1, d.c2, P_DEC1 + 9, (double)B * p->L2},
+                      {&p->decw[2], P_DEC3 + 1, d.u1, d.c3, P_DEC3 + 2, (double)B * p->L},
+                      {&p->decw[3], P_DEC3 + 8, d.a3, d.c4, P_DEC3 + 9, (double)B * p->L}};
+  for (int i = 0; i < 4; ++i) {
+    const Lay& l = lay[i];
+    CD c(1, l.w->cout_g, l.in);
+    c.term(l.in, 0, 0, l.w->cin_g, 3, l.w->pk_f).out(l.c, 0, 0).bias(P[l.pb]);
+    if (training) {
+      cudaMemsetAsync(d.bn[i].sum, 0, 2 * 128 * sizeof(double), s);  // sum and sq are adjacent
+      c.stats(d.bn[i].sum, d.bn[i].sq);
+    }
+    RUN(c.run(s));
+    RUN(bn_finalize(d.bn[i], l.w->cout_g, l.count, P[l.bnp], P[l.bnp + 1], const_cast<float*>(P[l.bnp + 2]),
+                    const_cast<float*>(P[l.bnp + 3]),
+                    reinterpret_cast<int64_t*>(const_cast<float*>(P[l.bnp + 4])), training, s));
+    if (i == 0) RUN(bn_relu(d.c1, d.bn[0].scale, d.bn[0].shift, d.a1, 0, s));
+    if (i == 1) RUN(bn_relu(d.c2, d.bn[1].scale, d.bn[1].shift, d.u1, 1, s));
+    if (i == 2) RUN(bn_relu(d.c3, d.bn[2].scale, d.bn[2].shift, d.a3, 0, s));
+  }
+  RUN(dec_out_fwd(d.c4, d.bn[3].scale, d.bn[3].shift, P[P_OUT_W], P[P_OUT_B], d.out, p->L, s));
+  if (out_user) {
+    cudaError_t e = cudaMemcpy2DAsync(out_user, (size_t)out_bstride * sizeof(float), d.out, (size_t)p->L * sizeof(float),
+                                      (size_t)p->L * sizeof(float), B, cudaMemcpyDeviceToDevice, s);
+    NEF_REQUIRE(e == cudaSuccess, "decoder_fwd: output copy failed: %s", cudaGetErrorString(e));
+  }
+  return 0;
+}
+
+static int latents_to_decoders(NefPlan* p, const float* const* P, const float* query_theta, const float* rest_theta,
+                               const int64_t* rois, int phase, int training, int V, float* out, float* out_p,
+                               float* out_l, float* rest_out, bool only_views, cudaStream_t s) {
+  const int B = p->B;
+  LatentArgs la;
+  la.z1 = p->z1; la.z2o = p->z2o; la.rois = rois; la.G = p->G; la.c1 = p->c1; la.c2 = p->c2;
+  for (int k = 0; k < 3; ++k) { la.lat[k] = p->lat[k]; la.u0[k] = p->u0[k]; }
+  if (!only_views) {
+    RUN(angular_fwd(query_theta, P[P_MLP2_W], P[P_MLP2_B], p->q, B, 256, s));
+    la.q = p->q; la.q_stride = 256; la.n_lat = 3; la.write_lat = 1;
+    RUN(latent_fwd(la, s));
+    float* outs[3] = {out, out_p, out_l};
+    for (int k = 0; k < 3; ++k) RUN(decoder_fwd(p, P, k, p->u0[k], training, outs[k], p->L, s));
+  } else {
+    // gen_ecg: build lat[0] only (mean latents); q unused for that -> use rq view 0 below
+    la.q = p->rq; la.q_stride = V * 256; la.n_lat = 1; la.write_lat = 1;
+  }
+  if (V > 0 && (phase == NEF_PHASE_TEST || only_views)) {
+    NEF_REQUIRE(V <= p->V, "nef_forward: V=%d exceeds the plan's V=%d", V, p->V);
+    RUN(angular_fwd(rest_theta, P[P_MLP2_W], P[P_MLP2_B], p->rq, B * V, 256, s));
+    for (int v = 0; v < V; ++v) {
+      la.q = p->rq + (size_t)v * 256; la.q_stride = V * 256; la.n_lat = 1;
+      la.write_lat = (only_views && v == 0) ? 1 : 0;
+      RUN(latent_fwd(la, s));
+      RUN(decoder_fwd(p, P, 0, p->u0[0], training, rest_out + (size_t)v * p->L, V * p->L, s));
+    }
+  }
+  return 0;
+}
+
+extern "C" int nef_forward(NefPlan* p, const NefForwardArgs* a, nef_stream_t sv) {
+  cudaStream_t s = (cudaStream_t)sv;
+  NEF_REQUIRE(p && p->bound, "nef_forward: plan not bound to a workspace");
+  const float* const* P = a->params;
+  const int G = p->G, B = p->B;
+  NEF_REQUIRE(a->lead_choice_z1 >= 0 && a->lead_choice_z1 < G && a->lead_choice_z2 >= 0 && a->lead_choice_z2 < G,
+              "nef_forward: lead choice out of range");
+  p->have_fwd = false;
+  p->c1 = a->lead_choice_z1; p->c2 = a->lead_choice_z2; p->drop_p = a->drop_p; p->bn_training = a->bn_training;
+  p->x_in = a->x; p->thetas_in = a->input_thetas; p->query_in = a->query_theta; p->rois_in = a->rois;
+
+  RUN(for_all_convw(p, [&](const ConvW& w) { return pack_fwd(w, P, s); }));
+  for (int t = 0; t < 2; ++t)  // ConvTranspose1d weight (Cin_total, Cout/groups, 2): one 1x1 conv per tap
+    RUN(nef_pack_weights(P[P_CT_W] + t, p->ct_f[t], 7 * G, 64, 128, 1, 128LL * 64 * 2, 2, 64 * 2, 0, 0, sv));
+
+  RUN(stem_fwd(a->x, P[P_STEM], p->s0, G, s));
+  RUN(angular_fwd(a->input_thetas, P[P_MLP1_W], P[P_MLP1_B], p->s_in, B * G, 128, s));
+  const float dp = a->drop_p;
+  const uint64_t seed = a->drop_seed * 16;
+  for (int i = 0; i < 3; ++i) {
+    BlockIO io{i == 0 ? p->s0 : p->ey[i - 1], 0, 32, p->eh[i], p->ey[i], &p->enc[2 * i], &p->enc[2 * i + 1], nullptr,
+               nullptr, G};
+    RUN(block_fwd(io, dp, seed + i, i == 2 ? p->s_in : nullptr, s));
+  }
+  {
+    BlockIO io{p->ey[2], 0, 32, p->hw, p->w, &p->wc[0], &p->wc[1], nullptr, nullptr, G};
+    RUN(block_fwd(io, dp, seed + 3, nullptr, s));
+  }
+  {
+    BlockIO io{p->w, 0, 32, p->h1, p->z1, &p->z1c[0], &p->z1c[1], &p->z1c[2], P[P_Z1 + 3], G};
+    RUN(block_fwd(io, dp, seed + 4, nullptr, s));
+  }
+  RUN(window_extract(p->w, p->xw, G, p->win, s));
+  {
+    BlockIO io{p->xw, 0, 16, p->hz, p->z2c, &p->z2c1[0], &p->z2c1[1], &p->z2c1[2], P[P_Z2C1 + 3], G};
+    RUN(block_fwd(io, dp, seed + 5, nullptr, s));
+  }
+  RUN(roi_align_fwd(p->z2c, a->rois, p->ra, p->win, p->L4, s));
+  {
+    BlockIO io{p->ra, 0, 32, p->h20, p->y20, &p->z2a[0], &p->z2a[1], nullptr, nullptr, 7 * G};
+    RUN(block_fwd(io, dp, seed + 6, nullptr, s));
+  }
+  for (int t = 0; t < 2; ++t) {  // ConvTranspose1d(k2, s2): out[2l + t] = W_t x[l] + b
+    CD c(7 * G, 64, p->y20);
+    c.term(p->y20, 0, 32, 128, 1, p->ct_f[t]).out(p->t21, 0, 16, 2, t).bias(P[P_CT_B]).round();
+    c.d.term[0].tap_off = 0;
+    RUN(c.run(s));
+  }
+  {
+    BlockIO io{p->t21, 0, 16, p->h22, p->z2o, &p->z2b[0], &p->z2b[1], &p->z2b[2], P[P_Z2B + 3], 7 * G};
+    RUN(block_fwd(io, dp, seed + 7, nullptr, s));
+  }
+  if (a->phase == NEF_PHASE_GEN) {
+    RUN(nef_cbl4_to_ncl(reinterpret_cast<const float*>(p->z1.p), a->out, B, p->C1, p->L4, sv));
+    RUN(nef_cbl4_to_ncl(reinterpret_cast<const float*>(p->z2o.p), a->out_p, B, 896 * G, 32, sv));
+    return 0;
+  }
+  RUN(latents_to_decoders(p, P, a->query_theta, a->rest_theta, a->rois, a->phase, a->bn_training,
+                          a->phase == NEF_PHASE_TEST ? p->V : 0, a->out, a->out_p, a->out_l, a->rest_out, false, s));
+  p->have_fwd = a->save_for_backward != 0 && a->phase == NEF_PHASE_TRAIN;
+  return 0;
+}
+
+extern "C" int nef_gen_ecg(NefPlan* p, const float* const* P, const float* z1, const float* z2, const float* query_theta,
+                           const int64_t* rois, int V, float* out, nef_stream_t sv) {
+  cudaStream_t s = (cudaStream_t)sv;
+  NEF_REQUIRE(p && p->bound, "nef_gen_ecg: plan not bound to a workspace");
+  NEF_REQUIRE(V >= 1 && V <= p->V, "nef_gen_ecg: V=%d not in [1, plan V=%d]", V, p->V);
+  p->have_fwd = false;
+  p->c1 = 0; p->c2 = 0;
+  for (int i = 0; i < 4; ++i) RUN(pack_fwd(p->decw[i], P, s));
+  RUN(nef_ncl_to_cbl4(z1, reinterpret_cast<float*>(p->z1.p), p->B, p->C1, p->L4, 0, sv));
+  RUN(nef_ncl_to_cbl4(z2, reinterpret_cast<float*>(p->z2o.p), p->B, 896 * p->G, 32, 0, sv));
+  return latents_to_decoders(p, P, nullptr, query_theta, rois, NEF_PHASE_TEST, 0, V, nullptr, nullptr, nullptr, out,
+                             true, s);
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward
+// ---------------------------------------------------------------------------------------------
+// residual block backward.  gy = grad w.r.t. the block's pre-ReLU output (already masked).
+// Produces gx through `fin` (a descriptor prepared by the caller with its output / mask / extras).
+struct BlockBwd {
+  BlockIO io;
+  T4 gy, gh;
+  float *dw1, *dw2, *dwr, *dbr;
+};
+static int block_bwd(const BlockBwd& b, float drop_p, CD& fin, cudaStream_t s) {
+  const BlockIO& io = b.io;
+  RUN(wgrad_std(b.gy, 0, 32, io.h, 0, 32, *io.c2, b.dw2, nullptr, s));
+  if (io.cr) RUN(wgrad_std(b.gy, 0, 32, io.x, io.x_off, io.x_gs, *io.cr, b.dwr, b.dbr, s));
+  CD a(io.groups, 128, io.x);
+  a.term(b.gy, 0, 32, 128, io.c2->taps, io.c2->pk_d).out(b.gh, 0, 32).mask(io.h, 0, 32, 1, 1.f / (1.f - drop_p)).round();
+  RUN(a.run(s));
+  RUN(wgrad_std(b.gh, 0, 32, io.x, io.x_off, io.x_gs, *io.c1, b.dw1, nullptr, s));
+  // gx = conv1^T(gh) + (identity: gy | 1x1: res^T(gy))
+  fin.term(b.gh, 0, 32, 128, io.c1->taps, io.c1->pk_d);
+  if (io.cr) fin.term(b.gy, 0, 32, 128, 1, io.cr->pk_d);
+  else fin.res(b.gy, 0, 32);
+  RUN(fin.run(s));
+  return 0;
+}
+
+static int decoder_bwd(NefPlan* p, const float* const* P, float* const* Gd, int slot, const float* dout, cudaStream_t s) {
+  DecBufs& d = p->dec[slot];
+  const int B = p->B;
+  const double n2 = (double)B * p->L2, n1 = (double)B * p->L;
+  auto g = [&](int i) { return Gd[i]; };
+  // output layer + bn4 statistics
+  RUN(dec_out_bwd(d.c4, d.bn[3], P[P_OUT_W], d.out, dout, p->dg4, g(P_OUT_W), g(P_OUT_B), s));
+  RUN(bnbwd_apply(p->dg4, d.c4, d.bn[3], P[P_DEC3 + 9], n1, p->dg4, g(P_DEC3 + 9), g(P_DEC3 + 10), s));
+  RUN(wgrad_std(p->dg4, 0, 0, d.a3, 0, 0, p->decw[3], g(P_DEC3 + 7), g(P_DEC3 + 8), s));
+  {
+    CD c(1, 64, p->dg4);
+    c.term(p->dg4, 0, 0, 64, 3, p->decw[3].pk_d).out(p->dg3, 0, 0);
+    RUN(c.run(s));
+  }
+  RUN(bnbwd_stats(p->dg3, d.c3, d.bn[2], s));
+  RUN(bnbwd_apply(p->dg3, d.c3, d.bn[2], P[P_DEC3 + 2], n1, p->dg3, g(P_DEC3 + 2), g(P_DEC3 + 3), s));
+  RUN(wgrad_std(p->dg3, 0, 0, d.u1, 0, 0, p->decw[2], g(P_DEC3 + 0), g(P_DEC3 + 1), s));
+  {
+    CD c(1, 128, p->dg3);
+    c.term(p->dg3, 0, 0, 64, 3, p->decw[2].pk_d).out(p->du1, 0, 0);
+    RUN(c.run(s));
+  }
+  RUN(up_adjoint(p->du1, p->dg2, s));
+  RUN(bnbwd_stats(p->dg2, d.c2, d.bn[1], s));
+  RUN(bnbwd_apply(p->dg2, d.c2, d.bn[1], P[P_DEC1 + 9], n2, p->dg2, g(P_DEC1 + 9), g(P_DEC1 + 10), s));
+  RUN(wgrad_std(p->dg2, 0, 0, d.a1, 0, 0, p->decw[1], g(P_DEC1 + 7), g(P_DEC1 + 8), s));
+  {
+    CD c(1, 128, p->dg2);
+    c.term(p->dg2, 0, 0, 128, 3, p->decw[1].pk_d).out(p->dg1, 0, 0);
+    RUN(c.run(s));
+  }
+  RUN(bnbwd_stats(p->dg1, d.c1, d.bn[0], s));
+  RUN(bnbwd_apply(p->dg1, d.c1, d.bn[0], P[P_DEC1 + 2], n2, p->dg1, g(P_DEC1 + 2), g(P_DEC1 + 3), s));
+  RUN(wgrad_std(p->dg1, 0, 0, p->u0[slot], 0, 0, p->decw[0], g(P_DEC1 + 0), g(P_DEC1 + 1), s));
+  {
+    CD c(2, 128, p->dg1);  // 256 output channels as two sub-groups reading the same input
+    c.term(p->dg1, 0, 0, 128, 3, p->decw[0].pk_d).out(p->du0[slot], 0, 32).round();
+    RUN(c.run(s));
+  }
+  return 0;
+}
+
+static int zero_t4(const T4& t, cudaStream_t s) {
+  cudaError_t e = cudaMemsetAsync(t.p, 0, (size_t)(t.C / 4) * t.cs * sizeof(float4), s);
+  NEF_REQUIRE(e == cudaSuccess, "memset failed: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+extern "C" int nef_backward(NefPlan* p, const NefBackwardArgs* a, nef_stream_t sv) {
+  cudaStream_t s = (cudaStream_t)sv;
+  NEF_REQUIRE(p && p->bound && p->have_fwd, "nef_backward: no saved training forward on this plan");
+  const float* const* P = a->params;
+  float* const* Gd = a->grads;
+  const int G = p->G, B = p->B;
+  const float dp = p->drop_p;
+  p->have_fwd = false;
+
+  RUN(for_all_convw(p, [&](const ConvW& w) { return pack_dgrad(w, P, s); }));
+  for (int t = 0; t < 2; ++t)  // ConvTranspose dgrad: dx[l] = sum_t W_t^T dy[2l + t] ; N' = ci (128), K' = co (64)
+    RUN(nef_pack_weights(P[P_CT_W] + t, p->ct_d[t], 7 * G, 128, 64, 1, 128LL * 64 * 2, 64 * 2, 2, 0, 0, sv));
+  // zero the BatchNorm backward accumulators (s1, s2 of every layer)
+  for (int k = 0; k < 3; ++k)
+    for (int i = 0; i < 4; ++i) cudaMemsetAsync(p->dec[k].bn[i].s1, 0, 2 * 128 * sizeof(double), s);
+
+  const float* douts[3] = {a->dout, a->dout_p, a->dout_l};
+  for (int k = 0; k < 3; ++k) {
+    if (douts[k]) RUN(decoder_bwd(p, P, Gd, k, douts[k], s));
+    else RUN(zero_t4(p->du0[k], s));
+  }
+  // latents
+  LatentBwdArgs lb;
+  for (int k = 0; k < 3; ++k) { lb.du0[k] = p->du0[k]; lb.lat[k] = p->lat[k]; }
+  lb.z1 = p->z1; lb.z2o = p->z2o; lb.rois = p->rois_in; lb.q = p->q; lb.q_stride = 256; lb.G = G; lb.c1 = p->c1; lb.c2 = p->c2;
+  lb.gz1 = p->GA[0]; lb.gz2o = p->gz2o; lb.dq = p->dq;
+  RUN(latent_bwd(lb, s));
+  if (Gd[P_MLP2_W]) RUN(angular_bwd(p->query_in, p->dq, Gd[P_MLP2_W], Gd[P_MLP2_B], B, 256, s));
+
+  // ---- z1 branch: gz1 = GA0, gh = GA1, result into the z1 half of g_w = GA2
+  {
+    BlockBwd bb{{p->w, 0, 32, p->h1, p->z1, &p->z1c[0], &p->z1c[1], &p->z1c[2], nullptr, G}, p->GA[0], p->GA[1],
+                Gd[P_Z1 + 0], Gd[P_Z1 + 1], Gd[P_Z1 + 2], Gd[P_Z1 + 3]};
+    CD fin(G, 64, p->w);
+    fin.out(p->GA[2], 0, 32).mask(p->w, 0, 32, 1, 1.f).round();
+    RUN(block_bwd(bb, dp, fin, s));
+  }
+  // ---- z2 branch
+  {
+    BlockBwd bb{{p->t21, 0, 16, p->h22, p->z2o, &p->z2b[0], &p->z2b[1], &p->z2b[2], nullptr, 7 * G}, p->gz2o, p->gh22,
+                Gd[P_Z2B + 0], Gd[P_Z2B + 1], Gd[P_Z2B + 2], Gd[P_Z2B + 3]};
+    CD fin(7 * G, 64, p->t21);
+    fin.out(p->dt21, 0, 16).round();
+    RUN(block_bwd(bb, dp, fin, s));
+  }
+  RUN(deinterleave2(p->dt21, p->dte, p->dto, s));
+  {
+    const T4* dts[2] = {&p->dte, &p->dto};
+    for (int t = 0; t < 2; ++t) {
+      float* dw = Gd[P_CT_W] ? Gd[P_CT_W] + t : nullptr;
+      if (dw) {
+        NefWgradDesc d;
+        memset(&d, 0, sizeof(d));
+        d.dy = reinterpret_cast<const float*>(dts[t]->p); d.dy_cstride = dts[t]->cs; d.dy_c4_off = 0; d.dy_c4_gstride = 16;
+        d.x = reinterpret_cast<const float*>(p->y20.p); d.x_cstride = p->y20.cs; d.x_c4_off = 0; d.x_c4_gstride = 32;
+        d.cout_g = 64; d.cin_g = 128; d.groups = 7 * G; d.taps = 1; d.tap_off = 0; d.rows = p->y20.cs;
+        d.dw = dw; d.sg = 128LL * 64 * 2; d.sm = 2; d.sn = 64 * 2; d.st = 0; d.db = Gd[P_CT_B];
+        RUN(nef_gconv_wgrad(&d, sv));
+      }
+    }
+    CD c(7 * G, 128, p->y20);
+    c.term(p->dte, 0, 16, 64, 1, p->ct_d[0]).term(p->dto, 0, 16, 64, 1, p->ct_d[1]);
+    c.d.term[0].tap_off = 0; c.d.term[1].tap_off = 0;
+    c.out(p->gy20, 0, 32).mask(p->y20, 0, 32, 1, 1.f).round();
+    RUN(c.run(s));
+  }
+  {
+    BlockBwd bb{{p->ra, 0, 32, p->h20, p->y20, &p->z2a[0], &p->z2a[1], nullptr, nullptr, 7 * G}, p->gy20, p->gh20,
+                Gd[P_Z2A + 0], Gd[P_Z2A + 1], nullptr, nullptr};
+    CD fin(7 * G, 128, p->ra);
+    fin.out(p->dra, 0, 32);
+    RUN(block_bwd(bb, dp, fin, s));
+  }
+  RUN(roi_align_bwd(p->dra, p->rois_in, p->z2c, p->gz2c, p->win, p->L4, s));
+  {
+    BlockBwd bb{{p->xw, 0, 16, p->hz, p->z2c, &p->z2c1[0], &p->z2c1[1], &p->z2c1[2], nullptr, G}, p->gz2c, p->ghz,
+                Gd[P_Z2C1 + 0], Gd[P_Z2C1 + 1], Gd[P_Z2C1 + 2], Gd[P_Z2C1 + 3]};
+    CD fin(G, 64, p->xw);
+    fin.out(p->gxw, 0, 16).mask(p->xw, 0, 16, 1, 1.f).round();
+    RUN(block_bwd(bb, dp, fin, s));
+  }
+  RUN(window_scatter(p->gxw, p->GA[2], G, p->win, s));
+  // ---- w_conv: g_w = GA2, gh = GA0, result (grad of the unscaled last encoder output, pre-ReLU) = GA1
+  cudaMemsetAsync(p->ds_in, 0, (size_t)B * p->C1 * sizeof(float), s);
+  {
+    BlockBwd bb{{p->ey[2], 0, 32, p->hw, p->w, &p->wc[0], &p->wc[1], nullptr, nullptr, G}, p->GA[2], p->GA[0],
+                Gd[P_WCONV + 0], Gd[P_WCONV + 1], nullptr, nullptr};
+    CD fin(G, 128, p->ey[2]);
+    fin.out(p->GA[1], 0, 32).bscale(p->s_in).bsgrad(p->ds_in).mask(p->ey[2], 0, 32, 2, 1.f).round();
+    RUN(block_bwd(bb, dp, fin, s));
+  }
+  if (Gd[P_MLP1_W]) RUN(angular_bwd(p->thetas_in, p->ds_in, Gd[P_MLP1_W], Gd[P_MLP1_B], B * G, 128, s));
+  // ---- encoder blocks 2, 1, 0
+  {
+    int gy_i = 1;  // GA index holding gy
+    for (int i = 2; i >= 0; --i) {
+      const int gx_i = gy_i == 1 ? 2 : 1;
+      BlockBwd bb{{i == 0 ? p->s0 : p->ey[i - 1], 0, 32, p->eh[i], p->ey[i], &p->enc[2 * i], &p->enc[2 * i + 1], nullptr,
+                   nullptr, G},
+                  p->GA[gy_i], p->GA[0], Gd[P_ENC + 2 * i], Gd[P_ENC + 2 * i + 1], nullptr, nullptr};
+      CD fin(G, 128, p->s0);
+      fin.out(p->GA[gx_i], 0, 32);
+      if (i > 0) fin.mask(p->ey[i - 1], 0, 32, 1, 1.f).round();
+      RUN(block_bwd(bb, dp, fin, s));
+      gy_i = gx_i;
+    }
+    if (Gd[P_STEM]) RUN(stem_bwd(p->x_in, P[P_STEM], p->GA[gy_i], Gd[P_STEM], G, s));
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// single-op exports for unit tests
+// ---------------------------------------------------------------------------------------------
+static T4 view_t4(const float* ptr, int C, int B, int L) {
+  T4 t;
+  t.p = reinterpret_cast<float4*>(const_cast<float*>(ptr));
+  t.C = C; t.B = B; t.L = L; t.Lp = L + 2 * NEF_HALO; t.cs = (long)B * t.Lp;
+  return t;
+}
+extern "C" int nef_stem_fwd(const float* x, const float* w, float* y, int B, int G, int L, nef_stream_t s) {
+  return stem_fwd(x, w, view_t4(y, 128 * G, B, L / 4), G, (cudaStream_t)s);
+}
+extern "C" int nef_stem_bwd(const float* x, const float* w, const float* dy, float* dw, int B, int G, int L,
+                            nef_stream_t s) {
+  return stem_bwd(x, w, view_t4(dy, 128 * G, B, L / 4), dw, G, (cudaStream_t)s);
+}
+extern "C" int nef_angular_fwd(const float* theta, const float* w, const float* b, float* out, int n, int D,
+                               nef_stream_t s) {
+  return angular_fwd(theta, w, b, out, n, D, (cudaStream_t)s);
+}
+extern "C" int nef_angular_bwd(const float* theta, const float* dout, float* dw, float* db, int n, int D,
+                               nef_stream_t s) {
+  return angular_bwd(theta, dout, dw, db, n, D, (cudaStream_t)s);
+}

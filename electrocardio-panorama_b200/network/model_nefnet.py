@@ -1,0 +1,357 @@
+"""Nef-Net on B200: the nn.Module surface of the reference's ``network.model_nefnet.Model_nefnet``
+(/root/reference/codes/network/model_nefnet.py:63-218) over the hand-written sm_100a kernels in
+``csrc/`` (through the C ABI in include/nefnet_b200.h).
+
+Same constructor, same ``forward(x, input_thetas, query_theta, rois, rest_theta=None, phase='train')``
+and ``gen_ecg(z1, z2, query_theta, rois)`` signatures and return tuples, same ``state_dict`` keys,
+shapes and default initialisation, same consumption of Python's ``random`` (two ``randint`` draws per
+train/val/test forward, z1 first).  There is no CPU or eager-PyTorch path: calling the module on a
+non-CUDA tensor raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import random
+
+import torch
+import torch.nn as nn
+
+from . import _native as N
+
+_UNUSED = ("w_feature_extractor.0.weight", "w_feature_extractor.0.bias", "w_conv.0.residual_conv.weight",
+           "w_conv.0.residual_conv.bias", "z2_conv2.0.residual_conv.weight", "z2_conv2.0.residual_conv.bias")
+
+
+def _param_specs(G):
+    """(name, shape, kind) in the reference's registration order (model_nefnet.py:67-107)."""
+    specs = [("W_encoder.conv1.weight", (128 * G, 1, 15), "enc")]
+    for i in range(3):
+        specs.append((f"W_encoder.layer1.{i}.conv1.weight", (128 * G, 128, 7), "enc"))
+        specs.append((f"W_encoder.layer1.{i}.conv2.weight", (128 * G, 128, 7), "enc"))
+    specs += [("mlp1.weight", (128, 12), "w"), ("mlp1.bias", (128,), "b"), ("mlp2.weight", (256, 12), "w"),
+              ("mlp2.bias", (256,), "b"), ("w_feature_extractor.0.weight", (128, 128, 3), "w"),
+              ("w_feature_extractor.0.bias", (128,), "b")]
+
+    def block(prefix, cin_g, groups):
+        return [(prefix + ".conv1.weight", (128 * groups, cin_g, 3), "w"),
+                (prefix + ".conv2.weight", (128 * groups, 128, 3), "w"),
+                (prefix + ".residual_conv.weight", (128 * groups, cin_g, 1), "w"),
+                (prefix + ".residual_conv.bias", (128 * groups,), "b")]
+
+    specs += block("w_conv.0", 128, G) + block("z1_conv.0", 64, G) + block("z2_conv1.0", 64, G)
+    specs += block("z2_conv2.0", 128, 7 * G)
+    specs += [("z2_conv2.1.weight", (896 * G, 64, 2), "wt"), ("z2_conv2.1.bias", (448 * G,), "bt")]
+    specs += block("z2_conv2.2", 64, 7 * G)
+    for stage, cin, cout in (("decoder.1", 256, 128), ("decoder.3", 128, 64)):
+        p = stage + ".double_conv."
+        specs += [(p + "0.weight", (cout, cin, 3), "w"), (p + "0.bias", (cout,), "b"),
+                  (p + "1.weight", (cout,), "one"), (p + "1.bias", (cout,), "zero"),
+                  (p + "1.running_mean", (cout,), "buf0"), (p + "1.running_var", (cout,), "buf1"),
+                  (p + "1.num_batches_tracked", (), "nbt"),
+                  (p + "3.weight", (cout, cout, 3), "w"), (p + "3.bias", (cout,), "b"),
+                  (p + "4.weight", (cout,), "one"), (p + "4.bias", (cout,), "zero"),
+                  (p + "4.running_mean", (cout,), "buf0"), (p + "4.running_var", (cout,), "buf1"),
+                  (p + "4.num_batches_tracked", (), "nbt")]
+    specs += [("decoder.4.weight", (1, 64, 3), "w"), ("decoder.4.bias", (1,), "b")]
+    return specs
+
+
+class _Node(nn.Module):
+    """Bare container so that parameters registered under dotted names give the reference's keys."""
+
+
+class _NefFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, model, x, input_thetas, query_theta, rois, c1, c2, *live_params):
+        outs = model._run_forward(x, input_thetas, query_theta, rois, None, N.PHASE_TRAIN, c1, c2, save=True)
+        ctx.model = model
+        ctx.token = model._fwd_token
+        return outs
+
+    @staticmethod
+    def backward(ctx, dout, dout_p, dout_l):
+        model = ctx.model
+        if ctx.token != model._fwd_token:
+            raise RuntimeError("Model_nefnet (B200): backward() after a newer forward(); only the latest training "
+                               "forward is retained")
+        grads = model._run_backward(dout, dout_p, dout_l)
+        return (None,) * 7 + tuple(grads)
+
+
+class Model_nefnet(nn.Module):
+    def __init__(self, theta_encoder_len=1, lead_num=1):
+        super().__init__()
+        if theta_encoder_len != 1:
+            # theta_encoder.py:13-29 ignores encoder_len (one frequency); mlp1/mlp2 take 12 features only
+            raise ValueError("theta_encoder_len must be 1 (the reference's ThetaEncoder emits 12 features)")
+        self.theta_encoder_len = theta_encoder_len
+        self.lead_num = int(lead_num)
+        self.dropout_p = 0.2          # nn.Dropout(0.2) of every residual block; active in train() mode
+        self._specs = _param_specs(self.lead_num)
+        self._names = [s[0] for s in self._specs]
+        self._plans = {}
+        self._fwd_token = 0
+        self._step = 0
+        self._flat = None
+        self._flat_grad = None
+        self._build_parameters()
+
+    # ------------------------------------------------------------------ parameters
+    def _register(self, dotted, tensor, is_buffer):
+        node = self
+        parts = dotted.split(".")
+        for part in parts[:-1]:
+            if part not in node._modules:
+                node.add_module(part, _Node())
+            node = node._modules[part]
+        if is_buffer:
+            node.register_buffer(parts[-1], tensor)
+        else:
+            node.register_parameter(parts[-1], nn.Parameter(tensor))
+
+    def _build_parameters(self):
+        """Default initialisation of the reference: N(0, sqrt(2 / (k*k*Cout))) for the resnet convs
+        (resnet_1d.py:114-120), PyTorch's Conv/Linear defaults elsewhere, BN gamma 1 / beta 0."""
+        for name, shape, kind in self._specs:
+            if kind == "nbt":
+                t = torch.zeros((), dtype=torch.long)
+            elif kind in ("buf0", "zero"):
+                t = torch.zeros(shape)
+            elif kind in ("buf1", "one"):
+                t = torch.ones(shape)
+            elif kind == "enc":
+                k = shape[2]
+                t = torch.randn(shape) * math.sqrt(2.0 / (k * k * shape[0]))
+            else:
+                if kind in ("w", "b"):
+                    wshape = shape if kind == "w" else dict((n, s) for n, s, _ in self._specs)[name[:-4] + "weight"]
+                    fan_in = 1
+                    for d in wshape[1:]:
+                        fan_in *= d
+                else:  # ConvTranspose1d: fan_in is computed from weight.size(1) * k
+                    wshape = (896 * self.lead_num, 64, 2)
+                    fan_in = wshape[1] * wshape[2]
+                bound = 1.0 / math.sqrt(fan_in)
+                t = (torch.rand(shape) * 2.0 - 1.0) * bound
+            self._register(name, t, is_buffer=kind in ("buf0", "buf1", "nbt"))
+
+    def _tensors(self):
+        """name -> tensor for every state_dict entry, in order."""
+        sd = dict(self.named_parameters())
+        sd.update(dict(self.named_buffers()))
+        return [sd[n] for n in self._names]
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)
+        self._flat = None  # parameter storage was replaced; re-flatten lazily on the next forward
+        self._flat_grad = None
+        for plan in self._plans.values():
+            plan.close()
+        self._plans = {}
+        return out
+
+    def _flatten(self, device):
+        """Moves all float parameters into one contiguous fp32 buffer (16-byte aligned slots) and points
+        the nn.Parameters at views of it; the gradient buffer has the same layout.  The optimiser step
+        and the data-parallel all-reduce then run over flat memory."""
+        live = [(n, p) for n, p in self.named_parameters()]
+        offs, total = {}, 0
+        for n, p in live:
+            offs[n] = total
+            total += (p.numel() + 3) // 4 * 4
+        flat = torch.zeros(total, dtype=torch.float32, device=device)
+        for n, p in live:
+            view = flat[offs[n]:offs[n] + p.numel()].view(p.shape)
+            view.copy_(p.data)
+            p.data = view
+        self._flat = flat
+        self._flat_grad = torch.zeros_like(flat)
+        self._offsets = offs
+        self._grad_views = {n: self._flat_grad[offs[n]:offs[n] + p.numel()].view(p.shape) for n, p in live}
+
+    @property
+    def flat_params(self):
+        return self._flat
+
+    @property
+    def flat_grads(self):
+        return self._flat_grad
+
+    def _ensure_ready(self, device):
+        if device.type != "cuda":
+            raise RuntimeError("Model_nefnet (B200) runs on an sm_100 CUDA device only; got tensors on %s. "
+                               "There is no CPU path." % device)
+        N.init(device.index if device.index is not None else torch.cuda.current_device())
+        p0 = next(self.parameters())
+        if p0.device != device:
+            raise RuntimeError("Model_nefnet: parameters are on %s but inputs on %s" % (p0.device, device))
+        ok = self._flat is not None and self._flat.device == device
+        if ok:
+            base = self._flat.data_ptr()
+            end = base + self._flat.numel() * 4
+            for n, p in self.named_parameters():
+                if not (base <= p.data_ptr() < end) or p.dtype != torch.float32:
+                    ok = False
+                    break
+        if not ok:
+            for p in self.parameters():
+                if p.dtype != torch.float32:
+                    raise RuntimeError("Model_nefnet (B200): parameters must be float32")
+            self._flatten(device)
+
+    def _param_ptr_array(self):
+        arr = (C.c_void_p * len(self._names))()
+        for i, t in enumerate(self._tensors()):
+            arr[i] = t.data_ptr()
+        return arr
+
+    # ------------------------------------------------------------------ plans / workspace
+    class _Plan:
+        def __init__(self, B, G, L, V, device):
+            lib = N.load()
+            h = C.c_void_p()
+            N.check(lib.nef_plan_create(B, G, L, V, C.byref(h)), "nef_plan_create")
+            self.handle = h
+            self.bytes = lib.nef_plan_workspace_bytes(h)
+            self.ws = torch.empty(self.bytes, dtype=torch.uint8, device=device)
+            N.check(lib.nef_plan_bind(h, C.c_void_p(self.ws.data_ptr()), self.bytes, N.stream_ptr()), "nef_plan_bind")
+
+        def close(self):
+            if self.handle is not None:
+                N.load().nef_plan_destroy(self.handle)
+                self.handle = None
+                self.ws = None
+
+    def _plan(self, B, L, V, device):
+        key = (B, L, V, device.index)
+        plan = self._plans.get(key)
+        if plan is None:
+            for old in self._plans.values():  # one live workspace at a time (tens of GB at batch 256)
+                old.close()
+            self._plans = {}
+            plan = Model_nefnet._Plan(B, self.lead_num, L, V, device)
+            self._plans[key] = plan
+        return plan
+
+    @staticmethod
+    def _f32(t, device):
+        return t.detach().to(device=device, dtype=torch.float32).contiguous()
+
+    # ------------------------------------------------------------------ execution
+    def _run_forward(self, x, input_thetas, query_theta, rois, rest_theta, phase, c1, c2, save):
+        device = x.device
+        self._ensure_ready(device)
+        lib = N.load()
+        B, G, L = x.shape
+        if G != self.lead_num:
+            raise ValueError("expected %d leads, got %d" % (self.lead_num, G))
+        if L % 4 != 0 or L < 16:
+            raise ValueError("segment length must be a multiple of 4 and >= 16")
+        V = int(rest_theta.shape[1]) if (rest_theta is not None and phase == N.PHASE_TEST) else 0
+        plan = self._plan(B, L, V, device)
+        x = self._f32(x, device)
+        input_thetas = self._f32(input_thetas, device)
+        query_theta = self._f32(query_theta, device)
+        rois = rois.detach().to(device=device, dtype=torch.int64).contiguous()
+        rest = self._f32(rest_theta, device) if V > 0 else None
+        a = N.NefForwardArgs()
+        self._params_arr = self._param_ptr_array()
+        a.params = C.cast(self._params_arr, C.POINTER(C.c_void_p))
+        a.x, a.input_thetas, a.query_theta, a.rois = x.data_ptr(), input_thetas.data_ptr(), query_theta.data_ptr(), rois.data_ptr()
+        a.rest_theta = rest.data_ptr() if rest is not None else None
+        a.phase = phase
+        a.bn_training = 1 if self.training else 0
+        a.lead_choice_z1, a.lead_choice_z2 = int(c1), int(c2)
+        a.drop_p = float(self.dropout_p) if self.training else 0.0
+        a.save_for_backward = 1 if save else 0
+        a.drop_seed = ((torch.initial_seed() * 6364136223846793005) + self._step) & 0x0FFFFFFFFFFFFFFF
+        self._step += 1
+        if phase == N.PHASE_GEN:
+            z1 = torch.empty((B, 128 * G, L // 4), dtype=torch.float32, device=device)
+            z2 = torch.empty((B, 128 * G, 7, 32), dtype=torch.float32, device=device)
+            a.out, a.out_p = z1.data_ptr(), z2.data_ptr()
+            outs = (z1, z2)
+        else:
+            o = [torch.empty((B, 1, L), dtype=torch.float32, device=device) for _ in range(3)]
+            a.out, a.out_p, a.out_l = o[0].data_ptr(), o[1].data_ptr(), o[2].data_ptr()
+            outs = tuple(o)
+            if V > 0:
+                ro = torch.empty((B, V, L), dtype=torch.float32, device=device)
+                a.rest_out = ro.data_ptr()
+                outs = outs + (ro,)
+        N.check(lib.nef_forward(plan.handle, C.byref(a), N.stream_ptr()), "nef_forward")
+        self._fwd_token += 1
+        # keep the inputs alive until backward (the plan holds raw pointers to them)
+        self._saved = (x, input_thetas, query_theta, rois, plan) if save else None
+        return outs
+
+    def _run_backward(self, dout, dout_p, dout_l):
+        lib = N.load()
+        x, input_thetas, query_theta, rois, plan = self._saved
+        device = x.device
+        self._flat_grad.zero_()
+        names = self._names
+        garr = (C.c_void_p * len(names))()
+        for i, n in enumerate(names):
+            gv = self._grad_views.get(n)
+            garr[i] = gv.data_ptr() if (gv is not None and n not in _UNUSED) else None
+        b = N.NefBackwardArgs()
+        self._params_arr = self._param_ptr_array()
+        b.params = C.cast(self._params_arr, C.POINTER(C.c_void_p))
+        b.grads = C.cast(garr, C.POINTER(C.c_void_p))
+        keep = []
+        for field, g in (("dout", dout), ("dout_p", dout_p), ("dout_l", dout_l)):
+            if g is not None:
+                g = self._f32(g, device)
+                keep.append(g)
+                setattr(b, field, g.data_ptr())
+        N.check(lib.nef_backward(plan.handle, C.byref(b), N.stream_ptr()), "nef_backward")
+        self._saved = None
+        return [self._grad_views[n] for n in self._live_names()]
+
+    def _live_names(self):
+        return [n for n, _ in self.named_parameters() if n not in _UNUSED]
+
+    def _live_params(self):
+        d = dict(self.named_parameters())
+        return [d[n] for n in self._live_names()]
+
+    # ------------------------------------------------------------------ public surface
+    def forward(self, x, input_thetas, query_theta, rois, rest_theta=None, phase="train"):
+        """model_nefnet.py:109-194.  x (B, lead_num, L) fp32, input_thetas (B, lead_num, 2), query_theta
+        (B, 2), rois (B, 7, 2) int64, rest_theta (B, V, 2)."""
+        if phase == "gen":  # latents before roi reverse (:140-141); no random draws
+            with torch.no_grad():
+                return self._run_forward(x, input_thetas, query_theta, rois, None, N.PHASE_GEN, 0, 0, save=False)
+        if phase not in ("train", "val", "test"):
+            raise KeyError("please type correct phase")  # :194
+        c1 = random.randint(0, self.lead_num - 1)  # :154
+        c2 = random.randint(0, self.lead_num - 1)  # :156
+        if phase == "train":
+            if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+                self._ensure_ready(x.device)
+                return _NefFunction.apply(self, x, input_thetas, query_theta, rois, c1, c2, *self._live_params())
+            return self._run_forward(x, input_thetas, query_theta, rois, None, N.PHASE_TRAIN, c1, c2, save=False)
+        with torch.no_grad():  # the reference runs val/test under no_grad (solver.py:121)
+            return self._run_forward(x, input_thetas, query_theta, rois, rest_theta, N.PHASE_TEST, c1, c2, save=False)
+
+    def gen_ecg(self, z1, z2, query_theta, rois):
+        """model_nefnet.py:196-218: decode V views from latents; flips the module to eval (:197)."""
+        self.eval()
+        device = z1.device
+        self._ensure_ready(device)
+        lib = N.load()
+        B = z1.shape[0]
+        L = z1.shape[2] * 4
+        V = int(query_theta.shape[1])
+        plan = self._plan(B, L, V, device)
+        z1 = self._f32(z1, device)
+        z2 = self._f32(z2, device)
+        q = self._f32(query_theta, device)
+        rois = rois.detach().to(device=device, dtype=torch.int64).contiguous()
+        out = torch.empty((B, V, L), dtype=torch.float32, device=device)
+        arr = self._param_ptr_array()
+        N.check(lib.nef_gen_ecg(plan.handle, C.cast(arr, C.POINTER(C.c_void_p)), N.ptr(z1), N.ptr(z2), N.ptr(q),
+                                N.ptr(rois), V, N.ptr(out), N.stream_ptr()), "nef_gen_ecg")
+        return out

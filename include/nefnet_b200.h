@@ -1,0 +1,208 @@
+/* nefnet_b200 -- C ABI of the B200-native Nef-Net hot path (libnefnet_b200.so).
+ *
+ * The reference (WhatAShot/Electrocardio-Panorama) is pure PyTorch and has no FFI of its own; the hot
+ * path it runs is codes/network/model_nefnet.py:109-218 (Model_nefnet.forward / gen_ecg),
+ * codes/network/encoder/{encoder.py:28-40,resnet_1d.py:39-53,102-105}, codes/network/utils/
+ * {theta_encoder.py:13-29,roi_pooling_1d.py:38-99} and codes/network/loss/losses.py:21-50, driven by
+ * codes/solver/solver.py:171-235.  Each entry point below names the reference lines it replaces.
+ *
+ * Conventions: every function returns 0 on success, non-zero on error (nef_last_error() gives the
+ * thread-local message).  All pointers are DEVICE pointers unless marked host.  The caller owns every
+ * buffer, including the workspace; the library never allocates device memory and never synchronises.
+ * Every launch goes to the stream passed in.  There is no CPU path: on a machine without an sm_100
+ * device nef_init() fails.
+ *
+ * Internal activation layout ("CBL4"): a tensor of C channels (C % 4 == 0), B segments, L samples is
+ *   float4 T[C/4][B * (L + 2*NEF_HALO)],  row = b * (L + 2*NEF_HALO) + NEF_HALO + l,  lane = c % 4
+ * with the halo rows kept zero.  nef_ncl_to_cbl4 / nef_cbl4_to_ncl convert from/to (B, C, L).
+ */
+#ifndef NEFNET_B200_H
+#define NEFNET_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NEF_ABI_VERSION 1
+#define NEF_HALO_ROWS 3
+#define NEF_GUARD_ROWS_ABI 272
+
+typedef void* nef_stream_t; /* cudaStream_t */
+
+/* ---- library ------------------------------------------------------------------------------- */
+int nef_version(void);
+const char* nef_last_error(void);
+/* Selects `device`, checks it is sm_100, opts the kernels into their shared-memory sizes. */
+int nef_init(int device);
+/* 0 = CUDA-core fp32 implicit GEMM, 1 = tcgen05 TF32 (default when built in).  Test hook. */
+int nef_set_conv_impl(int impl);
+int nef_get_conv_impl(void);
+
+/* ---- parameters (state_dict contract; model_nefnet.py:67-107) -------------------- */
+/* Number of state_dict entries for lead_num = G, their names (host strings), element counts.   */
+int nef_param_count(int G);
+const char* nef_param_name(int G, int index);
+int64_t nef_param_numel(int G, int index);
+
+/* ---- layout -------------------------------------------------------------------------------- */
+/* rows of one channel chunk of a CBL4 tensor, and float count of a whole tensor incl. tail guard */
+int64_t nef_cbl4_rows(int B, int L);
+int64_t nef_cbl4_floats(int C, int B, int L);
+int nef_ncl_to_cbl4(const float* src, float* dst, int B, int C, int L, int round_tf32, nef_stream_t s);
+int nef_cbl4_to_ncl(const float* src, float* dst, int B, int C, int L, nef_stream_t s);
+
+/* ---- grouped 1-D convolution as implicit GEMM ---------------------------------------------- */
+/* replaces every nn.Conv1d / nn.ConvTranspose1d call of resnet_1d.py:21-24,39-53 and
+ * model_nefnet.py:10-60,84-107 (forward and data-gradient; the latter is the same contraction with
+ * flipped / transposed packed weights).                                                         */
+typedef struct NefConvTerm {
+  const float* x;       /* CBL4 input */
+  int64_t x_cstride;    /* rows between channel chunks (= B * Lp) */
+  int32_t x_c4_off;     /* first chunk read by group 0 */
+  int32_t x_c4_gstride; /* chunk step between groups */
+  int32_t cin_g;        /* input channels per group, multiple of 32 */
+  int32_t taps;         /* 1, 3 or 7 */
+  int32_t tap_off;      /* row offset of tap 0 (= -(taps/2) for a "same" convolution) */
+  int32_t reserved;
+  const float* w;       /* packed weights [group][tap][cin_g/32][8][N][4], see nef_pack_weights */
+} NefConvTerm;
+
+typedef struct NefConvDesc {
+  int32_t n_terms;      /* 1 or 2: the terms accumulate into the same output */
+  int32_t groups;
+  int32_t N;            /* output channels per group: 64 or 128 */
+  int32_t round_tf32;   /* round the stored result to TF32 (it feeds another tensor-core conv) */
+  NefConvTerm term[2];
+  int64_t rows;         /* B * Lp rows of the input row space are visited */
+  int32_t Lp, L;        /* segment pitch and length of the input row space */
+  /* output mapping: input row (b, l) -> output row b * y_Lp + HALO + l * y_lmul + y_ladd */
+  float* y;
+  int64_t y_cstride;
+  int32_t y_c4_off, y_c4_gstride;
+  int32_t y_Lp, y_lmul, y_ladd;
+  /* epilogue, in this order: v = acc + bias + res ; stats(v) ; relu ; dropout ; bscale ;
+   * bscale_grad ; mask ; round ; store                                                        */
+  int32_t relu;
+  const float* bias;    /* [groups * N] or NULL */
+  const float* res;     /* CBL4, output row space, or NULL */
+  int64_t res_cstride;
+  int32_t res_c4_off, res_c4_gstride;
+  float drop_p;         /* 0 = no dropout; survivors are scaled by 1/(1-p) */
+  int32_t mask_mode;    /* 0 none, 1: v *= (mask > 0) * mask_scale, 2: v *= (mask != 0) * mask_scale */
+  uint64_t drop_seed;
+  const float* bscale;  /* [B][groups * N] per-segment channel scale (angular encoding), or NULL */
+  float* bscale_grad;   /* [B][groups * N] += sum_l v * mask / bscale, then v *= bscale ; needs mask_mode 2 */
+  const float* mask;    /* CBL4, output row space */
+  int64_t mask_cstride;
+  int32_t mask_c4_off, mask_c4_gstride;
+  float mask_scale;
+  int32_t reserved2;
+  double* stat_sum;     /* [groups * N] += sum over valid rows of v, or NULL (BatchNorm batch statistics) */
+  double* stat_sq;      /* [groups * N] += sum of v * v */
+} NefConvDesc;
+
+/* Packs reference-layout weights into the layout NefConvTerm.w expects, rounding to TF32 (RN):
+ *   dst[g][t][kb][c][n][j] = src[g*sg + n*sn + (kb*32 + c*4 + j)*sk + (flip ? taps-1-t : t)*st]   */
+int nef_pack_weights(const float* src, float* dst, int groups, int N, int K, int taps, int64_t sg, int64_t sn,
+                     int64_t sk, int64_t st, int flip, nef_stream_t s);
+int nef_gconv_fwd(const NefConvDesc* d, nef_stream_t s);
+
+/* weight gradient: dw[g*sg + m*sm + n*sn + t*st] += sum_rows dy[row][g, m] * x[row + t + tap_off][g, n];
+ * db[g*cout_g + m] += sum_rows dy[row][g, m]                                                     */
+typedef struct NefWgradDesc {
+  const float* dy;
+  int64_t dy_cstride;
+  int32_t dy_c4_off, dy_c4_gstride;
+  const float* x;
+  int64_t x_cstride;
+  int32_t x_c4_off, x_c4_gstride;
+  int32_t cout_g, cin_g; /* multiples of 64 */
+  int32_t groups, taps, tap_off, reserved;
+  int64_t rows;
+  float* dw;
+  int64_t sg, sm, sn, st;
+  float* db; /* or NULL */
+} NefWgradDesc;
+int nef_gconv_wgrad(const NefWgradDesc* d, nef_stream_t s);
+
+/* ---- whole path ---------------------------------------------------------------------------- */
+typedef struct NefPlan NefPlan;
+/* V = number of extra views decoded in phase 'test' (0 for training). host call. */
+int nef_plan_create(int B, int G, int L, int V, NefPlan** plan);
+void nef_plan_destroy(NefPlan* plan);
+size_t nef_plan_workspace_bytes(const NefPlan* plan);
+/* Carves the caller's workspace (must be nef_plan_workspace_bytes) and zero-fills it on `s`. */
+int nef_plan_bind(NefPlan* plan, void* workspace, size_t bytes, nef_stream_t s);
+
+enum { NEF_PHASE_TRAIN = 0, NEF_PHASE_TEST = 1, NEF_PHASE_GEN = 2 };
+
+typedef struct NefForwardArgs {
+  const float* const* params; /* host array of nef_param_count(G) device pointers, state_dict order
+                                 (BatchNorm running stats included; num_batches_tracked entries are int64) */
+  const float* x;             /* (B, G, L) */
+  const float* input_thetas;  /* (B, G, 2) */
+  const float* query_theta;   /* (B, 2) */
+  const int64_t* rois;        /* (B, 7, 2) */
+  const float* rest_theta;    /* (B, V, 2) or NULL */
+  int32_t phase;              /* NEF_PHASE_* */
+  int32_t bn_training;        /* module.training: batch statistics + running-stat update */
+  int32_t lead_choice_z1, lead_choice_z2; /* the two random.randint draws, model_nefnet.py:154,156 */
+  float drop_p;               /* 0.2 in training, 0 in eval */
+  int32_t save_for_backward;
+  uint64_t drop_seed;
+  float* out;                 /* (B, 1, L) x3 ; phase GEN: out = z1 (B,128G,L/4), out_p = z2 (B,128G,7,32) */
+  float* out_p;
+  float* out_l;
+  float* rest_out;            /* (B, V, L) */
+} NefForwardArgs;
+/* Model_nefnet.forward, model_nefnet.py:109-194 */
+int nef_forward(NefPlan* plan, const NefForwardArgs* a, nef_stream_t s);
+
+typedef struct NefBackwardArgs {
+  const float* const* params;
+  float* const* grads;        /* host array, same order; NULL entries are skipped; gradients ACCUMULATE (+=) */
+  const float* dout;          /* (B, 1, L) x3, NULL = zero */
+  const float* dout_p;
+  const float* dout_l;
+} NefBackwardArgs;
+/* autograd of the above (solver.py:233) for the last nef_forward(save_for_backward = 1) on this plan */
+int nef_backward(NefPlan* plan, const NefBackwardArgs* a, nef_stream_t s);
+
+/* Model_nefnet.gen_ecg, model_nefnet.py:196-218: decode V views from supplied latents (eval-mode BN) */
+int nef_gen_ecg(NefPlan* plan, const float* const* params, const float* z1, const float* z2,
+                const float* query_theta /* (B, V, 2) */, const int64_t* rois, int V, float* out /* (B, V, L) */,
+                nef_stream_t s);
+
+/* ---- Standin-Learning loss, losses.py:21-50 ------------------------------------------------- */
+/* sums[0..2] = sum|out - out_p|, sum|out - out_l|, sum|out - target| (or squared for mse) ; doubles,
+ * zeroed by the call.  losses[0..3] = total, l1*f0, l2*f1, l3*f2 as floats.                      */
+int nef_loss_fwd(const float* out, const float* out_p, const float* out_l, const float* target, int64_t n,
+                 int use_mse, const float* factors3_host, int using_mask, double* sums, float* losses,
+                 nef_stream_t s);
+/* gradients of the total w.r.t. the three predictions (out is detached in the first two terms) */
+int nef_loss_bwd(const float* out, const float* out_p, const float* out_l, const float* target, int64_t n,
+                 int use_mse, const float* factors3_host, int using_mask, const float* dloss /* device float[4] or NULL */,
+                 float* dout, float* dout_p, float* dout_l, nef_stream_t s);
+/* mean |a - b| or mean (a-b)^2 into result[0] (the unsupervised validation term, losses.py:47-49) */
+int nef_pair_loss(const float* a, const float* b, int64_t n, int use_mse, double* sum, float* result,
+                  nef_stream_t s);
+
+/* ---- optimiser (solver/optim_scheduler.py:10, solver.py:234-235) ---------------------------- */
+/* g *= gscale ; m = momentum * m + g ; p -= lr * m    over flat buffers (lr read from host value) */
+int nef_sgd_step(float* p, const float* g, float* m, int64_t n, float lr, float momentum, float gscale,
+                 nef_stream_t s);
+
+/* ---- single ops, exported for unit tests ---------------------------------------------------- */
+/* encoder stem, resnet_1d.py:102-105 + encoder.py:35-38: x (B,G,L) -> CBL4 (128G, L/4) */
+int nef_stem_fwd(const float* x, const float* w, float* y, int B, int G, int L, nef_stream_t s);
+int nef_stem_bwd(const float* x, const float* w, const float* dy, float* dw, int B, int G, int L, nef_stream_t s);
+/* Angular encoding + Linear, theta_encoder.py:13-29 + model_nefnet.py:76-77: (n,2) -> (n,D) */
+int nef_angular_fwd(const float* theta, const float* w, const float* b, float* out, int n, int D, nef_stream_t s);
+int nef_angular_bwd(const float* theta, const float* dout, float* dw, float* db, int n, int D, nef_stream_t s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
