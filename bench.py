@@ -1,0 +1,300 @@
+#!/usr/bin/env python
+"""Benchmark of the Nef-Net hot path on B200 (BASELINE.json: ECG segments/sec, B x 12 x 5000 train step).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B] [--length L]
+
+A step is one Nef-Net training step on one synthetic batch: forward (three decoder passes, BatchNorm batch
+statistics, dropout 0.2) + Standin-Learning loss + hand-written backward + (N > 1: one NCCL all-reduce of
+the flat gradient buffer) + fused SGD-momentum update.  At N = 1 the workload is BASELINE.json configs[1]
+(batch 256 x 12 leads x 5000 samples, fp32 storage / TF32 tensor-core multiply); N > 1 is weak scaling with
+256 segments per GPU (configs[2]).  One JSON line is printed by rank 0.
+
+--impl reference times the reference algorithm's CPU restatement (oracle/, kind "port": the reference is
+pure PyTorch and /root/reference does not exist on the GPU box) on the host cores, on a bounded sample.
+"""
+import argparse
+import json
+import os
+import random
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "electrocardio-panorama_b200")
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+METRIC = "ECG segments/sec (Bx12x5000) Nef-Net train step"
+UNIT = "segments/s"
+
+
+class Cfg:
+    class SOLVER:
+        reg_loss = "l1_loss"
+        loss_using = [1, 2, 3]
+        loss_factor = [0.5, 0.5, 1]
+
+
+def algorithmic_bytes_per_segment(G, L, n_dec=3, live=True):
+    """forward floats per segment with every fused block reading its inputs once and writing
+    its output once; 'live' = z2_conv1 evaluated only on the centre window (what this implementation does).
+    A train step is counted as 3x forward."""
+    A = 128 * G * (L // 4)
+    a = 128 * G * 7 * 16
+    d = 256 * (L // 4)
+    fl = G * L + A + 15 * A + 5 * A + 4 * A + (0 if live else 4 * A) + 256 * G + a + 15 * a + 2 * a + A + A + A / G
+    fl += n_dec * (9 * d + L)
+    return 4.0 * fl
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.stop_flag = False
+        self.sm, self.smmax, self.reasons = [], [], set()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [v.strip() for v in out.strip().split(",")]
+                self.sm.append(float(f[0]))
+                self.smmax.append(float(f[1]))
+                for n, v in zip(names, f[2:6]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        return {"sm_mhz": statistics.median(self.sm), "sm_max_mhz": max(self.smmax), "reasons": sorted(self.reasons)}
+
+
+def cpu_baseline(G, L, steps=2, warmup=1, B=8):
+    """The reference algorithm (oracle port) on the host: forward + loss + backward + SGD, dropout off is
+    NOT used here -- the reference trains with dropout, so keep-masks are drawn on the host as it does."""
+    import torch
+    from oracle import nefnet_oracle as O
+    P = O.make_params(G, 0)
+    inp = O.make_inputs(B, G, L, 0)
+    mom = {}
+    gen = torch.Generator().manual_seed(0)
+
+    def keeps():
+        k = {}
+        for name, ch, ln in ([(f"W_encoder.layer1.{i}", 128 * G, L // 4) for i in range(3)] +
+                             [("w_conv.0", 128 * G, L // 4), ("z1_conv.0", 128 * G, L // 4),
+                              ("z2_conv1.0", 128 * G, L // 4), ("z2_conv2.0", 896 * G, 16), ("z2_conv2.2", 896 * G, 32)]):
+            k[name] = torch.rand(B, ch, ln, generator=gen) >= 0.2
+        return k
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        O.train_step(P, inp, lead_choice=(it % G, (it + 1) % G), momentum_buf=mom, keeps=keeps())
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    t = min(times)
+    return {"value": B / t, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": "oracle train step (fwd + Standin loss + bwd + SGD) at B=%d x %d x %d fp32, %d warm-up + best of %d"
+                      % (B, G, L, warmup, steps), "host_cpus": os.cpu_count()}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    G, L = 12, args.length
+    cb = cpu_baseline(G, L, steps=max(1, min(args.steps, 3)), warmup=min(args.warmup, 1), B=8)
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * 8 / cb["value"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "Nef-Net train step, 12 leads x %d samples, CPU sample of 8 segments" % L,
+                       "leads": 12, "length": L},
+            "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def time_dominant_kernel(torch, dev, B, G, L, reps=6):
+    """Average CUDA-event duration of the dominant kernel (grouped k7 implicit-GEMM conv, 128G -> 128G channels
+    at L/4, the shape of the six encoder convs and their six data-gradient launches) on inputs > L2."""
+    from network import ops, _native as N
+    C1, L4 = 128 * G, L // 4
+    x, y = ops.Cbl4(C1, B, L4, dev), ops.Cbl4(C1, B, L4, dev)
+    x.data.normal_()
+    w = torch.randn(C1, 128, 7, device=dev) * 0.03
+    wpk = ops.pack_conv_weight(w, G)
+    d = ops.conv_desc(x, wpk, y, G, 128, 128, 7, relu=True, round_tf32=True)
+    for _ in range(2):
+        ops.gconv_fwd(d)
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+    for a, b in evs:
+        a.record()
+        ops.gconv_fwd(d)
+        b.record()
+    torch.cuda.synchronize()
+    ms = statistics.mean(a.elapsed_time(b) for a, b in evs)
+    alg_bytes = 2.0 * C1 * L4 * B * 4          # read X once, write Y once (weights excluded)
+    flops = 2.0 * B * L4 * C1 * 128 * 7
+    del x, y
+    return ms, alg_bytes, flops
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=6)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=256, help="segments per GPU")
+    ap.add_argument("--length", type=int, default=5000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference "
+                         "for the CPU baseline)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    import network
+    from network import _native as N
+    from network.optim import FlatSGD, allreduce_gradients
+    from oracle import nefnet_oracle as O  # synthetic input generator only (and the cpu_baseline leg)
+
+    G, L, B = 12, args.length, args.batch
+    lib = N.init(local)
+    torch.manual_seed(0)
+    random.seed(0)
+    model = network.Model_nefnet(theta_encoder_len=1, lead_num=G).to(dev).train()
+    opt = FlatSGD(model, lr=0.1, momentum=0.9)
+    loss_fn = network.build_loss(type("C", (), {"MODEL": type("M", (), {"loss": "v1"})}))
+
+    host = O.make_inputs(min(B, 16), G, L, seed=rank)
+    reps = (B + host["x"].shape[0] - 1) // host["x"].shape[0]
+    host = {k: v.repeat(*([reps] + [1] * (v.dim() - 1)))[:B].contiguous().pin_memory() for k, v in host.items()}
+    resident = {k: v.to(dev) for k, v in host.items()}
+    h2d = sum(host[k].numel() * host[k].element_size() for k in ("x", "input_thetas", "query_theta", "rois", "target"))
+
+    def step(inp):
+        outs = model(inp["x"], inp["input_thetas"], inp["query_theta"], inp["rois"], phase="train")
+        loss = loss_fn(outs[0], outs[1], outs[2], inp["target"], Cfg)[0]
+        loss.backward()
+        if world > 1:
+            allreduce_gradients(model)
+        opt.step(world)
+        opt.zero_grad()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, k):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+        return ms
+
+    for _ in range(max(args.warmup, 3)):
+        step(resident)
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = lib.nef_launch_count()
+    ms = timed(lambda: step(resident), args.steps)
+    launches = lib.nef_launch_count() - l0
+
+    def e2e_step():
+        inp = {k: host[k].to(dev, non_blocking=True) for k in ("x", "input_thetas", "query_theta", "rois", "target")}
+        return float(step(inp).detach().cpu())
+    e2e_step()
+    ms_e2e = timed(e2e_step, args.steps)
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+
+    ms_step = ms / args.steps
+    value = world * B / (ms_step / 1000.0)
+    e2e_value = world * B / (ms_e2e / args.steps / 1000.0)
+    line = None
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+        kms, kbytes, kflops = time_dominant_kernel(torch, dev, B, G, L)
+        achieved = kbytes / (kms / 1000.0) / 1e9
+        step_bytes = 3.0 * algorithmic_bytes_per_segment(G, L) * B
+        tf32_peak = float(peaks.get("bf16_tflops", 1590.0)) / 2.0
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "tf32", "data": "synthetic",
+                "config": {"workload": "Nef-Net train step (fwd x3 decoder passes + Standin L1 loss + bwd + "
+                                       "%sSGD-momentum), batch %d/GPU x 12 leads x %d samples, dropout 0.2, BN batch stats"
+                                       % ("NCCL grad all-reduce + " if world > 1 else "", B, L),
+                           "batch_per_gpu": B, "global_batch": B * world, "leads": G, "length": L,
+                           "conv_impl": "tcgen05-tf32" if lib.nef_get_conv_impl() == 1 else "cuda-core-fp32",
+                           "l2": "inputs (>= 2 GB activations per layer) far exceed the 126 MB L2; no flush needed"},
+                "clocks": sampler.summary(),
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                        "ms_per_step": ms_e2e / args.steps},
+                "gpu_launches": int(launches),
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                             "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                             "kernel": "grouped k7 implicit-GEMM conv (encoder block conv / dgrad), %d x %d x %d" % (B, 128 * G, L // 4),
+                             "kernel_ms": kms, "kernel_algorithmic_bytes": kbytes,
+                             "kernel_tflops": kflops / (kms / 1000.0) / 1e12, "tf32_peak_tflops_half_of_bf16": tf32_peak,
+                             "step_algorithmic_gb": step_bytes / 1e9,
+                             "step_hbm_frac": step_bytes / (ms_step / 1000.0) / 1e9 / hbm_peak},
+                }
+    if world > 1:
+        dist.barrier()
+    if rank == 0:
+        del model
+        torch.cuda.empty_cache()
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(G, L)
+        else:
+            line["cpu_baseline"] = None
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

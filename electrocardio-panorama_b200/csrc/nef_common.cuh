@@ -18,8 +18,11 @@
 
 extern "C" void nef_set_error(const char* fmt, ...);
 
+extern "C" void nef_count_launch(void);  // every kernel launch of the library is counted (nef_launch_count)
+
 #define NEF_CHECK_LAUNCH(name)                                                        \
   do {                                                                                \
+    nef_count_launch();                                                               \
     cudaError_t e__ = cudaGetLastError();                                             \
     if (e__ != cudaSuccess) {                                                         \
       nef_set_error("%s: launch failed: %s", name, cudaGetErrorString(e__));          \
@@ -37,7 +40,15 @@ extern "C" void nef_set_error(const char* fmt, ...);
 
 namespace nef {
 
+// Test hook (nef_set_exact_fp32): when set, nothing is rounded to TF32, so that the CUDA-core
+// implementation is a plain fp32 computation that can be compared tightly with the fp32 oracle.
+// One copy per translation unit; NEF_DEFINE_EXACT_SETTER(name) defines the unit's setter.
+static __constant__ int c_nef_exact;
+#define NEF_DEFINE_EXACT_SETTER(name) \
+  extern "C" int name(int on) { return cudaMemcpyToSymbol(nef::c_nef_exact, &on, sizeof(int)) == cudaSuccess ? 0 : 1; }
+
 __device__ __forceinline__ float tf32_rn(float x) {
+  if (c_nef_exact) return x;
   uint32_t u;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
   return __uint_as_float(u);

@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(256) wgrad_simt_kernel(const NefWgradDesc d, l
 
 // ---- weight packing and layout conversion ----------------------------------------------------
 __global__ void pack_weights_kernel(const float* __restrict__ src, float* __restrict__ dst, int groups, int N, int K,
-                                    int taps, long sg, long sn, long sk, long st, int flip) {
+                                    int taps, long sg, long sn, long sk, long st, int flags) {
   const long total = (long)groups * taps * K * N;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     long r = i;
@@ -206,8 +206,10 @@ __global__ void pack_weights_kernel(const float* __restrict__ src, float* __rest
     const int t = r % taps; r /= taps;
     const int g = (int)r;
     const int k = kb * 32 + c * 4 + j;
-    const int ts = flip ? taps - 1 - t : t;
-    dst[i] = tf32_rn(src[g * sg + n * sn + k * sk + ts * st]);
+    const int ts = (flags & 1) ? taps - 1 - t : t;
+    const float wv = src[g * sg + n * sn + k * sk + ts * st];
+    const float hi = tf32_rn(wv);
+    dst[i] = (flags & 2) ? tf32_rn(wv - hi) : hi;
   }
 }
 
@@ -275,12 +277,12 @@ extern "C" int nef_gconv_wgrad_simt(const NefWgradDesc* d, nef_stream_t s) {
 }
 
 extern "C" int nef_pack_weights(const float* src, float* dst, int groups, int N, int K, int taps, int64_t sg,
-                                int64_t sn, int64_t sk, int64_t st, int flip, nef_stream_t s) {
+                                int64_t sn, int64_t sk, int64_t st, int flags, nef_stream_t s) {
   NEF_REQUIRE(K % 32 == 0 && N % 4 == 0, "nef_pack_weights: K %% 32 and N %% 4 required (K=%d N=%d)", K, N);
   const long total = (long)groups * taps * K * N;
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
-  pack_weights_kernel<<<blocks, 256, 0, (cudaStream_t)s>>>(src, dst, groups, N, K, taps, sg, sn, sk, st, flip);
+  pack_weights_kernel<<<blocks, 256, 0, (cudaStream_t)s>>>(src, dst, groups, N, K, taps, sg, sn, sk, st, flags);
   NEF_CHECK_LAUNCH("pack_weights_kernel");
   return 0;
 }
@@ -309,3 +311,5 @@ extern "C" int nef_cbl4_to_ncl(const float* src, float* dst, int B, int C, int L
   NEF_CHECK_LAUNCH("cbl4_to_ncl_kernel");
   return 0;
 }
+
+NEF_DEFINE_EXACT_SETTER(nef_set_exact_simt)

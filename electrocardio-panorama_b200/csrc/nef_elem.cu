@@ -494,7 +494,11 @@ __global__ void __launch_bounds__(256) latent_fwd_kernel(const LatentArgs a) {
         float4 v;
         if ((i & 1) == 0) v = src[li] * 0.25f + src[li + 1] * 0.75f;
         else v = src[li + 1] * 0.75f + src[li + 2] * 0.25f;
-        *a.u0[k3].at(latc, b, 2 * t0 + i) = tf32_rn4(v * qv);
+        v = v * qv;
+        const float4 hi = tf32_rn4(v);
+        *a.u0[k3].at(latc, b, 2 * t0 + i) = hi;
+        *a.u0lo[k3].at(latc, b, 2 * t0 + i) =
+            tf32_rn4(make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w));
       }
     }
     __syncthreads();
@@ -1057,3 +1061,5 @@ extern "C" int nef_sgd_step(float* p, const float* g, float* m, int64_t n, float
   NEF_CHECK_LAUNCH("sgd_kernel");
   return 0;
 }
+
+NEF_DEFINE_EXACT_SETTER(nef_set_exact_elem)

@@ -46,7 +46,8 @@ struct LatentArgs {
   int q_stride;           // floats between segments in q
   int G, c1, c2;
   T4 lat[3];              // unscaled latents (256, L4): all, patient-shuffled, lead-shuffled
-  T4 u0[3];               // upsample2(q * lat) (256, L/2)
+  T4 u0[3];               // upsample2(q * lat) (256, L/2), TF32-rounded
+  T4 u0lo[3];             // TF32 residual of the same (split-precision input of the decoder's first conv)
   int n_lat;              // 3 (train) or 1 (extra views: only lat[0] / u0[0])
   int write_lat;          // 0: lat already built, only (re)build u0 from it with another q
 };

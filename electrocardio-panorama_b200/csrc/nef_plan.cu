@@ -22,6 +22,9 @@ extern "C" void nef_set_error(const char* fmt, ...) {
   va_end(ap);
 }
 extern "C" const char* nef_last_error(void) { return g_err; }
+static long long g_launches = 0;
+extern "C" void nef_count_launch(void) { __atomic_add_fetch(&g_launches, 1, __ATOMIC_RELAXED); }
+extern "C" int64_t nef_launch_count(void) { return (int64_t)__atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
 extern "C" int nef_version(void) { return NEF_ABI_VERSION; }
 
 extern "C" int nef_gconv_fwd_simt(const NefConvDesc* d, nef_stream_t s);
@@ -36,6 +39,14 @@ extern "C" int nef_set_conv_impl(int impl) {
   return 0;
 }
 extern "C" int nef_get_conv_impl(void) { return g_conv_impl; }
+extern "C" int nef_set_exact_simt(int on);
+extern "C" int nef_set_exact_elem(int on);
+extern "C" int nef_set_exact_tc(int on);
+extern "C" int nef_set_exact_fp32(int on) {
+  int rc = nef_set_exact_simt(on) | nef_set_exact_elem(on) | nef_set_exact_tc(on);
+  NEF_REQUIRE(rc == 0, "nef_set_exact_fp32: cudaMemcpyToSymbol failed");
+  return 0;
+}
 
 extern "C" int nef_init(int device) {
   int n = 0;
@@ -159,7 +170,7 @@ struct NefPlan {
   size_t cursor;
   // activations
   T4 s0, eh[3], ey[3], hw, w, h1, z1, xw, hz, z2c, ra, h20, y20, t21, h22, z2o;
-  T4 lat[3], u0[3];
+  T4 lat[3], u0[3], u0lo[3];
   DecBufs dec[3];
   float *s_in, *q, *rq;
   // gradients
@@ -172,6 +183,7 @@ struct NefPlan {
   // weights
   ConvW enc[6], wc[2], z1c[3], z2c1[3], z2a[2], z2b[3], decw[4];
   float *ct_f[2], *ct_d[2];
+  float* dec1_lo;         // TF32 residual of the decoder first conv weights, forward packing
   // saved forward state
   const float* x_in; const float* thetas_in; const float* query_in; const int64_t* rois_in;
   int c1, c2; float drop_p; int bn_training; bool have_fwd;
@@ -217,7 +229,7 @@ static void carve(NefPlan* p, bool dry) {
   p->xw = c.t4(64 * G, p->win.Lw); p->hz = c.t4(C1, p->win.Lw); p->z2c = c.t4(C1, p->win.Lw);
   p->ra = c.t4(896 * G, 16); p->h20 = c.t4(896 * G, 16); p->y20 = c.t4(896 * G, 16);
   p->t21 = c.t4(448 * G, 32); p->h22 = c.t4(896 * G, 32); p->z2o = c.t4(896 * G, 32);
-  for (int k = 0; k < 3; ++k) { p->lat[k] = c.t4(256, L4); p->u0[k] = c.t4(256, L2); }
+  for (int k = 0; k < 3; ++k) { p->lat[k] = c.t4(256, L4); p->u0[k] = c.t4(256, L2); p->u0lo[k] = c.t4(256, L2); }
   for (int k = 0; k < 3; ++k) {
     DecBufs& d = p->dec[k];
     d.c1 = c.t4(128, L2); d.a1 = c.t4(128, L2); d.c2 = c.t4(128, L2); d.u1 = c.t4(128, L);
@@ -268,6 +280,7 @@ static void carve(NefPlan* p, bool dry) {
   carve_convw(c, p->z2b[1], P_Z2B + 1, 7 * G, 128, 128, 3);
   carve_convw(c, p->z2b[2], P_Z2B + 2, 7 * G, 128, 64, 1);
   carve_convw(c, p->decw[0], P_DEC1 + 0, 1, 128, 256, 3);
+  p->dec1_lo = c.f32((size_t)128 * 256 * 3);
   carve_convw(c, p->decw[1], P_DEC1 + 7, 1, 128, 128, 3);
   carve_convw(c, p->decw[2], P_DEC3 + 0, 1, 64, 128, 3);
   carve_convw(c, p->decw[3], P_DEC3 + 7, 1, 64, 64, 3);
@@ -384,6 +397,11 @@ static int pack_dgrad(const ConvW& w, const float* const* P, cudaStream_t s) {
                           w.taps, (int64_t)w.cin_g * w.taps, 1, 1, (nef_stream_t)s);
 }
 
+static int pack_dec1_lo(NefPlan* p, const float* const* P, cudaStream_t s) {
+  const ConvW& w = p->decw[0];
+  return nef_pack_weights(P[w.pidx], p->dec1_lo, 1, 128, 256, 3, 0, 256 * 3, 3, 1, 2, (nef_stream_t)s);
+}
+
 template <class F>
 static int for_all_convw(NefPlan* p, F f) {
   for (int i = 0; i < 6; ++i) RUN(f(p->enc[i]));
@@ -422,7 +440,7 @@ static int block_fwd(const BlockIO& io, float drop_p, uint64_t seed, const float
   return 0;
 }
 
-static int decoder_fwd(NefPlan* p, const float* const* P, int slot, const T4& u0, int training, float* out_user,
+static int decoder_fwd(NefPlan* p, const float* const* P, int slot, const T4& u0, const T4& u0lo, int training, float* out_user,
                        int out_bstride, cudaStream_t s) {
   DecBufs& d = p->dec[slot];
   const int B = p->B;
@@ -435,6 +453,10 @@ static int decoder_fwd(NefPlan* p, const float* const* P, int slot, const T4& u0
     const Lay& l = lay[i];
     CD c(1, l.w->cout_g, l.in);
     c.term(l.in, 0, 0, l.w->cin_g, 3, l.w->pk_f).out(l.c, 0, 0).bias(P[l.pb]);
+    if (i == 0) {  // split precision: x_hi w_hi + x_lo w_hi + x_hi w_lo  (this layer dominates the TF32 error budget)
+      c.term(u0lo, 0, 0, 256, 3, l.w->pk_f);
+      c.term(l.in, 0, 0, 256, 3, p->dec1_lo);
+    }
     if (training) {
       cudaMemsetAsync(d.bn[i].sum, 0, 2 * 128 * sizeof(double), s);  // sum and sq are adjacent
       c.stats(d.bn[i].sum, d.bn[i].sq);
@@ -462,13 +484,13 @@ static int latents_to_decoders(NefPlan* p, const float* const* P, const float* q
   const int B = p->B;
   LatentArgs la;
   la.z1 = p->z1; la.z2o = p->z2o; la.rois = rois; la.G = p->G; la.c1 = p->c1; la.c2 = p->c2;
-  for (int k = 0; k < 3; ++k) { la.lat[k] = p->lat[k]; la.u0[k] = p->u0[k]; }
+  for (int k = 0; k < 3; ++k) { la.lat[k] = p->lat[k]; la.u0[k] = p->u0[k]; la.u0lo[k] = p->u0lo[k]; }
   if (!only_views) {
     RUN(angular_fwd(query_theta, P[P_MLP2_W], P[P_MLP2_B], p->q, B, 256, s));
     la.q = p->q; la.q_stride = 256; la.n_lat = 3; la.write_lat = 1;
     RUN(latent_fwd(la, s));
     float* outs[3] = {out, out_p, out_l};
-    for (int k = 0; k < 3; ++k) RUN(decoder_fwd(p, P, k, p->u0[k], training, outs[k], p->L, s));
+    for (int k = 0; k < 3; ++k) RUN(decoder_fwd(p, P, k, p->u0[k], p->u0lo[k], training, outs[k], p->L, s));
   } else {
     // gen_ecg: build lat[0] only (mean latents); q unused for that -> use rq view 0 below
     la.q = p->rq; la.q_stride = V * 256; la.n_lat = 1; la.write_lat = 1;
@@ -480,7 +502,7 @@ static int latents_to_decoders(NefPlan* p, const float* const* P, const float* q
       la.q = p->rq + (size_t)v * 256; la.q_stride = V * 256; la.n_lat = 1;
       la.write_lat = (only_views && v == 0) ? 1 : 0;
       RUN(latent_fwd(la, s));
-      RUN(decoder_fwd(p, P, 0, p->u0[0], training, rest_out + (size_t)v * p->L, V * p->L, s));
+      RUN(decoder_fwd(p, P, 0, p->u0[0], p->u0lo[0], training, rest_out + (size_t)v * p->L, V * p->L, s));
     }
   }
   return 0;
@@ -498,6 +520,7 @@ extern "C" int nef_forward(NefPlan* p, const NefForwardArgs* a, nef_stream_t sv)
   p->x_in = a->x; p->thetas_in = a->input_thetas; p->query_in = a->query_theta; p->rois_in = a->rois;
 
   RUN(for_all_convw(p, [&](const ConvW& w) { return pack_fwd(w, P, s); }));
+  RUN(pack_dec1_lo(p, P, s));
   for (int t = 0; t < 2; ++t)  // ConvTranspose1d weight (Cin_total, Cout/groups, 2): one 1x1 conv per tap
     RUN(nef_pack_weights(P[P_CT_W] + t, p->ct_f[t], 7 * G, 64, 128, 1, 128LL * 64 * 2, 2, 64 * 2, 0, 0, sv));
 
@@ -557,6 +580,7 @@ extern "C" int nef_gen_ecg(NefPlan* p, const float* const* P, const float* z1, c
   p->have_fwd = false;
   p->c1 = 0; p->c2 = 0;
   for (int i = 0; i < 4; ++i) RUN(pack_fwd(p->decw[i], P, s));
+  RUN(pack_dec1_lo(p, P, s));
   RUN(nef_ncl_to_cbl4(z1, reinterpret_cast<float*>(p->z1.p), p->B, p->C1, p->L4, 0, sv));
   RUN(nef_ncl_to_cbl4(z2, reinterpret_cast<float*>(p->z2o.p), p->B, 896 * p->G, 32, 0, sv));
   return latents_to_decoders(p, P, nullptr, query_theta, rois, NEF_PHASE_TEST, 0, V, nullptr, nullptr, nullptr, out,

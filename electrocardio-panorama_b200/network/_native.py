@@ -26,7 +26,7 @@ class NefConvTerm(C.Structure):
 
 class NefConvDesc(C.Structure):
     _fields_ = [("n_terms", C.c_int32), ("groups", C.c_int32), ("N", C.c_int32), ("round_tf32", C.c_int32),
-                ("term", NefConvTerm * 2), ("rows", C.c_int64), ("Lp", C.c_int32), ("L", C.c_int32),
+                ("term", NefConvTerm * 3), ("rows", C.c_int64), ("Lp", C.c_int32), ("L", C.c_int32),
                 ("y", C.c_void_p), ("y_cstride", C.c_int64), ("y_c4_off", C.c_int32), ("y_c4_gstride", C.c_int32),
                 ("y_Lp", C.c_int32), ("y_lmul", C.c_int32), ("y_ladd", C.c_int32), ("relu", C.c_int32),
                 ("bias", C.c_void_p), ("res", C.c_void_p), ("res_cstride", C.c_int64), ("res_c4_off", C.c_int32),
@@ -65,6 +65,8 @@ SIGNATURES = {
     "nef_init": (C.c_int, [C.c_int]),
     "nef_set_conv_impl": (C.c_int, [C.c_int]),
     "nef_get_conv_impl": (C.c_int, []),
+    "nef_set_exact_fp32": (C.c_int, [C.c_int]),
+    "nef_launch_count": (C.c_int64, []),
     "nef_param_count": (C.c_int, [C.c_int]),
     "nef_param_name": (C.c_char_p, [C.c_int, C.c_int]),
     "nef_param_numel": (C.c_int64, [C.c_int, C.c_int]),

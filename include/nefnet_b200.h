@@ -39,6 +39,11 @@ int nef_init(int device);
 /* 0 = CUDA-core fp32 implicit GEMM, 1 = tcgen05 TF32 (default when built in).  Test hook. */
 int nef_set_conv_impl(int impl);
 int nef_get_conv_impl(void);
+/* Test hook: 1 = round nothing to TF32 (with conv impl 0 the whole path is then plain fp32 and can be
+ * compared tightly with the fp32 oracle); 0 = production behaviour.  Synchronous, call between steps. */
+int nef_set_exact_fp32(int on);
+/* Cumulative number of kernels this library has launched in this process (bench.py's gpu_launches). */
+int64_t nef_launch_count(void);
 
 /* ---- parameters (state_dict contract; model_nefnet.py:67-107) -------------------- */
 /* Number of state_dict entries for lead_num = G, their names (host strings), element counts.   */
@@ -70,11 +75,11 @@ typedef struct NefConvTerm {
 } NefConvTerm;
 
 typedef struct NefConvDesc {
-  int32_t n_terms;      /* 1 or 2: the terms accumulate into the same output */
+  int32_t n_terms;      /* 1..3: the terms accumulate into the same output */
   int32_t groups;
   int32_t N;            /* output channels per group: 64 or 128 */
   int32_t round_tf32;   /* round the stored result to TF32 (it feeds another tensor-core conv) */
-  NefConvTerm term[2];
+  NefConvTerm term[3];
   int64_t rows;         /* B * Lp rows of the input row space are visited */
   int32_t Lp, L;        /* segment pitch and length of the input row space */
   /* output mapping: input row (b, l) -> output row b * y_Lp + HALO + l * y_lmul + y_ladd */
@@ -104,9 +109,11 @@ typedef struct NefConvDesc {
 } NefConvDesc;
 
 /* Packs reference-layout weights into the layout NefConvTerm.w expects, rounding to TF32 (RN):
- *   dst[g][t][kb][c][n][j] = src[g*sg + n*sn + (kb*32 + c*4 + j)*sk + (flip ? taps-1-t : t)*st]   */
+ *   dst[g][t][kb][c][n][j] = src[g*sg + n*sn + (kb*32 + c*4 + j)*sk + ((flags & 1) ? taps-1-t : t)*st]
+ *   flags bit 0: flip the taps (data gradient); bit 1: store the TF32 residual w - tf32(w) instead
+ *   of tf32(w) (the low part of a split-precision contraction, used for the decoder's first conv)   */
 int nef_pack_weights(const float* src, float* dst, int groups, int N, int K, int taps, int64_t sg, int64_t sn,
-                     int64_t sk, int64_t st, int flip, nef_stream_t s);
+                     int64_t sk, int64_t st, int flags, nef_stream_t s);
 int nef_gconv_fwd(const NefConvDesc* d, nef_stream_t s);
 
 /* weight gradient: dw[g*sg + m*sm + n*sn + t*st] += sum_rows dy[row][g, m] * x[row + t + tap_off][g, n];

@@ -1,8 +1,15 @@
 """GPU parity of the CUDA path (through the reference-facing module surface and the C ABI) against
 (1) the golden vectors the unmodified reference produced and (2) the CPU oracle on fresh seeded inputs.
 
-Tolerances: outputs within 1e-3 relative (north star); gradients are compared in relative L2 per
-tensor (the convolutions multiply in TF32, as the reference's own cuDNN path does by default)."""
+Two tiers:
+  * production (tcgen05 TF32 convolutions, activations stored TF32-rounded): synthesized waveforms within
+    1e-3 relative of the fp32 reference (the north-star bar).  Gradients of a ReLU network move by a few
+    percent in L2 between TF32 and fp32 whatever the implementation (ReLU masks within rounding distance
+    of zero flip; measured 2-8 % with a TF32-rounding CPU emulation of the oracle), so they are held to
+    cosine >= 0.99 / relative L2 <= 0.15 here ...
+  * ... and the backward LOGIC is pinned in the exact tier: CUDA-core convolutions with all TF32 rounding
+    switched off (nef_set_exact_fp32) must reproduce the fp32 oracle's gradients to 2e-3 relative L2.
+"""
 import glob
 import os
 import random
@@ -17,8 +24,32 @@ from oracle.make_golden import sample_idx
 pytestmark = pytest.mark.gpu
 
 GOLDEN = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
-OUT_RTOL = 1e-3
-GRAD_REL_L2 = 1e-2
+OUT_RTOL = 1e-3          # north star
+EXACT_OUT_RTOL = 2e-5
+EXACT_GRAD_REL_L2 = 5e-3  # a single ReLU-mask flip at a pre-activation within 1 ulp of 0 costs ~2e-3 (see make_golden.py)
+TF32_GRAD_REL_L2 = 0.15
+TF32_GRAD_COS = 0.99
+
+MODES = {"exact_simt": (0, 1), "tf32_simt": (0, 0), "tf32_tc": (1, 0)}
+
+
+class mode:
+    def __init__(self, name):
+        self.impl, self.exact = MODES[name]
+
+    def __enter__(self):
+        from network import _native as N
+        lib = N.init(0)
+        torch.cuda.synchronize()
+        lib.nef_set_conv_impl(self.impl)
+        N.check(lib.nef_set_exact_fp32(self.exact), "nef_set_exact_fp32")
+
+    def __exit__(self, *a):
+        from network import _native as N
+        lib = N.load()
+        torch.cuda.synchronize()
+        lib.nef_set_conv_impl(1)
+        lib.nef_set_exact_fp32(0)
 
 
 def _model(G, P, dev, train=True, dropout=0.0):
@@ -35,18 +66,34 @@ def _to(inp, dev):
     return {k: v.to(dev) for k, v in inp.items()}
 
 
-def _rel(a, b):
-    return float((a - b).abs().max() / b.abs().max())
+def _grad_check(named, ref_grads, exact, what):
+    worst = (0.0, "")
+    for n, ref in ref_grads.items():
+        if n in O.ZERO_GRAD_PARAMS:  # exactly zero in exact arithmetic; both sides hold rounding noise
+            assert bool(torch.isfinite(named[n].grad).all()), n
+            continue
+        got = named[n].grad.detach().cpu().double()
+        ref = ref.double()
+        err = float((got - ref).norm() / (ref.norm() + 1e-30))
+        cos = float((got * ref).sum() / (got.norm() * ref.norm() + 1e-30))
+        if err > worst[0]:
+            worst = (err, n)
+        if exact:
+            assert err < EXACT_GRAD_REL_L2, (what, n, err)
+        else:
+            assert err < TF32_GRAD_REL_L2 and cos > TF32_GRAD_COS, (what, n, err, cos)
+    print(what, "worst grad rel-L2 %.3e (%s)" % worst)
 
 
-@pytest.mark.parametrize("impl", [0, 1])
+@pytest.mark.parametrize("mode_name", list(MODES))
 @pytest.mark.parametrize("name", GOLDEN)
-def test_golden(name, impl, golden_dir, cfg):
-    from network import _native as N
+def test_golden(name, mode_name, golden_dir, cfg):
+    """Vectors produced by the unmodified reference (oracle/make_golden.py)."""
     from network import build_loss
     dev = torch.device("cuda:0")
-    N.init(0).nef_set_conv_impl(impl)
-    try:
+    exact = MODES[mode_name][1] == 1
+    out_rtol = EXACT_OUT_RTOL if exact else OUT_RTOL
+    with mode(mode_name):
         g = np.load(os.path.join(golden_dir, name + ".npz"))
         B, G, L, seed, V = (int(g[k]) for k in ("B", "G", "L", "seed", "V"))
         P = O.make_params(G, seed)
@@ -66,23 +113,26 @@ def test_golden(name, impl, golden_dir, cfg):
             random.seed(seed)
             z1, z2 = m(inp["x"], inp["input_thetas"], inp["query_theta"], inp["rois"], phase="gen")
             gen = m.gen_ecg(z1, z2, inp["rest_theta"], inp["rois"])
-            np.testing.assert_allclose(gen.cpu().numpy(), g["gen_ecg"], rtol=OUT_RTOL, atol=0)
-            zz1 = z1.cpu().flatten()[sample_idx(z1.numel(), 256)].numpy()
-            zz2 = z2.cpu().flatten()[sample_idx(z2.numel(), 256)].numpy()
-            np.testing.assert_allclose(zz1, g["gen_z1_sample"], rtol=5e-3, atol=5e-3 * float(np.abs(g["gen_z1_sample"]).max()))
-            np.testing.assert_allclose(zz2, g["gen_z2_sample"], rtol=5e-3, atol=5e-3 * float(np.abs(g["gen_z2_sample"]).max()))
+            np.testing.assert_allclose(gen.cpu().numpy(), g["gen_ecg"], rtol=out_rtol, atol=0)
+            ztol = 2e-5 if exact else 5e-3
+            for z, key in ((z1, "gen_z1_sample"), (z2, "gen_z2_sample")):
+                zz = z.cpu().flatten()[sample_idx(z.numel(), 256)].numpy()
+                np.testing.assert_allclose(zz, g[key], rtol=ztol, atol=ztol * float(np.abs(g[key]).max()))
         for i, o in enumerate(outs):
-            np.testing.assert_allclose(o.cpu().numpy(), g[f"out{i}"], rtol=OUT_RTOL, atol=0)
-        np.testing.assert_allclose(np.array([float(v) for v in losses]), g["losses"], rtol=2e-3, atol=1e-6)
+            np.testing.assert_allclose(o.detach().cpu().numpy(), g[f"out{i}"], rtol=out_rtol, atol=0)
+        np.testing.assert_allclose(np.array([float(v.detach()) for v in losses]), g["losses"],
+                                   rtol=1e-5 if exact else 2e-3, atol=1e-5)  # atol: BN statistics are summed
+        # with atomics, so two decoder calls on identical latents (G = 1) agree to ~1e-6, not bit-exactly
         sd = m.state_dict()
         for k in g.files:
             if k.startswith("bn/"):
-                np.testing.assert_allclose(sd[k[3:]].cpu().numpy(), g[k], rtol=2e-3, atol=2e-4)
+                np.testing.assert_allclose(sd[k[3:]].cpu().numpy(), g[k], rtol=1e-4 if exact else 2e-3,
+                                           atol=1e-5 if exact else 2e-4)
         if train:
+            assert int(sd["decoder.1.double_conv.1.num_batches_tracked"]) == 3
             named = dict(m.named_parameters())
             for n in O.UNUSED_PARAMS:
                 assert named[n].grad is None
-            worst = 0.0
             for n in O.live_param_names(G):
                 gr = named[n].grad
                 assert gr is not None, n
@@ -93,57 +143,89 @@ def test_golden(name, impl, golden_dir, cfg):
                 norm_ref = float(g["gn/" + n][0])
                 got = gr.flatten()[sample_idx(gr.numel())].numpy()
                 ref = g["gs/" + n]
-                err = float(np.linalg.norm(got - ref) / (np.linalg.norm(ref) + 1e-30))
                 nerr = abs(float(gr.double().norm()) - norm_ref) / norm_ref
-                worst = max(worst, err, nerr)
-                assert err < 3 * GRAD_REL_L2 and nerr < GRAD_REL_L2, (n, err, nerr)
-            print(name, "impl", impl, "worst grad err", worst)
-    finally:
-        N.load().nef_set_conv_impl(1)
+                if exact:  # same bound the oracle itself is held to against these vectors
+                    np.testing.assert_allclose(got, ref, rtol=5e-3, atol=5e-3 * norm_ref / np.sqrt(gr.numel()) + 1e-9)
+                    assert nerr < 1e-3, (n, nerr)
+                else:      # L1 loss: sign(out - target) flips make the comparison statistical
+                    assert nerr < 0.1, (n, nerr)
+                    cos = float(np.dot(got, ref) / (np.linalg.norm(got) * np.linalg.norm(ref) + 1e-30))
+                    assert cos > 0.9, (n, cos)
 
 
-@pytest.mark.parametrize("B,G,L,seed", [(4, 3, 512, 11), (2, 12, 1000, 12), (5, 2, 264, 13)])
-def test_oracle_fresh_inputs(B, G, L, seed, cfg):
-    """Fresh seeded inputs, full forward/backward against the CPU oracle (same weights)."""
-    from network import build_loss
+@pytest.mark.parametrize("mode_name", list(MODES))
+@pytest.mark.parametrize("B,G,L,seed,ragged", [(4, 3, 512, 11, False), (2, 12, 1000, 12, False), (5, 2, 264, 13, True),
+                                               (3, 1, 16, 14, False)])
+def test_oracle_fixed_upstream(B, G, L, seed, ragged, mode_name):
+    """Fresh seeded inputs; backward driven by fixed upstream gradients (no loss discontinuity)."""
     dev = torch.device("cuda:0")
+    exact = MODES[mode_name][1] == 1
     P = O.make_params(G, seed)
-    inp = O.make_inputs(B, G, L, seed)
-    m = _model(G, P, dev)
+    if L == 16:
+        inp = O.make_inputs(B, G, 64, seed)
+        inp = {k: (v[..., :16].contiguous() if k in ("x", "target") else v) for k, v in inp.items()}
+        inp["rois"] = torch.tensor([[0, 4], [4, 4], [4, 8], [8, 8], [8, 12], [12, 12], [12, 16]]).repeat(B, 1, 1)
+    else:
+        inp = O.make_inputs(B, G, L, seed, ragged_rois=ragged)
     random.seed(seed)
     c1, c2 = random.randint(0, G - 1), random.randint(0, G - 1)
-    random.seed(seed)
-    d = _to(inp, dev)
-    outs = m(d["x"], d["input_thetas"], d["query_theta"], d["rois"], phase="train")
-    losses = build_loss(cfg)(outs[0], outs[1], outs[2], d["target"], cfg)
-    losses[0].backward()
+    gen = torch.Generator().manual_seed(seed)
+    ups = [torch.randn(B, 1, inp["x"].shape[-1], generator=gen) for _ in range(3)]
+    with mode(mode_name):
+        m = _model(G, P, dev)
+        random.seed(seed)
+        d = _to(inp, dev)
+        outs = m(d["x"], d["input_thetas"], d["query_theta"], d["rois"], phase="train")
+        torch.autograd.backward(outs, [u.to(dev) for u in ups])
+        sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+        named = dict(m.named_parameters())
     Po = {k: v.clone() for k, v in P.items()}
     for n in O.live_param_names(G):
         Po[n].requires_grad_(True)
     stats = {k: v for k, v in Po.items() if "running_" in k or "num_batches" in k}
     oo = O.forward(Po, inp["x"], inp["input_thetas"], inp["query_theta"], inp["rois"], phase="train",
                    lead_choice=(c1, c2), stats_out=stats)
-    ol = O.standin_loss(*oo, inp["target"])
-    ol[0].backward()
+    torch.autograd.backward(oo, ups)
     for a, b in zip(outs, oo):
-        np.testing.assert_allclose(a.cpu().numpy(), b.detach().numpy(), rtol=OUT_RTOL, atol=0)
-    assert abs(float(losses[0]) - float(ol[0])) < 2e-3 * abs(float(ol[0]))
-    named = dict(m.named_parameters())
-    for n in O.live_param_names(G):
-        if n in O.ZERO_GRAD_PARAMS:
-            continue
-        ref = Po[n].grad
-        got = named[n].grad.cpu()
-        err = float((got - ref).norm() / (ref.norm() + 1e-30))
-        assert err < GRAD_REL_L2, (n, err)
-    sd = m.state_dict()
+        np.testing.assert_allclose(a.detach().cpu().numpy(), b.detach().numpy(), rtol=EXACT_OUT_RTOL if exact else OUT_RTOL,
+                                   atol=0)
+    _grad_check(named, {n: Po[n].grad for n in O.live_param_names(G)}, exact, "%s B%d G%d L%d" % (mode_name, B, G, L))
     for k, v in stats.items():
-        np.testing.assert_allclose(sd[k].cpu().numpy(), v.numpy(), rtol=2e-3, atol=2e-4)
+        np.testing.assert_allclose(sd[k].numpy(), v.numpy(), rtol=1e-4 if exact else 2e-3, atol=1e-5 if exact else 2e-4)
+
+
+def test_standin_loss_kernels(cfg):
+    """nef_loss_fwd / nef_loss_bwd against torch on identical inputs (exact op-level check)."""
+    from network import losswrapper
+    dev = torch.device("cuda:0")
+    gen = torch.Generator().manual_seed(3)
+    for reg in ("l1_loss", "l2_loss"):
+        class c2(cfg):
+            class SOLVER:
+                reg_loss = reg
+                loss_using = [1, 2, 3]
+                loss_factor = [0.5, 0.25, 1.5]
+        ts = [torch.rand(5, 1, 333, generator=gen) for _ in range(4)]
+        a = [t.clone().to(dev).requires_grad_(i < 3) for i, t in enumerate(ts)]
+        b = [t.clone().requires_grad_(i < 3) for i, t in enumerate(ts)]
+        got = losswrapper(a[0], a[1], a[2], a[3], c2)
+        ref = O.standin_loss(b[0], b[1], b[2], b[3], factor=(0.5, 0.25, 1.5), reg_loss="l1_loss" if reg == "l1_loss" else "mse")
+        np.testing.assert_allclose([float(v.detach()) for v in got], [float(v.detach()) for v in ref], rtol=2e-6)
+        got[0].backward()
+        ref[0].backward()
+        for x, y in zip(a[:3], b[:3]):
+            np.testing.assert_allclose(x.grad.cpu().numpy(), y.grad.numpy(), rtol=1e-6, atol=1e-12)
+        rest, view = torch.rand(5, 4, 333, generator=gen), torch.rand(5, 4, 333, generator=gen)
+        got5 = losswrapper(a[0], a[1], a[2], a[3], c2, rest.to(dev), view.to(dev))
+        ref5 = O.standin_loss(b[0], b[1], b[2], b[3], factor=(0.5, 0.25, 1.5),
+                              reg_loss="l1_loss" if reg == "l1_loss" else "mse", rest_out=rest, rest_view=view)
+        assert len(got5) == 5
+        np.testing.assert_allclose(float(got5[4]), float(ref5[4]), rtol=2e-6)
 
 
 def test_dropout_statistics():
-    """Dropout on: ~20% of the block activations are zeroed and survivors scaled; outputs stay finite and
-    two different steps draw different masks."""
+    """Dropout on (train mode): masks differ between steps, the kept fraction of the hidden activations is
+    ~0.8 in effect (outputs move), eval mode is deterministic."""
     dev = torch.device("cuda:0")
     G, B, L = 2, 3, 256
     P = O.make_params(G, 5)
@@ -157,8 +239,27 @@ def test_dropout_statistics():
     with torch.no_grad():
         c = m(d["x"], d["input_thetas"], d["query_theta"], d["rois"], phase="train")[0]
         e = m(d["x"], d["input_thetas"], d["query_theta"], d["rois"], phase="train")[0]
-    # eval: no dropout; the two lead draws differ but out (mean latents) does not depend on them
+    # eval: no dropout; the lead draws differ but `out` (mean latents) does not depend on them
     assert float((c - e).abs().max()) == 0.0
+
+
+def test_sgd_step_matches_torch():
+    from network import _native as N
+    dev = torch.device("cuda:0")
+    lib = N.init(0)
+    gen = torch.Generator().manual_seed(1)
+    n = 100003
+    p, g = torch.randn(n, generator=gen), torch.randn(n, generator=gen)
+    ref_p = torch.nn.Parameter(p.clone())
+    opt = torch.optim.SGD([ref_p], lr=0.1, momentum=0.9)
+    pd, md = p.to(dev), torch.zeros(n, device=dev)
+    for it in range(3):
+        gi = g * (it + 1)
+        ref_p.grad = gi.clone()
+        opt.step()
+        gd = gi.to(dev)
+        N.check(lib.nef_sgd_step(N.ptr(pd), N.ptr(gd), N.ptr(md), n, 0.1, 0.9, 1.0, N.stream_ptr()), "nef_sgd_step")
+    np.testing.assert_allclose(pd.cpu().numpy(), ref_p.detach().numpy(), rtol=1e-5, atol=1e-6)
 
 
 def test_cpu_input_raises():
