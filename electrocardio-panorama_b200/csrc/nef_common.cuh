@@ -12,7 +12,7 @@
 #include <stdint.h>
 
 #define NEF_HALO 3
-#define NEF_GUARD_ROWS 272   // readable rows after (and before) every CBL4 tensor: tiles may overrun
+#define NEF_GUARD_ROWS 528   // readable rows after (and before) every CBL4 tensor: tiles may overrun
 #define NEF_NROI 7
 #define NEF_ROI_SIZE 16
 

@@ -13,7 +13,7 @@ constexpr int ST_XROWS = ST_ROWS + 6;
 __global__ void __launch_bounds__(256, 2) conv_simt_kernel(const NefConvDesc d) {
   __shared__ float4 Xs[8][ST_XROWS];
   __shared__ float4 Ws[8][ST_N];
-  __shared__ float s_stat[2][ST_N];
+  __shared__ float s_stat[2][4][ST_N];  // [sum | sq][row quarter][channel]: one writer each (deterministic)
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int ntiles = d.N / ST_N;
@@ -68,10 +68,6 @@ __global__ void __launch_bounds__(256, 2) conv_simt_kernel(const NefConvDesc d) 
 
   // ---- epilogue
   const bool want_stats = d.stat_sum != nullptr;
-  if (want_stats) {
-    for (int i = tid; i < 2 * ST_N; i += 256) (&s_stat[0][0])[i] = 0.f;
-  }
-  __syncthreads();
   const EpiRow er = epi_row(d, r0 + rw);
   // is the whole warp inside one segment?  (for the bscale_grad reduction)
   const int b0 = __shfl_sync(0xffffffffu, er.b, 0);
@@ -87,8 +83,8 @@ __global__ void __launch_bounds__(256, 2) conv_simt_kernel(const NefConvDesc d) 
         float v = er.valid ? f4get(pre, j) : 0.f;
         float s1 = warp_sum(v), s2 = warp_sum(v * v);
         if (lane == 0) {
-          atomicAdd(&s_stat[0][half * 32 + i * 4 + j], s1);
-          atomicAdd(&s_stat[1][half * 32 + i * 4 + j], s2);
+          s_stat[0][warp & 3][half * 32 + i * 4 + j] = s1;
+          s_stat[1][warp & 3][half * 32 + i * 4 + j] = s2;
         }
       }
     }
@@ -110,9 +106,9 @@ __global__ void __launch_bounds__(256, 2) conv_simt_kernel(const NefConvDesc d) 
   if (want_stats) {
     __syncthreads();
     for (int i = tid; i < ST_N; i += 256) {
-      const long ch = (long)g * d.N + nt * ST_N + i;
-      atomicAdd(d.stat_sum + ch, (double)s_stat[0][i]);
-      atomicAdd(d.stat_sq + ch, (double)s_stat[1][i]);
+      const long o = (long)blockIdx.x * ((long)d.groups * d.N) + (long)g * d.N + nt * ST_N + i;
+      d.stat_sum[o] = (s_stat[0][0][i] + s_stat[0][1][i]) + (s_stat[0][2][i] + s_stat[0][3][i]);
+      d.stat_sq[o] = (s_stat[1][0][i] + s_stat[1][1][i]) + (s_stat[1][2][i] + s_stat[1][3][i]);
     }
   }
 }
@@ -122,7 +118,7 @@ constexpr int WG_TR = 64;        // rows per smem stage
 constexpr int WG_XS = WG_TR + 3; // odd chunk pitch -> conflict-free
 
 template <int TP>
-__global__ void __launch_bounds__(256) wgrad_simt_kernel(const NefWgradDesc d, long rows_per_split) {
+__global__ void __launch_bounds__(256) wgrad_simt_kernel(const NefWgradDesc d, long rows_per_split, long row0) {
   __shared__ float4 Ys[16][WG_TR];
   __shared__ float4 Xs[16][WG_XS];
   const int tid = threadIdx.x;
@@ -134,7 +130,7 @@ __global__ void __launch_bounds__(256) wgrad_simt_kernel(const NefWgradDesc d, l
   const int g = idx;
   const int tap_base = blockIdx.z * 4;
   const int ntap = min(TP, d.taps - tap_base);
-  const long rbeg = (long)blockIdx.x * rows_per_split;
+  const long rbeg = row0 + (long)blockIdx.x * rows_per_split;
   const long rend = min(d.rows, rbeg + rows_per_split);
 
   float acc[TP][4][4];
@@ -254,27 +250,31 @@ extern "C" int nef_gconv_fwd_simt(const NefConvDesc* d, nef_stream_t s) {
   return 0;
 }
 
-extern "C" int nef_gconv_wgrad_simt(const NefWgradDesc* d, nef_stream_t s) {
+// weight gradient over rows [row0, d->rows)
+extern "C" int nef_gconv_wgrad_simt_range(const NefWgradDesc* d, long row0, nef_stream_t s) {
+  const long nrows = d->rows - row0;
+  if (nrows <= 0) return 0;
   const int passes = (d->taps + 3) / 4;
   const int tiles = d->groups * (d->cout_g / 64) * (d->cin_g / 64);
   long splits = (148L * 4 + (long)tiles * passes - 1) / ((long)tiles * passes);
-  const long max_splits = (d->rows + WG_TR - 1) / WG_TR;
+  const long max_splits = (nrows + WG_TR - 1) / WG_TR;
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
-  long rps = (d->rows + splits - 1) / splits;
+  long rps = (nrows + splits - 1) / splits;
   rps = (rps + WG_TR - 1) / WG_TR * WG_TR;
-  splits = (d->rows + rps - 1) / rps;
+  splits = (nrows + rps - 1) / rps;
   dim3 grid((unsigned)splits, (unsigned)tiles, (unsigned)passes);
   const int tp = d->taps >= 4 ? 4 : d->taps;
   switch (tp) {
-    case 1: wgrad_simt_kernel<1><<<grid, 256, 0, (cudaStream_t)s>>>(*d, rps); break;
-    case 2: wgrad_simt_kernel<2><<<grid, 256, 0, (cudaStream_t)s>>>(*d, rps); break;
-    case 3: wgrad_simt_kernel<3><<<grid, 256, 0, (cudaStream_t)s>>>(*d, rps); break;
-    default: wgrad_simt_kernel<4><<<grid, 256, 0, (cudaStream_t)s>>>(*d, rps); break;
+    case 1: wgrad_simt_kernel<1><<<grid, 256, 0, (cudaStream_t)s>>>(*d, rps, row0); break;
+    case 2: wgrad_simt_kernel<2><<<grid, 256, 0, (cudaStream_t)s>>>(*d, rps, row0); break;
+    case 3: wgrad_simt_kernel<3><<<grid, 256, 0, (cudaStream_t)s>>>(*d, rps, row0); break;
+    default: wgrad_simt_kernel<4><<<grid, 256, 0, (cudaStream_t)s>>>(*d, rps, row0); break;
   }
   NEF_CHECK_LAUNCH("wgrad_simt_kernel");
   return 0;
 }
+extern "C" int nef_gconv_wgrad_simt(const NefWgradDesc* d, nef_stream_t s) { return nef_gconv_wgrad_simt_range(d, 0, s); }
 
 extern "C" int nef_pack_weights(const float* src, float* dst, int groups, int N, int K, int taps, int64_t sg,
                                 int64_t sn, int64_t sk, int64_t st, int flags, nef_stream_t s) {

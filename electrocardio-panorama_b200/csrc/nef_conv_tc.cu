@@ -1,9 +1,581 @@
-// placeholder: tcgen05 path not built yet
+// tcgen05 (5th-generation tensor core) implementation of the grouped implicit-GEMM convolution, its data
+// gradient (same kernel, flipped / transposed packed weights) and its weight gradient, for sm_100a.
+//
+//   * TF32 operands (fp32 storage, pre-rounded to TF32 by the producing kernel), fp32 accumulation in TMEM.
+//   * Operands are staged global -> shared with 1-D bulk async copies (cp.async.bulk, the TMA engine's
+//     linear mode) completing on mbarriers: a CBL4 tile is one contiguous run of 16-byte rows per 4-channel
+//     chunk, so no tensor map is needed, and that run IS a tcgen05 no-swizzle core-matrix column
+//     (8 rows x 16 B = 128 contiguous bytes).  A k-tap convolution issues the same staged tile k times with
+//     the descriptor start address advanced by 16 B per tap -- no im2col, no per-tap reload.
+//   * Warp-specialised: warp 0 = copy producer, warp 1 = TMEM owner + single-thread MMA issuer,
+//     warps 2..5 = epilogue (tcgen05.ld -> fused bias / residual / ReLU / dropout / angular scale /
+//     BatchNorm partial statistics -> coalesced float4 stores).
+//
+// forward / dgrad :  D[128 rows x N] += X[128 rows x 32 ch](shifted by tap) . W_tap[N x 32 ch]^T   (both K-major)
+//                    MT row tiles of 128 share every weight stage (weights come from L2 once per MT*128 rows)
+// wgrad           :  D_tap[cout x cin] += dY[rows x cout]^T . X[rows (+tap) x cin]                  (both MN-major)
+#include <cstdlib>
 #include "nef_conv.cuh"
+
 extern "C" int nef_gconv_fwd_simt(const NefConvDesc* d, nef_stream_t s);
-extern "C" int nef_gconv_wgrad_simt(const NefWgradDesc* d, nef_stream_t s);
-extern "C" int nef_gconv_fwd_tc(const NefConvDesc* d, nef_stream_t s) { return nef_gconv_fwd_simt(d, s); }
-extern "C" int nef_gconv_wgrad_tc(const NefWgradDesc* d, nef_stream_t s) { return nef_gconv_wgrad_simt(d, s); }
-extern "C" int nef_tc_init(void) { return 0; }
+extern "C" int nef_gconv_wgrad_simt_range(const NefWgradDesc* d, long row0, nef_stream_t s);
+
+namespace nef {
+namespace tc {
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// global -> shared bulk copy (bytes % 16 == 0, both addresses 16-byte aligned), completes on `bar`
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// arrives on `bar` when all tcgen05.mma issued so far by this thread have completed
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem] . B[smem]^T, TF32 inputs, fp32 accumulate
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread (thread = lane)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Shared-memory matrix descriptor, SWIZZLE_NONE ("interleave") canonical layouts, 16-byte units:
+//   K-major  (K = channels):  core matrix = 8 rows x 16 B;  SBO = next 8 rows,        LBO = next 4-channel chunk
+//   MN-major (K = rows)    :  core matrix = 8 rows x 16 B;  SBO = next 4-channel chunk, LBO = next 8 rows
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);
+}
+// Instruction descriptor: fp32 accumulate, TF32 x TF32, M x N
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward / data-gradient kernel
+// ---------------------------------------------------------------------------------------------
+constexpr int FW_THREADS = 192;
+constexpr int FW_XST = 2;  // activation stages (one per 32-channel block)
+constexpr int FW_WBYTES = 8 * 128 * 16;  // one weight stage: 32 input channels x up to 128 outputs x one tap
+
+template <int MT>
+struct FwSmem {
+  static constexpr int XROWS = MT * 128 + 8;          // rows per chunk in a stage (taps - 1 <= 6 extra)
+  static constexpr int XPITCH = XROWS * 16;           // bytes between channel chunks
+  static constexpr int XBYTES = 8 * XPITCH;           // one activation stage
+  static constexpr int WST_FIT = (227 * 1024 - 6144 - FW_XST * XBYTES) / FW_WBYTES;
+  static constexpr int WST = WST_FIT > 6 ? 6 : WST_FIT;  // weight stages
+  static constexpr int BAR_OFF = FW_XST * XBYTES + WST * FW_WBYTES;
+  static constexpr int STAT_OFF = BAR_OFF + 256;
+  static constexpr int TOTAL = STAT_OFF + 4 * 2 * 128 * 4 + 128;
+};
+
+template <int MT>
+__global__ void __launch_bounds__(FW_THREADS, 1) conv_tc_kernel(const __grid_constant__ NefConvDesc d) {
+  using S = FwSmem<MT>;
+  extern __shared__ __align__(128) uint8_t smem[];
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t xs0 = sbase, ws0 = sbase + FW_XST * S::XBYTES, bar0 = sbase + S::BAR_OFF;
+  // barriers (8 bytes each): full_x[2], empty_x[2], full_w[WST], empty_w[WST], acc_full ; then the TMEM base
+  auto full_x = [&](int i) { return bar0 + 8 * i; };
+  auto empty_x = [&](int i) { return bar0 + 8 * (FW_XST + i); };
+  auto full_w = [&](int i) { return bar0 + 8 * (2 * FW_XST + i); };
+  auto empty_w = [&](int i) { return bar0 + 8 * (2 * FW_XST + S::WST + i); };
+  const uint32_t acc_full = bar0 + 8 * (2 * FW_XST + 2 * S::WST);
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + S::BAR_OFF + 8 * (2 * FW_XST + 2 * S::WST + 1));
+  float* s_stat = reinterpret_cast<float*>(smem + S::STAT_OFF);  // [4 quarters][2][128]
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = blockIdx.y;
+  const long r0 = (long)blockIdx.x * (MT * 128);
+  const int N = d.N;
+  constexpr uint32_t TM_COLS = MT * 128 <= 32 ? 32 : (MT * 128 <= 64 ? 64 : (MT * 128 <= 128 ? 128 : (MT * 128 <= 256 ? 256 : 512)));
+
+  if (tid == 0) {
+    for (int i = 0; i < FW_XST; ++i) { mbar_init(full_x(i), 1); mbar_init(empty_x(i), 1); }
+    for (int i = 0; i < S::WST; ++i) { mbar_init(full_w(i), 1); mbar_init(empty_w(i), 1); }
+    mbar_init(acc_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32((const void*)tmem_slot), TM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== copy producer =====
+    if (lane == 0) {
+      int xs = 0, xph = 0, wst = 0, wph = 0;
+      for (int ti = 0; ti < d.n_terms; ++ti) {
+        const NefConvTerm& t = d.term[ti];
+        const int nkb = t.cin_g >> 5;
+        const uint32_t xbytes = (uint32_t)(MT * 128 + t.taps - 1) * 16;
+        const uint32_t wbytes = (uint32_t)(8 * N * 16);
+        const float4* xg = reinterpret_cast<const float4*>(t.x) + (r0 + t.tap_off);
+        const float4* wg = reinterpret_cast<const float4*>(t.w);
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(empty_x(xs), xph ^ 1);
+          mbar_expect_tx(full_x(xs), 8 * xbytes);
+          const long chunk0 = t.x_c4_off + (long)g * t.x_c4_gstride + kb * 8;
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            bulk_g2s(xs0 + xs * S::XBYTES + c * S::XPITCH, xg + (chunk0 + c) * t.x_cstride, xbytes, full_x(xs));
+          if (++xs == FW_XST) { xs = 0; xph ^= 1; }
+          for (int tp = 0; tp < t.taps; ++tp) {
+            mbar_wait(empty_w(wst), wph ^ 1);
+            mbar_expect_tx(full_w(wst), wbytes);
+            bulk_g2s(ws0 + wst * FW_WBYTES, wg + ((((long)g * t.taps + tp) * nkb + kb) * 8) * N, wbytes, full_w(wst));
+            if (++wst == S::WST) { wst = 0; wph ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (one thread) =====
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(128, N, 0, 0);
+      int xs = 0, xph = 0, wst = 0, wph = 0;
+      uint32_t accum = 0;
+      for (int ti = 0; ti < d.n_terms; ++ti) {
+        const NefConvTerm& t = d.term[ti];
+        const int nkb = t.cin_g >> 5;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(full_x(xs), xph);
+          for (int tp = 0; tp < t.taps; ++tp) {
+            mbar_wait(full_w(wst), wph);
+            tc_fence_after();
+            const uint32_t xa = xs0 + xs * S::XBYTES + tp * 16;
+            const uint32_t wa = ws0 + wst * FW_WBYTES;
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+              for (int k8 = 0; k8 < 4; ++k8) {
+                const uint64_t ad = make_desc(xa + (2 * k8) * S::XPITCH + mt * 128 * 16, S::XPITCH, 128);
+                const uint64_t bd = make_desc(wa + (2 * k8) * N * 16, N * 16, 128);
+                mma_tf32(tmem + mt * N, ad, bd, idesc, accum | (uint32_t)k8);
+              }
+            }
+            accum = 1;
+            tc_commit(empty_w(wst));
+            if (++wst == S::WST) { wst = 0; wph ^= 1; }
+          }
+          tc_commit(empty_x(xs));
+          if (++xs == FW_XST) { xs = 0; xph ^= 1; }
+        }
+      }
+      tc_commit(acc_full);
+    }
+  } else {
+    // ===== epilogue: warps 2..5 own TMEM lanes 32 * (warp % 4) .. + 31 =====
+    const int q = warp & 3;
+    const bool want_stats = d.stat_sum != nullptr;
+    const long ctot = (long)d.groups * N;
+    const long n_rec = (d.rows + 127) / 128;
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    for (int mt = 0; mt < MT; ++mt) {
+      const long row = r0 + mt * 128 + q * 32 + lane;
+      const EpiRow er = epi_row(d, row);
+      const int b0 = __shfl_sync(0xffffffffu, er.b, 0);
+      const bool uniform_b = __all_sync(0xffffffffu, er.b == b0);
+      for (int cg = 0; cg < N / 32; ++cg) {
+        uint32_t v[32];
+        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * N + cg * 32), v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int n4 = cg * 8 + i;
+          float4 acc = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]),
+                                   __uint_as_float(v[4 * i + 3]));
+          float4 pre = f4zero(), bsg = f4zero();
+          if (er.valid) epi_apply_store(d, er, g, n4, acc, &pre, &bsg);
+          if (want_stats) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float pv = er.valid ? f4get(pre, j) : 0.f;
+              const float s1 = warp_sum(pv), s2 = warp_sum(pv * pv);
+              if (lane == 0) {
+                s_stat[(q * 2 + 0) * 128 + n4 * 4 + j] = s1;
+                s_stat[(q * 2 + 1) * 128 + n4 * 4 + j] = s2;
+              }
+            }
+          }
+          if (d.bscale_grad) {
+            const long cbase = (long)g * N + n4 * 4;
+            if (uniform_b) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float s1 = warp_sum(er.valid ? f4get(bsg, j) : 0.f);
+                if (lane == 0 && s1 != 0.f) atomicAdd(d.bscale_grad + (long)b0 * ctot + cbase + j, s1);
+              }
+            } else if (er.valid) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) atomicAdd(d.bscale_grad + (long)er.b * ctot + cbase + j, f4get(bsg, j));
+            }
+          }
+        }
+      }
+      if (want_stats) {
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const int et = tid - 64;  // 0..127
+        const long rec = r0 / 128 + mt;
+        if (et < N && rec < n_rec) {
+          const long o = rec * ctot + (long)g * N + et;
+          d.stat_sum[o] = (s_stat[0 * 128 + et] + s_stat[2 * 128 + et]) + (s_stat[4 * 128 + et] + s_stat[6 * 128 + et]);
+          d.stat_sq[o] = (s_stat[1 * 128 + et] + s_stat[3 * 128 + et]) + (s_stat[5 * 128 + et] + s_stat[7 * 128 + et]);
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, TM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// weight-gradient kernel
+//
+// The contraction runs over rows, so both operands would be "MN-major" in the CBL4 layout -- and
+// tcgen05.mma kind::tf32 returns zeros for MN-major operands on this part (tools/probe_umma.cu,
+// profiles/r01_umma_tf32_mn_major_probe.txt; 16-bit kinds transpose fine, 32-bit ones do not).  The kernel
+// therefore re-tiles each staged CBL4 tile in shared memory into K-major core matrices with the four
+// epilogue warps (idle during the main loop) -- a register 4x4 transpose per (chunk, unit):
+//     unit a of a 32-row stage = rows (a, a+8, a+16, a+24) of one channel = one 16-byte K group
+// Because a K group strides over the stage instead of packing 4 adjacent rows, a tap shift of t rows is a
+// shift of t UNITS (16 bytes * plane pitch), so one transposed copy of x serves every tap: the descriptor
+// start address advances by one unit plane per tap, exactly as the forward kernel advances by one row.
+//     D_tap[cout x cin] += dY^T[cout x (a,b)] . X^T[cin x (a + tap, b)]
+// ---------------------------------------------------------------------------------------------
+constexpr int WG_THREADS = 192;
+constexpr int WG_KR = 32;                        // rows (= contraction length) per stage
+constexpr int WG_S = WG_KR / 4;                  // units per stage; unit a = rows a + WG_S * b
+constexpr int WG_YPITCH = WG_KR * 16;            // raw tiles: bytes between channel chunks
+constexpr int WG_XROWS = WG_KR + 8;
+constexpr int WG_XPITCH = WG_XROWS * 16;
+constexpr int WG_RAW = 32 * WG_YPITCH + 32 * WG_XPITCH;   // one raw stage (128 + 128 channels)
+constexpr int WG_NRAW = 3;
+constexpr int WG_LBO = 128 * 16 + 16;            // transposed tiles: bytes between unit planes (+16: conflict-free stores)
+constexpr int WG_TY = WG_S * WG_LBO;             // dY^T: units [0, 8)
+constexpr int WG_XUNITS = WG_S + 3;              // X^T: units [0, 8 + taps_per_pass - 1)
+constexpr int WG_TR = WG_TY + WG_XUNITS * WG_LBO;
+constexpr int WG_NTR = 2;
+constexpr int WG_BAR_OFF = WG_NRAW * WG_RAW + WG_NTR * WG_TR;
+constexpr int WG_TOTAL = WG_BAR_OFF + 128;
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+// grid: x = pass (taps [4*pass, 4*pass + 4)), y = row split, z = (group, cin tile)
+__global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_constant__ NefWgradDesc d, int NT, long rows_per_split,
+                                                                 long rows_main) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t tr0 = sbase + WG_NRAW * WG_RAW;
+  const uint32_t bar0 = sbase + WG_BAR_OFF;
+  auto raw_full = [&](int i) { return bar0 + 8 * i; };
+  auto raw_empty = [&](int i) { return bar0 + 8 * (WG_NRAW + i); };
+  auto tr_full = [&](int i) { return bar0 + 8 * (2 * WG_NRAW + i); };
+  auto tr_empty = [&](int i) { return bar0 + 8 * (2 * WG_NRAW + WG_NTR + i); };
+  const uint32_t acc_full = bar0 + 8 * (2 * WG_NRAW + 2 * WG_NTR);
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + WG_BAR_OFF + 8 * (2 * WG_NRAW + 2 * WG_NTR + 1));
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int ntile = d.cin_g / NT;
+  const int g = blockIdx.z / ntile, nt = blockIdx.z % ntile;
+  const int tap_base = blockIdx.x * 4;
+  const int ntap = min(4, d.taps - tap_base);
+  const long rbeg = (long)blockIdx.y * rows_per_split;
+  const long rend = min(rows_main, rbeg + rows_per_split);
+  const int nstage = (int)((rend - rbeg) / WG_KR);
+  const int ych = d.cout_g >> 2, xch = NT >> 2;  // chunks loaded per stage
+  const int xunits = WG_S + ntap - 1;
+  const uint32_t TM_COLS = 512;
+
+  if (tid == 0) {
+    for (int i = 0; i < WG_NRAW; ++i) { mbar_init(raw_full(i), 1); mbar_init(raw_empty(i), 128); }
+    for (int i = 0; i < WG_NTR; ++i) { mbar_init(tr_full(i), 128); mbar_init(tr_empty(i), 1); }
+    mbar_init(acc_full, 1);
+    fence_barrier_init();
+  }
+  if (ych < 32) {  // cout_g == 64: channels 64..127 of the M = 128 operand are zero (never written afterwards)
+    for (int u = 0; u < WG_NTR; ++u)
+      for (int i = tid; i < WG_S * 64; i += WG_THREADS) {
+        const int a = i >> 6, c = 64 + (i & 63);
+        *reinterpret_cast<float4*>(smem + WG_NRAW * WG_RAW + u * WG_TR + a * WG_LBO + c * 16) = f4zero();
+      }
+    fence_proxy_async();
+  }
+  if (warp == 1) tmem_alloc(smem_u32((const void*)tmem_slot), TM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== copy producer: raw CBL4 tiles =====
+    if (lane == 0) {
+      const float4* yg = reinterpret_cast<const float4*>(d.dy) + (long)(d.dy_c4_off + g * d.dy_c4_gstride) * d.dy_cstride;
+      const float4* xg = reinterpret_cast<const float4*>(d.x) + (long)(d.x_c4_off + g * d.x_c4_gstride + nt * xch) * d.x_cstride +
+                         (d.tap_off + tap_base);
+      const uint32_t xbytes = (uint32_t)(WG_KR + ntap - 1) * 16;
+      int st = 0, ph = 0;
+      for (int it = 0; it < nstage; ++it) {
+        const long r = rbeg + (long)it * WG_KR;
+        mbar_wait(raw_empty(st), ph ^ 1);
+        mbar_expect_tx(raw_full(st), (uint32_t)ych * WG_YPITCH + (uint32_t)xch * xbytes);
+        const uint32_t ys = sbase + st * WG_RAW, xs = ys + 32 * WG_YPITCH;
+        for (int c = 0; c < ych; ++c) bulk_g2s(ys + c * WG_YPITCH, yg + (long)c * d.dy_cstride + r, WG_YPITCH, raw_full(st));
+        for (int c = 0; c < xch; ++c) bulk_g2s(xs + c * WG_XPITCH, xg + (long)c * d.x_cstride + r, xbytes, raw_full(st));
+        if (++st == WG_NRAW) { st = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(128, NT, 0, 0);
+      int u = 0, ph = 0;
+      for (int it = 0; it < nstage; ++it) {
+        mbar_wait(tr_full(u), ph);
+        tc_fence_after();
+        const uint32_t ty = tr0 + u * WG_TR, tx = ty + WG_TY;
+#pragma unroll
+        for (int ks = 0; ks < WG_S / 2; ++ks) {
+          const uint64_t ad = make_desc(ty + (2 * ks) * WG_LBO, WG_LBO, 128);
+          for (int tp = 0; tp < ntap; ++tp) {
+            const uint64_t bd = make_desc(tx + (2 * ks + tp) * WG_LBO, WG_LBO, 128);
+            mma_tf32(tmem + tp * NT, ad, bd, idesc, (uint32_t)(it | ks));
+          }
+        }
+        tc_commit(tr_empty(u));
+        if (++u == WG_NTR) { u = 0; ph ^= 1; }
+      }
+      tc_commit(acc_full);
+    }
+  } else {
+    // ===== warps 2..5: re-tile every stage into K-major core matrices, then drain the accumulators =====
+    const int e = tid - 64;  // 0..127
+    {
+      int st = 0, rph = 0, u = 0, uph = 0;
+      for (int it = 0; it < nstage; ++it) {
+        mbar_wait(raw_full(st), rph);
+        mbar_wait(tr_empty(u), uph ^ 1);
+        tc_fence_after();
+        const uint8_t* ys = smem + st * WG_RAW;
+        const uint8_t* xs = ys + 32 * WG_YPITCH;
+        uint8_t* ty = smem + WG_NRAW * WG_RAW + u * WG_TR;
+        uint8_t* tx = ty + WG_TY;
+        // dY: ych chunks x 8 units
+        for (int id = e; id < ych * WG_S; id += 128) {
+          const int c = id >> 3, a = id & 7;
+          const float4* src = reinterpret_cast<const float4*>(ys + c * WG_YPITCH) + a;
+          const float4 r0 = src[0], r1 = src[WG_S], r2 = src[2 * WG_S], r3 = src[3 * WG_S];
+          float4* dst = reinterpret_cast<float4*>(ty + a * WG_LBO + (4 * c) * 16);
+          dst[0] = make_float4(r0.x, r1.x, r2.x, r3.x);
+          dst[1] = make_float4(r0.y, r1.y, r2.y, r3.y);
+          dst[2] = make_float4(r0.z, r1.z, r2.z, r3.z);
+          dst[3] = make_float4(r0.w, r1.w, r2.w, r3.w);
+        }
+        // X: xch chunks x (8 + ntap - 1) units
+        for (int id = e; id < xch * xunits; id += 128) {
+          const int c = id / xunits, a = id - c * xunits;
+          const float4* src = reinterpret_cast<const float4*>(xs + c * WG_XPITCH) + a;
+          const float4 r0 = src[0], r1 = src[WG_S], r2 = src[2 * WG_S], r3 = src[3 * WG_S];
+          float4* dst = reinterpret_cast<float4*>(tx + a * WG_LBO + (4 * c) * 16);
+          dst[0] = make_float4(r0.x, r1.x, r2.x, r3.x);
+          dst[1] = make_float4(r0.y, r1.y, r2.y, r3.y);
+          dst[2] = make_float4(r0.z, r1.z, r2.z, r3.z);
+          dst[3] = make_float4(r0.w, r1.w, r2.w, r3.w);
+        }
+        fence_proxy_async();
+        mbar_arrive(tr_full(u));
+        mbar_arrive(raw_empty(st));
+        if (++st == WG_NRAW) { st = 0; rph ^= 1; }
+        if (++u == WG_NTR) { u = 0; uph ^= 1; }
+      }
+    }
+    if (nstage > 0) {
+      const int q = warp & 3;
+      const int m = q * 32 + lane;  // output channel within the group
+      mbar_wait(acc_full, 0);
+      tc_fence_after();
+      for (int tp = 0; tp < ntap; ++tp) {
+        for (int cg = 0; cg < NT / 32; ++cg) {
+          uint32_t v[32];
+          tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(tp * NT + cg * 32), v);
+          tmem_ld_wait();
+          if (m < d.cout_g) {
+            float* dst = d.dw + (long)g * d.sg + (long)m * d.sm + (long)(nt * NT + cg * 32) * d.sn + (long)(tap_base + tp) * d.st;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) atomicAdd(dst + (long)i * d.sn, __uint_as_float(v[i]));
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, TM_COLS);
+  }
+}
+
+// db[g * cout_g + m] += sum over rows of dy[row][g, m]   (grid: x = row splits, y = 4-channel chunks of all groups)
+__global__ void __launch_bounds__(256) bias_grad_kernel(const NefWgradDesc d, long rows_per_split) {
+  __shared__ float4 red[8];
+  const int ch4 = blockIdx.y;  // chunk among groups * cout_g / 4
+  const int g = ch4 / (d.cout_g >> 2), c = ch4 % (d.cout_g >> 2);
+  const float4* yg = reinterpret_cast<const float4*>(d.dy) + (long)(d.dy_c4_off + g * d.dy_c4_gstride + c) * d.dy_cstride;
+  const long rbeg = (long)blockIdx.x * rows_per_split, rend = min(d.rows, rbeg + rows_per_split);
+  float4 acc = f4zero();
+  for (long r = rbeg + threadIdx.x; r < rend; r += 256) acc = acc + __ldg(yg + r);
+  acc.x = warp_sum(acc.x); acc.y = warp_sum(acc.y); acc.z = warp_sum(acc.z); acc.w = warp_sum(acc.w);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float4 t = f4zero();
+    for (int w = 0; w < 8; ++w) t = t + red[w];
+    float* o = d.db + (long)g * d.cout_g + c * 4;
+    atomicAdd(o + 0, t.x); atomicAdd(o + 1, t.y); atomicAdd(o + 2, t.z); atomicAdd(o + 3, t.w);
+  }
+}
+
+}  // namespace tc
+}  // namespace nef
+
+using namespace nef;
+
+static int g_sm_count = 148;
+
+extern "C" int nef_tc_init(void) {
+  cudaError_t e;
+  e = cudaFuncSetAttribute(tc::conv_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::FwSmem<4>::TOTAL);
+  NEF_REQUIRE(e == cudaSuccess, "nef_tc_init: conv_tc_kernel<4> smem opt-in failed: %s", cudaGetErrorString(e));
+  e = cudaFuncSetAttribute(tc::conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::FwSmem<1>::TOTAL);
+  NEF_REQUIRE(e == cudaSuccess, "nef_tc_init: conv_tc_kernel<1> smem opt-in failed: %s", cudaGetErrorString(e));
+  e = cudaFuncSetAttribute(tc::wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::WG_TOTAL);
+  NEF_REQUIRE(e == cudaSuccess, "nef_tc_init: wgrad_tc_kernel smem opt-in failed: %s", cudaGetErrorString(e));
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
+  return 0;
+}
+
+extern "C" int nef_gconv_fwd_tc(const NefConvDesc* d, nef_stream_t s) {
+  // small row spaces (the z2 deflection branch at small batch): one 128-row tile per CTA keeps the grid wide
+  const long tiles4 = (d->rows + 511) / 512;
+  if (tiles4 * d->groups >= g_sm_count) {
+    dim3 grid((unsigned)tiles4, (unsigned)d->groups);
+    tc::conv_tc_kernel<4><<<grid, tc::FW_THREADS, tc::FwSmem<4>::TOTAL, (cudaStream_t)s>>>(*d);
+  } else {
+    dim3 grid((unsigned)((d->rows + 127) / 128), (unsigned)d->groups);
+    tc::conv_tc_kernel<1><<<grid, tc::FW_THREADS, tc::FwSmem<1>::TOTAL, (cudaStream_t)s>>>(*d);
+  }
+  NEF_CHECK_LAUNCH("conv_tc_kernel");
+  return 0;
+}
+
+extern "C" int nef_gconv_wgrad_tc(const NefWgradDesc* d, nef_stream_t s) {
+  NEF_REQUIRE(d->cout_g == 64 || d->cout_g == 128, "nef_gconv_wgrad_tc: cout_g must be 64 or 128 (got %d)", d->cout_g);
+  const int NT = d->cin_g >= 128 ? 128 : 64;
+  NEF_REQUIRE(d->cin_g % NT == 0, "nef_gconv_wgrad_tc: cin_g must be 64 or a multiple of 128 (got %d)", d->cin_g);
+  const long nst_total = d->rows / tc::WG_KR;
+  const long rows_main = nst_total * tc::WG_KR;
+  if (nst_total > 0) {
+    const int passes = (d->taps + 3) / 4;
+    const long tiles = (long)d->groups * (d->cin_g / NT) * passes;
+    // row splits: the smallest count whose last wave is >= 90 % full (else the best seen), at most 64 per tile
+    long best = 1;
+    double best_eff = 0.0;
+    const long max_splits = nst_total < 64 ? nst_total : 64;
+    for (long sp = 1; sp <= max_splits; ++sp) {
+      const long ctas = tiles * sp;
+      const double eff = (double)ctas / (double)(((ctas + g_sm_count - 1) / g_sm_count) * g_sm_count);
+      if (eff > best_eff + 1e-9) { best_eff = eff; best = sp; }
+      if (eff >= 0.9) { best = sp; break; }
+    }
+    long st_per_split = (nst_total + best - 1) / best;
+    const long splits = (nst_total + st_per_split - 1) / st_per_split;
+    dim3 grid((unsigned)passes, (unsigned)splits, (unsigned)(d->groups * (d->cin_g / NT)));
+    tc::wgrad_tc_kernel<<<grid, tc::WG_THREADS, tc::WG_TOTAL, (cudaStream_t)s>>>(*d, NT, st_per_split * tc::WG_KR, rows_main);
+    NEF_CHECK_LAUNCH("wgrad_tc_kernel");
+  }
+  if (rows_main < d->rows) {  // ragged tail (< 32 rows): CUDA-core kernel over [rows_main, rows), no bias term
+    NefWgradDesc t = *d;
+    t.db = nullptr;
+    int rc = nef_gconv_wgrad_simt_range(&t, rows_main, s);
+    if (rc) return rc;
+  }
+  if (d->db) {
+    long splits = (d->rows + 4095) / 4096;
+    if (splits > 64) splits = 64;
+    const long rps = (d->rows + splits - 1) / splits;
+    dim3 grid((unsigned)((d->rows + rps - 1) / rps), (unsigned)(d->groups * (d->cout_g / 4)));
+    tc::bias_grad_kernel<<<grid, 256, 0, (cudaStream_t)s>>>(*d, rps);
+    NEF_CHECK_LAUNCH("bias_grad_kernel");
+  }
+  return 0;
+}
 
 NEF_DEFINE_EXACT_SETTER(nef_set_exact_tc)

@@ -618,36 +618,54 @@ int latent_bwd(const LatentBwdArgs& a, cudaStream_t s) {
 // ===========================================================================================
 // Decoder BatchNorm1d (train: batch statistics, eps 1e-5, momentum 0.1), model_nefnet.py:17-24
 // ===========================================================================================
-__global__ void bn_finalize_kernel(BnLayer bn, int C, double count, const float* __restrict__ gamma,
-                                   const float* __restrict__ beta, float* rmean, float* rvar, int64_t* nbt,
-                                   int training) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c < C) {
-    float mean, invstd;
-    if (training) {
-      const double m = bn.sum[c] / count;
-      double var = bn.sq[c] / count - m * m;
-      if (var < 0.0) var = 0.0;
-      mean = (float)m;
-      invstd = (float)(1.0 / sqrt(var + 1e-5));
-      const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
-      rmean[c] = 0.9f * rmean[c] + 0.1f * mean;
-      rvar[c] = 0.9f * rvar[c] + 0.1f * (float)unbiased;
-    } else {
-      mean = rmean[c];
-      invstd = 1.0f / sqrtf(rvar[c] + 1e-5f);
+// One block per channel: the per-tile partial sums are reduced in a fixed order (thread-strided double
+// accumulation, then a fixed shared-memory tree), so equal conv outputs give bit-equal statistics.
+__global__ void __launch_bounds__(128) bn_finalize_kernel(BnLayer bn, int C, double count, const float* __restrict__ gamma,
+                                                          const float* __restrict__ beta, float* rmean, float* rvar,
+                                                          int64_t* nbt, int training) {
+  __shared__ double r1[128], r2[128];
+  const int c = blockIdx.x, tid = threadIdx.x;
+  float mean, invstd;
+  if (training) {
+    double a = 0.0, b = 0.0;
+    for (int t = tid; t < bn.n_rec; t += 128) {
+      a += (double)bn.sum[(long)t * C + c];
+      b += (double)bn.sq[(long)t * C + c];
     }
-    bn.mean[c] = mean;
-    bn.invstd[c] = invstd;
-    const float sc = gamma[c] * invstd;
-    bn.scale[c] = sc;
-    bn.shift[c] = beta[c] - mean * sc;
+    r1[tid] = a;
+    r2[tid] = b;
+    __syncthreads();
+    for (int o = 64; o > 0; o >>= 1) {
+      if (tid < o) {
+        r1[tid] += r1[tid + o];
+        r2[tid] += r2[tid + o];
+      }
+      __syncthreads();
+    }
+    if (tid != 0) return;
+    const double m = r1[0] / count;
+    double var = r2[0] / count - m * m;
+    if (var < 0.0) var = 0.0;
+    mean = (float)m;
+    invstd = (float)(1.0 / sqrt(var + 1e-5));
+    const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+    rmean[c] = 0.9f * rmean[c] + 0.1f * mean;
+    rvar[c] = 0.9f * rvar[c] + 0.1f * (float)unbiased;
+    if (c == 0) nbt[0] += 1;
+  } else {
+    if (tid != 0) return;
+    mean = rmean[c];
+    invstd = 1.0f / sqrtf(rvar[c] + 1e-5f);
   }
-  if (training && c == 0) nbt[0] += 1;
+  bn.mean[c] = mean;
+  bn.invstd[c] = invstd;
+  const float sc = gamma[c] * invstd;
+  bn.scale[c] = sc;
+  bn.shift[c] = beta[c] - mean * sc;
 }
 int bn_finalize(const BnLayer& bn, int C, double count, const float* gamma, const float* beta, float* rmean,
                 float* rvar, int64_t* nbt, int training, cudaStream_t s) {
-  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(bn, C, count, gamma, beta, rmean, rvar, nbt, training);
+  bn_finalize_kernel<<<C, 128, 0, s>>>(bn, C, count, gamma, beta, rmean, rvar, nbt, training);
   NEF_CHECK_LAUNCH("bn_finalize_kernel");
   return 0;
 }

@@ -15,8 +15,9 @@ struct T4 {
 };
 
 struct BnLayer {          // one BatchNorm1d of the decoder for one decoder call
-  double* sum;            // [C] batch sum of the conv output   (zeroed before the conv)
-  double* sq;             // [C]
+  float* sum;             // [n_rec][C] per-128-row-tile sums of the conv output (NefConvDesc.stat_sum)
+  float* sq;              // [n_rec][C]
+  int n_rec;              // ceil(rows / 128)
   float* scale;           // [C] gamma * invstd
   float* shift;           // [C] beta - mean * scale
   float* mean;            // [C] saved for backward

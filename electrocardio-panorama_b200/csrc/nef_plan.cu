@@ -178,7 +178,7 @@ struct NefPlan {
   T4 gz2o, gh22, dt21, dte, dto, gy20, gh20, dra, gz2c, ghz, gxw;
   T4 dg4, dg3, du1, dg2, dg1, du0[3];
   float *ds_in, *dq;
-  double* bn_stats;       // all BnLayer doubles, contiguous (zeroed per step)
+  double* bn_stats;       // BatchNorm backward accumulators (s1, s2) of all layers, contiguous
   size_t bn_stats_count;
   // weights
   ConvW enc[6], wc[2], z1c[3], z2c1[3], z2a[2], z2b[3], decw[4];
@@ -241,15 +241,22 @@ static void carve(NefPlan* p, bool dry) {
       d.bn[i].mean = c.f32(ch[i]); d.bn[i].invstd = c.f32(ch[i]);
     }
   }
-  // BatchNorm double accumulators: 3 calls x 4 layers x 4 arrays x 128
-  p->bn_stats_count = 3 * 4 * 4 * 128;
+  // BatchNorm forward partial records (per 128-row tile) and backward double accumulators
+  for (int k = 0; k < 3; ++k)
+    for (int i = 0; i < 4; ++i) {
+      const int ch = i < 2 ? 128 : 64;
+      const long rows = (long)B * ((i < 2 ? L2 : L) + 2 * NEF_HALO);
+      const int n_rec = (int)((rows + 127) / 128);
+      p->dec[k].bn[i].n_rec = n_rec;
+      p->dec[k].bn[i].sum = c.f32((size_t)n_rec * ch);
+      p->dec[k].bn[i].sq = c.f32((size_t)n_rec * ch);
+    }
+  p->bn_stats_count = 3 * 4 * 2 * 128;
   p->bn_stats = reinterpret_cast<double*>(c.take(p->bn_stats_count * sizeof(double)));
   if (!dry) {
     double* q = p->bn_stats;
     for (int k = 0; k < 3; ++k)
       for (int i = 0; i < 4; ++i) {
-        p->dec[k].bn[i].sum = q; q += 128;
-        p->dec[k].bn[i].sq = q; q += 128;
         p->dec[k].bn[i].s1 = q; q += 128;
         p->dec[k].bn[i].s2 = q; q += 128;
       }
@@ -352,7 +359,7 @@ struct CD {
     d.mask_mode = mode; d.mask_scale = scale;
     return *this;
   }
-  CD& stats(double* s1, double* s2) { d.stat_sum = s1; d.stat_sq = s2; return *this; }
+  CD& stats(float* s1, float* s2) { d.stat_sum = s1; d.stat_sq = s2; return *this; }
   CD& round() { d.round_tf32 = 1; return *this; }
   int run(cudaStream_t s) { return nef_gconv_fwd(&d, (nef_stream_t)s); }
 };
@@ -457,10 +464,7 @@ static int decoder_fwd(NefPlan* p, const float* const* P, int slot, const T4& u0
       c.term(u0lo, 0, 0, 256, 3, l.w->pk_f);
       c.term(l.in, 0, 0, 256, 3, p->dec1_lo);
     }
-    if (training) {
-      cudaMemsetAsync(d.bn[i].sum, 0, 2 * 128 * sizeof(double), s);  // sum and sq are adjacent
-      c.stats(d.bn[i].sum, d.bn[i].sq);
-    }
+    if (training) c.stats(d.bn[i].sum, d.bn[i].sq);
     RUN(c.run(s));
     RUN(bn_finalize(d.bn[i], l.w->cout_g, l.count, P[l.bnp], P[l.bnp + 1], const_cast<float*>(P[l.bnp + 2]),
                     const_cast<float*>(P[l.bnp + 3]),

@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_PKG, "lib", "libnefnet_b200.so")
 
 PHASE_TRAIN, PHASE_TEST, PHASE_GEN = 0, 1, 2
 HALO = 3
-GUARD_ROWS = 272
+GUARD_ROWS = 528
 
 
 class NefConvTerm(C.Structure):

@@ -27,7 +27,7 @@ extern "C" {
 
 #define NEF_ABI_VERSION 1
 #define NEF_HALO_ROWS 3
-#define NEF_GUARD_ROWS_ABI 272
+#define NEF_GUARD_ROWS_ABI 528
 
 typedef void* nef_stream_t; /* cudaStream_t */
 
@@ -104,8 +104,11 @@ typedef struct NefConvDesc {
   int32_t mask_c4_off, mask_c4_gstride;
   float mask_scale;
   int32_t reserved2;
-  double* stat_sum;     /* [groups * N] += sum over valid rows of v, or NULL (BatchNorm batch statistics) */
-  double* stat_sq;      /* [groups * N] += sum of v * v */
+  /* BatchNorm batch statistics, or NULL: record t = the sums over the valid rows of the 128-row tile t of
+   * the input row space, [ceil(rows / 128)][groups * N] floats each, every record overwritten.  They are
+   * reduced in a fixed order (nef_plan's finalize kernel), so equal inputs give bit-equal statistics. */
+  float* stat_sum;      /* sum of v */
+  float* stat_sq;       /* sum of v * v */
 } NefConvDesc;
 
 /* Packs reference-layout weights into the layout NefConvTerm.w expects, rounding to TF32 (RN):
