@@ -109,7 +109,7 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, 
 // ---------------------------------------------------------------------------------------------
 // forward / data-gradient kernel
 // ---------------------------------------------------------------------------------------------
-constexpr int FW_THREADS = 192;
+constexpr int FW_THREADS = 320;  // warp 0 copy producer, warp 1 MMA issuer, warps 2..9 epilogue
 constexpr int FW_XST = 2;  // activation stages (one per 32-channel block)
 constexpr int FW_WBYTES = 8 * 128 * 16;  // one weight stage: 32 input channels x up to 128 outputs x one tap
 
@@ -159,24 +159,27 @@ __global__ void __launch_bounds__(FW_THREADS, 1) conv_tc_kernel(const __grid_con
   const uint32_t tmem = *tmem_slot;
 
   if (warp == 0) {
-    // ===== copy producer =====
-    if (lane == 0) {
-      int xs = 0, xph = 0, wst = 0, wph = 0;
-      for (int ti = 0; ti < d.n_terms; ++ti) {
-        const NefConvTerm& t = d.term[ti];
-        const int nkb = t.cin_g >> 5;
-        const uint32_t xbytes = (uint32_t)(MT * 128 + t.taps - 1) * 16;
-        const uint32_t wbytes = (uint32_t)(8 * N * 16);
-        const float4* xg = reinterpret_cast<const float4*>(t.x) + (r0 + t.tap_off);
-        const float4* wg = reinterpret_cast<const float4*>(t.w);
-        for (int kb = 0; kb < nkb; ++kb) {
+    // ===== copy producer (lane c copies channel chunk c of every activation stage, lane 0 the weight stages) =====
+    int xs = 0, xph = 0, wst = 0, wph = 0;
+    for (int ti = 0; ti < d.n_terms; ++ti) {
+      const NefConvTerm& t = d.term[ti];
+      const int nkb = t.cin_g >> 5;
+      const uint32_t xbytes = (uint32_t)(MT * 128 + t.taps - 1) * 16;
+      const uint32_t wbytes = (uint32_t)(8 * N * 16);
+      const float4* xg = reinterpret_cast<const float4*>(t.x) + (r0 + t.tap_off);
+      const float4* wg = reinterpret_cast<const float4*>(t.w);
+      for (int kb = 0; kb < nkb; ++kb) {
+        if (lane == 0) {
           mbar_wait(empty_x(xs), xph ^ 1);
           mbar_expect_tx(full_x(xs), 8 * xbytes);
-          const long chunk0 = t.x_c4_off + (long)g * t.x_c4_gstride + kb * 8;
-#pragma unroll
-          for (int c = 0; c < 8; ++c)
-            bulk_g2s(xs0 + xs * S::XBYTES + c * S::XPITCH, xg + (chunk0 + c) * t.x_cstride, xbytes, full_x(xs));
-          if (++xs == FW_XST) { xs = 0; xph ^= 1; }
+        }
+        __syncwarp();
+        if (lane < 8) {
+          const long chunk = t.x_c4_off + (long)g * t.x_c4_gstride + kb * 8 + lane;
+          bulk_g2s(xs0 + xs * S::XBYTES + lane * S::XPITCH, xg + chunk * t.x_cstride, xbytes, full_x(xs));
+        }
+        if (++xs == FW_XST) { xs = 0; xph ^= 1; }
+        if (lane == 0) {
           for (int tp = 0; tp < t.taps; ++tp) {
             mbar_wait(empty_w(wst), wph ^ 1);
             mbar_expect_tx(full_w(wst), wbytes);
@@ -184,6 +187,7 @@ __global__ void __launch_bounds__(FW_THREADS, 1) conv_tc_kernel(const __grid_con
             if (++wst == S::WST) { wst = 0; wph ^= 1; }
           }
         }
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
@@ -222,11 +226,18 @@ __global__ void __launch_bounds__(FW_THREADS, 1) conv_tc_kernel(const __grid_con
       tc_commit(acc_full);
     }
   } else {
-    // ===== epilogue: warps 2..5 own TMEM lanes 32 * (warp % 4) .. + 31 =====
-    const int q = warp & 3;
+    // ===== epilogue: 8 warps; warp w owns TMEM lanes 32 * (w % 4) .. + 31 and the 32-column groups cg = (w - 2) / 4 (mod 2)
+    const int q = warp & 3, chalf = (warp - 2) >> 2;
     const bool want_stats = d.stat_sum != nullptr;
+    const bool f_bias = d.bias != nullptr, f_res = d.res != nullptr, f_relu = d.relu != 0, f_drop = d.drop_p > 0.f;
+    const bool f_bscale = d.bscale != nullptr, f_bsgrad = d.bscale_grad != nullptr, f_round = d.round_tf32 != 0;
+    const int mask_mode = d.mask_mode;
+    const float mask_scale = d.mask_scale;
+    const uint32_t drop_thr = (uint32_t)(d.drop_p * 65536.f);
+    const float drop_sc = 1.f / (1.f - d.drop_p);
     const long ctot = (long)d.groups * N;
     const long n_rec = (d.rows + 127) / 128;
+    const float4* bias4 = reinterpret_cast<const float4*>(d.bias) + g * (N >> 2);
     mbar_wait(acc_full, 0);
     tc_fence_after();
     for (int mt = 0; mt < MT; ++mt) {
@@ -234,17 +245,76 @@ __global__ void __launch_bounds__(FW_THREADS, 1) conv_tc_kernel(const __grid_con
       const EpiRow er = epi_row(d, row);
       const int b0 = __shfl_sync(0xffffffffu, er.b, 0);
       const bool uniform_b = __all_sync(0xffffffffu, er.b == b0);
-      for (int cg = 0; cg < N / 32; ++cg) {
+      // per-row base pointers; chunk n4 of the group is n4 * (chunk stride) further
+      float4* yp = reinterpret_cast<float4*>(d.y) + (long)(d.y_c4_off + g * d.y_c4_gstride) * d.y_cstride + er.out_row;
+      const float4* rp = reinterpret_cast<const float4*>(d.res) + (long)(d.res_c4_off + g * d.res_c4_gstride) * d.res_cstride + er.out_row;
+      const float4* mp = reinterpret_cast<const float4*>(d.mask) + (long)(d.mask_c4_off + g * d.mask_c4_gstride) * d.mask_cstride + er.out_row;
+      const float4* bs4 = reinterpret_cast<const float4*>(d.bscale) + (long)er.b * (ctot >> 2) + g * (N >> 2);
+      for (int cg = chalf; cg < N / 32; cg += 2) {
         uint32_t v[32];
         tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * N + cg * 32), v);
+        // the residual / mask operands of these 8 chunks are fetched while the TMEM load is in flight
+        float4 rr[8], mm[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          rr[i] = f4zero();
+          mm[i] = f4zero();
+          if (er.valid) {
+            if (f_res) rr[i] = __ldg(rp + (long)(cg * 8 + i) * d.res_cstride);
+            if (mask_mode) mm[i] = __ldg(mp + (long)(cg * 8 + i) * d.mask_cstride);
+          }
+        }
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int n4 = cg * 8 + i;
-          float4 acc = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]),
-                                   __uint_as_float(v[4 * i + 3]));
-          float4 pre = f4zero(), bsg = f4zero();
-          if (er.valid) epi_apply_store(d, er, g, n4, acc, &pre, &bsg);
+          float4 x = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]),
+                                 __uint_as_float(v[4 * i + 3]));
+          if (f_bias) x = x + __ldg(bias4 + n4);
+          x = x + rr[i];
+          const float4 pre = x;
+          if (f_relu) x = make_float4(fmaxf(x.x, 0.f), fmaxf(x.y, 0.f), fmaxf(x.z, 0.f), fmaxf(x.w, 0.f));
+          if (f_drop) {
+            const uint64_t bits = drop_bits(d.drop_seed, er.out_row, d.y_c4_off + g * d.y_c4_gstride + n4);
+            x.x = ((bits & 0xffff) >= drop_thr) ? x.x * drop_sc : 0.f;
+            x.y = (((bits >> 16) & 0xffff) >= drop_thr) ? x.y * drop_sc : 0.f;
+            x.z = (((bits >> 32) & 0xffff) >= drop_thr) ? x.z * drop_sc : 0.f;
+            x.w = (((bits >> 48) & 0xffff) >= drop_thr) ? x.w * drop_sc : 0.f;
+          }
+          if (f_bscale) {
+            const float4 sc4 = er.valid ? __ldg(bs4 + n4) : make_float4(1.f, 1.f, 1.f, 1.f);
+            if (f_bsgrad) {  // forward was ys = relu(.) * s with the mask tensor = ys ; d s += x * ys / s
+              const float4 m = mm[i];
+              float4 bsg;
+              bsg.x = sc4.x != 0.f ? x.x * m.x / sc4.x : 0.f;
+              bsg.y = sc4.y != 0.f ? x.y * m.y / sc4.y : 0.f;
+              bsg.z = sc4.z != 0.f ? x.z * m.z / sc4.z : 0.f;
+              bsg.w = sc4.w != 0.f ? x.w * m.w / sc4.w : 0.f;
+              const long cbase = (long)g * N + n4 * 4;
+              if (uniform_b) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const float s1 = warp_sum(er.valid ? f4get(bsg, j) : 0.f);
+                  if (lane == 0 && s1 != 0.f) atomicAdd(d.bscale_grad + (long)b0 * ctot + cbase + j, s1);
+                }
+              } else if (er.valid) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) atomicAdd(d.bscale_grad + (long)er.b * ctot + cbase + j, f4get(bsg, j));
+              }
+            }
+            x = x * sc4;
+          }
+          if (mask_mode == 1) {
+            const float4 m = mm[i];
+            x = make_float4(m.x > 0.f ? x.x * mask_scale : 0.f, m.y > 0.f ? x.y * mask_scale : 0.f,
+                            m.z > 0.f ? x.z * mask_scale : 0.f, m.w > 0.f ? x.w * mask_scale : 0.f);
+          } else if (mask_mode == 2) {
+            const float4 m = mm[i];
+            x = make_float4(m.x != 0.f ? x.x * mask_scale : 0.f, m.y != 0.f ? x.y * mask_scale : 0.f,
+                            m.z != 0.f ? x.z * mask_scale : 0.f, m.w != 0.f ? x.w * mask_scale : 0.f);
+          }
+          if (f_round) x = tf32_rn4(x);
+          if (er.valid) yp[(long)n4 * d.y_cstride] = x;
           if (want_stats) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -256,31 +326,18 @@ __global__ void __launch_bounds__(FW_THREADS, 1) conv_tc_kernel(const __grid_con
               }
             }
           }
-          if (d.bscale_grad) {
-            const long cbase = (long)g * N + n4 * 4;
-            if (uniform_b) {
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float s1 = warp_sum(er.valid ? f4get(bsg, j) : 0.f);
-                if (lane == 0 && s1 != 0.f) atomicAdd(d.bscale_grad + (long)b0 * ctot + cbase + j, s1);
-              }
-            } else if (er.valid) {
-#pragma unroll
-              for (int j = 0; j < 4; ++j) atomicAdd(d.bscale_grad + (long)er.b * ctot + cbase + j, f4get(bsg, j));
-            }
-          }
         }
       }
       if (want_stats) {
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        const int et = tid - 64;  // 0..127
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const int et = tid - 64;  // 0..255
         const long rec = r0 / 128 + mt;
         if (et < N && rec < n_rec) {
           const long o = rec * ctot + (long)g * N + et;
           d.stat_sum[o] = (s_stat[0 * 128 + et] + s_stat[2 * 128 + et]) + (s_stat[4 * 128 + et] + s_stat[6 * 128 + et]);
           d.stat_sq[o] = (s_stat[1 * 128 + et] + s_stat[3 * 128 + et]) + (s_stat[5 * 128 + et] + s_stat[7 * 128 + et]);
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
       }
     }
     tc_fence_before();
@@ -373,22 +430,23 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
   const uint32_t tmem = *tmem_slot;
 
   if (warp == 0) {
-    // ===== copy producer: raw CBL4 tiles =====
-    if (lane == 0) {
-      const float4* yg = reinterpret_cast<const float4*>(d.dy) + (long)(d.dy_c4_off + g * d.dy_c4_gstride) * d.dy_cstride;
-      const float4* xg = reinterpret_cast<const float4*>(d.x) + (long)(d.x_c4_off + g * d.x_c4_gstride + nt * xch) * d.x_cstride +
-                         (d.tap_off + tap_base);
-      const uint32_t xbytes = (uint32_t)(WG_KR + ntap - 1) * 16;
-      int st = 0, ph = 0;
-      for (int it = 0; it < nstage; ++it) {
-        const long r = rbeg + (long)it * WG_KR;
+    // ===== copy producer: raw CBL4 tiles (lane c copies chunk c of dY and of X) =====
+    const float4* yg = reinterpret_cast<const float4*>(d.dy) + (long)(d.dy_c4_off + g * d.dy_c4_gstride) * d.dy_cstride;
+    const float4* xg = reinterpret_cast<const float4*>(d.x) + (long)(d.x_c4_off + g * d.x_c4_gstride + nt * xch) * d.x_cstride +
+                       (d.tap_off + tap_base);
+    const uint32_t xbytes = (uint32_t)(WG_KR + ntap - 1) * 16;
+    int st = 0, ph = 0;
+    for (int it = 0; it < nstage; ++it) {
+      const long r = rbeg + (long)it * WG_KR;
+      if (lane == 0) {
         mbar_wait(raw_empty(st), ph ^ 1);
         mbar_expect_tx(raw_full(st), (uint32_t)ych * WG_YPITCH + (uint32_t)xch * xbytes);
-        const uint32_t ys = sbase + st * WG_RAW, xs = ys + 32 * WG_YPITCH;
-        for (int c = 0; c < ych; ++c) bulk_g2s(ys + c * WG_YPITCH, yg + (long)c * d.dy_cstride + r, WG_YPITCH, raw_full(st));
-        for (int c = 0; c < xch; ++c) bulk_g2s(xs + c * WG_XPITCH, xg + (long)c * d.x_cstride + r, xbytes, raw_full(st));
-        if (++st == WG_NRAW) { st = 0; ph ^= 1; }
       }
+      __syncwarp();
+      const uint32_t ys = sbase + st * WG_RAW, xs = ys + 32 * WG_YPITCH;
+      if (lane < ych) bulk_g2s(ys + lane * WG_YPITCH, yg + (long)lane * d.dy_cstride + r, WG_YPITCH, raw_full(st));
+      if (lane < xch) bulk_g2s(xs + lane * WG_XPITCH, xg + (long)lane * d.x_cstride + r, xbytes, raw_full(st));
+      if (++st == WG_NRAW) { st = 0; ph ^= 1; }
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
