@@ -125,7 +125,22 @@ struct FwSmem {
   static constexpr int TOTAL = STAT_OFF + 4 * 2 * 128 * 4 + 128;
 };
 
-template <int MT>
+// EPI: compile-time epilogue selection (bit 0 bias, 1 residual tensor, 2 ReLU, 3 dropout, 4 mask mode 1, 5 TF32 rounding of
+// the stored value; bit 6 = generic: every option read from the descriptor at run time, incl. BatchNorm statistics, the
+// angular scale and its gradient, mask mode 2).  The specialised bodies are ~4x shorter, which matters: the epilogue runs
+// on 8 warps only and the generic body does not fit the instruction cache.
+constexpr int EPI_BIAS = 1, EPI_RES = 2, EPI_RELU = 4, EPI_DROP = 8, EPI_MASK1 = 16, EPI_ROUND = 32, EPI_GENERIC = 64;
+
+__device__ __forceinline__ float4 rn4_tf32(float4 v) {
+  uint32_t a, b, c, e;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(a) : "f"(v.x));
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(b) : "f"(v.y));
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(c) : "f"(v.z));
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(e) : "f"(v.w));
+  return make_float4(__uint_as_float(a), __uint_as_float(b), __uint_as_float(c), __uint_as_float(e));
+}
+
+template <int MT, int EPI>
 __global__ void __launch_bounds__(FW_THREADS, 1) conv_tc_kernel(const __grid_constant__ NefConvDesc d) {
   using S = FwSmem<MT>;
   extern __shared__ __align__(128) uint8_t smem[];
@@ -228,10 +243,15 @@ __global__ void __launch_bounds__(FW_THREADS, 1) conv_tc_kernel(const __grid_con
   } else {
     // ===== epilogue: 8 warps; warp w owns TMEM lanes 32 * (w % 4) .. + 31 and the 32-column groups cg = (w - 2) / 4 (mod 2)
     const int q = warp & 3, chalf = (warp - 2) >> 2;
-    const bool want_stats = d.stat_sum != nullptr;
-    const bool f_bias = d.bias != nullptr, f_res = d.res != nullptr, f_relu = d.relu != 0, f_drop = d.drop_p > 0.f;
-    const bool f_bscale = d.bscale != nullptr, f_bsgrad = d.bscale_grad != nullptr, f_round = d.round_tf32 != 0;
-    const int mask_mode = d.mask_mode;
+    constexpr bool GEN = (EPI & EPI_GENERIC) != 0;
+    const bool want_stats = GEN && d.stat_sum != nullptr;
+    const bool f_bias = GEN ? d.bias != nullptr : (EPI & EPI_BIAS) != 0;
+    const bool f_res = GEN ? d.res != nullptr : (EPI & EPI_RES) != 0;
+    const bool f_relu = GEN ? d.relu != 0 : (EPI & EPI_RELU) != 0;
+    const bool f_drop = GEN ? d.drop_p > 0.f : (EPI & EPI_DROP) != 0;
+    const bool f_round = GEN ? d.round_tf32 != 0 : (EPI & EPI_ROUND) != 0;
+    const bool f_bscale = GEN && d.bscale != nullptr, f_bsgrad = GEN && d.bscale_grad != nullptr;
+    const int mask_mode = GEN ? d.mask_mode : ((EPI & EPI_MASK1) ? 1 : 0);
     const float mask_scale = d.mask_scale;
     const uint32_t drop_thr = (uint32_t)(d.drop_p * 65536.f);
     const float drop_sc = 1.f / (1.f - d.drop_p);
@@ -313,7 +333,7 @@ __global__ void __launch_bounds__(FW_THREADS, 1) conv_tc_kernel(const __grid_con
             x = make_float4(m.x != 0.f ? x.x * mask_scale : 0.f, m.y != 0.f ? x.y * mask_scale : 0.f,
                             m.z != 0.f ? x.z * mask_scale : 0.f, m.w != 0.f ? x.w * mask_scale : 0.f);
           }
-          if (f_round) x = tf32_rn4(x);
+          if (f_round) x = rn4_tf32(x);
           if (er.valid) yp[(long)n4 * d.y_cstride] = x;
           if (want_stats) {
 #pragma unroll
@@ -363,7 +383,7 @@ __global__ void __launch_bounds__(FW_THREADS, 1) conv_tc_kernel(const __grid_con
 // start address advances by one unit plane per tap, exactly as the forward kernel advances by one row.
 //     D_tap[cout x cin] += dY^T[cout x (a,b)] . X^T[cin x (a + tap, b)]
 // ---------------------------------------------------------------------------------------------
-constexpr int WG_THREADS = 192;
+constexpr int WG_THREADS = 288;  // warps 0, 6, 7, 8: copy producers; warp 1: MMA issuer; warps 2..5: re-tiling + epilogue
 constexpr int WG_KR = 32;                        // rows (= contraction length) per stage
 constexpr int WG_S = WG_KR / 4;                  // units per stage; unit a = rows a + WG_S * b
 constexpr int WG_YPITCH = WG_KR * 16;            // raw tiles: bytes between channel chunks
@@ -410,7 +430,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
   const uint32_t TM_COLS = 512;
 
   if (tid == 0) {
-    for (int i = 0; i < WG_NRAW; ++i) { mbar_init(raw_full(i), 1); mbar_init(raw_empty(i), 128); }
+    for (int i = 0; i < WG_NRAW; ++i) { mbar_init(raw_full(i), 4); mbar_init(raw_empty(i), 128); }
     for (int i = 0; i < WG_NTR; ++i) { mbar_init(tr_full(i), 128); mbar_init(tr_empty(i), 1); }
     mbar_init(acc_full, 1);
     fence_barrier_init();
@@ -429,23 +449,30 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  if (warp == 0) {
-    // ===== copy producer: raw CBL4 tiles (lane c copies chunk c of dY and of X) =====
+  if (warp == 0 || warp >= 6) {
+    // ===== four copy-producer warps (a bulk copy is issued from the uniform datapath, one at a time per warp):
+    //       producer pw stages chunks [8 pw, 8 pw + 8) of dY (lanes 0..7) and of X (lanes 8..15) =====
+    const int pw = warp == 0 ? 0 : warp - 5;
     const float4* yg = reinterpret_cast<const float4*>(d.dy) + (long)(d.dy_c4_off + g * d.dy_c4_gstride) * d.dy_cstride;
     const float4* xg = reinterpret_cast<const float4*>(d.x) + (long)(d.x_c4_off + g * d.x_c4_gstride + nt * xch) * d.x_cstride +
                        (d.tap_off + tap_base);
     const uint32_t xbytes = (uint32_t)(WG_KR + ntap - 1) * 16;
+    const int c = pw * 8 + (lane & 7);
+    const int ny = min(max(ych - pw * 8, 0), 8), nx = min(max(xch - pw * 8, 0), 8);
     int st = 0, ph = 0;
     for (int it = 0; it < nstage; ++it) {
       const long r = rbeg + (long)it * WG_KR;
       if (lane == 0) {
         mbar_wait(raw_empty(st), ph ^ 1);
-        mbar_expect_tx(raw_full(st), (uint32_t)ych * WG_YPITCH + (uint32_t)xch * xbytes);
+        mbar_expect_tx(raw_full(st), (uint32_t)ny * WG_YPITCH + (uint32_t)nx * xbytes);
       }
       __syncwarp();
       const uint32_t ys = sbase + st * WG_RAW, xs = ys + 32 * WG_YPITCH;
-      if (lane < ych) bulk_g2s(ys + lane * WG_YPITCH, yg + (long)lane * d.dy_cstride + r, WG_YPITCH, raw_full(st));
-      if (lane < xch) bulk_g2s(xs + lane * WG_XPITCH, xg + (long)lane * d.x_cstride + r, xbytes, raw_full(st));
+      if (lane < 8) {
+        if (c < ych) bulk_g2s(ys + c * WG_YPITCH, yg + (long)c * d.dy_cstride + r, WG_YPITCH, raw_full(st));
+      } else if (lane < 16) {
+        if (c < xch) bulk_g2s(xs + c * WG_XPITCH, xg + (long)c * d.x_cstride + r, xbytes, raw_full(st));
+      }
       if (++st == WG_NRAW) { st = 0; ph ^= 1; }
     }
   } else if (warp == 1) {
@@ -470,7 +497,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
       }
       tc_commit(acc_full);
     }
-  } else {
+  } else if (warp < 6) {
     // ===== warps 2..5: re-tile every stage into K-major core matrices, then drain the accumulators =====
     const int e = tid - 64;  // 0..127
     {
@@ -566,13 +593,22 @@ using namespace nef;
 
 static int g_sm_count = 148;
 
+// the specialised epilogues instantiated for the 4-row-tile kernel (everything else takes the generic one)
+#define NEF_TC_EPI_LIST(X) X(0) X(2) X(32) X(33) X(36) X(37) X(38) X(44) X(48) X(50) X(64)
+
+template <int MT, int EPI>
+static int tc_optin() {
+  cudaError_t e = cudaFuncSetAttribute(tc::conv_tc_kernel<MT, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::FwSmem<MT>::TOTAL);
+  NEF_REQUIRE(e == cudaSuccess, "nef_tc_init: conv_tc_kernel<%d,%d> shared-memory opt-in failed: %s", MT, EPI, cudaGetErrorString(e));
+  return 0;
+}
+
 extern "C" int nef_tc_init(void) {
-  cudaError_t e;
-  e = cudaFuncSetAttribute(tc::conv_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::FwSmem<4>::TOTAL);
-  NEF_REQUIRE(e == cudaSuccess, "nef_tc_init: conv_tc_kernel<4> smem opt-in failed: %s", cudaGetErrorString(e));
-  e = cudaFuncSetAttribute(tc::conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::FwSmem<1>::TOTAL);
-  NEF_REQUIRE(e == cudaSuccess, "nef_tc_init: conv_tc_kernel<1> smem opt-in failed: %s", cudaGetErrorString(e));
-  e = cudaFuncSetAttribute(tc::wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::WG_TOTAL);
+#define X(E) { int rc = tc_optin<4, E>(); if (rc) return rc; }
+  NEF_TC_EPI_LIST(X)
+#undef X
+  { int rc = tc_optin<1, tc::EPI_GENERIC>(); if (rc) return rc; }
+  cudaError_t e = cudaFuncSetAttribute(tc::wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::WG_TOTAL);
   NEF_REQUIRE(e == cudaSuccess, "nef_tc_init: wgrad_tc_kernel smem opt-in failed: %s", cudaGetErrorString(e));
   int dev = 0;
   cudaGetDevice(&dev);
@@ -580,15 +616,32 @@ extern "C" int nef_tc_init(void) {
   return 0;
 }
 
+static int epi_code(const NefConvDesc* d) {
+  if (d->stat_sum || d->bscale || d->bscale_grad || d->mask_mode == 2) return tc::EPI_GENERIC;
+  int e = 0;
+  if (d->bias) e |= tc::EPI_BIAS;
+  if (d->res) e |= tc::EPI_RES;
+  if (d->relu) e |= tc::EPI_RELU;
+  if (d->drop_p > 0.f) e |= tc::EPI_DROP;
+  if (d->mask_mode == 1) e |= tc::EPI_MASK1;
+  if (d->round_tf32) e |= tc::EPI_ROUND;
+  return e;
+}
+
 extern "C" int nef_gconv_fwd_tc(const NefConvDesc* d, nef_stream_t s) {
   // small row spaces (the z2 deflection branch at small batch): one 128-row tile per CTA keeps the grid wide
   const long tiles4 = (d->rows + 511) / 512;
   if (tiles4 * d->groups >= g_sm_count) {
     dim3 grid((unsigned)tiles4, (unsigned)d->groups);
-    tc::conv_tc_kernel<4><<<grid, tc::FW_THREADS, tc::FwSmem<4>::TOTAL, (cudaStream_t)s>>>(*d);
+    switch (epi_code(d)) {
+#define X(E) case E: tc::conv_tc_kernel<4, E><<<grid, tc::FW_THREADS, tc::FwSmem<4>::TOTAL, (cudaStream_t)s>>>(*d); break;
+      NEF_TC_EPI_LIST(X)
+#undef X
+      default: tc::conv_tc_kernel<4, tc::EPI_GENERIC><<<grid, tc::FW_THREADS, tc::FwSmem<4>::TOTAL, (cudaStream_t)s>>>(*d); break;
+    }
   } else {
     dim3 grid((unsigned)((d->rows + 127) / 128), (unsigned)d->groups);
-    tc::conv_tc_kernel<1><<<grid, tc::FW_THREADS, tc::FwSmem<1>::TOTAL, (cudaStream_t)s>>>(*d);
+    tc::conv_tc_kernel<1, tc::EPI_GENERIC><<<grid, tc::FW_THREADS, tc::FwSmem<1>::TOTAL, (cudaStream_t)s>>>(*d);
   }
   NEF_CHECK_LAUNCH("conv_tc_kernel");
   return 0;
