@@ -265,23 +265,27 @@ __global__ void __launch_bounds__(FW_THREADS, 1) conv_tc_kernel(const __grid_con
       const EpiRow er = epi_row(d, row);
       const int b0 = __shfl_sync(0xffffffffu, er.b, 0);
       const bool uniform_b = __all_sync(0xffffffffu, er.b == b0);
-      // per-row base pointers; chunk n4 of the group is n4 * (chunk stride) further
-      float4* yp = reinterpret_cast<float4*>(d.y) + (long)(d.y_c4_off + g * d.y_c4_gstride) * d.y_cstride + er.out_row;
-      const float4* rp = reinterpret_cast<const float4*>(d.res) + (long)(d.res_c4_off + g * d.res_c4_gstride) * d.res_cstride + er.out_row;
-      const float4* mp = reinterpret_cast<const float4*>(d.mask) + (long)(d.mask_c4_off + g * d.mask_c4_gstride) * d.mask_cstride + er.out_row;
-      const float4* bs4 = reinterpret_cast<const float4*>(d.bscale) + (long)er.b * (ctot >> 2) + g * (N >> 2);
+      // per-row base pointers; chunk n4 of the group is n4 * (chunk stride) further.  Rows outside the tensor read row 0
+      // (always mapped) so that the operand loads are unconditional and can all be in flight together.
+      const long orow = er.valid ? er.out_row : 0;
+      float4* yp = reinterpret_cast<float4*>(d.y) + (long)(d.y_c4_off + g * d.y_c4_gstride) * d.y_cstride + orow;
+      const float4* rp = reinterpret_cast<const float4*>(d.res) + (long)(d.res_c4_off + g * d.res_c4_gstride) * d.res_cstride + orow;
+      const float4* mp = reinterpret_cast<const float4*>(d.mask) + (long)(d.mask_c4_off + g * d.mask_c4_gstride) * d.mask_cstride + orow;
+      const float4* bs4 = reinterpret_cast<const float4*>(d.bscale) + (long)(er.valid ? er.b : 0) * (ctot >> 2) + g * (N >> 2);
       for (int cg = chalf; cg < N / 32; cg += 2) {
         uint32_t v[32];
         tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * N + cg * 32), v);
         // the residual / mask operands of these 8 chunks are fetched while the TMEM load is in flight
         float4 rr[8], mm[8];
+        {
+          const float4* rpc = rp + (long)(cg * 8) * d.res_cstride;
+          const float4* mpc = mp + (long)(cg * 8) * d.mask_cstride;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          rr[i] = f4zero();
-          mm[i] = f4zero();
-          if (er.valid) {
-            if (f_res) rr[i] = __ldg(rp + (long)(cg * 8 + i) * d.res_cstride);
-            if (mask_mode) mm[i] = __ldg(mp + (long)(cg * 8 + i) * d.mask_cstride);
+          for (int i = 0; i < 8; ++i) {
+            rr[i] = f_res ? __ldg(rpc) : f4zero();
+            mm[i] = mask_mode ? __ldg(mpc) : f4zero();
+            rpc += d.res_cstride;
+            mpc += d.mask_cstride;
           }
         }
         tmem_ld_wait();
@@ -302,7 +306,7 @@ __global__ void __launch_bounds__(FW_THREADS, 1) conv_tc_kernel(const __grid_con
             x.w = (((bits >> 48) & 0xffff) >= drop_thr) ? x.w * drop_sc : 0.f;
           }
           if (f_bscale) {
-            const float4 sc4 = er.valid ? __ldg(bs4 + n4) : make_float4(1.f, 1.f, 1.f, 1.f);
+            const float4 sc4 = __ldg(bs4 + n4);
             if (f_bsgrad) {  // forward was ys = relu(.) * s with the mask tensor = ys ; d s += x * ys / s
               const float4 m = mm[i];
               float4 bsg;
