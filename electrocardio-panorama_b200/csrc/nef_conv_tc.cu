@@ -130,6 +130,23 @@ struct FwSmem {
 // angular scale and its gradient, mask mode 2).  The specialised bodies are ~4x shorter, which matters: the epilogue runs
 // on 8 warps only and the generic body does not fit the instruction cache.
 constexpr int EPI_BIAS = 1, EPI_RES = 2, EPI_RELU = 4, EPI_DROP = 8, EPI_MASK1 = 16, EPI_ROUND = 32, EPI_GENERIC = 64;
+constexpr int EPI_MASK2 = 128, EPI_BSCALE = 256, EPI_STATS = 512;  // mask mode 2, angular scale, BatchNorm partial statistics
+
+// Sum over the 32 lanes of 32 per-lane values at once: after the 5 exchange levels lane j holds the warp total of a[j].
+// 31 shuffles instead of 32 x 5.
+__device__ __forceinline__ float warp_sum32(float (&a)[32], int lane) {
+#pragma unroll
+  for (int bit = 16; bit >= 1; bit >>= 1) {
+    const bool upper = (lane & bit) != 0;
+#pragma unroll
+    for (int i = 0; i < bit; ++i) {
+      const float send = upper ? a[i] : a[i + bit];
+      const float keep = upper ? a[i + bit] : a[i];
+      a[i] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+    }
+  }
+  return a[0];
+}
 
 __device__ __forceinline__ float4 rn4_tf32(float4 v) {
   uint32_t a, b, c, e;
@@ -244,14 +261,15 @@ __global__ void __launch_bounds__(FW_THREADS, 1) conv_tc_kernel(const __grid_con
     // ===== epilogue: 8 warps; warp w owns TMEM lanes 32 * (w % 4) .. + 31 and the 32-column groups cg = (w - 2) / 4 (mod 2)
     const int q = warp & 3, chalf = (warp - 2) >> 2;
     constexpr bool GEN = (EPI & EPI_GENERIC) != 0;
-    const bool want_stats = GEN && d.stat_sum != nullptr;
+    const bool want_stats = GEN ? d.stat_sum != nullptr : (EPI & EPI_STATS) != 0;
     const bool f_bias = GEN ? d.bias != nullptr : (EPI & EPI_BIAS) != 0;
     const bool f_res = GEN ? d.res != nullptr : (EPI & EPI_RES) != 0;
     const bool f_relu = GEN ? d.relu != 0 : (EPI & EPI_RELU) != 0;
     const bool f_drop = GEN ? d.drop_p > 0.f : (EPI & EPI_DROP) != 0;
     const bool f_round = GEN ? d.round_tf32 != 0 : (EPI & EPI_ROUND) != 0;
-    const bool f_bscale = GEN && d.bscale != nullptr, f_bsgrad = GEN && d.bscale_grad != nullptr;
-    const int mask_mode = GEN ? d.mask_mode : ((EPI & EPI_MASK1) ? 1 : 0);
+    const bool f_bscale = GEN ? d.bscale != nullptr : (EPI & EPI_BSCALE) != 0;
+    const bool f_bsgrad = GEN && d.bscale_grad != nullptr;
+    const int mask_mode = GEN ? d.mask_mode : ((EPI & EPI_MASK1) ? 1 : ((EPI & EPI_MASK2) ? 2 : 0));
     const float mask_scale = d.mask_scale;
     const uint32_t drop_thr = (uint32_t)(d.drop_p * 65536.f);
     const float drop_sc = 1.f / (1.f - d.drop_p);
@@ -289,6 +307,7 @@ __global__ void __launch_bounds__(FW_THREADS, 1) conv_tc_kernel(const __grid_con
           }
         }
         tmem_ld_wait();
+        float st1[32], st2[32];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int n4 = cg * 8 + i;
@@ -343,13 +362,15 @@ __global__ void __launch_bounds__(FW_THREADS, 1) conv_tc_kernel(const __grid_con
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const float pv = er.valid ? f4get(pre, j) : 0.f;
-              const float s1 = warp_sum(pv), s2 = warp_sum(pv * pv);
-              if (lane == 0) {
-                s_stat[(q * 2 + 0) * 128 + n4 * 4 + j] = s1;
-                s_stat[(q * 2 + 1) * 128 + n4 * 4 + j] = s2;
-              }
+              st1[4 * i + j] = pv;
+              st2[4 * i + j] = pv * pv;
             }
           }
+        }
+        if (want_stats) {  // lane j ends up with the 32-row totals of channel cg * 32 + j
+          const float t1 = warp_sum32(st1, lane), t2 = warp_sum32(st2, lane);
+          s_stat[(q * 2 + 0) * 128 + cg * 32 + lane] = t1;
+          s_stat[(q * 2 + 1) * 128 + cg * 32 + lane] = t2;
         }
       }
       if (want_stats) {
@@ -598,7 +619,7 @@ using namespace nef;
 static int g_sm_count = 148;
 
 // the specialised epilogues instantiated for the 4-row-tile kernel (everything else takes the generic one)
-#define NEF_TC_EPI_LIST(X) X(0) X(2) X(32) X(33) X(36) X(37) X(38) X(44) X(48) X(50) X(64)
+#define NEF_TC_EPI_LIST(X) X(0) X(2) X(32) X(33) X(36) X(37) X(38) X(44) X(48) X(50) X(64) X(294) X(418) X(513)
 
 template <int MT, int EPI>
 static int tc_optin() {
@@ -621,8 +642,11 @@ extern "C" int nef_tc_init(void) {
 }
 
 static int epi_code(const NefConvDesc* d) {
-  if (d->stat_sum || d->bscale || d->bscale_grad || d->mask_mode == 2) return tc::EPI_GENERIC;
+  if (d->bscale_grad) return tc::EPI_GENERIC;
   int e = 0;
+  if (d->stat_sum) e |= tc::EPI_STATS;
+  if (d->bscale) e |= tc::EPI_BSCALE;
+  if (d->mask_mode == 2) e |= tc::EPI_MASK2;
   if (d->bias) e |= tc::EPI_BIAS;
   if (d->res) e |= tc::EPI_RES;
   if (d->relu) e |= tc::EPI_RELU;

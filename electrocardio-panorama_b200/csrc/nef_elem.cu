@@ -358,6 +358,34 @@ int roi_align_bwd(T4 dra, const int64_t* rois, T4 z2c, T4 gz2c, Window win, int 
   return 0;
 }
 
+__global__ void __launch_bounds__(128) bscale_grad_kernel(T4 gx, T4 ys, const float* __restrict__ scale, float* __restrict__ ds) {
+  __shared__ float4 red[4];
+  const int c4 = blockIdx.x, b = blockIdx.y;
+  const float4* gp = gx.at(c4, b, 0);
+  const float4* yp = ys.at(c4, b, 0);
+  float4 acc = f4zero();
+  for (int l = threadIdx.x; l < gx.L; l += 128) acc = acc + __ldg(gp + l) * __ldg(yp + l);
+  acc.x = warp_sum(acc.x); acc.y = warp_sum(acc.y); acc.z = warp_sum(acc.z); acc.w = warp_sum(acc.w);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const float4 t = (red[0] + red[1]) + (red[2] + red[3]);
+    const float4 sc = *reinterpret_cast<const float4*>(scale + (long)b * gx.C + c4 * 4);
+    float4 o;
+    o.x = sc.x != 0.f ? t.x / (sc.x * sc.x) : 0.f;
+    o.y = sc.y != 0.f ? t.y / (sc.y * sc.y) : 0.f;
+    o.z = sc.z != 0.f ? t.z / (sc.z * sc.z) : 0.f;
+    o.w = sc.w != 0.f ? t.w / (sc.w * sc.w) : 0.f;
+    *reinterpret_cast<float4*>(ds + (long)b * gx.C + c4 * 4) = o;
+  }
+}
+int bscale_grad(T4 gx, T4 ys, const float* scale, float* ds, cudaStream_t s) {
+  dim3 grid(gx.C / 4, gx.B);
+  bscale_grad_kernel<<<grid, 128, 0, s>>>(gx, ys, scale, ds);
+  NEF_CHECK_LAUNCH("bscale_grad_kernel");
+  return 0;
+}
+
 __global__ void deinterleave2_kernel(T4 src, T4 even, T4 odd) {
   const long total = (long)(src.C / 4) * src.B * even.L;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {

@@ -38,7 +38,10 @@ int window_extract(T4 w, T4 xw, int G, Window win, cudaStream_t s);             
 int window_scatter(T4 gxw, T4 gw, int G, Window win, cudaStream_t s);                // -> z2 half of g_w, zeros elsewhere
 int roi_align_fwd(T4 z2c, const int64_t* rois, T4 ra, Window win, int L4, cudaStream_t s);
 int roi_align_bwd(T4 dra, const int64_t* rois, T4 z2c, T4 gz2c, Window win, int L4, cudaStream_t s);
-int deinterleave2(T4 src, T4 even, T4 odd, cudaStream_t s);                          // (C, 2n) -> 2 x (C, n)
+int deinterleave2(T4 src, T4 even, T4 odd, cudaStream_t s);
+// gradient of the angular scale s (model_nefnet.py:120-123): ys = relu(u) * s[b, c]; gx = d ys * s * (ys != 0)  ->
+//   ds[b, c] = sum_l d ys * relu(u) = sum_l gx * ys / s^2      (overwrites ds)
+int bscale_grad(T4 gx, T4 ys, const float* scale, float* ds, cudaStream_t s);                          // (C, 2n) -> 2 x (C, n)
 
 struct LatentArgs {
   T4 z1, z2o;             // (128G, L4), (896G, 32)

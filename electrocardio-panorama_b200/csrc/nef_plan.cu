@@ -26,6 +26,16 @@ static long long g_launches = 0;
 extern "C" void nef_count_launch(void) { __atomic_add_fetch(&g_launches, 1, __ATOMIC_RELAXED); }
 extern "C" int64_t nef_launch_count(void) { return (int64_t)__atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
 extern "C" int nef_version(void) { return NEF_ABI_VERSION; }
+extern "C" size_t nef_struct_size(int which) {
+  switch (which) {
+    case 0: return sizeof(NefConvTerm);
+    case 1: return sizeof(NefConvDesc);
+    case 2: return sizeof(NefWgradDesc);
+    case 3: return sizeof(NefForwardArgs);
+    case 4: return sizeof(NefBackwardArgs);
+    default: return 0;
+  }
+}
 
 extern "C" int nef_gconv_fwd_simt(const NefConvDesc* d, nef_stream_t s);
 extern "C" int nef_gconv_wgrad_simt(const NefWgradDesc* d, nef_stream_t s);
@@ -748,13 +758,13 @@ extern "C" int nef_backward(NefPlan* p, const NefBackwardArgs* a, nef_stream_t s
   }
   RUN(window_scatter(p->gxw, p->GA[2], G, p->win, s));
   // ---- w_conv: g_w = GA2, gh = GA0, result (grad of the unscaled last encoder output, pre-ReLU) = GA1
-  cudaMemsetAsync(p->ds_in, 0, (size_t)B * p->C1 * sizeof(float), s);
   {
     BlockBwd bb{{p->ey[2], 0, 32, p->hw, p->w, &p->wc[0], &p->wc[1], nullptr, nullptr, G}, p->GA[2], p->GA[0],
                 Gd[P_WCONV + 0], Gd[P_WCONV + 1], nullptr, nullptr};
     CD fin(G, 128, p->ey[2]);
-    fin.out(p->GA[1], 0, 32).bscale(p->s_in).bsgrad(p->ds_in).mask(p->ey[2], 0, 32, 2, 1.f).round();
+    fin.out(p->GA[1], 0, 32).bscale(p->s_in).mask(p->ey[2], 0, 32, 2, 1.f).round();
     RUN(block_bwd(bb, dp, fin, s));
+    RUN(bscale_grad(p->GA[1], p->ey[2], p->s_in, p->ds_in, s));
   }
   if (Gd[P_MLP1_W]) RUN(angular_bwd(p->thetas_in, p->ds_in, Gd[P_MLP1_W], Gd[P_MLP1_B], B * G, 128, s));
   // ---- encoder blocks 2, 1, 0

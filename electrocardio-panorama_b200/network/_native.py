@@ -67,6 +67,7 @@ SIGNATURES = {
     "nef_get_conv_impl": (C.c_int, []),
     "nef_set_exact_fp32": (C.c_int, [C.c_int]),
     "nef_launch_count": (C.c_int64, []),
+    "nef_struct_size": (C.c_size_t, [C.c_int]),
     "nef_param_count": (C.c_int, [C.c_int]),
     "nef_param_name": (C.c_char_p, [C.c_int, C.c_int]),
     "nef_param_numel": (C.c_int64, [C.c_int, C.c_int]),

@@ -44,6 +44,9 @@ int nef_get_conv_impl(void);
 int nef_set_exact_fp32(int on);
 /* Cumulative number of kernels this library has launched in this process (bench.py's gpu_launches). */
 int64_t nef_launch_count(void);
+/* sizeof() of the ABI structs as this library was compiled (0 NefConvTerm, 1 NefConvDesc, 2 NefWgradDesc,
+ * 3 NefForwardArgs, 4 NefBackwardArgs): lets a foreign-language binding verify its mirror. */
+size_t nef_struct_size(int which);
 
 /* ---- parameters (state_dict contract; model_nefnet.py:67-107) -------------------- */
 /* Number of state_dict entries for lead_num = G, their names (host strings), element counts.   */

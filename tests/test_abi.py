@@ -1,0 +1,88 @@
+"""The C-ABI boundary (include/nefnet_b200.h): the shared library loads without a GPU and exports every
+symbol the header declares; the ctypes mirror covers the same set; the parameter table matches the
+reference's state_dict contract.  No compute call is made here."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from oracle import nefnet_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "nefnet_b200.h")
+
+
+def _declared():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(nef_[a-z0-9_]+)\s*\(", src)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from network import _native as N
+    if not os.path.exists(N.LIB_PATH):
+        import __graft_entry__ as g
+        g.build()
+    return N.load()
+
+
+def test_header_declares_the_expected_surface():
+    names = _declared()
+    for must in ("nef_init", "nef_forward", "nef_backward", "nef_gen_ecg", "nef_gconv_fwd", "nef_gconv_wgrad",
+                 "nef_loss_fwd", "nef_loss_bwd", "nef_sgd_step", "nef_plan_create", "nef_plan_bind"):
+        assert must in names
+
+
+def test_library_exports_every_declared_symbol(lib):
+    raw = ctypes.CDLL(lib._name)
+    for name in _declared():
+        assert hasattr(raw, name), "libnefnet_b200.so does not export %s" % name
+
+
+def test_ctypes_mirror_covers_the_header():
+    from network import _native as N
+    assert sorted(N.SIGNATURES) == _declared()
+
+
+def test_struct_sizes_match_the_compiled_layout(lib):
+    """ctypes mirrors of the descriptor structs against sizeof() as the library was compiled."""
+    from network import _native as N
+    for which, cls in enumerate((N.NefConvTerm, N.NefConvDesc, N.NefWgradDesc, N.NefForwardArgs, N.NefBackwardArgs)):
+        assert ctypes.sizeof(cls) == lib.nef_struct_size(which), cls.__name__
+
+
+@pytest.mark.parametrize("G", [1, 3, 12])
+def test_parameter_table_is_the_reference_state_dict(lib, G):
+    shapes = O.param_shapes(G)
+    n = lib.nef_param_count(G)
+    assert n == len(shapes)
+    for i, (name, shape) in enumerate(shapes.items()):
+        assert lib.nef_param_name(G, i).decode() == name
+        numel = 1
+        for d in shape:
+            numel *= d
+        assert lib.nef_param_numel(G, i) == numel
+
+
+def test_module_state_dict_keys_and_shapes():
+    """The nn.Module mirror can be constructed (not run) on CPU; its state_dict is the reference's."""
+    import network
+    m = network.Model_nefnet(theta_encoder_len=1, lead_num=3)
+    sd = m.state_dict()
+    shapes = O.param_shapes(3)
+    assert list(sd.keys()) == list(shapes.keys())
+    for k, v in sd.items():
+        assert tuple(v.shape) == tuple(shapes[k]), k
+    with pytest.raises(ValueError):
+        network.Model_nefnet(theta_encoder_len=2, lead_num=3)
+
+
+def test_no_gpu_means_loud_failure():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from network import _native as N
+    with pytest.raises(RuntimeError):
+        N.init(0)
