@@ -78,6 +78,29 @@ __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Weight-stationary form: the B operand is latched in collector buffer b0 by ::fill and re-used by ::use / ::lastuse
+// without being read from shared memory again (B = one weight stage, shared by the MT row tiles of a CTA).
+//   mode 0 = fill, 1 = use, 2 = lastuse, 3 = fill and discard (no re-use)
+template <int MODE>
+__device__ __forceinline__ void mma_tf32_ws(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  if constexpr (MODE == 0) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.ws.cta_group::1.kind::tf32.collector::b0::fill [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(adesc),
+                 "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+  } else if constexpr (MODE == 1) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.ws.cta_group::1.kind::tf32.collector::b0::use [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(adesc),
+                 "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+  } else if constexpr (MODE == 2) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.ws.cta_group::1.kind::tf32.collector::b0::lastuse [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(adesc),
+                 "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+  } else {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.ws.cta_group::1.kind::tf32.collector::b0::discard [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(adesc),
+                 "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+  }
+}
 // 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread (thread = lane)
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
   asm volatile(
@@ -106,6 +129,17 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, 
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// phase timestamps of the first CTAs of the last conv launch (profiling aid, read by nef_tc_debug_dump)
+__device__ unsigned long long g_tc_dbg[1024][8];
+__device__ __forceinline__ void dbg_stamp(int slot) {
+  const int cta = blockIdx.x + gridDim.x * blockIdx.y;
+  if (cta < 1024) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_tc_dbg[cta][slot] = t;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // forward / data-gradient kernel
 // ---------------------------------------------------------------------------------------------
@@ -118,7 +152,10 @@ struct FwSmem {
   static constexpr int XROWS = MT * 128 + 8;          // rows per chunk in a stage (taps - 1 <= 6 extra)
   static constexpr int XPITCH = XROWS * 16;           // bytes between channel chunks
   static constexpr int XBYTES = 8 * XPITCH;           // one activation stage
-  static constexpr int WST_FIT = (227 * 1024 - 6144 - FW_XST * XBYTES) / FW_WBYTES;
+  // MT == 4: one CTA per SM (all 512 TMEM columns).  MT == 2: two CTAs per SM (256 columns each), so that one CTA's
+  // epilogue overlaps the other's main loop; each gets half of the shared memory.
+  static constexpr int BUDGET = (MT == 2 ? 113 : 227) * 1024;
+  static constexpr int WST_FIT = (BUDGET - 6144 - FW_XST * XBYTES) / FW_WBYTES;
   static constexpr int WST = WST_FIT > 6 ? 6 : WST_FIT;  // weight stages
   static constexpr int BAR_OFF = FW_XST * XBYTES + WST * FW_WBYTES;
   static constexpr int STAT_OFF = BAR_OFF + 256;
@@ -158,8 +195,20 @@ __device__ __forceinline__ float4 rn4_tf32(float4 v) {
 }
 
 template <int MT, int EPI>
-__global__ void __launch_bounds__(FW_THREADS, 1) conv_tc_kernel(const __grid_constant__ NefConvDesc d) {
+__global__ void __launch_bounds__(FW_THREADS, MT == 2 ? 2 : 1) conv_tc_kernel(const __grid_constant__ NefConvDesc d,
+                                                                              int first_wave, int stagger_cycles, int use_ws) {
   using S = FwSmem<MT>;
+  // Two CTAs share an SM (MT == 2) so that one's epilogue and pipeline fill overlap the other's main loop -- but CTAs
+  // launched together run in lock step (same duration), both in the main loop, then both in the epilogue.  The CTAs
+  // that take the second slot of each SM in the first wave therefore start half a CTA lifetime late; equal durations
+  // keep the two slots out of phase for the rest of the launch.
+  if (stagger_cycles > 0) {
+    const int cta = blockIdx.x + gridDim.x * blockIdx.y;
+    if (cta >= first_wave / 2 && cta < first_wave) {
+      const long long t0 = clock64();
+      while (clock64() - t0 < stagger_cycles) {}
+    }
+  }
   extern __shared__ __align__(128) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
   const uint32_t xs0 = sbase, ws0 = sbase + FW_XST * S::XBYTES, bar0 = sbase + S::BAR_OFF;
@@ -178,6 +227,7 @@ __global__ void __launch_bounds__(FW_THREADS, 1) conv_tc_kernel(const __grid_con
   const int N = d.N;
   constexpr uint32_t TM_COLS = MT * 128 <= 32 ? 32 : (MT * 128 <= 64 ? 64 : (MT * 128 <= 128 ? 128 : (MT * 128 <= 256 ? 256 : 512)));
 
+  if (tid == 0) dbg_stamp(0);
   if (tid == 0) {
     for (int i = 0; i < FW_XST; ++i) { mbar_init(full_x(i), 1); mbar_init(empty_x(i), 1); }
     for (int i = 0; i < S::WST; ++i) { mbar_init(full_w(i), 1); mbar_init(empty_w(i), 1); }
@@ -189,6 +239,7 @@ __global__ void __launch_bounds__(FW_THREADS, 1) conv_tc_kernel(const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  if (tid == 0) dbg_stamp(1);
 
   if (warp == 0) {
     // ===== copy producer (lane c copies channel chunk c of every activation stage, lane 0 the weight stages) =====
@@ -235,16 +286,31 @@ __global__ void __launch_bounds__(FW_THREADS, 1) conv_tc_kernel(const __grid_con
           mbar_wait(full_x(xs), xph);
           for (int tp = 0; tp < t.taps; ++tp) {
             mbar_wait(full_w(wst), wph);
+            if (accum == 0) dbg_stamp(2);
             tc_fence_after();
             const uint32_t xa = xs0 + xs * S::XBYTES + tp * 16;
             const uint32_t wa = ws0 + wst * FW_WBYTES;
-#pragma unroll
-            for (int mt = 0; mt < MT; ++mt) {
+            if (use_ws && MT > 1) {
 #pragma unroll
               for (int k8 = 0; k8 < 4; ++k8) {
-                const uint64_t ad = make_desc(xa + (2 * k8) * S::XPITCH + mt * 128 * 16, S::XPITCH, 128);
                 const uint64_t bd = make_desc(wa + (2 * k8) * N * 16, N * 16, 128);
-                mma_tf32(tmem + mt * N, ad, bd, idesc, accum | (uint32_t)k8);
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) {
+                  const uint64_t ad = make_desc(xa + (2 * k8) * S::XPITCH + mt * 128 * 16, S::XPITCH, 128);
+                  if (mt == 0) mma_tf32_ws<0>(tmem + mt * N, ad, bd, idesc, accum | (uint32_t)k8);
+                  else if (mt == MT - 1) mma_tf32_ws<2>(tmem + mt * N, ad, bd, idesc, accum | (uint32_t)k8);
+                  else mma_tf32_ws<1>(tmem + mt * N, ad, bd, idesc, accum | (uint32_t)k8);
+                }
+              }
+            } else {
+#pragma unroll
+              for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+                for (int k8 = 0; k8 < 4; ++k8) {
+                  const uint64_t ad = make_desc(xa + (2 * k8) * S::XPITCH + mt * 128 * 16, S::XPITCH, 128);
+                  const uint64_t bd = make_desc(wa + (2 * k8) * N * 16, N * 16, 128);
+                  mma_tf32(tmem + mt * N, ad, bd, idesc, accum | (uint32_t)k8);
+                }
               }
             }
             accum = 1;
@@ -256,6 +322,7 @@ __global__ void __launch_bounds__(FW_THREADS, 1) conv_tc_kernel(const __grid_con
         }
       }
       tc_commit(acc_full);
+      dbg_stamp(3);
     }
   } else {
     // ===== epilogue: 8 warps; warp w owns TMEM lanes 32 * (w % 4) .. + 31 and the 32-column groups cg = (w - 2) / 4 (mod 2)
@@ -278,6 +345,7 @@ __global__ void __launch_bounds__(FW_THREADS, 1) conv_tc_kernel(const __grid_con
     const float4* bias4 = reinterpret_cast<const float4*>(d.bias) + g * (N >> 2);
     mbar_wait(acc_full, 0);
     tc_fence_after();
+    if (tid == 64) dbg_stamp(4);
     for (int mt = 0; mt < MT; ++mt) {
       const long row = r0 + mt * 128 + q * 32 + lane;
       const EpiRow er = epi_row(d, row);
@@ -385,6 +453,7 @@ __global__ void __launch_bounds__(FW_THREADS, 1) conv_tc_kernel(const __grid_con
         asm volatile("bar.sync 1, 256;" ::: "memory");
       }
     }
+    if (tid == 64) dbg_stamp(5);
     tc_fence_before();
   }
   __syncthreads();
@@ -392,6 +461,7 @@ __global__ void __launch_bounds__(FW_THREADS, 1) conv_tc_kernel(const __grid_con
     tc_fence_after();
     tmem_dealloc(tmem, TM_COLS);
   }
+  if (tid == 0) dbg_stamp(6);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -617,6 +687,9 @@ __global__ void __launch_bounds__(256) bias_grad_kernel(const NefWgradDesc d, lo
 using namespace nef;
 
 static int g_sm_count = 148;
+static int g_tc_stagger = -1;  // first-wave start stagger in cycles; -1 = one estimated CTA lifetime (NEF_TC_STAGGER)
+static int g_tc_ws = 0;   // 1 = weight-stationary MMA form (NEF_TC_WS)
+static int g_tc_mt = 0;  // 0 = automatic; 4 forces four row tiles per CTA, one CTA per SM (NEF_TC_MT, for A/B measurements)
 
 // the specialised epilogues instantiated for the 4-row-tile kernel (everything else takes the generic one)
 #define NEF_TC_EPI_LIST(X) X(0) X(2) X(32) X(33) X(36) X(37) X(38) X(44) X(48) X(50) X(64) X(294) X(418) X(513)
@@ -629,9 +702,12 @@ static int tc_optin() {
 }
 
 extern "C" int nef_tc_init(void) {
-#define X(E) { int rc = tc_optin<4, E>(); if (rc) return rc; }
+#define X(E) { int rc = tc_optin<4, E>(); if (rc) return rc; rc = tc_optin<2, E>(); if (rc) return rc; }
   NEF_TC_EPI_LIST(X)
 #undef X
+  if (getenv("NEF_TC_MT")) g_tc_mt = atoi(getenv("NEF_TC_MT"));
+  if (getenv("NEF_TC_STAGGER")) g_tc_stagger = atoi(getenv("NEF_TC_STAGGER"));
+  if (getenv("NEF_TC_WS")) g_tc_ws = atoi(getenv("NEF_TC_WS"));
   { int rc = tc_optin<1, tc::EPI_GENERIC>(); if (rc) return rc; }
   cudaError_t e = cudaFuncSetAttribute(tc::wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::WG_TOTAL);
   NEF_REQUIRE(e == cudaSuccess, "nef_tc_init: wgrad_tc_kernel smem opt-in failed: %s", cudaGetErrorString(e));
@@ -656,23 +732,44 @@ static int epi_code(const NefConvDesc* d) {
   return e;
 }
 
-extern "C" int nef_gconv_fwd_tc(const NefConvDesc* d, nef_stream_t s) {
-  // small row spaces (the z2 deflection branch at small batch): one 128-row tile per CTA keeps the grid wide
-  const long tiles4 = (d->rows + 511) / 512;
-  if (tiles4 * d->groups >= g_sm_count) {
-    dim3 grid((unsigned)tiles4, (unsigned)d->groups);
-    switch (epi_code(d)) {
-#define X(E) case E: tc::conv_tc_kernel<4, E><<<grid, tc::FW_THREADS, tc::FwSmem<4>::TOTAL, (cudaStream_t)s>>>(*d); break;
-      NEF_TC_EPI_LIST(X)
+
+template <int MT>
+static int launch_conv_tc(const NefConvDesc* d, cudaStream_t s) {
+  dim3 grid((unsigned)((d->rows + MT * 128 - 1) / (MT * 128)), (unsigned)d->groups);
+  const int fw = g_sm_count * (MT == 2 ? 2 : 1);
+  // one CTA lifetime ~ (cycles of MMA work per row tile) * MT + epilogue; the stagger spans about one lifetime
+  long kw = 0;
+  for (int i = 0; i < d->n_terms; ++i) kw += (long)(d->term[i].cin_g / 8) * d->term[i].taps;
+  const int stg = MT != 2 ? 0 : (g_tc_stagger < 0 ? (int)((kw * (d->N / 2) * 1.3 + 14000) * MT / 2) : g_tc_stagger);
+  switch (epi_code(d)) {
+#define X(E) case E: tc::conv_tc_kernel<MT, E><<<grid, tc::FW_THREADS, tc::FwSmem<MT>::TOTAL, s>>>(*d, fw, stg, g_tc_ws); break;
+    NEF_TC_EPI_LIST(X)
 #undef X
-      default: tc::conv_tc_kernel<4, tc::EPI_GENERIC><<<grid, tc::FW_THREADS, tc::FwSmem<4>::TOTAL, (cudaStream_t)s>>>(*d); break;
-    }
-  } else {
+    default: tc::conv_tc_kernel<MT, tc::EPI_GENERIC><<<grid, tc::FW_THREADS, tc::FwSmem<MT>::TOTAL, s>>>(*d, fw, stg, g_tc_ws); break;
+  }
+  return 0;
+}
+
+extern "C" int nef_gconv_fwd_tc(const NefConvDesc* d, nef_stream_t s) {
+  const long tiles4 = (d->rows + 511) / 512, tiles2 = (d->rows + 255) / 256;
+  int mt = 1;  // small row spaces (the z2 deflection branch at small batch): one 128-row tile per CTA keeps the grid wide
+  if (tiles2 * d->groups >= 2L * g_sm_count) mt = 2;
+  if (g_tc_mt == 4 && tiles4 * d->groups >= g_sm_count) mt = 4;
+  if (mt == 2) launch_conv_tc<2>(d, (cudaStream_t)s);
+  else if (mt == 4) launch_conv_tc<4>(d, (cudaStream_t)s);
+  else {
     dim3 grid((unsigned)((d->rows + 127) / 128), (unsigned)d->groups);
-    tc::conv_tc_kernel<1, tc::EPI_GENERIC><<<grid, tc::FW_THREADS, tc::FwSmem<1>::TOTAL, (cudaStream_t)s>>>(*d);
+    tc::conv_tc_kernel<1, tc::EPI_GENERIC><<<grid, tc::FW_THREADS, tc::FwSmem<1>::TOTAL, (cudaStream_t)s>>>(*d, 0, 0, 0);
   }
   NEF_CHECK_LAUNCH("conv_tc_kernel");
   return 0;
+}
+
+// profiling aid: copies the phase timestamps (ns, %globaltimer) of the first n CTAs of the last conv launch
+extern "C" int nef_tc_debug_dump(unsigned long long* host_out, int n) {
+  if (n > 1024) n = 1024;
+  cudaDeviceSynchronize();
+  return cudaMemcpyFromSymbol(host_out, tc::g_tc_dbg, sizeof(unsigned long long) * 8 * n) == cudaSuccess ? 0 : 1;
 }
 
 extern "C" int nef_gconv_wgrad_tc(const NefWgradDesc* d, nef_stream_t s) {
