@@ -478,7 +478,8 @@ __global__ void __launch_bounds__(FW_THREADS, MT == 2 ? 2 : 1) conv_tc_kernel(co
 // start address advances by one unit plane per tap, exactly as the forward kernel advances by one row.
 //     D_tap[cout x cin] += dY^T[cout x (a,b)] . X^T[cin x (a + tap, b)]
 // ---------------------------------------------------------------------------------------------
-constexpr int WG_THREADS = 288;  // warps 0, 6, 7, 8: copy producers; warp 1: MMA issuer; warps 2..5: re-tiling + epilogue
+constexpr int WG_THREADS = 416;  // warps 0, 10, 11, 12: copy producers; warp 1: MMA issuer; warps 2..9: re-tiling + epilogue
+constexpr int WG_RT = 256;       // re-tiling threads
 constexpr int WG_KR = 32;                        // rows (= contraction length) per stage
 constexpr int WG_S = WG_KR / 4;                  // units per stage; unit a = rows a + WG_S * b
 constexpr int WG_YPITCH = WG_KR * 16;            // raw tiles: bytes between channel chunks
@@ -499,8 +500,11 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 }
 
 // grid: x = pass (taps [4*pass, 4*pass + 4)), y = row split, z = (group, cin tile)
+// swap != 0 (used when cin_g >= 128): the accumulators are transposed, D_tap[cin x cout] = X^T(+tap) . dY, so that the
+// operand shared by the taps of a K step (dY^T) is the B operand: it is latched by the weight-stationary MMA form
+// (collector::b0 fill / use / lastuse) and read from shared memory once per K step instead of once per tap.
 __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_constant__ NefWgradDesc d, int NT, long rows_per_split,
-                                                                 long rows_main) {
+                                                                 long rows_main, int swap) {
   extern __shared__ __align__(128) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
   const uint32_t tr0 = sbase + WG_NRAW * WG_RAW;
@@ -525,8 +529,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
   const uint32_t TM_COLS = 512;
 
   if (tid == 0) {
-    for (int i = 0; i < WG_NRAW; ++i) { mbar_init(raw_full(i), 4); mbar_init(raw_empty(i), 128); }
-    for (int i = 0; i < WG_NTR; ++i) { mbar_init(tr_full(i), 128); mbar_init(tr_empty(i), 1); }
+    for (int i = 0; i < WG_NRAW; ++i) { mbar_init(raw_full(i), 4); mbar_init(raw_empty(i), WG_RT); }
+    for (int i = 0; i < WG_NTR; ++i) { mbar_init(tr_full(i), WG_RT); mbar_init(tr_empty(i), 1); }
     mbar_init(acc_full, 1);
     fence_barrier_init();
   }
@@ -544,10 +548,10 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  if (warp == 0 || warp >= 6) {
+  if (warp == 0 || warp >= 10) {
     // ===== four copy-producer warps (a bulk copy is issued from the uniform datapath, one at a time per warp):
     //       producer pw stages chunks [8 pw, 8 pw + 8) of dY (lanes 0..7) and of X (lanes 8..15) =====
-    const int pw = warp == 0 ? 0 : warp - 5;
+    const int pw = warp == 0 ? 0 : warp - 9;
     const float4* yg = reinterpret_cast<const float4*>(d.dy) + (long)(d.dy_c4_off + g * d.dy_c4_gstride) * d.dy_cstride;
     const float4* xg = reinterpret_cast<const float4*>(d.x) + (long)(d.x_c4_off + g * d.x_c4_gstride + nt * xch) * d.x_cstride +
                        (d.tap_off + tap_base);
@@ -573,7 +577,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
   } else if (warp == 1) {
     // ===== MMA issuer =====
     if (lane == 0) {
-      const uint32_t idesc = make_idesc(128, NT, 0, 0);
+      const uint32_t idesc = swap ? make_idesc(128, d.cout_g, 0, 0) : make_idesc(128, NT, 0, 0);
+      const int dcols = swap ? d.cout_g : NT;  // TMEM columns per tap
       int u = 0, ph = 0;
       for (int it = 0; it < nstage; ++it) {
         mbar_wait(tr_full(u), ph);
@@ -581,10 +586,18 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
         const uint32_t ty = tr0 + u * WG_TR, tx = ty + WG_TY;
 #pragma unroll
         for (int ks = 0; ks < WG_S / 2; ++ks) {
-          const uint64_t ad = make_desc(ty + (2 * ks) * WG_LBO, WG_LBO, 128);
-          for (int tp = 0; tp < ntap; ++tp) {
-            const uint64_t bd = make_desc(tx + (2 * ks + tp) * WG_LBO, WG_LBO, 128);
-            mma_tf32(tmem + tp * NT, ad, bd, idesc, (uint32_t)(it | ks));
+          const uint64_t yd = make_desc(ty + (2 * ks) * WG_LBO, WG_LBO, 128);
+          const uint32_t acc = (uint32_t)(it | ks);
+          if (!swap) {
+            for (int tp = 0; tp < ntap; ++tp)
+              mma_tf32(tmem + tp * dcols, yd, make_desc(tx + (2 * ks + tp) * WG_LBO, WG_LBO, 128), idesc, acc);
+          } else if (ntap == 1) {
+            mma_tf32(tmem, make_desc(tx + (2 * ks) * WG_LBO, WG_LBO, 128), yd, idesc, acc);
+          } else {
+            mma_tf32_ws<0>(tmem, make_desc(tx + (2 * ks) * WG_LBO, WG_LBO, 128), yd, idesc, acc);
+            for (int tp = 1; tp < ntap - 1; ++tp)
+              mma_tf32_ws<1>(tmem + tp * dcols, make_desc(tx + (2 * ks + tp) * WG_LBO, WG_LBO, 128), yd, idesc, acc);
+            mma_tf32_ws<2>(tmem + (ntap - 1) * dcols, make_desc(tx + (2 * ks + ntap - 1) * WG_LBO, WG_LBO, 128), yd, idesc, acc);
           }
         }
         tc_commit(tr_empty(u));
@@ -592,40 +605,53 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
       }
       tc_commit(acc_full);
     }
-  } else if (warp < 6) {
-    // ===== warps 2..5: re-tile every stage into K-major core matrices, then drain the accumulators =====
-    const int e = tid - 64;  // 0..127
+  } else if (warp < 10) {
+    // ===== warps 2..9: re-tile every stage into K-major core matrices, then drain the accumulators =====
+    const int e = tid - 64;  // 0..255
     {
+      // the (chunk, unit) blocks of a thread are the same in every stage: byte offsets precomputed, -1 = none
+      int ysrc = -1, ydst = 0, xsrc[2] = {-1, -1}, xdst[2] = {0, 0};
+      if (e < ych * WG_S) {
+        const int c = e >> 3, a = e & 7;
+        ysrc = c * WG_YPITCH + a * 16;
+        ydst = a * WG_LBO + (4 * c) * 16;
+      }
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const int id = e + k * WG_RT;
+        if (id < xch * xunits) {
+          const int c = id / xunits, a = id - c * xunits;
+          xsrc[k] = 32 * WG_YPITCH + c * WG_XPITCH + a * 16;
+          xdst[k] = WG_TY + a * WG_LBO + (4 * c) * 16;
+        }
+      }
       int st = 0, rph = 0, u = 0, uph = 0;
       for (int it = 0; it < nstage; ++it) {
         mbar_wait(raw_full(st), rph);
+        const uint8_t* raw = smem + st * WG_RAW;
+        // all loads of the stage first (up to 12 x 16 bytes in flight per thread), then the transposed stores
+        float4 r[3][4];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const int so = k == 0 ? ysrc : xsrc[k - 1];
+          if (so >= 0) {
+            const float4* src = reinterpret_cast<const float4*>(raw + so);
+            r[k][0] = src[0]; r[k][1] = src[WG_S]; r[k][2] = src[2 * WG_S]; r[k][3] = src[3 * WG_S];
+          }
+        }
         mbar_wait(tr_empty(u), uph ^ 1);
         tc_fence_after();
-        const uint8_t* ys = smem + st * WG_RAW;
-        const uint8_t* xs = ys + 32 * WG_YPITCH;
-        uint8_t* ty = smem + WG_NRAW * WG_RAW + u * WG_TR;
-        uint8_t* tx = ty + WG_TY;
-        // dY: ych chunks x 8 units
-        for (int id = e; id < ych * WG_S; id += 128) {
-          const int c = id >> 3, a = id & 7;
-          const float4* src = reinterpret_cast<const float4*>(ys + c * WG_YPITCH) + a;
-          const float4 r0 = src[0], r1 = src[WG_S], r2 = src[2 * WG_S], r3 = src[3 * WG_S];
-          float4* dst = reinterpret_cast<float4*>(ty + a * WG_LBO + (4 * c) * 16);
-          dst[0] = make_float4(r0.x, r1.x, r2.x, r3.x);
-          dst[1] = make_float4(r0.y, r1.y, r2.y, r3.y);
-          dst[2] = make_float4(r0.z, r1.z, r2.z, r3.z);
-          dst[3] = make_float4(r0.w, r1.w, r2.w, r3.w);
-        }
-        // X: xch chunks x (8 + ntap - 1) units
-        for (int id = e; id < xch * xunits; id += 128) {
-          const int c = id / xunits, a = id - c * xunits;
-          const float4* src = reinterpret_cast<const float4*>(xs + c * WG_XPITCH) + a;
-          const float4 r0 = src[0], r1 = src[WG_S], r2 = src[2 * WG_S], r3 = src[3 * WG_S];
-          float4* dst = reinterpret_cast<float4*>(tx + a * WG_LBO + (4 * c) * 16);
-          dst[0] = make_float4(r0.x, r1.x, r2.x, r3.x);
-          dst[1] = make_float4(r0.y, r1.y, r2.y, r3.y);
-          dst[2] = make_float4(r0.z, r1.z, r2.z, r3.z);
-          dst[3] = make_float4(r0.w, r1.w, r2.w, r3.w);
+        uint8_t* tr = smem + WG_NRAW * WG_RAW + u * WG_TR;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const int so = k == 0 ? ysrc : xsrc[k - 1];
+          if (so >= 0) {
+            float4* dst = reinterpret_cast<float4*>(tr + (k == 0 ? ydst : xdst[k - 1]));
+            dst[0] = make_float4(r[k][0].x, r[k][1].x, r[k][2].x, r[k][3].x);
+            dst[1] = make_float4(r[k][0].y, r[k][1].y, r[k][2].y, r[k][3].y);
+            dst[2] = make_float4(r[k][0].z, r[k][1].z, r[k][2].z, r[k][3].z);
+            dst[3] = make_float4(r[k][0].w, r[k][1].w, r[k][2].w, r[k][3].w);
+          }
         }
         fence_proxy_async();
         mbar_arrive(tr_full(u));
@@ -636,18 +662,26 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
     }
     if (nstage > 0) {
       const int q = warp & 3;
-      const int m = q * 32 + lane;  // output channel within the group
+      const int lr = q * 32 + lane;  // accumulator row: output channel (cout) -- or input channel of this tile when swapped
+      const int dcols = swap ? d.cout_g : NT;
+      const int chalf = (warp - 2) >> 2;  // the two warps of a TMEM lane quarter take alternate 32-column groups
       mbar_wait(acc_full, 0);
       tc_fence_after();
       for (int tp = 0; tp < ntap; ++tp) {
-        for (int cg = 0; cg < NT / 32; ++cg) {
+        for (int cg = chalf; cg < dcols / 32; cg += 2) {
           uint32_t v[32];
-          tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(tp * NT + cg * 32), v);
+          tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(tp * dcols + cg * 32), v);
           tmem_ld_wait();
-          if (m < d.cout_g) {
-            float* dst = d.dw + (long)g * d.sg + (long)m * d.sm + (long)(nt * NT + cg * 32) * d.sn + (long)(tap_base + tp) * d.st;
+          if (!swap) {
+            if (lr < d.cout_g) {
+              float* dst = d.dw + (long)g * d.sg + (long)lr * d.sm + (long)(nt * NT + cg * 32) * d.sn + (long)(tap_base + tp) * d.st;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) atomicAdd(dst + (long)i * d.sn, __uint_as_float(v[i]));
+              for (int i = 0; i < 32; ++i) atomicAdd(dst + (long)i * d.sn, __uint_as_float(v[i]));
+            }
+          } else {
+            float* dst = d.dw + (long)g * d.sg + (long)(cg * 32) * d.sm + (long)(nt * NT + lr) * d.sn + (long)(tap_base + tp) * d.st;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) atomicAdd(dst + (long)i * d.sm, __uint_as_float(v[i]));
           }
         }
       }
@@ -689,6 +723,7 @@ using namespace nef;
 static int g_sm_count = 148;
 static int g_tc_stagger = -1;  // first-wave start stagger in cycles; -1 = one estimated CTA lifetime (NEF_TC_STAGGER)
 static int g_tc_ws = 0;   // 1 = weight-stationary MMA form (NEF_TC_WS)
+static int g_wg_swap = 1;  // transposed weight-gradient accumulators + weight-stationary MMA (NEF_WG_SWAP=0 disables)
 static int g_tc_mt = 0;  // 0 = automatic; 4 forces four row tiles per CTA, one CTA per SM (NEF_TC_MT, for A/B measurements)
 
 // the specialised epilogues instantiated for the 4-row-tile kernel (everything else takes the generic one)
@@ -708,6 +743,7 @@ extern "C" int nef_tc_init(void) {
   if (getenv("NEF_TC_MT")) g_tc_mt = atoi(getenv("NEF_TC_MT"));
   if (getenv("NEF_TC_STAGGER")) g_tc_stagger = atoi(getenv("NEF_TC_STAGGER"));
   if (getenv("NEF_TC_WS")) g_tc_ws = atoi(getenv("NEF_TC_WS"));
+  if (getenv("NEF_WG_SWAP")) g_wg_swap = atoi(getenv("NEF_WG_SWAP"));
   { int rc = tc_optin<1, tc::EPI_GENERIC>(); if (rc) return rc; }
   cudaError_t e = cudaFuncSetAttribute(tc::wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::WG_TOTAL);
   NEF_REQUIRE(e == cudaSuccess, "nef_tc_init: wgrad_tc_kernel smem opt-in failed: %s", cudaGetErrorString(e));
@@ -779,12 +815,13 @@ extern "C" int nef_gconv_wgrad_tc(const NefWgradDesc* d, nef_stream_t s) {
   const long nst_total = d->rows / tc::WG_KR;
   const long rows_main = nst_total * tc::WG_KR;
   if (nst_total > 0) {
-    const int passes = (d->taps + 3) / 4;
+    int passes = (d->taps + 3) / 4;
+    if (getenv("NEF_WG_ONEPASS")) passes = 1;  // timing experiment only (drops taps >= 4)
     const long tiles = (long)d->groups * (d->cin_g / NT) * passes;
     // row splits: the smallest count whose last wave is >= 90 % full (else the best seen), at most 64 per tile
     long best = 1;
     double best_eff = 0.0;
-    const long max_splits = nst_total < 64 ? nst_total : 64;
+    const long max_splits = nst_total < 2L * g_sm_count ? nst_total : 2L * g_sm_count;
     for (long sp = 1; sp <= max_splits; ++sp) {
       const long ctas = tiles * sp;
       const double eff = (double)ctas / (double)(((ctas + g_sm_count - 1) / g_sm_count) * g_sm_count);
@@ -794,7 +831,8 @@ extern "C" int nef_gconv_wgrad_tc(const NefWgradDesc* d, nef_stream_t s) {
     long st_per_split = (nst_total + best - 1) / best;
     const long splits = (nst_total + st_per_split - 1) / st_per_split;
     dim3 grid((unsigned)passes, (unsigned)splits, (unsigned)(d->groups * (d->cin_g / NT)));
-    tc::wgrad_tc_kernel<<<grid, tc::WG_THREADS, tc::WG_TOTAL, (cudaStream_t)s>>>(*d, NT, st_per_split * tc::WG_KR, rows_main);
+    tc::wgrad_tc_kernel<<<grid, tc::WG_THREADS, tc::WG_TOTAL, (cudaStream_t)s>>>(*d, NT, st_per_split * tc::WG_KR, rows_main,
+                                                                                     (d->cin_g >= 128 && g_wg_swap) ? 1 : 0);
     NEF_CHECK_LAUNCH("wgrad_tc_kernel");
   }
   if (rows_main < d->rows) {  // ragged tail (< 32 rows): CUDA-core kernel over [rows_main, rows), no bias term
