@@ -123,6 +123,22 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
   return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
          ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);
 }
+// The issue loop must stay short: a descriptor is (hi = SBO | version, lo = start address | LBO) and only the start
+// address changes between the MMAs of a stage, so lo words are formed once per stage and advanced by plain adds.
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo_bytes) { return ((saddr >> 4) & 0x3FFF) | ((lbo_bytes >> 4) << 16); }
+__device__ __forceinline__ uint64_t desc_of(uint32_t hi, uint32_t lo) {
+  uint64_t d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
+  return d;
+}
+constexpr uint32_t DESC_HI_SBO128 = (128u >> 4) | (1u << 14);  // SBO = 128 bytes, descriptor version 1, SWIZZLE_NONE
+// one lane of a converged warp (the lowest); the MMAs and their commits are issued under it so that the compiler keeps
+// the operands in uniform registers instead of serialising every MMA through a lane-election loop
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 // Instruction descriptor: fp32 accumulate, TF32 x TF32, M x N
 __host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
@@ -274,29 +290,30 @@ __global__ void __launch_bounds__(FW_THREADS, MT == 2 ? 2 : 1) conv_tc_kernel(co
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer (one thread) =====
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc(128, N, 0, 0);
-      int xs = 0, xph = 0, wst = 0, wph = 0;
-      uint32_t accum = 0;
-      for (int ti = 0; ti < d.n_terms; ++ti) {
-        const NefConvTerm& t = d.term[ti];
-        const int nkb = t.cin_g >> 5;
-        for (int kb = 0; kb < nkb; ++kb) {
-          mbar_wait(full_x(xs), xph);
-          for (int tp = 0; tp < t.taps; ++tp) {
-            mbar_wait(full_w(wst), wph);
-            if (accum == 0) dbg_stamp(2);
-            tc_fence_after();
-            const uint32_t xa = xs0 + xs * S::XBYTES + tp * 16;
-            const uint32_t wa = ws0 + wst * FW_WBYTES;
+    // ===== MMA issuer: the warp runs the (warp-uniform) control flow converged, one elected lane issues =====
+    const uint32_t idesc = make_idesc(128, N, 0, 0);
+    const uint32_t nb = 2u * (uint32_t)N;                    // descriptor units between two K = 8 steps of a weight stage
+    int xs = 0, xph = 0, wst = 0, wph = 0;
+    uint32_t accum = 0;
+    for (int ti = 0; ti < d.n_terms; ++ti) {
+      const NefConvTerm& t = d.term[ti];
+      const int nkb = t.cin_g >> 5;
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(full_x(xs), xph);
+        for (int tp = 0; tp < t.taps; ++tp) {
+          mbar_wait(full_w(wst), wph);
+          if (accum == 0 && lane == 0) dbg_stamp(2);
+          tc_fence_after();
+          const uint32_t xa = desc_lo(xs0 + xs * S::XBYTES + tp * 16, S::XPITCH);
+          const uint32_t wa = desc_lo(ws0 + wst * FW_WBYTES, (uint32_t)N * 16);
+          if (elect_one()) {
             if (use_ws && MT > 1) {
 #pragma unroll
               for (int k8 = 0; k8 < 4; ++k8) {
-                const uint64_t bd = make_desc(wa + (2 * k8) * N * 16, N * 16, 128);
+                const uint64_t bd = desc_of(DESC_HI_SBO128, wa + k8 * nb);
 #pragma unroll
                 for (int mt = 0; mt < MT; ++mt) {
-                  const uint64_t ad = make_desc(xa + (2 * k8) * S::XPITCH + mt * 128 * 16, S::XPITCH, 128);
+                  const uint64_t ad = desc_of(DESC_HI_SBO128, xa + k8 * 2 * (S::XPITCH >> 4) + mt * 128);
                   if (mt == 0) mma_tf32_ws<0>(tmem + mt * N, ad, bd, idesc, accum | (uint32_t)k8);
                   else if (mt == MT - 1) mma_tf32_ws<2>(tmem + mt * N, ad, bd, idesc, accum | (uint32_t)k8);
                   else mma_tf32_ws<1>(tmem + mt * N, ad, bd, idesc, accum | (uint32_t)k8);
@@ -306,24 +323,25 @@ __global__ void __launch_bounds__(FW_THREADS, MT == 2 ? 2 : 1) conv_tc_kernel(co
 #pragma unroll
               for (int mt = 0; mt < MT; ++mt) {
 #pragma unroll
-                for (int k8 = 0; k8 < 4; ++k8) {
-                  const uint64_t ad = make_desc(xa + (2 * k8) * S::XPITCH + mt * 128 * 16, S::XPITCH, 128);
-                  const uint64_t bd = make_desc(wa + (2 * k8) * N * 16, N * 16, 128);
-                  mma_tf32(tmem + mt * N, ad, bd, idesc, accum | (uint32_t)k8);
-                }
+                for (int k8 = 0; k8 < 4; ++k8)
+                  mma_tf32(tmem + mt * N, desc_of(DESC_HI_SBO128, xa + k8 * 2 * (S::XPITCH >> 4) + mt * 128),
+                           desc_of(DESC_HI_SBO128, wa + k8 * nb), idesc, accum | (uint32_t)k8);
               }
             }
-            accum = 1;
             tc_commit(empty_w(wst));
-            if (++wst == S::WST) { wst = 0; wph ^= 1; }
           }
-          tc_commit(empty_x(xs));
-          if (++xs == FW_XST) { xs = 0; xph ^= 1; }
+          __syncwarp();
+          accum = 1;
+          if (++wst == S::WST) { wst = 0; wph ^= 1; }
         }
+        if (elect_one()) tc_commit(empty_x(xs));
+        __syncwarp();
+        if (++xs == FW_XST) { xs = 0; xph ^= 1; }
       }
-      tc_commit(acc_full);
-      dbg_stamp(3);
     }
+    if (elect_one()) tc_commit(acc_full);
+    __syncwarp();
+    if (lane == 0) dbg_stamp(3);
   } else {
     // ===== epilogue: 8 warps; warp w owns TMEM lanes 32 * (w % 4) .. + 31 and the 32-column groups cg = (w - 2) / 4 (mod 2)
     const int q = warp & 3, chalf = (warp - 2) >> 2;
@@ -480,29 +498,33 @@ __global__ void __launch_bounds__(FW_THREADS, MT == 2 ? 2 : 1) conv_tc_kernel(co
 // ---------------------------------------------------------------------------------------------
 constexpr int WG_THREADS = 416;  // warps 0, 10, 11, 12: copy producers; warp 1: MMA issuer; warps 2..9: re-tiling + epilogue
 constexpr int WG_RT = 256;       // re-tiling threads
-constexpr int WG_KR = 32;                        // rows (= contraction length) per stage
-constexpr int WG_S = WG_KR / 4;                  // units per stage; unit a = rows a + WG_S * b
-constexpr int WG_YPITCH = WG_KR * 16;            // raw tiles: bytes between channel chunks
-constexpr int WG_XROWS = WG_KR + 8;
-constexpr int WG_XPITCH = WG_XROWS * 16;
+constexpr int WG_KR = 32;                        // rows (= contraction length) per re-tiled sub-stage
+constexpr int WG_S = WG_KR / 4;                  // units per sub-stage; unit a = rows a + WG_S * b
+constexpr int WG_RROWS = 64;                     // rows per raw (copy) stage = 2 sub-stages: 1 KB contiguous per chunk from HBM
+constexpr int WG_YPITCH = WG_RROWS * 16;         // raw tiles: bytes between channel chunks
+constexpr int WG_XPITCH = (WG_RROWS + 8) * 16;
 constexpr int WG_RAW = 32 * WG_YPITCH + 32 * WG_XPITCH;   // one raw stage (128 + 128 channels)
-constexpr int WG_NRAW = 3;
+constexpr int WG_NRAW = 2;
 constexpr int WG_LBO = 128 * 16 + 16;            // transposed tiles: bytes between unit planes (+16: conflict-free stores)
 constexpr int WG_TY = WG_S * WG_LBO;             // dY^T: units [0, 8)
-constexpr int WG_XUNITS = WG_S + 3;              // X^T: units [0, 8 + taps_per_pass - 1)
+constexpr int WG_XUNITS = WG_S + 6;              // X^T: units [0, 8 + taps - 1)
 constexpr int WG_TR = WG_TY + WG_XUNITS * WG_LBO;
 constexpr int WG_NTR = 2;
 constexpr int WG_BAR_OFF = WG_NRAW * WG_RAW + WG_NTR * WG_TR;
 constexpr int WG_TOTAL = WG_BAR_OFF + 128;
+static_assert(WG_TOTAL <= 227 * 1024, "wgrad shared memory");
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
-// grid: x = pass (taps [4*pass, 4*pass + 4)), y = row split, z = (group, cin tile)
-// swap != 0 (used when cin_g >= 128): the accumulators are transposed, D_tap[cin x cout] = X^T(+tap) . dY, so that the
-// operand shared by the taps of a K step (dY^T) is the B operand: it is latched by the weight-stationary MMA form
-// (collector::b0 fill / use / lastuse) and read from shared memory once per K step instead of once per tap.
+// Two orientations.
+//  swap == 0 (cin_g == 64):  D_tap[cout x cin] = dY^T . X(+tap)     M = cout (64 is zero-padded to 128), N = cin tile, <= 4 taps
+//  swap == 1 (cin_g >= 128): D_tap[cin x cout_half] = X^T(+tap) . dY M = cin tile of 128, N = 64 output channels, ALL taps
+//     (<= 7 x 64 = 448 TMEM columns), so every row of X and dY is staged once per CTA; the operand shared by the taps of a
+//     K step (dY^T) is the B operand and is latched by the weight-stationary MMA form (collector::b0 fill/use/lastuse).
+//     The two CTAs that take the two halves of the output channels do identical work on the same rows of X.
+// grid: x = output-channel half (swap) or 0, y = row split, z = (group, cin tile)
 __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_constant__ NefWgradDesc d, int NT, long rows_per_split,
                                                                  long rows_main, int swap) {
   extern __shared__ __align__(128) uint8_t smem[];
@@ -519,12 +541,15 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int ntile = d.cin_g / NT;
   const int g = blockIdx.z / ntile, nt = blockIdx.z % ntile;
-  const int tap_base = blockIdx.x * 4;
-  const int ntap = min(4, d.taps - tap_base);
+  const int ntap = d.taps;
+  const int half = blockIdx.x;                       // swap: output channels [64 half, 64 half + 64)
+  const int ych = swap ? 16 : (d.cout_g >> 2);       // dY chunks staged
+  const int ych0 = swap ? half * 16 : 0;             // first dY chunk staged
+  const int xch = NT >> 2;
+  const int dcols = swap ? 64 : NT;                  // accumulator columns per tap
   const long rbeg = (long)blockIdx.y * rows_per_split;
   const long rend = min(rows_main, rbeg + rows_per_split);
-  const int nstage = (int)((rend - rbeg) / WG_KR);
-  const int ych = d.cout_g >> 2, xch = NT >> 2;  // chunks loaded per stage
+  const int nstage = (int)((rend - rbeg) / WG_RROWS);
   const int xunits = WG_S + ntap - 1;
   const uint32_t TM_COLS = 512;
 
@@ -534,7 +559,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
     mbar_init(acc_full, 1);
     fence_barrier_init();
   }
-  if (ych < 32) {  // cout_g == 64: channels 64..127 of the M = 128 operand are zero (never written afterwards)
+  if (!swap && ych < 32) {  // cout_g == 64: channels 64..127 of the M = 128 operand are zero (never written afterwards)
     for (int u = 0; u < WG_NTR; ++u)
       for (int i = tid; i < WG_S * 64; i += WG_THREADS) {
         const int a = i >> 6, c = 64 + (i & 63);
@@ -552,15 +577,14 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
     // ===== four copy-producer warps (a bulk copy is issued from the uniform datapath, one at a time per warp):
     //       producer pw stages chunks [8 pw, 8 pw + 8) of dY (lanes 0..7) and of X (lanes 8..15) =====
     const int pw = warp == 0 ? 0 : warp - 9;
-    const float4* yg = reinterpret_cast<const float4*>(d.dy) + (long)(d.dy_c4_off + g * d.dy_c4_gstride) * d.dy_cstride;
-    const float4* xg = reinterpret_cast<const float4*>(d.x) + (long)(d.x_c4_off + g * d.x_c4_gstride + nt * xch) * d.x_cstride +
-                       (d.tap_off + tap_base);
-    const uint32_t xbytes = (uint32_t)(WG_KR + ntap - 1) * 16;
+    const float4* yg = reinterpret_cast<const float4*>(d.dy) + (long)(d.dy_c4_off + g * d.dy_c4_gstride + ych0) * d.dy_cstride;
+    const float4* xg = reinterpret_cast<const float4*>(d.x) + (long)(d.x_c4_off + g * d.x_c4_gstride + nt * xch) * d.x_cstride + d.tap_off;
+    const uint32_t xbytes = (uint32_t)(WG_RROWS + ntap - 1) * 16;
     const int c = pw * 8 + (lane & 7);
     const int ny = min(max(ych - pw * 8, 0), 8), nx = min(max(xch - pw * 8, 0), 8);
     int st = 0, ph = 0;
     for (int it = 0; it < nstage; ++it) {
-      const long r = rbeg + (long)it * WG_KR;
+      const long r = rbeg + (long)it * WG_RROWS;
       if (lane == 0) {
         mbar_wait(raw_empty(st), ph ^ 1);
         mbar_expect_tx(raw_full(st), (uint32_t)ny * WG_YPITCH + (uint32_t)nx * xbytes);
@@ -575,41 +599,46 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
       if (++st == WG_NRAW) { st = 0; ph ^= 1; }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
-      const uint32_t idesc = swap ? make_idesc(128, d.cout_g, 0, 0) : make_idesc(128, NT, 0, 0);
-      const int dcols = swap ? d.cout_g : NT;  // TMEM columns per tap
-      int u = 0, ph = 0;
-      for (int it = 0; it < nstage; ++it) {
-        mbar_wait(tr_full(u), ph);
-        tc_fence_after();
-        const uint32_t ty = tr0 + u * WG_TR, tx = ty + WG_TY;
+    // ===== MMA issuer: converged warp, one elected lane issues (see the forward kernel) =====
+    const uint32_t idesc = make_idesc(128, dcols, 0, 0);
+    constexpr uint32_t UNIT = WG_LBO >> 4;  // descriptor units per K group plane
+    int u = 0, ph = 0;
+    for (int it = 0; it < 2 * nstage; ++it) {
+      mbar_wait(tr_full(u), ph);
+      tc_fence_after();
+      const uint32_t ty = desc_lo(tr0 + u * WG_TR, WG_LBO), tx = desc_lo(tr0 + u * WG_TR + WG_TY, WG_LBO);
+      if (elect_one()) {
 #pragma unroll
         for (int ks = 0; ks < WG_S / 2; ++ks) {
-          const uint64_t yd = make_desc(ty + (2 * ks) * WG_LBO, WG_LBO, 128);
+          const uint64_t yd = desc_of(DESC_HI_SBO128, ty + 2 * ks * UNIT);
+          const uint32_t xk = tx + 2 * ks * UNIT;
           const uint32_t acc = (uint32_t)(it | ks);
           if (!swap) {
-            for (int tp = 0; tp < ntap; ++tp)
-              mma_tf32(tmem + tp * dcols, yd, make_desc(tx + (2 * ks + tp) * WG_LBO, WG_LBO, 128), idesc, acc);
+#pragma unroll
+            for (int tp = 0; tp < 4; ++tp)
+              if (tp < ntap) mma_tf32(tmem + tp * dcols, yd, desc_of(DESC_HI_SBO128, xk + tp * UNIT), idesc, acc);
           } else if (ntap == 1) {
-            mma_tf32(tmem, make_desc(tx + (2 * ks) * WG_LBO, WG_LBO, 128), yd, idesc, acc);
+            mma_tf32(tmem, desc_of(DESC_HI_SBO128, xk), yd, idesc, acc);
           } else {
-            mma_tf32_ws<0>(tmem, make_desc(tx + (2 * ks) * WG_LBO, WG_LBO, 128), yd, idesc, acc);
-            for (int tp = 1; tp < ntap - 1; ++tp)
-              mma_tf32_ws<1>(tmem + tp * dcols, make_desc(tx + (2 * ks + tp) * WG_LBO, WG_LBO, 128), yd, idesc, acc);
-            mma_tf32_ws<2>(tmem + (ntap - 1) * dcols, make_desc(tx + (2 * ks + ntap - 1) * WG_LBO, WG_LBO, 128), yd, idesc, acc);
+            mma_tf32_ws<0>(tmem, desc_of(DESC_HI_SBO128, xk), yd, idesc, acc);
+#pragma unroll
+            for (int tp = 1; tp < 6; ++tp)
+              if (tp < ntap - 1) mma_tf32_ws<1>(tmem + tp * dcols, desc_of(DESC_HI_SBO128, xk + tp * UNIT), yd, idesc, acc);
+            mma_tf32_ws<2>(tmem + (ntap - 1) * dcols, desc_of(DESC_HI_SBO128, xk + (ntap - 1) * UNIT), yd, idesc, acc);
           }
         }
         tc_commit(tr_empty(u));
-        if (++u == WG_NTR) { u = 0; ph ^= 1; }
       }
-      tc_commit(acc_full);
+      __syncwarp();
+      if (++u == WG_NTR) { u = 0; ph ^= 1; }
     }
+    if (elect_one()) tc_commit(acc_full);
+    __syncwarp();
   } else if (warp < 10) {
-    // ===== warps 2..9: re-tile every stage into K-major core matrices, then drain the accumulators =====
+    // ===== warps 2..9: re-tile every sub-stage into K-major core matrices, then drain the accumulators =====
     const int e = tid - 64;  // 0..255
     {
-      // the (chunk, unit) blocks of a thread are the same in every stage: byte offsets precomputed, -1 = none
+      // the (chunk, unit) blocks of a thread are the same in every sub-stage: byte offsets precomputed, -1 = none
       int ysrc = -1, ydst = 0, xsrc[2] = {-1, -1}, xdst[2] = {0, 0};
       if (e < ych * WG_S) {
         const int c = e >> 3, a = e & 7;
@@ -628,42 +657,44 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
       int st = 0, rph = 0, u = 0, uph = 0;
       for (int it = 0; it < nstage; ++it) {
         mbar_wait(raw_full(st), rph);
-        const uint8_t* raw = smem + st * WG_RAW;
-        // all loads of the stage first (up to 12 x 16 bytes in flight per thread), then the transposed stores
-        float4 r[3][4];
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          const int so = k == 0 ? ysrc : xsrc[k - 1];
-          if (so >= 0) {
-            const float4* src = reinterpret_cast<const float4*>(raw + so);
-            r[k][0] = src[0]; r[k][1] = src[WG_S]; r[k][2] = src[2 * WG_S]; r[k][3] = src[3 * WG_S];
-          }
-        }
-        mbar_wait(tr_empty(u), uph ^ 1);
-        tc_fence_after();
-        uint8_t* tr = smem + WG_NRAW * WG_RAW + u * WG_TR;
+        for (int sub = 0; sub < 2; ++sub) {
+          const uint8_t* raw = smem + st * WG_RAW + sub * (WG_KR * 16);
+          // all loads of the sub-stage first (up to 12 x 16 bytes in flight per thread), then the transposed stores
+          float4 r[3][4];
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          const int so = k == 0 ? ysrc : xsrc[k - 1];
-          if (so >= 0) {
-            float4* dst = reinterpret_cast<float4*>(tr + (k == 0 ? ydst : xdst[k - 1]));
-            dst[0] = make_float4(r[k][0].x, r[k][1].x, r[k][2].x, r[k][3].x);
-            dst[1] = make_float4(r[k][0].y, r[k][1].y, r[k][2].y, r[k][3].y);
-            dst[2] = make_float4(r[k][0].z, r[k][1].z, r[k][2].z, r[k][3].z);
-            dst[3] = make_float4(r[k][0].w, r[k][1].w, r[k][2].w, r[k][3].w);
+          for (int k = 0; k < 3; ++k) {
+            const int so = k == 0 ? ysrc : xsrc[k - 1];
+            if (so >= 0) {
+              const float4* src = reinterpret_cast<const float4*>(raw + so);
+              r[k][0] = src[0]; r[k][1] = src[WG_S]; r[k][2] = src[2 * WG_S]; r[k][3] = src[3 * WG_S];
+            }
           }
+          mbar_wait(tr_empty(u), uph ^ 1);
+          tc_fence_after();
+          uint8_t* tr = smem + WG_NRAW * WG_RAW + u * WG_TR;
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            const int so = k == 0 ? ysrc : xsrc[k - 1];
+            if (so >= 0) {
+              float4* dst = reinterpret_cast<float4*>(tr + (k == 0 ? ydst : xdst[k - 1]));
+              dst[0] = make_float4(r[k][0].x, r[k][1].x, r[k][2].x, r[k][3].x);
+              dst[1] = make_float4(r[k][0].y, r[k][1].y, r[k][2].y, r[k][3].y);
+              dst[2] = make_float4(r[k][0].z, r[k][1].z, r[k][2].z, r[k][3].z);
+              dst[3] = make_float4(r[k][0].w, r[k][1].w, r[k][2].w, r[k][3].w);
+            }
+          }
+          fence_proxy_async();
+          mbar_arrive(tr_full(u));
+          if (sub == 1) mbar_arrive(raw_empty(st));   // both halves of the raw stage have been re-tiled
+          if (++u == WG_NTR) { u = 0; uph ^= 1; }
         }
-        fence_proxy_async();
-        mbar_arrive(tr_full(u));
-        mbar_arrive(raw_empty(st));
         if (++st == WG_NRAW) { st = 0; rph ^= 1; }
-        if (++u == WG_NTR) { u = 0; uph ^= 1; }
       }
     }
     if (nstage > 0) {
       const int q = warp & 3;
       const int lr = q * 32 + lane;  // accumulator row: output channel (cout) -- or input channel of this tile when swapped
-      const int dcols = swap ? d.cout_g : NT;
       const int chalf = (warp - 2) >> 2;  // the two warps of a TMEM lane quarter take alternate 32-column groups
       mbar_wait(acc_full, 0);
       tc_fence_after();
@@ -674,12 +705,12 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
           tmem_ld_wait();
           if (!swap) {
             if (lr < d.cout_g) {
-              float* dst = d.dw + (long)g * d.sg + (long)lr * d.sm + (long)(nt * NT + cg * 32) * d.sn + (long)(tap_base + tp) * d.st;
+              float* dst = d.dw + (long)g * d.sg + (long)lr * d.sm + (long)(nt * NT + cg * 32) * d.sn + (long)tp * d.st;
 #pragma unroll
               for (int i = 0; i < 32; ++i) atomicAdd(dst + (long)i * d.sn, __uint_as_float(v[i]));
             }
           } else {
-            float* dst = d.dw + (long)g * d.sg + (long)(cg * 32) * d.sm + (long)(nt * NT + lr) * d.sn + (long)(tap_base + tp) * d.st;
+            float* dst = d.dw + (long)g * d.sg + (long)(half * 64 + cg * 32) * d.sm + (long)(nt * NT + lr) * d.sn + (long)tp * d.st;
 #pragma unroll
             for (int i = 0; i < 32; ++i) atomicAdd(dst + (long)i * d.sm, __uint_as_float(v[i]));
           }
@@ -723,7 +754,6 @@ using namespace nef;
 static int g_sm_count = 148;
 static int g_tc_stagger = -1;  // first-wave start stagger in cycles; -1 = one estimated CTA lifetime (NEF_TC_STAGGER)
 static int g_tc_ws = 0;   // 1 = weight-stationary MMA form (NEF_TC_WS)
-static int g_wg_swap = 1;  // transposed weight-gradient accumulators + weight-stationary MMA (NEF_WG_SWAP=0 disables)
 static int g_tc_mt = 0;  // 0 = automatic; 4 forces four row tiles per CTA, one CTA per SM (NEF_TC_MT, for A/B measurements)
 
 // the specialised epilogues instantiated for the 4-row-tile kernel (everything else takes the generic one)
@@ -743,7 +773,6 @@ extern "C" int nef_tc_init(void) {
   if (getenv("NEF_TC_MT")) g_tc_mt = atoi(getenv("NEF_TC_MT"));
   if (getenv("NEF_TC_STAGGER")) g_tc_stagger = atoi(getenv("NEF_TC_STAGGER"));
   if (getenv("NEF_TC_WS")) g_tc_ws = atoi(getenv("NEF_TC_WS"));
-  if (getenv("NEF_WG_SWAP")) g_wg_swap = atoi(getenv("NEF_WG_SWAP"));
   { int rc = tc_optin<1, tc::EPI_GENERIC>(); if (rc) return rc; }
   cudaError_t e = cudaFuncSetAttribute(tc::wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::WG_TOTAL);
   NEF_REQUIRE(e == cudaSuccess, "nef_tc_init: wgrad_tc_kernel smem opt-in failed: %s", cudaGetErrorString(e));
@@ -812,13 +841,14 @@ extern "C" int nef_gconv_wgrad_tc(const NefWgradDesc* d, nef_stream_t s) {
   NEF_REQUIRE(d->cout_g == 64 || d->cout_g == 128, "nef_gconv_wgrad_tc: cout_g must be 64 or 128 (got %d)", d->cout_g);
   const int NT = d->cin_g >= 128 ? 128 : 64;
   NEF_REQUIRE(d->cin_g % NT == 0, "nef_gconv_wgrad_tc: cin_g must be 64 or a multiple of 128 (got %d)", d->cin_g);
-  const long nst_total = d->rows / tc::WG_KR;
-  const long rows_main = nst_total * tc::WG_KR;
+  const int swap = d->cin_g >= 128 ? 1 : 0;
+  NEF_REQUIRE(swap ? d->taps <= 7 : d->taps <= 4, "nef_gconv_wgrad_tc: at most %d taps here (got %d)", swap ? 7 : 4, d->taps);
+  const long nst_total = d->rows / tc::WG_RROWS;
+  const long rows_main = nst_total * tc::WG_RROWS;
   if (nst_total > 0) {
-    int passes = (d->taps + 3) / 4;
-    if (getenv("NEF_WG_ONEPASS")) passes = 1;  // timing experiment only (drops taps >= 4)
-    const long tiles = (long)d->groups * (d->cin_g / NT) * passes;
-    // row splits: the smallest count whose last wave is >= 90 % full (else the best seen), at most 64 per tile
+    const int halves = swap ? d->cout_g / 64 : 1;
+    const long tiles = (long)d->groups * (d->cin_g / NT) * halves;
+    // row splits: the smallest count whose last wave is >= 90 % full (else the best seen)
     long best = 1;
     double best_eff = 0.0;
     const long max_splits = nst_total < 2L * g_sm_count ? nst_total : 2L * g_sm_count;
@@ -830,12 +860,11 @@ extern "C" int nef_gconv_wgrad_tc(const NefWgradDesc* d, nef_stream_t s) {
     }
     long st_per_split = (nst_total + best - 1) / best;
     const long splits = (nst_total + st_per_split - 1) / st_per_split;
-    dim3 grid((unsigned)passes, (unsigned)splits, (unsigned)(d->groups * (d->cin_g / NT)));
-    tc::wgrad_tc_kernel<<<grid, tc::WG_THREADS, tc::WG_TOTAL, (cudaStream_t)s>>>(*d, NT, st_per_split * tc::WG_KR, rows_main,
-                                                                                     (d->cin_g >= 128 && g_wg_swap) ? 1 : 0);
+    dim3 grid((unsigned)halves, (unsigned)splits, (unsigned)(d->groups * (d->cin_g / NT)));
+    tc::wgrad_tc_kernel<<<grid, tc::WG_THREADS, tc::WG_TOTAL, (cudaStream_t)s>>>(*d, NT, st_per_split * tc::WG_RROWS, rows_main, swap);
     NEF_CHECK_LAUNCH("wgrad_tc_kernel");
   }
-  if (rows_main < d->rows) {  // ragged tail (< 32 rows): CUDA-core kernel over [rows_main, rows), no bias term
+  if (rows_main < d->rows) {  // ragged tail (< 64 rows): CUDA-core kernel over [rows_main, rows), no bias term
     NefWgradDesc t = *d;
     t.db = nullptr;
     int rc = nef_gconv_wgrad_simt_range(&t, rows_main, s);
