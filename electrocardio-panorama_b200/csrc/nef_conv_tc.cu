@@ -101,6 +101,24 @@ __device__ __forceinline__ void mma_tf32_ws(uint32_t tmem_d, uint64_t adesc, uin
                  "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
   }
 }
+// A-operand re-use: the A tile is latched in the collector by ::fill and re-used by ::use / ::lastuse (same encoding of
+// MODE as above) -- for consecutive MMAs that share A (the taps of a weight-gradient K step share dY^T).
+template <int MODE>
+__device__ __forceinline__ void mma_tf32_areuse(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  if constexpr (MODE == 0) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::tf32.collector::a::fill [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(adesc),
+                 "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+  } else if constexpr (MODE == 1) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::tf32.collector::a::use [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(adesc),
+                 "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+  } else {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::tf32.collector::a::lastuse [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(adesc),
+                 "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+  }
+}
 // 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread (thread = lane)
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
   asm volatile(
@@ -518,13 +536,15 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
-// Two orientations.
-//  swap == 0 (cin_g == 64):  D_tap[cout x cin] = dY^T . X(+tap)     M = cout (64 is zero-padded to 128), N = cin tile, <= 4 taps
-//  swap == 1 (cin_g >= 128): D_tap[cin x cout_half] = X^T(+tap) . dY M = cin tile of 128, N = 64 output channels, ALL taps
-//     (<= 7 x 64 = 448 TMEM columns), so every row of X and dY is staged once per CTA; the operand shared by the taps of a
-//     K step (dY^T) is the B operand and is latched by the weight-stationary MMA form (collector::b0 fill/use/lastuse).
-//     The two CTAs that take the two halves of the output channels do identical work on the same rows of X.
-// grid: x = output-channel half (swap) or 0, y = row split, z = (group, cin tile)
+// Every CTA accumulates ALL taps (<= 7) of a 128 x 64 block of the weight gradient (7 x 64 = 448 TMEM columns), so
+// each row of X and dY is staged once per CTA.  Two orientations:
+//  swap == 0 (cout_g == 128, or 64 x 64):  D_tap[cout x cin_half] = dY^T . X(+tap)   M = cout (64 is zero-padded to 128),
+//     N = 64 input channels; the taps of a K step share the A operand (dY^T): collector::a fill / use / lastuse, so the
+//     MMAs are not bound by re-reading A from shared memory (N = 64 alone would be: tools/probe_rate.cu, 48 vs 32 cycles)
+//  swap == 1 (cout_g == 64, cin_g >= 128): D_tap[cin_tile x cout] = X^T(+tap) . dY   M = 128 input channels, N = 64; the
+//     shared operand is B: weight-stationary form (collector::b0)
+// CTAs that take different 64-channel halves do identical work on the same rows of the shared operand (L2 serves it).
+// grid: x = input-channel half (swap == 0), y = row split, z = group (x cin tile of 128 when swap == 1)
 __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_constant__ NefWgradDesc d, int NT, long rows_per_split,
                                                                  long rows_main, int swap) {
   extern __shared__ __align__(128) uint8_t smem[];
@@ -539,14 +559,15 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + WG_BAR_OFF + 8 * (2 * WG_NRAW + 2 * WG_NTR + 1));
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int ntile = d.cin_g / NT;
+  const int ntile = swap ? d.cin_g / 128 : 1;
   const int g = blockIdx.z / ntile, nt = blockIdx.z % ntile;
   const int ntap = d.taps;
-  const int half = blockIdx.x;                       // swap: output channels [64 half, 64 half + 64)
-  const int ych = swap ? 16 : (d.cout_g >> 2);       // dY chunks staged
-  const int ych0 = swap ? half * 16 : 0;             // first dY chunk staged
-  const int xch = NT >> 2;
-  const int dcols = swap ? 64 : NT;                  // accumulator columns per tap
+  const int half = blockIdx.x;                       // swap == 0: input channels [64 half, 64 half + 64)
+  const int ych = d.cout_g >> 2;                     // dY chunks staged (all output channels of the group)
+  const int xch = swap ? 32 : 16;                    // X chunks staged
+  const int xch0 = swap ? nt * 32 : half * 16;       // first X chunk staged
+  constexpr int dcols = 64;                          // accumulator columns per tap
+  (void)NT;
   const long rbeg = (long)blockIdx.y * rows_per_split;
   const long rend = min(rows_main, rbeg + rows_per_split);
   const int nstage = (int)((rend - rbeg) / WG_RROWS);
@@ -577,8 +598,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
     // ===== four copy-producer warps (a bulk copy is issued from the uniform datapath, one at a time per warp):
     //       producer pw stages chunks [8 pw, 8 pw + 8) of dY (lanes 0..7) and of X (lanes 8..15) =====
     const int pw = warp == 0 ? 0 : warp - 9;
-    const float4* yg = reinterpret_cast<const float4*>(d.dy) + (long)(d.dy_c4_off + g * d.dy_c4_gstride + ych0) * d.dy_cstride;
-    const float4* xg = reinterpret_cast<const float4*>(d.x) + (long)(d.x_c4_off + g * d.x_c4_gstride + nt * xch) * d.x_cstride + d.tap_off;
+    const float4* yg = reinterpret_cast<const float4*>(d.dy) + (long)(d.dy_c4_off + g * d.dy_c4_gstride) * d.dy_cstride;
+    const float4* xg = reinterpret_cast<const float4*>(d.x) + (long)(d.x_c4_off + g * d.x_c4_gstride + xch0) * d.x_cstride + d.tap_off;
     const uint32_t xbytes = (uint32_t)(WG_RROWS + ntap - 1) * 16;
     const int c = pw * 8 + (lane & 7);
     const int ny = min(max(ych - pw * 8, 0), 8), nx = min(max(xch - pw * 8, 0), 8);
@@ -613,12 +634,15 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
           const uint64_t yd = desc_of(DESC_HI_SBO128, ty + 2 * ks * UNIT);
           const uint32_t xk = tx + 2 * ks * UNIT;
           const uint32_t acc = (uint32_t)(it | ks);
-          if (!swap) {
+          if (ntap == 1) {
+            if (!swap) mma_tf32(tmem, yd, desc_of(DESC_HI_SBO128, xk), idesc, acc);
+            else mma_tf32(tmem, desc_of(DESC_HI_SBO128, xk), yd, idesc, acc);
+          } else if (!swap) {
+            mma_tf32_areuse<0>(tmem, yd, desc_of(DESC_HI_SBO128, xk), idesc, acc);
 #pragma unroll
-            for (int tp = 0; tp < 4; ++tp)
-              if (tp < ntap) mma_tf32(tmem + tp * dcols, yd, desc_of(DESC_HI_SBO128, xk + tp * UNIT), idesc, acc);
-          } else if (ntap == 1) {
-            mma_tf32(tmem, desc_of(DESC_HI_SBO128, xk), yd, idesc, acc);
+            for (int tp = 1; tp < 6; ++tp)
+              if (tp < ntap - 1) mma_tf32_areuse<1>(tmem + tp * dcols, yd, desc_of(DESC_HI_SBO128, xk + tp * UNIT), idesc, acc);
+            mma_tf32_areuse<2>(tmem + (ntap - 1) * dcols, yd, desc_of(DESC_HI_SBO128, xk + (ntap - 1) * UNIT), idesc, acc);
           } else {
             mma_tf32_ws<0>(tmem, desc_of(DESC_HI_SBO128, xk), yd, idesc, acc);
 #pragma unroll
@@ -705,12 +729,12 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
           tmem_ld_wait();
           if (!swap) {
             if (lr < d.cout_g) {
-              float* dst = d.dw + (long)g * d.sg + (long)lr * d.sm + (long)(nt * NT + cg * 32) * d.sn + (long)tp * d.st;
+              float* dst = d.dw + (long)g * d.sg + (long)lr * d.sm + (long)(half * 64 + cg * 32) * d.sn + (long)tp * d.st;
 #pragma unroll
               for (int i = 0; i < 32; ++i) atomicAdd(dst + (long)i * d.sn, __uint_as_float(v[i]));
             }
           } else {
-            float* dst = d.dw + (long)g * d.sg + (long)(half * 64 + cg * 32) * d.sm + (long)(nt * NT + lr) * d.sn + (long)tp * d.st;
+            float* dst = d.dw + (long)g * d.sg + (long)(cg * 32) * d.sm + (long)(nt * 128 + lr) * d.sn + (long)tp * d.st;
 #pragma unroll
             for (int i = 0; i < 32; ++i) atomicAdd(dst + (long)i * d.sm, __uint_as_float(v[i]));
           }
@@ -839,15 +863,16 @@ extern "C" int nef_tc_debug_dump(unsigned long long* host_out, int n) {
 
 extern "C" int nef_gconv_wgrad_tc(const NefWgradDesc* d, nef_stream_t s) {
   NEF_REQUIRE(d->cout_g == 64 || d->cout_g == 128, "nef_gconv_wgrad_tc: cout_g must be 64 or 128 (got %d)", d->cout_g);
-  const int NT = d->cin_g >= 128 ? 128 : 64;
-  NEF_REQUIRE(d->cin_g % NT == 0, "nef_gconv_wgrad_tc: cin_g must be 64 or a multiple of 128 (got %d)", d->cin_g);
-  const int swap = d->cin_g >= 128 ? 1 : 0;
-  NEF_REQUIRE(swap ? d->taps <= 7 : d->taps <= 4, "nef_gconv_wgrad_tc: at most %d taps here (got %d)", swap ? 7 : 4, d->taps);
+  NEF_REQUIRE(d->cin_g % 64 == 0 && d->taps <= 7, "nef_gconv_wgrad_tc: cin_g %% 64 == 0 and at most 7 taps required (cin_g=%d taps=%d)",
+              d->cin_g, d->taps);
+  const int swap = (d->cout_g == 64 && d->cin_g % 128 == 0) ? 1 : 0;
+  const int NT = swap ? 128 : 64;
   const long nst_total = d->rows / tc::WG_RROWS;
   const long rows_main = nst_total * tc::WG_RROWS;
   if (nst_total > 0) {
-    const int halves = swap ? d->cout_g / 64 : 1;
-    const long tiles = (long)d->groups * (d->cin_g / NT) * halves;
+    const int halves = swap ? 1 : d->cin_g / 64;
+    const int ztiles = swap ? d->groups * (d->cin_g / 128) : d->groups;
+    const long tiles = (long)ztiles * halves;
     // row splits: the smallest count whose last wave is >= 90 % full (else the best seen)
     long best = 1;
     double best_eff = 0.0;
@@ -860,7 +885,7 @@ extern "C" int nef_gconv_wgrad_tc(const NefWgradDesc* d, nef_stream_t s) {
     }
     long st_per_split = (nst_total + best - 1) / best;
     const long splits = (nst_total + st_per_split - 1) / st_per_split;
-    dim3 grid((unsigned)halves, (unsigned)splits, (unsigned)(d->groups * (d->cin_g / NT)));
+    dim3 grid((unsigned)halves, (unsigned)splits, (unsigned)ztiles);
     tc::wgrad_tc_kernel<<<grid, tc::WG_THREADS, tc::WG_TOTAL, (cudaStream_t)s>>>(*d, NT, st_per_split * tc::WG_RROWS, rows_main, swap);
     NEF_CHECK_LAUNCH("wgrad_tc_kernel");
   }
