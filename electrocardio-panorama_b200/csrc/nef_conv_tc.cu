@@ -34,6 +34,9 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done;
   do {
@@ -228,6 +231,139 @@ __device__ __forceinline__ float4 rn4_tf32(float4 v) {
   return make_float4(__uint_as_float(a), __uint_as_float(b), __uint_as_float(c), __uint_as_float(e));
 }
 
+// Epilogue of one CTA tile (MT row tiles of 128 x N output channels of group g, rows from r0), run by the 8 epilogue
+// warps: warp w owns TMEM lanes 32 * (w % 4) .. + 31 and the 32-column groups cg = (w - 2) / 4 (mod 2).
+// tmem_acc = TMEM address of the tile's first accumulator column.
+template <int MT, int EPI>
+__device__ __forceinline__ void epilogue_tile(const NefConvDesc& d, int g, long r0, uint32_t tmem, int warp, int lane, int tid,
+                                              float* s_stat) {
+  const int N = d.N;
+  const int q = warp & 3, chalf = (warp - 2) >> 2;
+  constexpr bool GEN = (EPI & EPI_GENERIC) != 0;
+  const bool want_stats = GEN ? d.stat_sum != nullptr : (EPI & EPI_STATS) != 0;
+  const bool f_bias = GEN ? d.bias != nullptr : (EPI & EPI_BIAS) != 0;
+  const bool f_res = GEN ? d.res != nullptr : (EPI & EPI_RES) != 0;
+  const bool f_relu = GEN ? d.relu != 0 : (EPI & EPI_RELU) != 0;
+  const bool f_drop = GEN ? d.drop_p > 0.f : (EPI & EPI_DROP) != 0;
+  const bool f_round = GEN ? d.round_tf32 != 0 : (EPI & EPI_ROUND) != 0;
+  const bool f_bscale = GEN ? d.bscale != nullptr : (EPI & EPI_BSCALE) != 0;
+  const bool f_bsgrad = GEN && d.bscale_grad != nullptr;
+  const int mask_mode = GEN ? d.mask_mode : ((EPI & EPI_MASK1) ? 1 : ((EPI & EPI_MASK2) ? 2 : 0));
+  const float mask_scale = d.mask_scale;
+  const uint32_t drop_thr = (uint32_t)(d.drop_p * 65536.f);
+  const float drop_sc = 1.f / (1.f - d.drop_p);
+  const long ctot = (long)d.groups * N;
+  const long n_rec = (d.rows + 127) / 128;
+  const float4* bias4 = reinterpret_cast<const float4*>(d.bias) + g * (N >> 2);
+  for (int mt = 0; mt < MT; ++mt) {
+    const long row = r0 + mt * 128 + q * 32 + lane;
+    const EpiRow er = epi_row(d, row);
+    const int b0 = __shfl_sync(0xffffffffu, er.b, 0);
+    const bool uniform_b = __all_sync(0xffffffffu, er.b == b0);
+    // per-row base pointers; chunk n4 of the group is n4 * (chunk stride) further.  Rows outside the tensor read row 0
+    // (always mapped) so that the operand loads are unconditional and can all be in flight together.
+    const long orow = er.valid ? er.out_row : 0;
+    float4* yp = reinterpret_cast<float4*>(d.y) + (long)(d.y_c4_off + g * d.y_c4_gstride) * d.y_cstride + orow;
+    const float4* rp = reinterpret_cast<const float4*>(d.res) + (long)(d.res_c4_off + g * d.res_c4_gstride) * d.res_cstride + orow;
+    const float4* mp = reinterpret_cast<const float4*>(d.mask) + (long)(d.mask_c4_off + g * d.mask_c4_gstride) * d.mask_cstride + orow;
+    const float4* bs4 = reinterpret_cast<const float4*>(d.bscale) + (long)(er.valid ? er.b : 0) * (ctot >> 2) + g * (N >> 2);
+    for (int cg = chalf; cg < N / 32; cg += 2) {
+      uint32_t v[32];
+      tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * N + cg * 32), v);
+      // the residual / mask operands of these 8 chunks are fetched while the TMEM load is in flight
+      float4 rr[8], mm[8];
+      {
+        const float4* rpc = rp + (long)(cg * 8) * d.res_cstride;
+        const float4* mpc = mp + (long)(cg * 8) * d.mask_cstride;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          rr[i] = f_res ? __ldg(rpc) : f4zero();
+          mm[i] = mask_mode ? __ldg(mpc) : f4zero();
+          rpc += d.res_cstride;
+          mpc += d.mask_cstride;
+        }
+      }
+      tmem_ld_wait();
+      float st1[32], st2[32];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int n4 = cg * 8 + i;
+        float4 x = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]),
+                               __uint_as_float(v[4 * i + 3]));
+        if (f_bias) x = x + __ldg(bias4 + n4);
+        x = x + rr[i];
+        const float4 pre = x;
+        if (f_relu) x = make_float4(fmaxf(x.x, 0.f), fmaxf(x.y, 0.f), fmaxf(x.z, 0.f), fmaxf(x.w, 0.f));
+        if (f_drop) {
+          const uint64_t bits = drop_bits(d.drop_seed, er.out_row, d.y_c4_off + g * d.y_c4_gstride + n4);
+          x.x = ((bits & 0xffff) >= drop_thr) ? x.x * drop_sc : 0.f;
+          x.y = (((bits >> 16) & 0xffff) >= drop_thr) ? x.y * drop_sc : 0.f;
+          x.z = (((bits >> 32) & 0xffff) >= drop_thr) ? x.z * drop_sc : 0.f;
+          x.w = (((bits >> 48) & 0xffff) >= drop_thr) ? x.w * drop_sc : 0.f;
+        }
+        if (f_bscale) {
+          const float4 sc4 = __ldg(bs4 + n4);
+          if (f_bsgrad) {  // forward was ys = relu(.) * s with the mask tensor = ys ; d s += x * ys / s
+            const float4 m = mm[i];
+            float4 bsg;
+            bsg.x = sc4.x != 0.f ? x.x * m.x / sc4.x : 0.f;
+            bsg.y = sc4.y != 0.f ? x.y * m.y / sc4.y : 0.f;
+            bsg.z = sc4.z != 0.f ? x.z * m.z / sc4.z : 0.f;
+            bsg.w = sc4.w != 0.f ? x.w * m.w / sc4.w : 0.f;
+            const long cbase = (long)g * N + n4 * 4;
+            if (uniform_b) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float s1 = warp_sum(er.valid ? f4get(bsg, j) : 0.f);
+                if (lane == 0 && s1 != 0.f) atomicAdd(d.bscale_grad + (long)b0 * ctot + cbase + j, s1);
+              }
+            } else if (er.valid) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) atomicAdd(d.bscale_grad + (long)er.b * ctot + cbase + j, f4get(bsg, j));
+            }
+          }
+          x = x * sc4;
+        }
+        if (mask_mode == 1) {
+          const float4 m = mm[i];
+          x = make_float4(m.x > 0.f ? x.x * mask_scale : 0.f, m.y > 0.f ? x.y * mask_scale : 0.f,
+                          m.z > 0.f ? x.z * mask_scale : 0.f, m.w > 0.f ? x.w * mask_scale : 0.f);
+        } else if (mask_mode == 2) {
+          const float4 m = mm[i];
+          x = make_float4(m.x != 0.f ? x.x * mask_scale : 0.f, m.y != 0.f ? x.y * mask_scale : 0.f,
+                          m.z != 0.f ? x.z * mask_scale : 0.f, m.w != 0.f ? x.w * mask_scale : 0.f);
+        }
+        if (f_round) x = rn4_tf32(x);
+        if (er.valid) yp[(long)n4 * d.y_cstride] = x;
+        if (want_stats) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float pv = er.valid ? f4get(pre, j) : 0.f;
+            st1[4 * i + j] = pv;
+            st2[4 * i + j] = pv * pv;
+          }
+        }
+      }
+      if (want_stats) {  // lane j ends up with the 32-row totals of channel cg * 32 + j
+        const float t1 = warp_sum32(st1, lane), t2 = warp_sum32(st2, lane);
+        s_stat[(q * 2 + 0) * 128 + cg * 32 + lane] = t1;
+        s_stat[(q * 2 + 1) * 128 + cg * 32 + lane] = t2;
+      }
+    }
+    if (want_stats) {
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const int et = tid - 64;  // 0..255
+      const long rec = r0 / 128 + mt;
+      if (et < N && rec < n_rec) {
+        const long o = rec * ctot + (long)g * N + et;
+        d.stat_sum[o] = (s_stat[0 * 128 + et] + s_stat[2 * 128 + et]) + (s_stat[4 * 128 + et] + s_stat[6 * 128 + et]);
+        d.stat_sq[o] = (s_stat[1 * 128 + et] + s_stat[3 * 128 + et]) + (s_stat[5 * 128 + et] + s_stat[7 * 128 + et]);
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+    }
+  }
+}
+
 template <int MT, int EPI>
 __global__ void __launch_bounds__(FW_THREADS, MT == 2 ? 2 : 1) conv_tc_kernel(const __grid_constant__ NefConvDesc d,
                                                                               int first_wave, int stagger_cycles, int use_ws) {
@@ -362,133 +498,10 @@ __global__ void __launch_bounds__(FW_THREADS, MT == 2 ? 2 : 1) conv_tc_kernel(co
     if (lane == 0) dbg_stamp(3);
   } else {
     // ===== epilogue: 8 warps; warp w owns TMEM lanes 32 * (w % 4) .. + 31 and the 32-column groups cg = (w - 2) / 4 (mod 2)
-    const int q = warp & 3, chalf = (warp - 2) >> 2;
-    constexpr bool GEN = (EPI & EPI_GENERIC) != 0;
-    const bool want_stats = GEN ? d.stat_sum != nullptr : (EPI & EPI_STATS) != 0;
-    const bool f_bias = GEN ? d.bias != nullptr : (EPI & EPI_BIAS) != 0;
-    const bool f_res = GEN ? d.res != nullptr : (EPI & EPI_RES) != 0;
-    const bool f_relu = GEN ? d.relu != 0 : (EPI & EPI_RELU) != 0;
-    const bool f_drop = GEN ? d.drop_p > 0.f : (EPI & EPI_DROP) != 0;
-    const bool f_round = GEN ? d.round_tf32 != 0 : (EPI & EPI_ROUND) != 0;
-    const bool f_bscale = GEN ? d.bscale != nullptr : (EPI & EPI_BSCALE) != 0;
-    const bool f_bsgrad = GEN && d.bscale_grad != nullptr;
-    const int mask_mode = GEN ? d.mask_mode : ((EPI & EPI_MASK1) ? 1 : ((EPI & EPI_MASK2) ? 2 : 0));
-    const float mask_scale = d.mask_scale;
-    const uint32_t drop_thr = (uint32_t)(d.drop_p * 65536.f);
-    const float drop_sc = 1.f / (1.f - d.drop_p);
-    const long ctot = (long)d.groups * N;
-    const long n_rec = (d.rows + 127) / 128;
-    const float4* bias4 = reinterpret_cast<const float4*>(d.bias) + g * (N >> 2);
     mbar_wait(acc_full, 0);
     tc_fence_after();
     if (tid == 64) dbg_stamp(4);
-    for (int mt = 0; mt < MT; ++mt) {
-      const long row = r0 + mt * 128 + q * 32 + lane;
-      const EpiRow er = epi_row(d, row);
-      const int b0 = __shfl_sync(0xffffffffu, er.b, 0);
-      const bool uniform_b = __all_sync(0xffffffffu, er.b == b0);
-      // per-row base pointers; chunk n4 of the group is n4 * (chunk stride) further.  Rows outside the tensor read row 0
-      // (always mapped) so that the operand loads are unconditional and can all be in flight together.
-      const long orow = er.valid ? er.out_row : 0;
-      float4* yp = reinterpret_cast<float4*>(d.y) + (long)(d.y_c4_off + g * d.y_c4_gstride) * d.y_cstride + orow;
-      const float4* rp = reinterpret_cast<const float4*>(d.res) + (long)(d.res_c4_off + g * d.res_c4_gstride) * d.res_cstride + orow;
-      const float4* mp = reinterpret_cast<const float4*>(d.mask) + (long)(d.mask_c4_off + g * d.mask_c4_gstride) * d.mask_cstride + orow;
-      const float4* bs4 = reinterpret_cast<const float4*>(d.bscale) + (long)(er.valid ? er.b : 0) * (ctot >> 2) + g * (N >> 2);
-      for (int cg = chalf; cg < N / 32; cg += 2) {
-        uint32_t v[32];
-        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * N + cg * 32), v);
-        // the residual / mask operands of these 8 chunks are fetched while the TMEM load is in flight
-        float4 rr[8], mm[8];
-        {
-          const float4* rpc = rp + (long)(cg * 8) * d.res_cstride;
-          const float4* mpc = mp + (long)(cg * 8) * d.mask_cstride;
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            rr[i] = f_res ? __ldg(rpc) : f4zero();
-            mm[i] = mask_mode ? __ldg(mpc) : f4zero();
-            rpc += d.res_cstride;
-            mpc += d.mask_cstride;
-          }
-        }
-        tmem_ld_wait();
-        float st1[32], st2[32];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int n4 = cg * 8 + i;
-          float4 x = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]),
-                                 __uint_as_float(v[4 * i + 3]));
-          if (f_bias) x = x + __ldg(bias4 + n4);
-          x = x + rr[i];
-          const float4 pre = x;
-          if (f_relu) x = make_float4(fmaxf(x.x, 0.f), fmaxf(x.y, 0.f), fmaxf(x.z, 0.f), fmaxf(x.w, 0.f));
-          if (f_drop) {
-            const uint64_t bits = drop_bits(d.drop_seed, er.out_row, d.y_c4_off + g * d.y_c4_gstride + n4);
-            x.x = ((bits & 0xffff) >= drop_thr) ? x.x * drop_sc : 0.f;
-            x.y = (((bits >> 16) & 0xffff) >= drop_thr) ? x.y * drop_sc : 0.f;
-            x.z = (((bits >> 32) & 0xffff) >= drop_thr) ? x.z * drop_sc : 0.f;
-            x.w = (((bits >> 48) & 0xffff) >= drop_thr) ? x.w * drop_sc : 0.f;
-          }
-          if (f_bscale) {
-            const float4 sc4 = __ldg(bs4 + n4);
-            if (f_bsgrad) {  // forward was ys = relu(.) * s with the mask tensor = ys ; d s += x * ys / s
-              const float4 m = mm[i];
-              float4 bsg;
-              bsg.x = sc4.x != 0.f ? x.x * m.x / sc4.x : 0.f;
-              bsg.y = sc4.y != 0.f ? x.y * m.y / sc4.y : 0.f;
-              bsg.z = sc4.z != 0.f ? x.z * m.z / sc4.z : 0.f;
-              bsg.w = sc4.w != 0.f ? x.w * m.w / sc4.w : 0.f;
-              const long cbase = (long)g * N + n4 * 4;
-              if (uniform_b) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const float s1 = warp_sum(er.valid ? f4get(bsg, j) : 0.f);
-                  if (lane == 0 && s1 != 0.f) atomicAdd(d.bscale_grad + (long)b0 * ctot + cbase + j, s1);
-                }
-              } else if (er.valid) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) atomicAdd(d.bscale_grad + (long)er.b * ctot + cbase + j, f4get(bsg, j));
-              }
-            }
-            x = x * sc4;
-          }
-          if (mask_mode == 1) {
-            const float4 m = mm[i];
-            x = make_float4(m.x > 0.f ? x.x * mask_scale : 0.f, m.y > 0.f ? x.y * mask_scale : 0.f,
-                            m.z > 0.f ? x.z * mask_scale : 0.f, m.w > 0.f ? x.w * mask_scale : 0.f);
-          } else if (mask_mode == 2) {
-            const float4 m = mm[i];
-            x = make_float4(m.x != 0.f ? x.x * mask_scale : 0.f, m.y != 0.f ? x.y * mask_scale : 0.f,
-                            m.z != 0.f ? x.z * mask_scale : 0.f, m.w != 0.f ? x.w * mask_scale : 0.f);
-          }
-          if (f_round) x = rn4_tf32(x);
-          if (er.valid) yp[(long)n4 * d.y_cstride] = x;
-          if (want_stats) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float pv = er.valid ? f4get(pre, j) : 0.f;
-              st1[4 * i + j] = pv;
-              st2[4 * i + j] = pv * pv;
-            }
-          }
-        }
-        if (want_stats) {  // lane j ends up with the 32-row totals of channel cg * 32 + j
-          const float t1 = warp_sum32(st1, lane), t2 = warp_sum32(st2, lane);
-          s_stat[(q * 2 + 0) * 128 + cg * 32 + lane] = t1;
-          s_stat[(q * 2 + 1) * 128 + cg * 32 + lane] = t2;
-        }
-      }
-      if (want_stats) {
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        const int et = tid - 64;  // 0..255
-        const long rec = r0 / 128 + mt;
-        if (et < N && rec < n_rec) {
-          const long o = rec * ctot + (long)g * N + et;
-          d.stat_sum[o] = (s_stat[0 * 128 + et] + s_stat[2 * 128 + et]) + (s_stat[4 * 128 + et] + s_stat[6 * 128 + et]);
-          d.stat_sq[o] = (s_stat[1 * 128 + et] + s_stat[3 * 128 + et]) + (s_stat[5 * 128 + et] + s_stat[7 * 128 + et]);
-        }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-      }
-    }
+    epilogue_tile<MT, EPI>(d, g, r0, tmem, warp, lane, tid, s_stat);
     if (tid == 64) dbg_stamp(5);
     tc_fence_before();
   }
@@ -498,6 +511,160 @@ __global__ void __launch_bounds__(FW_THREADS, MT == 2 ? 2 : 1) conv_tc_kernel(co
     tmem_dealloc(tmem, TM_COLS);
   }
   if (tid == 0) dbg_stamp(6);
+}
+
+// ---------------------------------------------------------------------------------------------
+// persistent forward / data-gradient kernel: one CTA per SM walks (group, 256-row tile) work items; two accumulator
+// sets in TMEM (2 x (2 row tiles x N columns)), so the epilogue of tile i and the operand pipeline fill of tile i + 1
+// overlap the main loop.  Same operand staging, MMA issue and epilogue as conv_tc_kernel.
+// ---------------------------------------------------------------------------------------------
+struct PsSmem {
+  static constexpr int MT = 2;
+  static constexpr int XROWS = MT * 128 + 8;
+  static constexpr int XPITCH = XROWS * 16;
+  static constexpr int XBYTES = 8 * XPITCH;
+  static constexpr int XST = 3;
+  static constexpr int WST = 6;
+  static constexpr int BAR_OFF = XST * XBYTES + WST * FW_WBYTES;
+  static constexpr int STAT_OFF = BAR_OFF + 256;
+  static constexpr int TOTAL = STAT_OFF + 4 * 2 * 128 * 4 + 128;
+};
+static_assert(PsSmem::TOTAL <= 227 * 1024, "persistent conv shared memory");
+
+template <int EPI>
+__global__ void __launch_bounds__(FW_THREADS, 1) conv_tc_persist_kernel(const __grid_constant__ NefConvDesc d, int tiles_per_group,
+                                                                        int n_tiles) {
+  using S = PsSmem;
+  constexpr int MT = S::MT;
+  extern __shared__ __align__(128) uint8_t smem[];
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t xs0 = sbase, ws0 = sbase + S::XST * S::XBYTES, bar0 = sbase + S::BAR_OFF;
+  auto full_x = [&](int i) { return bar0 + 8 * i; };
+  auto empty_x = [&](int i) { return bar0 + 8 * (S::XST + i); };
+  auto full_w = [&](int i) { return bar0 + 8 * (2 * S::XST + i); };
+  auto empty_w = [&](int i) { return bar0 + 8 * (2 * S::XST + S::WST + i); };
+  auto acc_full = [&](int i) { return bar0 + 8 * (2 * S::XST + 2 * S::WST + i); };
+  auto acc_empty = [&](int i) { return bar0 + 8 * (2 * S::XST + 2 * S::WST + 2 + i); };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + S::BAR_OFF + 8 * (2 * S::XST + 2 * S::WST + 4));
+  float* s_stat = reinterpret_cast<float*>(smem + S::STAT_OFF);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int N = d.N;
+  constexpr uint32_t TM_COLS = 512;
+
+  if (tid == 0) {
+    for (int i = 0; i < S::XST; ++i) { mbar_init(full_x(i), 1); mbar_init(empty_x(i), 1); }
+    for (int i = 0; i < S::WST; ++i) { mbar_init(full_w(i), 1); mbar_init(empty_w(i), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(acc_full(i), 1); mbar_init(acc_empty(i), FW_THREADS - 64); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32((const void*)tmem_slot), TM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== copy producer =====
+    int xs = 0, xph = 0, wst = 0, wph = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const int g = tile / tiles_per_group;
+      const long r0 = (long)(tile - g * tiles_per_group) * (MT * 128);
+      for (int ti = 0; ti < d.n_terms; ++ti) {
+        const NefConvTerm& t = d.term[ti];
+        const int nkb = t.cin_g >> 5;
+        const uint32_t xbytes = (uint32_t)(MT * 128 + t.taps - 1) * 16;
+        const uint32_t wbytes = (uint32_t)(8 * N * 16);
+        const float4* xg = reinterpret_cast<const float4*>(t.x) + (r0 + t.tap_off);
+        const float4* wg = reinterpret_cast<const float4*>(t.w);
+        for (int kb = 0; kb < nkb; ++kb) {
+          if (lane == 0) {
+            mbar_wait(empty_x(xs), xph ^ 1);
+            mbar_expect_tx(full_x(xs), 8 * xbytes);
+          }
+          __syncwarp();
+          if (lane < 8) {
+            const long chunk = t.x_c4_off + (long)g * t.x_c4_gstride + kb * 8 + lane;
+            bulk_g2s(xs0 + xs * S::XBYTES + lane * S::XPITCH, xg + chunk * t.x_cstride, xbytes, full_x(xs));
+          }
+          if (++xs == S::XST) { xs = 0; xph ^= 1; }
+          if (lane == 0) {
+            for (int tp = 0; tp < t.taps; ++tp) {
+              mbar_wait(empty_w(wst), wph ^ 1);
+              mbar_expect_tx(full_w(wst), wbytes);
+              bulk_g2s(ws0 + wst * FW_WBYTES, wg + ((((long)g * t.taps + tp) * nkb + kb) * 8) * N, wbytes, full_w(wst));
+              if (++wst == S::WST) { wst = 0; wph ^= 1; }
+            }
+          } else {
+            wst = (wst + t.taps) % S::WST;  // (only lane 0 uses the weight stage counters)
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    const uint32_t idesc = make_idesc(128, N, 0, 0);
+    const uint32_t nb = 2u * (uint32_t)N;
+    int xs = 0, xph = 0, wst = 0, wph = 0, as = 0, aph = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      mbar_wait(acc_empty(as), aph ^ 1);
+      tc_fence_after();
+      const uint32_t acc0 = tmem + (uint32_t)(as * 256);
+      uint32_t accum = 0;
+      for (int ti = 0; ti < d.n_terms; ++ti) {
+        const NefConvTerm& t = d.term[ti];
+        const int nkb = t.cin_g >> 5;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(full_x(xs), xph);
+          for (int tp = 0; tp < t.taps; ++tp) {
+            mbar_wait(full_w(wst), wph);
+            tc_fence_after();
+            const uint32_t xa = desc_lo(xs0 + xs * S::XBYTES + tp * 16, S::XPITCH);
+            const uint32_t wa = desc_lo(ws0 + wst * FW_WBYTES, (uint32_t)N * 16);
+            if (elect_one()) {
+#pragma unroll
+              for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+                for (int k8 = 0; k8 < 4; ++k8)
+                  mma_tf32(acc0 + mt * N, desc_of(DESC_HI_SBO128, xa + k8 * 2 * (S::XPITCH >> 4) + mt * 128),
+                           desc_of(DESC_HI_SBO128, wa + k8 * nb), idesc, accum | (uint32_t)k8);
+              }
+              tc_commit(empty_w(wst));
+            }
+            __syncwarp();
+            accum = 1;
+            if (++wst == S::WST) { wst = 0; wph ^= 1; }
+          }
+          if (elect_one()) tc_commit(empty_x(xs));
+          __syncwarp();
+          if (++xs == S::XST) { xs = 0; xph ^= 1; }
+        }
+      }
+      if (elect_one()) tc_commit(acc_full(as));
+      __syncwarp();
+      if (++as == 2) { as = 0; aph ^= 1; }
+    }
+  } else {
+    // ===== epilogue warps =====
+    int as = 0, aph = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const int g = tile / tiles_per_group;
+      const long r0 = (long)(tile - g * tiles_per_group) * (MT * 128);
+      mbar_wait(acc_full(as), aph);
+      tc_fence_after();
+      epilogue_tile<MT, EPI>(d, g, r0, tmem + (uint32_t)(as * 256), warp, lane, tid, s_stat);
+      tc_fence_before();
+      mbar_arrive(acc_empty(as));
+      if (++as == 2) { as = 0; aph ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, TM_COLS);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -531,10 +698,6 @@ constexpr int WG_NTR = 2;
 constexpr int WG_BAR_OFF = WG_NRAW * WG_RAW + WG_NTR * WG_TR;
 constexpr int WG_TOTAL = WG_BAR_OFF + 128;
 static_assert(WG_TOTAL <= 227 * 1024, "wgrad shared memory");
-
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
 
 // Every CTA accumulates ALL taps (<= 7) of a 128 x 64 block of the weight gradient (7 x 64 = 448 TMEM columns), so
 // each row of X and dY is staged once per CTA.  Two orientations:
@@ -778,6 +941,7 @@ using namespace nef;
 static int g_sm_count = 148;
 static int g_tc_stagger = -1;  // first-wave start stagger in cycles; -1 = one estimated CTA lifetime (NEF_TC_STAGGER)
 static int g_tc_ws = 0;   // 1 = weight-stationary MMA form (NEF_TC_WS)
+static int g_tc_persist = 1;  // persistent forward kernel (NEF_TC_PERSIST=0: one CTA per tile)
 static int g_tc_mt = 0;  // 0 = automatic; 4 forces four row tiles per CTA, one CTA per SM (NEF_TC_MT, for A/B measurements)
 
 // the specialised epilogues instantiated for the 4-row-tile kernel (everything else takes the generic one)
@@ -791,10 +955,13 @@ static int tc_optin() {
 }
 
 extern "C" int nef_tc_init(void) {
-#define X(E) { int rc = tc_optin<4, E>(); if (rc) return rc; rc = tc_optin<2, E>(); if (rc) return rc; }
+#define X(E) { int rc = tc_optin<4, E>(); if (rc) return rc; rc = tc_optin<2, E>(); if (rc) return rc; \
+               cudaError_t pe = cudaFuncSetAttribute(tc::conv_tc_persist_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::PsSmem::TOTAL); \
+               NEF_REQUIRE(pe == cudaSuccess, "nef_tc_init: conv_tc_persist_kernel<%d> shared-memory opt-in failed: %s", E, cudaGetErrorString(pe)); }
   NEF_TC_EPI_LIST(X)
 #undef X
   if (getenv("NEF_TC_MT")) g_tc_mt = atoi(getenv("NEF_TC_MT"));
+  if (getenv("NEF_TC_PERSIST")) g_tc_persist = atoi(getenv("NEF_TC_PERSIST"));
   if (getenv("NEF_TC_STAGGER")) g_tc_stagger = atoi(getenv("NEF_TC_STAGGER"));
   if (getenv("NEF_TC_WS")) g_tc_ws = atoi(getenv("NEF_TC_WS"));
   { int rc = tc_optin<1, tc::EPI_GENERIC>(); if (rc) return rc; }
@@ -839,8 +1006,26 @@ static int launch_conv_tc(const NefConvDesc* d, cudaStream_t s) {
   return 0;
 }
 
+static int launch_conv_persist(const NefConvDesc* d, cudaStream_t s) {
+  const int tpg = (int)((d->rows + 255) / 256);
+  const int n_tiles = tpg * d->groups;
+  const int grid = n_tiles < g_sm_count ? n_tiles : g_sm_count;
+  switch (epi_code(d)) {
+#define X(E) case E: tc::conv_tc_persist_kernel<E><<<grid, tc::FW_THREADS, tc::PsSmem::TOTAL, s>>>(*d, tpg, n_tiles); break;
+    NEF_TC_EPI_LIST(X)
+#undef X
+    default: tc::conv_tc_persist_kernel<tc::EPI_GENERIC><<<grid, tc::FW_THREADS, tc::PsSmem::TOTAL, s>>>(*d, tpg, n_tiles); break;
+  }
+  return 0;
+}
+
 extern "C" int nef_gconv_fwd_tc(const NefConvDesc* d, nef_stream_t s) {
   const long tiles4 = (d->rows + 511) / 512, tiles2 = (d->rows + 255) / 256;
+  if (g_tc_persist && g_tc_mt == 0 && tiles2 * d->groups >= 2L * g_sm_count) {
+    launch_conv_persist(d, (cudaStream_t)s);
+    NEF_CHECK_LAUNCH("conv_tc_persist_kernel");
+    return 0;
+  }
   int mt = 1;  // small row spaces (the z2 deflection branch at small batch): one 128-row tile per CTA keeps the grid wide
   if (tiles2 * d->groups >= 2L * g_sm_count) mt = 2;
   if (g_tc_mt == 4 && tiles4 * d->groups >= g_sm_count) mt = 4;
