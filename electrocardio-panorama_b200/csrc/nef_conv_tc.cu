@@ -533,7 +533,7 @@ static_assert(PsSmem::TOTAL <= 227 * 1024, "persistent conv shared memory");
 
 template <int EPI>
 __global__ void __launch_bounds__(FW_THREADS, 1) conv_tc_persist_kernel(const __grid_constant__ NefConvDesc d, int tiles_per_group,
-                                                                        int n_tiles) {
+                                                                        int n_tiles, int use_ws) {
   using S = PsSmem;
   constexpr int MT = S::MT;
   extern __shared__ __align__(128) uint8_t smem[];
@@ -607,8 +607,12 @@ __global__ void __launch_bounds__(FW_THREADS, 1) conv_tc_persist_kernel(const __
     const uint32_t idesc = make_idesc(128, N, 0, 0);
     const uint32_t nb = 2u * (uint32_t)N;
     int xs = 0, xph = 0, wst = 0, wph = 0, as = 0, aph = 0;
+    long long wt_a = 0, wt_x = 0, wt_w = 0, tq;
+    const long long t_begin = clock64();
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      tq = clock64();
       mbar_wait(acc_empty(as), aph ^ 1);
+      wt_a += clock64() - tq;
       tc_fence_after();
       const uint32_t acc0 = tmem + (uint32_t)(as * 256);
       uint32_t accum = 0;
@@ -616,19 +620,32 @@ __global__ void __launch_bounds__(FW_THREADS, 1) conv_tc_persist_kernel(const __
         const NefConvTerm& t = d.term[ti];
         const int nkb = t.cin_g >> 5;
         for (int kb = 0; kb < nkb; ++kb) {
+          tq = clock64();
           mbar_wait(full_x(xs), xph);
+          wt_x += clock64() - tq;
           for (int tp = 0; tp < t.taps; ++tp) {
+            tq = clock64();
             mbar_wait(full_w(wst), wph);
+            wt_w += clock64() - tq;
             tc_fence_after();
             const uint32_t xa = desc_lo(xs0 + xs * S::XBYTES + tp * 16, S::XPITCH);
             const uint32_t wa = desc_lo(ws0 + wst * FW_WBYTES, (uint32_t)N * 16);
             if (elect_one()) {
+              if (use_ws) {  // the weight stage (B) is latched by the first row tile and re-used by the second
 #pragma unroll
-              for (int mt = 0; mt < MT; ++mt) {
+                for (int k8 = 0; k8 < 4; ++k8) {
+                  const uint64_t bd = desc_of(DESC_HI_SBO128, wa + k8 * nb);
+                  mma_tf32_ws<0>(acc0, desc_of(DESC_HI_SBO128, xa + k8 * 2 * (S::XPITCH >> 4)), bd, idesc, accum | (uint32_t)k8);
+                  mma_tf32_ws<2>(acc0 + N, desc_of(DESC_HI_SBO128, xa + k8 * 2 * (S::XPITCH >> 4) + 128), bd, idesc, accum | (uint32_t)k8);
+                }
+              } else {
 #pragma unroll
-                for (int k8 = 0; k8 < 4; ++k8)
-                  mma_tf32(acc0 + mt * N, desc_of(DESC_HI_SBO128, xa + k8 * 2 * (S::XPITCH >> 4) + mt * 128),
-                           desc_of(DESC_HI_SBO128, wa + k8 * nb), idesc, accum | (uint32_t)k8);
+                for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+                  for (int k8 = 0; k8 < 4; ++k8)
+                    mma_tf32(acc0 + mt * N, desc_of(DESC_HI_SBO128, xa + k8 * 2 * (S::XPITCH >> 4) + mt * 128),
+                             desc_of(DESC_HI_SBO128, wa + k8 * nb), idesc, accum | (uint32_t)k8);
+                }
               }
               tc_commit(empty_w(wst));
             }
@@ -644,6 +661,12 @@ __global__ void __launch_bounds__(FW_THREADS, 1) conv_tc_persist_kernel(const __
       if (elect_one()) tc_commit(acc_full(as));
       __syncwarp();
       if (++as == 2) { as = 0; aph ^= 1; }
+    }
+    if (lane == 0 && blockIdx.x < 1024) {  // profiling aid: cycles the issuer spent waiting (nef_tc_debug_dump)
+      g_tc_dbg[blockIdx.x][0] = (unsigned long long)(clock64() - t_begin);
+      g_tc_dbg[blockIdx.x][1] = (unsigned long long)wt_a;
+      g_tc_dbg[blockIdx.x][2] = (unsigned long long)wt_x;
+      g_tc_dbg[blockIdx.x][3] = (unsigned long long)wt_w;
     }
   } else {
     // ===== epilogue warps =====
@@ -1011,10 +1034,10 @@ static int launch_conv_persist(const NefConvDesc* d, cudaStream_t s) {
   const int n_tiles = tpg * d->groups;
   const int grid = n_tiles < g_sm_count ? n_tiles : g_sm_count;
   switch (epi_code(d)) {
-#define X(E) case E: tc::conv_tc_persist_kernel<E><<<grid, tc::FW_THREADS, tc::PsSmem::TOTAL, s>>>(*d, tpg, n_tiles); break;
+#define X(E) case E: tc::conv_tc_persist_kernel<E><<<grid, tc::FW_THREADS, tc::PsSmem::TOTAL, s>>>(*d, tpg, n_tiles, g_tc_ws); break;
     NEF_TC_EPI_LIST(X)
 #undef X
-    default: tc::conv_tc_persist_kernel<tc::EPI_GENERIC><<<grid, tc::FW_THREADS, tc::PsSmem::TOTAL, s>>>(*d, tpg, n_tiles); break;
+    default: tc::conv_tc_persist_kernel<tc::EPI_GENERIC><<<grid, tc::FW_THREADS, tc::PsSmem::TOTAL, s>>>(*d, tpg, n_tiles, g_tc_ws); break;
   }
   return 0;
 }
