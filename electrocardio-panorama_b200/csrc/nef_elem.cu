@@ -894,97 +894,75 @@ int dec_out_fwd(T4 c4, const float* scale, const float* shift, const float* w, c
 // backward of the output layer fused with pass 1 of bn4's backward:
 //   dy = dout * out (1 - out) / 3 ; dw[ci][t] += sum dy[l] a4[l+t-1][ci] ; db += sum dy
 //   g4[l][ci] = (sum_t dy[l-t+1] w[ci][t]) * (a4 > 0) ; s1 += g4 ; s2 += g4 * xhat
-__global__ void __launch_bounds__(128) dec_out_bwd_kernel(T4 c4t, BnLayer bn, const float* __restrict__ w,
+// grid: x = position blocks (grid-stride), y = the 16 channel chunks.  Every thread keeps its 5 float4 partial sums in
+// registers over all its positions; one block reduction at the end.
+__global__ void __launch_bounds__(256) dec_out_bwd_kernel(T4 c4t, BnLayer bn, const float* __restrict__ w,
                                                           const float* __restrict__ out, const float* __restrict__ dout,
                                                           T4 g4, float* __restrict__ dw, float* __restrict__ db) {
-  __shared__ float4 ws[3][16], scs[16], shs[16], mus[16], iss[16];
-  __shared__ float acc_s[16][20];  // per chunk: s1[4], s2[4], dw[3][4]
-  __shared__ float db_s;
-  const int tid = threadIdx.x, lane = tid & 31;
-  if (tid < 48) {
-    const int t = tid / 16, c = tid % 16;
-    ws[t][c] = make_float4(w[(c * 4 + 0) * 3 + t], w[(c * 4 + 1) * 3 + t], w[(c * 4 + 2) * 3 + t], w[(c * 4 + 3) * 3 + t]);
-  } else if (tid < 64) {
-    const int c = tid - 48;
-    scs[c] = reinterpret_cast<const float4*>(bn.scale)[c];
-    shs[c] = reinterpret_cast<const float4*>(bn.shift)[c];
-    mus[c] = reinterpret_cast<const float4*>(bn.mean)[c];
-    iss[c] = reinterpret_cast<const float4*>(bn.invstd)[c];
-  }
-  for (int i = tid; i < 16 * 20; i += 128) (&acc_s[0][0])[i] = 0.f;
-  if (tid == 0) db_s = 0.f;
-  __syncthreads();
+  __shared__ float red[8][21];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int c = blockIdx.y;
+  const float4 w0 = make_float4(w[(c * 4 + 0) * 3 + 0], w[(c * 4 + 1) * 3 + 0], w[(c * 4 + 2) * 3 + 0], w[(c * 4 + 3) * 3 + 0]);
+  const float4 w1 = make_float4(w[(c * 4 + 0) * 3 + 1], w[(c * 4 + 1) * 3 + 1], w[(c * 4 + 2) * 3 + 1], w[(c * 4 + 3) * 3 + 1]);
+  const float4 w2 = make_float4(w[(c * 4 + 0) * 3 + 2], w[(c * 4 + 1) * 3 + 2], w[(c * 4 + 2) * 3 + 2], w[(c * 4 + 3) * 3 + 2]);
+  const float4 sc = reinterpret_cast<const float4*>(bn.scale)[c], sh = reinterpret_cast<const float4*>(bn.shift)[c];
+  const float4 mu = reinterpret_cast<const float4*>(bn.mean)[c], is = reinterpret_cast<const float4*>(bn.invstd)[c];
   const int L = c4t.L;
   const long total = (long)c4t.B * L;
-  const long span = (long)gridDim.x * blockDim.x;
-  const long iters = (total + span - 1) / span;
+  float4 s1 = f4zero(), s2 = f4zero(), a_m = f4zero(), a_0 = f4zero(), a_p = f4zero();
   float dbl = 0.f;
-  for (long it = 0; it < iters; ++it) {
-    const long i = it * span + blockIdx.x * (long)blockDim.x + tid;
-    const bool ok = i < total;
-    const int l = ok ? (int)(i % L) : 0;
-    const int b = ok ? (int)(i / L) : 0;
-    float dym = 0.f, dy0 = 0.f, dyp = 0.f;  // dy at l-1, l, l+1
-    if (ok) {
-      const float* op = out + (long)b * L + l;
-      const float* dp = dout + (long)b * L + l;
-      dy0 = dp[0] * op[0] * (1.0f - op[0]) * (1.0f / 3.0f);
-      if (l > 0) dym = dp[-1] * op[-1] * (1.0f - op[-1]) * (1.0f / 3.0f);
-      if (l + 1 < L) dyp = dp[1] * op[1] * (1.0f - op[1]) * (1.0f / 3.0f);
-    }
+  for (long i = blockIdx.x * (long)blockDim.x + tid; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / L);
+    const int l = (int)(i - (long)b * L);
+    const float* op = out + (long)b * L + l;
+    const float* dp = dout + (long)b * L + l;
+    const float dy0 = dp[0] * op[0] * (1.0f - op[0]) * (1.0f / 3.0f);
+    const float dym = l > 0 ? dp[-1] * op[-1] * (1.0f - op[-1]) * (1.0f / 3.0f) : 0.f;
+    const float dyp = l + 1 < L ? dp[1] * op[1] * (1.0f - op[1]) * (1.0f / 3.0f) : 0.f;
+    const float4* p = c4t.at(c, b, l);
+    const float4 cv = p[0];
+    const float4 a0 = bn_relu4(cv, sc, sh);
+    const float4 am = l > 0 ? bn_relu4(p[-1], sc, sh) : f4zero();
+    const float4 ap = l + 1 < L ? bn_relu4(p[1], sc, sh) : f4zero();
+    // da4[l] = dy[l+1] w[.,0] + dy[l] w[.,1] + dy[l-1] w[.,2]
+    const float4 dd = w0 * dyp + w1 * dy0 + w2 * dym;
+    const float4 gv = make_float4(a0.x > 0.f ? dd.x : 0.f, a0.y > 0.f ? dd.y : 0.f, a0.z > 0.f ? dd.z : 0.f, a0.w > 0.f ? dd.w : 0.f);
+    const float4 xh = make_float4((cv.x - mu.x) * is.x, (cv.y - mu.y) * is.y, (cv.z - mu.z) * is.z, (cv.w - mu.w) * is.w);
+    *g4.at(c, b, l) = gv;
+    s1 = s1 + gv;
+    s2 = s2 + gv * xh;
+    a_m = a_m + am * dy0;
+    a_0 = a_0 + a0 * dy0;
+    a_p = a_p + ap * dy0;
     dbl += dy0;
-    for (int c = 0; c < 16; ++c) {
-      float4 gv = f4zero(), xh = f4zero(), a0 = f4zero(), am = f4zero(), ap = f4zero();
-      if (ok) {
-        const float4* p = c4t.at(c, b, l);
-        const float4 cv = p[0];
-        a0 = bn_relu4(cv, scs[c], shs[c]);
-        if (l > 0) am = bn_relu4(p[-1], scs[c], shs[c]);
-        if (l + 1 < L) ap = bn_relu4(p[1], scs[c], shs[c]);
-        // da4[l] = dy[l+1] w[.,0] + dy[l] w[.,1] + dy[l-1] w[.,2]
-        float4 d = ws[0][c] * dyp + ws[1][c] * dy0 + ws[2][c] * dym;
-        gv = make_float4(a0.x > 0.f ? d.x : 0.f, a0.y > 0.f ? d.y : 0.f, a0.z > 0.f ? d.z : 0.f, a0.w > 0.f ? d.w : 0.f);
-        xh = make_float4((cv.x - mus[c].x) * iss[c].x, (cv.y - mus[c].y) * iss[c].y, (cv.z - mus[c].z) * iss[c].z,
-                         (cv.w - mus[c].w) * iss[c].w);
-        *g4.at(c, b, l) = gv;
-      }
+  }
+  float v[21] = {s1.x, s1.y, s1.z, s1.w, s2.x, s2.y, s2.z, s2.w, a_m.x, a_m.y, a_m.z, a_m.w,
+                 a_0.x, a_0.y, a_0.z, a_0.w, a_p.x, a_p.y, a_p.z, a_p.w, dbl};
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float g = f4get(gv, k);
-        const float r1 = warp_sum(g), r2 = warp_sum(g * f4get(xh, k));
-        const float w0 = warp_sum(dy0 * f4get(am, k)), w1 = warp_sum(dy0 * f4get(a0, k)), w2 = warp_sum(dy0 * f4get(ap, k));
-        if (lane == 0) {
-          atomicAdd(&acc_s[c][k], r1);
-          atomicAdd(&acc_s[c][4 + k], r2);
-          atomicAdd(&acc_s[c][8 + k], w0);
-          atomicAdd(&acc_s[c][12 + k], w1);
-          atomicAdd(&acc_s[c][16 + k], w2);
-        }
-      }
-    }
+  for (int k = 0; k < 21; ++k) {
+    const float r = warp_sum(v[k]);
+    if (lane == 0) red[warp][k] = r;
   }
-  dbl = warp_sum(dbl);
-  if (lane == 0) atomicAdd(&db_s, dbl);
   __syncthreads();
-  for (int i = tid; i < 16 * 20; i += 128) {
-    const int c = i / 20, e = i % 20;
-    const float v = acc_s[c][e];
-    if (e < 4) atomicAdd(bn.s1 + c * 4 + e, (double)v);
-    else if (e < 8) atomicAdd(bn.s2 + c * 4 + e - 4, (double)v);
-    else {
-      const int t = (e - 8) / 4, k = (e - 8) % 4;
-      atomicAdd(dw + (c * 4 + k) * 3 + t, v);
-    }
+  if (tid < 21) {
+    float r = 0.f;
+    for (int wp = 0; wp < 8; ++wp) r += red[wp][tid];
+    if (tid < 4) atomicAdd(bn.s1 + c * 4 + tid, (double)r);
+    else if (tid < 8) atomicAdd(bn.s2 + c * 4 + tid - 4, (double)r);
+    else if (tid < 20) {
+      const int t = (tid - 8) / 4, k = (tid - 8) % 4;
+      atomicAdd(dw + (c * 4 + k) * 3 + t, r);
+    } else if (c == 0) atomicAdd(db, r);
   }
-  if (tid == 0) atomicAdd(db, db_s);
 }
 int dec_out_bwd(T4 c4, const BnLayer& bn, const float* w, const float* out, const float* dout, T4 g4, float* dw,
                 float* db, cudaStream_t s) {
   const long total = (long)c4.B * c4.L;
-  int g = (int)((total + 128 * 8 - 1) / (128 * 8));
-  if (g < 1) g = 1;
-  if (g > 148 * 8) g = 148 * 8;
-  dec_out_bwd_kernel<<<g, 128, 0, s>>>(c4, bn, w, out, dout, g4, dw, db);
+  int gx = (int)((total + 256 * 8 - 1) / (256 * 8));
+  if (gx < 1) gx = 1;
+  if (gx > 148 * 4) gx = 148 * 4;
+  dim3 grid(gx, 16);
+  dec_out_bwd_kernel<<<grid, 256, 0, s>>>(c4, bn, w, out, dout, g4, dw, db);
   NEF_CHECK_LAUNCH("dec_out_bwd_kernel");
   return 0;
 }

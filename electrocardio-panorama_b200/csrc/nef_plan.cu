@@ -632,10 +632,13 @@ static int decoder_bwd(NefPlan* p, const float* const* P, float* const* Gd, int 
   const int B = p->B;
   const double n2 = (double)B * p->L2, n1 = (double)B * p->L;
   auto g = [&](int i) { return Gd[i]; };
+  // A convolution bias followed by a training-mode BatchNorm has no gradient (the batch mean absorbs it; the reference's
+  // autograd value is rounding noise, oracle ZERO_GRAD_PARAMS): its slot is left at zero instead of spending a reduction.
+  auto gb = [&](int i) { return p->bn_training ? (float*)nullptr : Gd[i]; };
   // output layer + bn4 statistics
   RUN(dec_out_bwd(d.c4, d.bn[3], P[P_OUT_W], d.out, dout, p->dg4, g(P_OUT_W), g(P_OUT_B), s));
   RUN(bnbwd_apply(p->dg4, d.c4, d.bn[3], P[P_DEC3 + 9], n1, p->dg4, g(P_DEC3 + 9), g(P_DEC3 + 10), s));
-  RUN(wgrad_std(p->dg4, 0, 0, d.a3, 0, 0, p->decw[3], g(P_DEC3 + 7), g(P_DEC3 + 8), s));
+  RUN(wgrad_std(p->dg4, 0, 0, d.a3, 0, 0, p->decw[3], g(P_DEC3 + 7), gb(P_DEC3 + 8), s));
   {
     CD c(1, 64, p->dg4);
     c.term(p->dg4, 0, 0, 64, 3, p->decw[3].pk_d).out(p->dg3, 0, 0);
@@ -643,7 +646,7 @@ static int decoder_bwd(NefPlan* p, const float* const* P, float* const* Gd, int 
   }
   RUN(bnbwd_stats(p->dg3, d.c3, d.bn[2], s));
   RUN(bnbwd_apply(p->dg3, d.c3, d.bn[2], P[P_DEC3 + 2], n1, p->dg3, g(P_DEC3 + 2), g(P_DEC3 + 3), s));
-  RUN(wgrad_std(p->dg3, 0, 0, d.u1, 0, 0, p->decw[2], g(P_DEC3 + 0), g(P_DEC3 + 1), s));
+  RUN(wgrad_std(p->dg3, 0, 0, d.u1, 0, 0, p->decw[2], g(P_DEC3 + 0), gb(P_DEC3 + 1), s));
   {
     CD c(1, 128, p->dg3);
     c.term(p->dg3, 0, 0, 64, 3, p->decw[2].pk_d).out(p->du1, 0, 0);
@@ -652,7 +655,7 @@ static int decoder_bwd(NefPlan* p, const float* const* P, float* const* Gd, int 
   RUN(up_adjoint(p->du1, p->dg2, s));
   RUN(bnbwd_stats(p->dg2, d.c2, d.bn[1], s));
   RUN(bnbwd_apply(p->dg2, d.c2, d.bn[1], P[P_DEC1 + 9], n2, p->dg2, g(P_DEC1 + 9), g(P_DEC1 + 10), s));
-  RUN(wgrad_std(p->dg2, 0, 0, d.a1, 0, 0, p->decw[1], g(P_DEC1 + 7), g(P_DEC1 + 8), s));
+  RUN(wgrad_std(p->dg2, 0, 0, d.a1, 0, 0, p->decw[1], g(P_DEC1 + 7), gb(P_DEC1 + 8), s));
   {
     CD c(1, 128, p->dg2);
     c.term(p->dg2, 0, 0, 128, 3, p->decw[1].pk_d).out(p->dg1, 0, 0);
@@ -660,7 +663,7 @@ static int decoder_bwd(NefPlan* p, const float* const* P, float* const* Gd, int 
   }
   RUN(bnbwd_stats(p->dg1, d.c1, d.bn[0], s));
   RUN(bnbwd_apply(p->dg1, d.c1, d.bn[0], P[P_DEC1 + 2], n2, p->dg1, g(P_DEC1 + 2), g(P_DEC1 + 3), s));
-  RUN(wgrad_std(p->dg1, 0, 0, p->u0[slot], 0, 0, p->decw[0], g(P_DEC1 + 0), g(P_DEC1 + 1), s));
+  RUN(wgrad_std(p->dg1, 0, 0, p->u0[slot], 0, 0, p->decw[0], g(P_DEC1 + 0), gb(P_DEC1 + 1), s));
   {
     CD c(2, 128, p->dg1);  // 256 output channels as two sub-groups reading the same input
     c.term(p->dg1, 0, 0, 128, 3, p->decw[0].pk_d).out(p->du0[slot], 0, 32).round();
