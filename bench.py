@@ -39,6 +39,22 @@ class Cfg:
         loss_factor = [0.5, 0.5, 1]
 
 
+def workload_name(world, B, L):
+    return ("Nef-Net train step (fwd x3 decoder passes + Standin L1 loss + bwd + %sSGD-momentum), batch %d/GPU x 12 leads x %d "
+            "samples, dropout 0.2, BN batch stats" % ("NCCL grad all-reduce + " if world > 1 else "", B, L))
+
+
+def measured_traffic(B, G, L):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/), or None."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")))
+        if (t["B"], t["G"], t["L"]) == (B, G, L):
+            return float(t["dram_bytes_read"]) + float(t["dram_bytes_write"])
+    except Exception:
+        pass
+    return None
+
+
 def algorithmic_bytes_per_segment(G, L, n_dec=3, live=True):
     """forward floats per segment with every fused block reading its inputs once and writing
     its output once; 'live' = z2_conv1 evaluated only on the centre window (what this implementation does).
@@ -121,8 +137,10 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * 8 / cb["value"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "Nef-Net train step, 12 leads x %d samples, CPU sample of 8 segments" % L,
-                       "leads": 12, "length": L},
+            "config": {"workload": workload_name(1, args.batch, L), "batch_per_gpu": args.batch,
+                       "global_batch": args.batch * args.gpus, "leads": 12, "length": L,
+                       "sample": "each step = the same train step on a bounded sample of 8 segments on the host cores "
+                                 "(reference algorithm, oracle port; the reference is pure PyTorch and cannot travel to the box)"},
             "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -264,9 +282,7 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "tf32", "data": "synthetic",
-                "config": {"workload": "Nef-Net train step (fwd x3 decoder passes + Standin L1 loss + bwd + "
-                                       "%sSGD-momentum), batch %d/GPU x 12 leads x %d samples, dropout 0.2, BN batch stats"
-                                       % ("NCCL grad all-reduce + " if world > 1 else "", B, L),
+                "config": {"workload": workload_name(world, B, L),
                            "batch_per_gpu": B, "global_batch": B * world, "leads": G, "length": L,
                            "conv_impl": "tcgen05-tf32" if lib.nef_get_conv_impl() == 1 else "cuda-core-fp32",
                            "l2": "inputs (>= 2 GB activations per layer) far exceed the 126 MB L2; no flush needed"},
@@ -275,10 +291,11 @@ def main():
                         "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": int(launches),
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                             "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                             "frac": achieved / hbm_peak, "traffic": measured_traffic(B, G, L), "peak_source": peak_src,
                              "kernel": "grouped k7 implicit-GEMM conv (encoder block conv / dgrad), %d x %d x %d" % (B, 128 * G, L // 4),
                              "kernel_ms": kms, "kernel_algorithmic_bytes": kbytes,
                              "kernel_tflops": kflops / (kms / 1000.0) / 1e12, "tf32_peak_tflops_half_of_bf16": tf32_peak,
+                             "kernel_tensor_frac": kflops / (kms / 1000.0) / 1e12 / tf32_peak,
                              "step_algorithmic_gb": step_bytes / 1e9,
                              "step_hbm_frac": step_bytes / (ms_step / 1000.0) / 1e9 / hbm_peak},
                 }

@@ -272,3 +272,36 @@ def test_cpu_input_raises():
     m = network.Model_nefnet(1, 1)
     with pytest.raises(RuntimeError):
         m(torch.zeros(1, 1, 64), torch.zeros(1, 1, 2), torch.zeros(1, 2), torch.zeros(1, 7, 2, dtype=torch.long))
+
+
+def test_full_size_segment_independence():
+    """BASELINE.json configs[1] size (256 x 12 x 5000): in eval mode every segment is independent, so the synthesized lead of
+    a segment must not depend on which batch, row tile or CTA it was computed in.  The same 4 segments are run alone
+    (small grids, one-row-tile kernels) and inside the full batch at scattered positions (persistent 256-row-tile
+    kernels); outputs must agree to accumulation-order noise, and a batch permutation must permute the outputs exactly."""
+    dev = torch.device("cuda:0")
+    G, L, B = 12, 5000, 256
+    P = O.make_params(G, 3)
+    m = _model(G, P, dev, train=False)
+    small = O.make_inputs(4, G, L, 17)
+    big = {k: v.repeat(*([B // 4] + [1] * (v.dim() - 1))).contiguous() for k, v in small.items()}
+    gen = torch.Generator().manual_seed(5)
+    big["x"] = torch.rand(B, G, L, generator=gen)
+    pos = [3, 77, 130, 255]
+    for i, p_ in enumerate(pos):
+        for k in ("x", "input_thetas", "query_theta", "rois"):
+            big[k][p_] = small[k][i]
+    with torch.no_grad():
+        random.seed(1)
+        ds = _to(small, dev)
+        ref = m(ds["x"], ds["input_thetas"], ds["query_theta"], ds["rois"], phase="train")[0].cpu()
+        random.seed(1)
+        db = _to(big, dev)
+        out = m(db["x"], db["input_thetas"], db["query_theta"], db["rois"], phase="train")[0].cpu()
+        perm = torch.randperm(B, generator=gen)
+        dp = {k: v[perm].contiguous() for k, v in db.items()}
+        random.seed(1)
+        outp = m(dp["x"], dp["input_thetas"], dp["query_theta"], dp["rois"], phase="train")[0].cpu()
+    assert torch.isfinite(out).all()
+    np.testing.assert_allclose(out[pos].numpy(), ref.numpy(), rtol=2e-5, atol=0)
+    assert torch.equal(outp, out[perm])
