@@ -475,10 +475,15 @@ __global__ void __launch_bounds__(256) latent_fwd_kernel(const LatentArgs a) {
       } else if (half == 0) {
         m = f4zero();
         p = f4zero();
-        for (int g = 0; g < a.G; ++g) {
-          const float4 v = *a.z1.at(g * 32 + cc, b, l);
-          m = m + v;
-          if (g == a.c1) p = v;
+        for (int g0 = 0; g0 < a.G; g0 += 4) {  // four leads at a time: their loads are in flight together
+          float4 v[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) v[k] = (g0 + k < a.G) ? __ldg(a.z1.at((g0 + k) * 32 + cc, b, l)) : f4zero();
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            m = m + v[k];
+            if (g0 + k == a.c1) p = v[k];
+          }
         }
         m = m * invG;
       } else {
@@ -584,13 +589,22 @@ __global__ void __launch_bounds__(256) latent_bwd_kernel(const LatentBwdArgs a) 
       else dm = dm + d;
     }
     if (half == 0) {
-      for (int g = 0; g < a.G; ++g) {
-        const float4 z = *a.z1.at(g * 32 + cc, b, l);
-        float4 gsum = dm * invG;
-        if (g == a.c1) gsum = gsum + dp;
-        gsum = make_float4(z.x > 0.f ? gsum.x : 0.f, z.y > 0.f ? gsum.y : 0.f, z.z > 0.f ? gsum.z : 0.f,
-                           z.w > 0.f ? gsum.w : 0.f);
-        *a.gz1.at(g * 32 + cc, b, l) = tf32_rn4(gsum);
+      const float4 dmg = dm * invG;
+      for (int g0 = 0; g0 < a.G; g0 += 4) {  // four leads at a time: their loads are in flight together
+        float4 z[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) z[k] = (g0 + k < a.G) ? __ldg(a.z1.at((g0 + k) * 32 + cc, b, l)) : f4zero();
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int g = g0 + k;
+          if (g < a.G) {
+            float4 gsum = dmg;
+            if (g == a.c1) gsum = gsum + dp;
+            gsum = make_float4(z[k].x > 0.f ? gsum.x : 0.f, z[k].y > 0.f ? gsum.y : 0.f, z[k].z > 0.f ? gsum.z : 0.f,
+                               z[k].w > 0.f ? gsum.w : 0.f);
+            *a.gz1.at(g * 32 + cc, b, l) = tf32_rn4(gsum);
+          }
+        }
       }
     } else {
       int j = 0;
