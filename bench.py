@@ -103,6 +103,8 @@ def cpu_baseline(G, L, steps=2, warmup=1, B=8):
     NOT used here -- the reference trains with dropout, so keep-masks are drawn on the host as it does."""
     import torch
     from oracle import nefnet_oracle as O
+    if torch.get_num_threads() < (os.cpu_count() or 1):
+        torch.set_num_threads(os.cpu_count() or 1)
     P = O.make_params(G, 0)
     inp = O.make_inputs(B, G, L, 0)
     mom = {}
@@ -132,6 +134,10 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arm uses all the host threads it can (torch is not imported yet)
+    ncpu = os.cpu_count() or 1
+    for k in ("OMP_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[k] = str(ncpu)
     G, L = 12, args.length
     cb = cpu_baseline(G, L, steps=max(1, min(args.steps, 3)), warmup=min(args.warmup, 1), B=8)
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,

@@ -1,5 +1,5 @@
 // tcgen05 (5th-generation tensor core) implementation of the grouped implicit-GEMM convolution, its data
-// gradient (same kernel, flipped / transposed packed weights) and its weight gradient, for sm_100a.
+// gradient (same kernels, flipped / transposed packed weights) and its weight gradient, for sm_100a.
 //
 //   * TF32 operands (fp32 storage, pre-rounded to TF32 by the producing kernel), fp32 accumulation in TMEM.
 //   * Operands are staged global -> shared with 1-D bulk async copies (cp.async.bulk, the TMA engine's
@@ -7,13 +7,22 @@
 //     chunk, so no tensor map is needed, and that run IS a tcgen05 no-swizzle core-matrix column
 //     (8 rows x 16 B = 128 contiguous bytes).  A k-tap convolution issues the same staged tile k times with
 //     the descriptor start address advanced by 16 B per tap -- no im2col, no per-tap reload.
-//   * Warp-specialised: warp 0 = copy producer, warp 1 = TMEM owner + single-thread MMA issuer,
-//     warps 2..5 = epilogue (tcgen05.ld -> fused bias / residual / ReLU / dropout / angular scale /
-//     BatchNorm partial statistics -> coalesced float4 stores).
+//   * Warp-specialised: copy producer warp(s), one MMA warp (converged, one elected lane issues; descriptor
+//     words precomputed so that consecutive UTCHMMAs are back to back), 8 epilogue warps (tcgen05.ld ->
+//     fused bias / residual / ReLU / dropout / angular scale / mask / BatchNorm partial statistics ->
+//     coalesced float4 stores), epilogue specialised at compile time (EPI).
 //
 // forward / dgrad :  D[128 rows x N] += X[128 rows x 32 ch](shifted by tap) . W_tap[N x 32 ch]^T   (both K-major)
-//                    MT row tiles of 128 share every weight stage (weights come from L2 once per MT*128 rows)
-// wgrad           :  D_tap[cout x cin] += dY[rows x cout]^T . X[rows (+tap) x cin]                  (both MN-major)
+//     conv_tc_persist_kernel: one CTA per SM walks (group, 256-row tile) items, two TMEM accumulator sets, so the
+//     epilogue and the pipeline fill of the next tile overlap the main loop (production path);
+//     conv_tc_kernel<MT>: one CTA per MT x 128 rows (small row spaces, A/B measurements).
+// wgrad           :  D_tap[cout x cin] += dY[rows x cout]^T . X[rows (+tap) x cin]: the contraction runs over rows and
+//     kind::tf32 cannot read MN-major operands, so the staged tiles are re-tiled in shared memory (see wgrad_tc_kernel).
+//
+// Measured facts behind the structure (tools/probe_umma.cu, tools/probe_rate.cu, profiles/): kind::tf32 reads zeros for
+// MN-major operands; M128 x N128 x K8 issues every 64 cycles, N = 64 every 48 (A-operand bound) unless A or B is held in
+// the collector; SWIZZLE_NONE costs nothing over SWIZZLE_128B for these tiles; a bulk copy is issued from the uniform
+// datapath, one at a time per warp.
 #include <cstdlib>
 #include "nef_conv.cuh"
 
