@@ -717,84 +717,93 @@ __device__ __forceinline__ float4 bn_relu4(float4 c, float4 sc, float4 sh) {
                      fmaxf(c.w * sc.w + sh.w, 0.f));
 }
 
+// The elementwise decoder kernels run on a 2-D grid -- y = (4-channel chunk, segment), x = tiles of samples -- so that no
+// thread pays 64-bit divisions per element (they were ALU-bound on index arithmetic, not memory-bound).
+constexpr int EW_TPB = 128;   // threads per block
+constexpr int EW_PER = 4;     // samples per thread
+static inline dim3 ew_grid(int C, int B, int L) { return dim3((unsigned)((L + EW_TPB * EW_PER - 1) / (EW_TPB * EW_PER)), (unsigned)((C / 4) * B)); }
+
 // out = relu(bn(c)) ; with upsample: out = Upsample(x2, linear, align_corners=False)(relu(bn(c)))
-__global__ void bn_relu_kernel(T4 c, const float* __restrict__ scale, const float* __restrict__ shift, T4 out,
-                               int upsample) {
-  const long total = (long)(c.C / 4) * c.B * out.L;
-  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    const int l = i % out.L;
-    long r = i / out.L;
-    const int b = r % c.B;
-    const int c4 = r / c.B;
-    const float4 sc = reinterpret_cast<const float4*>(scale)[c4], sh = reinterpret_cast<const float4*>(shift)[c4];
+__global__ void __launch_bounds__(EW_TPB) bn_relu_kernel(T4 c, const float* __restrict__ scale, const float* __restrict__ shift,
+                                                         T4 out, int upsample) {
+  const int c4 = blockIdx.y / c.B, b = blockIdx.y - c4 * c.B;
+  const float4 sc = reinterpret_cast<const float4*>(scale)[c4], sh = reinterpret_cast<const float4*>(shift)[c4];
+  const float4* cp = c.at(c4, b, 0);
+  float4* op = out.at(c4, b, 0);
+  const int l0 = blockIdx.x * (EW_TPB * EW_PER) + threadIdx.x;
+#pragma unroll
+  for (int k = 0; k < EW_PER; ++k) {
+    const int l = l0 + k * EW_TPB;
+    if (l >= out.L) break;
     float4 v;
     if (!upsample) {
-      v = bn_relu4(*c.at(c4, b, l), sc, sh);
+      v = bn_relu4(cp[l], sc, sh);
     } else {
       const int li = l >> 1;
-      const float4 a1 = bn_relu4(*c.at(c4, b, li), sc, sh);
+      const float4 a1 = bn_relu4(cp[li], sc, sh);
       if ((l & 1) == 0) {
-        const float4 a0 = li > 0 ? bn_relu4(*c.at(c4, b, li - 1), sc, sh) : a1;
+        const float4 a0 = li > 0 ? bn_relu4(cp[li - 1], sc, sh) : a1;
         v = a0 * 0.25f + a1 * 0.75f;
       } else {
-        const float4 a2 = li + 1 < c.L ? bn_relu4(*c.at(c4, b, li + 1), sc, sh) : a1;
+        const float4 a2 = li + 1 < c.L ? bn_relu4(cp[li + 1], sc, sh) : a1;
         v = a1 * 0.75f + a2 * 0.25f;
       }
     }
-    *out.at(c4, b, l) = tf32_rn4(v);
+    op[l] = tf32_rn4(v);
   }
 }
 int bn_relu(T4 c, const float* scale, const float* shift, T4 out, int upsample, cudaStream_t s) {
-  const long total = (long)(c.C / 4) * c.B * out.L;
-  bn_relu_kernel<<<grid_for(total, 256), 256, 0, s>>>(c, scale, shift, out, upsample);
+  bn_relu_kernel<<<ew_grid(c.C, c.B, out.L), EW_TPB, 0, s>>>(c, scale, shift, out, upsample);
   NEF_CHECK_LAUNCH("bn_relu_kernel");
   return 0;
 }
 
 // adjoint of Upsample(x2, linear, align_corners=False): (C, 2n) -> (C, n)
-__global__ void up_adjoint_kernel(T4 du, T4 da) {
-  const long total = (long)(da.C / 4) * da.B * da.L;
+__global__ void __launch_bounds__(EW_TPB) up_adjoint_kernel(T4 du, T4 da) {
   const int n = da.L;
-  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    const int l = i % n;
-    long r = i / n;
-    const int b = r % da.B;
-    const int c4 = r / da.B;
-    const float4* p = du.at(c4, b, 0);
+  const int c4 = blockIdx.y / da.B, b = blockIdx.y - c4 * da.B;
+  const float4* p = du.at(c4, b, 0);
+  float4* o = da.at(c4, b, 0);
+  const int l0 = blockIdx.x * (EW_TPB * EW_PER) + threadIdx.x;
+#pragma unroll
+  for (int k = 0; k < EW_PER; ++k) {
+    const int l = l0 + k * EW_TPB;
+    if (l >= n) break;
     float4 d = p[2 * l] * 0.75f + p[2 * l + 1] * 0.75f;
     if (l + 1 < n) d = d + p[2 * l + 2] * 0.25f;
     if (l >= 1) d = d + p[2 * l - 1] * 0.25f;
     if (l == 0) d = d + p[0] * 0.25f;
     if (l == n - 1) d = d + p[2 * n - 1] * 0.25f;
-    *da.at(c4, b, l) = d;
+    o[l] = d;
   }
 }
 int up_adjoint(T4 du, T4 da, cudaStream_t s) {
-  const long total = (long)(da.C / 4) * da.B * da.L;
-  up_adjoint_kernel<<<grid_for(total, 256), 256, 0, s>>>(du, da);
+  up_adjoint_kernel<<<ew_grid(da.C, da.B, da.L), EW_TPB, 0, s>>>(du, da);
   NEF_CHECK_LAUNCH("up_adjoint_kernel");
   return 0;
 }
 
 // BatchNorm backward, pass 1: g = da * (bn(c) > 0);  s1 += sum g ; s2 += sum g * xhat      (per channel)
-// grid (row tiles, C/4); block 256
-__global__ void __launch_bounds__(256) bnbwd_stats_kernel(T4 da, T4 c, BnLayer bn) {
+// grid (sample tiles x segment groups, C/4); block 256
+__global__ void __launch_bounds__(256) bnbwd_stats_kernel(T4 da, T4 c, BnLayer bn, int seg_per_block) {
   __shared__ float red[8][8];
   const int c4 = blockIdx.y;
   const float4 sc = reinterpret_cast<const float4*>(bn.scale)[c4], sh = reinterpret_cast<const float4*>(bn.shift)[c4];
   const float4 mu = reinterpret_cast<const float4*>(bn.mean)[c4], is = reinterpret_cast<const float4*>(bn.invstd)[c4];
   float4 s1 = f4zero(), s2 = f4zero();
-  const long total = (long)c.B * c.L;
-  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    const int l = i % c.L;
-    const int b = i / c.L;
-    const float4 cv = *c.at(c4, b, l), dv = *da.at(c4, b, l);
+  const int b0 = blockIdx.x * seg_per_block, b1 = min(c.B, b0 + seg_per_block);
+  for (int b = b0; b < b1; ++b) {
+    const float4* cp = c.at(c4, b, 0);
+    const float4* dp = da.at(c4, b, 0);
+    for (int l = threadIdx.x; l < c.L; l += 256) {
+      const float4 cv = cp[l], dv = dp[l];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float x = f4get(cv, k);
-      const float g = (x * f4get(sc, k) + f4get(sh, k)) > 0.f ? f4get(dv, k) : 0.f;
-      f4at(s1, k) += g;
-      f4at(s2, k) += g * (x - f4get(mu, k)) * f4get(is, k);
+      for (int k = 0; k < 4; ++k) {
+        const float x = f4get(cv, k);
+        const float g = (x * f4get(sc, k) + f4get(sh, k)) > 0.f ? f4get(dv, k) : 0.f;
+        f4at(s1, k) += g;
+        f4at(s2, k) += g * (x - f4get(mu, k)) * f4get(is, k);
+      }
     }
   }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -815,39 +824,49 @@ __global__ void __launch_bounds__(256) bnbwd_stats_kernel(T4 da, T4 c, BnLayer b
   }
 }
 int bnbwd_stats(T4 da, T4 c, const BnLayer& bn, cudaStream_t s) {
-  const long total = (long)c.B * c.L;
-  int gx = (int)((total + 256 * 8 - 1) / (256 * 8));
-  if (gx < 1) gx = 1;
-  if (gx > 148 * 4) gx = 148 * 4;
-  dim3 grid(gx, c.C / 4);
-  bnbwd_stats_kernel<<<grid, 256, 0, s>>>(da, c, bn);
+  // about 148 * 8 blocks: segments per block so that (B / spb) * (C / 4) covers the GPU a few times
+  int spb = (int)(((long)c.B * (c.C / 4) + 148 * 8 - 1) / (148 * 8));
+  if (spb < 1) spb = 1;
+  dim3 grid((c.B + spb - 1) / spb, c.C / 4);
+  bnbwd_stats_kernel<<<grid, 256, 0, s>>>(da, c, bn, spb);
   NEF_CHECK_LAUNCH("bnbwd_stats_kernel");
   return 0;
 }
 
 // pass 2: dc = gamma * invstd * (g - s1/N - xhat * s2/N) ; dgamma += s2 ; dbeta += s1
-__global__ void bnbwd_apply_kernel(T4 da, T4 c, BnLayer bn, const float* __restrict__ gamma, double count, T4 dc,
-                                   float* dgamma, float* dbeta) {
-  const long total = (long)(c.C / 4) * c.B * c.L;
+__global__ void __launch_bounds__(EW_TPB) bnbwd_apply_kernel(T4 da, T4 c, BnLayer bn, const float* __restrict__ gamma, double count,
+                                                             T4 dc, float* dgamma, float* dbeta) {
   const float invn = (float)(1.0 / count);
-  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    const int l = i % c.L;
-    long r = i / c.L;
-    const int b = r % c.B;
-    const int c4 = r / c.B;
-    const float4 cv = *c.at(c4, b, l), dv = *da.at(c4, b, l);
+  const int c4 = blockIdx.y / c.B, b = blockIdx.y - c4 * c.B;
+  float sc[4], sh[4], mu[4], is[4], gi[4], m1[4], m2[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int ch = c4 * 4 + k;
+    sc[k] = bn.scale[ch]; sh[k] = bn.shift[ch]; mu[k] = bn.mean[ch]; is[k] = bn.invstd[ch];
+    gi[k] = gamma[ch] * is[k];
+    m1[k] = (float)bn.s1[ch] * invn;
+    m2[k] = (float)bn.s2[ch] * invn;
+  }
+  const float4* cp = c.at(c4, b, 0);
+  const float4* dp = da.at(c4, b, 0);
+  float4* op = dc.at(c4, b, 0);
+  const int l0 = blockIdx.x * (EW_TPB * EW_PER) + threadIdx.x;
+#pragma unroll
+  for (int j = 0; j < EW_PER; ++j) {
+    const int l = l0 + j * EW_TPB;
+    if (l >= c.L) break;
+    const float4 cv = cp[l], dv = dp[l];
     float4 o;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const int ch = c4 * 4 + k;
       const float x = f4get(cv, k);
-      const float g = (x * bn.scale[ch] + bn.shift[ch]) > 0.f ? f4get(dv, k) : 0.f;
-      const float xhat = (x - bn.mean[ch]) * bn.invstd[ch];
-      f4at(o, k) = gamma[ch] * bn.invstd[ch] * (g - (float)bn.s1[ch] * invn - xhat * (float)bn.s2[ch] * invn);
+      const float g = (x * sc[k] + sh[k]) > 0.f ? f4get(dv, k) : 0.f;
+      const float xhat = (x - mu[k]) * is[k];
+      f4at(o, k) = gi[k] * (g - m1[k] - xhat * m2[k]);
     }
-    *dc.at(c4, b, l) = tf32_rn4(o);
+    op[l] = tf32_rn4(o);
   }
-  if (blockIdx.x == 0) {
+  if (blockIdx.x == 0 && blockIdx.y == 0) {
     for (int ch = threadIdx.x; ch < c.C; ch += blockDim.x) {
       if (dgamma) dgamma[ch] += (float)bn.s2[ch];
       if (dbeta) dbeta[ch] += (float)bn.s1[ch];
@@ -856,8 +875,7 @@ __global__ void bnbwd_apply_kernel(T4 da, T4 c, BnLayer bn, const float* __restr
 }
 int bnbwd_apply(T4 da, T4 c, const BnLayer& bn, const float* gamma, double count, T4 dc, float* dgamma, float* dbeta,
                 cudaStream_t s) {
-  const long total = (long)(c.C / 4) * c.B * c.L;
-  bnbwd_apply_kernel<<<grid_for(total, 256), 256, 0, s>>>(da, c, bn, gamma, count, dc, dgamma, dbeta);
+  bnbwd_apply_kernel<<<ew_grid(c.C, c.B, c.L), EW_TPB, 0, s>>>(da, c, bn, gamma, count, dc, dgamma, dbeta);
   NEF_CHECK_LAUNCH("bnbwd_apply_kernel");
   return 0;
 }
