@@ -67,6 +67,19 @@ def algorithmic_bytes_per_segment(G, L, n_dec=3, live=True):
     return 4.0 * fl
 
 
+def forward_report(ms_fwd, world, B, G, L, hbm_peak):
+    """Training-mode forward alone against the HBM roofline, with both byte conventions of SURVEY 8(d): 'nominal'
+    (every reference block, 286.0 MB/segment at 12 x 5000) and 'live' (what this dataflow has to move)."""
+    nominal = algorithmic_bytes_per_segment(G, L, live=False) * B
+    live = algorithmic_bytes_per_segment(G, L, live=True) * B
+    sec = ms_fwd / 1000.0
+    return {"ms": ms_fwd, "segments_per_s": world * B / sec,
+            "algorithmic_gb_nominal": nominal / 1e9, "hbm_frac_nominal": nominal / sec / 1e9 / hbm_peak,
+            "algorithmic_gb_live": live / 1e9, "hbm_frac_live": live / sec / 1e9 / hbm_peak,
+            "what": "max over ranks of the training-mode forward (dropout, BN batch statistics, 3 decoder passes, "
+                    "activations saved for backward) per GPU"}
+
+
 class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
@@ -261,6 +274,13 @@ def main():
     ms = timed(lambda: step(resident), args.steps)
     launches = lib.nef_launch_count() - l0
 
+    # forward only (the north-star's "fused encoder+decoder forward" target): the same training-mode forward with its
+    # activations saved for backward (dropout, BN batch statistics, 3 decoder passes), no loss / backward / SGD
+    def fwd_only():
+        model(resident["x"], resident["input_thetas"], resident["query_theta"], resident["rois"], phase="train")
+    fwd_only()
+    ms_fwd = timed(fwd_only, args.steps) / args.steps
+
     def e2e_step():
         inp = {k: host[k].to(dev, non_blocking=True) for k in ("x", "input_thetas", "query_theta", "rois", "target")}
         return float(step(inp).detach().cpu())
@@ -304,6 +324,7 @@ def main():
                              "kernel_tensor_frac": kflops / (kms / 1000.0) / 1e12 / tf32_peak,
                              "step_algorithmic_gb": step_bytes / 1e9,
                              "step_hbm_frac": step_bytes / (ms_step / 1000.0) / 1e9 / hbm_peak},
+                "forward": forward_report(ms_fwd, world, B, G, L, hbm_peak),
                 }
     if world > 1:
         dist.barrier()

@@ -16,10 +16,13 @@ static inline int grid_for(long total, int block, int cap = 148 * 32) {
 // Encoder stem: Conv1d(G -> 128G, k15, s2, p7, groups=G, no bias) -> ReLU -> MaxPool1d(3,2,1)
 // network/encoder/resnet_1d.py:102-105, network/encoder/encoder.py:35-38
 // ===========================================================================================
-constexpr int STEM_TJ = 128;
+constexpr int STEM_TJ = 256;  // pooled outputs per block
 
+// Per output element the kernel also records WHICH of the three pooled conv positions won (first maximum in window
+// order 2j-1, 2j, 2j+1, as MaxPool1d does) or 3 if the ReLU clipped it: one byte per channel, a uint32 per float4,
+// same row indexing as the activation.  stem_bwd routes the gradient with it instead of recomputing the convolution.
 __global__ void __launch_bounds__(256) stem_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, T4 y,
-                                                       int G, int L) {
+                                                       uint32_t* __restrict__ amax, int G, int L) {
   __shared__ float xs[4 * STEM_TJ + 24];
   __shared__ float4 ws[15][32];
   const int tid = threadIdx.x;
@@ -27,7 +30,7 @@ __global__ void __launch_bounds__(256) stem_fwd_kernel(const float* __restrict__
   const int j0 = blockIdx.x * STEM_TJ;
   const int L2 = L / 2, L4 = L / 4;
   const float* xb = x + ((long)b * G + g) * L;
-  for (int i = tid; i < 4 * STEM_TJ + 19; i += 256) {
+  for (int i = tid; i < 4 * STEM_TJ + 24; i += 256) {
     int p = 4 * j0 - 9 + i;
     xs[i] = (p >= 0 && p < L) ? xb[p] : 0.f;
   }
@@ -37,88 +40,132 @@ __global__ void __launch_bounds__(256) stem_fwd_kernel(const float* __restrict__
     ws[t][c4] = make_float4(wp[0], wp[15], wp[30], wp[45]);
   }
   __syncthreads();
-  const int jl = tid & (STEM_TJ - 1), chalf = tid / STEM_TJ;
+  // a thread owns two adjacent pooled outputs (j, j+1): their windows share conv position 2j+1, so five conv
+  // positions 2j-1 .. 2j+3 are evaluated instead of six
+  const int jl = 2 * (tid & (STEM_TJ / 2 - 1)), chalf = tid / (STEM_TJ / 2);
   const int j = j0 + jl;
   if (j >= L4) return;
-  float xr[19];
+  float xr[23];
 #pragma unroll
-  for (int k = 0; k < 19; ++k) xr[k] = xs[4 * jl + k];
-  const bool v0 = (2 * j - 1) >= 0, v2 = (2 * j + 1) < L2;
+  for (int k = 0; k < 23; ++k) xr[k] = xs[4 * jl + k];
+  const bool va = (2 * j - 1) >= 0;            // window of j: positions 2j-1 (if valid), 2j, 2j+1
+  const bool vb = (2 * j + 3) < L2, has_b = j + 1 < L4;
   for (int cc = 0; cc < 16; ++cc) {
     const int c4 = chalf * 16 + cc;
-    float4 a0 = f4zero(), a1 = f4zero(), a2 = f4zero();
+    float4 a[5];
+#pragma unroll
+    for (int e = 0; e < 5; ++e) a[e] = f4zero();
 #pragma unroll
     for (int t = 0; t < 15; ++t) {
       const float4 wv = ws[t][c4];
-      a0 = a0 + wv * xr[t];
-      a1 = a1 + wv * xr[2 + t];
-      a2 = a2 + wv * xr[4 + t];
+#pragma unroll
+      for (int e = 0; e < 5; ++e) a[e] = a[e] + wv * xr[2 * e + t];
     }
-    float4 m = a1;
-    if (v0) m = make_float4(fmaxf(m.x, a0.x), fmaxf(m.y, a0.y), fmaxf(m.z, a0.z), fmaxf(m.w, a0.w));
-    if (v2) m = make_float4(fmaxf(m.x, a2.x), fmaxf(m.y, a2.y), fmaxf(m.z, a2.z), fmaxf(m.w, a2.w));
-    m = make_float4(fmaxf(m.x, 0.f), fmaxf(m.y, 0.f), fmaxf(m.z, 0.f), fmaxf(m.w, 0.f));
-    *y.at(g * 32 + c4, b, j) = tf32_rn4(m);
+    float4 m0, m1;
+    uint32_t code0 = 0, code1 = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      {
+        const float c0 = f4get(a[0], k), c1 = f4get(a[1], k), c2 = f4get(a[2], k);
+        uint32_t best = 1;
+        float bv = c1;
+        if (va && c0 >= c1) { best = 0; bv = c0; }   // first maximum wins (window order)
+        if (c2 > bv) { best = 2; bv = c2; }          // 2j+1 < L2 always
+        if (!(bv > 0.f)) { best = 3; bv = 0.f; }
+        f4at(m0, k) = bv;
+        code0 |= best << (8 * k);
+      }
+      {
+        const float c0 = f4get(a[2], k), c1 = f4get(a[3], k), c2 = f4get(a[4], k);
+        uint32_t best = 1;
+        float bv = c1;
+        if (c0 >= c1) { best = 0; bv = c0; }
+        if (vb && c2 > bv) { best = 2; bv = c2; }
+        if (!(bv > 0.f)) { best = 3; bv = 0.f; }
+        f4at(m1, k) = bv;
+        code1 |= best << (8 * k);
+      }
+    }
+    const long off = (long)(g * 32 + c4) * y.cs + y.row(b, j);
+    y.p[off] = tf32_rn4(m0);
+    if (has_b) y.p[off + 1] = tf32_rn4(m1);
+    if (amax) {
+      amax[off] = code0;
+      if (has_b) amax[off + 1] = code1;
+    }
   }
 }
 
 constexpr int STEMB_TJ = 256;
 
-// weight gradient of the stem (the input needs none): recompute the three conv taps of every pooled
-// output, route the gradient to the first maximum (MaxPool1d) if it is positive (ReLU).
-__global__ void __launch_bounds__(256) stem_bwd_kernel(const float* __restrict__ x, const float* __restrict__ w, T4 dy,
-                                                       float* __restrict__ dw, int G, int L) {
-  __shared__ float xs[4 * STEMB_TJ + 24];
+// Weight gradient of the stem (the input needs none).  The pooled gradient of (channel, j) goes to conv position
+// 2j-1+code; positions 2j-1 (code 0 of j, code 2 of j-1) and 2j (code 1 of j) are accumulated per step, so every conv
+// position costs its 15 taps once:  dW[c][t] += gA * x[4j-9+t] + gB * x[4j-7+t].
+// One warp per 32 consecutive j of one (segment, lead); lane = 4-channel chunk.
+__global__ void __launch_bounds__(256, 2) stem_bwd_kernel(const float* __restrict__ x, const uint32_t* __restrict__ amax,
+                                                          T4 dy, float* __restrict__ dw, int G, int L) {
+  __shared__ __align__(16) float xs[4 * STEMB_TJ + 24];
   __shared__ float sdw[15][128];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = blockIdx.y, b = blockIdx.z;
   const int j0 = blockIdx.x * STEMB_TJ;
-  const int L2 = L / 2, L4 = L / 4;
+  const int L4 = L / 4;
   const float* xb = x + ((long)b * G + g) * L;
-  for (int i = tid; i < 4 * STEMB_TJ + 19; i += 256) {
+  for (int i = tid; i < 4 * STEMB_TJ + 24; i += 256) {
     int p = 4 * j0 - 9 + i;
     xs[i] = (p >= 0 && p < L) ? xb[p] : 0.f;
   }
   for (int i = tid; i < 15 * 128; i += 256) (&sdw[0][0])[i] = 0.f;
-  float4 wv[15], acc[15];
+  float4 acc[15];
 #pragma unroll
-  for (int t = 0; t < 15; ++t) {
-    const float* wp = w + ((long)g * 128 + lane * 4) * 15 + t;
-    wv[t] = make_float4(wp[0], wp[15], wp[30], wp[45]);
-    acc[t] = f4zero();
-  }
+  for (int t = 0; t < 15; ++t) acc[t] = f4zero();
   __syncthreads();
-  for (int jj = 0; jj < 32; ++jj) {
-    const int jl = warp * 32 + jj;
-    const int j = j0 + jl;
-    if (j >= L4) break;
-    const float4 gy = *dy.at(g * 32 + lane, b, j);
-    float xr[19];
+  const long base = (long)(g * 32 + lane) * dy.cs + dy.row(b, 0);
+  const float4* gp = dy.p + base;
+  const uint32_t* ap = amax + base;
+  const int jw = j0 + warp * 32;
+  float4 carry = f4zero();   // gradient of j-1 that belongs to conv position 2j-1 (its code 2)
+  if (jw > 0 && jw < L4) {
+    const float4 gq = gp[jw - 1];
+    const uint32_t cq = ap[jw - 1];
 #pragma unroll
-    for (int k = 0; k < 19; ++k) xr[k] = xs[4 * jl + k];
-    float4 a0 = f4zero(), a1 = f4zero(), a2 = f4zero();
+    for (int k = 0; k < 4; ++k) f4at(carry, k) = ((cq >> (8 * k)) & 0xffu) == 2u ? f4get(gq, k) : 0.f;
+  }
+  constexpr int CH = 4;      // j per batch of loads
+  for (int jj = 0; jj < 32; jj += CH) {
+    if (jw + jj >= L4) break;
+    float4 gv[CH];
+    uint32_t cv[CH];
 #pragma unroll
-    for (int t = 0; t < 15; ++t) {
-      a0 = a0 + wv[t] * xr[t];
-      a1 = a1 + wv[t] * xr[2 + t];
-      a2 = a2 + wv[t] * xr[4 + t];
-    }
-    const bool v0 = (2 * j - 1) >= 0, v2 = (2 * j + 1) < L2;
-    float4 s0 = f4zero(), s1 = f4zero(), s2 = f4zero();
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float c0 = f4get(a0, k), c1 = f4get(a1, k), c2 = f4get(a2, k);
-      int best = 1;
-      float bv = c1;
-      if (v0 && c0 >= c1) { best = 0; bv = c0; }   // first maximum wins (window order 2j-1, 2j, 2j+1)
-      if (v2 && c2 > bv) { best = 2; bv = c2; }
-      const float gk = bv > 0.f ? f4get(gy, k) : 0.f;
-      f4at(s0, k) = best == 0 ? gk : 0.f;
-      f4at(s1, k) = best == 1 ? gk : 0.f;
-      f4at(s2, k) = best == 2 ? gk : 0.f;
+    for (int u = 0; u < CH; ++u) {
+      const bool ok = jw + jj + u < L4;
+      gv[u] = ok ? gp[jw + jj + u] : f4zero();
+      cv[u] = ok ? ap[jw + jj + u] : 0x03030303u;
     }
 #pragma unroll
-    for (int t = 0; t < 15; ++t) acc[t] = acc[t] + s0 * xr[t] + s1 * xr[2 + t] + s2 * xr[4 + t];
+    for (int u = 0; u < CH; ++u) {
+      const int jl = warp * 32 + jj + u;
+      float xr[20];
+#pragma unroll
+      for (int q = 0; q < 5; ++q) *reinterpret_cast<float4*>(&xr[4 * q]) = *reinterpret_cast<const float4*>(&xs[4 * jl + 4 * q]);
+      float4 gA, gB, nc;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t c = (cv[u] >> (8 * k)) & 0xffu;
+        const float gk = f4get(gv[u], k);
+        f4at(gA, k) = f4get(carry, k) + (c == 0u ? gk : 0.f);
+        f4at(gB, k) = c == 1u ? gk : 0.f;
+        f4at(nc, k) = c == 2u ? gk : 0.f;
+      }
+      carry = nc;
+#pragma unroll
+      for (int t = 0; t < 15; ++t) acc[t] = acc[t] + gA * xr[t] + gB * xr[2 + t];
+      if (j0 + jl == L4 - 1) {  // last pooled window of the segment: its code 2 has no successor to carry into
+#pragma unroll
+        for (int t = 0; t < 15; ++t) acc[t] = acc[t] + carry * xr[4 + t];
+        carry = f4zero();
+      }
+    }
   }
 #pragma unroll
   for (int t = 0; t < 15; ++t) {
@@ -135,17 +182,17 @@ __global__ void __launch_bounds__(256) stem_bwd_kernel(const float* __restrict__
   }
 }
 
-int stem_fwd(const float* x, const float* w, T4 y, int G, cudaStream_t s) {
+int stem_fwd(const float* x, const float* w, T4 y, uint32_t* amax, int G, cudaStream_t s) {
   const int L = y.L * 4;
   dim3 grid((y.L + STEM_TJ - 1) / STEM_TJ, G, y.B);
-  stem_fwd_kernel<<<grid, 256, 0, s>>>(x, w, y, G, L);
+  stem_fwd_kernel<<<grid, 256, 0, s>>>(x, w, y, amax, G, L);
   NEF_CHECK_LAUNCH("stem_fwd_kernel");
   return 0;
 }
-int stem_bwd(const float* x, const float* w, T4 dy, float* dw, int G, cudaStream_t s) {
+int stem_bwd(const float* x, const uint32_t* amax, T4 dy, float* dw, int G, cudaStream_t s) {
   const int L = dy.L * 4;
   dim3 grid((dy.L + STEMB_TJ - 1) / STEMB_TJ, G, dy.B);
-  stem_bwd_kernel<<<grid, 256, 0, s>>>(x, w, dy, dw, G, L);
+  stem_bwd_kernel<<<grid, 256, 0, s>>>(x, amax, dy, dw, G, L);
   NEF_CHECK_LAUNCH("stem_bwd_kernel");
   return 0;
 }
@@ -438,6 +485,7 @@ __device__ __forceinline__ void interp_src(int i, int n, int& i0, int& i1, float
 }
 
 constexpr int LAT_TL = 256;  // latent positions per inner tile
+constexpr int LAT_GB = 12;   // leads whose loads are batched in the backward kernel
 
 __global__ void __launch_bounds__(256) latent_fwd_kernel(const LatentArgs a) {
   extern __shared__ float4 sm[];
@@ -552,7 +600,7 @@ int latent_fwd(const LatentArgs& a, cudaStream_t s) {
 }
 
 // Backward of the above.  d lat_k = q * up^T(d u0_k);  d q += sum lat_k * up^T(d u0_k)
-__global__ void __launch_bounds__(256) latent_bwd_kernel(const LatentBwdArgs a) {
+__global__ void __launch_bounds__(256, 3) latent_bwd_kernel(const LatentBwdArgs a) {
   extern __shared__ float4 sm[];
   const int L4 = a.z1.L;
   const int b = blockIdx.x, cc = blockIdx.y, half = blockIdx.z;
@@ -573,7 +621,7 @@ __global__ void __launch_bounds__(256) latent_bwd_kernel(const LatentBwdArgs a) 
   float4 dq = f4zero();
   const int L2 = 2 * L4;
   for (int l = tid; l < L4; l += 256) {
-    float4 dm = f4zero(), dp = f4zero();
+    float4 dk[3];
 #pragma unroll
     for (int k3 = 0; k3 < 3; ++k3) {
       const float4* du = a.du0[k3].at(latc, b, 0);
@@ -582,30 +630,31 @@ __global__ void __launch_bounds__(256) latent_bwd_kernel(const LatentBwdArgs a) 
       if (l >= 1) d = d + du[2 * l - 1] * 0.25f;
       if (l == 0) d = d + du[0] * 0.25f;
       if (l == L4 - 1) d = d + du[L2 - 1] * 0.25f;
-      dq = dq + d * (*a.lat[k3].at(latc, b, l));
-      d = d * qv;
-      const bool use_pick = (k3 == 1 && half == 0) || (k3 == 2 && half == 1);
-      if (use_pick) dp = dp + d;
-      else dm = dm + d;
+      dk[k3] = d;
     }
     if (half == 0) {
-      const float4 dmg = dm * invG;
-      for (int g0 = 0; g0 < a.G; g0 += 4) {  // four leads at a time: their loads are in flight together
-        float4 z[4];
+      // lat_0 = lat_2 = mean over leads, lat_1 = lead c1 (this half): both are rebuilt from the z1 loads the ReLU mask
+      // needs anyway (same summation order as latent_fwd), so the stored latents are not re-read.
+      const float4 dmg = (dk[0] + dk[2]) * qv * invG, dp = dk[1] * qv;
+      float4 msum = f4zero(), pick = f4zero();
+      for (int g0 = 0; g0 < a.G; g0 += LAT_GB) {  // LAT_GB leads at a time: their loads are in flight together
+        float4 z[LAT_GB];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) z[k] = (g0 + k < a.G) ? __ldg(a.z1.at((g0 + k) * 32 + cc, b, l)) : f4zero();
+        for (int k = 0; k < LAT_GB; ++k) z[k] = (g0 + k < a.G) ? __ldg(a.z1.at((g0 + k) * 32 + cc, b, l)) : f4zero();
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
+        for (int k = 0; k < LAT_GB; ++k) {
           const int g = g0 + k;
           if (g < a.G) {
+            msum = msum + z[k];
             float4 gsum = dmg;
-            if (g == a.c1) gsum = gsum + dp;
+            if (g == a.c1) { gsum = gsum + dp; pick = z[k]; }
             gsum = make_float4(z[k].x > 0.f ? gsum.x : 0.f, z[k].y > 0.f ? gsum.y : 0.f, z[k].z > 0.f ? gsum.z : 0.f,
                                z[k].w > 0.f ? gsum.w : 0.f);
             *a.gz1.at(g * 32 + cc, b, l) = tf32_rn4(gsum);
           }
         }
       }
+      dq = dq + (dk[0] + dk[2]) * (msum * invG) + dk[1] * pick;
     } else {
       int j = 0;
       while (j < NEF_NROI - 1 && l >= tab.start[j + 1]) ++j;
@@ -613,6 +662,10 @@ __global__ void __launch_bounds__(256) latent_bwd_kernel(const LatentBwdArgs a) 
       int i0, i1;
       float lam;
       interp_src(l - tab.start[j], n > 0 ? n : 1, i0, i1, lam);
+      // lat_0 = lat_1 = mean (this half), lat_2 = lead c2
+      const float4 lm = *a.lat[0].at(latc, b, l), lp = *a.lat[2].at(latc, b, l);
+      dq = dq + (dk[0] + dk[1]) * lm + dk[2] * lp;
+      const float4 dm = (dk[0] + dk[1]) * qv, dp = dk[2] * qv;
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const float vm = f4get(dm, k), vp = f4get(dp, k);

@@ -49,6 +49,14 @@ extern "C" int nef_set_conv_impl(int impl) {
   return 0;
 }
 extern "C" int nef_get_conv_impl(void) { return g_conv_impl; }
+// Decoder first conv (256 -> 128 on the query-scaled latent): number of split-precision terms.
+//   3: x_hi w_hi + x_lo w_hi + x_hi w_lo   2: x_hi w_hi + x_lo w_hi   1: x_hi w_hi only
+static int g_dec1_terms = 3;
+extern "C" int nef_set_dec1_terms(int n) {
+  NEF_REQUIRE(n >= 1 && n <= 3, "nef_set_dec1_terms: 1, 2 or 3");
+  g_dec1_terms = n;
+  return 0;
+}
 extern "C" int nef_set_exact_simt(int on);
 extern "C" int nef_set_exact_elem(int on);
 extern "C" int nef_set_exact_tc(int on);
@@ -183,6 +191,7 @@ struct NefPlan {
   T4 lat[3], u0[3], u0lo[3];
   DecBufs dec[3];
   float *s_in, *q, *rq;
+  uint32_t* s0_amax;      // stem max-pool argmax / ReLU codes, indexed like s0
   // gradients
   T4 GA[3];
   T4 gz2o, gh22, dt21, dte, dto, gy20, gh20, dra, gz2c, ghz, gxw;
@@ -234,6 +243,7 @@ static void carve(NefPlan* p, bool dry) {
   c.take(NEF_GUARD_ROWS * sizeof(float4));  // front guard
   const int G = p->G, C1 = p->C1, L4 = p->L4, L2 = p->L2, L = p->L, B = p->B;
   p->s0 = c.t4(C1, L4);
+  p->s0_amax = reinterpret_cast<uint32_t*>(c.take(((size_t)(C1 / 4) * p->s0.cs + NEF_GUARD_ROWS) * sizeof(uint32_t)));
   for (int i = 0; i < 3; ++i) { p->eh[i] = c.t4(C1, L4); p->ey[i] = c.t4(C1, L4); }
   p->hw = c.t4(C1, L4); p->w = c.t4(C1, L4); p->h1 = c.t4(C1, L4); p->z1 = c.t4(C1, L4);
   p->xw = c.t4(64 * G, p->win.Lw); p->hz = c.t4(C1, p->win.Lw); p->z2c = c.t4(C1, p->win.Lw);
@@ -471,8 +481,8 @@ static int decoder_fwd(NefPlan* p, const float* const* P, int slot, const T4& u0
     CD c(1, l.w->cout_g, l.in);
     c.term(l.in, 0, 0, l.w->cin_g, 3, l.w->pk_f).out(l.c, 0, 0).bias(P[l.pb]);
     if (i == 0) {  // split precision: x_hi w_hi + x_lo w_hi + x_hi w_lo  (this layer dominates the TF32 error budget)
-      c.term(u0lo, 0, 0, 256, 3, l.w->pk_f);
-      c.term(l.in, 0, 0, 256, 3, p->dec1_lo);
+      if (g_dec1_terms >= 2) c.term(u0lo, 0, 0, 256, 3, l.w->pk_f);
+      if (g_dec1_terms >= 3) c.term(l.in, 0, 0, 256, 3, p->dec1_lo);
     }
     if (training) c.stats(d.bn[i].sum, d.bn[i].sq);
     RUN(c.run(s));
@@ -538,7 +548,7 @@ extern "C" int nef_forward(NefPlan* p, const NefForwardArgs* a, nef_stream_t sv)
   for (int t = 0; t < 2; ++t)  // ConvTranspose1d weight (Cin_total, Cout/groups, 2): one 1x1 conv per tap
     RUN(nef_pack_weights(P[P_CT_W] + t, p->ct_f[t], 7 * G, 64, 128, 1, 128LL * 64 * 2, 2, 64 * 2, 0, 0, sv));
 
-  RUN(stem_fwd(a->x, P[P_STEM], p->s0, G, s));
+  RUN(stem_fwd(a->x, P[P_STEM], p->s0, a->save_for_backward ? p->s0_amax : nullptr, G, s));
   RUN(angular_fwd(a->input_thetas, P[P_MLP1_W], P[P_MLP1_B], p->s_in, B * G, 128, s));
   const float dp = a->drop_p;
   const uint64_t seed = a->drop_seed * 16;
@@ -784,7 +794,7 @@ extern "C" int nef_backward(NefPlan* p, const NefBackwardArgs* a, nef_stream_t s
       RUN(block_bwd(bb, dp, fin, s));
       gy_i = gx_i;
     }
-    if (Gd[P_STEM]) RUN(stem_bwd(p->x_in, P[P_STEM], p->GA[gy_i], Gd[P_STEM], G, s));
+    if (Gd[P_STEM]) RUN(stem_bwd(p->x_in, p->s0_amax, p->GA[gy_i], Gd[P_STEM], G, s));
   }
   return 0;
 }
@@ -798,12 +808,14 @@ static T4 view_t4(const float* ptr, int C, int B, int L) {
   t.C = C; t.B = B; t.L = L; t.Lp = L + 2 * NEF_HALO; t.cs = (long)B * t.Lp;
   return t;
 }
-extern "C" int nef_stem_fwd(const float* x, const float* w, float* y, int B, int G, int L, nef_stream_t s) {
-  return stem_fwd(x, w, view_t4(y, 128 * G, B, L / 4), G, (cudaStream_t)s);
-}
-extern "C" int nef_stem_bwd(const float* x, const float* w, const float* dy, float* dw, int B, int G, int L,
+extern "C" int nef_stem_fwd(const float* x, const float* w, float* y, uint32_t* argmax, int B, int G, int L,
                             nef_stream_t s) {
-  return stem_bwd(x, w, view_t4(dy, 128 * G, B, L / 4), dw, G, (cudaStream_t)s);
+  return stem_fwd(x, w, view_t4(y, 128 * G, B, L / 4), argmax, G, (cudaStream_t)s);
+}
+extern "C" int nef_stem_bwd(const float* x, const uint32_t* argmax, const float* dy, float* dw, int B, int G, int L,
+                            nef_stream_t s) {
+  NEF_REQUIRE(argmax, "nef_stem_bwd: the argmax codes written by nef_stem_fwd are required");
+  return stem_bwd(x, argmax, view_t4(dy, 128 * G, B, L / 4), dw, G, (cudaStream_t)s);
 }
 extern "C" int nef_angular_fwd(const float* theta, const float* w, const float* b, float* out, int n, int D,
                                nef_stream_t s) {

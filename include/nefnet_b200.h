@@ -39,6 +39,9 @@ int nef_init(int device);
 /* 0 = CUDA-core fp32 implicit GEMM, 1 = tcgen05 TF32 (default when built in).  Test hook. */
 int nef_set_conv_impl(int impl);
 int nef_get_conv_impl(void);
+/* Split-precision terms of the decoder's first convolution (model_nefnet.py:101-103, DoubleConv conv 256 -> 128):
+ * 3 = x_hi w_hi + x_lo w_hi + x_hi w_lo (default), 2 = without x_hi w_lo, 1 = plain TF32.  Measurement hook. */
+int nef_set_dec1_terms(int n);
 /* Test hook: 1 = round nothing to TF32 (with conv impl 0 the whole path is then plain fp32 and can be
  * compared tightly with the fp32 oracle); 0 = production behaviour.  Synchronous, call between steps. */
 int nef_set_exact_fp32(int on);
@@ -209,8 +212,10 @@ int nef_sgd_step(float* p, const float* g, float* m, int64_t n, float lr, float 
 
 /* ---- single ops, exported for unit tests ---------------------------------------------------- */
 /* encoder stem, resnet_1d.py:102-105 + encoder.py:35-38: x (B,G,L) -> CBL4 (128G, L/4) */
-int nef_stem_fwd(const float* x, const float* w, float* y, int B, int G, int L, nef_stream_t s);
-int nef_stem_bwd(const float* x, const float* w, const float* dy, float* dw, int B, int G, int L, nef_stream_t s);
+/* argmax: one byte per output element (a uint32 per float4 row of y, same indexing): which pooled conv position won
+ * (0..2, MaxPool1d's first maximum) or 3 where the ReLU clipped; written by fwd (may be NULL), required by bwd. */
+int nef_stem_fwd(const float* x, const float* w, float* y, uint32_t* argmax, int B, int G, int L, nef_stream_t s);
+int nef_stem_bwd(const float* x, const uint32_t* argmax, const float* dy, float* dw, int B, int G, int L, nef_stream_t s);
 /* Angular encoding + Linear, theta_encoder.py:13-29 + model_nefnet.py:76-77: (n,2) -> (n,D) */
 int nef_angular_fwd(const float* theta, const float* w, const float* b, float* out, int n, int D, nef_stream_t s);
 int nef_angular_bwd(const float* theta, const float* dout, float* dw, float* db, int n, int D, nef_stream_t s);
