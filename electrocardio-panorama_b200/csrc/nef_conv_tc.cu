@@ -738,10 +738,12 @@ static_assert(WG_TOTAL <= 227 * 1024, "wgrad shared memory");
 //     MMAs are not bound by re-reading A from shared memory (N = 64 alone would be: tools/probe_rate.cu, 48 vs 32 cycles)
 //  swap == 1 (cout_g == 64, cin_g >= 128): D_tap[cin_tile x cout] = X^T(+tap) . dY   M = 128 input channels, N = 64; the
 //     shared operand is B: weight-stationary form (collector::b0)
-// CTAs that take different 64-channel halves do identical work on the same rows of the shared operand (L2 serves it).
-// grid: x = input-channel half (swap == 0), y = row split, z = group (x cin tile of 128 when swap == 1)
+//  wide (mode 2; cout_g == 128, cin_g % 128 == 0, <= 3 taps): as swap == 0 with N = 128 input channels per CTA
+//     (3 x 128 = 384 TMEM columns), so dY is staged and re-tiled once per 128 input channels instead of once per 64
+// CTAs that take different input-channel tiles do identical work on the same rows of the shared operand (L2 serves it).
+// grid: x = input-channel tile (swap == 0), y = row split, z = group (x cin tile of 128 when swap == 1)
 __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_constant__ NefWgradDesc d, int NT, long rows_per_split,
-                                                                 long rows_main, int swap) {
+                                                                 long rows_main, int mode) {
   extern __shared__ __align__(128) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
   const uint32_t tr0 = sbase + WG_NRAW * WG_RAW;
@@ -754,14 +756,15 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + WG_BAR_OFF + 8 * (2 * WG_NRAW + 2 * WG_NTR + 1));
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int swap = mode == 1, wide = mode == 2;
   const int ntile = swap ? d.cin_g / 128 : 1;
   const int g = blockIdx.z / ntile, nt = blockIdx.z % ntile;
   const int ntap = d.taps;
   const int half = blockIdx.x;                       // swap == 0: input channels [64 half, 64 half + 64)
   const int ych = d.cout_g >> 2;                     // dY chunks staged (all output channels of the group)
-  const int xch = swap ? 32 : 16;                    // X chunks staged
-  const int xch0 = swap ? nt * 32 : half * 16;       // first X chunk staged
-  constexpr int dcols = 64;                          // accumulator columns per tap
+  const int xch = (swap || wide) ? 32 : 16;          // X chunks staged
+  const int xch0 = swap ? nt * 32 : half * xch;      // first X chunk staged
+  const int dcols = wide ? 128 : 64;                 // accumulator columns per tap
   (void)NT;
   const long rbeg = (long)blockIdx.y * rows_per_split;
   const long rend = min(rows_main, rbeg + rows_per_split);
@@ -924,7 +927,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
           tmem_ld_wait();
           if (!swap) {
             if (lr < d.cout_g) {
-              float* dst = d.dw + (long)g * d.sg + (long)lr * d.sm + (long)(half * 64 + cg * 32) * d.sn + (long)tp * d.st;
+              float* dst = d.dw + (long)g * d.sg + (long)lr * d.sm + (long)(half * dcols + cg * 32) * d.sn + (long)tp * d.st;
 #pragma unroll
               for (int i = 0; i < 32; ++i) atomicAdd(dst + (long)i * d.sn, __uint_as_float(v[i]));
             }
@@ -1078,16 +1081,20 @@ extern "C" int nef_tc_debug_dump(unsigned long long* host_out, int n) {
   return cudaMemcpyFromSymbol(host_out, tc::g_tc_dbg, sizeof(unsigned long long) * 8 * n) == cudaSuccess ? 0 : 1;
 }
 
+static int g_wg_wide = 1;
+extern "C" int nef_tc_set_wgrad_wide(int on) { g_wg_wide = on; return 0; }  // A/B measurement hook
+
 extern "C" int nef_gconv_wgrad_tc(const NefWgradDesc* d, nef_stream_t s) {
   NEF_REQUIRE(d->cout_g == 64 || d->cout_g == 128, "nef_gconv_wgrad_tc: cout_g must be 64 or 128 (got %d)", d->cout_g);
   NEF_REQUIRE(d->cin_g % 64 == 0 && d->taps <= 7, "nef_gconv_wgrad_tc: cin_g %% 64 == 0 and at most 7 taps required (cin_g=%d taps=%d)",
               d->cin_g, d->taps);
   const int swap = (d->cout_g == 64 && d->cin_g % 128 == 0) ? 1 : 0;
-  const int NT = swap ? 128 : 64;
+  const int wide = (!swap && g_wg_wide && d->cout_g == 128 && d->cin_g % 128 == 0 && d->taps <= 3) ? 1 : 0;
+  const int NT = (swap || wide) ? 128 : 64;
   const long nst_total = d->rows / tc::WG_RROWS;
   const long rows_main = nst_total * tc::WG_RROWS;
   if (nst_total > 0) {
-    const int halves = swap ? 1 : d->cin_g / 64;
+    const int halves = swap ? 1 : d->cin_g / (wide ? 128 : 64);
     const int ztiles = swap ? d->groups * (d->cin_g / 128) : d->groups;
     const long tiles = (long)ztiles * halves;
     // row splits: the smallest count whose last wave is >= 90 % full (else the best seen)
@@ -1103,7 +1110,7 @@ extern "C" int nef_gconv_wgrad_tc(const NefWgradDesc* d, nef_stream_t s) {
     long st_per_split = (nst_total + best - 1) / best;
     const long splits = (nst_total + st_per_split - 1) / st_per_split;
     dim3 grid((unsigned)halves, (unsigned)splits, (unsigned)ztiles);
-    tc::wgrad_tc_kernel<<<grid, tc::WG_THREADS, tc::WG_TOTAL, (cudaStream_t)s>>>(*d, NT, st_per_split * tc::WG_RROWS, rows_main, swap);
+    tc::wgrad_tc_kernel<<<grid, tc::WG_THREADS, tc::WG_TOTAL, (cudaStream_t)s>>>(*d, NT, st_per_split * tc::WG_RROWS, rows_main, swap ? 1 : (wide ? 2 : 0));
     NEF_CHECK_LAUNCH("wgrad_tc_kernel");
   }
   if (rows_main < d->rows) {  // ragged tail (< 64 rows): CUDA-core kernel over [rows_main, rows), no bias term

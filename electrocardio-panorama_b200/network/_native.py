@@ -136,6 +136,9 @@ def init(device_index: int):
     if device_index not in _inited_devices:
         check(lib.nef_init(int(device_index)), "nef_init")
         _inited_devices.add(device_index)
+        terms = os.environ.get("NEF_DEC1_TERMS")  # measurement hook, see nef_set_dec1_terms
+        if terms:
+            check(lib.nef_set_dec1_terms(int(terms)), "nef_set_dec1_terms")
     return lib
 
 

@@ -47,6 +47,7 @@ CASES = [
     (64, 1250, 3, 128, 128, 7),   # enough tiles for the 4-row-tile kernel (the production configuration)
     (96, 2500, 1, 128, 64, 3),
     (200, 16, 14, 128, 128, 3),   # the z2 deflection branch shape (many groups, 16 samples)
+    (16, 1250, 2, 128, 128, 3),   # k3 128 -> 128 with many row stages (the wide weight-gradient tile)
 ]
 
 

@@ -29,6 +29,7 @@ EXACT_OUT_RTOL = 2e-5
 EXACT_GRAD_REL_L2 = 5e-3  # a single ReLU-mask flip at a pre-activation within 1 ulp of 0 costs ~2e-3 (see make_golden.py)
 TF32_GRAD_REL_L2 = 0.15
 TF32_GRAD_COS = 0.99
+GOLDEN_TF32_COS = 0.8   # golden L1-loss gradients at TF32: statistical (sign flips), see test_golden
 
 MODES = {"exact_simt": (0, 1), "tf32_simt": (0, 0), "tf32_tc": (1, 0)}
 
@@ -155,7 +156,9 @@ def test_golden(name, mode_name, golden_dir, cfg):
                     # the TF32-tier gradient bar proper is test_oracle_fixed_upstream (cosine >= 0.99)
                     assert nerr < (0.3 if gr.dim() == 1 else 0.15), (n, nerr)   # a bias gradient is ONE sum over positions
                     cos = float(np.dot(got, ref) / (np.linalg.norm(got) * np.linalg.norm(ref) + 1e-30))
-                    assert cos > 0.8, (n, cos)
+                    if os.environ.get("NEF_TEST_VERBOSE"):
+                        print("golden-cos", name, n, "%.4f" % cos)
+                    assert cos > GOLDEN_TF32_COS, (n, cos)
 
 
 @pytest.mark.parametrize("mode_name", list(MODES))
