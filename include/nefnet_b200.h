@@ -210,6 +210,24 @@ int nef_pair_loss(const float* a, const float* b, int64_t n, int use_mse, double
 int nef_sgd_step(float* p, const float* g, float* m, int64_t n, float lr, float momentum, float gscale,
                  nef_stream_t s);
 
+/* ---- callers either side of the path ---------------------------------- */
+/* utils/mertic.py:7-21 PSNR(pred, gt, rois): per (segment, view) row 20 log10(1 / rmse) over [0, rois[b, 6, 0]) (whole
+ * row when rois is NULL), 100 when rmse == 0.  rows: scratch double[B * V] (the per-row values, kept for inspection);
+ * acc: double[2] = {sum of row values, rows seen}, accumulated across calls (zero it at the start of an epoch);
+ * result (optional, device float): running mean acc[0] / acc[1].  No host synchronisation.                     */
+int nef_psnr(const float* pred, const float* gt, const int64_t* rois, int B, int V, int L, double* rows, double* acc,
+             float* result, nef_stream_t s);
+/* dataset/tianchi.py:84-111, 212-225 for a batch of whole records already in device memory.
+ * raw: packed records, record b = 8 leads x rec_len[b] doubles (row-major) starting at element rec_off[b];
+ * marks (B, 7) int64 = p_on, p_off, r_on, r_off, t_on, t_off, end_point of the chosen heartbeat (:96-102);
+ * derives III, aVR, aVL, aVF (:88-93), crops [p_on, end_point) (:107), min-max normalises over the 12 x crop block
+ * (:110-111), zero-pads / truncates to L (:212-219).  Outputs (each optional): ori (B, 12, L) = 'ori_data';
+ * data (B, G, L) = leads select[b, :] ('data'); target (B, L) = lead target_index[b] ('target_view');
+ * rois (B, 7, 2) int64 (:103-106, the literal 512 is L).                                                         */
+int nef_prepare_segments(const double* raw, const int64_t* rec_off, const int32_t* rec_len, const int64_t* marks,
+                         int B, int L, const int32_t* select, int G, const int32_t* target_index, float* ori,
+                         float* data, float* target, int64_t* rois, nef_stream_t s);
+
 /* ---- single ops, exported for unit tests ---------------------------------------------------- */
 /* encoder stem, resnet_1d.py:102-105 + encoder.py:35-38: x (B,G,L) -> CBL4 (128G, L/4) */
 /* argmax: one byte per output element (a uint32 per float4 row of y, same indexing): which pooled conv position won

@@ -23,7 +23,7 @@ from oracle.make_golden import sample_idx
 
 pytestmark = pytest.mark.gpu
 
-GOLDEN = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+GOLDEN = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "t*_b*.npz")))  # the hot-path vectors (data_*.npz: test_data_oracle.py)
 OUT_RTOL = 1e-3          # north star
 EXACT_OUT_RTOL = 2e-5
 EXACT_GRAD_REL_L2 = 5e-3  # a single ReLU-mask flip at a pre-activation within 1 ulp of 0 costs ~2e-3 (see make_golden.py)

@@ -10,7 +10,7 @@ import torch
 from oracle import nefnet_oracle as O
 from oracle.make_golden import sample_idx
 
-CASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+CASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "t*_b*.npz")))  # the hot-path vectors (data_*.npz: test_data_oracle.py)
 
 
 def test_golden_present():
