@@ -38,6 +38,24 @@ extern "C" void nef_count_launch(void);  // every kernel launch of the library i
     }                                   \
   } while (0)
 
+// One launch packs up to NEF_PACK_MAX weight tensors (nef_pack_weights semantics per job); the table is a kernel parameter.
+#define NEF_PACK_MAX 40
+#define NEF_PACK_CHUNK 4096   // elements of a job per block
+struct NefPackJob {
+  const float* src;
+  float* dst;
+  int groups, N, K, taps;
+  long sg, sn, sk, st;
+  int flags;        // bit 0: flip taps, bit 1: TF32 residual
+  int first_block;  // filled by nef_pack_weights_batch
+};
+struct NefPackTable {
+  NefPackJob job[NEF_PACK_MAX];
+  int n;
+};
+static_assert(sizeof(NefPackTable) <= 4000, "the packing table travels as a kernel parameter");
+int nef_pack_weights_batch(NefPackTable* tab, cudaStream_t s);  // launches the jobs queued in tab and empties it
+
 namespace nef {
 
 // Test hook (nef_set_exact_fp32): when set, nothing is rounded to TF32, so that the CUDA-core

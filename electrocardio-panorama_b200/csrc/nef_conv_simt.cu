@@ -209,6 +209,32 @@ __global__ void pack_weights_kernel(const float* __restrict__ src, float* __rest
   }
 }
 
+// Several packing jobs in one launch (the plan packs ~28 weight tensors per pass): the job table travels as a kernel
+// parameter, a block finds its job from the cumulative block counts and packs NEF_PACK_CHUNK elements of it.
+__global__ void __launch_bounds__(256) pack_weights_batch_kernel(const __grid_constant__ NefPackTable tab) {
+  int jb = 0;
+  while (jb + 1 < tab.n && (int)blockIdx.x >= tab.job[jb + 1].first_block) ++jb;
+  const NefPackJob& q = tab.job[jb];
+  const long total = (long)q.groups * q.taps * q.K * q.N;
+  const long beg = (long)((int)blockIdx.x - q.first_block) * NEF_PACK_CHUNK;
+  const long end = beg + NEF_PACK_CHUNK < total ? beg + NEF_PACK_CHUNK : total;
+  const int nkb = q.K >> 5;
+  for (long i = beg + threadIdx.x; i < end; i += 256) {
+    long r = i;
+    const int j = r & 3; r >>= 2;
+    const int n = r % q.N; r /= q.N;
+    const int c = r & 7; r >>= 3;
+    const int kb = r % nkb; r /= nkb;
+    const int t = r % q.taps; r /= q.taps;
+    const int g = (int)r;
+    const int k = kb * 32 + c * 4 + j;
+    const int ts = (q.flags & 1) ? q.taps - 1 - t : t;
+    const float wv = q.src[g * q.sg + n * q.sn + k * q.sk + ts * q.st];
+    const float hi = tf32_rn(wv);
+    q.dst[i] = (q.flags & 2) ? tf32_rn(wv - hi) : hi;
+  }
+}
+
 __global__ void ncl_to_cbl4_kernel(const float* __restrict__ src, float4* __restrict__ dst, int B, int C, int L,
                                    int round_tf32) {
   const int Lp = L + 2 * NEF_HALO;
@@ -284,6 +310,22 @@ extern "C" int nef_pack_weights(const float* src, float* dst, int groups, int N,
   if (blocks > 148 * 16) blocks = 148 * 16;
   pack_weights_kernel<<<blocks, 256, 0, (cudaStream_t)s>>>(src, dst, groups, N, K, taps, sg, sn, sk, st, flags);
   NEF_CHECK_LAUNCH("pack_weights_kernel");
+  return 0;
+}
+
+int nef_pack_weights_batch(NefPackTable* tab, cudaStream_t s) {
+  if (tab->n == 0) return 0;
+  int blocks = 0;
+  for (int i = 0; i < tab->n; ++i) {
+    NefPackJob& q = tab->job[i];
+    NEF_REQUIRE(q.K % 32 == 0 && q.N % 4 == 0, "nef_pack_weights_batch: K %% 32 and N %% 4 required (K=%d N=%d)", q.K, q.N);
+    q.first_block = blocks;
+    const long total = (long)q.groups * q.taps * q.K * q.N;
+    blocks += (int)((total + NEF_PACK_CHUNK - 1) / NEF_PACK_CHUNK);
+  }
+  pack_weights_batch_kernel<<<blocks, 256, 0, s>>>(*tab);
+  NEF_CHECK_LAUNCH("pack_weights_batch_kernel");
+  tab->n = 0;
   return 0;
 }
 

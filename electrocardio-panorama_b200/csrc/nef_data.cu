@@ -76,37 +76,36 @@ __device__ __forceinline__ double lead_value(const double* rec, long T, int k, l
   }
 }
 
-// one block per segment
-__global__ void __launch_bounds__(256) prepare_segments_kernel(const double* __restrict__ raw, const int64_t* __restrict__ rec_off,
-                                                               const int32_t* __restrict__ rec_len,
-                                                               const int64_t* __restrict__ marks, int L,
-                                                               const int32_t* __restrict__ select, int G,
-                                                               const int32_t* __restrict__ target_index,
-                                                               float* __restrict__ ori, float* __restrict__ data,
-                                                               float* __restrict__ target, int64_t* __restrict__ rois) {
-  __shared__ double smin[8], smax[8];
-  __shared__ double s_lo, s_hi;
-  const int b = blockIdx.x, tid = threadIdx.x;
-  const int64_t* mk = marks + (long)b * 7;
-  const long T = rec_len[b];
-  const double* rec = raw + rec_off[b];
-  long p_on = mk[0], end = mk[6];
-  // numpy slice [p_on:end_point] on an axis of length T
-  long lo = p_on < 0 ? p_on + T : p_on, hi = end < 0 ? end + T : end;
+// numpy slice [p_on:end_point] on an axis of length T -> [lo, lo + n)
+__device__ __forceinline__ void crop_range(const int64_t* mk, long T, long& lo, long& n) {
+  const long p_on = mk[0], end = mk[6];
+  lo = p_on < 0 ? p_on + T : p_on;
+  long hi = end < 0 ? end + T : end;
   lo = lo < 0 ? 0 : (lo > T ? T : lo);
   hi = hi < 0 ? 0 : (hi > T ? T : hi);
-  const long n = hi > lo ? hi - lo : 0;
-  if (rois && tid < 7) {  // tianchi.py:103-106
-    const int64_t e = tid < 6 ? mk[tid + 1] : (int64_t)L + mk[0];
-    rois[((long)b * 7 + tid) * 2 + 0] = mk[tid] - mk[0];
-    rois[((long)b * 7 + tid) * 2 + 1] = e - mk[0];
-  }
+  n = hi > lo ? hi - lo : 0;
+}
+
+constexpr int PREP_SPLITS = 16;  // blocks per segment (both passes)
+
+// pass 1: partial min / max of the 12 x crop block (tianchi.py:110), one (segment, split) per block
+__global__ void __launch_bounds__(256) prepare_minmax_kernel(const double* __restrict__ raw, const int64_t* __restrict__ rec_off,
+                                                             const int32_t* __restrict__ rec_len,
+                                                             const int64_t* __restrict__ marks, double* __restrict__ part) {
+  __shared__ double smin[8], smax[8];
+  const int b = blockIdx.y, sp = blockIdx.x, tid = threadIdx.x;
+  const long T = rec_len[b];
+  const double* rec = raw + rec_off[b];
+  long lo, n;
+  crop_range(marks + (long)b * 7, T, lo, n);
   double mn = INFINITY, mx = -INFINITY;
-  for (long i = tid; i < 12 * n; i += 256) {
-    const int k = (int)(i / n);
-    const double v = lead_value(rec, T, k, lo + (i - (long)k * n));
-    mn = fmin(mn, v);
-    mx = fmax(mx, v);
+  for (long l = (long)sp * 256 + tid; l < n; l += (long)PREP_SPLITS * 256) {
+#pragma unroll
+    for (int k = 0; k < 12; ++k) {
+      const double v = lead_value(rec, T, k, lo + l);
+      mn = fmin(mn, v);
+      mx = fmax(mx, v);
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -117,25 +116,57 @@ __global__ void __launch_bounds__(256) prepare_segments_kernel(const double* __r
   __syncthreads();
   if (tid == 0) {
     for (int i = 1; i < 8; ++i) { mn = fmin(mn, smin[i]); mx = fmax(mx, smax[i]); }
-    s_lo = mn;
-    s_hi = mx;
+    part[((long)b * PREP_SPLITS + sp) * 2 + 0] = mn;
+    part[((long)b * PREP_SPLITS + sp) * 2 + 1] = mx;
   }
-  __syncthreads();
-  const double vmin = s_lo, range = s_hi - s_lo;  // (x - min) / (max - min)  (:110-111)
+}
+
+// pass 2: normalise, pad / truncate, select; one (segment, split) per block
+__global__ void __launch_bounds__(256) prepare_segments_kernel(const double* __restrict__ raw, const int64_t* __restrict__ rec_off,
+                                                               const int32_t* __restrict__ rec_len,
+                                                               const int64_t* __restrict__ marks, int L,
+                                                               const int32_t* __restrict__ select, int G,
+                                                               const int32_t* __restrict__ target_index,
+                                                               const double* __restrict__ part,
+                                                               float* __restrict__ ori, float* __restrict__ data,
+                                                               float* __restrict__ target, int64_t* __restrict__ rois) {
+  const int b = blockIdx.y, sp = blockIdx.x, tid = threadIdx.x;
+  const int64_t* mk = marks + (long)b * 7;
+  const long T = rec_len[b];
+  const double* rec = raw + rec_off[b];
+  long lo, n;
+  crop_range(mk, T, lo, n);
+  if (rois && sp == 0 && tid < 7) {  // tianchi.py:103-106
+    const int64_t e = tid < 6 ? mk[tid + 1] : (int64_t)L + mk[0];
+    rois[((long)b * 7 + tid) * 2 + 0] = mk[tid] - mk[0];
+    rois[((long)b * 7 + tid) * 2 + 1] = e - mk[0];
+  }
+  double mn = INFINITY, mx = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < PREP_SPLITS; ++i) {
+    mn = fmin(mn, part[((long)b * PREP_SPLITS + i) * 2 + 0]);
+    mx = fmax(mx, part[((long)b * PREP_SPLITS + i) * 2 + 1]);
+  }
+  const double vmin = mn, range = mx - mn;  // (x - min) / (max - min)  (:110-111)
   const int tgt = target_index ? target_index[b] : -1;
-  for (long i = tid; i < 12L * L; i += 256) {
-    const int k = (int)(i / L);
-    const long l = i - (long)k * L;
-    const float v = l < n ? (float)((lead_value(rec, T, k, lo + l) - vmin) / range) : 0.f;  // pad / truncate (:212-219)
-    if (ori) ori[((long)b * 12 + k) * L + l] = v;
-    if (k == tgt) target[(long)b * L + l] = v;
-  }
-  if (data) {
-    for (long i = tid; i < (long)G * L; i += 256) {
-      const int gi = (int)(i / L);
-      const long l = i - (long)gi * L;
-      const int k = select[(long)b * G + gi];
-      data[((long)b * G + gi) * L + l] = l < n ? (float)((lead_value(rec, T, k, lo + l) - vmin) / range) : 0.f;
+  for (long l = (long)sp * 256 + tid; l < L; l += (long)PREP_SPLITS * 256) {
+    float v[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k)
+      v[k] = l < n ? (float)((lead_value(rec, T, k, lo + l) - vmin) / range) : 0.f;  // pad / truncate (:212-219)
+#pragma unroll
+    for (int k = 0; k < 12; ++k) {
+      if (ori) ori[((long)b * 12 + k) * L + l] = v[k];
+      if (k == tgt) target[(long)b * L + l] = v[k];
+    }
+    if (data) {
+      for (int gi = 0; gi < G; ++gi) {
+        const int k = select[(long)b * G + gi];
+        float sel = 0.f;
+#pragma unroll
+        for (int kk = 0; kk < 12; ++kk) sel = kk == k ? v[kk] : sel;
+        data[((long)b * G + gi) * L + l] = sel;
+      }
     }
   }
 }
@@ -154,14 +185,20 @@ extern "C" int nef_psnr(const float* pred, const float* gt, const int64_t* rois,
   return 0;
 }
 
+extern "C" size_t nef_prepare_scratch_bytes(int B) { return (size_t)B * nef::PREP_SPLITS * 2 * sizeof(double); }
+
 extern "C" int nef_prepare_segments(const double* raw, const int64_t* rec_off, const int32_t* rec_len, const int64_t* marks,
-                                    int B, int L, const int32_t* select, int G, const int32_t* target_index, float* ori,
-                                    float* data, float* target, int64_t* rois, nef_stream_t s) {
-  NEF_REQUIRE(raw && rec_off && rec_len && marks && B >= 1 && L >= 1, "nef_prepare_segments: bad arguments");
+                                    int B, int L, const int32_t* select, int G, const int32_t* target_index, double* scratch,
+                                    float* ori, float* data, float* target, int64_t* rois, nef_stream_t s) {
+  NEF_REQUIRE(raw && rec_off && rec_len && marks && scratch && B >= 1 && L >= 1, "nef_prepare_segments: bad arguments");
   NEF_REQUIRE(!data || (select && G >= 1), "nef_prepare_segments: data needs select (B, G)");
   NEF_REQUIRE(!target_index || target, "nef_prepare_segments: target_index needs target (B, L)");
-  prepare_segments_kernel<<<(unsigned)B, 256, 0, (cudaStream_t)s>>>(raw, rec_off, rec_len, marks, L, select, G, target_index,
-                                                                    ori, data, target, rois);
+  NEF_REQUIRE(B <= 65535, "nef_prepare_segments: at most 65535 segments per call");
+  dim3 grid(PREP_SPLITS, (unsigned)B);
+  prepare_minmax_kernel<<<grid, 256, 0, (cudaStream_t)s>>>(raw, rec_off, rec_len, marks, scratch);
+  NEF_CHECK_LAUNCH("prepare_minmax_kernel");
+  prepare_segments_kernel<<<grid, 256, 0, (cudaStream_t)s>>>(raw, rec_off, rec_len, marks, L, select, G, target_index, scratch,
+                                                            ori, data, target, rois);
   NEF_CHECK_LAUNCH("prepare_segments_kernel");
   return 0;
 }

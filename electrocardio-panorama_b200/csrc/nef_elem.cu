@@ -490,7 +490,7 @@ constexpr int LAT_GB = 12;   // leads whose loads are batched in the backward ke
 __global__ void __launch_bounds__(256) latent_fwd_kernel(const LatentArgs a) {
   extern __shared__ float4 sm[];
   const int L4 = a.z1.L;
-  const int b = blockIdx.x, cc = blockIdx.y, half = blockIdx.z;
+  const int half = blockIdx.x, cc = blockIdx.y, b = blockIdx.z;  // the two halves interleave in launch order
   const int tid = threadIdx.x;
   float4* z2s = sm;                                   // [G][7 chunks][32]   (z2 half only)
   float4* mt = sm + (half ? a.G * 7 * 32 : 0);        // [LAT_TL + 2] mean
@@ -593,7 +593,7 @@ int latent_fwd(const LatentArgs& a, cudaStream_t s) {
     cudaFuncSetAttribute(latent_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     configured = smem;
   }
-  dim3 grid(a.z1.B, 32, 2);
+  dim3 grid(2, 32, a.z1.B);
   latent_fwd_kernel<<<grid, 256, smem, s>>>(a);
   NEF_CHECK_LAUNCH("latent_fwd_kernel");
   return 0;
@@ -603,7 +603,7 @@ int latent_fwd(const LatentArgs& a, cudaStream_t s) {
 __global__ void __launch_bounds__(256, 3) latent_bwd_kernel(const LatentBwdArgs a) {
   extern __shared__ float4 sm[];
   const int L4 = a.z1.L;
-  const int b = blockIdx.x, cc = blockIdx.y, half = blockIdx.z;
+  const int half = blockIdx.x, cc = blockIdx.y, b = blockIdx.z;  // memory-bound z1 blocks next to atomics-bound z2 blocks
   const int tid = threadIdx.x, lane = tid & 31;
   float* Tm = reinterpret_cast<float*>(sm);  // [4][7][32] adjoint-resampled d(mean) / d(pick)   (z2 half)
   float* Tp = Tm + 4 * 7 * 32;
@@ -704,7 +704,7 @@ __global__ void __launch_bounds__(256, 3) latent_bwd_kernel(const LatentBwdArgs 
 
 int latent_bwd(const LatentBwdArgs& a, cudaStream_t s) {
   const size_t smem = (size_t)2 * 4 * 7 * 32 * sizeof(float);
-  dim3 grid(a.z1.B, 32, 2);
+  dim3 grid(2, 32, a.z1.B);
   latent_bwd_kernel<<<grid, 256, smem, s>>>(a);
   NEF_CHECK_LAUNCH("latent_bwd_kernel");
   return 0;
@@ -981,6 +981,7 @@ int dec_out_fwd(T4 c4, const float* scale, const float* shift, const float* w, c
 //   g4[l][ci] = (sum_t dy[l-t+1] w[ci][t]) * (a4 > 0) ; s1 += g4 ; s2 += g4 * xhat
 // grid: x = position blocks (grid-stride), y = the 16 channel chunks.  Every thread keeps its 5 float4 partial sums in
 // registers over all its positions; one block reduction at the end.
+constexpr int DOB_SPAN = 1024;
 __global__ void __launch_bounds__(256) dec_out_bwd_kernel(T4 c4t, BnLayer bn, const float* __restrict__ w,
                                                           const float* __restrict__ out, const float* __restrict__ dout,
                                                           T4 g4, float* __restrict__ dw, float* __restrict__ db) {
@@ -993,12 +994,15 @@ __global__ void __launch_bounds__(256) dec_out_bwd_kernel(T4 c4t, BnLayer bn, co
   const float4 sc = reinterpret_cast<const float4*>(bn.scale)[c], sh = reinterpret_cast<const float4*>(bn.shift)[c];
   const float4 mu = reinterpret_cast<const float4*>(bn.mean)[c], is = reinterpret_cast<const float4*>(bn.invstd)[c];
   const int L = c4t.L;
-  const long total = (long)c4t.B * L;
   float4 s1 = f4zero(), s2 = f4zero(), a_m = f4zero(), a_0 = f4zero(), a_p = f4zero();
   float dbl = 0.f;
-  for (long i = blockIdx.x * (long)blockDim.x + tid; i < total; i += (long)gridDim.x * blockDim.x) {
-    const int b = (int)(i / L);
-    const int l = (int)(i - (long)b * L);
+  // blockIdx.x walks (segment, DOB_SPAN-sample span) pairs: no per-element division
+  const int spans = (L + DOB_SPAN - 1) / DOB_SPAN;
+  for (long u = blockIdx.x; u < (long)c4t.B * spans; u += gridDim.x) {
+    const int b = (int)(u / spans);
+    const int l0 = (int)(u - (long)b * spans) * DOB_SPAN;
+    const int l1 = min(L, l0 + DOB_SPAN);
+   for (int l = l0 + tid; l < l1; l += 256) {
     const float* op = out + (long)b * L + l;
     const float* dp = dout + (long)b * L + l;
     const float dy0 = dp[0] * op[0] * (1.0f - op[0]) * (1.0f / 3.0f);
@@ -1020,6 +1024,7 @@ __global__ void __launch_bounds__(256) dec_out_bwd_kernel(T4 c4t, BnLayer bn, co
     a_0 = a_0 + a0 * dy0;
     a_p = a_p + ap * dy0;
     dbl += dy0;
+   }
   }
   float v[21] = {s1.x, s1.y, s1.z, s1.w, s2.x, s2.y, s2.z, s2.w, a_m.x, a_m.y, a_m.z, a_m.w,
                  a_0.x, a_0.y, a_0.z, a_0.w, a_p.x, a_p.y, a_p.z, a_p.w, dbl};
@@ -1042,10 +1047,9 @@ __global__ void __launch_bounds__(256) dec_out_bwd_kernel(T4 c4t, BnLayer bn, co
 }
 int dec_out_bwd(T4 c4, const BnLayer& bn, const float* w, const float* out, const float* dout, T4 g4, float* dw,
                 float* db, cudaStream_t s) {
-  const long total = (long)c4.B * c4.L;
-  int gx = (int)((total + 256 * 8 - 1) / (256 * 8));
+  const long units = (long)c4.B * ((c4.L + DOB_SPAN - 1) / DOB_SPAN);
+  int gx = (int)(units < 148 * 4 ? units : 148 * 4);
   if (gx < 1) gx = 1;
-  if (gx > 148 * 4) gx = 148 * 4;
   dim3 grid(gx, 16);
   dec_out_bwd_kernel<<<grid, 256, 0, s>>>(c4, bn, w, out, dout, g4, dw, db);
   NEF_CHECK_LAUNCH("dec_out_bwd_kernel");

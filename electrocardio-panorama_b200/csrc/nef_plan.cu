@@ -412,24 +412,33 @@ static int wgrad_std(const T4& dy, int dy_off, int dy_gs, const T4& x, int x_off
     if (rc__) return rc__; \
   } while (0)
 
-static int pack_fwd(const ConvW& w, const float* const* P, cudaStream_t s) {
-  return nef_pack_weights(P[w.pidx], w.pk_f, w.groups, w.cout_g, w.cin_g, w.taps, (int64_t)w.cout_g * w.cin_g * w.taps,
-                          (int64_t)w.cin_g * w.taps, w.taps, 1, 0, (nef_stream_t)s);
+// packing jobs are queued in a table and launched together (nef_pack_weights_batch)
+static int queue_pack(NefPackTable& t, const float* src, float* dst, int groups, int N, int K, int taps, int64_t sg, int64_t sn,
+                      int64_t sk, int64_t st, int flags, cudaStream_t s) {
+  if (t.n == NEF_PACK_MAX) RUN(nef_pack_weights_batch(&t, s));
+  NefPackJob& q = t.job[t.n++];
+  q.src = src; q.dst = dst; q.groups = groups; q.N = N; q.K = K; q.taps = taps;
+  q.sg = sg; q.sn = sn; q.sk = sk; q.st = st; q.flags = flags; q.first_block = 0;
+  return 0;
+}
+static int pack_fwd(NefPackTable& t, const ConvW& w, const float* const* P, cudaStream_t s) {
+  return queue_pack(t, P[w.pidx], w.pk_f, w.groups, w.cout_g, w.cin_g, w.taps, (int64_t)w.cout_g * w.cin_g * w.taps,
+                    (int64_t)w.cin_g * w.taps, w.taps, 1, 0, s);
 }
 // dgrad: N' = cin_g (split into sub-groups of 128 when larger; only for groups == 1), K' = cout_g, flipped taps
-static int pack_dgrad(const ConvW& w, const float* const* P, cudaStream_t s) {
+static int pack_dgrad(NefPackTable& t, const ConvW& w, const float* const* P, cudaStream_t s) {
   if (w.cin_g > 128) {
     const int sub = w.cin_g / 128;
-    return nef_pack_weights(P[w.pidx], w.pk_d, sub, 128, w.cout_g, w.taps, (int64_t)128 * w.taps, w.taps,
-                            (int64_t)w.cin_g * w.taps, 1, 1, (nef_stream_t)s);
+    return queue_pack(t, P[w.pidx], w.pk_d, sub, 128, w.cout_g, w.taps, (int64_t)128 * w.taps, w.taps,
+                      (int64_t)w.cin_g * w.taps, 1, 1, s);
   }
-  return nef_pack_weights(P[w.pidx], w.pk_d, w.groups, w.cin_g, w.cout_g, w.taps, (int64_t)w.cout_g * w.cin_g * w.taps,
-                          w.taps, (int64_t)w.cin_g * w.taps, 1, 1, (nef_stream_t)s);
+  return queue_pack(t, P[w.pidx], w.pk_d, w.groups, w.cin_g, w.cout_g, w.taps, (int64_t)w.cout_g * w.cin_g * w.taps,
+                    w.taps, (int64_t)w.cin_g * w.taps, 1, 1, s);
 }
 
-static int pack_dec1_lo(NefPlan* p, const float* const* P, cudaStream_t s) {
+static int pack_dec1_lo(NefPackTable& t, NefPlan* p, const float* const* P, cudaStream_t s) {
   const ConvW& w = p->decw[0];
-  return nef_pack_weights(P[w.pidx], p->dec1_lo, 1, 128, 256, 3, 0, 256 * 3, 3, 1, 2, (nef_stream_t)s);
+  return queue_pack(t, P[w.pidx], p->dec1_lo, 1, 128, 256, 3, 0, 256 * 3, 3, 1, 2, s);
 }
 
 template <class F>
@@ -546,10 +555,13 @@ extern "C" int nef_forward(NefPlan* p, const NefForwardArgs* a, nef_stream_t sv)
   p->c1 = a->lead_choice_z1; p->c2 = a->lead_choice_z2; p->drop_p = a->drop_p; p->bn_training = a->bn_training;
   p->x_in = a->x; p->thetas_in = a->input_thetas; p->query_in = a->query_theta; p->rois_in = a->rois;
 
-  RUN(for_all_convw(p, [&](const ConvW& w) { return pack_fwd(w, P, s); }));
-  RUN(pack_dec1_lo(p, P, s));
+  NefPackTable packs;
+  packs.n = 0;
+  RUN(for_all_convw(p, [&](const ConvW& w) { return pack_fwd(packs, w, P, s); }));
+  RUN(pack_dec1_lo(packs, p, P, s));
   for (int t = 0; t < 2; ++t)  // ConvTranspose1d weight (Cin_total, Cout/groups, 2): one 1x1 conv per tap
-    RUN(nef_pack_weights(P[P_CT_W] + t, p->ct_f[t], 7 * G, 64, 128, 1, 128LL * 64 * 2, 2, 64 * 2, 0, 0, sv));
+    RUN(queue_pack(packs, P[P_CT_W] + t, p->ct_f[t], 7 * G, 64, 128, 1, 128LL * 64 * 2, 2, 64 * 2, 0, 0, s));
+  RUN(nef_pack_weights_batch(&packs, s));
 
   RUN(stem_fwd(a->x, P[P_STEM], p->s0, a->save_for_backward ? p->s0_amax : nullptr, G, s));
   RUN(angular_fwd(a->input_thetas, P[P_MLP1_W], P[P_MLP1_B], p->s_in, B * G, 128, s));
@@ -606,8 +618,11 @@ extern "C" int nef_gen_ecg(NefPlan* p, const float* const* P, const float* z1, c
   NEF_REQUIRE(V >= 1 && V <= p->V, "nef_gen_ecg: V=%d not in [1, plan V=%d]", V, p->V);
   p->have_fwd = false;
   p->c1 = 0; p->c2 = 0;
-  for (int i = 0; i < 4; ++i) RUN(pack_fwd(p->decw[i], P, s));
-  RUN(pack_dec1_lo(p, P, s));
+  NefPackTable packs;
+  packs.n = 0;
+  for (int i = 0; i < 4; ++i) RUN(pack_fwd(packs, p->decw[i], P, s));
+  RUN(pack_dec1_lo(packs, p, P, s));
+  RUN(nef_pack_weights_batch(&packs, s));
   RUN(nef_ncl_to_cbl4(z1, reinterpret_cast<float*>(p->z1.p), p->B, p->C1, p->L4, 0, sv));
   RUN(nef_ncl_to_cbl4(z2, reinterpret_cast<float*>(p->z2o.p), p->B, 896 * p->G, 32, 0, sv));
   return latents_to_decoders(p, P, nullptr, query_theta, rois, NEF_PHASE_TEST, 0, V, nullptr, nullptr, nullptr, out,
@@ -700,9 +715,12 @@ extern "C" int nef_backward(NefPlan* p, const NefBackwardArgs* a, nef_stream_t s
   const float dp = p->drop_p;
   p->have_fwd = false;
 
-  RUN(for_all_convw(p, [&](const ConvW& w) { return pack_dgrad(w, P, s); }));
+  NefPackTable packs;
+  packs.n = 0;
+  RUN(for_all_convw(p, [&](const ConvW& w) { return pack_dgrad(packs, w, P, s); }));
   for (int t = 0; t < 2; ++t)  // ConvTranspose dgrad: dx[l] = sum_t W_t^T dy[2l + t] ; N' = ci (128), K' = co (64)
-    RUN(nef_pack_weights(P[P_CT_W] + t, p->ct_d[t], 7 * G, 128, 64, 1, 128LL * 64 * 2, 64 * 2, 2, 0, 0, sv));
+    RUN(queue_pack(packs, P[P_CT_W] + t, p->ct_d[t], 7 * G, 128, 64, 1, 128LL * 64 * 2, 64 * 2, 2, 0, 0, s));
+  RUN(nef_pack_weights_batch(&packs, s));
   // zero the BatchNorm backward accumulators (s1, s2 of every layer)
   for (int k = 0; k < 3; ++k)
     for (int i = 0; i < 4; ++i) cudaMemsetAsync(p->dec[k].bn[i].s1, 0, 2 * 128 * sizeof(double), s);

@@ -50,8 +50,10 @@ def prepare_segments(raw, rec_off, rec_len, marks, L=512, select_index=None, tar
         tidx = torch.as_tensor(target_index).to(device=dev, dtype=torch.int32).contiguous()
         tgt = torch.empty((B, 1, L), dtype=torch.float32, device=dev)
     rois = torch.empty((B, 7, 2), dtype=torch.int64, device=dev)
+    scratch = torch.empty(lib.nef_prepare_scratch_bytes(B) // 8, dtype=torch.float64, device=dev)
     N.check(lib.nef_prepare_segments(N.ptr(raw), N.ptr(rec_off), N.ptr(rec_len), N.ptr(marks), B, L, N.ptr(sel), G,
-                                     N.ptr(tidx), N.ptr(ori), N.ptr(data), N.ptr(tgt), N.ptr(rois), N.stream_ptr()),
+                                     N.ptr(tidx), N.ptr(scratch), N.ptr(ori), N.ptr(data), N.ptr(tgt), N.ptr(rois),
+                                     N.stream_ptr()),
             "nef_prepare_segments")
     return {"data": data, "target_view": tgt, "ori_data": ori, "rois": rois}
 

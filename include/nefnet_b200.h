@@ -223,10 +223,12 @@ int nef_psnr(const float* pred, const float* gt, const int64_t* rois, int B, int
  * derives III, aVR, aVL, aVF (:88-93), crops [p_on, end_point) (:107), min-max normalises over the 12 x crop block
  * (:110-111), zero-pads / truncates to L (:212-219).  Outputs (each optional): ori (B, 12, L) = 'ori_data';
  * data (B, G, L) = leads select[b, :] ('data'); target (B, L) = lead target_index[b] ('target_view');
- * rois (B, 7, 2) int64 (:103-106, the literal 512 is L).                                                         */
+ * rois (B, 7, 2) int64 (:103-106, the literal 512 is L).  scratch: nef_prepare_scratch_bytes(B) bytes of device
+ * memory (partial minima / maxima).                                                                              */
+size_t nef_prepare_scratch_bytes(int B);
 int nef_prepare_segments(const double* raw, const int64_t* rec_off, const int32_t* rec_len, const int64_t* marks,
-                         int B, int L, const int32_t* select, int G, const int32_t* target_index, float* ori,
-                         float* data, float* target, int64_t* rois, nef_stream_t s);
+                         int B, int L, const int32_t* select, int G, const int32_t* target_index, double* scratch,
+                         float* ori, float* data, float* target, int64_t* rois, nef_stream_t s);
 
 /* ---- single ops, exported for unit tests ---------------------------------------------------- */
 /* encoder stem, resnet_1d.py:102-105 + encoder.py:35-38: x (B,G,L) -> CBL4 (128G, L/4) */
