@@ -107,63 +107,70 @@ __global__ void __launch_bounds__(256, 2) stem_bwd_kernel(const float* __restric
   __shared__ __align__(16) float xs[4 * STEMB_TJ + 24];
   __shared__ float sdw[15][128];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int g = blockIdx.y, b = blockIdx.z;
-  const int j0 = blockIdx.x * STEMB_TJ;
+  const int g = blockIdx.y;
   const int L4 = L / 4;
-  const float* xb = x + ((long)b * G + g) * L;
-  for (int i = tid; i < 4 * STEMB_TJ + 24; i += 256) {
-    int p = 4 * j0 - 9 + i;
-    xs[i] = (p >= 0 && p < L) ? xb[p] : 0.f;
-  }
+  const int ntile = (L4 + STEMB_TJ - 1) / STEMB_TJ;
   for (int i = tid; i < 15 * 128; i += 256) (&sdw[0][0])[i] = 0.f;
   float4 acc[15];
 #pragma unroll
   for (int t = 0; t < 15; ++t) acc[t] = f4zero();
-  __syncthreads();
-  const long base = (long)(g * 32 + lane) * dy.cs + dy.row(b, 0);
-  const float4* gp = dy.p + base;
-  const uint32_t* ap = amax + base;
-  const int jw = j0 + warp * 32;
-  float4 carry = f4zero();   // gradient of j-1 that belongs to conv position 2j-1 (its code 2)
-  if (jw > 0 && jw < L4) {
-    const float4 gq = gp[jw - 1];
-    const uint32_t cq = ap[jw - 1];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) f4at(carry, k) = ((cq >> (8 * k)) & 0xffu) == 2u ? f4get(gq, k) : 0.f;
-  }
-  constexpr int CH = 4;      // j per batch of loads
-  for (int jj = 0; jj < 32; jj += CH) {
-    if (jw + jj >= L4) break;
-    float4 gv[CH];
-    uint32_t cv[CH];
-#pragma unroll
-    for (int u = 0; u < CH; ++u) {
-      const bool ok = jw + jj + u < L4;
-      gv[u] = ok ? gp[jw + jj + u] : f4zero();
-      cv[u] = ok ? ap[jw + jj + u] : 0x03030303u;
+  // a block walks (segment, 256-window tile) units of one lead and keeps its partial gradient in registers, so the
+  // shared-memory and global atomics at the end are paid once per block, not once per tile
+  for (int u0 = blockIdx.x; u0 < dy.B * ntile; u0 += gridDim.x) {
+    const int b = u0 / ntile;
+    const int j0 = (u0 - b * ntile) * STEMB_TJ;
+    const float* xb = x + ((long)b * G + g) * L;
+    __syncthreads();
+    for (int i = tid; i < 4 * STEMB_TJ + 24; i += 256) {
+      int p = 4 * j0 - 9 + i;
+      xs[i] = (p >= 0 && p < L) ? xb[p] : 0.f;
     }
+    __syncthreads();
+    const long base = (long)(g * 32 + lane) * dy.cs + dy.row(b, 0);
+    const float4* gp = dy.p + base;
+    const uint32_t* ap = amax + base;
+    const int jw = j0 + warp * 32;
+    float4 carry = f4zero();   // gradient of j-1 that belongs to conv position 2j-1 (its code 2)
+    if (jw > 0 && jw < L4) {
+      const float4 gq = gp[jw - 1];
+      const uint32_t cq = ap[jw - 1];
 #pragma unroll
-    for (int u = 0; u < CH; ++u) {
-      const int jl = warp * 32 + jj + u;
-      float xr[20];
+      for (int k = 0; k < 4; ++k) f4at(carry, k) = ((cq >> (8 * k)) & 0xffu) == 2u ? f4get(gq, k) : 0.f;
+    }
+    constexpr int CH = 4;      // j per batch of loads
+    for (int jj = 0; jj < 32; jj += CH) {
+      if (jw + jj >= L4) break;
+      float4 gv[CH];
+      uint32_t cv[CH];
 #pragma unroll
-      for (int q = 0; q < 5; ++q) *reinterpret_cast<float4*>(&xr[4 * q]) = *reinterpret_cast<const float4*>(&xs[4 * jl + 4 * q]);
-      float4 gA, gB, nc;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const uint32_t c = (cv[u] >> (8 * k)) & 0xffu;
-        const float gk = f4get(gv[u], k);
-        f4at(gA, k) = f4get(carry, k) + (c == 0u ? gk : 0.f);
-        f4at(gB, k) = c == 1u ? gk : 0.f;
-        f4at(nc, k) = c == 2u ? gk : 0.f;
+      for (int u = 0; u < CH; ++u) {
+        const bool ok = jw + jj + u < L4;
+        gv[u] = ok ? gp[jw + jj + u] : f4zero();
+        cv[u] = ok ? ap[jw + jj + u] : 0x03030303u;
       }
-      carry = nc;
 #pragma unroll
-      for (int t = 0; t < 15; ++t) acc[t] = acc[t] + gA * xr[t] + gB * xr[2 + t];
-      if (j0 + jl == L4 - 1) {  // last pooled window of the segment: its code 2 has no successor to carry into
+      for (int u = 0; u < CH; ++u) {
+        const int jl = warp * 32 + jj + u;
+        float xr[20];
 #pragma unroll
-        for (int t = 0; t < 15; ++t) acc[t] = acc[t] + carry * xr[4 + t];
-        carry = f4zero();
+        for (int q = 0; q < 5; ++q) *reinterpret_cast<float4*>(&xr[4 * q]) = *reinterpret_cast<const float4*>(&xs[4 * jl + 4 * q]);
+        float4 gA, gB, nc;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint32_t c = (cv[u] >> (8 * k)) & 0xffu;
+          const float gk = f4get(gv[u], k);
+          f4at(gA, k) = f4get(carry, k) + (c == 0u ? gk : 0.f);
+          f4at(gB, k) = c == 1u ? gk : 0.f;
+          f4at(nc, k) = c == 2u ? gk : 0.f;
+        }
+        carry = nc;
+#pragma unroll
+        for (int t = 0; t < 15; ++t) acc[t] = acc[t] + gA * xr[t] + gB * xr[2 + t];
+        if (j0 + jl == L4 - 1) {  // last pooled window of the segment: its code 2 has no successor to carry into
+#pragma unroll
+          for (int t = 0; t < 15; ++t) acc[t] = acc[t] + carry * xr[4 + t];
+          carry = f4zero();
+        }
       }
     }
   }
@@ -191,7 +198,11 @@ int stem_fwd(const float* x, const float* w, T4 y, uint32_t* amax, int G, cudaSt
 }
 int stem_bwd(const float* x, const uint32_t* amax, T4 dy, float* dw, int G, cudaStream_t s) {
   const int L = dy.L * 4;
-  dim3 grid((dy.L + STEMB_TJ - 1) / STEMB_TJ, G, dy.B);
+  const int units = dy.B * ((dy.L + STEMB_TJ - 1) / STEMB_TJ);
+  int gx = (2 * 148) / G;               // one wave of two resident blocks per SM over all leads
+  if (gx < 1) gx = 1;
+  if (gx > units) gx = units;
+  dim3 grid(gx, G);
   stem_bwd_kernel<<<grid, 256, 0, s>>>(x, amax, dy, dw, G, L);
   NEF_CHECK_LAUNCH("stem_bwd_kernel");
   return 0;
@@ -485,12 +496,13 @@ __device__ __forceinline__ void interp_src(int i, int n, int& i0, int& i1, float
 }
 
 constexpr int LAT_TL = 256;  // latent positions per inner tile
+constexpr int LB_TL = 1024;  // latent positions per tile of the backward kernel
 constexpr int LAT_GB = 12;   // leads whose loads are batched in the backward kernel
 
 __global__ void __launch_bounds__(256) latent_fwd_kernel(const LatentArgs a) {
   extern __shared__ float4 sm[];
   const int L4 = a.z1.L;
-  const int half = blockIdx.x, cc = blockIdx.y, b = blockIdx.z;  // the two halves interleave in launch order
+  const int b = blockIdx.x, cc = blockIdx.y, half = blockIdx.z;
   const int tid = threadIdx.x;
   float4* z2s = sm;                                   // [G][7 chunks][32]   (z2 half only)
   float4* mt = sm + (half ? a.G * 7 * 32 : 0);        // [LAT_TL + 2] mean
@@ -593,7 +605,7 @@ int latent_fwd(const LatentArgs& a, cudaStream_t s) {
     cudaFuncSetAttribute(latent_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     configured = smem;
   }
-  dim3 grid(2, 32, a.z1.B);
+  dim3 grid(a.z1.B, 32, 2);
   latent_fwd_kernel<<<grid, 256, smem, s>>>(a);
   NEF_CHECK_LAUNCH("latent_fwd_kernel");
   return 0;
@@ -607,20 +619,24 @@ __global__ void __launch_bounds__(256, 3) latent_bwd_kernel(const LatentBwdArgs 
   const int tid = threadIdx.x, lane = tid & 31;
   float* Tm = reinterpret_cast<float*>(sm);  // [4][7][32] adjoint-resampled d(mean) / d(pick)   (z2 half)
   float* Tp = Tm + 4 * 7 * 32;
+  float4* sdm = sm + 2 * 7 * 32;             // [LB_TL] d(mean latent), d(picked latent) of the current tile (z2 half)
+  float4* sdp = sdm + LB_TL;
   __shared__ RoiTab tab;
   __shared__ float dq_s[4];
   if (tid < 4) dq_s[tid] = 0.f;
-  if (half == 1) {
-    if (tid == 0) roi_table(a.rois, b, tab);
-    for (int i = tid; i < 2 * 4 * 7 * 32; i += 256) Tm[i] = 0.f;
-  }
+  if (half == 1 && tid == 0) roi_table(a.rois, b, tab);
   __syncthreads();
+  // z2 half: thread (roi j, source sample pos) gathers the adjoint of the linear resampling over the latent positions that
+  // read its sample -- no atomics, fixed summation order
+  float accM[4] = {0.f, 0.f, 0.f, 0.f}, accP[4] = {0.f, 0.f, 0.f, 0.f};
   const int latc = half * 32 + cc;
   const float4 qv = *reinterpret_cast<const float4*>(a.q + (long)b * a.q_stride + latc * 4);
   const float invG = 1.0f / (float)a.G;
   float4 dq = f4zero();
   const int L2 = 2 * L4;
-  for (int l = tid; l < L4; l += 256) {
+  for (int t0 = 0; t0 < L4; t0 += LB_TL) {
+   const int nl = min(LB_TL, L4 - t0);
+   for (int l = t0 + tid; l < t0 + nl; l += 256) {
     float4 dk[3];
 #pragma unroll
     for (int k3 = 0; k3 < 3; ++k3) {
@@ -656,24 +672,49 @@ __global__ void __launch_bounds__(256, 3) latent_bwd_kernel(const LatentBwdArgs 
       }
       dq = dq + (dk[0] + dk[2]) * (msum * invG) + dk[1] * pick;
     } else {
-      int j = 0;
-      while (j < NEF_NROI - 1 && l >= tab.start[j + 1]) ++j;
-      const int n = tab.start[j + 1] - tab.start[j];
-      int i0, i1;
-      float lam;
-      interp_src(l - tab.start[j], n > 0 ? n : 1, i0, i1, lam);
       // lat_0 = lat_1 = mean (this half), lat_2 = lead c2
       const float4 lm = *a.lat[0].at(latc, b, l), lp = *a.lat[2].at(latc, b, l);
       dq = dq + (dk[0] + dk[1]) * lm + dk[2] * lp;
-      const float4 dm = (dk[0] + dk[1]) * qv, dp = dk[2] * qv;
+      sdm[l - t0] = (dk[0] + dk[1]) * qv;
+      sdp[l - t0] = dk[2] * qv;
+    }
+   }
+   if (half == 1) {
+    __syncthreads();
+    if (tid < NEF_NROI * 32) {
+      const int j = tid >> 5, pos = tid & 31;
+      const int s0 = tab.start[j], n = tab.start[j + 1] - s0;
+      if (n > 0) {
+        // positions i of roi j whose interpolation reads sample pos: src(i) in [pos - 1, pos + 1) (clamps included), +- 2 margin
+        const float f = (float)n * (1.0f / 32.0f);
+        int ilo = (int)floorf(((float)pos - 0.5f) * f - 0.5f) - 2, ihi = (int)ceilf(((float)pos + 1.5f) * f - 0.5f) + 2;
+        ilo = max(max(ilo, 0), t0 - s0);
+        ihi = min(min(ihi, n - 1), t0 + nl - 1 - s0);
+        for (int i = ilo; i <= ihi; ++i) {
+          int i0, i1;
+          float lam;
+          interp_src(i, n, i0, i1, lam);
+          const float w = (i0 == pos ? 1.0f - lam : 0.f) + (i1 == pos ? lam : 0.f);
+          if (w != 0.f) {
+            const float4 dm = sdm[s0 + i - t0], dp = sdp[s0 + i - t0];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float vm = f4get(dm, k), vp = f4get(dp, k);
-        atomicAdd(&Tm[(k * 7 + j) * 32 + i0], (1.0f - lam) * vm);
-        atomicAdd(&Tm[(k * 7 + j) * 32 + i1], lam * vm);
-        atomicAdd(&Tp[(k * 7 + j) * 32 + i0], (1.0f - lam) * vp);
-        atomicAdd(&Tp[(k * 7 + j) * 32 + i1], lam * vp);
+            for (int k = 0; k < 4; ++k) {
+              accM[k] += w * f4get(dm, k);
+              accP[k] += w * f4get(dp, k);
+            }
+          }
+        }
       }
+    }
+    __syncthreads();
+   }
+  }
+  if (half == 1 && tid < NEF_NROI * 32) {
+    const int j = tid >> 5, pos = tid & 31;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      Tm[(k * 7 + j) * 32 + pos] = accM[k];
+      Tp[(k * 7 + j) * 32 + pos] = accP[k];
     }
   }
 #pragma unroll
@@ -703,7 +744,7 @@ __global__ void __launch_bounds__(256, 3) latent_bwd_kernel(const LatentBwdArgs 
 }
 
 int latent_bwd(const LatentBwdArgs& a, cudaStream_t s) {
-  const size_t smem = (size_t)2 * 4 * 7 * 32 * sizeof(float);
+  const size_t smem = (size_t)2 * 4 * 7 * 32 * sizeof(float) + (size_t)2 * LB_TL * sizeof(float4);
   dim3 grid(2, 32, a.z1.B);
   latent_bwd_kernel<<<grid, 256, smem, s>>>(a);
   NEF_CHECK_LAUNCH("latent_bwd_kernel");
