@@ -1022,7 +1022,8 @@ int dec_out_fwd(T4 c4, const float* scale, const float* shift, const float* w, c
 //   g4[l][ci] = (sum_t dy[l-t+1] w[ci][t]) * (a4 > 0) ; s1 += g4 ; s2 += g4 * xhat
 // grid: x = position blocks (grid-stride), y = the 16 channel chunks.  Every thread keeps its 5 float4 partial sums in
 // registers over all its positions; one block reduction at the end.
-constexpr int DOB_SPAN = 1024;
+constexpr int DOB_R = 4;               // consecutive samples per thread
+constexpr int DOB_SPAN = 256 * DOB_R;  // samples per block unit
 __global__ void __launch_bounds__(256) dec_out_bwd_kernel(T4 c4t, BnLayer bn, const float* __restrict__ w,
                                                           const float* __restrict__ out, const float* __restrict__ dout,
                                                           T4 g4, float* __restrict__ dw, float* __restrict__ db) {
@@ -1043,29 +1044,43 @@ __global__ void __launch_bounds__(256) dec_out_bwd_kernel(T4 c4t, BnLayer bn, co
     const int b = (int)(u / spans);
     const int l0 = (int)(u - (long)b * spans) * DOB_SPAN;
     const int l1 = min(L, l0 + DOB_SPAN);
-   for (int l = l0 + tid; l < l1; l += 256) {
-    const float* op = out + (long)b * L + l;
-    const float* dp = dout + (long)b * L + l;
-    const float dy0 = dp[0] * op[0] * (1.0f - op[0]) * (1.0f / 3.0f);
-    const float dym = l > 0 ? dp[-1] * op[-1] * (1.0f - op[-1]) * (1.0f / 3.0f) : 0.f;
-    const float dyp = l + 1 < L ? dp[1] * op[1] * (1.0f - op[1]) * (1.0f / 3.0f) : 0.f;
-    const float4* p = c4t.at(c, b, l);
-    const float4 cv = p[0];
-    const float4 a0 = bn_relu4(cv, sc, sh);
-    const float4 am = l > 0 ? bn_relu4(p[-1], sc, sh) : f4zero();
-    const float4 ap = l + 1 < L ? bn_relu4(p[1], sc, sh) : f4zero();
-    // da4[l] = dy[l+1] w[.,0] + dy[l] w[.,1] + dy[l-1] w[.,2]
-    const float4 dd = w0 * dyp + w1 * dy0 + w2 * dym;
-    const float4 gv = make_float4(a0.x > 0.f ? dd.x : 0.f, a0.y > 0.f ? dd.y : 0.f, a0.z > 0.f ? dd.z : 0.f, a0.w > 0.f ? dd.w : 0.f);
-    const float4 xh = make_float4((cv.x - mu.x) * is.x, (cv.y - mu.y) * is.y, (cv.z - mu.z) * is.z, (cv.w - mu.w) * is.w);
-    *g4.at(c, b, l) = gv;
-    s1 = s1 + gv;
-    s2 = s2 + gv * xh;
-    a_m = a_m + am * dy0;
-    a_0 = a_0 + a0 * dy0;
-    a_p = a_p + ap * dy0;
-    dbl += dy0;
-   }
+    // a thread owns DOB_R consecutive samples: the rows l-1 .. l+DOB_R are loaded once (all loads issued before use)
+    // and the three-tap neighbours come from registers
+    const int l = l0 + tid * DOB_R;
+    if (l < l1) {
+      const float* op = out + (long)b * L;
+      const float* dp = dout + (long)b * L;
+      const float4* p = c4t.at(c, b, 0);
+      float dy[DOB_R + 2];
+      float4 av[DOB_R + 2], cv[DOB_R];
+#pragma unroll
+      for (int i = 0; i < DOB_R + 2; ++i) {
+        const int li = l - 1 + i;
+        const bool ok = li >= 0 && li < L;
+        const float o = ok ? op[li] : 0.f, d = ok ? dp[li] : 0.f;
+        dy[i] = d * o * (1.0f - o) * (1.0f / 3.0f);
+        const float4 cr = ok ? p[li] : f4zero();
+        if (i >= 1 && i <= DOB_R) cv[i - 1] = cr;
+        av[i] = ok ? bn_relu4(cr, sc, sh) : f4zero();
+      }
+#pragma unroll
+      for (int i = 1; i <= DOB_R; ++i) {
+        if (l + i - 1 < L) {
+          // da4[l] = dy[l+1] w[.,0] + dy[l] w[.,1] + dy[l-1] w[.,2]
+          const float4 dd = w0 * dy[i + 1] + w1 * dy[i] + w2 * dy[i - 1];
+          const float4 a0 = av[i], cc = cv[i - 1];
+          const float4 gv = make_float4(a0.x > 0.f ? dd.x : 0.f, a0.y > 0.f ? dd.y : 0.f, a0.z > 0.f ? dd.z : 0.f, a0.w > 0.f ? dd.w : 0.f);
+          const float4 xh = make_float4((cc.x - mu.x) * is.x, (cc.y - mu.y) * is.y, (cc.z - mu.z) * is.z, (cc.w - mu.w) * is.w);
+          *g4.at(c, b, l + i - 1) = gv;
+          s1 = s1 + gv;
+          s2 = s2 + gv * xh;
+          a_m = a_m + av[i - 1] * dy[i];
+          a_0 = a_0 + a0 * dy[i];
+          a_p = a_p + av[i + 1] * dy[i];
+          dbl += dy[i];
+        }
+      }
+    }
   }
   float v[21] = {s1.x, s1.y, s1.z, s1.w, s2.x, s2.y, s2.z, s2.w, a_m.x, a_m.y, a_m.z, a_m.w,
                  a_0.x, a_0.y, a_0.z, a_0.w, a_p.x, a_p.y, a_p.z, a_p.w, dbl};
