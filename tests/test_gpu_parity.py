@@ -202,6 +202,60 @@ def test_oracle_fixed_upstream(B, G, L, seed, ragged, mode_name):
         np.testing.assert_allclose(sd[k].numpy(), v.numpy(), rtol=1e-4 if exact else 2e-3, atol=1e-5 if exact else 2e-4)
 
 
+def test_long_sequence_config4_shape():
+    """BASELINE config 4 shape (12 leads x 20000 samples, PTB rate) at a batch the CPU oracle finishes in seconds:
+    training-mode outputs of the production path within the north-star tolerance."""
+    dev = torch.device("cuda:0")
+    B, G, L, seed = 1, 12, 20000, 21
+    P = O.make_params(G, seed)
+    inp = O.make_inputs(B, G, L, seed)
+    random.seed(seed)
+    c1, c2 = random.randint(0, G - 1), random.randint(0, G - 1)
+    with mode("tf32_tc"):
+        m = _model(G, P, dev)
+        random.seed(seed)
+        d = _to(inp, dev)
+        with torch.no_grad():
+            outs = m(d["x"], d["input_thetas"], d["query_theta"], d["rois"], phase="train")
+        outs = [o.cpu() for o in outs]
+    with torch.no_grad():
+        oo = O.forward({k: v.clone() for k, v in P.items()}, inp["x"], inp["input_thetas"], inp["query_theta"], inp["rois"],
+                       phase="train", lead_choice=(c1, c2))
+    for a, b in zip(outs, oo):
+        np.testing.assert_allclose(a.numpy(), b.numpy(), rtol=OUT_RTOL, atol=0)
+
+
+def test_panorama_sweep_config5_shape():
+    """BASELINE config 5 shape: encode once, decode 24 Angular-Encoding query views (eval mode, running statistics),
+    through forward(phase='test') and through gen_ecg on the 'gen' latents; both against the oracle."""
+    dev = torch.device("cuda:0")
+    B, G, L, V, seed = 2, 12, 5000, 24, 22
+    P = O.make_params(G, seed)
+    for k in P:   # non-trivial running statistics, as after training
+        if k.endswith("running_mean"):
+            P[k] = 0.05 * torch.randn_like(P[k])
+        if k.endswith("running_var"):
+            P[k] = 0.5 + torch.rand_like(P[k])
+    inp = O.make_inputs(B, G, L, seed, V=V)
+    random.seed(seed)
+    c1, c2 = random.randint(0, G - 1), random.randint(0, G - 1)
+    with mode("tf32_tc"):
+        m = _model(G, P, dev, train=False)
+        random.seed(seed)
+        d = _to(inp, dev)
+        outs = m(d["x"], d["input_thetas"], d["query_theta"], d["rois"], rest_theta=d["rest_theta"], phase="test")
+        z1, z2 = m(d["x"], d["input_thetas"], d["query_theta"], d["rois"], phase="gen")
+        gen = m.gen_ecg(z1, z2, d["rest_theta"], d["rois"]).cpu()
+        outs = [o.cpu() for o in outs]
+    with torch.no_grad():
+        oo = O.forward({k: v.clone() for k, v in P.items()}, inp["x"], inp["input_thetas"], inp["query_theta"], inp["rois"],
+                       rest_theta=inp["rest_theta"], phase="test", lead_choice=(c1, c2), bn_training=False)
+    assert outs[3].shape == (B, V, L)
+    for a, b in zip(outs, oo):
+        np.testing.assert_allclose(a.numpy(), b.numpy(), rtol=OUT_RTOL, atol=0)
+    np.testing.assert_allclose(gen.numpy(), oo[3].numpy(), rtol=OUT_RTOL, atol=0)
+
+
 def test_standin_loss_kernels(cfg):
     """nef_loss_fwd / nef_loss_bwd against torch on identical inputs (exact op-level check)."""
     from network import losswrapper
