@@ -756,22 +756,29 @@ int latent_bwd(const LatentBwdArgs& a, cudaStream_t s) {
 // ===========================================================================================
 // One block per channel: the per-tile partial sums are reduced in a fixed order (thread-strided double
 // accumulation, then a fixed shared-memory tree), so equal conv outputs give bit-equal statistics.
-__global__ void __launch_bounds__(128) bn_finalize_kernel(BnLayer bn, int C, double count, const float* __restrict__ gamma,
-                                                          const float* __restrict__ beta, float* rmean, float* rvar,
-                                                          int64_t* nbt, int training) {
-  __shared__ double r1[128], r2[128];
+// (A coalesced variant -- 8 channels x 32 record lanes per block -- was 6x slower: 157 dependent-latency steps per thread.)
+constexpr int BNF_T = 512;  // the reduction is latency-bound (one strided load per record): many short per-thread chains
+__global__ void __launch_bounds__(BNF_T) bn_finalize_kernel(BnLayer bn, int C, double count, const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta, float* rmean, float* rvar,
+                                                            int64_t* nbt, int training) {
+  __shared__ double r1[BNF_T], r2[BNF_T];
   const int c = blockIdx.x, tid = threadIdx.x;
   float mean, invstd;
   if (training) {
     double a = 0.0, b = 0.0;
-    for (int t = tid; t < bn.n_rec; t += 128) {
-      a += (double)bn.sum[(long)t * C + c];
-      b += (double)bn.sq[(long)t * C + c];
+    for (int t = tid; t < bn.n_rec; t += 2 * BNF_T) {   // two records per step: their loads are in flight together
+      const int t2 = t + BNF_T;
+      const float a0 = bn.sum[(long)t * C + c], b0 = bn.sq[(long)t * C + c];
+      const float a1 = t2 < bn.n_rec ? bn.sum[(long)t2 * C + c] : 0.f, b1 = t2 < bn.n_rec ? bn.sq[(long)t2 * C + c] : 0.f;
+      a += (double)a0;
+      b += (double)b0;
+      a += (double)a1;
+      b += (double)b1;
     }
     r1[tid] = a;
     r2[tid] = b;
     __syncthreads();
-    for (int o = 64; o > 0; o >>= 1) {
+    for (int o = BNF_T / 2; o > 0; o >>= 1) {
       if (tid < o) {
         r1[tid] += r1[tid + o];
         r2[tid] += r2[tid + o];
@@ -801,7 +808,7 @@ __global__ void __launch_bounds__(128) bn_finalize_kernel(BnLayer bn, int C, dou
 }
 int bn_finalize(const BnLayer& bn, int C, double count, const float* gamma, const float* beta, float* rmean,
                 float* rvar, int64_t* nbt, int training, cudaStream_t s) {
-  bn_finalize_kernel<<<C, 128, 0, s>>>(bn, C, count, gamma, beta, rmean, rvar, nbt, training);
+  bn_finalize_kernel<<<C, BNF_T, 0, s>>>(bn, C, count, gamma, beta, rmean, rvar, nbt, training);
   NEF_CHECK_LAUNCH("bn_finalize_kernel");
   return 0;
 }
