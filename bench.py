@@ -220,7 +220,7 @@ def main():
     import network
     from network import _native as N
     from network.optim import FlatSGD, allreduce_gradients
-    from oracle import nefnet_oracle as O  # synthetic input generator only (and the cpu_baseline leg)
+    from dataset.synthetic import make_inputs  # product-side synthetic batches; oracle/ is only used by cpu_baseline()
 
     G, L, B = 12, args.length, args.batch
     lib = N.init(local)
@@ -230,7 +230,7 @@ def main():
     opt = FlatSGD(model, lr=0.1, momentum=0.9)
     loss_fn = network.build_loss(type("C", (), {"MODEL": type("M", (), {"loss": "v1"})}))
 
-    host = O.make_inputs(min(B, 16), G, L, seed=rank)
+    host = make_inputs(min(B, 16), G, L, seed=rank)
     reps = (B + host["x"].shape[0] - 1) // host["x"].shape[0]
     host = {k: v.repeat(*([reps] + [1] * (v.dim() - 1)))[:B].contiguous().pin_memory() for k, v in host.items()}
     resident = {k: v.to(dev) for k, v in host.items()}

@@ -51,7 +51,7 @@ extern "C" int nef_set_conv_impl(int impl) {
 extern "C" int nef_get_conv_impl(void) { return g_conv_impl; }
 // Decoder first conv (256 -> 128 on the query-scaled latent): number of split-precision terms.
 //   3: x_hi w_hi + x_lo w_hi + x_hi w_lo   2: x_hi w_hi + x_lo w_hi   1: x_hi w_hi only
-// Default 3.  Measured worst output error (tools/dec1_terms_probe.py, profiles/r01_dec1_split_terms_probe.txt): 9.4e-4 /
+// Default 3.  Measured worst output error (tests/probe_dec1_terms.py, profiles/r01_dec1_split_terms_probe.txt): 9.4e-4 /
 // 6.4e-4 / 5.9e-4 relative for 1 / 2 / 3 terms against the 1e-3 bar; 2 terms save ~0.2 ms per decoder call at batch 256 but
 // leave less margin (and move the noisiest weight gradient, W_encoder.layer1.2.conv2, from cosine 0.86 to 0.75 at B = 1).
 static int g_dec1_terms = 3;

@@ -1,6 +1,6 @@
 """Worst relative output error of the production (tcgen05 TF32) path against the fp32 oracle for 1, 2 and 3
 split-precision terms in the decoder's first convolution (nef_set_dec1_terms).  Run on the GPU box:
-    python tools/dec1_terms_probe.py"""
+    python tests/probe_dec1_terms.py"""
 import os, random, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "electrocardio-panorama_b200"))

@@ -86,3 +86,30 @@ def test_no_gpu_means_loud_failure():
     from network import _native as N
     with pytest.raises(RuntimeError):
         N.init(0)
+
+
+def test_product_never_touches_the_oracle():
+    """oracle/ is test infrastructure: nothing in the product package, the C sources or the tools may import it, and
+    bench.py only inside cpu_baseline() (the reported CPU leg)."""
+    import ast
+    import glob
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = os.path.join(root, "electrocardio-panorama_b200")
+    files = glob.glob(os.path.join(pkg, "**", "*.py"), recursive=True) + glob.glob(os.path.join(root, "tools", "*.py"))
+    assert files
+    for f in files:
+        tree = ast.parse(open(f).read())
+        for node in ast.walk(tree):
+            mods = []
+            if isinstance(node, ast.Import):
+                mods = [a.name for a in node.names]
+            elif isinstance(node, ast.ImportFrom):
+                mods = [node.module or ""]
+            assert not any(m.split(".")[0] == "oracle" for m in mods), f
+    tree = ast.parse(open(os.path.join(root, "bench.py")).read())
+    for fn in [n for n in ast.walk(tree) if isinstance(n, ast.FunctionDef)]:
+        for node in ast.walk(fn):
+            if isinstance(node, ast.ImportFrom) and (node.module or "").split(".")[0] == "oracle":
+                assert fn.name == "cpu_baseline", fn.name
+    for node in tree.body:   # no module-level import either
+        assert not (isinstance(node, (ast.Import, ast.ImportFrom)) and "oracle" in ast.dump(node))

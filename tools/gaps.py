@@ -6,7 +6,7 @@ import torch
 from torch.profiler import profile, ProfilerActivity
 import network, bench
 from network.optim import FlatSGD
-from oracle import nefnet_oracle as O
+from dataset import synthetic as O  # synthetic input generator
 dev = torch.device("cuda:0")
 G, L, B = 12, 5000, 256
 torch.manual_seed(0); random.seed(0)

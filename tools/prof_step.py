@@ -13,7 +13,7 @@ a = ap.parse_args()
 import network
 from network import _native as N, ops
 from network.optim import FlatSGD
-from oracle import nefnet_oracle as O  # synthetic input generator only
+from dataset import synthetic as O  # synthetic input generator
 dev = torch.device("cuda:0")
 lib = N.init(0)
 G, L, B = 12, a.length, a.batch

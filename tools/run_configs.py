@@ -6,7 +6,7 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "electrocardio-p
 import torch
 import network, bench
 from network.optim import FlatSGD
-from oracle import nefnet_oracle as O
+from dataset import synthetic as O  # synthetic input generator
 dev = torch.device("cuda:0")
 G = 12
 torch.manual_seed(0); random.seed(0)
