@@ -598,13 +598,18 @@ __global__ void __launch_bounds__(256) latent_fwd_kernel(const LatentArgs a) {
   }
 }
 
+constexpr int LAT_FWD_SMEM_MAX = 200 * 1024;
+// per-device opt-in to large dynamic shared memory, called once from nef_init (no lazily-set static state in the launchers)
+int elem_init() {
+  cudaError_t e = cudaFuncSetAttribute(latent_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LAT_FWD_SMEM_MAX);
+  NEF_REQUIRE(e == cudaSuccess, "nef_init: shared-memory opt-in failed: %s", cudaGetErrorString(e));
+  return 0;
+}
+
 int latent_fwd(const LatentArgs& a, cudaStream_t s) {
   const size_t smem = ((size_t)a.G * 7 * 32 + 2 * (LAT_TL + 2)) * sizeof(float4);
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    cudaFuncSetAttribute(latent_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured = smem;
-  }
+  NEF_REQUIRE(smem <= LAT_FWD_SMEM_MAX, "latent_fwd: %d leads need %zu bytes of shared memory (max %d)", a.G, smem,
+              LAT_FWD_SMEM_MAX);
   dim3 grid(a.z1.B, 32, 2);
   latent_fwd_kernel<<<grid, 256, smem, s>>>(a);
   NEF_CHECK_LAUNCH("latent_fwd_kernel");

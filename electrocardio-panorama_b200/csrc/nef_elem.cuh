@@ -56,6 +56,7 @@ struct LatentArgs {
   int write_lat;          // 0: lat already built, only (re)build u0 from it with another q
 };
 int latent_fwd(const LatentArgs& a, cudaStream_t s);
+int elem_init();  // shared-memory opt-ins of the kernels in nef_elem.cu (once per device, from nef_init)
 struct LatentBwdArgs {
   T4 du0[3]; T4 lat[3]; T4 z1, z2o; const int64_t* rois; const float* q; int q_stride; int G, c1, c2;
   T4 gz1;                 // out: grad wrt pre-ReLU z1 (128G, L4)

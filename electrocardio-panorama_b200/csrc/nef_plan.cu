@@ -80,6 +80,8 @@ extern "C" int nef_init(int device) {
   NEF_REQUIRE(p.major == 10, "nef_init: device %d is sm_%d%d; this library is built for sm_100a (B200) only", device,
               p.major, p.minor);
   cudaSetDevice(device);
+  int rc = elem_init();
+  if (rc) return rc;
   return nef_tc_init();
 }
 

@@ -9,18 +9,31 @@ import torch
 from . import _native as N
 
 
-class FlatSGD:
+class FlatSGD(torch.optim.Optimizer):
+    """SGD with momentum over the module's flat parameter / gradient buffers.  It is a ``torch.optim.Optimizer`` (one
+    param group), so the reference's schedulers (``StepLR(optim, 50, gamma=0.1)`` / ``MultiStepLR``,
+    optim_scheduler.py:13-18) and ``optim.zero_grad()`` / ``optim.step()`` (solver.py:232-235) drive it unchanged; the
+    learning rate is read from ``param_groups[0]['lr']`` at every step."""
+
     def __init__(self, model, lr=0.1, momentum=0.9):
         self.model = model
-        self.lr = float(lr)
-        self.momentum = float(momentum)
         self._mom = None
+        super().__init__(list(model.parameters()), dict(lr=float(lr), momentum=float(momentum)))
 
-    def zero_grad(self):
+    @property
+    def lr(self):
+        return float(self.param_groups[0]["lr"])
+
+    @property
+    def momentum(self):
+        return float(self.param_groups[0]["momentum"])
+
+    def zero_grad(self, set_to_none=True):
         for p in self.model.parameters():
             p.grad = None
 
-    def step(self, world_size=1):
+    @torch.no_grad()
+    def step(self, world_size=1, closure=None):
         m = self.model
         flat, grad = m.flat_params, m.flat_grads
         if flat is None:
@@ -30,6 +43,38 @@ class FlatSGD:
         lib = N.load()
         N.check(lib.nef_sgd_step(N.ptr(flat), N.ptr(grad), N.ptr(self._mom), flat.numel(), self.lr, self.momentum,
                                  1.0 / float(world_size), N.stream_ptr()), "nef_sgd_step")
+
+    # checkpoints (utils/checkpointer.py:28-31 saves optimizer.state_dict()): the momentum lives in one flat buffer
+    def state_dict(self):
+        return {"param_groups": [{k: v for k, v in self.param_groups[0].items() if k != "params"}],
+                "flat_momentum": None if self._mom is None else self._mom.detach().cpu()}
+
+    def load_state_dict(self, sd):
+        for k, v in sd["param_groups"][0].items():
+            self.param_groups[0][k] = v
+        mom = sd.get("flat_momentum")
+        self._mom = None if mom is None else mom.to(self.model.flat_params.device if self.model.flat_params is not None
+                                                    else "cuda")
+
+
+def get_optimizer(cfg, model):
+    """optim_scheduler.py:5-10 with the model instead of its parameter list: 'sgd' -> FlatSGD(momentum 0.9); 'adam' is
+    not on the hot path and stays torch's."""
+    if cfg.SOLVER.optim == "sgd":
+        return FlatSGD(model, lr=cfg.SOLVER.lr, momentum=0.9)
+    if cfg.SOLVER.optim == "adam":
+        return torch.optim.Adam(model.parameters(), lr=cfg.SOLVER.lr)
+    raise ValueError("get_optimizer: unknown optimiser %r" % (cfg.SOLVER.optim,))
+
+
+def get_lr_scheduler(cfg, optim=None):
+    """optim_scheduler.py:13-18, unchanged semantics."""
+    from torch.optim.lr_scheduler import MultiStepLR, StepLR
+    if cfg.SOLVER.scheduler == "steplr":
+        return StepLR(optim, 50, gamma=0.1)
+    if cfg.SOLVER.scheduler == "MultiStep":
+        return MultiStepLR(optim, cfg.SOLVER.lr_step, gamma=0.1)
+    return None
 
 
 def allreduce_gradients(model, group=None):

@@ -324,6 +324,43 @@ def test_sgd_step_matches_torch():
     np.testing.assert_allclose(pd.cpu().numpy(), ref_p.detach().numpy(), rtol=1e-5, atol=1e-6)
 
 
+def test_flat_sgd_with_reference_scheduler(cfg):
+    """FlatSGD is a torch Optimizer: the reference's StepLR / MultiStepLR (optim_scheduler.py:13-18) drive its learning
+    rate, and the trajectory equals torch.optim.SGD(momentum=0.9) + the same scheduler on the same gradients."""
+    from network.optim import FlatSGD
+    from torch.optim.lr_scheduler import MultiStepLR
+    dev = torch.device("cuda:0")
+    G, B, L, seed = 2, 2, 64, 5
+    P = O.make_params(G, seed)
+    inp = _to(O.make_inputs(B, G, L, seed), dev)
+    with mode("exact_simt"):
+        m = _model(G, P, dev)
+        opt = FlatSGD(m, lr=0.1, momentum=0.9)
+        sch = MultiStepLR(opt, [1, 2], gamma=0.1)
+        ref = {n: torch.nn.Parameter(p.detach().clone()) for n, p in m.named_parameters() if n in O.live_param_names(G)}
+        ropt = torch.optim.SGD(list(ref.values()), lr=0.1, momentum=0.9)
+        rsch = MultiStepLR(ropt, [1, 2], gamma=0.1)
+        lrs = []
+        for it in range(3):
+            random.seed(seed + it)
+            outs = m(inp["x"], inp["input_thetas"], inp["query_theta"], inp["rois"], phase="train")
+            network_loss = __import__("network").losswrapper(outs[0], outs[1], outs[2], inp["target"], cfg)[0]
+            network_loss.backward()
+            for n, p in m.named_parameters():
+                if n in ref:
+                    ref[n].grad = p.grad.detach().clone()
+            lrs.append(opt.lr)
+            opt.step(); ropt.step()
+            opt.zero_grad(); ropt.zero_grad()
+            sch.step(); rsch.step()
+        assert lrs == pytest.approx([0.1, 0.01, 0.001])
+        got = dict(m.named_parameters())
+        for n, r in ref.items():
+            np.testing.assert_allclose(got[n].detach().cpu().numpy(), r.detach().cpu().numpy(), rtol=2e-5, atol=1e-6, err_msg=n)
+        sd = opt.state_dict()
+        assert float(sd["flat_momentum"].abs().max()) > 0 and sd["param_groups"][0]["lr"] == pytest.approx(0.001)
+
+
 def test_cpu_input_raises():
     import network
     m = network.Model_nefnet(1, 1)
