@@ -48,6 +48,8 @@ struct NefPackJob {
   long sg, sn, sk, st;
   int flags;        // bit 0: flip taps, bit 1: TF32 residual
   int first_block;  // filled by nef_pack_weights_batch
+  const float* nscale;  // optional [groups * N]: the weights of output channel (g, n) are multiplied by nscale[g * N + n]
+                        //   before rounding (inference-time BatchNorm folding)
 };
 struct NefPackTable {
   NefPackJob job[NEF_PACK_MAX];

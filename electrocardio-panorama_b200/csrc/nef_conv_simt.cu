@@ -229,7 +229,8 @@ __global__ void __launch_bounds__(256) pack_weights_batch_kernel(const __grid_co
     const int g = (int)r;
     const int k = kb * 32 + c * 4 + j;
     const int ts = (q.flags & 1) ? q.taps - 1 - t : t;
-    const float wv = q.src[g * q.sg + n * q.sn + k * q.sk + ts * q.st];
+    float wv = q.src[g * q.sg + n * q.sn + k * q.sk + ts * q.st];
+    if (q.nscale) wv *= q.nscale[g * q.N + n];
     const float hi = tf32_rn(wv);
     q.dst[i] = (q.flags & 2) ? tf32_rn(wv - hi) : hi;
   }

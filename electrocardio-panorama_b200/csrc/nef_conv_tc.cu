@@ -980,7 +980,7 @@ static int g_tc_persist = 1;  // persistent forward kernel (NEF_TC_PERSIST=0: on
 static int g_tc_mt = 0;  // 0 = automatic; 4 forces four row tiles per CTA, one CTA per SM (NEF_TC_MT, for A/B measurements)
 
 // the specialised epilogues instantiated for the 4-row-tile kernel (everything else takes the generic one)
-#define NEF_TC_EPI_LIST(X) X(0) X(2) X(32) X(33) X(36) X(37) X(38) X(44) X(48) X(50) X(64) X(294) X(418) X(513)
+#define NEF_TC_EPI_LIST(X) X(0) X(2) X(5) X(32) X(33) X(36) X(37) X(38) X(44) X(48) X(50) X(64) X(294) X(418) X(513)
 
 template <int MT, int EPI>
 static int tc_optin() {

@@ -579,7 +579,7 @@ __global__ void __launch_bounds__(256) latent_fwd_kernel(const LatentArgs a) {
       // lat_all = [z1m, z2m], lat_p = [z1[c1], z2m], lat_l = [z1m, z2[c2]]
       const bool use_pick = (k3 == 1 && half == 0) || (k3 == 2 && half == 1);
       const float4* src = use_pick ? pt : mt;
-      if (a.write_lat) {
+      if (a.write_lat && ((a.store_mask >> (2 * k3 + half)) & 1)) {
         for (int i = tid; i < nl; i += 256) *a.lat[k3].at(latc, b, t0 + i) = src[i + 1];
       }
       for (int i = tid; i < 2 * nl; i += 256) {
@@ -815,6 +815,34 @@ int bn_finalize(const BnLayer& bn, int C, double count, const float* gamma, cons
                 float* rvar, int64_t* nbt, int training, cudaStream_t s) {
   bn_finalize_kernel<<<C, BNF_T, 0, s>>>(bn, C, count, gamma, beta, rmean, rvar, nbt, training);
   NEF_CHECK_LAUNCH("bn_finalize_kernel");
+  return 0;
+}
+
+__global__ void fill_f32_kernel(float* p, float v, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+int fill_f32(float* p, float v, int n, cudaStream_t s) {
+  fill_f32_kernel<<<(n + 127) / 128, 128, 0, s>>>(p, v, n);
+  NEF_CHECK_LAUNCH("fill_f32_kernel");
+  return 0;
+}
+
+// Inference: BatchNorm with running statistics folded into the preceding convolution,
+//   bn(conv(x) + b) = conv_{w * s}(x) + (b * s + beta - mean * s),  s = gamma / sqrt(var + eps)
+__global__ void bn_fold_eval_kernel(const float* __restrict__ gamma, const float* __restrict__ beta,
+                                    const float* __restrict__ rmean, const float* __restrict__ rvar,
+                                    const float* __restrict__ bias, float* __restrict__ wscale, float* __restrict__ fbias, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float sc = gamma[c] * (1.0f / sqrtf(rvar[c] + 1e-5f));
+  wscale[c] = sc;
+  fbias[c] = bias[c] * sc + (beta[c] - rmean[c] * sc);
+}
+int bn_fold_eval(const float* gamma, const float* beta, const float* rmean, const float* rvar, const float* bias, float* wscale,
+                 float* fbias, int C, cudaStream_t s) {
+  bn_fold_eval_kernel<<<(C + 127) / 128, 128, 0, s>>>(gamma, beta, rmean, rvar, bias, wscale, fbias, C);
+  NEF_CHECK_LAUNCH("bn_fold_eval_kernel");
   return 0;
 }
 

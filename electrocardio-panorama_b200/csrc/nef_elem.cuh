@@ -54,6 +54,9 @@ struct LatentArgs {
   T4 u0lo[3];             // TF32 residual of the same (split-precision input of the decoder's first conv)
   int n_lat;              // 3 (train) or 1 (extra views: only lat[0] / u0[0])
   int write_lat;          // 0: lat already built, only (re)build u0 from it with another q
+  int store_mask;         // with write_lat: bit (2 k + half) = store half (0: z1 channels, 1: z2 channels) of lat[k].
+                          //   training needs only the z2 halves of lat[0] and lat[2] (latent_bwd rebuilds the rest from z1);
+                          //   the extra views of the test phase / gen_ecg re-read both halves of lat[0]
 };
 int latent_fwd(const LatentArgs& a, cudaStream_t s);
 int elem_init();  // shared-memory opt-ins of the kernels in nef_elem.cu (once per device, from nef_init)
@@ -67,6 +70,9 @@ int latent_bwd(const LatentBwdArgs& a, cudaStream_t s);
 
 int bn_finalize(const BnLayer& bn, int C, double count, const float* gamma, const float* beta, float* rmean,
                 float* rvar, int64_t* nbt, int training, cudaStream_t s);
+int fill_f32(float* p, float v, int n, cudaStream_t s);
+int bn_fold_eval(const float* gamma, const float* beta, const float* rmean, const float* rvar, const float* bias, float* wscale,
+                 float* fbias, int C, cudaStream_t s);
 int bn_relu(T4 c, const float* scale, const float* shift, T4 out, int upsample, cudaStream_t s);
 int up_adjoint(T4 du, T4 da, cudaStream_t s);
 int bnbwd_stats(T4 da, T4 c, const BnLayer& bn, cudaStream_t s);

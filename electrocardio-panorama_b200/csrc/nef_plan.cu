@@ -208,6 +208,9 @@ struct NefPlan {
   ConvW enc[6], wc[2], z1c[3], z2c1[3], z2a[2], z2b[3], decw[4];
   float *ct_f[2], *ct_d[2];
   float* dec1_lo;         // TF32 residual of the decoder first conv weights, forward packing
+  float *fold_scale[4], *fold_bias[4];  // inference: BatchNorm folded into the decoder convolutions (per output channel)
+  float *ident_scale, *ident_shift;     // 128 ones / zeros: identity "BatchNorm" for the kernels that still apply one
+  bool folded;            // the packed decoder weights of this forward carry the folded BatchNorm
   // saved forward state
   const float* x_in; const float* thetas_in; const float* query_in; const int64_t* rois_in;
   int c1, c2; float drop_p; int bn_training; bool have_fwd;
@@ -316,6 +319,8 @@ static void carve(NefPlan* p, bool dry) {
   carve_convw(c, p->decw[1], P_DEC1 + 7, 1, 128, 128, 3);
   carve_convw(c, p->decw[2], P_DEC3 + 0, 1, 64, 128, 3);
   carve_convw(c, p->decw[3], P_DEC3 + 7, 1, 64, 64, 3);
+  for (int i = 0; i < 4; ++i) { p->fold_scale[i] = c.f32(128); p->fold_bias[i] = c.f32(128); }
+  p->ident_scale = c.f32(128); p->ident_shift = c.f32(128);
   for (int t = 0; t < 2; ++t) {
     p->ct_f[t] = c.f32((size_t)7 * G * 128 * 64);
     p->ct_d[t] = c.f32((size_t)7 * G * 128 * 64);
@@ -344,6 +349,10 @@ extern "C" int nef_plan_bind(NefPlan* p, void* ws, size_t bytes, nef_stream_t s)
   carve(p, false);
   cudaError_t e = cudaMemsetAsync(ws, 0, p->ws_bytes, (cudaStream_t)s);
   NEF_REQUIRE(e == cudaSuccess, "nef_plan_bind: memset failed: %s", cudaGetErrorString(e));
+  {
+    int rc = fill_f32(p->ident_scale, 1.0f, 128, (cudaStream_t)s);
+    if (rc) return rc;
+  }
   p->bound = true;
   p->have_fwd = false;
   return 0;
@@ -416,16 +425,16 @@ static int wgrad_std(const T4& dy, int dy_off, int dy_gs, const T4& x, int x_off
 
 // packing jobs are queued in a table and launched together (nef_pack_weights_batch)
 static int queue_pack(NefPackTable& t, const float* src, float* dst, int groups, int N, int K, int taps, int64_t sg, int64_t sn,
-                      int64_t sk, int64_t st, int flags, cudaStream_t s) {
+                      int64_t sk, int64_t st, int flags, cudaStream_t s, const float* nscale = nullptr) {
   if (t.n == NEF_PACK_MAX) RUN(nef_pack_weights_batch(&t, s));
   NefPackJob& q = t.job[t.n++];
   q.src = src; q.dst = dst; q.groups = groups; q.N = N; q.K = K; q.taps = taps;
-  q.sg = sg; q.sn = sn; q.sk = sk; q.st = st; q.flags = flags; q.first_block = 0;
+  q.sg = sg; q.sn = sn; q.sk = sk; q.st = st; q.flags = flags; q.first_block = 0; q.nscale = nscale;
   return 0;
 }
-static int pack_fwd(NefPackTable& t, const ConvW& w, const float* const* P, cudaStream_t s) {
+static int pack_fwd(NefPackTable& t, const ConvW& w, const float* const* P, cudaStream_t s, const float* nscale = nullptr) {
   return queue_pack(t, P[w.pidx], w.pk_f, w.groups, w.cout_g, w.cin_g, w.taps, (int64_t)w.cout_g * w.cin_g * w.taps,
-                    (int64_t)w.cin_g * w.taps, w.taps, 1, 0, s);
+                    (int64_t)w.cin_g * w.taps, w.taps, 1, 0, s, nscale);
 }
 // dgrad: N' = cin_g (split into sub-groups of 128 when larger; only for groups == 1), K' = cout_g, flipped taps
 static int pack_dgrad(NefPackTable& t, const ConvW& w, const float* const* P, cudaStream_t s) {
@@ -438,9 +447,30 @@ static int pack_dgrad(NefPackTable& t, const ConvW& w, const float* const* P, cu
                     w.taps, (int64_t)w.cin_g * w.taps, 1, 1, s);
 }
 
-static int pack_dec1_lo(NefPackTable& t, NefPlan* p, const float* const* P, cudaStream_t s) {
+static int pack_dec1_lo(NefPackTable& t, NefPlan* p, const float* const* P, cudaStream_t s, const float* nscale = nullptr) {
   const ConvW& w = p->decw[0];
-  return queue_pack(t, P[w.pidx], p->dec1_lo, 1, 128, 256, 3, 0, 256 * 3, 3, 1, 2, s);
+  return queue_pack(t, P[w.pidx], p->dec1_lo, 1, 128, 256, 3, 0, 256 * 3, 3, 1, 2, s, nscale);
+}
+
+// decoder layer i: parameter indices of its conv bias and of its BatchNorm (weight, bias, running_mean, running_var, nbt)
+static const int kDecBias[4] = {P_DEC1 + 1, P_DEC1 + 8, P_DEC3 + 1, P_DEC3 + 8};
+static const int kDecBn[4] = {P_DEC1 + 2, P_DEC1 + 9, P_DEC3 + 2, P_DEC3 + 9};
+
+// Inference (running statistics, nothing saved for backward): fold every decoder BatchNorm into its convolution and queue
+// the decoder weight packing with the folded scales.  The decoder then runs conv + bias + ReLU epilogues only.
+static int queue_decoder_packs(NefPlan* p, NefPackTable& t, const float* const* P, bool fold, cudaStream_t s) {
+  p->folded = fold;
+  for (int i = 0; i < 4; ++i) {
+    const float* ns = nullptr;
+    if (fold) {
+      RUN(bn_fold_eval(P[kDecBn[i]], P[kDecBn[i] + 1], P[kDecBn[i] + 2], P[kDecBn[i] + 3], P[kDecBias[i]], p->fold_scale[i],
+                       p->fold_bias[i], p->decw[i].cout_g, s));
+      ns = p->fold_scale[i];
+    }
+    RUN(pack_fwd(t, p->decw[i], P, s, ns));
+    if (i == 0) RUN(pack_dec1_lo(t, p, P, s, ns));
+  }
+  return 0;
 }
 
 template <class F>
@@ -485,6 +515,23 @@ static int decoder_fwd(NefPlan* p, const float* const* P, int slot, const T4& u0
                        int out_bstride, cudaStream_t s) {
   DecBufs& d = p->dec[slot];
   const int B = p->B;
+  if (p->folded) {  // inference: conv (BatchNorm folded into weights and bias) + ReLU epilogues, one upsample pass
+    const T4 ins[4] = {u0, d.a1, d.u1, d.a3};
+    const T4 outs[4] = {d.a1, d.c2, d.a3, d.c4};
+    for (int i = 0; i < 4; ++i) {
+      const ConvW& w = p->decw[i];
+      CD c(1, w.cout_g, ins[i]);
+      c.term(ins[i], 0, 0, w.cin_g, 3, w.pk_f).out(outs[i], 0, 0).bias(p->fold_bias[i]).relu();
+      if (i == 0) {
+        if (g_dec1_terms >= 2) c.term(u0lo, 0, 0, 256, 3, w.pk_f);
+        if (g_dec1_terms >= 3) c.term(ins[i], 0, 0, 256, 3, p->dec1_lo);
+      }
+      if (i == 0 || i == 2) c.round();  // a1, a3 feed the next tensor-core convolution directly
+      RUN(c.run(s));
+      if (i == 1) RUN(bn_relu(d.c2, p->ident_scale, p->ident_shift, d.u1, 1, s));
+    }
+    RUN(dec_out_fwd(d.c4, p->ident_scale, p->ident_shift, P[P_OUT_W], P[P_OUT_B], d.out, p->L, s));
+  } else {
   struct Lay { const ConvW* w; int pb; T4 in; T4 c; int bnp; double count; };
   const Lay lay[4] = {{&p->decw[0], P_DEC1 + 1, u0, d.c1, P_DEC1 + 2, (double)B * p->L2},
                       {&p->decw[1], P_DEC1 + 8, d.a1, d.c2, P_DEC1 + 9, (double)B * p->L2},
@@ -508,6 +555,7 @@ static int decoder_fwd(NefPlan* p, const float* const* P, int slot, const T4& u0
     if (i == 2) RUN(bn_relu(d.c3, d.bn[2].scale, d.bn[2].shift, d.a3, 0, s));
   }
   RUN(dec_out_fwd(d.c4, d.bn[3].scale, d.bn[3].shift, P[P_OUT_W], P[P_OUT_B], d.out, p->L, s));
+  }
   if (out_user) {
     cudaError_t e = cudaMemcpy2DAsync(out_user, (size_t)out_bstride * sizeof(float), d.out, (size_t)p->L * sizeof(float),
                                       (size_t)p->L * sizeof(float), B, cudaMemcpyDeviceToDevice, s);
@@ -526,12 +574,13 @@ static int latents_to_decoders(NefPlan* p, const float* const* P, const float* q
   if (!only_views) {
     RUN(angular_fwd(query_theta, P[P_MLP2_W], P[P_MLP2_B], p->q, B, 256, s));
     la.q = p->q; la.q_stride = 256; la.n_lat = 3; la.write_lat = 1;
+    la.store_mask = phase == NEF_PHASE_TEST ? 3 : (2 | 32);
     RUN(latent_fwd(la, s));
     float* outs[3] = {out, out_p, out_l};
     for (int k = 0; k < 3; ++k) RUN(decoder_fwd(p, P, k, p->u0[k], p->u0lo[k], training, outs[k], p->L, s));
   } else {
     // gen_ecg: build lat[0] only (mean latents); q unused for that -> use rq view 0 below
-    la.q = p->rq; la.q_stride = V * 256; la.n_lat = 1; la.write_lat = 1;
+    la.q = p->rq; la.q_stride = V * 256; la.n_lat = 1; la.write_lat = 1; la.store_mask = 3;
   }
   if (V > 0 && (phase == NEF_PHASE_TEST || only_views)) {
     NEF_REQUIRE(V <= p->V, "nef_forward: V=%d exceeds the plan's V=%d", V, p->V);
@@ -539,6 +588,7 @@ static int latents_to_decoders(NefPlan* p, const float* const* P, const float* q
     for (int v = 0; v < V; ++v) {
       la.q = p->rq + (size_t)v * 256; la.q_stride = V * 256; la.n_lat = 1;
       la.write_lat = (only_views && v == 0) ? 1 : 0;
+      la.store_mask = 3;
       RUN(latent_fwd(la, s));
       RUN(decoder_fwd(p, P, 0, p->u0[0], p->u0lo[0], training, rest_out + (size_t)v * p->L, V * p->L, s));
     }
@@ -559,8 +609,8 @@ extern "C" int nef_forward(NefPlan* p, const NefForwardArgs* a, nef_stream_t sv)
 
   NefPackTable packs;
   packs.n = 0;
-  RUN(for_all_convw(p, [&](const ConvW& w) { return pack_fwd(packs, w, P, s); }));
-  RUN(pack_dec1_lo(packs, p, P, s));
+  RUN(for_all_convw(p, [&](const ConvW& w) { return (&w >= p->decw && &w < p->decw + 4) ? 0 : pack_fwd(packs, w, P, s); }));
+  RUN(queue_decoder_packs(p, packs, P, !a->bn_training && !a->save_for_backward, s));
   for (int t = 0; t < 2; ++t)  // ConvTranspose1d weight (Cin_total, Cout/groups, 2): one 1x1 conv per tap
     RUN(queue_pack(packs, P[P_CT_W] + t, p->ct_f[t], 7 * G, 64, 128, 1, 128LL * 64 * 2, 2, 64 * 2, 0, 0, s));
   RUN(nef_pack_weights_batch(&packs, s));
@@ -622,8 +672,7 @@ extern "C" int nef_gen_ecg(NefPlan* p, const float* const* P, const float* z1, c
   p->c1 = 0; p->c2 = 0;
   NefPackTable packs;
   packs.n = 0;
-  for (int i = 0; i < 4; ++i) RUN(pack_fwd(packs, p->decw[i], P, s));
-  RUN(pack_dec1_lo(packs, p, P, s));
+  RUN(queue_decoder_packs(p, packs, P, true, s));   // gen_ecg runs the module in eval mode (model_nefnet.py:197)
   RUN(nef_pack_weights_batch(&packs, s));
   RUN(nef_ncl_to_cbl4(z1, reinterpret_cast<float*>(p->z1.p), p->B, p->C1, p->L4, 0, sv));
   RUN(nef_ncl_to_cbl4(z2, reinterpret_cast<float*>(p->z2o.p), p->B, 896 * p->G, 32, 0, sv));
