@@ -214,6 +214,7 @@ struct FwSmem {
 // on 8 warps only and the generic body does not fit the instruction cache.
 constexpr int EPI_BIAS = 1, EPI_RES = 2, EPI_RELU = 4, EPI_DROP = 8, EPI_MASK1 = 16, EPI_ROUND = 32, EPI_GENERIC = 64;
 constexpr int EPI_MASK2 = 128, EPI_BSCALE = 256, EPI_STATS = 512;  // mask mode 2, angular scale, BatchNorm partial statistics
+constexpr int EPI_OBITS = 1024, EPI_MBITS = 2048;                  // write / read one-bit activation masks
 
 // Sum over the 32 lanes of 32 per-lane values at once: after the 5 exchange levels lane j holds the warp total of a[j].
 // 31 shuffles instead of 32 x 5.
@@ -257,7 +258,10 @@ __device__ __forceinline__ void epilogue_tile(const NefConvDesc& d, int g, long 
   const bool f_round = GEN ? d.round_tf32 != 0 : (EPI & EPI_ROUND) != 0;
   const bool f_bscale = GEN ? d.bscale != nullptr : (EPI & EPI_BSCALE) != 0;
   const bool f_bsgrad = GEN && d.bscale_grad != nullptr;
-  const int mask_mode = GEN ? d.mask_mode : ((EPI & EPI_MASK1) ? 1 : ((EPI & EPI_MASK2) ? 2 : 0));
+  const bool f_obits = GEN ? d.out_bits != nullptr : (EPI & EPI_OBITS) != 0;
+  const bool f_mbits = GEN ? (d.mask_bits != nullptr && d.mask_mode != 0) : (EPI & EPI_MBITS) != 0;
+  // mask operand: 0 none, 1 / 2 float tensor (> 0 / != 0), 3 one-bit masks
+  const int mask_mode = f_mbits ? 3 : (GEN ? d.mask_mode : ((EPI & EPI_MASK1) ? 1 : ((EPI & EPI_MASK2) ? 2 : 0)));
   const float mask_scale = d.mask_scale;
   const uint32_t drop_thr = (uint32_t)(d.drop_p * 65536.f);
   const float drop_sc = 1.f / (1.f - d.drop_p);
@@ -276,9 +280,13 @@ __device__ __forceinline__ void epilogue_tile(const NefConvDesc& d, int g, long 
     const float4* rp = reinterpret_cast<const float4*>(d.res) + (long)(d.res_c4_off + g * d.res_c4_gstride) * d.res_cstride + orow;
     const float4* mp = reinterpret_cast<const float4*>(d.mask) + (long)(d.mask_c4_off + g * d.mask_c4_gstride) * d.mask_cstride + orow;
     const float4* bs4 = reinterpret_cast<const float4*>(d.bscale) + (long)(er.valid ? er.b : 0) * (ctot >> 2) + g * (N >> 2);
+    const uint32_t* mbp = d.mask_bits + (long)((d.mask_c4_off + g * d.mask_c4_gstride) >> 3) * d.mask_cstride + orow;
+    uint32_t* obp = d.out_bits + (long)((d.y_c4_off + g * d.y_c4_gstride) >> 3) * d.y_cstride + orow;
     for (int cg = chalf; cg < N / 32; cg += 2) {
       uint32_t v[32];
       tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * N + cg * 32), v);
+      const uint32_t mword = mask_mode == 3 ? __ldg(mbp + (long)cg * d.mask_cstride) : 0u;
+      uint32_t oword = 0u;
       // the residual / mask operands of these 8 chunks are fetched while the TMEM load is in flight
       float4 rr[8], mm[8];
       {
@@ -287,7 +295,7 @@ __device__ __forceinline__ void epilogue_tile(const NefConvDesc& d, int g, long 
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           rr[i] = f_res ? __ldg(rpc) : f4zero();
-          mm[i] = mask_mode ? __ldg(mpc) : f4zero();
+          mm[i] = (mask_mode == 1 || mask_mode == 2) ? __ldg(mpc) : f4zero();
           rpc += d.res_cstride;
           mpc += d.mask_cstride;
         }
@@ -341,9 +349,15 @@ __device__ __forceinline__ void epilogue_tile(const NefConvDesc& d, int g, long 
           const float4 m = mm[i];
           x = make_float4(m.x != 0.f ? x.x * mask_scale : 0.f, m.y != 0.f ? x.y * mask_scale : 0.f,
                           m.z != 0.f ? x.z * mask_scale : 0.f, m.w != 0.f ? x.w * mask_scale : 0.f);
+        } else if (mask_mode == 3) {
+          const uint32_t mb = mword >> (4 * i);
+          x = make_float4((mb & 1u) ? x.x * mask_scale : 0.f, (mb & 2u) ? x.y * mask_scale : 0.f,
+                          (mb & 4u) ? x.z * mask_scale : 0.f, (mb & 8u) ? x.w * mask_scale : 0.f);
         }
         if (f_round) x = rn4_tf32(x);
         if (er.valid) yp[(long)n4 * d.y_cstride] = x;
+        if (f_obits)
+          oword |= ((x.x != 0.f ? 1u : 0u) | (x.y != 0.f ? 2u : 0u) | (x.z != 0.f ? 4u : 0u) | (x.w != 0.f ? 8u : 0u)) << (4 * i);
         if (want_stats) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -353,6 +367,7 @@ __device__ __forceinline__ void epilogue_tile(const NefConvDesc& d, int g, long 
           }
         }
       }
+      if (f_obits && er.valid) obp[(long)cg * d.y_cstride] = oword;
       if (want_stats) {  // lane j ends up with the 32-row totals of channel cg * 32 + j
         const float t1 = warp_sum32(st1, lane), t2 = warp_sum32(st2, lane);
         s_stat[(q * 2 + 0) * 128 + cg * 32 + lane] = t1;
@@ -980,7 +995,8 @@ static int g_tc_persist = 1;  // persistent forward kernel (NEF_TC_PERSIST=0: on
 static int g_tc_mt = 0;  // 0 = automatic; 4 forces four row tiles per CTA, one CTA per SM (NEF_TC_MT, for A/B measurements)
 
 // the specialised epilogues instantiated for the 4-row-tile kernel (everything else takes the generic one)
-#define NEF_TC_EPI_LIST(X) X(0) X(2) X(5) X(32) X(33) X(36) X(37) X(38) X(44) X(48) X(50) X(64) X(294) X(418) X(513)
+#define NEF_TC_EPI_LIST(X) X(0) X(2) X(5) X(32) X(33) X(36) X(37) X(38) X(44) X(48) X(50) X(64) X(294) X(418) X(513) \
+  X(1062) X(1068) X(1318) X(2080) X(2082) X(2338)
 
 template <int MT, int EPI>
 static int tc_optin() {
@@ -1013,12 +1029,15 @@ static int epi_code(const NefConvDesc* d) {
   int e = 0;
   if (d->stat_sum) e |= tc::EPI_STATS;
   if (d->bscale) e |= tc::EPI_BSCALE;
-  if (d->mask_mode == 2) e |= tc::EPI_MASK2;
+  const bool mbits = d->mask_bits != nullptr && d->mask_mode != 0;
+  if (d->mask_mode == 2 && !mbits) e |= tc::EPI_MASK2;
+  if (mbits) e |= tc::EPI_MBITS;
+  if (d->out_bits) e |= tc::EPI_OBITS;
   if (d->bias) e |= tc::EPI_BIAS;
   if (d->res) e |= tc::EPI_RES;
   if (d->relu) e |= tc::EPI_RELU;
   if (d->drop_p > 0.f) e |= tc::EPI_DROP;
-  if (d->mask_mode == 1) e |= tc::EPI_MASK1;
+  if (d->mask_mode == 1 && !mbits) e |= tc::EPI_MASK1;
   if (d->round_tf32) e |= tc::EPI_ROUND;
   return e;
 }

@@ -197,6 +197,9 @@ struct NefPlan {
   DecBufs dec[3];
   float *s_in, *q, *rq;
   uint32_t* s0_amax;      // stem max-pool argmax / ReLU codes, indexed like s0
+  // one-bit (value != 0) masks of the big post-ReLU activations, written by the forward epilogues and read by the masked
+  // data-gradient epilogues instead of the fp32 tensors (NefConvDesc.out_bits / mask_bits)
+  uint32_t *b_eh[3], *b_ey[3], *b_hw, *b_w, *b_h1;
   // gradients
   T4 GA[3];
   T4 gz2o, gh22, dt21, dte, dto, gy20, gh20, dra, gz2c, ghz, gxw;
@@ -254,6 +257,11 @@ static void carve(NefPlan* p, bool dry) {
   p->s0_amax = reinterpret_cast<uint32_t*>(c.take(((size_t)(C1 / 4) * p->s0.cs + NEF_GUARD_ROWS) * sizeof(uint32_t)));
   for (int i = 0; i < 3; ++i) { p->eh[i] = c.t4(C1, L4); p->ey[i] = c.t4(C1, L4); }
   p->hw = c.t4(C1, L4); p->w = c.t4(C1, L4); p->h1 = c.t4(C1, L4); p->z1 = c.t4(C1, L4);
+  {
+    const size_t words = (size_t)(C1 / 32) * p->s0.cs + NEF_GUARD_ROWS;
+    uint32_t** bp[9] = {&p->b_eh[0], &p->b_eh[1], &p->b_eh[2], &p->b_ey[0], &p->b_ey[1], &p->b_ey[2], &p->b_hw, &p->b_w, &p->b_h1};
+    for (auto q : bp) *q = reinterpret_cast<uint32_t*>(c.take(words * sizeof(uint32_t)));
+  }
   p->xw = c.t4(64 * G, p->win.Lw); p->hz = c.t4(C1, p->win.Lw); p->z2c = c.t4(C1, p->win.Lw);
   p->ra = c.t4(896 * G, 16); p->h20 = c.t4(896 * G, 16); p->y20 = c.t4(896 * G, 16);
   p->t21 = c.t4(448 * G, 32); p->h22 = c.t4(896 * G, 32); p->z2o = c.t4(896 * G, 32);
@@ -394,6 +402,8 @@ struct CD {
     return *this;
   }
   CD& stats(float* s1, float* s2) { d.stat_sum = s1; d.stat_sq = s2; return *this; }
+  CD& obits(uint32_t* b) { d.out_bits = b; return *this; }          // record (output != 0) bits next to the output
+  CD& mbits(const uint32_t* b) { d.mask_bits = b; return *this; }   // read the mask from bits (same chunk offsets as .mask)
   CD& round() { d.round_tf32 = 1; return *this; }
   int run(cudaStream_t s) { return nef_gconv_fwd(&d, (nef_stream_t)s); }
 };
@@ -495,11 +505,14 @@ struct BlockIO {
   const ConvW* c1; const ConvW* c2; const ConvW* cr;  // cr == nullptr: identity residual
   const float* res_bias;
   int groups;
+  uint32_t* hbits = nullptr;   // one-bit masks of h and y (big layers only)
+  uint32_t* ybits = nullptr;
 };
 
 static int block_fwd(const BlockIO& io, float drop_p, uint64_t seed, const float* bscale, cudaStream_t s) {
   CD a(io.groups, 128, io.x);
   a.term(io.x, io.x_off, io.x_gs, io.c1->cin_g, io.c1->taps, io.c1->pk_f).out(io.h, 0, 32).relu().round();
+  if (io.hbits) a.obits(io.hbits);
   if (drop_p > 0.f) a.drop(drop_p, seed);
   RUN(a.run(s));
   CD b(io.groups, 128, io.x);
@@ -507,6 +520,7 @@ static int block_fwd(const BlockIO& io, float drop_p, uint64_t seed, const float
   if (io.cr) b.term(io.x, io.x_off, io.x_gs, io.cr->cin_g, 1, io.cr->pk_f).bias(io.res_bias);
   else b.res(io.x, io.x_off, io.x_gs);
   if (bscale) b.bscale(bscale);
+  if (io.ybits) b.obits(io.ybits);
   RUN(b.run(s));
   return 0;
 }
@@ -622,14 +636,17 @@ extern "C" int nef_forward(NefPlan* p, const NefForwardArgs* a, nef_stream_t sv)
   for (int i = 0; i < 3; ++i) {
     BlockIO io{i == 0 ? p->s0 : p->ey[i - 1], 0, 32, p->eh[i], p->ey[i], &p->enc[2 * i], &p->enc[2 * i + 1], nullptr,
                nullptr, G};
+    if (a->save_for_backward) { io.hbits = p->b_eh[i]; io.ybits = p->b_ey[i]; }
     RUN(block_fwd(io, dp, seed + i, i == 2 ? p->s_in : nullptr, s));
   }
   {
     BlockIO io{p->ey[2], 0, 32, p->hw, p->w, &p->wc[0], &p->wc[1], nullptr, nullptr, G};
+    if (a->save_for_backward) { io.hbits = p->b_hw; io.ybits = p->b_w; }
     RUN(block_fwd(io, dp, seed + 3, nullptr, s));
   }
   {
     BlockIO io{p->w, 0, 32, p->h1, p->z1, &p->z1c[0], &p->z1c[1], &p->z1c[2], P[P_Z1 + 3], G};
+    if (a->save_for_backward) io.hbits = p->b_h1;
     RUN(block_fwd(io, dp, seed + 4, nullptr, s));
   }
   RUN(window_extract(p->w, p->xw, G, p->win, s));
@@ -696,6 +713,7 @@ static int block_bwd(const BlockBwd& b, float drop_p, CD& fin, cudaStream_t s) {
   if (io.cr) RUN(wgrad_std(b.gy, 0, 32, io.x, io.x_off, io.x_gs, *io.cr, b.dwr, b.dbr, s));
   CD a(io.groups, 128, io.x);
   a.term(b.gy, 0, 32, 128, io.c2->taps, io.c2->pk_d).out(b.gh, 0, 32).mask(io.h, 0, 32, 1, 1.f / (1.f - drop_p)).round();
+  if (io.hbits) a.mbits(io.hbits);
   RUN(a.run(s));
   RUN(wgrad_std(b.gh, 0, 32, io.x, io.x_off, io.x_gs, *io.c1, b.dw1, nullptr, s));
   // gx = conv1^T(gh) + (identity: gy | 1x1: res^T(gy))
@@ -793,8 +811,9 @@ extern "C" int nef_backward(NefPlan* p, const NefBackwardArgs* a, nef_stream_t s
   {
     BlockBwd bb{{p->w, 0, 32, p->h1, p->z1, &p->z1c[0], &p->z1c[1], &p->z1c[2], nullptr, G}, p->GA[0], p->GA[1],
                 Gd[P_Z1 + 0], Gd[P_Z1 + 1], Gd[P_Z1 + 2], Gd[P_Z1 + 3]};
+    bb.io.hbits = p->b_h1;
     CD fin(G, 64, p->w);
-    fin.out(p->GA[2], 0, 32).mask(p->w, 0, 32, 1, 1.f).round();
+    fin.out(p->GA[2], 0, 32).mask(p->w, 0, 32, 1, 1.f).mbits(p->b_w).round();
     RUN(block_bwd(bb, dp, fin, s));
   }
   // ---- z2 branch
@@ -846,8 +865,9 @@ extern "C" int nef_backward(NefPlan* p, const NefBackwardArgs* a, nef_stream_t s
   {
     BlockBwd bb{{p->ey[2], 0, 32, p->hw, p->w, &p->wc[0], &p->wc[1], nullptr, nullptr, G}, p->GA[2], p->GA[0],
                 Gd[P_WCONV + 0], Gd[P_WCONV + 1], nullptr, nullptr};
+    bb.io.hbits = p->b_hw;
     CD fin(G, 128, p->ey[2]);
-    fin.out(p->GA[1], 0, 32).bscale(p->s_in).mask(p->ey[2], 0, 32, 2, 1.f).round();
+    fin.out(p->GA[1], 0, 32).bscale(p->s_in).mask(p->ey[2], 0, 32, 2, 1.f).mbits(p->b_ey[2]).round();
     RUN(block_bwd(bb, dp, fin, s));
     RUN(bscale_grad(p->GA[1], p->ey[2], p->s_in, p->ds_in, s));
   }
@@ -860,9 +880,10 @@ extern "C" int nef_backward(NefPlan* p, const NefBackwardArgs* a, nef_stream_t s
       BlockBwd bb{{i == 0 ? p->s0 : p->ey[i - 1], 0, 32, p->eh[i], p->ey[i], &p->enc[2 * i], &p->enc[2 * i + 1], nullptr,
                    nullptr, G},
                   p->GA[gy_i], p->GA[0], Gd[P_ENC + 2 * i], Gd[P_ENC + 2 * i + 1], nullptr, nullptr};
+      bb.io.hbits = p->b_eh[i];
       CD fin(G, 128, p->s0);
       fin.out(p->GA[gx_i], 0, 32);
-      if (i > 0) fin.mask(p->ey[i - 1], 0, 32, 1, 1.f).round();
+      if (i > 0) fin.mask(p->ey[i - 1], 0, 32, 1, 1.f).mbits(p->b_ey[i - 1]).round();
       RUN(block_bwd(bb, dp, fin, s));
       gy_i = gx_i;
     }

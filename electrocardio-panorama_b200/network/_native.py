@@ -34,7 +34,7 @@ class NefConvDesc(C.Structure):
                 ("drop_seed", C.c_uint64), ("bscale", C.c_void_p), ("bscale_grad", C.c_void_p), ("mask", C.c_void_p),
                 ("mask_cstride", C.c_int64), ("mask_c4_off", C.c_int32), ("mask_c4_gstride", C.c_int32),
                 ("mask_scale", C.c_float), ("reserved2", C.c_int32), ("stat_sum", C.c_void_p),
-                ("stat_sq", C.c_void_p)]
+                ("stat_sq", C.c_void_p), ("out_bits", C.c_void_p), ("mask_bits", C.c_void_p)]
 
 
 class NefWgradDesc(C.Structure):

@@ -115,6 +115,14 @@ typedef struct NefConvDesc {
    * reduced in a fixed order (nef_plan's finalize kernel), so equal inputs give bit-equal statistics. */
   float* stat_sum;      /* sum of v */
   float* stat_sq;       /* sum of v * v */
+  /* One-bit activation masks (tensor-core implementation; the CUDA-core cross-check keeps using `mask`):
+   * word [(chunk / 8)][row], bit 4 i + j <-> channel 32 (chunk / 8) + 4 i + j; planes are y_cstride (mask_cstride) words
+   * apart and rows index like the float tensors.  out_bits: the epilogue also records (stored value != 0) of every
+   * output element; mask_bits: mask modes 1 / 2 read these bits (plane (mask_c4_off + g * mask_c4_gstride) / 8 + ...)
+   * instead of the float `mask` tensor -- 4 bytes instead of 128 per row and 32 channels.  Chunk offsets must be
+   * multiples of 8.                                                                                          */
+  uint32_t* out_bits;
+  const uint32_t* mask_bits;
 } NefConvDesc;
 
 /* Packs reference-layout weights into the layout NefConvTerm.w expects, rounding to TF32 (RN):
