@@ -219,20 +219,27 @@ __global__ void __launch_bounds__(256) pack_weights_batch_kernel(const __grid_co
   const long beg = (long)((int)blockIdx.x - q.first_block) * NEF_PACK_CHUNK;
   const long end = beg + NEF_PACK_CHUNK < total ? beg + NEF_PACK_CHUNK : total;
   const int nkb = q.K >> 5;
-  for (long i = beg + threadIdx.x; i < end; i += 256) {
-    long r = i;
-    const int j = r & 3; r >>= 2;
+  // one thread per float4 of the packed layout (4 consecutive input channels of one output channel): the index
+  // arithmetic is paid once per four elements
+  for (long i4 = (beg >> 2) + threadIdx.x; i4 < (end >> 2); i4 += 256) {
+    long r = i4;
     const int n = r % q.N; r /= q.N;
     const int c = r & 7; r >>= 3;
     const int kb = r % nkb; r /= nkb;
     const int t = r % q.taps; r /= q.taps;
     const int g = (int)r;
-    const int k = kb * 32 + c * 4 + j;
+    const int k = kb * 32 + c * 4;
     const int ts = (q.flags & 1) ? q.taps - 1 - t : t;
-    float wv = q.src[g * q.sg + n * q.sn + k * q.sk + ts * q.st];
-    if (q.nscale) wv *= q.nscale[g * q.N + n];
-    const float hi = tf32_rn(wv);
-    q.dst[i] = (q.flags & 2) ? tf32_rn(wv - hi) : hi;
+    const float* sp = q.src + g * q.sg + n * q.sn + k * q.sk + ts * q.st;
+    const float sc = q.nscale ? q.nscale[g * q.N + n] : 1.0f;
+    float o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float wv = sp[j * q.sk] * sc;
+      const float hi = tf32_rn(wv);
+      o[j] = (q.flags & 2) ? tf32_rn(wv - hi) : hi;
+    }
+    reinterpret_cast<float4*>(q.dst)[i4] = make_float4(o[0], o[1], o[2], o[3]);
   }
 }
 
