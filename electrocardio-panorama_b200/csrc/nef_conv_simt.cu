@@ -215,9 +215,33 @@ __global__ void __launch_bounds__(256) pack_weights_batch_kernel(const __grid_co
   int jb = 0;
   while (jb + 1 < tab.n && (int)blockIdx.x >= tab.job[jb + 1].first_block) ++jb;
   const NefPackJob& q = tab.job[jb];
-  const long total = (long)q.groups * q.taps * q.K * q.N;
+  const bool f16 = (q.flags & 4) != 0;  // fp16 operand packing: a 16-byte slot holds 8 consecutive input channels
+  const long total = (long)q.groups * q.taps * (f16 ? q.K >> 1 : q.K) * q.N;   // in 4-byte units of the destination
   const long beg = (long)((int)blockIdx.x - q.first_block) * NEF_PACK_CHUNK;
   const long end = beg + NEF_PACK_CHUNK < total ? beg + NEF_PACK_CHUNK : total;
+  if (f16) {
+    const int nkb16 = q.K >> 6;
+    for (long i4 = (beg >> 2) + threadIdx.x; i4 < (end >> 2); i4 += 256) {
+      long r = i4;
+      const int n = r % q.N; r /= q.N;
+      const int c = r & 7; r >>= 3;
+      const int kb = r % nkb16; r /= nkb16;
+      const int t = r % q.taps; r /= q.taps;
+      const int g = (int)r;
+      const int k = kb * 64 + c * 8;
+      const int ts = (q.flags & 1) ? q.taps - 1 - t : t;
+      const float* sp = q.src + g * q.sg + n * q.sn + k * q.sk + ts * q.st;
+      const float sc = q.nscale ? q.nscale[g * q.N + n] : 1.0f;
+      uint32_t o[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float lo = sp[(2 * j) * q.sk] * sc, hi = sp[(2 * j + 1) * q.sk] * sc;
+        asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(o[j]) : "f"(hi), "f"(lo));
+      }
+      reinterpret_cast<uint4*>(q.dst)[i4] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+    return;
+  }
   const int nkb = q.K >> 5;
   // one thread per float4 of the packed layout (4 consecutive input channels of one output channel): the index
   // arithmetic is paid once per four elements
@@ -327,8 +351,9 @@ int nef_pack_weights_batch(NefPackTable* tab, cudaStream_t s) {
   for (int i = 0; i < tab->n; ++i) {
     NefPackJob& q = tab->job[i];
     NEF_REQUIRE(q.K % 32 == 0 && q.N % 4 == 0, "nef_pack_weights_batch: K %% 32 and N %% 4 required (K=%d N=%d)", q.K, q.N);
+    NEF_REQUIRE(!(q.flags & 4) || q.K % 64 == 0, "nef_pack_weights_batch: fp16 packing needs K %% 64 (K=%d)", q.K);
     q.first_block = blocks;
-    const long total = (long)q.groups * q.taps * q.K * q.N;
+    const long total = (long)q.groups * q.taps * ((q.flags & 4) ? q.K >> 1 : q.K) * q.N;
     blocks += (int)((total + NEF_PACK_CHUNK - 1) / NEF_PACK_CHUNK);
   }
   pack_weights_batch_kernel<<<blocks, 256, 0, s>>>(*tab);

@@ -90,6 +90,16 @@ __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Same contraction with fp16 operands (K = 16 halves = the same 32 bytes per K step, so the shared-memory descriptors are
+// those of the TF32 form): twice the MMA rate, the same 11-bit significand.
+__device__ __forceinline__ void mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // Weight-stationary form: the B operand is latched in collector buffer b0 by ::fill and re-used by ::use / ::lastuse
 // without being read from shared memory again (B = one weight stage, shared by the MT row tiles of a CTA).
 //   mode 0 = fill, 1 = use, 2 = lastuse, 3 = fill and discard (no re-use)
@@ -175,6 +185,11 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, 
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// Instruction descriptor: fp32 accumulate, F16 x F16 (kind::f16, operand format 0), M x N, both operands K-major
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
 // phase timestamps of the first CTAs of the last conv launch (profiling aid, read by nef_tc_debug_dump)
 __device__ unsigned long long g_tc_dbg[1024][8];
 __device__ __forceinline__ void dbg_stamp(int slot) {
@@ -215,6 +230,7 @@ struct FwSmem {
 constexpr int EPI_BIAS = 1, EPI_RES = 2, EPI_RELU = 4, EPI_DROP = 8, EPI_MASK1 = 16, EPI_ROUND = 32, EPI_GENERIC = 64;
 constexpr int EPI_MASK2 = 128, EPI_BSCALE = 256, EPI_STATS = 512;  // mask mode 2, angular scale, BatchNorm partial statistics
 constexpr int EPI_OBITS = 1024, EPI_MBITS = 2048;                  // write / read one-bit activation masks
+constexpr int EPI_Y16 = 4096;                                      // also store an fp16 copy of the output (next conv's operand)
 
 // Sum over the 32 lanes of 32 per-lane values at once: after the 5 exchange levels lane j holds the warp total of a[j].
 // 31 shuffles instead of 32 x 5.
@@ -230,6 +246,13 @@ __device__ __forceinline__ float warp_sum32(float (&a)[32], int lane) {
     }
   }
   return a[0];
+}
+
+// two floats -> packed fp16 pair (lo in the low half = lower address), saturating to the largest finite value
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
 }
 
 __device__ __forceinline__ float4 rn4_tf32(float4 v) {
@@ -258,6 +281,7 @@ __device__ __forceinline__ void epilogue_tile(const NefConvDesc& d, int g, long 
   const bool f_round = GEN ? d.round_tf32 != 0 : (EPI & EPI_ROUND) != 0;
   const bool f_bscale = GEN ? d.bscale != nullptr : (EPI & EPI_BSCALE) != 0;
   const bool f_bsgrad = GEN && d.bscale_grad != nullptr;
+  const bool f_y16 = GEN ? d.y16 != nullptr : (EPI & EPI_Y16) != 0;
   const bool f_obits = GEN ? d.out_bits != nullptr : (EPI & EPI_OBITS) != 0;
   const bool f_mbits = GEN ? (d.mask_bits != nullptr && d.mask_mode != 0) : (EPI & EPI_MBITS) != 0;
   // mask operand: 0 none, 1 / 2 float tensor (> 0 / != 0), 3 one-bit masks
@@ -282,6 +306,7 @@ __device__ __forceinline__ void epilogue_tile(const NefConvDesc& d, int g, long 
     const float4* bs4 = reinterpret_cast<const float4*>(d.bscale) + (long)(er.valid ? er.b : 0) * (ctot >> 2) + g * (N >> 2);
     const uint32_t* mbp = d.mask_bits + (long)((d.mask_c4_off + g * d.mask_c4_gstride) >> 3) * d.mask_cstride + orow;
     uint32_t* obp = d.out_bits + (long)((d.y_c4_off + g * d.y_c4_gstride) >> 3) * d.y_cstride + orow;
+    uint4* y16p = reinterpret_cast<uint4*>(d.y16) + (long)((d.y_c4_off + g * d.y_c4_gstride) >> 1) * d.y_cstride + orow;
     for (int cg = chalf; cg < N / 32; cg += 2) {
       uint32_t v[32];
       tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * N + cg * 32), v);
@@ -302,6 +327,7 @@ __device__ __forceinline__ void epilogue_tile(const NefConvDesc& d, int g, long 
       }
       tmem_ld_wait();
       float st1[32], st2[32];
+      uint32_t h16[4];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int n4 = cg * 8 + i;
@@ -356,6 +382,11 @@ __device__ __forceinline__ void epilogue_tile(const NefConvDesc& d, int g, long 
         }
         if (f_round) x = rn4_tf32(x);
         if (er.valid) yp[(long)n4 * d.y_cstride] = x;
+        if (f_y16) {  // chunks n4 = 2m, 2m + 1 form the 8-channel fp16 chunk m
+          h16[(i & 1) * 2 + 0] = pack_f16x2(x.x, x.y);
+          h16[(i & 1) * 2 + 1] = pack_f16x2(x.z, x.w);
+          if ((i & 1) && er.valid) y16p[(long)(n4 >> 1) * d.y_cstride] = make_uint4(h16[0], h16[1], h16[2], h16[3]);
+        }
         if (f_obits)
           oword |= ((x.x != 0.f ? 1u : 0u) | (x.y != 0.f ? 2u : 0u) | (x.z != 0.f ? 4u : 0u) | (x.w != 0.f ? 8u : 0u)) << (4 * i);
         if (want_stats) {
@@ -469,7 +500,7 @@ __global__ void __launch_bounds__(FW_THREADS, MT == 2 ? 2 : 1) conv_tc_kernel(co
     }
   } else if (warp == 1) {
     // ===== MMA issuer: the warp runs the (warp-uniform) control flow converged, one elected lane issues =====
-    const uint32_t idesc = make_idesc(128, N, 0, 0);
+    const uint32_t idesc = make_idesc(128, N, 0, 0), idesc16 = make_idesc_f16(128, N);
     const uint32_t nb = 2u * (uint32_t)N;                    // descriptor units between two K = 8 steps of a weight stage
     int xs = 0, xph = 0, wst = 0, wph = 0;
     uint32_t accum = 0;
@@ -485,7 +516,7 @@ __global__ void __launch_bounds__(FW_THREADS, MT == 2 ? 2 : 1) conv_tc_kernel(co
           const uint32_t xa = desc_lo(xs0 + xs * S::XBYTES + tp * 16, S::XPITCH);
           const uint32_t wa = desc_lo(ws0 + wst * FW_WBYTES, (uint32_t)N * 16);
           if (elect_one()) {
-            if (use_ws && MT > 1) {
+            if (use_ws && MT > 1 && !t.x_f16) {
 #pragma unroll
               for (int k8 = 0; k8 < 4; ++k8) {
                 const uint64_t bd = desc_of(DESC_HI_SBO128, wa + k8 * nb);
@@ -496,6 +527,14 @@ __global__ void __launch_bounds__(FW_THREADS, MT == 2 ? 2 : 1) conv_tc_kernel(co
                   else if (mt == MT - 1) mma_tf32_ws<2>(tmem + mt * N, ad, bd, idesc, accum | (uint32_t)k8);
                   else mma_tf32_ws<1>(tmem + mt * N, ad, bd, idesc, accum | (uint32_t)k8);
                 }
+              }
+            } else if (t.x_f16) {
+#pragma unroll
+              for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+                for (int k8 = 0; k8 < 4; ++k8)
+                  mma_f16(tmem + mt * N, desc_of(DESC_HI_SBO128, xa + k8 * 2 * (S::XPITCH >> 4) + mt * 128),
+                          desc_of(DESC_HI_SBO128, wa + k8 * nb), idesc16, accum | (uint32_t)k8);
               }
             } else {
 #pragma unroll
@@ -628,7 +667,7 @@ __global__ void __launch_bounds__(FW_THREADS, 1) conv_tc_persist_kernel(const __
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
-    const uint32_t idesc = make_idesc(128, N, 0, 0);
+    const uint32_t idesc = make_idesc(128, N, 0, 0), idesc16 = make_idesc_f16(128, N);
     const uint32_t nb = 2u * (uint32_t)N;
     int xs = 0, xph = 0, wst = 0, wph = 0, as = 0, aph = 0;
     long long wt_a = 0, wt_x = 0, wt_w = 0, tq;
@@ -655,7 +694,15 @@ __global__ void __launch_bounds__(FW_THREADS, 1) conv_tc_persist_kernel(const __
             const uint32_t xa = desc_lo(xs0 + xs * S::XBYTES + tp * 16, S::XPITCH);
             const uint32_t wa = desc_lo(ws0 + wst * FW_WBYTES, (uint32_t)N * 16);
             if (elect_one()) {
-              if (use_ws) {  // the weight stage (B) is latched by the first row tile and re-used by the second
+              if (t.x_f16) {
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+                  for (int k8 = 0; k8 < 4; ++k8)
+                    mma_f16(acc0 + mt * N, desc_of(DESC_HI_SBO128, xa + k8 * 2 * (S::XPITCH >> 4) + mt * 128),
+                            desc_of(DESC_HI_SBO128, wa + k8 * nb), idesc16, accum | (uint32_t)k8);
+                }
+              } else if (use_ws) {  // the weight stage (B) is latched by the first row tile and re-used by the second
 #pragma unroll
                 for (int k8 = 0; k8 < 4; ++k8) {
                   const uint64_t bd = desc_of(DESC_HI_SBO128, wa + k8 * nb);
@@ -996,7 +1043,7 @@ static int g_tc_mt = 0;  // 0 = automatic; 4 forces four row tiles per CTA, one 
 
 // the specialised epilogues instantiated for the 4-row-tile kernel (everything else takes the generic one)
 #define NEF_TC_EPI_LIST(X) X(0) X(2) X(5) X(32) X(33) X(36) X(37) X(38) X(44) X(48) X(50) X(64) X(294) X(418) X(513) \
-  X(1062) X(1068) X(1318) X(2080) X(2082) X(2338)
+  X(1062) X(1068) X(1318) X(2080) X(2082) X(2338) X(5158) X(5164)
 
 template <int MT, int EPI>
 static int tc_optin() {
@@ -1033,6 +1080,7 @@ static int epi_code(const NefConvDesc* d) {
   if (d->mask_mode == 2 && !mbits) e |= tc::EPI_MASK2;
   if (mbits) e |= tc::EPI_MBITS;
   if (d->out_bits) e |= tc::EPI_OBITS;
+  if (d->y16) e |= tc::EPI_Y16;
   if (d->bias) e |= tc::EPI_BIAS;
   if (d->res) e |= tc::EPI_RES;
   if (d->relu) e |= tc::EPI_RELU;

@@ -21,8 +21,14 @@ constexpr int STEM_TJ = 256;  // pooled outputs per block
 // Per output element the kernel also records WHICH of the three pooled conv positions won (first maximum in window
 // order 2j-1, 2j, 2j+1, as MaxPool1d does) or 3 if the ReLU clipped it: one byte per channel, a uint32 per float4,
 // same row indexing as the activation.  stem_bwd routes the gradient with it instead of recomputing the convolution.
+__device__ __forceinline__ uint32_t f16x2_sat(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+
 __global__ void __launch_bounds__(256) stem_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, T4 y,
-                                                       uint32_t* __restrict__ amax, int G, int L) {
+                                                       uint32_t* __restrict__ amax, uint4* __restrict__ y16, int G, int L) {
   __shared__ float xs[4 * STEM_TJ + 24];
   __shared__ float4 ws[15][32];
   const int tid = threadIdx.x;
@@ -50,6 +56,7 @@ __global__ void __launch_bounds__(256) stem_fwd_kernel(const float* __restrict__
   for (int k = 0; k < 23; ++k) xr[k] = xs[4 * jl + k];
   const bool va = (2 * j - 1) >= 0;            // window of j: positions 2j-1 (if valid), 2j, 2j+1
   const bool vb = (2 * j + 3) < L2, has_b = j + 1 < L4;
+  uint32_t h0[2], h1[2];   // fp16 halves of the even chunk of a pair, for the two pooled outputs
   for (int cc = 0; cc < 16; ++cc) {
     const int c4 = chalf * 16 + cc;
     float4 a[5];
@@ -87,8 +94,20 @@ __global__ void __launch_bounds__(256) stem_fwd_kernel(const float* __restrict__
       }
     }
     const long off = (long)(g * 32 + c4) * y.cs + y.row(b, j);
-    y.p[off] = tf32_rn4(m0);
-    if (has_b) y.p[off + 1] = tf32_rn4(m1);
+    m0 = tf32_rn4(m0);
+    m1 = tf32_rn4(m1);
+    y.p[off] = m0;
+    if (has_b) y.p[off + 1] = m1;
+    if (y16) {  // fp16 copy for the first encoder convolution: 8 channels (chunks c4, c4 + 1) per 16-byte row
+      if ((cc & 1) == 0) {
+        h0[0] = f16x2_sat(m0.x, m0.y); h0[1] = f16x2_sat(m0.z, m0.w);
+        h1[0] = f16x2_sat(m1.x, m1.y); h1[1] = f16x2_sat(m1.z, m1.w);
+      } else {
+        const long o16 = (long)((g * 32 + c4) >> 1) * y.cs + y.row(b, j);
+        y16[o16] = make_uint4(h0[0], h0[1], f16x2_sat(m0.x, m0.y), f16x2_sat(m0.z, m0.w));
+        if (has_b) y16[o16 + 1] = make_uint4(h1[0], h1[1], f16x2_sat(m1.x, m1.y), f16x2_sat(m1.z, m1.w));
+      }
+    }
     if (amax) {
       amax[off] = code0;
       if (has_b) amax[off + 1] = code1;
@@ -189,10 +208,10 @@ __global__ void __launch_bounds__(256, 2) stem_bwd_kernel(const float* __restric
   }
 }
 
-int stem_fwd(const float* x, const float* w, T4 y, uint32_t* amax, int G, cudaStream_t s) {
+int stem_fwd(const float* x, const float* w, T4 y, uint32_t* amax, void* y16, int G, cudaStream_t s) {
   const int L = y.L * 4;
   dim3 grid((y.L + STEM_TJ - 1) / STEM_TJ, G, y.B);
-  stem_fwd_kernel<<<grid, 256, 0, s>>>(x, w, y, amax, G, L);
+  stem_fwd_kernel<<<grid, 256, 0, s>>>(x, w, y, amax, reinterpret_cast<uint4*>(y16), G, L);
   NEF_CHECK_LAUNCH("stem_fwd_kernel");
   return 0;
 }

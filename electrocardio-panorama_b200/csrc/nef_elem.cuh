@@ -26,7 +26,7 @@ struct BnLayer {          // one BatchNorm1d of the decoder for one decoder call
   double* s2;             // [C] backward: sum g * xhat
 };
 
-int stem_fwd(const float* x, const float* w, T4 y, uint32_t* amax, int G, cudaStream_t s);
+int stem_fwd(const float* x, const float* w, T4 y, uint32_t* amax, void* y16, int G, cudaStream_t s);  // y16: optional fp16 copy
 int stem_bwd(const float* x, const uint32_t* amax, T4 dy, float* dw, int G, cudaStream_t s);
 int angular_fwd(const float* theta, const float* w, const float* b, float* out, int n, int D, cudaStream_t s);
 int angular_bwd(const float* theta, const float* dout, float* dw, float* db, int n, int D, cudaStream_t s);

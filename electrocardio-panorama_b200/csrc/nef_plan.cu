@@ -55,6 +55,10 @@ extern "C" int nef_get_conv_impl(void) { return g_conv_impl; }
 // 6.4e-4 / 5.9e-4 relative for 1 / 2 / 3 terms against the 1e-3 bar; 2 terms save ~0.2 ms per decoder call at batch 256 but
 // leave less margin (and move the noisiest weight gradient, W_encoder.layer1.2.conv2, from cosine 0.86 to 0.75 at B = 1).
 static int g_dec1_terms = 3;
+// Encoder forward convolutions on fp16 operand copies (kind::f16: the significand of TF32, twice the MMA rate, half the
+// operand bytes).  Only the forward reads the copies; the backward pass keeps using the fp32 (TF32-rounded) tensors.
+static int g_fwd_f16 = 1;
+extern "C" int nef_set_fwd_f16(int on) { g_fwd_f16 = on; return 0; }
 extern "C" int nef_set_dec1_terms(int n) {
   NEF_REQUIRE(n >= 1 && n <= 3, "nef_set_dec1_terms: 1, 2 or 3");
   g_dec1_terms = n;
@@ -175,6 +179,7 @@ struct ConvW {            // one convolution's weights: reference tensor + packe
   int groups, cout_g, cin_g, taps;
   float* pk_f;            // forward packing  [g][t][cin_g/32][8][cout_g][4]
   float* pk_d;            // data-gradient packing (flipped taps, transposed); N = min(cin_g, 128)
+  void* pk_h;             // forward packing in fp16 (encoder convolutions only), or nullptr
 };
 
 struct DecBufs {          // one decoder call
@@ -200,6 +205,8 @@ struct NefPlan {
   // one-bit (value != 0) masks of the big post-ReLU activations, written by the forward epilogues and read by the masked
   // data-gradient epilogues instead of the fp32 tensors (NefConvDesc.out_bits / mask_bits)
   uint32_t *b_eh[3], *b_ey[3], *b_hw, *b_w, *b_h1;
+  void *s0_h, *eh_h[3], *ey_h[2];   // fp16 operand copies (8 channels per 16-byte row) of s0, eh[i], ey[0..1]
+  bool fwd_f16;                     // this forward runs the encoder convolutions on them
   // gradients
   T4 GA[3];
   T4 gz2o, gh22, dt21, dte, dto, gy20, gh20, dra, gz2c, ghz, gxw;
@@ -247,6 +254,7 @@ static void carve_convw(Carver& c, ConvW& w, int pidx, int groups, int cout_g, i
   const size_t n = (size_t)groups * cout_g * cin_g * taps;
   w.pk_f = c.f32(n);
   w.pk_d = c.f32(n);
+  w.pk_h = nullptr;
 }
 
 static void carve(NefPlan* p, bool dry) {
@@ -257,6 +265,11 @@ static void carve(NefPlan* p, bool dry) {
   p->s0_amax = reinterpret_cast<uint32_t*>(c.take(((size_t)(C1 / 4) * p->s0.cs + NEF_GUARD_ROWS) * sizeof(uint32_t)));
   for (int i = 0; i < 3; ++i) { p->eh[i] = c.t4(C1, L4); p->ey[i] = c.t4(C1, L4); }
   p->hw = c.t4(C1, L4); p->w = c.t4(C1, L4); p->h1 = c.t4(C1, L4); p->z1 = c.t4(C1, L4);
+  {
+    const size_t bytes = ((size_t)(C1 / 8) * p->s0.cs + NEF_GUARD_ROWS) * 16;
+    void** hp[6] = {&p->s0_h, &p->eh_h[0], &p->eh_h[1], &p->eh_h[2], &p->ey_h[0], &p->ey_h[1]};
+    for (auto q : hp) *q = c.take(bytes);
+  }
   {
     const size_t words = (size_t)(C1 / 32) * p->s0.cs + NEF_GUARD_ROWS;
     uint32_t** bp[9] = {&p->b_eh[0], &p->b_eh[1], &p->b_eh[2], &p->b_ey[0], &p->b_ey[1], &p->b_ey[2], &p->b_hw, &p->b_w, &p->b_h1};
@@ -308,7 +321,10 @@ static void carve(NefPlan* p, bool dry) {
   p->dg4 = c.t4(64, L); p->dg3 = c.t4(64, L); p->du1 = c.t4(128, L); p->dg2 = c.t4(128, L2); p->dg1 = c.t4(128, L2);
   for (int k = 0; k < 3; ++k) p->du0[k] = c.t4(256, L2);
   // weights
-  for (int i = 0; i < 6; ++i) carve_convw(c, p->enc[i], P_ENC + i, G, 128, 128, 7);
+  for (int i = 0; i < 6; ++i) {
+    carve_convw(c, p->enc[i], P_ENC + i, G, 128, 128, 7);
+    p->enc[i].pk_h = c.take((size_t)G * 128 * 128 * 7 * 2);
+  }
   carve_convw(c, p->wc[0], P_WCONV + 0, G, 128, 128, 3);
   carve_convw(c, p->wc[1], P_WCONV + 1, G, 128, 128, 3);
   carve_convw(c, p->z1c[0], P_Z1 + 0, G, 128, 64, 3);
@@ -402,6 +418,14 @@ struct CD {
     return *this;
   }
   CD& stats(float* s1, float* s2) { d.stat_sum = s1; d.stat_sq = s2; return *this; }
+  // fp16 operand term: x16 = fp16 copy (8 channels per row) of a tensor with the row space of `space`, cin real channels
+  CD& term16(const void* x16, long cs, int off8, int gs8, int cin, int taps, const void* w16) {
+    NefConvTerm& t = d.term[d.n_terms++];
+    t.x = reinterpret_cast<const float*>(x16); t.x_cstride = cs; t.x_c4_off = off8; t.x_c4_gstride = gs8;
+    t.cin_g = cin / 2; t.taps = taps; t.tap_off = -(taps / 2); t.w = reinterpret_cast<const float*>(w16); t.x_f16 = 1;
+    return *this;
+  }
+  CD& y16(void* h) { d.y16 = h; return *this; }                     // also store the fp16 copy of the output
   CD& obits(uint32_t* b) { d.out_bits = b; return *this; }          // record (output != 0) bits next to the output
   CD& mbits(const uint32_t* b) { d.mask_bits = b; return *this; }   // read the mask from bits (same chunk offsets as .mask)
   CD& round() { d.round_tf32 = 1; return *this; }
@@ -507,16 +531,24 @@ struct BlockIO {
   int groups;
   uint32_t* hbits = nullptr;   // one-bit masks of h and y (big layers only)
   uint32_t* ybits = nullptr;
+  const void* x16 = nullptr;   // fp16 operand copies: when x16 is set the two convolutions run in kind::f16 and also
+  void* h16 = nullptr;         //   write h16 (required) and y16 (optional, the next block's x16)
+  void* y16 = nullptr;
 };
 
 static int block_fwd(const BlockIO& io, float drop_p, uint64_t seed, const float* bscale, cudaStream_t s) {
   CD a(io.groups, 128, io.x);
-  a.term(io.x, io.x_off, io.x_gs, io.c1->cin_g, io.c1->taps, io.c1->pk_f).out(io.h, 0, 32).relu().round();
+  if (io.x16) a.term16(io.x16, io.x.cs, io.x_off / 2, io.x_gs / 2, io.c1->cin_g, io.c1->taps, io.c1->pk_h).y16(io.h16);
+  else a.term(io.x, io.x_off, io.x_gs, io.c1->cin_g, io.c1->taps, io.c1->pk_f);
+  a.out(io.h, 0, 32).relu().round();
   if (io.hbits) a.obits(io.hbits);
   if (drop_p > 0.f) a.drop(drop_p, seed);
   RUN(a.run(s));
   CD b(io.groups, 128, io.x);
-  b.term(io.h, 0, 32, 128, io.c2->taps, io.c2->pk_f).out(io.y, 0, 32).relu().round();
+  if (io.x16) b.term16(io.h16, io.h.cs, 0, 16, 128, io.c2->taps, io.c2->pk_h);
+  else b.term(io.h, 0, 32, 128, io.c2->taps, io.c2->pk_f);
+  b.out(io.y, 0, 32).relu().round();
+  if (io.y16) b.y16(io.y16);
   if (io.cr) b.term(io.x, io.x_off, io.x_gs, io.cr->cin_g, 1, io.cr->pk_f).bias(io.res_bias);
   else b.res(io.x, io.x_off, io.x_gs);
   if (bscale) b.bscale(bscale);
@@ -623,13 +655,20 @@ extern "C" int nef_forward(NefPlan* p, const NefForwardArgs* a, nef_stream_t sv)
 
   NefPackTable packs;
   packs.n = 0;
-  RUN(for_all_convw(p, [&](const ConvW& w) { return (&w >= p->decw && &w < p->decw + 4) ? 0 : pack_fwd(packs, w, P, s); }));
+  p->fwd_f16 = g_fwd_f16 && g_conv_impl == 1;
+  RUN(for_all_convw(p, [&](const ConvW& w) {
+    if (&w >= p->decw && &w < p->decw + 4) return 0;
+    if (p->fwd_f16 && w.pk_h)
+      return queue_pack(packs, P[w.pidx], reinterpret_cast<float*>(w.pk_h), w.groups, w.cout_g, w.cin_g, w.taps,
+                        (int64_t)w.cout_g * w.cin_g * w.taps, (int64_t)w.cin_g * w.taps, w.taps, 1, 4, s);
+    return pack_fwd(packs, w, P, s);
+  }));
   RUN(queue_decoder_packs(p, packs, P, !a->bn_training && !a->save_for_backward, s));
   for (int t = 0; t < 2; ++t)  // ConvTranspose1d weight (Cin_total, Cout/groups, 2): one 1x1 conv per tap
     RUN(queue_pack(packs, P[P_CT_W] + t, p->ct_f[t], 7 * G, 64, 128, 1, 128LL * 64 * 2, 2, 64 * 2, 0, 0, s));
   RUN(nef_pack_weights_batch(&packs, s));
 
-  RUN(stem_fwd(a->x, P[P_STEM], p->s0, a->save_for_backward ? p->s0_amax : nullptr, G, s));
+  RUN(stem_fwd(a->x, P[P_STEM], p->s0, a->save_for_backward ? p->s0_amax : nullptr, p->fwd_f16 ? p->s0_h : nullptr, G, s));
   RUN(angular_fwd(a->input_thetas, P[P_MLP1_W], P[P_MLP1_B], p->s_in, B * G, 128, s));
   const float dp = a->drop_p;
   const uint64_t seed = a->drop_seed * 16;
@@ -637,6 +676,11 @@ extern "C" int nef_forward(NefPlan* p, const NefForwardArgs* a, nef_stream_t sv)
     BlockIO io{i == 0 ? p->s0 : p->ey[i - 1], 0, 32, p->eh[i], p->ey[i], &p->enc[2 * i], &p->enc[2 * i + 1], nullptr,
                nullptr, G};
     if (a->save_for_backward) { io.hbits = p->b_eh[i]; io.ybits = p->b_ey[i]; }
+    if (p->fwd_f16) {
+      io.x16 = i == 0 ? p->s0_h : p->ey_h[i - 1];
+      io.h16 = p->eh_h[i];
+      io.y16 = i < 2 ? p->ey_h[i] : nullptr;
+    }
     RUN(block_fwd(io, dp, seed + i, i == 2 ? p->s_in : nullptr, s));
   }
   {
@@ -903,7 +947,7 @@ static T4 view_t4(const float* ptr, int C, int B, int L) {
 }
 extern "C" int nef_stem_fwd(const float* x, const float* w, float* y, uint32_t* argmax, int B, int G, int L,
                             nef_stream_t s) {
-  return stem_fwd(x, w, view_t4(y, 128 * G, B, L / 4), argmax, G, (cudaStream_t)s);
+  return stem_fwd(x, w, view_t4(y, 128 * G, B, L / 4), argmax, nullptr, G, (cudaStream_t)s);
 }
 extern "C" int nef_stem_bwd(const float* x, const uint32_t* argmax, const float* dy, float* dw, int B, int G, int L,
                             nef_stream_t s) {

@@ -20,7 +20,7 @@ GUARD_ROWS = 528
 
 class NefConvTerm(C.Structure):
     _fields_ = [("x", C.c_void_p), ("x_cstride", C.c_int64), ("x_c4_off", C.c_int32), ("x_c4_gstride", C.c_int32),
-                ("cin_g", C.c_int32), ("taps", C.c_int32), ("tap_off", C.c_int32), ("reserved", C.c_int32),
+                ("cin_g", C.c_int32), ("taps", C.c_int32), ("tap_off", C.c_int32), ("x_f16", C.c_int32),
                 ("w", C.c_void_p)]
 
 
@@ -34,7 +34,7 @@ class NefConvDesc(C.Structure):
                 ("drop_seed", C.c_uint64), ("bscale", C.c_void_p), ("bscale_grad", C.c_void_p), ("mask", C.c_void_p),
                 ("mask_cstride", C.c_int64), ("mask_c4_off", C.c_int32), ("mask_c4_gstride", C.c_int32),
                 ("mask_scale", C.c_float), ("reserved2", C.c_int32), ("stat_sum", C.c_void_p),
-                ("stat_sq", C.c_void_p), ("out_bits", C.c_void_p), ("mask_bits", C.c_void_p)]
+                ("stat_sq", C.c_void_p), ("out_bits", C.c_void_p), ("mask_bits", C.c_void_p), ("y16", C.c_void_p)]
 
 
 class NefWgradDesc(C.Structure):
@@ -96,6 +96,7 @@ SIGNATURES = {
     "nef_sgd_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_float, C.c_float,
                                C.c_void_p]),
     "nef_set_dec1_terms": (C.c_int, [C.c_int]),
+    "nef_set_fwd_f16": (C.c_int, [C.c_int]),
     "nef_psnr": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                            C.c_void_p, C.c_void_p]),
     "nef_prepare_scratch_bytes": (C.c_size_t, [C.c_int]),
@@ -142,6 +143,8 @@ def init(device_index: int):
     if device_index not in _inited_devices:
         check(lib.nef_init(int(device_index)), "nef_init")
         _inited_devices.add(device_index)
+        if os.environ.get("NEF_FWD_F16"):  # measurement hook, see nef_set_fwd_f16
+            check(lib.nef_set_fwd_f16(int(os.environ["NEF_FWD_F16"])), "nef_set_fwd_f16")
         terms = os.environ.get("NEF_DEC1_TERMS")  # measurement hook, see nef_set_dec1_terms
         if terms:
             check(lib.nef_set_dec1_terms(int(terms)), "nef_set_dec1_terms")

@@ -42,6 +42,9 @@ int nef_get_conv_impl(void);
 /* Split-precision terms of the decoder's first convolution (model_nefnet.py:101-103, DoubleConv conv 256 -> 128):
  * 3 = x_hi w_hi + x_lo w_hi + x_hi w_lo (default), 2 = without x_hi w_lo, 1 = plain TF32.  Measurement hook. */
 int nef_set_dec1_terms(int n);
+/* 1 (default) = the encoder's forward convolutions read fp16 operand copies (NefConvTerm.x_f16); 0 = TF32 operands
+ * everywhere.  Measurement hook. */
+int nef_set_fwd_f16(int on);
 /* Test hook: 1 = round nothing to TF32 (with conv impl 0 the whole path is then plain fp32 and can be
  * compared tightly with the fp32 oracle); 0 = production behaviour.  Synchronous, call between steps. */
 int nef_set_exact_fp32(int on);
@@ -76,7 +79,10 @@ typedef struct NefConvTerm {
   int32_t cin_g;        /* input channels per group, multiple of 32 */
   int32_t taps;         /* 1, 3 or 7 */
   int32_t tap_off;      /* row offset of tap 0 (= -(taps/2) for a "same" convolution) */
-  int32_t reserved;
+  int32_t x_f16;        /* 1: x and w hold fp16 pairs -- 8 channels per 16-byte row (chunk = 8 channels), cin_g counts PAIRS
+                         * of channels (a 128-channel group has cin_g = 64, 16 chunks), weights packed with flag bit 2.
+                         * Same 11-bit significand as TF32 at twice the MMA rate and half the operand bytes; tensor-core
+                         * implementation only.                                                                   */
   const float* w;       /* packed weights [group][tap][cin_g/32][8][N][4], see nef_pack_weights */
 } NefConvTerm;
 
@@ -123,6 +129,9 @@ typedef struct NefConvDesc {
    * multiples of 8.                                                                                          */
   uint32_t* out_bits;
   const uint32_t* mask_bits;
+  /* fp16 copy of the output, or NULL: 8 channels per 16-byte row, chunk (y chunk / 2), planes y_cstride rows apart,
+   * values saturate to the largest finite fp16.  It is the x_f16 operand of the next convolution.          */
+  void* y16;
 } NefConvDesc;
 
 /* Packs reference-layout weights into the layout NefConvTerm.w expects, rounding to TF32 (RN):
