@@ -307,7 +307,7 @@ def main():
         tf32_peak = float(peaks.get("bf16_tflops", 1590.0)) / 2.0
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "tf32", "data": "synthetic",
+                "vs_baseline": None, "dtype": "tf32 (fp16 operands in the encoder forward; fp32 accumulate everywhere)", "data": "synthetic",
                 "config": {"workload": workload_name(world, B, L),
                            "batch_per_gpu": B, "global_batch": B * world, "leads": G, "length": L,
                            "conv_impl": "tcgen05-tf32" if lib.nef_get_conv_impl() == 1 else "cuda-core-fp32",
