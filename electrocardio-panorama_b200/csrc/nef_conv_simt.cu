@@ -1,6 +1,7 @@
 // CUDA-core fp32 implementation of the grouped implicit-GEMM convolution and its weight gradient.
 // This is the bring-up / cross-check implementation of the contraction (nef_set_conv_impl(0));
 // the production path is the tcgen05 TF32 kernel in nef_conv_tc.cu.  Same descriptor, same epilogue.
+#include <cuda_fp16.h>
 #include "nef_conv.cuh"
 
 namespace nef {
@@ -235,8 +236,14 @@ __global__ void __launch_bounds__(256) pack_weights_batch_kernel(const __grid_co
       uint32_t o[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const float lo = sp[(2 * j) * q.sk] * sc, hi = sp[(2 * j + 1) * q.sk] * sc;
+        float lo = sp[(2 * j) * q.sk] * sc, hi = sp[(2 * j + 1) * q.sk] * sc;
         asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(o[j]) : "f"(hi), "f"(lo));
+        if (q.flags & 2) {  // residual w - fp16(w), itself in fp16
+          const __half2 h2 = *reinterpret_cast<const __half2*>(&o[j]);
+          lo -= __low2float(h2);
+          hi -= __high2float(h2);
+          asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(o[j]) : "f"(hi), "f"(lo));
+        }
       }
       reinterpret_cast<uint4*>(q.dst)[i4] = make_uint4(o[0], o[1], o[2], o[3]);
     }

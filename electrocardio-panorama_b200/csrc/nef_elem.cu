@@ -609,8 +609,14 @@ __global__ void __launch_bounds__(256) latent_fwd_kernel(const LatentArgs a) {
         v = v * qv;
         const float4 hi = tf32_rn4(v);
         *a.u0[k3].at(latc, b, 2 * t0 + i) = hi;
-        *a.u0lo[k3].at(latc, b, 2 * t0 + i) =
-            tf32_rn4(make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w));
+        const float4 lo = make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w);
+        if (a.u0h[k3]) {  // this block's 4 channels are one half of an 8-channel fp16 row
+          const long o8 = ((long)(latc >> 1) * a.u0[k3].cs + a.u0[k3].row(b, 2 * t0 + i)) * 2 + (latc & 1);
+          reinterpret_cast<uint2*>(a.u0h[k3])[o8] = make_uint2(f16x2_sat(hi.x, hi.y), f16x2_sat(hi.z, hi.w));
+          reinterpret_cast<uint2*>(a.u0loh[k3])[o8] = make_uint2(f16x2_sat(lo.x, lo.y), f16x2_sat(lo.z, lo.w));
+        } else {
+          *a.u0lo[k3].at(latc, b, 2 * t0 + i) = tf32_rn4(lo);
+        }
       }
     }
     __syncthreads();

@@ -52,6 +52,8 @@ struct LatentArgs {
   T4 lat[3];              // unscaled latents (256, L4): all, patient-shuffled, lead-shuffled
   T4 u0[3];               // upsample2(q * lat) (256, L/2), TF32-rounded
   T4 u0lo[3];             // TF32 residual of the same (split-precision input of the decoder's first conv)
+  void* u0h[3];           // optional fp16 operand copies (8 channels per 16-byte row) of u0 and of its residual; when set,
+  void* u0loh[3];         //   the fp32 residual u0lo is not written (only the fp16 forward convolution reads a residual)
   int n_lat;              // 3 (train) or 1 (extra views: only lat[0] / u0[0])
   int write_lat;          // 0: lat already built, only (re)build u0 from it with another q
   int store_mask;         // with write_lat: bit (2 k + half) = store half (0: z1 channels, 1: z2 channels) of lat[k].

@@ -206,6 +206,8 @@ struct NefPlan {
   // data-gradient epilogues instead of the fp32 tensors (NefConvDesc.out_bits / mask_bits)
   uint32_t *b_eh[3], *b_ey[3], *b_hw, *b_w, *b_h1;
   void *s0_h, *eh_h[3], *ey_h[2];   // fp16 operand copies (8 channels per 16-byte row) of s0, eh[i], ey[0..1]
+  void *u0_h[3], *u0lo_h[3];        //   ... of the decoder inputs u0 and of their rounding residuals
+  void* dec1_lo_h;                  // fp16 residual of the decoder first conv weights (decw[0].pk_h holds the fp16 weights)
   bool fwd_f16;                     // this forward runs the encoder convolutions on them
   // gradients
   T4 GA[3];
@@ -280,6 +282,11 @@ static void carve(NefPlan* p, bool dry) {
   p->t21 = c.t4(448 * G, 32); p->h22 = c.t4(896 * G, 32); p->z2o = c.t4(896 * G, 32);
   for (int k = 0; k < 3; ++k) { p->lat[k] = c.t4(256, L4); p->u0[k] = c.t4(256, L2); p->u0lo[k] = c.t4(256, L2); }
   for (int k = 0; k < 3; ++k) {
+    const size_t bytes = ((size_t)(256 / 8) * p->u0[k].cs + NEF_GUARD_ROWS) * 16;
+    p->u0_h[k] = c.take(bytes);
+    p->u0lo_h[k] = c.take(bytes);
+  }
+  for (int k = 0; k < 3; ++k) {
     DecBufs& d = p->dec[k];
     d.c1 = c.t4(128, L2); d.a1 = c.t4(128, L2); d.c2 = c.t4(128, L2); d.u1 = c.t4(128, L);
     d.c3 = c.t4(64, L); d.a3 = c.t4(64, L); d.c4 = c.t4(64, L);
@@ -339,6 +346,8 @@ static void carve(NefPlan* p, bool dry) {
   carve_convw(c, p->z2b[1], P_Z2B + 1, 7 * G, 128, 128, 3);
   carve_convw(c, p->z2b[2], P_Z2B + 2, 7 * G, 128, 64, 1);
   carve_convw(c, p->decw[0], P_DEC1 + 0, 1, 128, 256, 3);
+  p->decw[0].pk_h = c.take((size_t)128 * 256 * 3 * 2);
+  p->dec1_lo_h = c.take((size_t)128 * 256 * 3 * 2);
   p->dec1_lo = c.f32((size_t)128 * 256 * 3);
   carve_convw(c, p->decw[1], P_DEC1 + 7, 1, 128, 128, 3);
   carve_convw(c, p->decw[2], P_DEC3 + 0, 1, 64, 128, 3);
@@ -501,6 +510,12 @@ static int queue_decoder_packs(NefPlan* p, NefPackTable& t, const float* const* 
                        p->fold_bias[i], p->decw[i].cout_g, s));
       ns = p->fold_scale[i];
     }
+    if (i == 0 && p->fwd_f16) {  // first conv in kind::f16: weights and their residuals in fp16
+      const ConvW& w = p->decw[0];
+      RUN(queue_pack(t, P[w.pidx], reinterpret_cast<float*>(w.pk_h), 1, 128, 256, 3, 0, 256 * 3, 3, 1, 4, s, ns));
+      RUN(queue_pack(t, P[w.pidx], reinterpret_cast<float*>(p->dec1_lo_h), 1, 128, 256, 3, 0, 256 * 3, 3, 1, 4 | 2, s, ns));
+      continue;
+    }
     RUN(pack_fwd(t, p->decw[i], P, s, ns));
     if (i == 0) RUN(pack_dec1_lo(t, p, P, s, ns));
   }
@@ -557,9 +572,11 @@ static int block_fwd(const BlockIO& io, float drop_p, uint64_t seed, const float
   return 0;
 }
 
-static int decoder_fwd(NefPlan* p, const float* const* P, int slot, const T4& u0, const T4& u0lo, int training, float* out_user,
-                       int out_bstride, cudaStream_t s) {
+static int decoder_fwd(NefPlan* p, const float* const* P, int slot, int lslot, const T4& u0, const T4& u0lo, int training,
+                       float* out_user, int out_bstride, cudaStream_t s) {
   DecBufs& d = p->dec[slot];
+  const void* u0h = p->u0_h[lslot];       // fp16 copies of u0 / its residual (latent slot lslot), used when p->fwd_f16
+  const void* u0loh = p->u0lo_h[lslot];
   const int B = p->B;
   if (p->folded) {  // inference: conv (BatchNorm folded into weights and bias) + ReLU epilogues, one upsample pass
     const T4 ins[4] = {u0, d.a1, d.u1, d.a3};
@@ -567,11 +584,18 @@ static int decoder_fwd(NefPlan* p, const float* const* P, int slot, const T4& u0
     for (int i = 0; i < 4; ++i) {
       const ConvW& w = p->decw[i];
       CD c(1, w.cout_g, ins[i]);
-      c.term(ins[i], 0, 0, w.cin_g, 3, w.pk_f).out(outs[i], 0, 0).bias(p->fold_bias[i]).relu();
-      if (i == 0) {
-        if (g_dec1_terms >= 2) c.term(u0lo, 0, 0, 256, 3, w.pk_f);
-        if (g_dec1_terms >= 3) c.term(ins[i], 0, 0, 256, 3, p->dec1_lo);
+      if (i == 0 && p->fwd_f16) {
+        c.term16(u0h, u0.cs, 0, 0, 256, 3, w.pk_h);
+        if (g_dec1_terms >= 2) c.term16(u0loh, u0.cs, 0, 0, 256, 3, w.pk_h);
+        if (g_dec1_terms >= 3) c.term16(u0h, u0.cs, 0, 0, 256, 3, p->dec1_lo_h);
+      } else {
+        c.term(ins[i], 0, 0, w.cin_g, 3, w.pk_f);
+        if (i == 0) {
+          if (g_dec1_terms >= 2) c.term(u0lo, 0, 0, 256, 3, w.pk_f);
+          if (g_dec1_terms >= 3) c.term(ins[i], 0, 0, 256, 3, p->dec1_lo);
+        }
       }
+      c.out(outs[i], 0, 0).bias(p->fold_bias[i]).relu();
       if (i == 0 || i == 2) c.round();  // a1, a3 feed the next tensor-core convolution directly
       RUN(c.run(s));
       if (i == 1) RUN(bn_relu(d.c2, p->ident_scale, p->ident_shift, d.u1, 1, s));
@@ -586,11 +610,18 @@ static int decoder_fwd(NefPlan* p, const float* const* P, int slot, const T4& u0
   for (int i = 0; i < 4; ++i) {
     const Lay& l = lay[i];
     CD c(1, l.w->cout_g, l.in);
-    c.term(l.in, 0, 0, l.w->cin_g, 3, l.w->pk_f).out(l.c, 0, 0).bias(P[l.pb]);
-    if (i == 0) {  // split precision: x_hi w_hi + x_lo w_hi + x_hi w_lo  (this layer dominates the TF32 error budget)
-      if (g_dec1_terms >= 2) c.term(u0lo, 0, 0, 256, 3, l.w->pk_f);
-      if (g_dec1_terms >= 3) c.term(l.in, 0, 0, 256, 3, p->dec1_lo);
+    if (i == 0 && p->fwd_f16) {  // split precision in kind::f16 (same significand as TF32): x_hi w_hi + x_lo w_hi + x_hi w_lo
+      c.term16(u0h, u0.cs, 0, 0, 256, 3, l.w->pk_h);
+      if (g_dec1_terms >= 2) c.term16(u0loh, u0.cs, 0, 0, 256, 3, l.w->pk_h);
+      if (g_dec1_terms >= 3) c.term16(u0h, u0.cs, 0, 0, 256, 3, p->dec1_lo_h);
+    } else {
+      c.term(l.in, 0, 0, l.w->cin_g, 3, l.w->pk_f);
+      if (i == 0) {  // split precision: x_hi w_hi + x_lo w_hi + x_hi w_lo  (this layer dominates the TF32 error budget)
+        if (g_dec1_terms >= 2) c.term(u0lo, 0, 0, 256, 3, l.w->pk_f);
+        if (g_dec1_terms >= 3) c.term(l.in, 0, 0, 256, 3, p->dec1_lo);
+      }
     }
+    c.out(l.c, 0, 0).bias(P[l.pb]);
     if (training) c.stats(d.bn[i].sum, d.bn[i].sq);
     RUN(c.run(s));
     RUN(bn_finalize(d.bn[i], l.w->cout_g, l.count, P[l.bnp], P[l.bnp + 1], const_cast<float*>(P[l.bnp + 2]),
@@ -616,14 +647,18 @@ static int latents_to_decoders(NefPlan* p, const float* const* P, const float* q
   const int B = p->B;
   LatentArgs la;
   la.z1 = p->z1; la.z2o = p->z2o; la.rois = rois; la.G = p->G; la.c1 = p->c1; la.c2 = p->c2;
-  for (int k = 0; k < 3; ++k) { la.lat[k] = p->lat[k]; la.u0[k] = p->u0[k]; la.u0lo[k] = p->u0lo[k]; }
+  for (int k = 0; k < 3; ++k) {
+    la.lat[k] = p->lat[k]; la.u0[k] = p->u0[k]; la.u0lo[k] = p->u0lo[k];
+    la.u0h[k] = p->fwd_f16 ? p->u0_h[k] : nullptr;
+    la.u0loh[k] = p->fwd_f16 ? p->u0lo_h[k] : nullptr;
+  }
   if (!only_views) {
     RUN(angular_fwd(query_theta, P[P_MLP2_W], P[P_MLP2_B], p->q, B, 256, s));
     la.q = p->q; la.q_stride = 256; la.n_lat = 3; la.write_lat = 1;
     la.store_mask = phase == NEF_PHASE_TEST ? 3 : (2 | 32);
     RUN(latent_fwd(la, s));
     float* outs[3] = {out, out_p, out_l};
-    for (int k = 0; k < 3; ++k) RUN(decoder_fwd(p, P, k, p->u0[k], p->u0lo[k], training, outs[k], p->L, s));
+    for (int k = 0; k < 3; ++k) RUN(decoder_fwd(p, P, k, k, p->u0[k], p->u0lo[k], training, outs[k], p->L, s));
   } else {
     // gen_ecg: build lat[0] only (mean latents); q unused for that -> use rq view 0 below
     la.q = p->rq; la.q_stride = V * 256; la.n_lat = 1; la.write_lat = 1; la.store_mask = 3;
@@ -636,7 +671,7 @@ static int latents_to_decoders(NefPlan* p, const float* const* P, const float* q
       la.write_lat = (only_views && v == 0) ? 1 : 0;
       la.store_mask = 3;
       RUN(latent_fwd(la, s));
-      RUN(decoder_fwd(p, P, 0, p->u0[0], p->u0lo[0], training, rest_out + (size_t)v * p->L, V * p->L, s));
+      RUN(decoder_fwd(p, P, 0, 0, p->u0[0], p->u0lo[0], training, rest_out + (size_t)v * p->L, V * p->L, s));
     }
   }
   return 0;
@@ -733,6 +768,7 @@ extern "C" int nef_gen_ecg(NefPlan* p, const float* const* P, const float* z1, c
   p->c1 = 0; p->c2 = 0;
   NefPackTable packs;
   packs.n = 0;
+  p->fwd_f16 = g_fwd_f16 && g_conv_impl == 1;
   RUN(queue_decoder_packs(p, packs, P, true, s));   // gen_ecg runs the module in eval mode (model_nefnet.py:197)
   RUN(nef_pack_weights_batch(&packs, s));
   RUN(nef_ncl_to_cbl4(z1, reinterpret_cast<float*>(p->z1.p), p->B, p->C1, p->L4, 0, sv));
