@@ -518,34 +518,42 @@ constexpr int LAT_TL = 256;  // latent positions per inner tile
 constexpr int LB_TL = 1024;  // latent positions per tile of the backward kernel
 constexpr int LAT_GB = 12;   // leads whose loads are batched in the backward kernel
 
+// One block per (segment b, PAIR of 4-channel chunks of the 128 latent channels of a half, half: z1 | z2).  Adjacent lanes
+// take the two chunks of the pair, so a warp writes whole 16-byte rows of the 8-channel fp16 copies (lanes exchange their
+// halves by shuffle) and 256-byte runs of each fp32 chunk plane.  The z2 half first reduces the leads (mean and picked
+// lead of the 32-sample ROI codes) into shared memory and resamples those two -- linear resampling commutes with the mean.
 __global__ void __launch_bounds__(256) latent_fwd_kernel(const LatentArgs a) {
-  extern __shared__ float4 sm[];
-  const int L4 = a.z1.L;
-  const int b = blockIdx.x, cc = blockIdx.y, half = blockIdx.z;
-  const int tid = threadIdx.x;
-  float4* z2s = sm;                                   // [G][7 chunks][32]   (z2 half only)
-  float4* mt = sm + (half ? a.G * 7 * 32 : 0);        // [LAT_TL + 2] mean
-  float4* pt = mt + (LAT_TL + 2);                     // [LAT_TL + 2] pick
+  __shared__ float4 mt[2][LAT_TL + 2], pt[2][LAT_TL + 2];   // [chunk of the pair][position t0-1 .. t0+LAT_TL]: mean, pick
+  __shared__ float4 zm[2][NEF_NROI][32], zp[2][NEF_NROI][32];
   __shared__ RoiTab tab;
-  if (half == 1) {
+  const int L4 = a.z1.L;
+  const int b = blockIdx.x, cc0 = 2 * blockIdx.y, half = blockIdx.z;
+  const int tid = threadIdx.x;
+  const float invG = 1.0f / (float)a.G;
+  if (half == 1 && a.write_lat) {
     if (tid == 0) roi_table(a.rois, b, tab);
-    if (a.write_lat) {
-      for (int i = tid; i < a.G * 7 * 32; i += 256) {
-        const int pos = i & 31, r = i >> 5;
-        const int g = r / 7, m = r % 7;
-        z2s[i] = *a.z2o.at(g * 224 + cc * 7 + m, b, pos);
+    for (int i = tid; i < 2 * NEF_NROI * 32; i += 256) {
+      const int pos = i & 31, m = (i >> 5) % NEF_NROI, h2 = i / (NEF_NROI * 32);
+      float4 sum = f4zero(), pick = f4zero();
+      for (int g = 0; g < a.G; ++g) {
+        const float4 v = __ldg(a.z2o.at(g * 224 + (cc0 + h2) * 7 + m, b, pos));
+        sum = sum + v;
+        if (g == a.c2) pick = v;
       }
+      zm[h2][m][pos] = sum * invG;
+      zp[h2][m][pos] = pick;
     }
   }
   __syncthreads();
-  const int latc = half * 32 + cc;  // chunk in the 256-channel latent
+  const int h2 = tid & 1;                  // this lane's chunk of the pair
+  const int latc = half * 32 + cc0 + h2;   // chunk in the 256-channel latent
   const float4 qv = *reinterpret_cast<const float4*>(a.q + (long)b * a.q_stride + latc * 4);
-  const float invG = 1.0f / (float)a.G;
 
   for (int t0 = 0; t0 < L4; t0 += LAT_TL) {
     // ---- stage 1: lat values for positions t0-1 .. t0+LAT_TL (clamped) into smem
-    for (int i = tid; i < LAT_TL + 2; i += 256) {
-      int l = t0 - 1 + i;
+    for (int i = tid; i < 2 * (LAT_TL + 2); i += 256) {
+      const int ii = i >> 1;
+      int l = t0 - 1 + ii;
       l = l < 0 ? 0 : (l > L4 - 1 ? L4 - 1 : l);
       float4 m, p;
       if (!a.write_lat) {
@@ -557,7 +565,7 @@ __global__ void __launch_bounds__(256) latent_fwd_kernel(const LatentArgs a) {
         for (int g0 = 0; g0 < a.G; g0 += 4) {  // four leads at a time: their loads are in flight together
           float4 v[4];
 #pragma unroll
-          for (int k = 0; k < 4; ++k) v[k] = (g0 + k < a.G) ? __ldg(a.z1.at((g0 + k) * 32 + cc, b, l)) : f4zero();
+          for (int k = 0; k < 4; ++k) v[k] = (g0 + k < a.G) ? __ldg(a.z1.at((g0 + k) * 32 + cc0 + h2, b, l)) : f4zero();
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             m = m + v[k];
@@ -572,24 +580,15 @@ __global__ void __launch_bounds__(256) latent_fwd_kernel(const LatentArgs a) {
         int i0, i1;
         float lam;
         interp_src(l - tab.start[j], n > 0 ? n : 1, i0, i1, lam);
-        m = f4zero();
-        p = f4zero();
-        for (int g = 0; g < a.G; ++g) {
-          float4 v;
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const int chl = k * 7 + j;  // local channel among the 28 of this (g, cc)
-            const float4* zp = z2s + (g * 7 + (chl >> 2)) * 32;
-            const float x0 = f4get(zp[i0], chl & 3), x1 = f4get(zp[i1], chl & 3);
-            f4at(v, k) = (1.0f - lam) * x0 + lam * x1;
-          }
-          m = m + v;
-          if (g == a.c2) p = v;
+        for (int k = 0; k < 4; ++k) {
+          const int chl = k * 7 + j;  // local channel among the 28 (channel, roi) codes of this chunk
+          f4at(m, k) = (1.0f - lam) * f4get(zm[h2][chl >> 2][i0], chl & 3) + lam * f4get(zm[h2][chl >> 2][i1], chl & 3);
+          f4at(p, k) = (1.0f - lam) * f4get(zp[h2][chl >> 2][i0], chl & 3) + lam * f4get(zp[h2][chl >> 2][i1], chl & 3);
         }
-        m = m * invG;
       }
-      mt[i] = m;
-      pt[i] = p;
+      mt[h2][ii] = m;
+      pt[h2][ii] = p;
     }
     __syncthreads();
     // ---- stage 2: write the latents and their query-scaled x2 upsamples
@@ -597,25 +596,36 @@ __global__ void __launch_bounds__(256) latent_fwd_kernel(const LatentArgs a) {
     for (int k3 = 0; k3 < a.n_lat; ++k3) {
       // lat_all = [z1m, z2m], lat_p = [z1[c1], z2m], lat_l = [z1m, z2[c2]]
       const bool use_pick = (k3 == 1 && half == 0) || (k3 == 2 && half == 1);
-      const float4* src = use_pick ? pt : mt;
+      const float4* src = use_pick ? pt[h2] : mt[h2];
       if (a.write_lat && ((a.store_mask >> (2 * k3 + half)) & 1)) {
-        for (int i = tid; i < nl; i += 256) *a.lat[k3].at(latc, b, t0 + i) = src[i + 1];
+        for (int i = tid; i < 2 * nl; i += 256) *a.lat[k3].at(latc, b, t0 + (i >> 1)) = src[(i >> 1) + 1];
       }
-      for (int i = tid; i < 2 * nl; i += 256) {
-        const int li = i >> 1;  // latent position t0 + li ; smem index li + 1
+      // 4 * nl is a multiple of 32 only if nl is a multiple of 8: the shuffles below need every lane of a warp, so the loop
+      // runs whole warps and the stores are predicated
+      for (int i0 = tid & ~31; i0 < 4 * nl; i0 += 256) {
+        const int i = i0 + (tid & 31);
+        const bool ok = i < 4 * nl;
+        const int u = i >> 1;   // upsampled position 2 * t0 + u ; latent position t0 + li ; smem index li + 1
+        const int li = ok ? u >> 1 : 0;
         float4 v;
-        if ((i & 1) == 0) v = src[li] * 0.25f + src[li + 1] * 0.75f;
+        if ((u & 1) == 0) v = src[li] * 0.25f + src[li + 1] * 0.75f;
         else v = src[li + 1] * 0.75f + src[li + 2] * 0.25f;
         v = v * qv;
         const float4 hi = tf32_rn4(v);
-        *a.u0[k3].at(latc, b, 2 * t0 + i) = hi;
         const float4 lo = make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w);
-        if (a.u0h[k3]) {  // this block's 4 channels are one half of an 8-channel fp16 row
-          const long o8 = ((long)(latc >> 1) * a.u0[k3].cs + a.u0[k3].row(b, 2 * t0 + i)) * 2 + (latc & 1);
-          reinterpret_cast<uint2*>(a.u0h[k3])[o8] = make_uint2(f16x2_sat(hi.x, hi.y), f16x2_sat(hi.z, hi.w));
-          reinterpret_cast<uint2*>(a.u0loh[k3])[o8] = make_uint2(f16x2_sat(lo.x, lo.y), f16x2_sat(lo.z, lo.w));
-        } else {
-          *a.u0lo[k3].at(latc, b, 2 * t0 + i) = tf32_rn4(lo);
+        if (ok) *a.u0[k3].at(latc, b, 2 * t0 + u) = hi;
+        if (a.u0h[k3]) {
+          // even lane (channels 0..3 of the row) stores the fp16 row of hi, odd lane (channels 4..7) the row of lo
+          const uint32_t hx = f16x2_sat(hi.x, hi.y), hy = f16x2_sat(hi.z, hi.w);
+          const uint32_t lx = f16x2_sat(lo.x, lo.y), ly = f16x2_sat(lo.z, lo.w);
+          const uint32_t sx = __shfl_xor_sync(0xffffffffu, h2 ? hx : lx, 1), sy = __shfl_xor_sync(0xffffffffu, h2 ? hy : ly, 1);
+          if (ok) {
+            const long o16 = (long)(latc >> 1) * a.u0[k3].cs + a.u0[k3].row(b, 2 * t0 + u);
+            if (h2 == 0) reinterpret_cast<uint4*>(a.u0h[k3])[o16] = make_uint4(hx, hy, sx, sy);
+            else reinterpret_cast<uint4*>(a.u0loh[k3])[o16] = make_uint4(sx, sy, lx, ly);
+          }
+        } else if (ok) {
+          *a.u0lo[k3].at(latc, b, 2 * t0 + u) = tf32_rn4(lo);
         }
       }
     }
@@ -623,20 +633,12 @@ __global__ void __launch_bounds__(256) latent_fwd_kernel(const LatentArgs a) {
   }
 }
 
-constexpr int LAT_FWD_SMEM_MAX = 200 * 1024;
-// per-device opt-in to large dynamic shared memory, called once from nef_init (no lazily-set static state in the launchers)
-int elem_init() {
-  cudaError_t e = cudaFuncSetAttribute(latent_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LAT_FWD_SMEM_MAX);
-  NEF_REQUIRE(e == cudaSuccess, "nef_init: shared-memory opt-in failed: %s", cudaGetErrorString(e));
-  return 0;
-}
+// per-device setup of the kernels in this file, called once from nef_init (none of them needs a shared-memory opt-in now)
+int elem_init() { return 0; }
 
 int latent_fwd(const LatentArgs& a, cudaStream_t s) {
-  const size_t smem = ((size_t)a.G * 7 * 32 + 2 * (LAT_TL + 2)) * sizeof(float4);
-  NEF_REQUIRE(smem <= LAT_FWD_SMEM_MAX, "latent_fwd: %d leads need %zu bytes of shared memory (max %d)", a.G, smem,
-              LAT_FWD_SMEM_MAX);
-  dim3 grid(a.z1.B, 32, 2);
-  latent_fwd_kernel<<<grid, 256, smem, s>>>(a);
+  dim3 grid(a.z1.B, 16, 2);
+  latent_fwd_kernel<<<grid, 256, 0, s>>>(a);
   NEF_CHECK_LAUNCH("latent_fwd_kernel");
   return 0;
 }

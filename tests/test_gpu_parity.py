@@ -151,7 +151,8 @@ def test_golden(name, mode_name, golden_dir, cfg):
                     # each flip moving a 1-D gradient (a bias: one sum over positions) by ~1/L of its norm.
                     # The flip-free check of the backward logic is test_oracle_fixed_upstream (2e-3 relative L2).
                     np.testing.assert_allclose(got, ref, rtol=1e-2, atol=1e-2 * norm_ref / np.sqrt(gr.numel()) + 1e-9)
-                    assert nerr < 5e-3, (n, nerr)
+                    # (a bias gradient is ONE sum over positions: two sign flips at B = 1 move it by 0.5 %)
+                    assert nerr < (1e-2 if gr.dim() == 1 else 5e-3), (n, nerr)
                 else:      # L1 loss: sign(out - target) flips make the comparison statistical (B = 1: few samples);
                     # the TF32-tier gradient bar proper is test_oracle_fixed_upstream (cosine >= 0.99)
                     assert nerr < (0.3 if gr.dim() == 1 else 0.15), (n, nerr)   # a bias gradient is ONE sum over positions
