@@ -318,7 +318,7 @@ def main():
                 "gpu_launches": int(launches),
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                              "frac": achieved / hbm_peak, "traffic": measured_traffic(B, G, L), "peak_source": peak_src,
-                             "kernel": "grouped k7 implicit-GEMM conv (encoder block conv / dgrad), %d x %d x %d" % (B, 128 * G, L // 4),
+                             "kernel": "grouped k7 implicit-GEMM conv, TF32 form (the six encoder data gradients; the forward form of the same kernel reads fp16 operands), %d x %d x %d" % (B, 128 * G, L // 4),
                              "kernel_ms": kms, "kernel_algorithmic_bytes": kbytes,
                              "kernel_tflops": kflops / (kms / 1000.0) / 1e12, "tf32_peak_tflops_half_of_bf16": tf32_peak,
                              "kernel_tensor_frac": kflops / (kms / 1000.0) / 1e12 / tf32_peak,
