@@ -68,3 +68,44 @@ def test_pack_records_offsets():
     assert off.tolist() == [0, 40, 112] and lens.tolist() == [5, 9, 4]
     assert float(raw[off[1] + 9 * 2 + 3]) == float(recs[1][2, 3])
     assert LEAD_THETA.shape == (12, 2)
+
+
+def test_checkpoint_interchange_with_the_reference_state_dict(tmp_path):
+    """checkpointer.py:28,79-81 saves / restores `model.state_dict()` with torch.save / load_state_dict: a reference-shaped
+    checkpoint loads strictly, survives .float() (solver.py:22) and a save / load round trip bit for bit."""
+    import network
+    from oracle import nefnet_oracle as O
+    P = O.make_params(2, seed=9)
+    m = network.Model_nefnet(theta_encoder_len=1, lead_num=2).float()
+    res = m.load_state_dict({k: v.clone() for k, v in P.items()}, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    path = tmp_path / "best_valid.pkl"
+    torch.save({"model": m.state_dict(), "epoch": 3}, path)
+    back = torch.load(path, map_location="cpu")
+    m2 = network.Model_nefnet(theta_encoder_len=1, lead_num=2)
+    m2.load_state_dict(back["model"])
+    for k, v in m2.state_dict().items():
+        assert v.dtype == P[k].dtype and torch.equal(v, P[k]), k
+    assert m2.state_dict()["decoder.1.double_conv.1.num_batches_tracked"].dtype == torch.long
+    with pytest.raises(RuntimeError):   # a 3-lead checkpoint does not fit a 2-lead model: same loud failure as nn.Module
+        m2.load_state_dict(O.make_params(3, seed=9))
+
+
+def test_default_initialisation_scales():
+    """resnet_1d.py:114-120: encoder convs ~ N(0, sqrt(2 / (k * k * out_channels))); PyTorch defaults elsewhere
+    (uniform within 1 / sqrt(fan_in)); BatchNorm gamma 1, beta 0, running stats (0, 1)."""
+    import network
+    torch.manual_seed(0)
+    G = 2
+    sd = network.Model_nefnet(theta_encoder_len=1, lead_num=G).state_dict()
+    w = sd["W_encoder.layer1.0.conv1.weight"]
+    assert float(w.std()) == pytest.approx(math.sqrt(2.0 / (7 * 7 * 128 * G)), rel=0.03) and abs(float(w.mean())) < 1e-4
+    w = sd["W_encoder.conv1.weight"]
+    assert float(w.std()) == pytest.approx(math.sqrt(2.0 / (15 * 15 * 128 * G)), rel=0.06)
+    for name, fan_in in (("w_conv.0.conv1.weight", 128 * 3), ("z1_conv.0.residual_conv.weight", 64), ("z1_conv.0.residual_conv.bias", 64),
+                         ("z2_conv2.1.weight", 64 * 2), ("z2_conv2.1.bias", 64 * 2), ("decoder.1.double_conv.0.weight", 256 * 3),
+                         ("decoder.4.bias", 64 * 3), ("mlp1.weight", 12), ("mlp2.bias", 12)):
+        b = 1.0 / math.sqrt(fan_in)
+        assert float(sd[name].abs().max()) <= b and (sd[name].numel() < 100 or float(sd[name].abs().max()) > 0.9 * b), name
+    assert bool((sd["decoder.3.double_conv.4.weight"] == 1).all()) and bool((sd["decoder.3.double_conv.4.bias"] == 0).all())
+    assert bool((sd["decoder.1.double_conv.1.running_var"] == 1).all()) and int(sd["decoder.1.double_conv.1.num_batches_tracked"]) == 0
