@@ -178,6 +178,18 @@ class Model_nefnet(nn.Module):
     def flat_grads(self):
         return self._flat_grad
 
+    @torch.no_grad()
+    def sync_param_grads(self):
+        """Writes the flat gradient buffer back into every ``p.grad`` that does not alias it.  Autograd stores COPIES
+        of the views ``backward`` returns, so after ``allreduce_gradients`` changed the flat buffer a stock torch
+        optimiser (which reads ``p.grad``) needs this; ``FlatSGD`` reads the flat buffer and does not."""
+        if self._flat_grad is None:
+            raise RuntimeError("Model_nefnet.sync_param_grads() before the first forward/backward")
+        for n, p in self.named_parameters():
+            gv = self._grad_views[n]
+            if p.grad is not None and p.grad.data_ptr() != gv.data_ptr():
+                p.grad.copy_(gv)
+
     def _ensure_ready(self, device):
         if device.type != "cuda":
             raise RuntimeError("Model_nefnet (B200) runs on an sm_100 CUDA device only; got tensors on %s. "

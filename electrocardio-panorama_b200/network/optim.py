@@ -77,8 +77,16 @@ def get_lr_scheduler(cfg, optim=None):
     return None
 
 
-def allreduce_gradients(model, group=None):
-    """One all-reduce (sum) of the flat gradient buffer; the unused parameters have zero slots."""
+def allreduce_gradients(model, group=None, average=False):
+    """One all-reduce (sum) of the flat gradient buffer; the unused parameters have zero slots.
+
+    ``FlatSGD`` reads the flat buffer and folds 1 / world_size into its kernel (``opt.step(world_size)``), so it needs
+    nothing else.  A stock torch optimiser (the reference's own ``get_optimizer``, optim_scheduler.py:5-10) reads
+    ``p.grad``, which autograd fills with COPIES of the flat views: pass ``average=True`` to scale the buffer by
+    1 / world_size and write the reduced values back into every ``p.grad`` (``Model_nefnet.sync_param_grads``)."""
     import torch.distributed as dist
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(model.flat_grads, op=dist.ReduceOp.SUM, group=group)
+        if average:
+            model.flat_grads.mul_(1.0 / dist.get_world_size(group))
+            model.sync_param_grads()

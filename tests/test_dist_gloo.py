@@ -65,6 +65,21 @@ def _worker(rank, world, port, ret):
             e = sum(g[n] for g in expect) / world
             got = mean[holder.offsets[n]:holder.offsets[n] + e.numel()].view_as(e)
             worst = max(worst, float((got - e).abs().max() / (e.abs().max() + 1e-30)))
+        # the stock-optimiser route: the real module's flat buffers (host logic only, CPU tensors), p.grad holding COPIES
+        # of the flat views as autograd leaves them; average=True must write the mean back into every p.grad
+        import network
+        m = network.Model_nefnet(theta_encoder_len=1, lead_num=G)
+        m._flatten(torch.device("cpu"))
+        params = dict(m.named_parameters())
+        for n in names:
+            m._grad_views[n].copy_(mine[n])
+            params[n].grad = m._grad_views[n].clone()
+        allreduce_gradients(m, average=True)
+        for n in names:
+            e = sum(g[n] for g in expect) / world
+            assert params[n].grad.data_ptr() != m._grad_views[n].data_ptr()
+            worst = max(worst, float((params[n].grad - e).abs().max() / (e.abs().max() + 1e-30)))
+        assert all(params[n].grad is None for n in O.UNUSED_PARAMS)
         ret[rank] = worst
     finally:
         dist.destroy_process_group()

@@ -109,3 +109,20 @@ def test_default_initialisation_scales():
         assert float(sd[name].abs().max()) <= b and (sd[name].numel() < 100 or float(sd[name].abs().max()) > 0.9 * b), name
     assert bool((sd["decoder.3.double_conv.4.weight"] == 1).all()) and bool((sd["decoder.3.double_conv.4.bias"] == 0).all())
     assert bool((sd["decoder.1.double_conv.1.running_var"] == 1).all()) and int(sd["decoder.1.double_conv.1.num_batches_tracked"]) == 0
+
+
+def test_sync_param_grads_writes_the_flat_buffer_back():
+    """Autograd stores copies of the flat gradient views in p.grad; after the flat buffer changed (all-reduce) a stock
+    optimiser needs them refreshed.  Host logic only: the flat buffers are built on the CPU here."""
+    import network
+    m = network.Model_nefnet(theta_encoder_len=1, lead_num=1)
+    with pytest.raises(RuntimeError):
+        m.sync_param_grads()
+    m._flatten(torch.device("cpu"))
+    params = dict(m.named_parameters())
+    assert all(p.data_ptr() >= m.flat_params.data_ptr() for p in params.values())   # parameters are views of the flat buffer
+    params["mlp1.weight"].grad = torch.zeros(128, 12)
+    m.flat_grads.fill_(0.5)
+    m.sync_param_grads()
+    assert bool((params["mlp1.weight"].grad == 0.5).all()) and params["mlp2.weight"].grad is None
+    assert m.flat_grads.numel() % 4 == 0 and m.flat_grads.numel() >= 2702081
