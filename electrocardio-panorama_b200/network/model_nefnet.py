@@ -191,6 +191,11 @@ class Model_nefnet(nn.Module):
                 p.grad.copy_(gv)
 
     def _ensure_ready(self, device):
+        if getattr(self, "_is_replica", False):
+            # solver.py:32-34 wraps the module in nn.DataParallel when several GPUs are visible; its per-call replicas
+            # share this object's plans and flat buffers across devices.  The B200 path is one process per GPU.
+            raise RuntimeError("Model_nefnet (B200) does not run under nn.DataParallel: launch one process per GPU "
+                               "(CUDA_VISIBLE_DEVICES=<rank>) and use network.optim.allreduce_gradients")
         if device.type != "cuda":
             raise RuntimeError("Model_nefnet (B200) runs on an sm_100 CUDA device only; got tensors on %s. "
                                "There is no CPU path." % device)

@@ -13,7 +13,11 @@ class FlatSGD(torch.optim.Optimizer):
     """SGD with momentum over the module's flat parameter / gradient buffers.  It is a ``torch.optim.Optimizer`` (one
     param group), so the reference's schedulers (``StepLR(optim, 50, gamma=0.1)`` / ``MultiStepLR``,
     optim_scheduler.py:13-18) and ``optim.zero_grad()`` / ``optim.step()`` (solver.py:232-235) drive it unchanged; the
-    learning rate is read from ``param_groups[0]['lr']`` at every step."""
+    learning rate is read from ``param_groups[0]['lr']`` at every step.
+
+    The step reads ``model.flat_grads`` -- the buffer ``backward`` writes -- not the ``p.grad`` tensors (autograd keeps
+    copies of the flat views there).  Anything that edits gradients between ``backward`` and ``step`` (clipping, noise; the
+    reference does neither) must edit ``model.flat_grads``, which is one tensor: ``flat_grads.mul_(coef)``."""
 
     def __init__(self, model, lr=0.1, momentum=0.9):
         self.model = model

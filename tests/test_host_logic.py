@@ -126,3 +126,15 @@ def test_sync_param_grads_writes_the_flat_buffer_back():
     m.sync_param_grads()
     assert bool((params["mlp1.weight"].grad == 0.5).all()) and params["mlp2.weight"].grad is None
     assert m.flat_grads.numel() % 4 == 0 and m.flat_grads.numel() >= 2702081
+
+
+def test_data_parallel_replicas_fail_loudly():
+    """solver.py:32-34 wraps the model in nn.DataParallel when it sees several GPUs; the B200 path is one process per GPU,
+    and a replica must say so instead of running on buffers that belong to another device."""
+    import network
+    m = network.Model_nefnet(theta_encoder_len=1, lead_num=1)
+    replica = m._replicate_for_data_parallel()
+    with pytest.raises(RuntimeError, match="DataParallel"):
+        replica(torch.zeros(1, 1, 64), torch.zeros(1, 1, 2), torch.zeros(1, 2), torch.zeros(1, 7, 2, dtype=torch.long))
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        m(torch.zeros(1, 1, 64), torch.zeros(1, 1, 2), torch.zeros(1, 2), torch.zeros(1, 7, 2, dtype=torch.long))
