@@ -156,7 +156,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * 8 / cb["value"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(1, args.batch, L), "batch_per_gpu": args.batch,
+            "config": {"workload": workload_name(args.gpus, args.batch, L), "batch_per_gpu": args.batch,
                        "global_batch": args.batch * args.gpus, "leads": 12, "length": L,
                        "sample": "each step = the same train step on a bounded sample of 8 segments on the host cores "
                                  "(reference algorithm, oracle port; the reference is pure PyTorch and cannot travel to the box)"},
