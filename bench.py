@@ -138,9 +138,19 @@ def cpu_baseline(G, L, steps=2, warmup=1, B=8):
         if it >= warmup:
             times.append(dt)
     t = min(times)
-    return {"value": B / t, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-            "sample": "oracle train step (fwd + Standin loss + bwd + SGD) at B=%d x %d x %d fp32, %d warm-up + best of %d"
-                      % (B, G, L, warmup, steps), "host_cpus": os.cpu_count()}
+    # the forward alone (training mode: dropout masks, BN batch statistics, 3 decoder passes), next to bench.py's `forward`
+    ftimes = []
+    for it in range(2):
+        k = keeps()
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            O.forward(P, inp["x"], inp["input_thetas"], inp["query_theta"], inp["rois"], phase="train", lead_choice=(0, 1 % G),
+                      keeps=k)
+        ftimes.append(time.perf_counter() - t0)
+    return {"value": B / t, "forward_value": B / min(ftimes), "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": "oracle train step (fwd + Standin loss + bwd + SGD) at B=%d x %d x %d fp32, %d warm-up + best of %d; "
+                      "forward_value = the training-mode forward alone, best of 2" % (B, G, L, warmup, steps),
+            "host_cpus": os.cpu_count()}
 
 
 def run_reference(args):
