@@ -1,0 +1,42 @@
+"""CPU: the byte / unit accounting bench.py reports is the one SURVEY 8(d) states (no GPU, no timing)."""
+import json
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+
+
+def test_algorithmic_bytes_match_the_survey():
+    """286.0 MB / segment forward at G = 12, L = 5000, n_dec = 3 (nominal); 1106.7 MB at L = 20000;
+    528.3 MB for the 24-view sweep; a train step is 3 x forward -> 219.6 GB at batch 256."""
+    nominal = bench.algorithmic_bytes_per_segment(12, 5000, live=False)
+    assert nominal / 1e6 == pytest.approx(286.0, abs=0.05)
+    assert 3 * nominal * 256 / 1e9 == pytest.approx(219.6, abs=0.1)
+    assert bench.algorithmic_bytes_per_segment(12, 20000, live=False) / 1e6 == pytest.approx(1106.7, abs=0.1)
+    assert bench.algorithmic_bytes_per_segment(12, 5000, n_dec=24, live=False) / 1e6 == pytest.approx(528.3, abs=0.1)
+    live = bench.algorithmic_bytes_per_segment(12, 5000, live=True)
+    assert live < nominal and (nominal - live) == 4 * 4 * 128 * 12 * 1250   # z2_conv1 on the live window
+    assert 3 * live * 256 / 1e9 == pytest.approx(196.04, abs=0.01)
+
+
+def test_forward_report_and_workload_names():
+    r = bench.forward_report(18.6, 1, 256, 12, 5000, 6547.2)
+    assert r["hbm_frac_nominal"] == pytest.approx(0.60, abs=0.005)           # SURVEY: 18.6 ms <=> 60 % of 6547 GB/s
+    assert r["segments_per_s"] == pytest.approx(256 / 0.0186)
+    assert "NCCL" in bench.workload_name(8, 256, 5000) and "NCCL" not in bench.workload_name(1, 256, 5000)
+    assert bench.METRIC.startswith("ECG segments/sec") and bench.UNIT == "segments/s"
+
+
+def test_dominant_kernel_traffic_fixture_is_the_bench_shape():
+    """roofline.traffic comes from the committed ncu capture; it must describe the shape bench.py times by default and agree
+    with the kernel's algorithmic bytes (no wasted re-reads)."""
+    t = json.load(open(os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")))
+    assert (t["B"], t["G"], t["L"]) == (256, 12, 5000)
+    traffic = bench.measured_traffic(256, 12, 5000)
+    alg = 2.0 * 128 * 12 * 1250 * 256 * 4
+    assert traffic is not None and 0.95 < traffic / alg < 1.10
+    assert bench.measured_traffic(64, 12, 20000) is None
