@@ -113,3 +113,23 @@ def test_product_never_touches_the_oracle():
                 assert fn.name == "cpu_baseline", fn.name
     for node in tree.body:   # no module-level import either
         assert not (isinstance(node, (ast.Import, ast.ImportFrom)) and "oracle" in ast.dump(node))
+
+
+def test_plan_sizing_is_host_only_and_fits_the_part(lib):
+    """nef_plan_create / nef_plan_workspace_bytes make no CUDA call: the caller-owned workspace of every BASELINE
+    configuration is known before a device exists, and fits the 180 GB of HBM3e (57.6 GB at C2)."""
+    import ctypes as C
+    sizes = {}
+    for name, (B, G, L, V) in {"C2": (256, 12, 5000, 0), "C4": (64, 12, 20000, 0), "C5": (64, 12, 5000, 24),
+                               "C5_one_gpu": (512, 12, 5000, 24), "tiny": (1, 1, 16, 0)}.items():
+        h = C.c_void_p()
+        assert lib.nef_plan_create(B, G, L, V, C.byref(h)) == 0, lib.nef_last_error()
+        sizes[name] = lib.nef_plan_workspace_bytes(h)
+        lib.nef_plan_destroy(h)
+    assert sizes["C2"] / 1e9 == pytest.approx(57.6, abs=0.1)
+    assert all(v < 180e9 * 0.9 for v in sizes.values()) and sizes["tiny"] < 64e6
+    assert sizes["C5"] < sizes["C2"] / 3      # nothing is saved for backward per view: the 24 views reuse one decoder slot
+    for bad in ((0, 1, 16, 0), (1, 0, 16, 0), (1, 1, 18, 0), (1, 1, 8, 0)):
+        h = C.c_void_p()
+        assert lib.nef_plan_create(*bad, C.byref(h)) != 0
+        assert b"nef_plan_create" in lib.nef_last_error()
