@@ -133,3 +133,15 @@ def test_plan_sizing_is_host_only_and_fits_the_part(lib):
         h = C.c_void_p()
         assert lib.nef_plan_create(*bad, C.byref(h)) != 0
         assert b"nef_plan_create" in lib.nef_last_error()
+
+
+def test_host_only_helpers(lib):
+    """Layout arithmetic and switch validation that need no device (CBL4 rows = B * (L + 6))."""
+    assert lib.nef_cbl4_rows(256, 1250) == 256 * (1250 + 6)
+    assert lib.nef_cbl4_floats(128, 2, 40) == ((128 // 4) * 2 * 46 + 528) * 4      # + tail guard rows
+    assert lib.nef_prepare_scratch_bytes(256) > 0
+    assert lib.nef_set_dec1_terms(0) != 0 and b"nef_set_dec1_terms" in lib.nef_last_error()
+    assert lib.nef_set_dec1_terms(4) != 0
+    assert lib.nef_set_dec1_terms(3) == 0                                           # the default stays selected
+    assert lib.nef_param_numel(12, 10**6) == -1 and lib.nef_param_name(12, -1) == b""
+    assert lib.nef_struct_size(99) == 0
