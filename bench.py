@@ -111,7 +111,7 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": statistics.median(self.sm), "sm_max_mhz": max(self.smmax), "reasons": sorted(self.reasons)}
 
 
-def cpu_baseline(G, L, steps=2, warmup=1, B=8):
+def cpu_baseline(G, L, steps=2, warmup=1, B=8, device="cpu"):
     """The reference algorithm (oracle port) on the host: forward + loss + backward + SGD, dropout off is
     NOT used here -- the reference trains with dropout, so keep-masks are drawn on the host as it does."""
     import torch
@@ -120,20 +120,28 @@ def cpu_baseline(G, L, steps=2, warmup=1, B=8):
         torch.set_num_threads(os.cpu_count() or 1)
     P = O.make_params(G, 0)
     inp = O.make_inputs(B, G, L, 0)
+    on_gpu = device != "cpu"   # opt-in context number (--ref-device cuda): the same port in PyTorch eager on the GPU, library kernels
+    if on_gpu:
+        P = {k: v.to(device) for k, v in P.items()}
+        inp = {k: v.to(device) for k, v in inp.items()}
     mom = {}
     gen = torch.Generator().manual_seed(0)
+    sync = torch.cuda.synchronize if on_gpu else (lambda: None)
 
     def keeps():
         k = {}
         for name, ch, ln in ([(f"W_encoder.layer1.{i}", 128 * G, L // 4) for i in range(3)] +
                              [("w_conv.0", 128 * G, L // 4), ("z1_conv.0", 128 * G, L // 4),
                               ("z2_conv1.0", 128 * G, L // 4), ("z2_conv2.0", 896 * G, 16), ("z2_conv2.2", 896 * G, 32)]):
-            k[name] = torch.rand(B, ch, ln, generator=gen) >= 0.2
+            k[name] = (torch.rand(B, ch, ln, generator=gen) >= 0.2).to(device)
         return k
     times = []
     for it in range(warmup + steps):
+        kk = keeps()
+        sync()
         t0 = time.perf_counter()
-        O.train_step(P, inp, lead_choice=(it % G, (it + 1) % G), momentum_buf=mom, keeps=keeps())
+        O.train_step(P, inp, lead_choice=(it % G, (it + 1) % G), momentum_buf=mom, keeps=kk)
+        sync()
         dt = time.perf_counter() - t0
         if it >= warmup:
             times.append(dt)
@@ -142,12 +150,15 @@ def cpu_baseline(G, L, steps=2, warmup=1, B=8):
     ftimes = []
     for it in range(2):
         k = keeps()
+        sync()
         t0 = time.perf_counter()
         with torch.no_grad():
             O.forward(P, inp["x"], inp["input_thetas"], inp["query_theta"], inp["rois"], phase="train", lead_choice=(0, 1 % G),
                       keeps=k)
+        sync()
         ftimes.append(time.perf_counter() - t0)
-    return {"value": B / t, "forward_value": B / min(ftimes), "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+    return {"value": B / t, "forward_value": B / min(ftimes), "unit": UNIT, "cores": torch.get_num_threads(),
+            "kind": "port" if not on_gpu else "port on the GPU (PyTorch eager, cuDNN / library kernels; context only)",
             "sample": "oracle train step (fwd + Standin loss + bwd + SGD) at B=%d x %d x %d fp32, %d warm-up + best of %d; "
                       "forward_value = the training-mode forward alone, best of 2" % (B, G, L, warmup, steps),
             "host_cpus": os.cpu_count()}
@@ -162,13 +173,14 @@ def run_reference(args):
     for k in ("OMP_NUM_THREADS", "MKL_NUM_THREADS"):
         os.environ[k] = str(ncpu)
     G, L = 12, args.length
-    cb = cpu_baseline(G, L, steps=max(1, min(args.steps, 3)), warmup=min(args.warmup, 1), B=8)
+    cb = cpu_baseline(G, L, steps=max(1, min(args.steps, 3)), warmup=min(args.warmup, 1), B=args.ref_batch,
+                      device=args.ref_device)
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * 8 / cb["value"],
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * args.ref_batch / cb["value"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(args.gpus, args.batch, L), "batch_per_gpu": args.batch,
                        "global_batch": args.batch * args.gpus, "leads": 12, "length": L,
-                       "sample": "each step = the same train step on a bounded sample of 8 segments on the host cores "
+                       "sample": "each step = the same train step on a bounded sample of %d segments on the host cores " % args.ref_batch +
                                  "(reference algorithm, oracle port; the reference is pure PyTorch and cannot travel to the box)"},
             "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -210,6 +222,9 @@ def main():
     ap.add_argument("--batch", type=int, default=256, help="segments per GPU")
     ap.add_argument("--length", type=int, default=5000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-device", default="cpu", help="--impl reference only: 'cuda' times the oracle port in PyTorch eager on "
+                    "the GPU (library kernels) as a context number; the reference arm proper is the default, 'cpu'")
+    ap.add_argument("--ref-batch", type=int, default=8, help="--impl reference only: segments per step of the bounded sample")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
