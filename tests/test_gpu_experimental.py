@@ -1,0 +1,79 @@
+"""GPU, OPT-IN: kernels that compile for sm_100a but have not been run on hardware yet.  Skipped unless NEF_RUN_UNVERIFIED=1, so
+that an unverified kernel can never turn the parity suite red (or hang it); nothing here is on the product path.
+
+    NEF_RUN_UNVERIFIED=1 timeout 120 python -m pytest tests/test_gpu_experimental.py -m gpu -x -q -s
+
+nef_gconv_wgrad_f16 (csrc/nef_wgrad_f16.cu): weight gradient from fp16 operand copies read MN-major as the bulk copy lands
+them -- no re-tile pass ("the largest step left")."""
+import ctypes as C
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("NEF_RUN_UNVERIFIED") != "1",
+                                 reason="unverified on hardware; opt in with NEF_RUN_UNVERIFIED=1")]
+
+
+def _half8(t):
+    """CBL4 fp32 tensor (ops.Cbl4) -> fp16 copy `half8 [C/8][rows]` with the same guard rows on both sides."""
+    from network import _native as N
+    c4 = t.C // 4
+    v = t.data.view(c4 // 2, 2, t.rows, 4).permute(0, 2, 1, 3).contiguous().view(-1).half()
+    g = N.GUARD_ROWS * 8
+    buf = torch.zeros(v.numel() + 2 * g, dtype=torch.float16, device=v.device)
+    buf[g:g + v.numel()] = v
+    return buf, buf[g:]
+
+
+@pytest.mark.parametrize("B,L,groups,cin_g,taps", [(2, 122, 1, 64, 1), (3, 250, 2, 128, 3), (4, 500, 2, 128, 7), (1, 40, 3, 64, 7),
+                                                   (16, 1250, 2, 128, 7)])
+def test_wgrad_f16_matches_autograd(B, L, groups, cin_g, taps):
+    from network import _native as N, ops
+    dev = torch.device("cuda:0")
+    lib = N.init(0)
+    raw = C.CDLL(lib._name)
+    fn = raw.nef_gconv_wgrad_f16
+    fn.restype = C.c_int
+    fn.argtypes = [C.POINTER(N.NefWgradDesc), C.c_void_p, C.c_void_p, C.c_float, C.c_void_p]
+    cout_g = 128
+    a, b = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        gen = torch.Generator(device="cpu").manual_seed(B * 1000 + L + taps)
+        x = torch.randn(B, groups * cin_g, L, generator=gen).half().float().to(dev)      # exactly representable in fp16
+        dy = torch.randn(B, groups * cout_g, L, generator=gen).half().float().to(dev)
+        w = torch.zeros(groups * cout_g, cin_g, taps, device=dev, requires_grad=True)
+        F.conv1d(x, w, None, padding=taps // 2, groups=groups).backward(dy)
+        xt = ops.Cbl4(groups * cin_g, B, L, dev).from_ncl(x)
+        dyt = ops.Cbl4(groups * cout_g, B, L, dev).from_ncl(dy)
+        xkeep, x16 = _half8(xt)
+        ykeep, dy16 = _half8(dyt)
+        dw = torch.zeros_like(w)
+        d = N.NefWgradDesc()
+        d.dy, d.dy_cstride, d.dy_c4_off, d.dy_c4_gstride = dyt.ptr, dyt.rows, 0, cout_g // 4
+        d.x, d.x_cstride, d.x_c4_off, d.x_c4_gstride = xt.ptr, xt.rows, 0, cin_g // 4
+        d.cout_g, d.cin_g, d.groups, d.taps, d.tap_off = cout_g, cin_g, groups, taps, -(taps // 2)
+        d.rows = dyt.rows
+        d.dw, d.sg, d.sm, d.sn, d.st = dw.data_ptr(), cout_g * cin_g * taps, cin_g * taps, taps, 1
+        scale = 0.25
+        N.check(fn(C.byref(d), C.c_void_p(dy16.data_ptr()), C.c_void_p(x16.data_ptr()), scale, N.stream_ptr()),
+                "nef_gconv_wgrad_f16")
+        torch.cuda.synchronize()
+        ref = w.grad * scale
+        tol = 5e-4 * float(ref.abs().max())
+        err = float((dw - ref).abs().max())
+        print("wgrad_f16 B%d L%d g%d cin%d k%d: max err %.3e (bar %.3e)" % (B, L, groups, cin_g, taps, err, tol))
+        assert err < tol
+        # cross-check against the production TF32 kernel on the same tensors, and accumulation (+=)
+        dw2 = torch.zeros_like(w)
+        ops.gconv_wgrad(dyt, xt, dw2, groups, cout_g, cin_g, taps)
+        assert float((dw - scale * dw2).abs().max()) < 2 * tol
+        N.check(fn(C.byref(d), C.c_void_p(dy16.data_ptr()), C.c_void_p(x16.data_ptr()), scale, N.stream_ptr()),
+                "nef_gconv_wgrad_f16")
+        assert float((dw - 2 * ref).abs().max()) < 2 * tol
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = a, b
