@@ -111,7 +111,7 @@ def test_standin_loss_equals_the_reference_wrapper(reg_loss, using):
             res = O.standin_loss(o, p, l, base[3], factor=(0.5, 0.25, 2.0), loss_using=tuple(using), reg_loss=reg_loss,
                                  rest_out=rest[0], rest_view=rest[1])
         res[0].backward()
-        vals.append([float(v.detach()) for v in res])
+        vals.append([float(v.detach()) if torch.is_tensor(v) else float(v) for v in res])
         grads.append([t.grad if t.grad is not None else torch.zeros_like(t) for t in (o, p, l)])
     assert vals[0] == pytest.approx(vals[1], rel=1e-6, abs=1e-9) and len(vals[0]) == 5
     for a, b in zip(*grads):
