@@ -7,7 +7,7 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo, uint64_t lt = 0) {
   return ((uint64_t)lt << 61) | (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | (1ull << 46);
 }
-__global__ void probe(int a_major, uint32_t a_lbo, uint32_t a_sbo, int lt, float* out) {
+__global__ void probe(int a_major, uint32_t a_lbo, uint32_t a_sbo, int lt, float* out, uint32_t a_shift = 0) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __nv_bfloat16* A = reinterpret_cast<__nv_bfloat16*>(smem);            // 64 KB = 32768 halves
   __nv_bfloat16* Bm = reinterpret_cast<__nv_bfloat16*>(smem + 65536);
@@ -30,7 +30,7 @@ __global__ void probe(int a_major, uint32_t a_lbo, uint32_t a_sbo, int lt, float
   if (tid == 0) {
     // c=f32 (1<<4), a=bf16 (1<<7), b=bf16 (1<<10)
     uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_major << 15) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
-    uint64_t ad = make_desc(smem_u32(A), a_lbo, a_sbo, lt), bd = make_desc(smem_u32(Bm), 128 * 16, 128);
+    uint64_t ad = make_desc(smem_u32(A) + a_shift, a_lbo, a_sbo, lt), bd = make_desc(smem_u32(Bm), 128 * 16, 128);
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem), "l"(ad), "l"(bd), "r"(idesc), "r"(0u) : "memory");
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
   }
@@ -52,16 +52,20 @@ int main() {
   float* out; cudaMalloc(&out, 128 * 32 * 4);
   static float h[128 * 32];
   cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 131072 + 256);
-  struct V { const char* name; int a_major; uint32_t lbo, sbo; int lt; } vs[] = {
+  struct V { const char* name; int a_major; uint32_t lbo, sbo; int lt; uint32_t shift; } vs[] = {
     {"bf16 A K-major  LBO=2048 SBO=128 (sanity): m -> unit m (k<8), unit 128+m (k>=8)", 0, 2048, 128, 0},
     {"bf16 A MN-major NONE LBO=128 SBO=1024", 1, 128, 1024, 0},
     {"bf16 A MN-major NONE LBO=1024 SBO=128", 1, 1024, 128, 0},
     {"bf16 A MN-major SW128 LBO=2048 SBO=1024", 1, 2048, 1024, 2},
     {"bf16 A MN-major SW128 LBO=1024 SBO=2048", 1, 1024, 2048, 2},
+    // the weight-gradient kernel without a re-tile pass (csrc/nef_wgrad_f16.cu) shifts the start address by one 16-byte
+    // row per tap: expected = every unit index of the LBO=128 / SBO=1024 variant above plus 1 (plus 3)
+    {"bf16 A MN-major NONE LBO=128 SBO=1024, start + 16 B", 1, 128, 1024, 0, 16},
+    {"bf16 A MN-major NONE LBO=128 SBO=1024, start + 48 B", 1, 128, 1024, 0, 48},
   };
   for (auto& v : vs) {
     cudaMemset(out, 0xff, 128 * 32 * 4);
-    probe<<<1, 128, 131072 + 256>>>(v.a_major, v.lbo, v.sbo, v.lt, out);
+    probe<<<1, 128, 131072 + 256>>>(v.a_major, v.lbo, v.sbo, v.lt, out, v.shift);
     cudaError_t e = cudaDeviceSynchronize();
     cudaMemcpy(h, out, sizeof(h), cudaMemcpyDeviceToHost);
     printf("== %s : %s\n", v.name, cudaGetErrorString(e));
