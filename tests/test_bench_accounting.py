@@ -40,3 +40,20 @@ def test_dominant_kernel_traffic_fixture_is_the_bench_shape():
     alg = 2.0 * 128 * 12 * 1250 * 256 * 4
     assert traffic is not None and 0.95 < traffic / alg < 1.10
     assert bench.measured_traffic(64, 12, 20000) is None
+
+
+def test_profile_summaries_regenerate_from_the_committed_launch_lists():
+    """profiles/*_summary.txt are tools/ output over the committed ncu launch lists: regenerate and compare, so the per-kernel
+    shares quoted in DESIGN.md can be traced to raw captures."""
+    import subprocess
+    prof = os.path.join(ROOT, "profiles")
+    for tool, args, summary in (
+            ("kernel_metrics.py", ["r01_step_b256_per_kernel_metrics.csv", "6457.4"], "r01_step_b256_per_kernel_metrics_summary.txt"),
+            ("launch_summary.py", ["r01_launches_step_b256.csv", "0", "--second-half"], "r01_launches_step_b256_summary.txt")):
+        cmd = [sys.executable, os.path.join(ROOT, "tools", tool), os.path.join(prof, args[0])] + args[1:]
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=120)
+        assert out.returncode == 0, out.stderr
+        want = [l.rstrip() for l in open(os.path.join(prof, summary)).read().strip().splitlines()]
+        got = [l.rstrip() for l in out.stdout.strip().splitlines()]
+        assert got[:len(want)] == want or want[:len(got)] == got, (tool, got[:3], want[:3])
+        assert any("wgrad_tc_kernel" in l for l in got[:3])          # the largest share of the step, as DESIGN.md says
