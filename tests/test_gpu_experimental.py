@@ -77,3 +77,56 @@ def test_wgrad_f16_matches_autograd(B, L, groups, cin_g, taps):
         assert float((dw - 2 * ref).abs().max()) < 2 * tol
     finally:
         torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = a, b
+
+
+def _pack_f16(w, groups):
+    """Conv1d weight (groups*N, K, taps) -> the fp16 operand packing of the plan's batch packer (flag bit 2):
+    [g][tap][K/64][8][N][8 halves], a 16-byte slot = 8 consecutive input channels of one output channel."""
+    GN, K, taps = w.shape
+    n = GN // groups
+    v = w.view(groups, n, K // 64, 8, 8, taps).permute(0, 5, 2, 3, 1, 4).contiguous()
+    return v.half().view(-1)
+
+
+@pytest.mark.parametrize("B,L,groups,cin_g,cout_g,taps", [(3, 100, 2, 128, 128, 7), (4, 333, 3, 64, 128, 3), (16, 1250, 2, 128, 128, 7)])
+def test_fp16_operand_conv_and_its_data_gradient(B, L, groups, cin_g, cout_g, taps):
+    """The production conv kernel with fp16 operand copies (NefConvTerm.x_f16) at op level -- forward, and the same kernel in the
+    data-gradient direction (flipped / transposed weights, dY16 as the operand), which is the route the fp16 backward takes."""
+    from network import _native as N, ops
+    dev = torch.device("cuda:0")
+    N.init(0)
+    a, b = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        gen = torch.Generator(device="cpu").manual_seed(B + L + taps)
+        x = torch.randn(B, groups * cin_g, L, generator=gen).half().float().to(dev).requires_grad_(True)
+        w = (torch.randn(groups * cout_g, cin_g, taps, generator=gen) * 0.05).half().float().to(dev)
+        dy = torch.randn(B, groups * cout_g, L, generator=gen).half().float().to(dev)
+        yref = F.conv1d(x, w, None, padding=taps // 2, groups=groups)
+        yref.backward(dy)
+
+        def run(inp, weight, cin, cout):
+            xt = ops.Cbl4(groups * cin, B, L, dev).from_ncl(inp)
+            keep, x16 = _half8(xt)
+            w16 = _pack_f16(weight, groups)
+            yt = ops.Cbl4(groups * cout, B, L, dev)
+            d = ops.conv_desc(xt, w16, yt, groups, cin, cout, taps)
+            t = d.term[0]
+            t.x, t.x_c4_off, t.x_c4_gstride, t.cin_g, t.x_f16 = x16.data_ptr(), 0, cin // 8, cin // 2, 1
+            ops.gconv_fwd(d)
+            torch.cuda.synchronize()
+            return yt.to_ncl()
+
+        y = run(x.detach(), w, cin_g, cout_g)
+        tol = 5e-4 * float(yref.abs().max())
+        print("fp16 conv fwd: max err %.3e (bar %.3e)" % (float((y - yref).abs().max()), tol))
+        assert float((y - yref).abs().max()) < tol
+        # data gradient = the same convolution of dY with wd[g*cin + n, m, t] = w[g*cout + m, n, taps-1-t]
+        wd = w.view(groups, cout_g, cin_g, taps).flip(3).permute(0, 2, 1, 3).reshape(groups * cin_g, cout_g, taps).contiguous()
+        dx = run(dy, wd, cout_g, cin_g)
+        tol = 5e-4 * float(x.grad.abs().max())
+        print("fp16 conv dgrad: max err %.3e (bar %.3e)" % (float((dx - x.grad).abs().max()), tol))
+        assert float((dx - x.grad).abs().max()) < tol
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = a, b
