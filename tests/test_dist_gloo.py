@@ -109,3 +109,25 @@ def test_allreduce_is_a_noop_without_a_process_group():
     h = _FlatHolder({"a": torch.ones(5)}, ["a"])
     allreduce_gradients(h)
     assert float(h.flat_grads.sum()) == 5.0
+
+
+@pytest.mark.timeout(600)
+def test_reference_arm_under_torchrun_prints_one_line_from_rank_0():
+    """bench.py --impl reference launched the way the driver launches it for N > 1: rank 0 alone times the CPU arm and prints
+    ONE JSON line, the other rank exits 0 without work (and without importing torch.distributed)."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", str(_free_port()), os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2",
+           "--steps", "1", "--warmup", "0", "--length", "512", "--ref-batch", "2"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=500, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, lines
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["steps"] == 1 and d["unit"] == "segments/s"
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["value"] > 0
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "NCCL" in d["config"]["workload"] and d["higher_is_better"] is True
