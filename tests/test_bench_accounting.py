@@ -57,3 +57,15 @@ def test_profile_summaries_regenerate_from_the_committed_launch_lists():
         got = [l.rstrip() for l in out.stdout.strip().splitlines()]
         assert got[:len(want)] == want or want[:len(got)] == got, (tool, got[:3], want[:3])
         assert any("wgrad_tc_kernel" in l for l in got[:3])          # the largest share of the step, as DESIGN.md says
+
+
+def test_bench_without_a_gpu_fails_loudly():
+    """The product arm has no CPU fallback: without a CUDA device bench.py exits non-zero and says so (it does not quietly time
+    the oracle)."""
+    import subprocess
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "0"], capture_output=True,
+                       text=True, timeout=300, cwd=ROOT)
+    assert r.returncode != 0 and "no CUDA device" in (r.stderr + r.stdout) and not r.stdout.strip().startswith("{")
