@@ -144,3 +144,31 @@ def test_launcher_substitutes_network_only(tmp_path):
                        capture_output=True, text=True, timeout=300, cwd=str(codes))
     assert r.returncode == 0, r.stdout + r.stderr
     assert os.path.join(PKG, "network") in r.stdout and " 1 2 ['--config-file', 'config/nef_net.yml'] __main__" in r.stdout
+
+
+def test_in_package_backend_switch(tmp_path):
+    """The reference-side variant INTEGRATION.md shows: a few lines at the top of codes/network/__init__.py hand the import
+    over to this package when NEFNET_BACKEND=b200 (Python re-reads sys.modules after the package body ran)."""
+    codes = tmp_path / "codes"
+    (codes / "network").mkdir(parents=True)
+    (codes / "utils").mkdir()
+    (codes / "utils" / "__init__.py").write_text("X = 1\n")
+    (codes / "network" / "__init__.py").write_text(
+        "import os, sys\n"
+        "if os.environ.get('NEFNET_BACKEND') == 'b200':\n"
+        "    sys.path.append(os.environ['NEFNET_B200_DIR'])\n"
+        "    del sys.modules['network']\n"
+        "    import dropin; dropin.install()\n"
+        "    from network import build_model, build_loss\n"
+        "else:\n"
+        "    def build_model(cfg):\n        return 'reference'\n")
+    (codes / "main.py").write_text("from network import build_model\nimport network, utils\n"
+                                   "print(network.__file__, build_model.__module__, utils.X)\n")
+    env = dict(os.environ, NEFNET_BACKEND="b200", NEFNET_B200_DIR=PKG)
+    env.pop("PYTHONPATH", None)
+    r = subprocess.run([sys.executable, "main.py"], capture_output=True, text=True, timeout=300, cwd=str(codes), env=env)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert os.path.join(PKG, "network") in r.stdout and " network 1" in r.stdout
+    env.pop("NEFNET_BACKEND")
+    r = subprocess.run([sys.executable, "main.py"], capture_output=True, text=True, timeout=300, cwd=str(codes), env=env)
+    assert r.returncode == 0 and str(codes) in r.stdout            # without the switch the tree's own package is used
