@@ -208,6 +208,30 @@ def theta_features(theta: torch.Tensor) -> torch.Tensor:
     return feat.reshape(*theta.shape[:-1], 12)
 
 
+# ----------------------------------------------------------------------------------------
+# optional arithmetic model ("prec"): None = plain fp32, the reference's arithmetic.  An object with
+# conv / store / pre hooks (oracle/b200_precision.py) restates WHERE the B200 path rounds (operands of the
+# tensor-core convolutions, stored activations, stored gradients), so that tests can separate precision
+# effects (ReLU masks that flip within rounding distance of zero) from logic errors.
+# ----------------------------------------------------------------------------------------
+def _conv(prec, kind, x, w, b=None, **kw):
+    """F.conv1d as the reference evaluates it (fp32), or as `prec` models the device's operand rounding.
+    kind: 'fp16' (encoder k7 convs), 'tf32' (every other grouped / decoder conv), 'fp32' (CUDA-core / split-precision)."""
+    if prec is None:
+        return F.conv1d(x, w, b, **kw)
+    return prec.conv(kind, x, w, b, **kw)
+
+
+def _st(prec, x):
+    """a stored activation (the device rounds most of them to TF32 when it writes them)"""
+    return x if prec is None else prec.store(x)
+
+
+def _pre(prec, x):
+    """a pre-activation whose GRADIENT the device stores rounded (identity in the forward direction)"""
+    return x if prec is None else prec.pre(x)
+
+
 def _maybe_drop(h: torch.Tensor, keep: Optional[torch.Tensor], p: float) -> torch.Tensor:
     """nn.Dropout(0.2) of the residual blocks (resnet_1d.py:37,45; model_nefnet.py:46,52).  The
     oracle takes the keep-mask explicitly (None = dropout disabled) so that parity can be
@@ -217,29 +241,34 @@ def _maybe_drop(h: torch.Tensor, keep: Optional[torch.Tensor], p: float) -> torc
     return h * keep.to(h.dtype) / (1.0 - p)
 
 
-def residual_block(x, w1, w2, groups, res_w=None, res_b=None, keep=None, p=0.2):
+def residual_block(x, w1, w2, groups, res_w=None, res_b=None, keep=None, p=0.2, prec=None, kind="tf32", scale=None):
     """conv -> ReLU -> Dropout -> conv -> (+ 1x1 residual conv iff channel counts differ) -> add
-    -> ReLU.  resnet_1d.py:39-53 (k=7, identity residual) and model_nefnet.py:48-60 (k=3)."""
+    -> ReLU.  resnet_1d.py:39-53 (k=7, identity residual) and model_nefnet.py:48-60 (k=3).
+    scale: optional per-(segment, channel) factor applied to the block output (the angular scaling of
+    model_nefnet.py:120-123, which the device fuses into the last encoder block's epilogue)."""
     pad = w1.shape[2] // 2
-    h = F.relu(F.conv1d(x, w1, padding=pad, groups=groups))
-    h = _maybe_drop(h, keep, p)
-    y = F.conv1d(h, w2, padding=pad, groups=groups)
+    h = F.relu(_pre(prec, _conv(prec, kind, x, w1, padding=pad, groups=groups)))
+    h = _st(prec, _maybe_drop(h, keep, p))
+    y = _conv(prec, kind, h, w2, padding=pad, groups=groups)
     if y.shape[1] != x.shape[1]:
-        r = F.conv1d(x, res_w, res_b, groups=groups)
+        r = _conv(prec, "tf32", x, res_w, res_b, groups=groups)
     else:
         r = x
-    return F.relu(y + r)
+    y = F.relu(_pre(prec, y + r))
+    if scale is not None:
+        y = y * scale
+    return _st(prec, y)
 
 
-def encoder(P, x, G, keeps=None):
+def encoder(P, x, G, keeps=None, prec=None, out_scale=None):
     """encoder/encoder.py:28-40 with resnet_1d.py:102-105: grouped stem k15 s2 p7 -> ReLU ->
-    MaxPool(3,2,1) -> three k7 residual blocks."""
-    h = F.conv1d(x, P["W_encoder.conv1.weight"], stride=2, padding=7, groups=G)
-    h = F.max_pool1d(F.relu(h), kernel_size=3, stride=2, padding=1)
+    MaxPool(3,2,1) -> three k7 residual blocks.  out_scale: see residual_block (last block)."""
+    h = _conv(prec, "fp32", x, P["W_encoder.conv1.weight"], stride=2, padding=7, groups=G)
+    h = _st(prec, F.max_pool1d(F.relu(h), kernel_size=3, stride=2, padding=1))
     for i in range(3):
         keep = None if keeps is None else keeps.get(f"W_encoder.layer1.{i}")
         h = residual_block(h, P[f"W_encoder.layer1.{i}.conv1.weight"], P[f"W_encoder.layer1.{i}.conv2.weight"], G,
-                           keep=keep)
+                           keep=keep, prec=prec, kind="fp16", scale=out_scale if i == 2 else None)
     return h
 
 
@@ -299,46 +328,62 @@ def _bn(x, P, prefix, training, stats_out):
     return y
 
 
-def decoder(P, lat, training, stats_out=None):
+def decoder(P, lat, training, stats_out=None, prec=None):
     """model_nefnet.py:101-107: Upsample x2 -> DoubleConv(256,128) -> Upsample x2 ->
     DoubleConv(128,64) -> Conv1d(64,1,3); then sigmoid(x/3) (:168)."""
     h = F.interpolate(lat, scale_factor=2, mode="linear", align_corners=False)
+    first = True
     for stage in ("decoder.1", "decoder.3"):
         for conv, bn in (("0", "1"), ("3", "4")):
             pre = f"{stage}.double_conv."
-            h = F.conv1d(h, P[pre + conv + ".weight"], P[pre + conv + ".bias"], padding=1)
+            # the device evaluates the first convolution split-precision (x_hi w_hi + x_lo w_hi + x_hi w_lo): fp32-like
+            h = _pre(prec, _conv(prec, "fp32" if first else "tf32", h, P[pre + conv + ".weight"], P[pre + conv + ".bias"],
+                                 padding=1))
+            first = False
             h = F.relu(_bn(h, P, pre + bn, training, stats_out))
+            if conv == "0":          # stored (rounded) as the next convolution's operand; after the second conv of a stage the
+                h = _st(prec, h)     # device stores the UPSAMPLED tensor (decoder.1) or feeds the fp32 output kernel (decoder.3)
         if stage == "decoder.1":
-            h = F.interpolate(h, scale_factor=2, mode="linear", align_corners=False)
-    h = F.conv1d(h, P["decoder.4.weight"], P["decoder.4.bias"], padding=1)
+            h = _st(prec, F.interpolate(h, scale_factor=2, mode="linear", align_corners=False))
+    h = _conv(prec, "fp32", h, P["decoder.4.weight"], P["decoder.4.bias"], padding=1)
     return torch.sigmoid(h / 3)
 
 
-def latents(P, x, input_thetas, rois, G, keeps=None, stop_before_reverse=False):
+def latents(P, x, input_thetas, rois, G, keeps=None, stop_before_reverse=False, prec=None):
     """model_nefnet.py:117-143: encoder, input-view angular scaling, w_conv, z1/z2 split,
     z1_conv, z2_conv1, roi_algin, z2_conv2 chain, roi_pooling_reverse."""
     kp = (lambda n: None) if keeps is None else keeps.get
     B = x.shape[0]
-    w = encoder(P, x, G, keeps)  # (B,128G,L4)
-    L4 = w.shape[-1]
     enc = F.linear(theta_features(input_thetas), P["mlp1.weight"], P["mlp1.bias"])  # (B,G,128) :118,121
-    w = (w.view(B, G, 128, L4) * enc[..., None]).view(B, 128 * G, L4)  # :122-123
-    w = residual_block(w, P["w_conv.0.conv1.weight"], P["w_conv.0.conv2.weight"], G, keep=kp("w_conv.0"))  # :124
+    if prec is None:
+        w = encoder(P, x, G, keeps)  # (B,128G,L4)
+        L4 = w.shape[-1]
+        w = (w.view(B, G, 128, L4) * enc[..., None]).view(B, 128 * G, L4)  # :122-123
+    else:  # the device applies the scale in the last encoder block's epilogue, before the stored value is rounded
+        w = encoder(P, x, G, keeps, prec=prec, out_scale=enc.reshape(B, 128 * G, 1))
+        L4 = w.shape[-1]
+    w = residual_block(w, P["w_conv.0.conv1.weight"], P["w_conv.0.conv2.weight"], G, keep=kp("w_conv.0"), prec=prec)  # :124
     w = w.view(B, G, 2, 64, L4)  # :125-131 each lead's 128 ch -> (z1 half, z2 half)
     z1 = w[:, :, 0].reshape(B, 64 * G, L4)
     z2 = w[:, :, 1].reshape(B, 64 * G, L4)
     z1 = residual_block(z1, P["z1_conv.0.conv1.weight"], P["z1_conv.0.conv2.weight"], G,
-                        P["z1_conv.0.residual_conv.weight"], P["z1_conv.0.residual_conv.bias"], keep=kp("z1_conv.0"))
+                        P["z1_conv.0.residual_conv.weight"], P["z1_conv.0.residual_conv.bias"], keep=kp("z1_conv.0"),
+                        prec=prec)
     z2 = residual_block(z2, P["z2_conv1.0.conv1.weight"], P["z2_conv1.0.conv2.weight"], G,
                         P["z2_conv1.0.residual_conv.weight"], P["z2_conv1.0.residual_conv.bias"],
-                        keep=kp("z2_conv1.0"))
-    z2 = roi_align_center(z2, rois)  # (B,128G,7,16) :136
+                        keep=kp("z2_conv1.0"), prec=prec)
+    z2 = _st(prec, roi_align_center(z2, rois))  # (B,128G,7,16) :136
     z2 = z2.reshape(B, 128 * G * N_ROI, ROI_SIZE)  # :137
-    z2 = residual_block(z2, P["z2_conv2.0.conv1.weight"], P["z2_conv2.0.conv2.weight"], 7 * G, keep=kp("z2_conv2.0"))
-    z2 = F.conv_transpose1d(z2, P["z2_conv2.1.weight"], P["z2_conv2.1.bias"], stride=2, groups=7 * G)
+    z2 = residual_block(z2, P["z2_conv2.0.conv1.weight"], P["z2_conv2.0.conv2.weight"], 7 * G, keep=kp("z2_conv2.0"),
+                        prec=prec)
+    if prec is None:
+        z2 = F.conv_transpose1d(z2, P["z2_conv2.1.weight"], P["z2_conv2.1.bias"], stride=2, groups=7 * G)
+    else:
+        z2 = _st(prec, _pre(prec, prec.conv_transpose(z2, P["z2_conv2.1.weight"], P["z2_conv2.1.bias"], stride=2,
+                                                      groups=7 * G)))
     z2 = residual_block(z2, P["z2_conv2.2.conv1.weight"], P["z2_conv2.2.conv2.weight"], 7 * G,
                         P["z2_conv2.2.residual_conv.weight"], P["z2_conv2.2.residual_conv.bias"],
-                        keep=kp("z2_conv2.2"))
+                        keep=kp("z2_conv2.2"), prec=prec)
     z2 = z2.view(B, 128 * G, N_ROI, 2 * ROI_SIZE)  # :138
     if stop_before_reverse:
         return z1, z2
@@ -347,15 +392,15 @@ def latents(P, x, input_thetas, rois, G, keeps=None, stop_before_reverse=False):
 
 
 def forward(P, x, input_thetas, query_theta, rois, rest_theta=None, phase="train", lead_choice=(0, 0),
-            bn_training=True, keeps=None, stats_out=None):
+            bn_training=True, keeps=None, stats_out=None, prec=None):
     """Model_nefnet.forward, model_nefnet.py:109-194.  ``lead_choice`` are the two
     ``random.randint(0, G-1)`` draws (:154,156; z1 first).  ``stats_out``: dict of BN buffers
     updated in place (three sequential updates per train forward, in call order out, p, l)."""
     G = x.shape[1]
     B = x.shape[0]
     if phase == "gen":
-        return latents(P, x, input_thetas, rois, G, keeps, stop_before_reverse=True)  # :140-141
-    z1, z2 = latents(P, x, input_thetas, rois, G, keeps)
+        return latents(P, x, input_thetas, rois, G, keeps, stop_before_reverse=True, prec=prec)  # :140-141
+    z1, z2 = latents(P, x, input_thetas, rois, G, keeps, prec=prec)
     L4 = z1.shape[-1]
     z1g, z2g = z1.view(B, G, 128, L4), z2.view(B, G, 128, L4)
     z1_mean, z2_mean = z1g.mean(dim=1), z2g.mean(dim=1)  # :146-149
@@ -364,12 +409,12 @@ def forward(P, x, input_thetas, query_theta, rois, rest_theta=None, phase="train
     lat_p = torch.cat([z1g[:, c1], z2_mean], dim=1)  # :159
     lat_l = torch.cat([z1_mean, z2g[:, c2]], dim=1)  # :160
     q = F.linear(theta_features(query_theta).view(B, -1), P["mlp2.weight"], P["mlp2.bias"])  # :163-164
-    outs = [decoder(P, q[:, :, None] * lat, bn_training, stats_out) for lat in (lat_all, lat_p, lat_l)]  # :166-176
+    outs = [decoder(P, q[:, :, None] * lat, bn_training, stats_out, prec) for lat in (lat_all, lat_p, lat_l)]  # :166-176
     if phase == "train":
         return tuple(outs)
     if phase in ("val", "test"):
         rq = F.linear(theta_features(rest_theta), P["mlp2.weight"], P["mlp2.bias"])  # (B,V,256) :182-183
-        rest = [decoder(P, rq[:, v, :, None] * lat_all, bn_training, stats_out) for v in range(rq.shape[1])]
+        rest = [decoder(P, rq[:, v, :, None] * lat_all, bn_training, stats_out, prec) for v in range(rq.shape[1])]
         return tuple(outs) + (torch.cat(rest, dim=1),)  # :185-192
     raise KeyError("please type correct phase")  # :194
 
