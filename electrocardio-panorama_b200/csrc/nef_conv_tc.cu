@@ -231,6 +231,7 @@ constexpr int EPI_BIAS = 1, EPI_RES = 2, EPI_RELU = 4, EPI_DROP = 8, EPI_MASK1 =
 constexpr int EPI_MASK2 = 128, EPI_BSCALE = 256, EPI_STATS = 512;  // mask mode 2, angular scale, BatchNorm partial statistics
 constexpr int EPI_OBITS = 1024, EPI_MBITS = 2048;                  // write / read one-bit activation masks
 constexpr int EPI_Y16 = 4096;                                      // also store an fp16 copy of the output (next conv's operand)
+constexpr int EPI_GSCALE = 8192;   // backward pass with loss-scaled fp16 copies: acc *= acc_scale[0]; y16 = fp16(v * y16_scale[0])
 
 // Sum over the 32 lanes of 32 per-lane values at once: after the 5 exchange levels lane j holds the warp total of a[j].
 // 31 shuffles instead of 32 x 5.
@@ -284,6 +285,10 @@ __device__ __forceinline__ void epilogue_tile(const NefConvDesc& d, int g, long 
   const bool f_y16 = GEN ? d.y16 != nullptr : (EPI & EPI_Y16) != 0;
   const bool f_obits = GEN ? d.out_bits != nullptr : (EPI & EPI_OBITS) != 0;
   const bool f_mbits = GEN ? (d.mask_bits != nullptr && d.mask_mode != 0) : (EPI & EPI_MBITS) != 0;
+  const bool f_gs = GEN ? (d.acc_scale != nullptr || d.y16_scale != nullptr) : (EPI & EPI_GSCALE) != 0;
+  const float acc_sc = (f_gs && d.acc_scale) ? __ldg(d.acc_scale) : 1.f;
+  const float y16_sc = (f_gs && d.y16_scale) ? __ldg(d.y16_scale) : 1.f;
+  const bool store_y = d.y != nullptr;   // NULL: only the fp16 copy (and the bit plane) of the result is kept
   // mask operand: 0 none, 1 / 2 float tensor (> 0 / != 0), 3 one-bit masks
   const int mask_mode = f_mbits ? 3 : (GEN ? d.mask_mode : ((EPI & EPI_MASK1) ? 1 : ((EPI & EPI_MASK2) ? 2 : 0)));
   const float mask_scale = d.mask_scale;
@@ -333,6 +338,7 @@ __device__ __forceinline__ void epilogue_tile(const NefConvDesc& d, int g, long 
         const int n4 = cg * 8 + i;
         float4 x = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]),
                                __uint_as_float(v[4 * i + 3]));
+        if (f_gs) x = x * acc_sc;
         if (f_bias) x = x + __ldg(bias4 + n4);
         x = x + rr[i];
         const float4 pre = x;
@@ -381,10 +387,11 @@ __device__ __forceinline__ void epilogue_tile(const NefConvDesc& d, int g, long 
                           (mb & 4u) ? x.z * mask_scale : 0.f, (mb & 8u) ? x.w * mask_scale : 0.f);
         }
         if (f_round) x = rn4_tf32(x);
-        if (er.valid) yp[(long)n4 * d.y_cstride] = x;
+        if (er.valid && store_y) yp[(long)n4 * d.y_cstride] = x;
         if (f_y16) {  // chunks n4 = 2m, 2m + 1 form the 8-channel fp16 chunk m
-          h16[(i & 1) * 2 + 0] = pack_f16x2(x.x, x.y);
-          h16[(i & 1) * 2 + 1] = pack_f16x2(x.z, x.w);
+          const float4 xs = f_gs ? x * y16_sc : x;
+          h16[(i & 1) * 2 + 0] = pack_f16x2(xs.x, xs.y);
+          h16[(i & 1) * 2 + 1] = pack_f16x2(xs.z, xs.w);
           if ((i & 1) && er.valid) y16p[(long)(n4 >> 1) * d.y_cstride] = make_uint4(h16[0], h16[1], h16[2], h16[3]);
         }
         if (f_obits)
@@ -1039,11 +1046,13 @@ static int g_sm_count = 148;
 static int g_tc_stagger = -1;  // first-wave start stagger in cycles; -1 = one estimated CTA lifetime (NEF_TC_STAGGER)
 static int g_tc_ws = 0;   // 1 = weight-stationary MMA form (NEF_TC_WS)
 static int g_tc_persist = 1;  // persistent forward kernel (NEF_TC_PERSIST=0: one CTA per tile)
+static int g_tc_persist_min = 0;  // row-tile x group count from which the persistent kernel is used; 0 = 2 x SM count
+extern "C" int nef_tc_set_persist_min(int tiles) { g_tc_persist_min = tiles; return 0; }  // test hook: 1 = always persistent
 static int g_tc_mt = 0;  // 0 = automatic; 4 forces four row tiles per CTA, one CTA per SM (NEF_TC_MT, for A/B measurements)
 
 // the specialised epilogues instantiated for the 4-row-tile kernel (everything else takes the generic one)
 #define NEF_TC_EPI_LIST(X) X(0) X(2) X(5) X(32) X(33) X(36) X(37) X(38) X(44) X(48) X(50) X(64) X(294) X(418) X(513) \
-  X(1062) X(1068) X(1318) X(2080) X(2082) X(2338) X(5158) X(5164)
+  X(1062) X(1068) X(1318) X(2080) X(2082) X(2338) X(5158) X(5164) X(5414) X(14368) X(14370) X(14626)
 
 template <int MT, int EPI>
 static int tc_optin() {
@@ -1071,6 +1080,27 @@ extern "C" int nef_tc_init(void) {
   return 0;
 }
 
+// Dispatch record (test hook, nef_tc_dispatch_stats): which kernel forms and which specialised epilogues have been launched, so
+// that a parity test can assert that it exercised the dispatch the benchmark times.
+static long long g_disp[8];           // 0 persistent, 1 one-CTA-per-tile (MT 2 / 4), 2 single-tile generic, 3 wgrad_tc, 4 wgrad simt tail, 5 wgrad_f16
+static int g_disp_epi[64], g_disp_nepi = 0;   // distinct EPI codes launched through the persistent kernel
+static void note_persist_epi(int e) {
+  for (int i = 0; i < g_disp_nepi; ++i)
+    if (g_disp_epi[i] == e) return;
+  if (g_disp_nepi < 64) g_disp_epi[g_disp_nepi++] = e;
+}
+extern "C" void nef_tc_note_dispatch(int which) { __atomic_add_fetch(&g_disp[which & 7], 1, __ATOMIC_RELAXED); }
+extern "C" int nef_tc_dispatch_stats(int64_t* out, int n) {
+  for (int i = 0; i < n; ++i) out[i] = -1;
+  for (int i = 0; i < 8 && i < n; ++i) out[i] = g_disp[i];
+  for (int i = 0; i < g_disp_nepi && 8 + i < n; ++i) out[8 + i] = g_disp_epi[i];
+  return g_disp_nepi;
+}
+extern "C" void nef_tc_dispatch_reset(void) {
+  for (int i = 0; i < 8; ++i) g_disp[i] = 0;
+  g_disp_nepi = 0;
+}
+
 static int epi_code(const NefConvDesc* d) {
   if (d->bscale_grad) return tc::EPI_GENERIC;
   int e = 0;
@@ -1081,6 +1111,7 @@ static int epi_code(const NefConvDesc* d) {
   if (mbits) e |= tc::EPI_MBITS;
   if (d->out_bits) e |= tc::EPI_OBITS;
   if (d->y16) e |= tc::EPI_Y16;
+  if (d->acc_scale || d->y16_scale) e |= tc::EPI_GSCALE;
   if (d->bias) e |= tc::EPI_BIAS;
   if (d->res) e |= tc::EPI_RES;
   if (d->relu) e |= tc::EPI_RELU;
@@ -1112,6 +1143,15 @@ static int launch_conv_persist(const NefConvDesc* d, cudaStream_t s) {
   const int tpg = (int)((d->rows + 255) / 256);
   const int n_tiles = tpg * d->groups;
   const int grid = n_tiles < g_sm_count ? n_tiles : g_sm_count;
+  bool specialised = false;
+  switch (epi_code(d)) {
+#define X(E) case E: specialised = true; break;
+    NEF_TC_EPI_LIST(X)
+#undef X
+    default: break;
+  }
+  nef_tc_note_dispatch(0);
+  note_persist_epi(specialised ? epi_code(d) : tc::EPI_GENERIC);
   switch (epi_code(d)) {
 #define X(E) case E: tc::conv_tc_persist_kernel<E><<<grid, tc::FW_THREADS, tc::PsSmem::TOTAL, s>>>(*d, tpg, n_tiles, g_tc_ws); break;
     NEF_TC_EPI_LIST(X)
@@ -1123,7 +1163,8 @@ static int launch_conv_persist(const NefConvDesc* d, cudaStream_t s) {
 
 extern "C" int nef_gconv_fwd_tc(const NefConvDesc* d, nef_stream_t s) {
   const long tiles4 = (d->rows + 511) / 512, tiles2 = (d->rows + 255) / 256;
-  if (g_tc_persist && g_tc_mt == 0 && tiles2 * d->groups >= 2L * g_sm_count) {
+  const long persist_min = g_tc_persist_min > 0 ? g_tc_persist_min : 2L * g_sm_count;
+  if (g_tc_persist && g_tc_mt == 0 && tiles2 * d->groups >= persist_min) {
     launch_conv_persist(d, (cudaStream_t)s);
     NEF_CHECK_LAUNCH("conv_tc_persist_kernel");
     return 0;
@@ -1131,6 +1172,7 @@ extern "C" int nef_gconv_fwd_tc(const NefConvDesc* d, nef_stream_t s) {
   int mt = 1;  // small row spaces (the z2 deflection branch at small batch): one 128-row tile per CTA keeps the grid wide
   if (tiles2 * d->groups >= 2L * g_sm_count) mt = 2;
   if (g_tc_mt == 4 && tiles4 * d->groups >= g_sm_count) mt = 4;
+  nef_tc_note_dispatch(mt == 1 ? 2 : 1);
   if (mt == 2) launch_conv_tc<2>(d, (cudaStream_t)s);
   else if (mt == 4) launch_conv_tc<4>(d, (cudaStream_t)s);
   else {
@@ -1179,12 +1221,14 @@ extern "C" int nef_gconv_wgrad_tc(const NefWgradDesc* d, nef_stream_t s) {
     dim3 grid((unsigned)halves, (unsigned)splits, (unsigned)ztiles);
     tc::wgrad_tc_kernel<<<grid, tc::WG_THREADS, tc::WG_TOTAL, (cudaStream_t)s>>>(*d, NT, st_per_split * tc::WG_RROWS, rows_main, swap ? 1 : (wide ? 2 : 0));
     NEF_CHECK_LAUNCH("wgrad_tc_kernel");
+    nef_tc_note_dispatch(3);
   }
   if (rows_main < d->rows) {  // ragged tail (< 64 rows): CUDA-core kernel over [rows_main, rows), no bias term
     NefWgradDesc t = *d;
     t.db = nullptr;
     int rc = nef_gconv_wgrad_simt_range(&t, rows_main, s);
     if (rc) return rc;
+    nef_tc_note_dispatch(4);
   }
   if (d->db) {
     long splits = (d->rows + 4095) / 4096;

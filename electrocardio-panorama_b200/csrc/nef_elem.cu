@@ -328,18 +328,29 @@ __global__ void window_extract_kernel(T4 w, T4 xw, int G, Window win) {
   }
 }
 
-__global__ void window_scatter_kernel(T4 gxw, T4 gw, int G, Window win) {
-  const long total = (long)G * 16 * gw.B * gw.L;
+// One thread per (pair of 4-channel chunks, segment, position) of the z2 half, so that the optional loss-scaled fp16 copy
+// (8 channels per 16-byte row) is written by the same thread.
+__global__ void window_scatter_kernel(T4 gxw, T4 gw, int G, Window win, uint4* __restrict__ gw16, const float* __restrict__ s16) {
+  const long total = (long)G * 8 * gw.B * gw.L;
+  const float sc = (gw16 && s16) ? __ldg(s16) : 1.f;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     const int l = i % gw.L;
     long r = i / gw.L;
     const int b = r % gw.B;
-    const int c = r / gw.B;
-    const int g = c / 16, cc = c % 16;
+    const int c2 = r / gw.B;              // pair index among G * 8
+    const int g = c2 / 8, cc = (c2 % 8) * 2;
     const int lw = l - win.w0;
-    float4 v = f4zero();
-    if (lw >= 0 && lw < win.Lw) v = *gxw.at(c, b, lw);
-    *gw.at(g * 32 + 16 + cc, b, l) = v;
+    float4 v0 = f4zero(), v1 = f4zero();
+    if (lw >= 0 && lw < win.Lw) {
+      v0 = *gxw.at(g * 16 + cc, b, lw);
+      v1 = *gxw.at(g * 16 + cc + 1, b, lw);
+    }
+    *gw.at(g * 32 + 16 + cc, b, l) = v0;
+    *gw.at(g * 32 + 16 + cc + 1, b, l) = v1;
+    if (gw16)
+      gw16[(long)((g * 32 + 16 + cc) >> 1) * gw.cs + gw.row(b, l)] =
+          make_uint4(f16x2_sat(v0.x * sc, v0.y * sc), f16x2_sat(v0.z * sc, v0.w * sc), f16x2_sat(v1.x * sc, v1.y * sc),
+                     f16x2_sat(v1.z * sc, v1.w * sc));
   }
 }
 
@@ -349,9 +360,9 @@ int window_extract(T4 w, T4 xw, int G, Window win, cudaStream_t s) {
   NEF_CHECK_LAUNCH("window_extract_kernel");
   return 0;
 }
-int window_scatter(T4 gxw, T4 gw, int G, Window win, cudaStream_t s) {
-  const long total = (long)G * 16 * gw.B * gw.L;
-  window_scatter_kernel<<<grid_for(total, 256), 256, 0, s>>>(gxw, gw, G, win);
+int window_scatter(T4 gxw, T4 gw, int G, Window win, void* gw16, const float* s16, cudaStream_t s) {
+  const long total = (long)G * 8 * gw.B * gw.L;
+  window_scatter_kernel<<<grid_for(total, 256), 256, 0, s>>>(gxw, gw, G, win, reinterpret_cast<uint4*>(gw16), s16);
   NEF_CHECK_LAUNCH("window_scatter_kernel");
   return 0;
 }
@@ -1233,6 +1244,34 @@ __global__ void loss_bwd_kernel(const float* __restrict__ o, const float* __rest
     }
   }
 }
+// Loss scale of the fp16 gradient copies: S = 2^k with S * max|upstream gradient| in [32, 64)  (the largest back-propagated
+// gradient of the network is within ~50x of the upstream one, DESIGN.md: 20x headroom under 65504; conversions saturate).
+__global__ void __launch_bounds__(256) grad_amax_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                        const float* __restrict__ c, long n, unsigned int* amax_bits) {
+  float m = 0.f;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    if (a) m = fmaxf(m, fabsf(a[i]));
+    if (b) m = fmaxf(m, fabsf(b[i]));
+    if (c) m = fmaxf(m, fabsf(c[i]));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(amax_bits, __float_as_uint(m));   // non-negative floats order like their bits
+}
+__global__ void grad_scale_finish_kernel(float* scale) {
+  const float m = scale[2];
+  float S = 1.f;
+  if (m > 0.f && m < 3.0e38f) {
+    int e;
+    frexpf(m, &e);                       // m = f * 2^e, f in [0.5, 1)  ->  m in [2^(e-1), 2^e)
+    int k = 6 - e;                       // S * m in [32, 64)
+    k = k < -60 ? -60 : (k > 60 ? 60 : k);
+    S = ldexpf(1.f, k);
+  }
+  scale[0] = S;
+  scale[1] = 1.f / S;
+}
+
 __global__ void pair_finish_kernel(const double* sum, long n, float* result) { result[0] = (float)(sum[2] / (double)n); }
 
 __global__ void sgd_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, long n, float lr,
@@ -1297,5 +1336,16 @@ extern "C" int nef_sgd_step(float* p, const float* g, float* m, int64_t n, float
   NEF_CHECK_LAUNCH("sgd_kernel");
   return 0;
 }
+
+namespace nef {
+int grad_loss_scale(const float* d0, const float* d1, const float* d2, long n, float* scale, cudaStream_t s) {
+  cudaMemsetAsync(scale + 2, 0, sizeof(float), s);
+  grad_amax_kernel<<<grid_for(n, 256, 148 * 4), 256, 0, s>>>(d0, d1, d2, n, reinterpret_cast<unsigned int*>(scale + 2));
+  NEF_CHECK_LAUNCH("grad_amax_kernel");
+  grad_scale_finish_kernel<<<1, 1, 0, s>>>(scale);
+  NEF_CHECK_LAUNCH("grad_scale_finish_kernel");
+  return 0;
+}
+}  // namespace nef
 
 NEF_DEFINE_EXACT_SETTER(nef_set_exact_elem)

@@ -59,6 +59,12 @@ static int g_dec1_terms = 3;
 // operand bytes).  Only the forward reads the copies; the backward pass keeps using the fp32 (TF32-rounded) tensors.
 static int g_fwd_f16 = 1;
 extern "C" int nef_set_fwd_f16(int on) { g_fwd_f16 = on; return 0; }
+// Backward pass on fp16 operand copies (needs the fp16 forward): the weight gradients of the big 128-channel layers read
+// loss-scaled fp16 copies of dY and fp16 copies of the saved activations MN-major, straight as the bulk copy lands them
+// (nef_gconv_wgrad_f16; the TF32 kernel has to re-tile every staged tile in shared memory).  0 = TF32 backward everywhere.
+static int g_bwd_f16 = 1;
+extern "C" int nef_set_bwd_f16(int on) { g_bwd_f16 = on; return 0; }
+extern "C" int nef_gconv_wgrad_f16(const NefWgradDesc* d, const void* dy16, const void* x16, const float* out_scale, nef_stream_t s);
 extern "C" int nef_set_dec1_terms(int n) {
   NEF_REQUIRE(n >= 1 && n <= 3, "nef_set_dec1_terms: 1, 2 or 3");
   g_dec1_terms = n;
@@ -205,7 +211,11 @@ struct NefPlan {
   // one-bit (value != 0) masks of the big post-ReLU activations, written by the forward epilogues and read by the masked
   // data-gradient epilogues instead of the fp32 tensors (NefConvDesc.out_bits / mask_bits)
   uint32_t *b_eh[3], *b_ey[3], *b_hw, *b_w, *b_h1;
-  void *s0_h, *eh_h[3], *ey_h[2];   // fp16 operand copies (8 channels per 16-byte row) of s0, eh[i], ey[0..1]
+  void *s0_h, *eh_h[3], *ey_h[3];   // fp16 operand copies (8 channels per 16-byte row) of s0, eh[i], ey[i]
+  void *hw_h, *w_h;                 //   ... of w_conv's h and y (operands of the fp16 weight gradients)
+  void* GA_h[3];                    // loss-scaled fp16 copies of the gradient buffers GA[i] (backward, bwd_f16)
+  float* lscale;                    // device scalars {S, 1 / S}: loss scale of the fp16 gradient copies; [2] = amax scratch
+  bool bwd_f16;                     // this forward / backward pair runs the fp16 weight gradients
   void *u0_h[3], *u0lo_h[3];        //   ... of the decoder inputs u0 and of their rounding residuals
   void* dec1_lo_h;                  // fp16 residual of the decoder first conv weights (decw[0].pk_h holds the fp16 weights)
   bool fwd_f16;                     // this forward runs the encoder convolutions on them
@@ -269,8 +279,10 @@ static void carve(NefPlan* p, bool dry) {
   p->hw = c.t4(C1, L4); p->w = c.t4(C1, L4); p->h1 = c.t4(C1, L4); p->z1 = c.t4(C1, L4);
   {
     const size_t bytes = ((size_t)(C1 / 8) * p->s0.cs + NEF_GUARD_ROWS) * 16;
-    void** hp[6] = {&p->s0_h, &p->eh_h[0], &p->eh_h[1], &p->eh_h[2], &p->ey_h[0], &p->ey_h[1]};
+    void** hp[12] = {&p->s0_h, &p->eh_h[0], &p->eh_h[1], &p->eh_h[2], &p->ey_h[0], &p->ey_h[1], &p->ey_h[2], &p->hw_h, &p->w_h,
+                     &p->GA_h[0], &p->GA_h[1], &p->GA_h[2]};
     for (auto q : hp) *q = c.take(bytes);
+    p->lscale = c.f32(4);
   }
   {
     const size_t words = (size_t)(C1 / 32) * p->s0.cs + NEF_GUARD_ROWS;
@@ -435,6 +447,7 @@ struct CD {
     return *this;
   }
   CD& y16(void* h) { d.y16 = h; return *this; }                     // also store the fp16 copy of the output
+  CD& y16s(void* h, const float* scale) { d.y16 = h; d.y16_scale = scale; return *this; }   // ... multiplied by scale[0] (device)
   CD& obits(uint32_t* b) { d.out_bits = b; return *this; }          // record (output != 0) bits next to the output
   CD& mbits(const uint32_t* b) { d.mask_bits = b; return *this; }   // read the mask from bits (same chunk offsets as .mask)
   CD& round() { d.round_tf32 = 1; return *this; }
@@ -546,15 +559,16 @@ struct BlockIO {
   int groups;
   uint32_t* hbits = nullptr;   // one-bit masks of h and y (big layers only)
   uint32_t* ybits = nullptr;
-  const void* x16 = nullptr;   // fp16 operand copies: when x16 is set the two convolutions run in kind::f16 and also
-  void* h16 = nullptr;         //   write h16 (required) and y16 (optional, the next block's x16)
-  void* y16 = nullptr;
+  const void* x16 = nullptr;   // fp16 operand copies: when x16 is set the two convolutions run in kind::f16 (h16 required)
+  void* h16 = nullptr;         // fp16 copies of h / y written by the epilogues (operands of the next convolution and / or of
+  void* y16 = nullptr;         //   the fp16 weight gradients); optional, also without x16
 };
 
 static int block_fwd(const BlockIO& io, float drop_p, uint64_t seed, const float* bscale, cudaStream_t s) {
   CD a(io.groups, 128, io.x);
-  if (io.x16) a.term16(io.x16, io.x.cs, io.x_off / 2, io.x_gs / 2, io.c1->cin_g, io.c1->taps, io.c1->pk_h).y16(io.h16);
+  if (io.x16) a.term16(io.x16, io.x.cs, io.x_off / 2, io.x_gs / 2, io.c1->cin_g, io.c1->taps, io.c1->pk_h);
   else a.term(io.x, io.x_off, io.x_gs, io.c1->cin_g, io.c1->taps, io.c1->pk_f);
+  if (io.h16) a.y16(io.h16);
   a.out(io.h, 0, 32).relu().round();
   if (io.hbits) a.obits(io.hbits);
   if (drop_p > 0.f) a.drop(drop_p, seed);
@@ -691,6 +705,7 @@ extern "C" int nef_forward(NefPlan* p, const NefForwardArgs* a, nef_stream_t sv)
   NefPackTable packs;
   packs.n = 0;
   p->fwd_f16 = g_fwd_f16 && g_conv_impl == 1;
+  p->bwd_f16 = p->fwd_f16 && g_bwd_f16 && a->save_for_backward;
   RUN(for_all_convw(p, [&](const ConvW& w) {
     if (&w >= p->decw && &w < p->decw + 4) return 0;
     if (p->fwd_f16 && w.pk_h)
@@ -714,13 +729,14 @@ extern "C" int nef_forward(NefPlan* p, const NefForwardArgs* a, nef_stream_t sv)
     if (p->fwd_f16) {
       io.x16 = i == 0 ? p->s0_h : p->ey_h[i - 1];
       io.h16 = p->eh_h[i];
-      io.y16 = i < 2 ? p->ey_h[i] : nullptr;
+      io.y16 = (i < 2 || p->bwd_f16) ? p->ey_h[i] : nullptr;
     }
     RUN(block_fwd(io, dp, seed + i, i == 2 ? p->s_in : nullptr, s));
   }
   {
     BlockIO io{p->ey[2], 0, 32, p->hw, p->w, &p->wc[0], &p->wc[1], nullptr, nullptr, G};
     if (a->save_for_backward) { io.hbits = p->b_hw; io.ybits = p->b_w; }
+    if (p->bwd_f16) { io.h16 = p->hw_h; io.y16 = p->w_h; }
     RUN(block_fwd(io, dp, seed + 3, nullptr, s));
   }
   {
@@ -786,16 +802,37 @@ struct BlockBwd {
   BlockIO io;
   T4 gy, gh;
   float *dw1, *dw2, *dwr, *dbr;
+  // fp16 backward (nullptr = the TF32 kernels): loss-scaled fp16 copies of gy (given) and gh (written here), the scale
+  // scalars {S, 1 / S}; the saved activations' fp16 copies are io.x16 / io.h16
+  const void* gy16 = nullptr;
+  void* gh16 = nullptr;
+  const float* lscale = nullptr;
 };
+// weight gradient from fp16 copies (same geometry arguments as wgrad_std; chunk offsets in 4-channel units)
+static int wgrad_h(const void* dy16, const T4& dy, int dy_off, int dy_gs, const void* x16, const T4& x, int x_off, int x_gs,
+                   const ConvW& w, float* dw, const float* inv_scale, cudaStream_t s) {
+  if (!dw) return 0;
+  NefWgradDesc d;
+  memset(&d, 0, sizeof(d));
+  d.dy_cstride = dy.cs; d.dy_c4_off = dy_off; d.dy_c4_gstride = dy_gs;
+  d.x_cstride = x.cs; d.x_c4_off = x_off; d.x_c4_gstride = x_gs;
+  d.cout_g = w.cout_g; d.cin_g = w.cin_g; d.groups = w.groups; d.taps = w.taps; d.tap_off = -(w.taps / 2);
+  d.rows = dy.cs; d.dw = dw;
+  d.sg = (int64_t)w.cout_g * w.cin_g * w.taps; d.sm = (int64_t)w.cin_g * w.taps; d.sn = w.taps; d.st = 1;
+  return nef_gconv_wgrad_f16(&d, dy16, x16, inv_scale, (nef_stream_t)s);
+}
 static int block_bwd(const BlockBwd& b, float drop_p, CD& fin, cudaStream_t s) {
   const BlockIO& io = b.io;
-  RUN(wgrad_std(b.gy, 0, 32, io.h, 0, 32, *io.c2, b.dw2, nullptr, s));
+  if (b.gy16 && io.h16) RUN(wgrad_h(b.gy16, b.gy, 0, 32, io.h16, io.h, 0, 32, *io.c2, b.dw2, b.lscale + 1, s));
+  else RUN(wgrad_std(b.gy, 0, 32, io.h, 0, 32, *io.c2, b.dw2, nullptr, s));
   if (io.cr) RUN(wgrad_std(b.gy, 0, 32, io.x, io.x_off, io.x_gs, *io.cr, b.dwr, b.dbr, s));
   CD a(io.groups, 128, io.x);
   a.term(b.gy, 0, 32, 128, io.c2->taps, io.c2->pk_d).out(b.gh, 0, 32).mask(io.h, 0, 32, 1, 1.f / (1.f - drop_p)).round();
   if (io.hbits) a.mbits(io.hbits);
+  if (b.gh16) a.y16s(b.gh16, b.lscale);
   RUN(a.run(s));
-  RUN(wgrad_std(b.gh, 0, 32, io.x, io.x_off, io.x_gs, *io.c1, b.dw1, nullptr, s));
+  if (b.gh16 && io.x16) RUN(wgrad_h(b.gh16, b.gh, 0, 32, io.x16, io.x, io.x_off, io.x_gs, *io.c1, b.dw1, b.lscale + 1, s));
+  else RUN(wgrad_std(b.gh, 0, 32, io.x, io.x_off, io.x_gs, *io.c1, b.dw1, nullptr, s));
   // gx = conv1^T(gh) + (identity: gy | 1x1: res^T(gy))
   fin.term(b.gh, 0, 32, 128, io.c1->taps, io.c1->pk_d);
   if (io.cr) fin.term(b.gy, 0, 32, 128, 1, io.cr->pk_d);
@@ -875,6 +912,9 @@ extern "C" int nef_backward(NefPlan* p, const NefBackwardArgs* a, nef_stream_t s
     for (int i = 0; i < 4; ++i) cudaMemsetAsync(p->dec[k].bn[i].s1, 0, 2 * 128 * sizeof(double), s);
 
   const float* douts[3] = {a->dout, a->dout_p, a->dout_l};
+  const bool f16 = p->bwd_f16 && g_conv_impl == 1;
+  const float* ls = p->lscale;
+  if (f16) RUN(grad_loss_scale(a->dout, a->dout_p, a->dout_l, (long)B * p->L, p->lscale, s));
   for (int k = 0; k < 3; ++k) {
     if (douts[k]) RUN(decoder_bwd(p, P, Gd, k, douts[k], s));
     else RUN(zero_t4(p->du0[k], s));
@@ -894,6 +934,10 @@ extern "C" int nef_backward(NefPlan* p, const NefBackwardArgs* a, nef_stream_t s
     bb.io.hbits = p->b_h1;
     CD fin(G, 64, p->w);
     fin.out(p->GA[2], 0, 32).mask(p->w, 0, 32, 1, 1.f).mbits(p->b_w).round();
+    if (f16) {   // conv1's weight gradient reads gh16 and the z1 half of w's fp16 copy; gy comes from latent_bwd (fp32 only)
+      bb.io.x16 = p->w_h; bb.gh16 = p->GA_h[1]; bb.lscale = ls;
+      fin.y16s(p->GA_h[2], ls);
+    }
     RUN(block_bwd(bb, dp, fin, s));
   }
   // ---- z2 branch
@@ -940,7 +984,7 @@ extern "C" int nef_backward(NefPlan* p, const NefBackwardArgs* a, nef_stream_t s
     fin.out(p->gxw, 0, 16).mask(p->xw, 0, 16, 1, 1.f).round();
     RUN(block_bwd(bb, dp, fin, s));
   }
-  RUN(window_scatter(p->gxw, p->GA[2], G, p->win, s));
+  RUN(window_scatter(p->gxw, p->GA[2], G, p->win, f16 ? p->GA_h[2] : nullptr, ls, s));
   // ---- w_conv: g_w = GA2, gh = GA0, result (grad of the unscaled last encoder output, pre-ReLU) = GA1
   {
     BlockBwd bb{{p->ey[2], 0, 32, p->hw, p->w, &p->wc[0], &p->wc[1], nullptr, nullptr, G}, p->GA[2], p->GA[0],
@@ -948,6 +992,10 @@ extern "C" int nef_backward(NefPlan* p, const NefBackwardArgs* a, nef_stream_t s
     bb.io.hbits = p->b_hw;
     CD fin(G, 128, p->ey[2]);
     fin.out(p->GA[1], 0, 32).bscale(p->s_in).mask(p->ey[2], 0, 32, 2, 1.f).mbits(p->b_ey[2]).round();
+    if (f16) {
+      bb.io.x16 = p->ey_h[2]; bb.io.h16 = p->hw_h; bb.gy16 = p->GA_h[2]; bb.gh16 = p->GA_h[0]; bb.lscale = ls;
+      fin.y16s(p->GA_h[1], ls);
+    }
     RUN(block_bwd(bb, dp, fin, s));
     RUN(bscale_grad(p->GA[1], p->ey[2], p->s_in, p->ds_in, s));
   }
@@ -964,11 +1012,71 @@ extern "C" int nef_backward(NefPlan* p, const NefBackwardArgs* a, nef_stream_t s
       CD fin(G, 128, p->s0);
       fin.out(p->GA[gx_i], 0, 32);
       if (i > 0) fin.mask(p->ey[i - 1], 0, 32, 1, 1.f).mbits(p->b_ey[i - 1]).round();
+      if (f16) {
+        bb.io.x16 = i == 0 ? p->s0_h : p->ey_h[i - 1]; bb.io.h16 = p->eh_h[i];
+        bb.gy16 = p->GA_h[gy_i]; bb.gh16 = p->GA_h[0]; bb.lscale = ls;
+        if (i > 0) fin.y16s(p->GA_h[gx_i], ls);
+      }
       RUN(block_bwd(bb, dp, fin, s));
       gy_i = gx_i;
     }
     if (Gd[P_STEM]) RUN(stem_bwd(p->x_in, p->s0_amax, p->GA[gy_i], Gd[P_STEM], G, s));
   }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// workspace inspection (test hook): named internal tensors of the last forward
+// ---------------------------------------------------------------------------------------------
+struct NamedTensor { const T4* t; const float* v; int n; };
+static bool find_tensor(const NefPlan* p, const char* name, NamedTensor* out) {
+  out->t = nullptr; out->v = nullptr; out->n = 0;
+  const std::string n(name);
+  auto is = [&](const char* s) { return n == s; };
+  auto blk = [&](const char* prefix, const T4& h, const T4& y) {
+    const std::string pre(prefix);
+    if (n == pre + ".h") { out->t = &h; return true; }
+    if (n == pre + ".y") { out->t = &y; return true; }
+    return false;
+  };
+  if (is("stem")) { out->t = &p->s0; return true; }
+  for (int i = 0; i < 3; ++i)
+    if (blk(("W_encoder.layer1." + std::to_string(i)).c_str(), p->eh[i], p->ey[i])) return true;
+  if (blk("w_conv.0", p->hw, p->w) || blk("z1_conv.0", p->h1, p->z1) || blk("z2_conv1.0", p->hz, p->z2c) ||
+      blk("z2_conv2.0", p->h20, p->y20) || blk("z2_conv2.2", p->h22, p->z2o))
+    return true;
+  if (is("roi_align")) { out->t = &p->ra; return true; }
+  if (is("z2_conv2.1")) { out->t = &p->t21; return true; }
+  for (int k = 0; k < 3; ++k) {
+    const DecBufs& d = p->dec[k];
+    const std::string pre = "dec" + std::to_string(k) + ".";
+    const T4* ts[7] = {&d.c1, &d.a1, &d.c2, &d.u1, &d.c3, &d.a3, &d.c4};
+    const char* nm[7] = {"decoder.1.0", "a1", "decoder.1.3", "u1", "decoder.3.0", "a3", "decoder.3.3"};
+    for (int i = 0; i < 7; ++i)
+      if (n == pre + nm[i]) { out->t = ts[i]; return true; }
+    if (n == pre + "u0") { out->t = &p->u0[k]; return true; }
+    for (int i = 0; i < 4; ++i) {
+      const std::string b = pre + "bn" + std::to_string(i) + ".";
+      const int ch = i < 2 ? 128 : 64;
+      if (n == b + "scale") { out->v = d.bn[i].scale; out->n = ch; return true; }
+      if (n == b + "shift") { out->v = d.bn[i].shift; out->n = ch; return true; }
+    }
+  }
+  return false;
+}
+extern "C" int nef_plan_tensor_info(const NefPlan* p, const char* name, int* C, int* L) {
+  NamedTensor t;
+  NEF_REQUIRE(p && name && find_tensor(p, name, &t), "nef_plan_tensor_info: unknown tensor '%s'", name ? name : "");
+  if (t.t) { *C = t.t->C; *L = t.t->L; }
+  else { *C = t.n; *L = 0; }
+  return 0;
+}
+extern "C" int nef_plan_export(NefPlan* p, const char* name, float* dst, nef_stream_t s) {
+  NamedTensor t;
+  NEF_REQUIRE(p && p->bound && name && find_tensor(p, name, &t), "nef_plan_export: unknown tensor '%s'", name ? name : "");
+  if (t.t) return nef_cbl4_to_ncl(reinterpret_cast<const float*>(t.t->p), dst, p->B, t.t->C, t.t->L, s);
+  cudaError_t e = cudaMemcpyAsync(dst, t.v, (size_t)t.n * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)s);
+  NEF_REQUIRE(e == cudaSuccess, "nef_plan_export: copy failed: %s", cudaGetErrorString(e));
   return 0;
 }
 

@@ -1,6 +1,5 @@
-// EXPERIMENTAL -- compiled for sm_100a, NOT YET RUN ON HARDWARE (round 1 ended without GPU budget for it) and NOT called by
-// nef_forward / nef_backward / nef_gconv_wgrad.  It is the kernel DESIGN.md section 7 names as the largest step left; the
-// op-level parity test is tests/test_gpu_experimental.py (skipped unless NEF_RUN_UNVERIFIED=1).
+// nef_gconv_wgrad_f16 (include/nefnet_b200.h): op-level parity in tests/test_gpu_conv_ops.py, used by nef_backward for the
+// big 128-output-channel layers when the fp16 backward is on (nef_set_bwd_f16).
 //
 // Weight gradient of a grouped k-tap convolution from fp16 operand copies, WITHOUT a re-tile pass:
 //     D_tap[cout x cin] += dY16[rows x cout]^T . X16[rows (+tap) x cin]          (fp32 accumulation in TMEM)
@@ -129,7 +128,7 @@ static_assert(STAGE % 128 == 0 && YBYTES % 128 == 0, "stage alignment");
 
 // grid: x = input-channel tile (dcols channels), y = row split, z = group
 __global__ void __launch_bounds__(THREADS, 1) wgrad_f16_kernel(const __grid_constant__ NefWgradDesc d, const uint4* __restrict__ dy16,
-                                                               const uint4* __restrict__ x16, float out_scale, int dcols,
+                                                               const uint4* __restrict__ x16, const float* __restrict__ out_scale_p, int dcols,
                                                                long rows_per_split, long rows_main) {
   extern __shared__ __align__(128) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
@@ -231,6 +230,7 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_f16_kernel(const __grid_cons
     // ===== warps 4..7: drain the accumulators (TMEM lane quarter = warp % 4), scaled fp32 RED into the gradient =====
     const int q = warp & 3;
     const int lr = q * 32 + lane;   // output channel
+    const float out_scale = out_scale_p ? __ldg(out_scale_p) : 1.f;
     mbar_wait(acc_full, 0);
     tc_fence_after();
     for (int tp = 0; tp < ntap; ++tp) {
@@ -254,7 +254,7 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_f16_kernel(const __grid_cons
 
 // rows [row0, d.rows): one thread per (group, cout, cin, tap)
 __global__ void __launch_bounds__(256) wgrad_f16_tail_kernel(const NefWgradDesc d, const __half* __restrict__ dy16,
-                                                             const __half* __restrict__ x16, float out_scale, long row0) {
+                                                             const __half* __restrict__ x16, const float* __restrict__ out_scale_p, long row0) {
   const long total = (long)d.groups * d.cout_g * d.cin_g * d.taps;
   const long idx = (long)blockIdx.x * 256 + threadIdx.x;
   if (idx >= total) return;
@@ -267,17 +267,18 @@ __global__ void __launch_bounds__(256) wgrad_f16_tail_kernel(const NefWgradDesc 
   float acc = 0.f;
   for (long r = row0; r < d.rows; ++r)
     acc += __half2float(dy16[(yc + r) * 8 + (m & 7)]) * __half2float(x16[(xc + r) * 8 + (n & 7)]);
-  atomicAdd(d.dw + (long)g * d.sg + (long)m * d.sm + (long)n * d.sn + (long)t * d.st, acc * out_scale);
+  atomicAdd(d.dw + (long)g * d.sg + (long)m * d.sm + (long)n * d.sn + (long)t * d.st, acc * (out_scale_p ? __ldg(out_scale_p) : 1.f));
 }
 
 }  // namespace wf16
 }  // namespace nef
 
 using namespace nef;
+extern "C" void nef_tc_note_dispatch(int which);
 
 // d: the fp32 descriptor of the same gradient (geometry, dw and its strides; d->dy, d->x and d->db are not read here);
 // dy16 / x16: the fp16 copies, `half8 [C/8][cstride rows]`, addressed from the same row origin as the fp32 tensors.
-extern "C" int nef_gconv_wgrad_f16(const NefWgradDesc* d, const void* dy16, const void* x16, float out_scale, nef_stream_t s) {
+extern "C" int nef_gconv_wgrad_f16(const NefWgradDesc* d, const void* dy16, const void* x16, const float* out_scale, nef_stream_t s) {
   NEF_REQUIRE(d && dy16 && x16, "nef_gconv_wgrad_f16: null argument");
   NEF_REQUIRE(d->cout_g == 128, "nef_gconv_wgrad_f16: cout_g must be 128 (got %d)", d->cout_g);
   NEF_REQUIRE(d->cin_g % 64 == 0 && d->taps >= 1 && d->taps <= 7, "nef_gconv_wgrad_f16: cin_g %% 64 == 0 and 1..7 taps required");
@@ -293,16 +294,25 @@ extern "C" int nef_gconv_wgrad_f16(const NefWgradDesc* d, const void* dy16, cons
   const long rows_main = nst_total * wf16::ROWS;
   if (nst_total > 0) {
     const long tiles = (long)(d->cin_g / dcols) * d->groups;
-    long splits = (2L * sms + tiles - 1) / tiles;
-    if (splits > nst_total) splits = nst_total;
-    if (splits < 1) splits = 1;
-    const long st_per_split = (nst_total + splits - 1) / splits;
-    splits = (nst_total + st_per_split - 1) / st_per_split;
+    // row splits: the smallest count whose last wave is >= 90 % full (else the best seen) -- every extra split costs
+    // another cout x cin x taps block of fp32 REDs
+    long best = 1;
+    double best_eff = 0.0;
+    const long max_splits = nst_total < 2L * sms ? nst_total : 2L * sms;
+    for (long sp = 1; sp <= max_splits; ++sp) {
+      const long ctas = tiles * sp;
+      const double eff = (double)ctas / (double)(((ctas + sms - 1) / sms) * sms);
+      if (eff > best_eff + 1e-9) { best_eff = eff; best = sp; }
+      if (eff >= 0.9) { best = sp; break; }
+    }
+    const long st_per_split = (nst_total + best - 1) / best;
+    const long splits = (nst_total + st_per_split - 1) / st_per_split;
     dim3 grid((unsigned)(d->cin_g / dcols), (unsigned)splits, (unsigned)d->groups);
     wf16::wgrad_f16_kernel<<<grid, wf16::THREADS, wf16::TOTAL, (cudaStream_t)s>>>(
         *d, reinterpret_cast<const uint4*>(dy16), reinterpret_cast<const uint4*>(x16), out_scale, dcols,
         st_per_split * wf16::ROWS, rows_main);
     NEF_CHECK_LAUNCH("wgrad_f16_kernel");
+    nef_tc_note_dispatch(5);
   }
   if (rows_main < d->rows) {
     const long total = (long)d->groups * d->cout_g * d->cin_g * d->taps;

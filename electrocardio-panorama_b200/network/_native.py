@@ -34,7 +34,8 @@ class NefConvDesc(C.Structure):
                 ("drop_seed", C.c_uint64), ("bscale", C.c_void_p), ("bscale_grad", C.c_void_p), ("mask", C.c_void_p),
                 ("mask_cstride", C.c_int64), ("mask_c4_off", C.c_int32), ("mask_c4_gstride", C.c_int32),
                 ("mask_scale", C.c_float), ("reserved2", C.c_int32), ("stat_sum", C.c_void_p),
-                ("stat_sq", C.c_void_p), ("out_bits", C.c_void_p), ("mask_bits", C.c_void_p), ("y16", C.c_void_p)]
+                ("stat_sq", C.c_void_p), ("out_bits", C.c_void_p), ("mask_bits", C.c_void_p), ("y16", C.c_void_p),
+                ("acc_scale", C.c_void_p), ("y16_scale", C.c_void_p)]
 
 
 class NefWgradDesc(C.Structure):
@@ -68,6 +69,9 @@ SIGNATURES = {
     "nef_set_exact_fp32": (C.c_int, [C.c_int]),
     "nef_launch_count": (C.c_int64, []),
     "nef_struct_size": (C.c_size_t, [C.c_int]),
+    "nef_tc_dispatch_stats": (C.c_int, [C.POINTER(C.c_int64), C.c_int]),
+    "nef_tc_dispatch_reset": (None, []),
+    "nef_tc_set_persist_min": (C.c_int, [C.c_int]),
     "nef_param_count": (C.c_int, [C.c_int]),
     "nef_param_name": (C.c_char_p, [C.c_int, C.c_int]),
     "nef_param_numel": (C.c_int64, [C.c_int, C.c_int]),
@@ -79,10 +83,13 @@ SIGNATURES = {
                                    C.c_int64, C.c_int64, C.c_int, C.c_void_p]),
     "nef_gconv_fwd": (C.c_int, [C.POINTER(NefConvDesc), C.c_void_p]),
     "nef_gconv_wgrad": (C.c_int, [C.POINTER(NefWgradDesc), C.c_void_p]),
+    "nef_gconv_wgrad_f16": (C.c_int, [C.POINTER(NefWgradDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "nef_plan_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     "nef_plan_destroy": (None, [C.c_void_p]),
     "nef_plan_workspace_bytes": (C.c_size_t, [C.c_void_p]),
     "nef_plan_bind": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "nef_plan_tensor_info": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "nef_plan_export": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_void_p]),
     "nef_forward": (C.c_int, [C.c_void_p, C.POINTER(NefForwardArgs), C.c_void_p]),
     "nef_backward": (C.c_int, [C.c_void_p, C.POINTER(NefBackwardArgs), C.c_void_p]),
     "nef_gen_ecg": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
@@ -158,6 +165,13 @@ def stream_ptr():
 
 def ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def dispatch_stats():
+    """(counts[8], set of specialised epilogue codes the persistent kernel ran with) since the last reset; test hook."""
+    buf = (C.c_int64 * 72)()
+    n = load().nef_tc_dispatch_stats(buf, 72)
+    return list(buf[:8]), set(int(buf[8 + i]) for i in range(n))
 
 
 def param_names(G: int):

@@ -230,6 +230,7 @@ class Model_nefnet(nn.Module):
             h = C.c_void_p()
             N.check(lib.nef_plan_create(B, G, L, V, C.byref(h)), "nef_plan_create")
             self.handle = h
+            self.B = B
             self.bytes = lib.nef_plan_workspace_bytes(h)
             self.ws = torch.empty(self.bytes, dtype=torch.uint8, device=device)
             N.check(lib.nef_plan_bind(h, C.c_void_p(self.ws.data_ptr()), self.bytes, N.stream_ptr()), "nef_plan_bind")
@@ -284,6 +285,7 @@ class Model_nefnet(nn.Module):
         a.save_for_backward = 1 if save else 0
         a.drop_seed = ((torch.initial_seed() * 6364136223846793005) + self._step) & 0x0FFFFFFFFFFFFFFF
         self._step += 1
+        self._last_drop_seed = int(a.drop_seed)   # tests rebuild the keep masks from it (tests/_dropmask.py)
         if phase == N.PHASE_GEN:
             z1 = torch.empty((B, 128 * G, L // 4), dtype=torch.float32, device=device)
             z2 = torch.empty((B, 128 * G, 7, 32), dtype=torch.float32, device=device)
@@ -326,6 +328,20 @@ class Model_nefnet(nn.Module):
         N.check(lib.nef_backward(plan.handle, C.byref(b), N.stream_ptr()), "nef_backward")
         self._saved = None
         return [self._grad_views[n] for n in self._live_names()]
+
+    def export_activation(self, name):
+        """Test hook (nef_plan_export): a named internal activation of the last forward as a (B, C, L) tensor."""
+        lib = N.load()
+        if not self._plans:
+            raise RuntimeError("Model_nefnet.export_activation() before the first forward")
+        plan = next(iter(self._plans.values()))
+        c, l = C.c_int(), C.c_int()
+        N.check(lib.nef_plan_tensor_info(plan.handle, name.encode(), C.byref(c), C.byref(l)), "nef_plan_tensor_info")
+        B = plan.B
+        shape = (B, c.value, l.value) if l.value > 0 else (c.value,)
+        out = torch.empty(shape, dtype=torch.float32, device=self._flat.device)
+        N.check(lib.nef_plan_export(plan.handle, name.encode(), N.ptr(out), N.stream_ptr()), "nef_plan_export")
+        return out
 
     def _live_names(self):
         return [n for n, _ in self.named_parameters() if n not in _UNUSED]

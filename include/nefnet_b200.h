@@ -50,6 +50,16 @@ int nef_set_fwd_f16(int on);
 int nef_set_exact_fp32(int on);
 /* Cumulative number of kernels this library has launched in this process (bench.py's gpu_launches). */
 int64_t nef_launch_count(void);
+/* Test hook: which kernel forms have been launched since the last reset.  out[0..7] = launches of: 0 the persistent
+ * convolution kernel, 1 the one-CTA-per-tile forms, 2 the single-tile generic form, 3 the tcgen05 weight gradient,
+ * 4 its CUDA-core ragged tail, 5 the fp16-operand weight gradient; out[8..] = the distinct specialised-epilogue codes the
+ * persistent kernel ran with (64 = the generic epilogue), -1 padded.  Returns the number of distinct codes.  A parity test
+ * uses it to prove that it exercised the dispatch the benchmark times. */
+int nef_tc_dispatch_stats(int64_t* out_host, int n);
+void nef_tc_dispatch_reset(void);
+/* Test hook: number of (256-row tile, group) work items from which nef_gconv_fwd takes the persistent kernel
+ * (0 = default, twice the SM count; 1 = always), so that small shapes can run the production kernel form. */
+int nef_tc_set_persist_min(int tiles);
 /* sizeof() of the ABI structs as this library was compiled (0 NefConvTerm, 1 NefConvDesc, 2 NefWgradDesc,
  * 3 NefForwardArgs, 4 NefBackwardArgs): lets a foreign-language binding verify its mirror. */
 size_t nef_struct_size(int which);
@@ -132,6 +142,11 @@ typedef struct NefConvDesc {
   /* fp16 copy of the output, or NULL: 8 channels per 16-byte row, chunk (y chunk / 2), planes y_cstride rows apart,
    * values saturate to the largest finite fp16.  It is the x_f16 operand of the next convolution.          */
   void* y16;
+  /* Loss-scaled fp16 gradient copies (backward pass; device scalars, NULL = 1): the accumulators are multiplied by
+   * acc_scale[0] before anything else (fp16 gradient operands carry the scale S, acc_scale = 1 / S), and the fp16 copy
+   * stores fp16(value * y16_scale[0]) (= S).  y may be NULL when y16 is set: only the fp16 copy is kept.        */
+  const float* acc_scale;
+  const float* y16_scale;
 } NefConvDesc;
 
 /* Packs reference-layout weights into the layout NefConvTerm.w expects, rounding to TF32 (RN):
@@ -159,6 +174,13 @@ typedef struct NefWgradDesc {
   float* db; /* or NULL */
 } NefWgradDesc;
 int nef_gconv_wgrad(const NefWgradDesc* d, nef_stream_t s);
+/* The same weight gradient from fp16 operand copies (`half8 [C/8][rows]`: 8 channels per 16-byte row, the layout of
+ * NefConvDesc.y16, addressed from the same row origin as the fp32 tensors), read by the tensor core as the bulk copy lands
+ * them (MN-major, no shared-memory re-tile pass).  d gives the geometry, dw and its strides (d->dy, d->x, d->db are not
+ * read; chunk offsets / group strides must be even); cout_g must be 128, cin_g a multiple of 64.  The accumulated block is
+ * multiplied by out_scale[0] (device scalar, NULL = 1: the inverse of the loss scale the dy16 copy carries) before the
+ * fp32 accumulation into dw.  tcgen05 kind::f16: 11-bit significands like TF32, twice the rate, half the operand bytes. */
+int nef_gconv_wgrad_f16(const NefWgradDesc* d, const void* dy16, const void* x16, const float* out_scale, nef_stream_t s);
 
 /* ---- whole path ---------------------------------------------------------------------------- */
 typedef struct NefPlan NefPlan;
@@ -202,6 +224,15 @@ typedef struct NefBackwardArgs {
 } NefBackwardArgs;
 /* autograd of the above (solver.py:233) for the last nef_forward(save_for_backward = 1) on this plan */
 int nef_backward(NefPlan* plan, const NefBackwardArgs* a, nef_stream_t s);
+
+/* Test hook: internal activations of the last nef_forward on this plan, by name, as (B, C, L) fp32 (vectors: C floats,
+ * L = 0).  Names: "stem"; "<block>.h" / "<block>.y" for the residual blocks W_encoder.layer1.{0,1,2}, w_conv.0, z1_conv.0,
+ * z2_conv1.0 (centre window only), z2_conv2.0, z2_conv2.2; "roi_align"; "z2_conv2.1"; per decoder call k = 0..2:
+ * "dec<k>.u0", "dec<k>.decoder.{1,3}.{0,3}" (convolution outputs before BatchNorm), "dec<k>.a1|u1|a3",
+ * "dec<k>.bn<i>.scale|shift".  The parity tests compare them layer by layer with the oracle and evaluate the oracle's
+ * backward pass on the device's own ReLU / dropout patterns. */
+int nef_plan_tensor_info(const NefPlan* plan, const char* name, int* C, int* L);
+int nef_plan_export(NefPlan* plan, const char* name, float* dst, nef_stream_t s);
 
 /* Model_nefnet.gen_ecg, model_nefnet.py:196-218: decode V views from supplied latents (eval-mode BN) */
 int nef_gen_ecg(NefPlan* plan, const float* const* params, const float* z1, const float* z2,

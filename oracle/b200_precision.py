@@ -13,6 +13,7 @@ fp32 oracle the production gradients differ by several percent in L2 whatever th
                         from ``store``); 'fp16' -> both operands additionally through fp16 (saturating, RN-even: the encoder
                         forward); 'fp32' -> untouched (stem and output kernels on CUDA cores; the decoder's first
                         convolution is evaluated split-precision, x_hi w_hi + x_lo w_hi + x_hi w_lo, i.e. to ~2^-22)
+  pattern(name)         optional observed (value != 0) pattern of a ReLU output, see B200Precision
   store(x)              a stored activation: rounded to TF32
   pre(x)                identity forward; the GRADIENT passing through is rounded to TF32 (the device stores the gradient of
                         every pre-activation rounded: masked data-gradient epilogues, bnbwd_apply)
@@ -64,8 +65,21 @@ class _RoundGrad(torch.autograd.Function):
 
 
 class B200Precision:
-    def __init__(self, fwd_f16: bool = True):
+    """patterns: optional name -> 0/1 tensor, the (value != 0) pattern of an activation as observed on the device
+    ('<block>.h', '<block>.y', 'dec<k>.<stage>.<bn>'); the oracle then multiplies by it instead of applying ReLU (and the
+    dropout keep-mask, which the pattern of a block's h contains).  acts: filled with the named intermediates of a run."""
+
+    def __init__(self, fwd_f16: bool = True, patterns=None, record: bool = False):
         self.fwd_f16 = fwd_f16
+        self.patterns = patterns or {}
+        self.acts = {} if record else None
+
+    def pattern(self, name):
+        return self.patterns.get(name)
+
+    def observe(self, name, x):
+        if self.acts is not None:
+            self.acts[name] = x.detach()
 
     def _ops(self, kind, x, w):
         if kind == "fp32":

@@ -232,6 +232,24 @@ def _pre(prec, x):
     return x if prec is None else prec.pre(x)
 
 
+def _relu(prec, name, x):
+    """F.relu, or -- when `prec` carries activation patterns observed on the device (prec.pattern(name)) -- x * pattern:
+    the same function wherever the pattern equals (x > 0), and a way to evaluate the backward pass on EXACTLY the device's
+    ReLU / dropout pattern, so that gradient parity is not blurred by masks that flip within rounding distance of zero."""
+    if prec is not None:
+        m = prec.pattern(name)
+        if m is not None:
+            return x * m.to(x.dtype)
+    return F.relu(x)
+
+
+def _obs(prec, name, x):
+    """lets `prec` record a named intermediate tensor (layer-by-layer comparison with the device's workspace)"""
+    if prec is not None:
+        prec.observe(name, x)
+    return x
+
+
 def _maybe_drop(h: torch.Tensor, keep: Optional[torch.Tensor], p: float) -> torch.Tensor:
     """nn.Dropout(0.2) of the residual blocks (resnet_1d.py:37,45; model_nefnet.py:46,52).  The
     oracle takes the keep-mask explicitly (None = dropout disabled) so that parity can be
@@ -241,34 +259,40 @@ def _maybe_drop(h: torch.Tensor, keep: Optional[torch.Tensor], p: float) -> torc
     return h * keep.to(h.dtype) / (1.0 - p)
 
 
-def residual_block(x, w1, w2, groups, res_w=None, res_b=None, keep=None, p=0.2, prec=None, kind="tf32", scale=None):
+def residual_block(x, w1, w2, groups, res_w=None, res_b=None, keep=None, p=0.2, prec=None, kind="tf32", scale=None,
+                   name=""):
     """conv -> ReLU -> Dropout -> conv -> (+ 1x1 residual conv iff channel counts differ) -> add
     -> ReLU.  resnet_1d.py:39-53 (k=7, identity residual) and model_nefnet.py:48-60 (k=3).
     scale: optional per-(segment, channel) factor applied to the block output (the angular scaling of
     model_nefnet.py:120-123, which the device fuses into the last encoder block's epilogue)."""
     pad = w1.shape[2] // 2
-    h = F.relu(_pre(prec, _conv(prec, kind, x, w1, padding=pad, groups=groups)))
-    h = _st(prec, _maybe_drop(h, keep, p))
+    h = _relu(prec, name + ".h", _pre(prec, _conv(prec, kind, x, w1, padding=pad, groups=groups)))
+    if prec is not None and prec.pattern(name + ".h") is not None and keep is not None:
+        h = h / (1.0 - p)   # the observed pattern of h already contains the dropout keep-mask
+    else:
+        h = _maybe_drop(h, keep, p)
+    h = _obs(prec, name + ".h", _st(prec, h))
     y = _conv(prec, kind, h, w2, padding=pad, groups=groups)
     if y.shape[1] != x.shape[1]:
         r = _conv(prec, "tf32", x, res_w, res_b, groups=groups)
     else:
         r = x
-    y = F.relu(_pre(prec, y + r))
+    y = _relu(prec, name + ".y", _pre(prec, y + r))
     if scale is not None:
         y = y * scale
-    return _st(prec, y)
+    return _obs(prec, name + ".y", _st(prec, y))
 
 
 def encoder(P, x, G, keeps=None, prec=None, out_scale=None):
     """encoder/encoder.py:28-40 with resnet_1d.py:102-105: grouped stem k15 s2 p7 -> ReLU ->
     MaxPool(3,2,1) -> three k7 residual blocks.  out_scale: see residual_block (last block)."""
     h = _conv(prec, "fp32", x, P["W_encoder.conv1.weight"], stride=2, padding=7, groups=G)
-    h = _st(prec, F.max_pool1d(F.relu(h), kernel_size=3, stride=2, padding=1))
+    h = _obs(prec, "stem", _st(prec, F.max_pool1d(F.relu(h), kernel_size=3, stride=2, padding=1)))
     for i in range(3):
         keep = None if keeps is None else keeps.get(f"W_encoder.layer1.{i}")
         h = residual_block(h, P[f"W_encoder.layer1.{i}.conv1.weight"], P[f"W_encoder.layer1.{i}.conv2.weight"], G,
-                           keep=keep, prec=prec, kind="fp16", scale=out_scale if i == 2 else None)
+                           keep=keep, prec=prec, kind="fp16", scale=out_scale if i == 2 else None,
+                           name=f"W_encoder.layer1.{i}")
     return h
 
 
@@ -328,7 +352,7 @@ def _bn(x, P, prefix, training, stats_out):
     return y
 
 
-def decoder(P, lat, training, stats_out=None, prec=None):
+def decoder(P, lat, training, stats_out=None, prec=None, name="dec"):
     """model_nefnet.py:101-107: Upsample x2 -> DoubleConv(256,128) -> Upsample x2 ->
     DoubleConv(128,64) -> Conv1d(64,1,3); then sigmoid(x/3) (:168)."""
     h = F.interpolate(lat, scale_factor=2, mode="linear", align_corners=False)
@@ -339,8 +363,9 @@ def decoder(P, lat, training, stats_out=None, prec=None):
             # the device evaluates the first convolution split-precision (x_hi w_hi + x_lo w_hi + x_hi w_lo): fp32-like
             h = _pre(prec, _conv(prec, "fp32" if first else "tf32", h, P[pre + conv + ".weight"], P[pre + conv + ".bias"],
                                  padding=1))
+            _obs(prec, f"{name}.{stage}.{conv}", h)
             first = False
-            h = F.relu(_bn(h, P, pre + bn, training, stats_out))
+            h = _relu(prec, f"{name}.{stage}.{bn}", _bn(h, P, pre + bn, training, stats_out))
             if conv == "0":          # stored (rounded) as the next convolution's operand; after the second conv of a stage the
                 h = _st(prec, h)     # device stores the UPSAMPLED tensor (decoder.1) or feeds the fp32 output kernel (decoder.3)
         if stage == "decoder.1":
@@ -362,20 +387,21 @@ def latents(P, x, input_thetas, rois, G, keeps=None, stop_before_reverse=False, 
     else:  # the device applies the scale in the last encoder block's epilogue, before the stored value is rounded
         w = encoder(P, x, G, keeps, prec=prec, out_scale=enc.reshape(B, 128 * G, 1))
         L4 = w.shape[-1]
-    w = residual_block(w, P["w_conv.0.conv1.weight"], P["w_conv.0.conv2.weight"], G, keep=kp("w_conv.0"), prec=prec)  # :124
+    w = residual_block(w, P["w_conv.0.conv1.weight"], P["w_conv.0.conv2.weight"], G, keep=kp("w_conv.0"), prec=prec,
+                       name="w_conv.0")  # :124
     w = w.view(B, G, 2, 64, L4)  # :125-131 each lead's 128 ch -> (z1 half, z2 half)
     z1 = w[:, :, 0].reshape(B, 64 * G, L4)
     z2 = w[:, :, 1].reshape(B, 64 * G, L4)
     z1 = residual_block(z1, P["z1_conv.0.conv1.weight"], P["z1_conv.0.conv2.weight"], G,
                         P["z1_conv.0.residual_conv.weight"], P["z1_conv.0.residual_conv.bias"], keep=kp("z1_conv.0"),
-                        prec=prec)
+                        prec=prec, name="z1_conv.0")
     z2 = residual_block(z2, P["z2_conv1.0.conv1.weight"], P["z2_conv1.0.conv2.weight"], G,
                         P["z2_conv1.0.residual_conv.weight"], P["z2_conv1.0.residual_conv.bias"],
-                        keep=kp("z2_conv1.0"), prec=prec)
-    z2 = _st(prec, roi_align_center(z2, rois))  # (B,128G,7,16) :136
+                        keep=kp("z2_conv1.0"), prec=prec, name="z2_conv1.0")
+    z2 = _obs(prec, "roi_align", _st(prec, roi_align_center(z2, rois)))  # (B,128G,7,16) :136
     z2 = z2.reshape(B, 128 * G * N_ROI, ROI_SIZE)  # :137
     z2 = residual_block(z2, P["z2_conv2.0.conv1.weight"], P["z2_conv2.0.conv2.weight"], 7 * G, keep=kp("z2_conv2.0"),
-                        prec=prec)
+                        prec=prec, name="z2_conv2.0")
     if prec is None:
         z2 = F.conv_transpose1d(z2, P["z2_conv2.1.weight"], P["z2_conv2.1.bias"], stride=2, groups=7 * G)
     else:
@@ -383,7 +409,7 @@ def latents(P, x, input_thetas, rois, G, keeps=None, stop_before_reverse=False, 
                                                       groups=7 * G)))
     z2 = residual_block(z2, P["z2_conv2.2.conv1.weight"], P["z2_conv2.2.conv2.weight"], 7 * G,
                         P["z2_conv2.2.residual_conv.weight"], P["z2_conv2.2.residual_conv.bias"],
-                        keep=kp("z2_conv2.2"), prec=prec)
+                        keep=kp("z2_conv2.2"), prec=prec, name="z2_conv2.2")
     z2 = z2.view(B, 128 * G, N_ROI, 2 * ROI_SIZE)  # :138
     if stop_before_reverse:
         return z1, z2
@@ -409,7 +435,8 @@ def forward(P, x, input_thetas, query_theta, rois, rest_theta=None, phase="train
     lat_p = torch.cat([z1g[:, c1], z2_mean], dim=1)  # :159
     lat_l = torch.cat([z1_mean, z2g[:, c2]], dim=1)  # :160
     q = F.linear(theta_features(query_theta).view(B, -1), P["mlp2.weight"], P["mlp2.bias"])  # :163-164
-    outs = [decoder(P, q[:, :, None] * lat, bn_training, stats_out, prec) for lat in (lat_all, lat_p, lat_l)]  # :166-176
+    outs = [decoder(P, q[:, :, None] * lat, bn_training, stats_out, prec, name=f"dec{k}")
+            for k, lat in enumerate((lat_all, lat_p, lat_l))]  # :166-176
     if phase == "train":
         return tuple(outs)
     if phase in ("val", "test"):

@@ -1,10 +1,8 @@
-"""GPU, OPT-IN: kernels that compile for sm_100a but have not been run on hardware yet.  Skipped unless NEF_RUN_UNVERIFIED=1, so
-that an unverified kernel can never turn the parity suite red (or hang it); nothing here is on the product path.
-
-    NEF_RUN_UNVERIFIED=1 timeout 120 python -m pytest tests/test_gpu_experimental.py -m gpu -x -q -s
+"""GPU, op level: the fp16-operand kernels against conv1d / autograd.
 
 nef_gconv_wgrad_f16 (csrc/nef_wgrad_f16.cu): weight gradient from fp16 operand copies read MN-major as the bulk copy lands
-them -- no re-tile pass ("the largest step left")."""
+them -- no re-tile pass; and the production convolution kernel with fp16 operand copies (NefConvTerm.x_f16) in the forward and
+the data-gradient direction.  First run on hardware in round 2 (profiles/r02_wgrad_f16_first_hardware_run.txt)."""
 import ctypes as C
 import os
 
@@ -12,9 +10,7 @@ import pytest
 import torch
 import torch.nn.functional as F
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("NEF_RUN_UNVERIFIED") != "1",
-                                 reason="unverified on hardware; opt in with NEF_RUN_UNVERIFIED=1")]
+pytestmark = pytest.mark.gpu
 
 
 def _half8(t):
@@ -29,15 +25,12 @@ def _half8(t):
 
 
 @pytest.mark.parametrize("B,L,groups,cin_g,taps", [(2, 122, 1, 64, 1), (3, 250, 2, 128, 3), (4, 500, 2, 128, 7), (1, 40, 3, 64, 7),
-                                                   (16, 1250, 2, 128, 7)])
+                                                   (16, 1250, 2, 128, 7), (64, 1250, 12, 128, 7), (64, 1250, 12, 64, 3)])
 def test_wgrad_f16_matches_autograd(B, L, groups, cin_g, taps):
     from network import _native as N, ops
     dev = torch.device("cuda:0")
     lib = N.init(0)
-    raw = C.CDLL(lib._name)
-    fn = raw.nef_gconv_wgrad_f16
-    fn.restype = C.c_int
-    fn.argtypes = [C.POINTER(N.NefWgradDesc), C.c_void_p, C.c_void_p, C.c_float, C.c_void_p]
+    fn = lib.nef_gconv_wgrad_f16
     cout_g = 128
     a, b = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
     torch.backends.cudnn.allow_tf32 = False
@@ -60,7 +53,8 @@ def test_wgrad_f16_matches_autograd(B, L, groups, cin_g, taps):
         d.rows = dyt.rows
         d.dw, d.sg, d.sm, d.sn, d.st = dw.data_ptr(), cout_g * cin_g * taps, cin_g * taps, taps, 1
         scale = 0.25
-        N.check(fn(C.byref(d), C.c_void_p(dy16.data_ptr()), C.c_void_p(x16.data_ptr()), scale, N.stream_ptr()),
+        scale_dev = torch.tensor([scale], device=dev)   # out_scale is a DEVICE scalar (the inverse loss scale)
+        N.check(fn(C.byref(d), C.c_void_p(dy16.data_ptr()), C.c_void_p(x16.data_ptr()), N.ptr(scale_dev), N.stream_ptr()),
                 "nef_gconv_wgrad_f16")
         torch.cuda.synchronize()
         ref = w.grad * scale
@@ -72,7 +66,7 @@ def test_wgrad_f16_matches_autograd(B, L, groups, cin_g, taps):
         dw2 = torch.zeros_like(w)
         ops.gconv_wgrad(dyt, xt, dw2, groups, cout_g, cin_g, taps)
         assert float((dw - scale * dw2).abs().max()) < 2 * tol
-        N.check(fn(C.byref(d), C.c_void_p(dy16.data_ptr()), C.c_void_p(x16.data_ptr()), scale, N.stream_ptr()),
+        N.check(fn(C.byref(d), C.c_void_p(dy16.data_ptr()), C.c_void_p(x16.data_ptr()), N.ptr(scale_dev), N.stream_ptr()),
                 "nef_gconv_wgrad_f16")
         assert float((dw - 2 * ref).abs().max()) < 2 * tol
     finally:

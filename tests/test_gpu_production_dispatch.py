@@ -1,0 +1,188 @@
+"""GPU parity of the DISPATCH THE BENCHMARK TIMES: full train steps at sizes where nef_gconv_fwd takes the persistent
+tcgen05 kernel with its specialised epilogues (dropout, one-bit masks, fp16 operand copies, BatchNorm statistics) and the
+multi-split weight-gradient kernels -- against the CPU oracle, with dropout OFF and ON (the oracle consumes the keep masks
+the device generated, rebuilt on the host by tests/_dropmask.py).
+
+Three references per case:
+  * the fp32 oracle (the reference's arithmetic): synthesized waveforms within 1e-3 relative (north-star bar); gradients
+    only loosely -- TF32 flips ReLU masks that sit within rounding distance of zero, whatever the implementation;
+  * the oracle under the B200 arithmetic model (oracle/b200_precision.py: the device's operand / stored-activation
+    roundings, fp32 accumulation).  A rounded computation is chaotic at the 1e-7 level (a 1e-7 input perturbation moves the
+    MODEL's own outputs by 3e-4 and its gradients by 2-3 %: rounding and mask flips cascade through the BatchNorm layers), so
+    this comparison is reported, and bounds the error by the model's own sensitivity, but cannot be tight either;
+  * the same model evaluated ON THE DEVICE'S OWN ReLU / DROPOUT PATTERNS (exported from the plan's workspace through
+    nef_plan_export and forced into the oracle): no mask can flip, every intermediate activation is compared layer by layer,
+    and the backward pass -- a linear map once the patterns are fixed -- must match TIGHTLY.  This is the bar that catches a
+    kernel error of a percent.
+Each test asserts through nef_tc_dispatch_stats that the persistent specialised kernels actually ran.
+"""
+import json
+import os
+import random
+import time
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import nefnet_oracle as O
+from oracle.b200_precision import B200Precision
+import _dropmask  # tests/_dropmask.py (pytest puts the test directory on sys.path)
+
+pytestmark = pytest.mark.gpu
+
+OUT_RTOL = 1e-3            # north star, vs the fp32 oracle
+PAT_GRAD_REL_L2 = 5e-3     # gradients vs the model evaluated on the device's activation patterns
+PAT_ACT_REL_L2 = 1e-3      # every exported intermediate activation vs the same
+FP32_GRAD_REL_L2 = 0.15    # gradients vs the fp32 oracle (ReLU-mask flips, see module docstring)
+FP32_GRAD_COS = 0.99
+
+# epilogue codes of conv_tc_persist_kernel the 256 x 12 x 5000 training step launches (profiles/r01_step_b256_per_kernel_*):
+#   5164 / 5158 / 1318 encoder forward (dropout, fp16 copies, bit planes, angular scale), 1068 / 1062 / 37 k3 forward,
+#   513 decoder forward with BatchNorm statistics, 2080 / 2082 / 2338 / 2 masked data gradients, 0 / 32 decoder data gradients
+BENCH_EPI_DROPOUT = {5164, 5158, 1318, 1068, 1062, 37, 513, 2080, 2082, 2338, 2, 0, 32}
+
+
+BLOCKS = ("W_encoder.layer1.0", "W_encoder.layer1.1", "W_encoder.layer1.2", "w_conv.0", "z1_conv.0", "z2_conv1.0", "z2_conv2.0",
+          "z2_conv2.2")
+
+
+def _device_patterns(m, B, G, L):
+    """(value != 0) patterns of every ReLU output of the device's last forward, keyed like the oracle's ReLU sites, and the
+    exported activations themselves (CPU tensors) for the layer-by-layer comparison."""
+    L4 = L // 4
+    pat, acts = {}, {}
+    acts["stem"] = m.export_activation("stem").cpu()
+    for blk in BLOCKS:
+        for s in ("h", "y"):
+            a = m.export_activation("%s.%s" % (blk, s)).cpu()
+            acts["%s.%s" % (blk, s)] = a
+            if blk == "z2_conv1.0":   # evaluated on the centre window only; the other columns reach no output
+                w0, Lw = _dropmask.centre_window(L4)
+                full = torch.ones(B, a.shape[1], L4, dtype=torch.bool)
+                full[:, :, w0:w0 + Lw] = a != 0
+                pat["%s.%s" % (blk, s)] = full
+            else:
+                pat["%s.%s" % (blk, s)] = a != 0
+    acts["roi_align"] = m.export_activation("roi_align").cpu()
+    for k in range(3):
+        for i, (conv, bn) in enumerate((("decoder.1.0", "decoder.1.1"), ("decoder.1.3", "decoder.1.4"),
+                                        ("decoder.3.0", "decoder.3.1"), ("decoder.3.3", "decoder.3.4"))):
+            c = m.export_activation("dec%d.%s" % (k, conv))
+            sc = m.export_activation("dec%d.bn%d.scale" % (k, i)).double()
+            sh = m.export_activation("dec%d.bn%d.shift" % (k, i)).double()
+            # the device evaluates fma(c, scale, shift) > 0: one rounding, so its sign is the sign of the exact value
+            pat["dec%d.%s" % (k, bn)] = ((c.double() * sc[None, :, None] + sh[None, :, None]) > 0).cpu()
+            acts["dec%d.%s" % (k, conv)] = c.cpu()
+    return pat, acts
+
+
+def _run_case(B, G, L, seed, dropout, persist_min):
+    import network
+    from network import _native as N
+    dev = torch.device("cuda:0")
+    lib = N.init(0)
+    P = O.make_params(G, seed)
+    inp = O.make_inputs(B, G, L, seed)
+    random.seed(seed)
+    c1, c2 = random.randint(0, G - 1), random.randint(0, G - 1)
+    gen = torch.Generator().manual_seed(seed)
+    ups = [torch.randn(B, 1, L, generator=gen) for _ in range(3)]
+    m = network.Model_nefnet(theta_encoder_len=1, lead_num=G)
+    m.load_state_dict({k: v.clone() for k, v in P.items()}, strict=True)
+    m = m.float().to(dev).train()
+    m.dropout_p = dropout
+    torch.cuda.synchronize()
+    lib.nef_tc_set_persist_min(persist_min)
+    lib.nef_tc_dispatch_reset()
+    try:
+        random.seed(seed)
+        d = {k: v.to(dev) for k, v in inp.items()}
+        outs = m(d["x"], d["input_thetas"], d["query_theta"], d["rois"], phase="train")
+        torch.autograd.backward(outs, [u.to(dev) for u in ups])
+        torch.cuda.synchronize()
+        counts, epis = N.dispatch_stats()
+    finally:
+        lib.nef_tc_set_persist_min(0)
+    keeps = _dropmask.keeps_for(m._last_drop_seed, B, G, L, dropout) if dropout > 0 else None
+    got_out = [o.detach().cpu() for o in outs]
+    named = dict(m.named_parameters())
+    got_grad = {n: named[n].grad.detach().cpu().double() for n in O.live_param_names(G)}
+    patterns, dev_acts = _device_patterns(m, B, G, L)
+    report = {"case": "B%d G%d L%d dropout %.1f persist_min %d" % (B, G, L, dropout, persist_min),
+              "dispatch_counts": counts, "persistent_epilogues": sorted(epis)}
+    for label, prec in (("fp32", None), ("b200_model", B200Precision()),
+                        ("b200_model_on_device_patterns", B200Precision(patterns=patterns, record=True))):
+        t0 = time.time()
+        Po = {k: v.clone() for k, v in P.items()}
+        for n in O.live_param_names(G):
+            Po[n].requires_grad_(True)
+        oo = O.forward(Po, inp["x"], inp["input_thetas"], inp["query_theta"], inp["rois"], phase="train",
+                       lead_choice=(c1, c2), keeps=keeps, prec=prec)
+        torch.autograd.backward(oo, ups)
+        out_err = max(float(((a - b.detach()).abs() / b.detach().abs()).max()) for a, b in zip(got_out, oo))
+        worst, worst_cos, rows = (0.0, ""), 1.0, {}
+        for n in O.live_param_names(G):
+            if n in O.ZERO_GRAD_PARAMS:
+                continue
+            ref = Po[n].grad.double()
+            err = float((got_grad[n] - ref).norm() / (ref.norm() + 1e-30))
+            cos = float((got_grad[n] * ref).sum() / (got_grad[n].norm() * ref.norm() + 1e-30))
+            rows[n] = (err, cos)
+            worst_cos = min(worst_cos, cos)
+            if err > worst[0]:
+                worst = (err, n)
+        report[label] = {"out_max_rel": out_err, "grad_worst_rel_l2": worst[0], "grad_worst_name": worst[1],
+                         "grad_worst_cos": worst_cos, "oracle_seconds": round(time.time() - t0, 1),
+                         "grad_rel_l2": {k: round(v[0], 6) for k, v in rows.items()}}
+        print("%s vs %-30s: out max-rel %.3e, worst grad rel-L2 %.3e (%s), min cos %.6f  [%.1fs CPU]"
+              % (report["case"], label, out_err, worst[0], worst[1], worst_cos, time.time() - t0), flush=True)
+        if prec is not None and prec.acts is not None:   # layer by layer
+            acts = {}
+            for name, dv in dev_acts.items():
+                ref = prec.acts[name]
+                if name.startswith("z2_conv1.0"):
+                    w0, Lw = _dropmask.centre_window(L // 4)
+                    ref = ref[:, :, w0 + 2:w0 + 4] if name.endswith(".y") else ref[:, :, w0 + 1:w0 + Lw - 1]
+                    dv = dv[:, :, 2:4] if name.endswith(".y") else dv[:, :, 1:Lw - 1]
+                ref = ref.reshape(dv.shape).double()
+                acts[name] = float((dv.double() - ref).norm() / (ref.norm() + 1e-30))
+            report[label]["act_rel_l2"] = {k: round(v, 7) for k, v in acts.items()}
+            wa = max(acts.items(), key=lambda kv: kv[1])
+            print("    layer by layer: worst activation rel-L2 %.3e (%s) over %d tensors" % (wa[1], wa[0], len(acts)), flush=True)
+        del Po, oo
+    out_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(out_dir):
+        with open(os.path.join(out_dir, "production_dispatch_parity.jsonl"), "a") as f:
+            f.write(json.dumps(report) + "\n")
+    return report
+
+
+def _check(r):
+    assert r["fp32"]["out_max_rel"] < OUT_RTOL, r["fp32"]
+    assert r["fp32"]["grad_worst_rel_l2"] < FP32_GRAD_REL_L2 and r["fp32"]["grad_worst_cos"] > FP32_GRAD_COS, r["fp32"]
+    assert r["b200_model"]["out_max_rel"] < OUT_RTOL, r["b200_model"]
+    assert r["b200_model"]["grad_worst_rel_l2"] <= r["fp32"]["grad_worst_rel_l2"], "the arithmetic model explains nothing"
+    pat = r["b200_model_on_device_patterns"]
+    assert pat["out_max_rel"] < OUT_RTOL, pat
+    assert pat["grad_worst_rel_l2"] < PAT_GRAD_REL_L2, (pat["grad_worst_name"], pat["grad_worst_rel_l2"])
+    worst = max(pat["act_rel_l2"].items(), key=lambda kv: kv[1])
+    assert worst[1] < PAT_ACT_REL_L2, worst
+
+
+def test_bench_dispatch_dropout_on():
+    """32 x 12 x 5000, dropout 0.2, natural dispatch: every big convolution (encoder, w_conv, z1_conv, decoder; forward, data
+    gradient) runs the persistent kernel with the epilogues of the benchmarked step, the weight gradients run multi-split."""
+    r = _run_case(32, 12, 5000, 31, 0.2, 0)
+    assert r["dispatch_counts"][0] > 0 and r["dispatch_counts"][3] > 0, r["dispatch_counts"]
+    missing = BENCH_EPI_DROPOUT - set(r["persistent_epilogues"])
+    assert not missing, ("persistent epilogues of the benchmarked step that this test did not run", sorted(missing))
+    _check(r)
+
+
+def test_persistent_everywhere_dropout_off():
+    """8 x 12 x 5000, dropout off, persistent kernel forced for every convolution (including the small z2 deflection branch
+    that only reaches it at batch 256): 64 = the generic epilogue the dropout-free blocks fall to."""
+    r = _run_case(8, 12, 5000, 32, 0.0, 1)
+    assert r["dispatch_counts"][0] > 0 and r["dispatch_counts"][1] == 0 and r["dispatch_counts"][2] == 0, r["dispatch_counts"]
+    _check(r)
