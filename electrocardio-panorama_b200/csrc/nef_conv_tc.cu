@@ -1052,7 +1052,7 @@ static int g_tc_mt = 0;  // 0 = automatic; 4 forces four row tiles per CTA, one 
 
 // the specialised epilogues instantiated for the 4-row-tile kernel (everything else takes the generic one)
 #define NEF_TC_EPI_LIST(X) X(0) X(2) X(5) X(32) X(33) X(36) X(37) X(38) X(44) X(48) X(50) X(64) X(294) X(418) X(513) \
-  X(1062) X(1068) X(1318) X(2080) X(2082) X(2338) X(5158) X(5164) X(5414) X(14368) X(14370) X(14626)
+  X(1062) X(1068) X(1318) X(2080) X(2082) X(2338) X(5158) X(5164) X(5414) X(8194) X(14368) X(14370) X(14626)
 
 template <int MT, int EPI>
 static int tc_optin() {
@@ -1238,6 +1238,17 @@ extern "C" int nef_gconv_wgrad_tc(const NefWgradDesc* d, nef_stream_t s) {
     tc::bias_grad_kernel<<<grid, 256, 0, (cudaStream_t)s>>>(*d, rps);
     NEF_CHECK_LAUNCH("bias_grad_kernel");
   }
+  return 0;
+}
+
+// db[g * cout_g + m] += sum over rows of dy[row][g, m] alone (the weight gradient of the layer ran on fp16 copies)
+extern "C" int nef_bias_grad_tc(const NefWgradDesc* d, nef_stream_t s) {
+  long splits = (d->rows + 4095) / 4096;
+  if (splits > 64) splits = 64;
+  const long rps = (d->rows + splits - 1) / splits;
+  dim3 grid((unsigned)((d->rows + rps - 1) / rps), (unsigned)(d->groups * (d->cout_g / 4)));
+  tc::bias_grad_kernel<<<grid, 256, 0, (cudaStream_t)s>>>(*d, rps);
+  NEF_CHECK_LAUNCH("bias_grad_kernel");
   return 0;
 }
 

@@ -677,6 +677,7 @@ __global__ void __launch_bounds__(256, 3) latent_bwd_kernel(const LatentBwdArgs 
   const float invG = 1.0f / (float)a.G;
   float4 dq = f4zero();
   const int L2 = 2 * L4;
+  const float s16 = (a.gz1_h && a.s16) ? __ldg(a.s16) : 1.f;
   for (int t0 = 0; t0 < L4; t0 += LB_TL) {
    const int nl = min(LB_TL, L4 - t0);
    for (int l = t0 + tid; l < t0 + nl; l += 256) {
@@ -709,7 +710,12 @@ __global__ void __launch_bounds__(256, 3) latent_bwd_kernel(const LatentBwdArgs 
             if (g == a.c1) { gsum = gsum + dp; pick = z[k]; }
             gsum = make_float4(z[k].x > 0.f ? gsum.x : 0.f, z[k].y > 0.f ? gsum.y : 0.f, z[k].z > 0.f ? gsum.z : 0.f,
                                z[k].w > 0.f ? gsum.w : 0.f);
-            *a.gz1.at(g * 32 + cc, b, l) = tf32_rn4(gsum);
+            gsum = tf32_rn4(gsum);
+            *a.gz1.at(g * 32 + cc, b, l) = gsum;
+            if (a.gz1_h) {   // this block's 4 channels are one half of the 16-byte fp16 row (the block of chunk cc ^ 1 writes the other)
+              uint2* hp = reinterpret_cast<uint2*>(reinterpret_cast<uint4*>(a.gz1_h) + (long)((g * 32 + cc) >> 1) * a.gz1.cs + a.gz1.row(b, l));
+              hp[cc & 1] = make_uint2(f16x2_sat(gsum.x * s16, gsum.y * s16), f16x2_sat(gsum.z * s16, gsum.w * s16));
+            }
           }
         }
       }
@@ -1006,9 +1012,11 @@ int bnbwd_stats(T4 da, T4 c, const BnLayer& bn, cudaStream_t s) {
 }
 
 // pass 2: dc = gamma * invstd * (g - s1/N - xhat * s2/N) ; dgamma += s2 ; dbeta += s1
+// With running statistics (module in eval mode, training == 0) mean and variance are constants of the batch:
+// dc = gamma * invstd * g  -- what autograd gives the reference there (F.batch_norm(training=False)).
 __global__ void __launch_bounds__(EW_TPB) bnbwd_apply_kernel(T4 da, T4 c, BnLayer bn, const float* __restrict__ gamma, double count,
-                                                             T4 dc, float* dgamma, float* dbeta) {
-  const float invn = (float)(1.0 / count);
+                                                             T4 dc, float* dgamma, float* dbeta, int training) {
+  const float invn = training ? (float)(1.0 / count) : 0.f;
   const int c4 = blockIdx.y / c.B, b = blockIdx.y - c4 * c.B;
   float sc[4], sh[4], mu[4], is[4], gi[4], m1[4], m2[4];
 #pragma unroll
@@ -1046,8 +1054,8 @@ __global__ void __launch_bounds__(EW_TPB) bnbwd_apply_kernel(T4 da, T4 c, BnLaye
   }
 }
 int bnbwd_apply(T4 da, T4 c, const BnLayer& bn, const float* gamma, double count, T4 dc, float* dgamma, float* dbeta,
-                cudaStream_t s) {
-  bnbwd_apply_kernel<<<ew_grid(c.C, c.B, c.L), EW_TPB, 0, s>>>(da, c, bn, gamma, count, dc, dgamma, dbeta);
+                int training, cudaStream_t s) {
+  bnbwd_apply_kernel<<<ew_grid(c.C, c.B, c.L), EW_TPB, 0, s>>>(da, c, bn, gamma, count, dc, dgamma, dbeta, training);
   NEF_CHECK_LAUNCH("bnbwd_apply_kernel");
   return 0;
 }

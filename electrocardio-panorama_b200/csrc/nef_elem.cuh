@@ -68,6 +68,8 @@ int elem_init();  // shared-memory opt-ins of the kernels in nef_elem.cu (once p
 struct LatentBwdArgs {
   T4 du0[3]; T4 lat[3]; T4 z1, z2o; const int64_t* rois; const float* q; int q_stride; int G, c1, c2;
   T4 gz1;                 // out: grad wrt pre-ReLU z1 (128G, L4)
+  void* gz1_h;            // optional: fp16 copy of gz1 (8 channels per 16-byte row) multiplied by s16[0] (device scalar)
+  const float* s16;
   T4 gz2o;                // out: grad wrt pre-ReLU z2o (896G, 32)
   float* dq;              // out (B, 256), overwritten
 };
@@ -81,8 +83,9 @@ int bn_fold_eval(const float* gamma, const float* beta, const float* rmean, cons
 int bn_relu(T4 c, const float* scale, const float* shift, T4 out, int upsample, cudaStream_t s);
 int up_adjoint(T4 du, T4 da, cudaStream_t s);
 int bnbwd_stats(T4 da, T4 c, const BnLayer& bn, cudaStream_t s);
+// training == 0: the forward used running statistics, so the batch-mean terms of the BatchNorm gradient vanish
 int bnbwd_apply(T4 da, T4 c, const BnLayer& bn, const float* gamma, double count, T4 dc, float* dgamma, float* dbeta,
-                cudaStream_t s);
+                int training, cudaStream_t s);
 int dec_out_fwd(T4 c4, const float* scale, const float* shift, const float* w, const float* b, float* out,
                 int out_bstride, cudaStream_t s);
 int dec_out_bwd(T4 c4, const BnLayer& bn, const float* w, const float* out, const float* dout, T4 g4, float* dw,

@@ -186,6 +186,7 @@ struct ConvW {            // one convolution's weights: reference tensor + packe
   float* pk_f;            // forward packing  [g][t][cin_g/32][8][cout_g][4]
   float* pk_d;            // data-gradient packing (flipped taps, transposed); N = min(cin_g, 128)
   void* pk_h;             // forward packing in fp16 (encoder convolutions only), or nullptr
+  void* pk_dh;            // data-gradient packing in fp16 (layers of the fp16 backward), or nullptr
 };
 
 struct DecBufs {          // one decoder call
@@ -212,7 +213,7 @@ struct NefPlan {
   // data-gradient epilogues instead of the fp32 tensors (NefConvDesc.out_bits / mask_bits)
   uint32_t *b_eh[3], *b_ey[3], *b_hw, *b_w, *b_h1;
   void *s0_h, *eh_h[3], *ey_h[3];   // fp16 operand copies (8 channels per 16-byte row) of s0, eh[i], ey[i]
-  void *hw_h, *w_h;                 //   ... of w_conv's h and y (operands of the fp16 weight gradients)
+  void *hw_h, *w_h, *h1_h;          //   ... of w_conv's h and y and of z1_conv's h (operands of the fp16 backward)
   void* GA_h[3];                    // loss-scaled fp16 copies of the gradient buffers GA[i] (backward, bwd_f16)
   float* lscale;                    // device scalars {S, 1 / S}: loss scale of the fp16 gradient copies; [2] = amax scratch
   bool bwd_f16;                     // this forward / backward pair runs the fp16 weight gradients
@@ -267,6 +268,7 @@ static void carve_convw(Carver& c, ConvW& w, int pidx, int groups, int cout_g, i
   w.pk_f = c.f32(n);
   w.pk_d = c.f32(n);
   w.pk_h = nullptr;
+  w.pk_dh = nullptr;
 }
 
 static void carve(NefPlan* p, bool dry) {
@@ -279,8 +281,8 @@ static void carve(NefPlan* p, bool dry) {
   p->hw = c.t4(C1, L4); p->w = c.t4(C1, L4); p->h1 = c.t4(C1, L4); p->z1 = c.t4(C1, L4);
   {
     const size_t bytes = ((size_t)(C1 / 8) * p->s0.cs + NEF_GUARD_ROWS) * 16;
-    void** hp[12] = {&p->s0_h, &p->eh_h[0], &p->eh_h[1], &p->eh_h[2], &p->ey_h[0], &p->ey_h[1], &p->ey_h[2], &p->hw_h, &p->w_h,
-                     &p->GA_h[0], &p->GA_h[1], &p->GA_h[2]};
+    void** hp[13] = {&p->s0_h, &p->eh_h[0], &p->eh_h[1], &p->eh_h[2], &p->ey_h[0], &p->ey_h[1], &p->ey_h[2], &p->hw_h, &p->w_h,
+                     &p->h1_h, &p->GA_h[0], &p->GA_h[1], &p->GA_h[2]};
     for (auto q : hp) *q = c.take(bytes);
     p->lscale = c.f32(4);
   }
@@ -343,12 +345,15 @@ static void carve(NefPlan* p, bool dry) {
   for (int i = 0; i < 6; ++i) {
     carve_convw(c, p->enc[i], P_ENC + i, G, 128, 128, 7);
     p->enc[i].pk_h = c.take((size_t)G * 128 * 128 * 7 * 2);
+    p->enc[i].pk_dh = c.take((size_t)G * 128 * 128 * 7 * 2);
   }
   carve_convw(c, p->wc[0], P_WCONV + 0, G, 128, 128, 3);
   carve_convw(c, p->wc[1], P_WCONV + 1, G, 128, 128, 3);
   carve_convw(c, p->z1c[0], P_Z1 + 0, G, 128, 64, 3);
   carve_convw(c, p->z1c[1], P_Z1 + 1, G, 128, 128, 3);
   carve_convw(c, p->z1c[2], P_Z1 + 2, G, 128, 64, 1);
+  for (ConvW* w : {&p->wc[0], &p->wc[1], &p->z1c[0], &p->z1c[1], &p->z1c[2]})
+    w->pk_dh = c.take((size_t)w->groups * w->cout_g * w->cin_g * w->taps * 2);
   carve_convw(c, p->z2c1[0], P_Z2C1 + 0, G, 128, 64, 3);
   carve_convw(c, p->z2c1[1], P_Z2C1 + 1, G, 128, 128, 3);
   carve_convw(c, p->z2c1[2], P_Z2C1 + 2, G, 128, 64, 1);
@@ -501,6 +506,12 @@ static int pack_dgrad(NefPackTable& t, const ConvW& w, const float* const* P, cu
   }
   return queue_pack(t, P[w.pidx], w.pk_d, w.groups, w.cin_g, w.cout_g, w.taps, (int64_t)w.cout_g * w.cin_g * w.taps,
                     w.taps, (int64_t)w.cin_g * w.taps, 1, 1, s);
+}
+
+// the same in fp16 (layers of the fp16 backward; cin_g <= 128 there)
+static int pack_dgrad_h(NefPackTable& t, const ConvW& w, const float* const* P, cudaStream_t s) {
+  return queue_pack(t, P[w.pidx], reinterpret_cast<float*>(w.pk_dh), w.groups, w.cin_g, w.cout_g, w.taps,
+                    (int64_t)w.cout_g * w.cin_g * w.taps, w.taps, (int64_t)w.cin_g * w.taps, 1, 1 | 4, s);
 }
 
 static int pack_dec1_lo(NefPackTable& t, NefPlan* p, const float* const* P, cudaStream_t s, const float* nscale = nullptr) {
@@ -742,6 +753,7 @@ extern "C" int nef_forward(NefPlan* p, const NefForwardArgs* a, nef_stream_t sv)
   {
     BlockIO io{p->w, 0, 32, p->h1, p->z1, &p->z1c[0], &p->z1c[1], &p->z1c[2], P[P_Z1 + 3], G};
     if (a->save_for_backward) io.hbits = p->b_h1;
+    if (p->bwd_f16) io.h16 = p->h1_h;
     RUN(block_fwd(io, dp, seed + 4, nullptr, s));
   }
   RUN(window_extract(p->w, p->xw, G, p->win, s));
@@ -821,8 +833,40 @@ static int wgrad_h(const void* dy16, const T4& dy, int dy_off, int dy_gs, const 
   d.sg = (int64_t)w.cout_g * w.cin_g * w.taps; d.sm = (int64_t)w.cin_g * w.taps; d.sn = w.taps; d.st = 1;
   return nef_gconv_wgrad_f16(&d, dy16, x16, inv_scale, (nef_stream_t)s);
 }
+extern "C" int nef_bias_grad_tc(const NefWgradDesc* d, nef_stream_t s);
 static int block_bwd(const BlockBwd& b, float drop_p, CD& fin, cudaStream_t s) {
   const BlockIO& io = b.io;
+  // Full fp16 backward of the block: every operand of its convolutions' data and weight gradients is an fp16 copy (the
+  // gradient copies carry the loss scale S: accumulators are multiplied by 1 / S, lscale[1]).  gh is then kept in fp16 only.
+  const bool h = b.lscale && b.gy16 && b.gh16 && io.x16 && io.h16 && io.c1->pk_dh && io.c2->pk_dh && (!io.cr || io.cr->pk_dh);
+  if (h) {
+    const float* inv = b.lscale + 1;
+    RUN(wgrad_h(b.gy16, b.gy, 0, 32, io.h16, io.h, 0, 32, *io.c2, b.dw2, inv, s));
+    if (io.cr) {
+      RUN(wgrad_h(b.gy16, b.gy, 0, 32, io.x16, io.x, io.x_off, io.x_gs, *io.cr, b.dwr, inv, s));
+      if (b.dbr) {
+        NefWgradDesc d;
+        memset(&d, 0, sizeof(d));
+        d.dy = reinterpret_cast<const float*>(b.gy.p); d.dy_cstride = b.gy.cs; d.dy_c4_off = 0; d.dy_c4_gstride = 32;
+        d.cout_g = io.cr->cout_g; d.groups = io.cr->groups; d.rows = b.gy.cs; d.db = b.dbr;
+        RUN(nef_bias_grad_tc(&d, (nef_stream_t)s));
+      }
+    }
+    CD a(io.groups, 128, io.x);
+    a.term16(b.gy16, b.gy.cs, 0, 16, 128, io.c2->taps, io.c2->pk_dh).out(b.gh, 0, 32)
+        .mask(io.h, 0, 32, 1, 1.f / (1.f - drop_p)).round().y16s(b.gh16, b.lscale);
+    a.d.acc_scale = inv;
+    a.d.y = nullptr;   // gh: fp16 copy only
+    if (io.hbits) a.mbits(io.hbits);
+    RUN(a.run(s));
+    RUN(wgrad_h(b.gh16, b.gh, 0, 32, io.x16, io.x, io.x_off, io.x_gs, *io.c1, b.dw1, inv, s));
+    fin.term16(b.gh16, b.gh.cs, 0, 16, 128, io.c1->taps, io.c1->pk_dh);
+    fin.d.acc_scale = inv;
+    if (io.cr) fin.term16(b.gy16, b.gy.cs, 0, 16, 128, 1, io.cr->pk_dh);
+    else fin.res(b.gy, 0, 32);
+    RUN(fin.run(s));
+    return 0;
+  }
   if (b.gy16 && io.h16) RUN(wgrad_h(b.gy16, b.gy, 0, 32, io.h16, io.h, 0, 32, *io.c2, b.dw2, b.lscale + 1, s));
   else RUN(wgrad_std(b.gy, 0, 32, io.h, 0, 32, *io.c2, b.dw2, nullptr, s));
   if (io.cr) RUN(wgrad_std(b.gy, 0, 32, io.x, io.x_off, io.x_gs, *io.cr, b.dwr, b.dbr, s));
@@ -851,7 +895,7 @@ static int decoder_bwd(NefPlan* p, const float* const* P, float* const* Gd, int 
   auto gb = [&](int i) { return p->bn_training ? (float*)nullptr : Gd[i]; };
   // output layer + bn4 statistics
   RUN(dec_out_bwd(d.c4, d.bn[3], P[P_OUT_W], d.out, dout, p->dg4, g(P_OUT_W), g(P_OUT_B), s));
-  RUN(bnbwd_apply(p->dg4, d.c4, d.bn[3], P[P_DEC3 + 9], n1, p->dg4, g(P_DEC3 + 9), g(P_DEC3 + 10), s));
+  RUN(bnbwd_apply(p->dg4, d.c4, d.bn[3], P[P_DEC3 + 9], n1, p->dg4, g(P_DEC3 + 9), g(P_DEC3 + 10), p->bn_training, s));
   RUN(wgrad_std(p->dg4, 0, 0, d.a3, 0, 0, p->decw[3], g(P_DEC3 + 7), gb(P_DEC3 + 8), s));
   {
     CD c(1, 64, p->dg4);
@@ -859,7 +903,7 @@ static int decoder_bwd(NefPlan* p, const float* const* P, float* const* Gd, int 
     RUN(c.run(s));
   }
   RUN(bnbwd_stats(p->dg3, d.c3, d.bn[2], s));
-  RUN(bnbwd_apply(p->dg3, d.c3, d.bn[2], P[P_DEC3 + 2], n1, p->dg3, g(P_DEC3 + 2), g(P_DEC3 + 3), s));
+  RUN(bnbwd_apply(p->dg3, d.c3, d.bn[2], P[P_DEC3 + 2], n1, p->dg3, g(P_DEC3 + 2), g(P_DEC3 + 3), p->bn_training, s));
   RUN(wgrad_std(p->dg3, 0, 0, d.u1, 0, 0, p->decw[2], g(P_DEC3 + 0), gb(P_DEC3 + 1), s));
   {
     CD c(1, 128, p->dg3);
@@ -868,7 +912,7 @@ static int decoder_bwd(NefPlan* p, const float* const* P, float* const* Gd, int 
   }
   RUN(up_adjoint(p->du1, p->dg2, s));
   RUN(bnbwd_stats(p->dg2, d.c2, d.bn[1], s));
-  RUN(bnbwd_apply(p->dg2, d.c2, d.bn[1], P[P_DEC1 + 9], n2, p->dg2, g(P_DEC1 + 9), g(P_DEC1 + 10), s));
+  RUN(bnbwd_apply(p->dg2, d.c2, d.bn[1], P[P_DEC1 + 9], n2, p->dg2, g(P_DEC1 + 9), g(P_DEC1 + 10), p->bn_training, s));
   RUN(wgrad_std(p->dg2, 0, 0, d.a1, 0, 0, p->decw[1], g(P_DEC1 + 7), gb(P_DEC1 + 8), s));
   {
     CD c(1, 128, p->dg2);
@@ -876,7 +920,7 @@ static int decoder_bwd(NefPlan* p, const float* const* P, float* const* Gd, int 
     RUN(c.run(s));
   }
   RUN(bnbwd_stats(p->dg1, d.c1, d.bn[0], s));
-  RUN(bnbwd_apply(p->dg1, d.c1, d.bn[0], P[P_DEC1 + 2], n2, p->dg1, g(P_DEC1 + 2), g(P_DEC1 + 3), s));
+  RUN(bnbwd_apply(p->dg1, d.c1, d.bn[0], P[P_DEC1 + 2], n2, p->dg1, g(P_DEC1 + 2), g(P_DEC1 + 3), p->bn_training, s));
   RUN(wgrad_std(p->dg1, 0, 0, p->u0[slot], 0, 0, p->decw[0], g(P_DEC1 + 0), gb(P_DEC1 + 1), s));
   {
     CD c(2, 128, p->dg1);  // 256 output channels as two sub-groups reading the same input
@@ -903,7 +947,11 @@ extern "C" int nef_backward(NefPlan* p, const NefBackwardArgs* a, nef_stream_t s
 
   NefPackTable packs;
   packs.n = 0;
-  RUN(for_all_convw(p, [&](const ConvW& w) { return pack_dgrad(packs, w, P, s); }));
+  const bool f16 = p->bwd_f16 && g_conv_impl == 1;
+  RUN(for_all_convw(p, [&](const ConvW& w) {
+    if (f16 && w.pk_dh) return pack_dgrad_h(packs, w, P, s);   // the TF32 data-gradient packing of these layers is not read
+    return pack_dgrad(packs, w, P, s);
+  }));
   for (int t = 0; t < 2; ++t)  // ConvTranspose dgrad: dx[l] = sum_t W_t^T dy[2l + t] ; N' = ci (128), K' = co (64)
     RUN(queue_pack(packs, P[P_CT_W] + t, p->ct_d[t], 7 * G, 128, 64, 1, 128LL * 64 * 2, 64 * 2, 2, 0, 0, s));
   RUN(nef_pack_weights_batch(&packs, s));
@@ -912,7 +960,6 @@ extern "C" int nef_backward(NefPlan* p, const NefBackwardArgs* a, nef_stream_t s
     for (int i = 0; i < 4; ++i) cudaMemsetAsync(p->dec[k].bn[i].s1, 0, 2 * 128 * sizeof(double), s);
 
   const float* douts[3] = {a->dout, a->dout_p, a->dout_l};
-  const bool f16 = p->bwd_f16 && g_conv_impl == 1;
   const float* ls = p->lscale;
   if (f16) RUN(grad_loss_scale(a->dout, a->dout_p, a->dout_l, (long)B * p->L, p->lscale, s));
   for (int k = 0; k < 3; ++k) {
@@ -924,6 +971,7 @@ extern "C" int nef_backward(NefPlan* p, const NefBackwardArgs* a, nef_stream_t s
   for (int k = 0; k < 3; ++k) { lb.du0[k] = p->du0[k]; lb.lat[k] = p->lat[k]; }
   lb.z1 = p->z1; lb.z2o = p->z2o; lb.rois = p->rois_in; lb.q = p->q; lb.q_stride = 256; lb.G = G; lb.c1 = p->c1; lb.c2 = p->c2;
   lb.gz1 = p->GA[0]; lb.gz2o = p->gz2o; lb.dq = p->dq;
+  lb.gz1_h = f16 ? p->GA_h[0] : nullptr; lb.s16 = ls;
   RUN(latent_bwd(lb, s));
   if (Gd[P_MLP2_W]) RUN(angular_bwd(p->query_in, p->dq, Gd[P_MLP2_W], Gd[P_MLP2_B], B, 256, s));
 
@@ -934,8 +982,8 @@ extern "C" int nef_backward(NefPlan* p, const NefBackwardArgs* a, nef_stream_t s
     bb.io.hbits = p->b_h1;
     CD fin(G, 64, p->w);
     fin.out(p->GA[2], 0, 32).mask(p->w, 0, 32, 1, 1.f).mbits(p->b_w).round();
-    if (f16) {   // conv1's weight gradient reads gh16 and the z1 half of w's fp16 copy; gy comes from latent_bwd (fp32 only)
-      bb.io.x16 = p->w_h; bb.gh16 = p->GA_h[1]; bb.lscale = ls;
+    if (f16) {
+      bb.io.x16 = p->w_h; bb.io.h16 = p->h1_h; bb.gy16 = p->GA_h[0]; bb.gh16 = p->GA_h[1]; bb.lscale = ls;
       fin.y16s(p->GA_h[2], ls);
     }
     RUN(block_bwd(bb, dp, fin, s));

@@ -1,6 +1,6 @@
 """GPU: where does the production path differ from the oracle under the B200 arithmetic model?  Compares the 'gen' latents
 (z1 after z1_conv, z2 after the z2_conv2 chain) and the three outputs, dropout off, for the production path and its
-precision switches.  python tools/diag_model_vs_gpu.py"""
+precision switches.  python tests/probe_model_vs_device.py"""
 import os, random, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "electrocardio-panorama_b200"))

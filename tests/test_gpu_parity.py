@@ -203,6 +203,45 @@ def test_oracle_fixed_upstream(B, G, L, seed, ragged, mode_name):
         np.testing.assert_allclose(sd[k].numpy(), v.numpy(), rtol=1e-4 if exact else 2e-3, atol=1e-5 if exact else 2e-4)
 
 
+@pytest.mark.parametrize("mode_name", ["exact_simt", "tf32_tc"])
+def test_eval_mode_backward(mode_name):
+    """module.eval() + phase='train' under autograd (a caller fine-tuning with frozen BatchNorm statistics): the forward uses
+    the running statistics, so the BatchNorm gradient has no batch-mean terms (dc = gamma * invstd * g) and the convolution
+    biases in front of it DO get gradients.  Exact tier against the oracle with bn_training=False."""
+    dev = torch.device("cuda:0")
+    exact = MODES[mode_name][1] == 1
+    B, G, L, seed = 3, 2, 256, 19
+    P = O.make_params(G, seed)
+    inp = O.make_inputs(B, G, L, seed)
+    random.seed(seed)
+    c1, c2 = random.randint(0, G - 1), random.randint(0, G - 1)
+    gen = torch.Generator().manual_seed(seed)
+    ups = [torch.randn(B, 1, L, generator=gen) for _ in range(3)]
+    with mode(mode_name):
+        m = _model(G, P, dev, train=False)
+        random.seed(seed)
+        d = _to(inp, dev)
+        outs = m(d["x"], d["input_thetas"], d["query_theta"], d["rois"], phase="train")
+        torch.autograd.backward(outs, [u.to(dev) for u in ups])
+        sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+        named = dict(m.named_parameters())
+    Po = {k: v.clone() for k, v in P.items()}
+    for n in O.live_param_names(G):
+        Po[n].requires_grad_(True)
+    oo = O.forward(Po, inp["x"], inp["input_thetas"], inp["query_theta"], inp["rois"], phase="train", lead_choice=(c1, c2),
+                   bn_training=False)
+    torch.autograd.backward(oo, ups)
+    for a, b in zip(outs, oo):
+        np.testing.assert_allclose(a.detach().cpu().numpy(), b.detach().numpy(), rtol=EXACT_OUT_RTOL if exact else OUT_RTOL, atol=0)
+    for n in O.live_param_names(G):   # including the conv biases in front of the BatchNorms (ZERO_GRAD_PARAMS in training mode)
+        got, ref = named[n].grad.detach().cpu().double(), Po[n].grad.double()
+        err = float((got - ref).norm() / (ref.norm() + 1e-30))
+        assert err < (EXACT_GRAD_REL_L2 if exact else TF32_GRAD_REL_L2), (n, err)
+    for k in P:   # running statistics untouched
+        if "running_" in k or "num_batches" in k:
+            assert torch.equal(sd[k], P[k]), k
+
+
 def test_long_sequence_config4_shape():
     """BASELINE config 4 shape (12 leads x 20000 samples, PTB rate) at a batch the CPU oracle finishes in seconds:
     training-mode outputs of the production path within the north-star tolerance."""

@@ -37,10 +37,11 @@ PAT_ACT_REL_L2 = 1e-3      # every exported intermediate activation vs the same
 FP32_GRAD_REL_L2 = 0.15    # gradients vs the fp32 oracle (ReLU-mask flips, see module docstring)
 FP32_GRAD_COS = 0.99
 
-# epilogue codes of conv_tc_persist_kernel the 256 x 12 x 5000 training step launches (profiles/r01_step_b256_per_kernel_*):
-#   5164 / 5158 / 1318 encoder forward (dropout, fp16 copies, bit planes, angular scale), 1068 / 1062 / 37 k3 forward,
-#   513 decoder forward with BatchNorm statistics, 2080 / 2082 / 2338 / 2 masked data gradients, 0 / 32 decoder data gradients
-BENCH_EPI_DROPOUT = {5164, 5158, 1318, 1068, 1062, 37, 513, 2080, 2082, 2338, 2, 0, 32}
+# epilogue codes of conv_tc_persist_kernel the 256 x 12 x 5000 training step launches (profiles/r02_step_b256_per_kernel_*):
+#   5164 / 5158 / 5414 encoder and w_conv forward (dropout, fp16 copies, bit planes, angular scale), 1068 / 37 z1_conv forward,
+#   513 decoder forward with BatchNorm statistics, 14368 / 14370 / 14626 masked data gradients that also write the loss-scaled
+#   fp16 gradient copy, 8194 the unmasked one of the first encoder block, 0 / 32 decoder data gradients
+BENCH_EPI_DROPOUT = {5164, 5158, 5414, 37, 513, 14368, 14370, 14626, 8194, 0, 32}
 
 
 BLOCKS = ("W_encoder.layer1.0", "W_encoder.layer1.1", "W_encoder.layer1.2", "w_conv.0", "z1_conv.0", "z2_conv1.0", "z2_conv2.0",
@@ -174,7 +175,7 @@ def test_bench_dispatch_dropout_on():
     """32 x 12 x 5000, dropout 0.2, natural dispatch: every big convolution (encoder, w_conv, z1_conv, decoder; forward, data
     gradient) runs the persistent kernel with the epilogues of the benchmarked step, the weight gradients run multi-split."""
     r = _run_case(32, 12, 5000, 31, 0.2, 0)
-    assert r["dispatch_counts"][0] > 0 and r["dispatch_counts"][3] > 0, r["dispatch_counts"]
+    assert r["dispatch_counts"][0] > 0 and r["dispatch_counts"][3] > 0 and r["dispatch_counts"][5] > 0, r["dispatch_counts"]
     missing = BENCH_EPI_DROPOUT - set(r["persistent_epilogues"])
     assert not missing, ("persistent epilogues of the benchmarked step that this test did not run", sorted(missing))
     _check(r)

@@ -2,6 +2,8 @@
     python tools/kernel_metrics.py gpurun_out/x.csv [hbm_peak_gbs]
 Aggregates by kernel: launches, total ms, DRAM GB moved, achieved DRAM GB/s (and % of the measured peak), tensor pipe %."""
 import collections, csv, json, os, sys
+second_half = "--second-half" in sys.argv   # two identical steps were profiled: keep the second (no first-call setup)
+sys.argv = [a for a in sys.argv if a != "--second-half"]
 path = sys.argv[1]
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 try:
@@ -19,6 +21,10 @@ for r in rows:
     if n.startswith("dram__bytes"):
         v *= {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
     d[n] = v
+if second_half:
+    keys = list(launch.keys())
+    for k in keys[:len(keys) // 2]:
+        del launch[k]
 agg = collections.OrderedDict()
 for d in launch.values():
     a = agg.setdefault(d["name"][:58], {"n": 0, "ms": 0.0, "bytes": 0.0, "tc": 0.0})
