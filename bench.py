@@ -266,7 +266,7 @@ def main():
             os.close(saved_fd)
     import network
     from network import _native as N
-    from network.optim import FlatSGD, allreduce_gradients
+    from network.optim import FlatSGD
     from dataset.synthetic import make_inputs  # product-side synthetic batches; oracle/ is only used by cpu_baseline()
 
     G, L, B = 12, args.length, args.batch
@@ -286,10 +286,8 @@ def main():
     def step(inp):
         outs = model(inp["x"], inp["input_thetas"], inp["query_theta"], inp["rois"], phase="train")
         loss = loss_fn(outs[0], outs[1], outs[2], inp["target"], Cfg)[0]
-        loss.backward()
-        if world > 1:
-            allreduce_gradients(model)
-        opt.step(world)
+        loss.backward()      # world > 1: backward() itself averages the gradients over the ranks (two bucketed NCCL
+        opt.step()           # all-reduces of the flat buffer, the first overlapped with the encoder's backward)
         opt.zero_grad()
         return loss
 

@@ -304,9 +304,64 @@ __global__ void cbl4_to_ncl_kernel(const float4* __restrict__ src, float* __rest
   }
 }
 
+// fp16 copy `half8 [C/8][B * Lp]` (NefConvDesc.y16) -> (B, C, L) fp32
+__global__ void h8_to_ncl_kernel(const uint4* __restrict__ src, float* __restrict__ dst, int B, int C, int L) {
+  const int Lp = L + 2 * NEF_HALO;
+  const long total = (long)B * (C / 8) * L;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int l = i % L;
+    long r = i / L;
+    const int b = r % B;
+    const int c8 = r / B;
+    const uint4 v = src[(long)c8 * B * Lp + (long)b * Lp + NEF_HALO + l];
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    float* o = dst + ((long)b * C + c8 * 8) * L + l;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const __half2 h = *reinterpret_cast<const __half2*>(&w[j]);
+      o[(long)(2 * j) * L] = __low2float(h);
+      o[(long)(2 * j + 1) * L] = __high2float(h);
+    }
+  }
+}
+
+// one-bit planes `uint32 [C/32][B * Lp]` (NefConvDesc.out_bits: bit 4 i + j <-> channel 32 plane + 4 i + j) -> (B, C, L) 0 / 1
+__global__ void bits_to_ncl_kernel(const uint32_t* __restrict__ src, float* __restrict__ dst, int B, int C, int L) {
+  const int Lp = L + 2 * NEF_HALO;
+  const long total = (long)B * (C / 32) * L;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int l = i % L;
+    long r = i / L;
+    const int b = r % B;
+    const int pl = r / B;
+    const uint32_t w = src[(long)pl * B * Lp + (long)b * Lp + NEF_HALO + l];
+    float* o = dst + ((long)b * C + pl * 32) * L + l;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) o[(long)j * L] = (w >> j) & 1u ? 1.f : 0.f;
+  }
+}
+
 }  // namespace nef
 
 using namespace nef;
+
+extern "C" int nef_bits_to_ncl(const uint32_t* src, float* dst, int B, int C, int L, nef_stream_t s) {
+  const long total = (long)B * (C / 32) * L;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  bits_to_ncl_kernel<<<blocks, 256, 0, (cudaStream_t)s>>>(src, dst, B, C, L);
+  NEF_CHECK_LAUNCH("bits_to_ncl_kernel");
+  return 0;
+}
+
+extern "C" int nef_h8_to_ncl(const void* src, float* dst, int B, int C, int L, nef_stream_t s) {
+  const long total = (long)B * (C / 8) * L;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  h8_to_ncl_kernel<<<blocks, 256, 0, (cudaStream_t)s>>>(reinterpret_cast<const uint4*>(src), dst, B, C, L);
+  NEF_CHECK_LAUNCH("h8_to_ncl_kernel");
+  return 0;
+}
 
 extern "C" int nef_gconv_fwd_simt(const NefConvDesc* d, nef_stream_t s) {
   dim3 grid((unsigned)((d->rows + ST_ROWS - 1) / ST_ROWS), (unsigned)(d->groups * (d->N / ST_N)));

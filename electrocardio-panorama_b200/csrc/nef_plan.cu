@@ -3,6 +3,7 @@
 // kernel; every launch goes to the caller's stream, all memory comes from the caller's workspace.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -42,6 +43,8 @@ extern "C" int nef_gconv_wgrad_simt(const NefWgradDesc* d, nef_stream_t s);
 extern "C" int nef_gconv_fwd_tc(const NefConvDesc* d, nef_stream_t s);
 extern "C" int nef_gconv_wgrad_tc(const NefWgradDesc* d, nef_stream_t s);
 extern "C" int nef_tc_init(void);
+extern "C" int nef_h8_to_ncl(const void* src, float* dst, int B, int C, int L, nef_stream_t s);
+extern "C" int nef_bits_to_ncl(const uint32_t* src, float* dst, int B, int C, int L, nef_stream_t s);
 
 static int g_conv_impl = 1;
 extern "C" int nef_set_conv_impl(int impl) {
@@ -64,6 +67,9 @@ extern "C" int nef_set_fwd_f16(int on) { g_fwd_f16 = on; return 0; }
 // (nef_gconv_wgrad_f16; the TF32 kernel has to re-tile every staged tile in shared memory).  0 = TF32 backward everywhere.
 static int g_bwd_f16 = 1;
 extern "C" int nef_set_bwd_f16(int on) { g_bwd_f16 = on; return 0; }
+// A/B switches (environment, read at nef_init): NEF_KEEP_H32=1 also stores the fp32 hidden activations of the big blocks;
+// NEF_K3_TF32=1 runs the forward of w_conv / z1_conv on TF32 operands
+static int g_keep_h32 = 0, g_k3_tf32 = 0;
 extern "C" int nef_gconv_wgrad_f16(const NefWgradDesc* d, const void* dy16, const void* x16, const float* out_scale, nef_stream_t s);
 extern "C" int nef_set_dec1_terms(int n) {
   NEF_REQUIRE(n >= 1 && n <= 3, "nef_set_dec1_terms: 1, 2 or 3");
@@ -90,6 +96,9 @@ extern "C" int nef_init(int device) {
   NEF_REQUIRE(p.major == 10, "nef_init: device %d is sm_%d%d; this library is built for sm_100a (B200) only", device,
               p.major, p.minor);
   cudaSetDevice(device);
+  if (getenv("NEF_KEEP_H32")) g_keep_h32 = atoi(getenv("NEF_KEEP_H32"));
+  if (getenv("NEF_K3_TF32")) g_k3_tf32 = atoi(getenv("NEF_K3_TF32"));
+  if (getenv("NEF_BWD_F16")) g_bwd_f16 = atoi(getenv("NEF_BWD_F16"));
   int rc = elem_init();
   if (rc) return rc;
   return nef_tc_init();
@@ -216,7 +225,8 @@ struct NefPlan {
   void *hw_h, *w_h, *h1_h;          //   ... of w_conv's h and y and of z1_conv's h (operands of the fp16 backward)
   void* GA_h[3];                    // loss-scaled fp16 copies of the gradient buffers GA[i] (backward, bwd_f16)
   float* lscale;                    // device scalars {S, 1 / S}: loss scale of the fp16 gradient copies; [2] = amax scratch
-  bool bwd_f16;                     // this forward / backward pair runs the fp16 weight gradients
+  bool bwd_f16;                     // this forward / backward pair runs the fp16 backward of the big blocks
+  bool h_f16_only;                  // the hidden activations of the big blocks (eh, hw, h1) were stored as fp16 copies only
   void *u0_h[3], *u0lo_h[3];        //   ... of the decoder inputs u0 and of their rounding residuals
   void* dec1_lo_h;                  // fp16 residual of the decoder first conv weights (decw[0].pk_h holds the fp16 weights)
   bool fwd_f16;                     // this forward runs the encoder convolutions on them
@@ -352,8 +362,10 @@ static void carve(NefPlan* p, bool dry) {
   carve_convw(c, p->z1c[0], P_Z1 + 0, G, 128, 64, 3);
   carve_convw(c, p->z1c[1], P_Z1 + 1, G, 128, 128, 3);
   carve_convw(c, p->z1c[2], P_Z1 + 2, G, 128, 64, 1);
-  for (ConvW* w : {&p->wc[0], &p->wc[1], &p->z1c[0], &p->z1c[1], &p->z1c[2]})
+  for (ConvW* w : {&p->wc[0], &p->wc[1], &p->z1c[0], &p->z1c[1], &p->z1c[2]}) {
+    w->pk_h = c.take((size_t)w->groups * w->cout_g * w->cin_g * w->taps * 2);
     w->pk_dh = c.take((size_t)w->groups * w->cout_g * w->cin_g * w->taps * 2);
+  }
   carve_convw(c, p->z2c1[0], P_Z2C1 + 0, G, 128, 64, 3);
   carve_convw(c, p->z2c1[1], P_Z2C1 + 1, G, 128, 128, 3);
   carve_convw(c, p->z2c1[2], P_Z2C1 + 2, G, 128, 64, 1);
@@ -573,6 +585,7 @@ struct BlockIO {
   const void* x16 = nullptr;   // fp16 operand copies: when x16 is set the two convolutions run in kind::f16 (h16 required)
   void* h16 = nullptr;         // fp16 copies of h / y written by the epilogues (operands of the next convolution and / or of
   void* y16 = nullptr;         //   the fp16 weight gradients); optional, also without x16
+  bool h_f16_only = false;     // do not store the fp32 h at all (needs x16 and h16: nothing reads it then)
 };
 
 static int block_fwd(const BlockIO& io, float drop_p, uint64_t seed, const float* bscale, cudaStream_t s) {
@@ -583,13 +596,15 @@ static int block_fwd(const BlockIO& io, float drop_p, uint64_t seed, const float
   a.out(io.h, 0, 32).relu().round();
   if (io.hbits) a.obits(io.hbits);
   if (drop_p > 0.f) a.drop(drop_p, seed);
+  if (io.h_f16_only && io.x16 && io.h16) a.d.y = nullptr;
   RUN(a.run(s));
   CD b(io.groups, 128, io.x);
   if (io.x16) b.term16(io.h16, io.h.cs, 0, 16, 128, io.c2->taps, io.c2->pk_h);
   else b.term(io.h, 0, 32, 128, io.c2->taps, io.c2->pk_f);
   b.out(io.y, 0, 32).relu().round();
   if (io.y16) b.y16(io.y16);
-  if (io.cr) b.term(io.x, io.x_off, io.x_gs, io.cr->cin_g, 1, io.cr->pk_f).bias(io.res_bias);
+  if (io.cr && io.x16) b.term16(io.x16, io.x.cs, io.x_off / 2, io.x_gs / 2, io.cr->cin_g, 1, io.cr->pk_h).bias(io.res_bias);
+  else if (io.cr) b.term(io.x, io.x_off, io.x_gs, io.cr->cin_g, 1, io.cr->pk_f).bias(io.res_bias);
   else b.res(io.x, io.x_off, io.x_gs);
   if (bscale) b.bscale(bscale);
   if (io.ybits) b.obits(io.ybits);
@@ -717,9 +732,12 @@ extern "C" int nef_forward(NefPlan* p, const NefForwardArgs* a, nef_stream_t sv)
   packs.n = 0;
   p->fwd_f16 = g_fwd_f16 && g_conv_impl == 1;
   p->bwd_f16 = p->fwd_f16 && g_bwd_f16 && a->save_for_backward;
+  // the fp32 hidden activations of the big blocks have a reader only in the TF32 backward (its weight gradients)
+  p->h_f16_only = p->fwd_f16 && (p->bwd_f16 || !a->save_for_backward) && !g_keep_h32;
   RUN(for_all_convw(p, [&](const ConvW& w) {
     if (&w >= p->decw && &w < p->decw + 4) return 0;
-    if (p->fwd_f16 && w.pk_h)
+    const bool k3 = (&w >= p->wc && &w < p->wc + 2) || (&w >= p->z1c && &w < p->z1c + 3);
+    if (p->fwd_f16 && w.pk_h && !(k3 && g_k3_tf32))
       return queue_pack(packs, P[w.pidx], reinterpret_cast<float*>(w.pk_h), w.groups, w.cout_g, w.cin_g, w.taps,
                         (int64_t)w.cout_g * w.cin_g * w.taps, (int64_t)w.cin_g * w.taps, w.taps, 1, 4, s);
     return pack_fwd(packs, w, P, s);
@@ -740,20 +758,23 @@ extern "C" int nef_forward(NefPlan* p, const NefForwardArgs* a, nef_stream_t sv)
     if (p->fwd_f16) {
       io.x16 = i == 0 ? p->s0_h : p->ey_h[i - 1];
       io.h16 = p->eh_h[i];
-      io.y16 = (i < 2 || p->bwd_f16) ? p->ey_h[i] : nullptr;
+      io.y16 = p->ey_h[i];
+      io.h_f16_only = p->h_f16_only;
     }
     RUN(block_fwd(io, dp, seed + i, i == 2 ? p->s_in : nullptr, s));
   }
   {
     BlockIO io{p->ey[2], 0, 32, p->hw, p->w, &p->wc[0], &p->wc[1], nullptr, nullptr, G};
     if (a->save_for_backward) { io.hbits = p->b_hw; io.ybits = p->b_w; }
-    if (p->bwd_f16) { io.h16 = p->hw_h; io.y16 = p->w_h; }
+    if (p->fwd_f16 && !g_k3_tf32) { io.x16 = p->ey_h[2]; io.h16 = p->hw_h; io.y16 = p->w_h; io.h_f16_only = p->h_f16_only; }
+    else if (p->bwd_f16) { io.h16 = p->hw_h; io.y16 = p->w_h; }
     RUN(block_fwd(io, dp, seed + 3, nullptr, s));
   }
   {
     BlockIO io{p->w, 0, 32, p->h1, p->z1, &p->z1c[0], &p->z1c[1], &p->z1c[2], P[P_Z1 + 3], G};
     if (a->save_for_backward) io.hbits = p->b_h1;
-    if (p->bwd_f16) io.h16 = p->h1_h;
+    if (p->fwd_f16 && !g_k3_tf32) { io.x16 = p->w_h; io.h16 = p->h1_h; io.h_f16_only = p->h_f16_only; }
+    else if (p->bwd_f16) io.h16 = p->h1_h;
     RUN(block_fwd(io, dp, seed + 4, nullptr, s));
   }
   RUN(window_extract(p->w, p->xw, G, p->win, s));
@@ -1033,6 +1054,10 @@ extern "C" int nef_backward(NefPlan* p, const NefBackwardArgs* a, nef_stream_t s
     RUN(block_bwd(bb, dp, fin, s));
   }
   RUN(window_scatter(p->gxw, p->GA[2], G, p->win, f16 ? p->GA_h[2] : nullptr, ls, s));
+  if (a->ev_late_params_done) {   // every parameter gradient from z1_conv.0 on is final: the caller may start reducing them
+    cudaError_t e = cudaEventRecord((cudaEvent_t)a->ev_late_params_done, s);
+    NEF_REQUIRE(e == cudaSuccess, "nef_backward: cudaEventRecord failed: %s", cudaGetErrorString(e));
+  }
   // ---- w_conv: g_w = GA2, gh = GA0, result (grad of the unscaled last encoder output, pre-ReLU) = GA1
   {
     BlockBwd bb{{p->ey[2], 0, 32, p->hw, p->w, &p->wc[0], &p->wc[1], nullptr, nullptr, G}, p->GA[2], p->GA[0],
@@ -1076,10 +1101,22 @@ extern "C" int nef_backward(NefPlan* p, const NefBackwardArgs* a, nef_stream_t s
 // ---------------------------------------------------------------------------------------------
 // workspace inspection (test hook): named internal tensors of the last forward
 // ---------------------------------------------------------------------------------------------
-struct NamedTensor { const T4* t; const float* v; int n; };
+struct NamedTensor { const T4* t; const float* v; int n; const void* h16; const uint32_t* bits; };
 static bool find_tensor(const NefPlan* p, const char* name, NamedTensor* out) {
-  out->t = nullptr; out->v = nullptr; out->n = 0;
-  const std::string n(name);
+  out->t = nullptr; out->v = nullptr; out->n = 0; out->h16 = nullptr; out->bits = nullptr;
+  std::string n(name);
+  // "<block>.h.mask" / "<block>.y.mask": the one-bit (value != 0) plane the masked data-gradient epilogues read, as 0 / 1 floats
+  if (n.size() > 5 && n.substr(n.size() - 5) == ".mask") {
+    n = n.substr(0, n.size() - 5);
+    struct { const char* name; const T4* t; const uint32_t* b; } planes[] = {
+        {"W_encoder.layer1.0.h", &p->eh[0], p->b_eh[0]}, {"W_encoder.layer1.1.h", &p->eh[1], p->b_eh[1]},
+        {"W_encoder.layer1.2.h", &p->eh[2], p->b_eh[2]}, {"W_encoder.layer1.0.y", &p->ey[0], p->b_ey[0]},
+        {"W_encoder.layer1.1.y", &p->ey[1], p->b_ey[1]}, {"W_encoder.layer1.2.y", &p->ey[2], p->b_ey[2]},
+        {"w_conv.0.h", &p->hw, p->b_hw}, {"w_conv.0.y", &p->w, p->b_w}, {"z1_conv.0.h", &p->h1, p->b_h1}};
+    for (auto& q : planes)
+      if (n == q.name) { out->t = q.t; out->bits = q.b; return true; }
+    return false;
+  }
   auto is = [&](const char* s) { return n == s; };
   auto blk = [&](const char* prefix, const T4& h, const T4& y) {
     const std::string pre(prefix);
@@ -1088,9 +1125,13 @@ static bool find_tensor(const NefPlan* p, const char* name, NamedTensor* out) {
     return false;
   };
   if (is("stem")) { out->t = &p->s0; return true; }
+  // hidden activations that the last forward kept as fp16 copies only
+  auto h_only = [&](const void* h16) { if (p->h_f16_only && out->t && n.size() > 2 && n.substr(n.size() - 2) == ".h") out->h16 = h16; return true; };
   for (int i = 0; i < 3; ++i)
-    if (blk(("W_encoder.layer1." + std::to_string(i)).c_str(), p->eh[i], p->ey[i])) return true;
-  if (blk("w_conv.0", p->hw, p->w) || blk("z1_conv.0", p->h1, p->z1) || blk("z2_conv1.0", p->hz, p->z2c) ||
+    if (blk(("W_encoder.layer1." + std::to_string(i)).c_str(), p->eh[i], p->ey[i])) return h_only(p->eh_h[i]);
+  if (blk("w_conv.0", p->hw, p->w)) return h_only(p->hw_h);
+  if (blk("z1_conv.0", p->h1, p->z1)) return h_only(p->h1_h);
+  if ( blk("z2_conv1.0", p->hz, p->z2c) ||
       blk("z2_conv2.0", p->h20, p->y20) || blk("z2_conv2.2", p->h22, p->z2o))
     return true;
   if (is("roi_align")) { out->t = &p->ra; return true; }
@@ -1119,9 +1160,20 @@ extern "C" int nef_plan_tensor_info(const NefPlan* p, const char* name, int* C, 
   else { *C = t.n; *L = 0; }
   return 0;
 }
+// Test hook: overwrite the fp32 storage of a named activation (valid rows only; the zero halo is part of the layout) with
+// NaN, so that a test can prove that nothing reads a tensor the dataflow claims to have dropped.
+extern "C" int nef_plan_poison(NefPlan* p, const char* name, float* scratch, nef_stream_t s) {
+  NamedTensor t;
+  NEF_REQUIRE(p && p->bound && name && scratch && find_tensor(p, name, &t) && t.t && !t.bits,
+              "nef_plan_poison: unknown tensor '%s'", name ? name : "");
+  cudaMemsetAsync(scratch, 0xFF, (size_t)p->B * t.t->C * t.t->L * sizeof(float), (cudaStream_t)s);   // all-ones bits = NaN
+  return nef_ncl_to_cbl4(scratch, reinterpret_cast<float*>(t.t->p), p->B, t.t->C, t.t->L, 0, s);
+}
 extern "C" int nef_plan_export(NefPlan* p, const char* name, float* dst, nef_stream_t s) {
   NamedTensor t;
   NEF_REQUIRE(p && p->bound && name && find_tensor(p, name, &t), "nef_plan_export: unknown tensor '%s'", name ? name : "");
+  if (t.t && t.bits) return nef_bits_to_ncl(t.bits, dst, p->B, t.t->C, t.t->L, s);
+  if (t.t && t.h16) return nef_h8_to_ncl(t.h16, dst, p->B, t.t->C, t.t->L, s);
   if (t.t) return nef_cbl4_to_ncl(reinterpret_cast<const float*>(t.t->p), dst, p->B, t.t->C, t.t->L, s);
   cudaError_t e = cudaMemcpyAsync(dst, t.v, (size_t)t.n * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)s);
   NEF_REQUIRE(e == cudaSuccess, "nef_plan_export: copy failed: %s", cudaGetErrorString(e));

@@ -56,7 +56,7 @@ class NefForwardArgs(C.Structure):
 
 class NefBackwardArgs(C.Structure):
     _fields_ = [("params", C.POINTER(C.c_void_p)), ("grads", C.POINTER(C.c_void_p)), ("dout", C.c_void_p),
-                ("dout_p", C.c_void_p), ("dout_l", C.c_void_p)]
+                ("dout_p", C.c_void_p), ("dout_l", C.c_void_p), ("ev_late_params_done", C.c_void_p)]
 
 
 # name -> (restype, argtypes); every symbol include/nefnet_b200.h declares
@@ -90,6 +90,7 @@ SIGNATURES = {
     "nef_plan_bind": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "nef_plan_tensor_info": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "nef_plan_export": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_void_p]),
+    "nef_plan_poison": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_void_p]),
     "nef_forward": (C.c_int, [C.c_void_p, C.POINTER(NefForwardArgs), C.c_void_p]),
     "nef_backward": (C.c_int, [C.c_void_p, C.POINTER(NefBackwardArgs), C.c_void_p]),
     "nef_gen_ecg": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,

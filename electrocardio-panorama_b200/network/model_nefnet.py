@@ -67,6 +67,7 @@ class _NefFunction(torch.autograd.Function):
         outs = model._run_forward(x, input_thetas, query_theta, rois, None, N.PHASE_TRAIN, c1, c2, save=True)
         ctx.model = model
         ctx.token = model._fwd_token
+        ctx.n_live = len(live_params)
         return outs
 
     @staticmethod
@@ -75,8 +76,11 @@ class _NefFunction(torch.autograd.Function):
         if ctx.token != model._fwd_token:
             raise RuntimeError("Model_nefnet (B200): backward() after a newer forward(); only the latest training "
                                "forward is retained")
-        grads = model._run_backward(dout, dout_p, dout_l)
-        return (None,) * 7 + tuple(grads)
+        # The parameter gradients are written straight into the flat gradient buffer and every p.grad is pointed at its view
+        # of it (no per-step copies; a stock torch optimiser, FlatSGD and the data-parallel all-reduce all see one buffer),
+        # so autograd itself receives no parameter gradients.
+        model._run_backward(dout, dout_p, dout_l)
+        return (None,) * (7 + ctx.n_live)
 
 
 class Model_nefnet(nn.Module):
@@ -95,6 +99,13 @@ class Model_nefnet(nn.Module):
         self._step = 0
         self._flat = None
         self._flat_grad = None
+        # data parallel (one process per GPU): when a torch.distributed process group with more than one rank is initialised,
+        # backward() itself averages the gradients over the ranks -- two bucketed all-reduces, the first overlapped with
+        # the encoder's backward -- so the reference's unmodified solver.py:232-235 (backward(); optim.step()) trains data
+        # parallel under torchrun.  Set False to exchange gradients yourself (network.optim.allreduce_gradients).
+        self.ddp_allreduce = True
+        self._ddp_ready = False
+        self._grads_valid = False
         self._build_parameters()
 
     # ------------------------------------------------------------------ parameters
@@ -216,6 +227,9 @@ class Model_nefnet(nn.Module):
                 if p.dtype != torch.float32:
                     raise RuntimeError("Model_nefnet (B200): parameters must be float32")
             self._flatten(device)
+            self._ddp_ready = False
+        if not self._ddp_ready and self._ddp_world() > 1 and self.training:
+            self._ddp_setup(device)
 
     def _param_ptr_array(self):
         arr = (C.c_void_p * len(self._names))()
@@ -283,7 +297,8 @@ class Model_nefnet(nn.Module):
         a.lead_choice_z1, a.lead_choice_z2 = int(c1), int(c2)
         a.drop_p = float(self.dropout_p) if self.training else 0.0
         a.save_for_backward = 1 if save else 0
-        a.drop_seed = ((torch.initial_seed() * 6364136223846793005) + self._step) & 0x0FFFFFFFFFFFFFFF
+        a.drop_seed = (((torch.initial_seed() * 6364136223846793005) + self._step) ^ (self._rank() * 0x9E3779B97F4A7C15)) \
+            & 0x0FFFFFFFFFFFFFFF   # per step, and per rank: data-parallel replicas must not share dropout masks
         self._step += 1
         self._last_drop_seed = int(a.drop_seed)   # tests rebuild the keep masks from it (tests/_dropmask.py)
         if phase == N.PHASE_GEN:
@@ -305,11 +320,44 @@ class Model_nefnet(nn.Module):
         self._saved = (x, input_thetas, query_theta, rois, plan) if save else None
         return outs
 
+    @staticmethod
+    def _rank():
+        import torch.distributed as dist
+        return dist.get_rank() if (dist.is_available() and dist.is_initialized()) else 0
+
+    def _ddp_world(self):
+        import torch.distributed as dist
+        if self.ddp_allreduce and dist.is_available() and dist.is_initialized():
+            return dist.get_world_size()
+        return 1
+
+    def _ddp_setup(self, device):
+        """Once per process group: every rank starts from rank 0's parameters and BatchNorm buffers (what DataParallel's
+        replicate does every step, solver.py:32-34), and the side stream / event of the overlapped all-reduce exist."""
+        import torch.distributed as dist
+        with torch.no_grad():
+            dist.broadcast(self._flat, src=0)
+            for b in self.buffers():
+                dist.broadcast(b, src=0)
+        self._ddp_stream = torch.cuda.Stream(device=device)
+        self._ddp_event = torch.cuda.Event()
+        self._ddp_event.record()          # creates the underlying cudaEvent_t; nef_backward re-records it
+        self._ddp_split = self._offsets["z1_conv.0.conv1.weight"]
+        self._ddp_ready = True
+
     def _run_backward(self, dout, dout_p, dout_l):
+        import torch.distributed as dist
         lib = N.load()
         x, input_thetas, query_theta, rois, plan = self._saved
         device = x.device
-        self._flat_grad.zero_()
+        world = self._ddp_world()
+        params = dict(self.named_parameters())
+        # nef_backward accumulates (+=) like autograd: start from zero unless the caller kept the previous gradients (p.grad
+        # still set).  With the built-in all-reduce that stays exact: what was accumulated before is already the same mean on
+        # every rank, and averaging (mean + local) over the ranks gives mean + mean(local).
+        accumulate = any(p.grad is not None and p.grad.data_ptr() == self._grad_views[n].data_ptr() for n, p in params.items())
+        if not accumulate:
+            self._flat_grad.zero_()
         names = self._names
         garr = (C.c_void_p * len(names))()
         for i, n in enumerate(names):
@@ -325,9 +373,27 @@ class Model_nefnet(nn.Module):
                 g = self._f32(g, device)
                 keep.append(g)
                 setattr(b, field, g.data_ptr())
+        if world > 1:
+            if not self._ddp_ready:
+                self._ddp_setup(device)
+            b.ev_late_params_done = self._ddp_event.cuda_event
         N.check(lib.nef_backward(plan.handle, C.byref(b), N.stream_ptr()), "nef_backward")
         self._saved = None
-        return [self._grad_views[n] for n in self._live_names()]
+        if world > 1:
+            # bucket 1 (z1_conv .. decoder, 2/3 of the bytes) is final long before the encoder's backward ends: reduce it on
+            # a side stream behind the event nef_backward recorded; bucket 0 (stem, encoder, mlp, w_conv) follows on the
+            # main stream.  ReduceOp.AVG: the mean over ranks, as DataParallel's gradient of the batch-mean loss.
+            split = self._ddp_split
+            self._ddp_stream.wait_event(self._ddp_event)
+            with torch.cuda.stream(self._ddp_stream):
+                w1 = dist.all_reduce(self._flat_grad[split:], op=dist.ReduceOp.AVG, async_op=True)
+            w0 = dist.all_reduce(self._flat_grad[:split], op=dist.ReduceOp.AVG, async_op=True)
+            w1.wait()
+            w0.wait()
+        for n, p in params.items():
+            if n not in _UNUSED and p.requires_grad:
+                p.grad = self._grad_views[n]
+        self._grads_valid = True
 
     def export_activation(self, name):
         """Test hook (nef_plan_export): a named internal activation of the last forward as a (B, C, L) tensor."""
@@ -342,6 +408,15 @@ class Model_nefnet(nn.Module):
         out = torch.empty(shape, dtype=torch.float32, device=self._flat.device)
         N.check(lib.nef_plan_export(plan.handle, name.encode(), N.ptr(out), N.stream_ptr()), "nef_plan_export")
         return out
+
+    def poison_activation(self, name):
+        """Test hook (nef_plan_poison): NaN-fill the fp32 storage of a named activation of the last forward."""
+        lib = N.load()
+        plan = next(iter(self._plans.values()))
+        c, l = C.c_int(), C.c_int()
+        N.check(lib.nef_plan_tensor_info(plan.handle, name.encode(), C.byref(c), C.byref(l)), "nef_plan_tensor_info")
+        scratch = torch.empty((plan.B, c.value, l.value), dtype=torch.float32, device=self._flat.device)
+        N.check(lib.nef_plan_poison(plan.handle, name.encode(), N.ptr(scratch), N.stream_ptr()), "nef_plan_poison")
 
     def _live_names(self):
         return [n for n, _ in self.named_parameters() if n not in _UNUSED]

@@ -15,9 +15,13 @@ class FlatSGD(torch.optim.Optimizer):
     optim_scheduler.py:13-18) and ``optim.zero_grad()`` / ``optim.step()`` (solver.py:232-235) drive it unchanged; the
     learning rate is read from ``param_groups[0]['lr']`` at every step.
 
-    The step reads ``model.flat_grads`` -- the buffer ``backward`` writes -- not the ``p.grad`` tensors (autograd keeps
-    copies of the flat views there).  Anything that edits gradients between ``backward`` and ``step`` (clipping, noise; the
-    reference does neither) must edit ``model.flat_grads``, which is one tensor: ``flat_grads.mul_(coef)``."""
+    The step reads ``model.flat_grads``, the buffer ``backward`` writes; every ``p.grad`` is a VIEW of it, so editing
+    gradients between ``backward`` and ``step`` (clipping, noise; the reference does neither) through ``p.grad`` or through
+    ``flat_grads`` is the same thing.  As with ``torch.optim.SGD``: a ``step()`` without fresh gradients (none computed since
+    ``zero_grad()``) changes nothing; parameters with ``requires_grad=False`` are not updated; ``step(closure)`` evaluates
+    the closure first.  In a data-parallel run the module's ``backward`` has already averaged the gradients over the ranks
+    (``Model_nefnet.ddp_allreduce``); ``world_size`` is only for callers that all-reduce SUMS themselves
+    (``allreduce_gradients(model)`` + ``step(world_size=n)`` folds the 1 / n into the update kernel)."""
 
     def __init__(self, model, lr=0.1, momentum=0.9):
         self.model = model
@@ -35,30 +39,61 @@ class FlatSGD(torch.optim.Optimizer):
     def zero_grad(self, set_to_none=True):
         for p in self.model.parameters():
             p.grad = None
+        self.model._grads_valid = False   # the flat buffer is re-zeroed by the next backward
 
-    @torch.no_grad()
-    def step(self, world_size=1, closure=None):
+    def step(self, closure=None, *, world_size=1):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
         m = self.model
         flat, grad = m.flat_params, m.flat_grads
         if flat is None:
             raise RuntimeError("FlatSGD.step() before the first forward/backward")
-        if self._mom is None or self._mom.data_ptr() == 0 or self._mom.numel() != flat.numel():
-            self._mom = torch.zeros_like(flat)
-        lib = N.load()
-        N.check(lib.nef_sgd_step(N.ptr(flat), N.ptr(grad), N.ptr(self._mom), flat.numel(), self.lr, self.momentum,
-                                 1.0 / float(world_size), N.stream_ptr()), "nef_sgd_step")
+        if not getattr(m, "_grads_valid", True):
+            return loss                   # no gradient since zero_grad(): torch.optim.SGD skips parameters without one
+        with torch.no_grad():
+            if self._mom is None or self._mom.data_ptr() == 0 or self._mom.numel() != flat.numel():
+                self._mom = torch.zeros_like(flat)
+            for n, p in m.named_parameters():   # frozen parameters: zero gradient and momentum slots leave them untouched
+                if not p.requires_grad:
+                    o = m._offsets[n]
+                    grad[o:o + p.numel()].zero_()
+                    self._mom[o:o + p.numel()].zero_()
+            lib = N.load()
+            N.check(lib.nef_sgd_step(N.ptr(flat), N.ptr(grad), N.ptr(self._mom), flat.numel(), self.lr, self.momentum,
+                                     1.0 / float(world_size), N.stream_ptr()), "nef_sgd_step")
+        return loss
 
     # checkpoints (utils/checkpointer.py:28-31 saves optimizer.state_dict()): the momentum lives in one flat buffer
     def state_dict(self):
-        return {"param_groups": [{k: v for k, v in self.param_groups[0].items() if k != "params"}],
+        return {"param_groups": [{k: v for k, v in self.param_groups[0].items() if k != "params"}], "state": {},
                 "flat_momentum": None if self._mom is None else self._mom.detach().cpu()}
 
     def load_state_dict(self, sd):
+        """Accepts its own format and ``torch.optim.SGD``'s (a checkpoint the reference's solver wrote with the stock optimiser,
+        utils/checkpointer.py:28-31: ``state[i]['momentum_buffer']`` per parameter index)."""
         for k, v in sd["param_groups"][0].items():
-            self.param_groups[0][k] = v
+            if k != "params":
+                self.param_groups[0][k] = v
+        m = self.model
+        dev = m.flat_params.device if m.flat_params is not None else "cuda"
         mom = sd.get("flat_momentum")
-        self._mom = None if mom is None else mom.to(self.model.flat_params.device if self.model.flat_params is not None
-                                                    else "cuda")
+        if mom is not None:
+            self._mom = mom.to(dev)
+            return
+        self._mom = None
+        state = sd.get("state") or {}
+        if state:
+            if m.flat_params is None:
+                raise RuntimeError("FlatSGD.load_state_dict: move the model to its device and run one forward before loading a "
+                                   "torch.optim.SGD state (the flat layout does not exist yet)")
+            self._mom = torch.zeros_like(m.flat_params)
+            for i, (n, p) in enumerate(m.named_parameters()):
+                buf = state.get(i, state.get(str(i), {})).get("momentum_buffer")
+                if buf is not None:
+                    o = m._offsets[n]
+                    self._mom[o:o + p.numel()].copy_(buf.reshape(-1))
 
 
 def get_optimizer(cfg, model):
@@ -82,12 +117,9 @@ def get_lr_scheduler(cfg, optim=None):
 
 
 def allreduce_gradients(model, group=None, average=False):
-    """One all-reduce (sum) of the flat gradient buffer; the unused parameters have zero slots.
-
-    ``FlatSGD`` reads the flat buffer and folds 1 / world_size into its kernel (``opt.step(world_size)``), so it needs
-    nothing else.  A stock torch optimiser (the reference's own ``get_optimizer``, optim_scheduler.py:5-10) reads
-    ``p.grad``, which autograd fills with COPIES of the flat views: pass ``average=True`` to scale the buffer by
-    1 / world_size and write the reduced values back into every ``p.grad`` (``Model_nefnet.sync_param_grads``)."""
+    """One all-reduce (sum) of the flat gradient buffer; the unused parameters have zero slots.  Manual route for
+    callers that switched the module's built-in exchange off (``model.ddp_allreduce = False``): ``FlatSGD`` folds
+    1 / world_size into its kernel (``opt.step(world_size=n)``); for a stock torch optimiser pass ``average=True``."""
     import torch.distributed as dist
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(model.flat_grads, op=dist.ReduceOp.SUM, group=group)

@@ -221,6 +221,11 @@ typedef struct NefBackwardArgs {
   const float* dout;          /* (B, 1, L) x3, NULL = zero */
   const float* dout_p;
   const float* dout_l;
+  /* Optional cudaEvent_t, recorded on the stream as soon as the gradients of every parameter from "z1_conv.0.conv1.weight"
+   * to the end of the state_dict order (z1_conv, z2_conv1, z2_conv2, decoder: 2/3 of the bytes) are final -- before the
+   * w_conv and encoder blocks run their backward.  A data-parallel caller all-reduces that bucket on a side stream behind
+   * this event, overlapped with the rest of the backward pass.                                         */
+  void* ev_late_params_done;
 } NefBackwardArgs;
 /* autograd of the above (solver.py:233) for the last nef_forward(save_for_backward = 1) on this plan */
 int nef_backward(NefPlan* plan, const NefBackwardArgs* a, nef_stream_t s);
@@ -229,10 +234,14 @@ int nef_backward(NefPlan* plan, const NefBackwardArgs* a, nef_stream_t s);
  * L = 0).  Names: "stem"; "<block>.h" / "<block>.y" for the residual blocks W_encoder.layer1.{0,1,2}, w_conv.0, z1_conv.0,
  * z2_conv1.0 (centre window only), z2_conv2.0, z2_conv2.2; "roi_align"; "z2_conv2.1"; per decoder call k = 0..2:
  * "dec<k>.u0", "dec<k>.decoder.{1,3}.{0,3}" (convolution outputs before BatchNorm), "dec<k>.a1|u1|a3",
- * "dec<k>.bn<i>.scale|shift".  The parity tests compare them layer by layer with the oracle and evaluate the oracle's
+ * "dec<k>.bn<i>.scale|shift"; "<block>.h.mask" / "<block>.y.mask" (encoder blocks, w_conv.0, z1_conv.0.h): the one-bit
+ * (value != 0) planes the masked data gradients read, as 0 / 1 floats.  The parity tests compare them layer by layer with the oracle and evaluate the oracle's
  * backward pass on the device's own ReLU / dropout patterns. */
 int nef_plan_tensor_info(const NefPlan* plan, const char* name, int* C, int* L);
 int nef_plan_export(NefPlan* plan, const char* name, float* dst, nef_stream_t s);
+/* Test hook: fills the fp32 storage of a named activation with NaN (a test then proves that nothing reads a tensor the
+ * dataflow dropped).  scratch: B * C * L floats of device memory (shape from nef_plan_tensor_info). */
+int nef_plan_poison(NefPlan* plan, const char* name, float* scratch, nef_stream_t s);
 
 /* Model_nefnet.gen_ecg, model_nefnet.py:196-218: decode V views from supplied latents (eval-mode BN) */
 int nef_gen_ecg(NefPlan* plan, const float* const* params, const float* z1, const float* z2,

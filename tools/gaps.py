@@ -17,7 +17,7 @@ inp = {k: v.repeat(*([16] + [1] * (v.dim() - 1)))[:B].contiguous().to(dev) for k
 def step():
     outs = model(inp["x"], inp["input_thetas"], inp["query_theta"], inp["rois"], phase="train")
     loss = network.losswrapper(outs[0], outs[1], outs[2], inp["target"], bench.Cfg)[0]
-    loss.backward(); opt.step(1); opt.zero_grad()
+    loss.backward(); opt.step(); opt.zero_grad()
 for _ in range(3): step()
 torch.cuda.synchronize()
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:

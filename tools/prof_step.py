@@ -29,7 +29,7 @@ if a.mode == "step":
         outs = model(inp["x"], inp["input_thetas"], inp["query_theta"], inp["rois"], phase="train")
         loss = network.losswrapper(outs[0], outs[1], outs[2], inp["target"], bench.Cfg)[0]
         loss.backward()
-        opt.step(1); opt.zero_grad()
+        opt.step(); opt.zero_grad()
     torch.cuda.synchronize()
     print("loss", float(loss))
 else:

@@ -27,7 +27,7 @@ inp = rep(O.make_inputs(8, G, L, seed=0), B)
 def step():
     outs = model(inp["x"], inp["input_thetas"], inp["query_theta"], inp["rois"], phase="train")
     loss = network.losswrapper(outs[0], outs[1], outs[2], inp["target"], bench.Cfg)[0]
-    loss.backward(); opt.step(1); opt.zero_grad()
+    loss.backward(); opt.step(); opt.zero_grad()
     return loss
 dt, loss = timed(step)
 print("config 4: train step B=%d L=%d  %.1f ms  %.1f segments/s  loss %.5f finite=%s" % (B, L, dt * 1e3, B / dt, float(loss), bool(torch.isfinite(loss))))
