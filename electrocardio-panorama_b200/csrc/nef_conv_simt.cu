@@ -189,27 +189,6 @@ __global__ void __launch_bounds__(256) wgrad_simt_kernel(const NefWgradDesc d, l
   }
 }
 
-// ---- weight packing and layout conversion ----------------------------------------------------
-__global__ void pack_weights_kernel(const float* __restrict__ src, float* __restrict__ dst, int groups, int N, int K,
-                                    int taps, long sg, long sn, long sk, long st, int flags) {
-  const long total = (long)groups * taps * K * N;
-  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    long r = i;
-    const int j = r & 3; r >>= 2;
-    const int n = r % N; r /= N;
-    const int c = r & 7; r >>= 3;
-    const int nkb = K >> 5;
-    const int kb = r % nkb; r /= nkb;
-    const int t = r % taps; r /= taps;
-    const int g = (int)r;
-    const int k = kb * 32 + c * 4 + j;
-    const int ts = (flags & 1) ? taps - 1 - t : t;
-    const float wv = src[g * sg + n * sn + k * sk + ts * st];
-    const float hi = tf32_rn(wv);
-    dst[i] = (flags & 2) ? tf32_rn(wv - hi) : hi;
-  }
-}
-
 // Several packing jobs in one launch (the plan packs ~28 weight tensors per pass): the job table travels as a kernel
 // parameter, a block finds its job from the cumulative block counts and packs NEF_PACK_CHUNK elements of it.
 __global__ void __launch_bounds__(256) pack_weights_batch_kernel(const __grid_constant__ NefPackTable tab) {
@@ -398,12 +377,42 @@ extern "C" int nef_gconv_wgrad_simt(const NefWgradDesc* d, nef_stream_t s) { ret
 
 extern "C" int nef_pack_weights(const float* src, float* dst, int groups, int N, int K, int taps, int64_t sg,
                                 int64_t sn, int64_t sk, int64_t st, int flags, nef_stream_t s) {
-  NEF_REQUIRE(K % 32 == 0 && N % 4 == 0, "nef_pack_weights: K %% 32 and N %% 4 required (K=%d N=%d)", K, N);
-  const long total = (long)groups * taps * K * N;
+  // one job of the batched packer (the kernel the plan uses), so that every flag -- including bit 2, the fp16 operand
+  // packing of NefConvTerm.x_f16 -- is available through the C ABI
+  NefPackTable t;
+  t.n = 1;
+  NefPackJob& q = t.job[0];
+  q.src = src; q.dst = dst; q.groups = groups; q.N = N; q.K = K; q.taps = taps;
+  q.sg = sg; q.sn = sn; q.sk = sk; q.st = st; q.flags = flags; q.first_block = 0; q.nscale = nullptr;
+  return nef_pack_weights_batch(&t, (cudaStream_t)s);
+}
+
+// (B, C, L) fp32 -> fp16 copy `half8 [C/8][B * Lp]` (the layout of NefConvDesc.y16), values multiplied by scale, saturating
+__global__ void ncl_to_h8_kernel(const float* __restrict__ src, uint4* __restrict__ dst, int B, int C, int L, float scale) {
+  const int Lp = L + 2 * NEF_HALO;
+  const long total = (long)B * (C / 8) * L;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int l = i % L;
+    long r = i / L;
+    const int b = r % B;
+    const int c8 = r / B;
+    const float* p = src + ((long)b * C + c8 * 8) * L + l;
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float lo = p[(long)(2 * j) * L] * scale, hi = p[(long)(2 * j + 1) * L] * scale;
+      asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(o[j]) : "f"(hi), "f"(lo));
+    }
+    dst[(long)c8 * B * Lp + (long)b * Lp + NEF_HALO + l] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+extern "C" int nef_ncl_to_h8(const float* src, void* dst, int B, int C, int L, float scale, nef_stream_t s) {
+  NEF_REQUIRE(C % 8 == 0, "nef_ncl_to_h8: C %% 8 required");
+  const long total = (long)B * (C / 8) * L;
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
-  pack_weights_kernel<<<blocks, 256, 0, (cudaStream_t)s>>>(src, dst, groups, N, K, taps, sg, sn, sk, st, flags);
-  NEF_CHECK_LAUNCH("pack_weights_kernel");
+  ncl_to_h8_kernel<<<blocks, 256, 0, (cudaStream_t)s>>>(src, reinterpret_cast<uint4*>(dst), B, C, L, scale);
+  NEF_CHECK_LAUNCH("ncl_to_h8_kernel");
   return 0;
 }
 

@@ -24,6 +24,7 @@
 // the collector; SWIZZLE_NONE costs nothing over SWIZZLE_128B for these tiles; a bulk copy is issued from the uniform
 // datapath, one at a time per warp.
 #include <cstdlib>
+#include <cuda_fp16.h>
 #include "nef_conv.cuh"
 
 extern "C" int nef_gconv_fwd_simt(const NefConvDesc* d, nef_stream_t s);
@@ -231,6 +232,7 @@ constexpr int EPI_BIAS = 1, EPI_RES = 2, EPI_RELU = 4, EPI_DROP = 8, EPI_MASK1 =
 constexpr int EPI_MASK2 = 128, EPI_BSCALE = 256, EPI_STATS = 512;  // mask mode 2, angular scale, BatchNorm partial statistics
 constexpr int EPI_OBITS = 1024, EPI_MBITS = 2048;                  // write / read one-bit activation masks
 constexpr int EPI_Y16 = 4096;                                      // also store an fp16 copy of the output (next conv's operand)
+constexpr int EPI_RES16 = 16384;   // the residual operand is read from an fp16 copy (times res16_scale[0]) instead of the fp32 tensor
 constexpr int EPI_GSCALE = 8192;   // backward pass with loss-scaled fp16 copies: acc *= acc_scale[0]; y16 = fp16(v * y16_scale[0])
 
 // Sum over the 32 lanes of 32 per-lane values at once: after the 5 exchange levels lane j holds the warp total of a[j].
@@ -289,6 +291,8 @@ __device__ __forceinline__ void epilogue_tile(const NefConvDesc& d, int g, long 
   const float acc_sc = (f_gs && d.acc_scale) ? __ldg(d.acc_scale) : 1.f;
   const float y16_sc = (f_gs && d.y16_scale) ? __ldg(d.y16_scale) : 1.f;
   const bool store_y = d.y != nullptr;   // NULL: only the fp16 copy (and the bit plane) of the result is kept
+  const bool f_res16 = GEN ? d.res16 != nullptr : (EPI & EPI_RES16) != 0;
+  const float res_sc = (f_res16 && d.res16_scale) ? __ldg(d.res16_scale) : 1.f;
   // mask operand: 0 none, 1 / 2 float tensor (> 0 / != 0), 3 one-bit masks
   const int mask_mode = f_mbits ? 3 : (GEN ? d.mask_mode : ((EPI & EPI_MASK1) ? 1 : ((EPI & EPI_MASK2) ? 2 : 0)));
   const float mask_scale = d.mask_scale;
@@ -312,6 +316,7 @@ __device__ __forceinline__ void epilogue_tile(const NefConvDesc& d, int g, long 
     const uint32_t* mbp = d.mask_bits + (long)((d.mask_c4_off + g * d.mask_c4_gstride) >> 3) * d.mask_cstride + orow;
     uint32_t* obp = d.out_bits + (long)((d.y_c4_off + g * d.y_c4_gstride) >> 3) * d.y_cstride + orow;
     uint4* y16p = reinterpret_cast<uint4*>(d.y16) + (long)((d.y_c4_off + g * d.y_c4_gstride) >> 1) * d.y_cstride + orow;
+    const uint4* r16p = reinterpret_cast<const uint4*>(d.res16) + (long)((d.res_c4_off + g * d.res_c4_gstride) >> 1) * d.res_cstride + orow;
     for (int cg = chalf; cg < N / 32; cg += 2) {
       uint32_t v[32];
       tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * N + cg * 32), v);
@@ -328,6 +333,18 @@ __device__ __forceinline__ void epilogue_tile(const NefConvDesc& d, int g, long 
           mm[i] = (mask_mode == 1 || mask_mode == 2) ? __ldg(mpc) : f4zero();
           rpc += d.res_cstride;
           mpc += d.mask_cstride;
+        }
+        if (f_res16) {   // 8 channels per 16-byte row: chunk pair (2 m, 2 m + 1) of this column group
+          const uint4* rq = r16p + (long)(cg * 4) * d.res_cstride;
+#pragma unroll
+          for (int m = 0; m < 4; ++m) {
+            const uint4 h = __ldg(rq);
+            rq += d.res_cstride;
+            const float2 a0 = __half22float2(*reinterpret_cast<const __half2*>(&h.x)), a1 = __half22float2(*reinterpret_cast<const __half2*>(&h.y));
+            const float2 b0 = __half22float2(*reinterpret_cast<const __half2*>(&h.z)), b1 = __half22float2(*reinterpret_cast<const __half2*>(&h.w));
+            rr[2 * m] = make_float4(a0.x * res_sc, a0.y * res_sc, a1.x * res_sc, a1.y * res_sc);
+            rr[2 * m + 1] = make_float4(b0.x * res_sc, b0.y * res_sc, b1.x * res_sc, b1.y * res_sc);
+          }
         }
       }
       tmem_ld_wait();
@@ -1052,7 +1069,7 @@ static int g_tc_mt = 0;  // 0 = automatic; 4 forces four row tiles per CTA, one 
 
 // the specialised epilogues instantiated for the 4-row-tile kernel (everything else takes the generic one)
 #define NEF_TC_EPI_LIST(X) X(0) X(2) X(5) X(32) X(33) X(36) X(37) X(38) X(44) X(48) X(50) X(64) X(294) X(418) X(513) \
-  X(1062) X(1068) X(1318) X(2080) X(2082) X(2338) X(4132) X(4134) X(4390) X(5158) X(5164) X(5414) X(8194) X(14368) X(14370) X(14626)
+  X(1062) X(1068) X(1318) X(2080) X(2082) X(2338) X(4132) X(4134) X(4390) X(5158) X(5164) X(5414) X(8194) X(14368) X(14370) X(14626) X(21540) X(21796) X(24576) X(30752) X(31008)
 
 template <int MT, int EPI>
 static int tc_optin() {
@@ -1114,6 +1131,7 @@ static int epi_code(const NefConvDesc* d) {
   if (d->acc_scale || d->y16_scale) e |= tc::EPI_GSCALE;
   if (d->bias) e |= tc::EPI_BIAS;
   if (d->res) e |= tc::EPI_RES;
+  if (d->res16) e |= tc::EPI_RES16;
   if (d->relu) e |= tc::EPI_RELU;
   if (d->drop_p > 0.f) e |= tc::EPI_DROP;
   if (d->mask_mode == 1 && !mbits) e |= tc::EPI_MASK1;

@@ -330,7 +330,8 @@ __global__ void window_extract_kernel(T4 w, T4 xw, int G, Window win) {
 
 // One thread per (pair of 4-channel chunks, segment, position) of the z2 half, so that the optional loss-scaled fp16 copy
 // (8 channels per 16-byte row) is written by the same thread.
-__global__ void window_scatter_kernel(T4 gxw, T4 gw, int G, Window win, uint4* __restrict__ gw16, const float* __restrict__ s16) {
+__global__ void window_scatter_kernel(T4 gxw, T4 gw, int G, Window win, uint4* __restrict__ gw16, const float* __restrict__ s16,
+                                      int store32) {
   const long total = (long)G * 8 * gw.B * gw.L;
   const float sc = (gw16 && s16) ? __ldg(s16) : 1.f;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
@@ -345,8 +346,10 @@ __global__ void window_scatter_kernel(T4 gxw, T4 gw, int G, Window win, uint4* _
       v0 = *gxw.at(g * 16 + cc, b, lw);
       v1 = *gxw.at(g * 16 + cc + 1, b, lw);
     }
-    *gw.at(g * 32 + 16 + cc, b, l) = v0;
-    *gw.at(g * 32 + 16 + cc + 1, b, l) = v1;
+    if (store32) {
+      *gw.at(g * 32 + 16 + cc, b, l) = v0;
+      *gw.at(g * 32 + 16 + cc + 1, b, l) = v1;
+    }
     if (gw16)
       gw16[(long)((g * 32 + 16 + cc) >> 1) * gw.cs + gw.row(b, l)] =
           make_uint4(f16x2_sat(v0.x * sc, v0.y * sc), f16x2_sat(v0.z * sc, v0.w * sc), f16x2_sat(v1.x * sc, v1.y * sc),
@@ -360,9 +363,9 @@ int window_extract(T4 w, T4 xw, int G, Window win, cudaStream_t s) {
   NEF_CHECK_LAUNCH("window_extract_kernel");
   return 0;
 }
-int window_scatter(T4 gxw, T4 gw, int G, Window win, void* gw16, const float* s16, cudaStream_t s) {
+int window_scatter(T4 gxw, T4 gw, int G, Window win, void* gw16, const float* s16, int store32, cudaStream_t s) {
   const long total = (long)G * 8 * gw.B * gw.L;
-  window_scatter_kernel<<<grid_for(total, 256), 256, 0, s>>>(gxw, gw, G, win, reinterpret_cast<uint4*>(gw16), s16);
+  window_scatter_kernel<<<grid_for(total, 256), 256, 0, s>>>(gxw, gw, G, win, reinterpret_cast<uint4*>(gw16), s16, store32);
   NEF_CHECK_LAUNCH("window_scatter_kernel");
   return 0;
 }

@@ -36,7 +36,8 @@ struct Window { int w0, Lw, y0; float wy1; };
 Window centre_window(int L4);
 int window_extract(T4 w, T4 xw, int G, Window win, cudaStream_t s);                  // w z2-half -> (64G, Lw)
 // -> z2 half of g_w, zeros elsewhere; gw16 (optional): fp16 copy of the same rows scaled by s16[0] (device scalar)
-int window_scatter(T4 gxw, T4 gw, int G, Window win, void* gw16, const float* s16, cudaStream_t s);
+//   store32 = 0: only the fp16 copy is written
+int window_scatter(T4 gxw, T4 gw, int G, Window win, void* gw16, const float* s16, int store32, cudaStream_t s);
 // scale[0] = S, scale[1] = 1 / S, S = 2^k with S * max|d0, d1, d2| in [32, 64) (1 if all zero); scale[2] is scratch
 int grad_loss_scale(const float* d0, const float* d1, const float* d2, long n, float* scale, cudaStream_t s);
 int roi_align_fwd(T4 z2c, const int64_t* rois, T4 ra, Window win, int L4, cudaStream_t s);

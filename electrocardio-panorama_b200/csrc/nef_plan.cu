@@ -446,6 +446,11 @@ struct CD {
     d.res = reinterpret_cast<const float*>(r.p); d.res_cstride = r.cs; d.res_c4_off = off; d.res_c4_gstride = gs;
     return *this;
   }
+  // residual operand from the fp16 copy of a tensor with geometry (cs, off, gs in 4-channel chunk units), times scale[0]
+  CD& res16(const void* r16, long cs, int off, int gs, const float* scale = nullptr) {
+    d.res16 = r16; d.res_cstride = cs; d.res_c4_off = off; d.res_c4_gstride = gs; d.res16_scale = scale;
+    return *this;
+  }
   CD& relu() { d.relu = 1; return *this; }
   CD& drop(float p, uint64_t seed) { d.drop_p = p; d.drop_seed = seed; return *this; }
   CD& bscale(const float* s) { d.bscale = s; return *this; }
@@ -586,6 +591,7 @@ struct BlockIO {
   void* h16 = nullptr;         // fp16 copies of h / y written by the epilogues (operands of the next convolution and / or of
   void* y16 = nullptr;         //   the fp16 weight gradients); optional, also without x16
   bool h_f16_only = false;     // do not store the fp32 h at all (needs x16 and h16: nothing reads it then)
+  bool y_f16_only = false;     // the same for y (needs y16; its readers take the fp16 copy and the bit plane)
 };
 
 static int block_fwd(const BlockIO& io, float drop_p, uint64_t seed, const float* bscale, cudaStream_t s) {
@@ -605,9 +611,11 @@ static int block_fwd(const BlockIO& io, float drop_p, uint64_t seed, const float
   if (io.y16) b.y16(io.y16);
   if (io.cr && io.x16) b.term16(io.x16, io.x.cs, io.x_off / 2, io.x_gs / 2, io.cr->cin_g, 1, io.cr->pk_h).bias(io.res_bias);
   else if (io.cr) b.term(io.x, io.x_off, io.x_gs, io.cr->cin_g, 1, io.cr->pk_f).bias(io.res_bias);
+  else if (io.x16) b.res16(io.x16, io.x.cs, io.x_off, io.x_gs);   // identity residual from the fp16 copy (same significand)
   else b.res(io.x, io.x_off, io.x_gs);
   if (bscale) b.bscale(bscale);
   if (io.ybits) b.obits(io.ybits);
+  if (io.y_f16_only && io.y16) b.d.y = nullptr;
   RUN(b.run(s));
   return 0;
 }
@@ -760,6 +768,7 @@ extern "C" int nef_forward(NefPlan* p, const NefForwardArgs* a, nef_stream_t sv)
       io.h16 = p->eh_h[i];
       io.y16 = p->ey_h[i];
       io.h_f16_only = p->h_f16_only;
+      io.y_f16_only = p->h_f16_only && i < 2;   // ey[2] (bscale_grad) keeps its fp32 storage
     }
     RUN(block_fwd(io, dp, seed + i, i == 2 ? p->s_in : nullptr, s));
   }
@@ -884,7 +893,7 @@ static int block_bwd(const BlockBwd& b, float drop_p, CD& fin, cudaStream_t s) {
     fin.term16(b.gh16, b.gh.cs, 0, 16, 128, io.c1->taps, io.c1->pk_dh);
     fin.d.acc_scale = inv;
     if (io.cr) fin.term16(b.gy16, b.gy.cs, 0, 16, 128, 1, io.cr->pk_dh);
-    else fin.res(b.gy, 0, 32);
+    else fin.res16(b.gy16, b.gy.cs, 0, 32, inv);
     RUN(fin.run(s));
     return 0;
   }
@@ -1006,6 +1015,7 @@ extern "C" int nef_backward(NefPlan* p, const NefBackwardArgs* a, nef_stream_t s
     if (f16) {
       bb.io.x16 = p->w_h; bb.io.h16 = p->h1_h; bb.gy16 = p->GA_h[0]; bb.gh16 = p->GA_h[1]; bb.lscale = ls;
       fin.y16s(p->GA_h[2], ls);
+      fin.d.y = nullptr;   // g_w is read as fp16 only (w_conv's data / weight gradients, its residual operand)
     }
     RUN(block_bwd(bb, dp, fin, s));
   }
@@ -1053,7 +1063,7 @@ extern "C" int nef_backward(NefPlan* p, const NefBackwardArgs* a, nef_stream_t s
     fin.out(p->gxw, 0, 16).mask(p->xw, 0, 16, 1, 1.f).round();
     RUN(block_bwd(bb, dp, fin, s));
   }
-  RUN(window_scatter(p->gxw, p->GA[2], G, p->win, f16 ? p->GA_h[2] : nullptr, ls, s));
+  RUN(window_scatter(p->gxw, p->GA[2], G, p->win, f16 ? p->GA_h[2] : nullptr, ls, f16 ? 0 : 1, s));
   if (a->ev_late_params_done) {   // every parameter gradient from z1_conv.0 on is final: the caller may start reducing them
     cudaError_t e = cudaEventRecord((cudaEvent_t)a->ev_late_params_done, s);
     NEF_REQUIRE(e == cudaSuccess, "nef_backward: cudaEventRecord failed: %s", cudaGetErrorString(e));
@@ -1088,7 +1098,10 @@ extern "C" int nef_backward(NefPlan* p, const NefBackwardArgs* a, nef_stream_t s
       if (f16) {
         bb.io.x16 = i == 0 ? p->s0_h : p->ey_h[i - 1]; bb.io.h16 = p->eh_h[i];
         bb.gy16 = p->GA_h[gy_i]; bb.gh16 = p->GA_h[0]; bb.lscale = ls;
-        if (i > 0) fin.y16s(p->GA_h[gx_i], ls);
+        if (i > 0) {
+          fin.y16s(p->GA_h[gx_i], ls);
+          fin.d.y = nullptr;   // the next block reads this gradient as fp16 only
+        }
       }
       RUN(block_bwd(bb, dp, fin, s));
       gy_i = gx_i;
@@ -1128,7 +1141,10 @@ static bool find_tensor(const NefPlan* p, const char* name, NamedTensor* out) {
   // hidden activations that the last forward kept as fp16 copies only
   auto h_only = [&](const void* h16) { if (p->h_f16_only && out->t && n.size() > 2 && n.substr(n.size() - 2) == ".h") out->h16 = h16; return true; };
   for (int i = 0; i < 3; ++i)
-    if (blk(("W_encoder.layer1." + std::to_string(i)).c_str(), p->eh[i], p->ey[i])) return h_only(p->eh_h[i]);
+    if (blk(("W_encoder.layer1." + std::to_string(i)).c_str(), p->eh[i], p->ey[i])) {
+      if (p->h_f16_only && i < 2 && out->t == &p->ey[i]) { out->h16 = p->ey_h[i]; return true; }
+      return h_only(p->eh_h[i]);
+    }
   if (blk("w_conv.0", p->hw, p->w)) return h_only(p->hw_h);
   if (blk("z1_conv.0", p->h1, p->z1)) return h_only(p->h1_h);
   if ( blk("z2_conv1.0", p->hz, p->z2c) ||

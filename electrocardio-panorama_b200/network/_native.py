@@ -35,7 +35,7 @@ class NefConvDesc(C.Structure):
                 ("mask_cstride", C.c_int64), ("mask_c4_off", C.c_int32), ("mask_c4_gstride", C.c_int32),
                 ("mask_scale", C.c_float), ("reserved2", C.c_int32), ("stat_sum", C.c_void_p),
                 ("stat_sq", C.c_void_p), ("out_bits", C.c_void_p), ("mask_bits", C.c_void_p), ("y16", C.c_void_p),
-                ("acc_scale", C.c_void_p), ("y16_scale", C.c_void_p)]
+                ("acc_scale", C.c_void_p), ("y16_scale", C.c_void_p), ("res16", C.c_void_p), ("res16_scale", C.c_void_p)]
 
 
 class NefWgradDesc(C.Structure):
@@ -79,6 +79,8 @@ SIGNATURES = {
     "nef_cbl4_floats": (C.c_int64, [C.c_int, C.c_int, C.c_int]),
     "nef_ncl_to_cbl4": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "nef_cbl4_to_ncl": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "nef_ncl_to_h8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p]),
+    "nef_h8_to_ncl": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "nef_pack_weights": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64,
                                    C.c_int64, C.c_int64, C.c_int, C.c_void_p]),
     "nef_gconv_fwd": (C.c_int, [C.POINTER(NefConvDesc), C.c_void_p]),

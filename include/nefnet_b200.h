@@ -76,6 +76,11 @@ int64_t nef_cbl4_rows(int B, int L);
 int64_t nef_cbl4_floats(int C, int B, int L);
 int nef_ncl_to_cbl4(const float* src, float* dst, int B, int C, int L, int round_tf32, nef_stream_t s);
 int nef_cbl4_to_ncl(const float* src, float* dst, int B, int C, int L, nef_stream_t s);
+/* fp16 operand copies: `half8 T16[C/8][B * (L + 2*NEF_HALO)]`, 8 channels per 16-byte row, same row indexing and zero halo
+ * as CBL4 (C %% 8 == 0; NEF_GUARD_ROWS_ABI readable 16-byte rows on both sides).  nef_ncl_to_h8 multiplies by `scale` and
+ * saturates to the largest finite fp16. */
+int nef_ncl_to_h8(const float* src, void* dst, int B, int C, int L, float scale, nef_stream_t s);
+int nef_h8_to_ncl(const void* src, float* dst, int B, int C, int L, nef_stream_t s);
 
 /* ---- grouped 1-D convolution as implicit GEMM ---------------------------------------------- */
 /* replaces every nn.Conv1d / nn.ConvTranspose1d call of resnet_1d.py:21-24,39-53 and
@@ -147,12 +152,19 @@ typedef struct NefConvDesc {
    * stores fp16(value * y16_scale[0]) (= S).  y may be NULL when y16 is set: only the fp16 copy is kept.        */
   const float* acc_scale;
   const float* y16_scale;
+  /* Residual operand from an fp16 copy (same layout as y16, geometry = the res_* fields, chunk offsets even) instead of
+   * the fp32 tensor `res`: v += res16 * res16_scale[0] (device scalar, NULL = 1).  TF32-rounded activations and the
+   * loss-scaled gradient copies hold the same 11-bit significands as their fp32 originals, at half the bytes.  */
+  const void* res16;
+  const float* res16_scale;
 } NefConvDesc;
 
 /* Packs reference-layout weights into the layout NefConvTerm.w expects, rounding to TF32 (RN):
  *   dst[g][t][kb][c][n][j] = src[g*sg + n*sn + (kb*32 + c*4 + j)*sk + ((flags & 1) ? taps-1-t : t)*st]
  *   flags bit 0: flip the taps (data gradient); bit 1: store the TF32 residual w - tf32(w) instead
- *   of tf32(w) (the low part of a split-precision contraction, used for the decoder's first conv)   */
+ *   of tf32(w) (the low part of a split-precision contraction, used for the decoder's first conv);
+ *   bit 2: fp16 operand packing for NefConvTerm.x_f16 -- dst[g][t][K/64][8][n][8 halves], a 16-byte slot = 8 consecutive
+ *   input channels of one output channel, RN-even from the fp32 weight, saturating (K %% 64 == 0)      */
 int nef_pack_weights(const float* src, float* dst, int groups, int N, int K, int taps, int64_t sg, int64_t sn,
                      int64_t sk, int64_t st, int flags, nef_stream_t s);
 int nef_gconv_fwd(const NefConvDesc* d, nef_stream_t s);

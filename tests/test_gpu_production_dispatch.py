@@ -38,10 +38,10 @@ FP32_GRAD_REL_L2 = 0.15    # gradients vs the fp32 oracle (ReLU-mask flips, see 
 FP32_GRAD_COS = 0.99
 
 # epilogue codes of conv_tc_persist_kernel the 256 x 12 x 5000 training step launches (profiles/r02_step_b256_per_kernel_*):
-#   5164 / 5158 / 5414 encoder and w_conv forward (dropout, fp16 copies, bit planes, angular scale), 1068 / 37 z1_conv forward,
-#   513 decoder forward with BatchNorm statistics, 14368 / 14370 / 14626 masked data gradients that also write the loss-scaled
-#   fp16 gradient copy, 8194 the unmasked one of the first encoder block, 0 / 32 decoder data gradients
-BENCH_EPI_DROPOUT = {5164, 5158, 5414, 37, 513, 14368, 14370, 14626, 8194, 0, 32}
+#   5164 first convolutions of the big blocks (dropout, fp16 copy, bit plane), 21540 / 21796 their second convolutions
+#   (residual read from the fp16 copy; angular scale), 37 z1_conv's second convolution, 513 decoder forward with BatchNorm
+#   statistics, 14368 / 30752 / 31008 / 24576 the loss-scaled fp16 data gradients, 0 / 32 decoder data gradients
+BENCH_EPI_DROPOUT = {5164, 21540, 21796, 37, 513, 14368, 30752, 31008, 24576, 0, 32}
 
 
 BLOCKS = ("W_encoder.layer1.0", "W_encoder.layer1.1", "W_encoder.layer1.2", "w_conv.0", "z1_conv.0", "z2_conv1.0", "z2_conv2.0",
@@ -49,7 +49,8 @@ BLOCKS = ("W_encoder.layer1.0", "W_encoder.layer1.1", "W_encoder.layer1.2", "w_c
 
 
 # hidden activations of the big blocks: not stored in fp32 by the production dataflow (nothing may read that storage)
-DROPPED_FP32 = ("W_encoder.layer1.0.h", "W_encoder.layer1.1.h", "W_encoder.layer1.2.h", "w_conv.0.h", "z1_conv.0.h")
+DROPPED_FP32 = ("W_encoder.layer1.0.h", "W_encoder.layer1.1.h", "W_encoder.layer1.2.h", "w_conv.0.h", "z1_conv.0.h",
+                "W_encoder.layer1.0.y", "W_encoder.layer1.1.y")
 
 
 def _device_patterns(m, B, G, L):
