@@ -77,14 +77,23 @@ __device__ __forceinline__ float4 tf32_rn4(float4 v) {
   return make_float4(tf32_rn(v.x), tf32_rn(v.y), tf32_rn(v.z), tf32_rn(v.w));
 }
 
-__device__ __forceinline__ uint64_t mix64(uint64_t z) {  // splitmix64 finaliser
-  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-  return z ^ (z >> 31);
+// Counter-based dropout bits.  The epilogues that apply dropout are instruction-issue-bound, so the generator is built from
+// 32-bit multiplies only (a 64-bit splitmix per float4 cost ~25 instructions per element, this costs ~6): hash32 is the
+// two-multiply "lowbias32" finaliser (full avalanche); the row index goes through it once, keyed by the seed (a bijection
+// per seed, hoisted out of the chunk loop by the compiler), and every float4 takes two more hashes of row key + chunk * odd.
+__device__ __forceinline__ uint32_t hash32(uint32_t x) {
+  x ^= x >> 16; x *= 0x7feb352dU;
+  x ^= x >> 15; x *= 0x846ca68bU;
+  return x ^ (x >> 16);
 }
 // four 16-bit uniforms for the float4 at (row, chunk) of a tensor; keep lane i iff u_i >= p * 65536
+// (host mirror: tests/_dropmask.py)
 __device__ __forceinline__ uint64_t drop_bits(uint64_t seed, long row, int c4) {
-  return mix64(seed ^ (uint64_t(row) * 0x9E3779B97F4A7C15ull) ^ (uint64_t(c4) << 40) ^ (uint64_t(c4) * 0xD1B54A32D192ED03ull));
+  const uint32_t sk = hash32((uint32_t)seed ^ hash32((uint32_t)(seed >> 32) + 0x9E3779B9u));
+  const uint32_t rk = hash32((uint32_t)row ^ sk);
+  const uint32_t k = rk + (uint32_t)c4 * 0x9E3779B1u;
+  const uint32_t lo = hash32(k), hi = hash32(k ^ 0x85EBCA6Bu);
+  return ((uint64_t)hi << 32) | lo;
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

@@ -124,6 +124,20 @@ __device__ __forceinline__ void mma_tf32_ws(uint32_t tmem_d, uint64_t adesc, uin
                  "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
   }
 }
+// the same for fp16 operands: at kind::f16 rate the MMAs are bound by shared-memory operand reads (4 KB of A + 4 KB of B per
+// M128 x N128 x K16 step), so re-using the weight stage B for the second row tile of the CTA removes a quarter of them
+template <int MODE>
+__device__ __forceinline__ void mma_f16_ws(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  if constexpr (MODE == 0) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.ws.cta_group::1.kind::f16.collector::b0::fill [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(adesc),
+                 "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+  } else {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.ws.cta_group::1.kind::f16.collector::b0::lastuse [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(adesc),
+                 "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+  }
+}
 // A-operand re-use: the A tile is latched in the collector by ::fill and re-used by ::use / ::lastuse (same encoding of
 // MODE as above) -- for consecutive MMAs that share A (the taps of a weight-gradient K step share dY^T).
 template <int MODE>
@@ -233,6 +247,7 @@ constexpr int EPI_MASK2 = 128, EPI_BSCALE = 256, EPI_STATS = 512;  // mask mode 
 constexpr int EPI_OBITS = 1024, EPI_MBITS = 2048;                  // write / read one-bit activation masks
 constexpr int EPI_Y16 = 4096;                                      // also store an fp16 copy of the output (next conv's operand)
 constexpr int EPI_RES16 = 16384;   // the residual operand is read from an fp16 copy (times res16_scale[0]) instead of the fp32 tensor
+constexpr int EPI_NOY = 32768;     // no fp32 store at all (y == NULL): only the fp16 copy / the bit plane of the result is kept
 constexpr int EPI_GSCALE = 8192;   // backward pass with loss-scaled fp16 copies: acc *= acc_scale[0]; y16 = fp16(v * y16_scale[0])
 
 // Sum over the 32 lanes of 32 per-lane values at once: after the 5 exchange levels lane j holds the warp total of a[j].
@@ -270,11 +285,11 @@ __device__ __forceinline__ float4 rn4_tf32(float4 v) {
 // Epilogue of one CTA tile (MT row tiles of 128 x N output channels of group g, rows from r0), run by the 8 epilogue
 // warps: warp w owns TMEM lanes 32 * (w % 4) .. + 31 and the 32-column groups cg = (w - 2) / 4 (mod 2).
 // tmem_acc = TMEM address of the tile's first accumulator column.
-template <int MT, int EPI>
+template <int MT, int EPI, int EW = 8>
 __device__ __forceinline__ void epilogue_tile(const NefConvDesc& d, int g, long r0, uint32_t tmem, int warp, int lane, int tid,
                                               float* s_stat) {
   const int N = d.N;
-  const int q = warp & 3, chalf = (warp - 2) >> 2;
+  const int q = warp & 3, chalf = (warp - 2) >> 2;   // EW epilogue warps: EW / 4 share a lane quarter, splitting its column groups
   constexpr bool GEN = (EPI & EPI_GENERIC) != 0;
   const bool want_stats = GEN ? d.stat_sum != nullptr : (EPI & EPI_STATS) != 0;
   const bool f_bias = GEN ? d.bias != nullptr : (EPI & EPI_BIAS) != 0;
@@ -290,7 +305,7 @@ __device__ __forceinline__ void epilogue_tile(const NefConvDesc& d, int g, long 
   const bool f_gs = GEN ? (d.acc_scale != nullptr || d.y16_scale != nullptr) : (EPI & EPI_GSCALE) != 0;
   const float acc_sc = (f_gs && d.acc_scale) ? __ldg(d.acc_scale) : 1.f;
   const float y16_sc = (f_gs && d.y16_scale) ? __ldg(d.y16_scale) : 1.f;
-  const bool store_y = d.y != nullptr;   // NULL: only the fp16 copy (and the bit plane) of the result is kept
+  const bool store_y = GEN ? d.y != nullptr : (EPI & EPI_NOY) == 0;   // NULL: only the fp16 copy (and the bit plane) of the result is kept
   const bool f_res16 = GEN ? d.res16 != nullptr : (EPI & EPI_RES16) != 0;
   const float res_sc = (f_res16 && d.res16_scale) ? __ldg(d.res16_scale) : 1.f;
   // mask operand: 0 none, 1 / 2 float tensor (> 0 / != 0), 3 one-bit masks
@@ -317,7 +332,7 @@ __device__ __forceinline__ void epilogue_tile(const NefConvDesc& d, int g, long 
     uint32_t* obp = d.out_bits + (long)((d.y_c4_off + g * d.y_c4_gstride) >> 3) * d.y_cstride + orow;
     uint4* y16p = reinterpret_cast<uint4*>(d.y16) + (long)((d.y_c4_off + g * d.y_c4_gstride) >> 1) * d.y_cstride + orow;
     const uint4* r16p = reinterpret_cast<const uint4*>(d.res16) + (long)((d.res_c4_off + g * d.res_c4_gstride) >> 1) * d.res_cstride + orow;
-    for (int cg = chalf; cg < N / 32; cg += 2) {
+    for (int cg = chalf; cg < N / 32; cg += EW / 4) {
       uint32_t v[32];
       tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * N + cg * 32), v);
       const uint32_t mword = mask_mode == 3 ? __ldg(mbp + (long)cg * d.mask_cstride) : 0u;
@@ -357,15 +372,16 @@ __device__ __forceinline__ void epilogue_tile(const NefConvDesc& d, int g, long 
                                __uint_as_float(v[4 * i + 3]));
         if (f_gs) x = x * acc_sc;
         if (f_bias) x = x + __ldg(bias4 + n4);
-        x = x + rr[i];
+        if (f_res || f_res16) x = x + rr[i];
         const float4 pre = x;
         if (f_relu) x = make_float4(fmaxf(x.x, 0.f), fmaxf(x.y, 0.f), fmaxf(x.z, 0.f), fmaxf(x.w, 0.f));
         if (f_drop) {
           const uint64_t bits = drop_bits(d.drop_seed, er.out_row, d.y_c4_off + g * d.y_c4_gstride + n4);
-          x.x = ((bits & 0xffff) >= drop_thr) ? x.x * drop_sc : 0.f;
-          x.y = (((bits >> 16) & 0xffff) >= drop_thr) ? x.y * drop_sc : 0.f;
-          x.z = (((bits >> 32) & 0xffff) >= drop_thr) ? x.z * drop_sc : 0.f;
-          x.w = (((bits >> 48) & 0xffff) >= drop_thr) ? x.w * drop_sc : 0.f;
+          const uint32_t blo = (uint32_t)bits, bhi = (uint32_t)(bits >> 32);   // 32-bit compares (a 64-bit one is two instructions)
+          x.x = ((blo & 0xffffu) >= drop_thr) ? x.x * drop_sc : 0.f;
+          x.y = ((blo >> 16) >= drop_thr) ? x.y * drop_sc : 0.f;
+          x.z = ((bhi & 0xffffu) >= drop_thr) ? x.z * drop_sc : 0.f;
+          x.w = ((bhi >> 16) >= drop_thr) ? x.w * drop_sc : 0.f;
         }
         if (f_bscale) {
           const float4 sc4 = __ldg(bs4 + n4);
@@ -403,7 +419,9 @@ __device__ __forceinline__ void epilogue_tile(const NefConvDesc& d, int g, long 
           x = make_float4((mb & 1u) ? x.x * mask_scale : 0.f, (mb & 2u) ? x.y * mask_scale : 0.f,
                           (mb & 4u) ? x.z * mask_scale : 0.f, (mb & 8u) ? x.w * mask_scale : 0.f);
         }
-        if (f_round) x = rn4_tf32(x);
+        // The stored fp32 value is pre-rounded to TF32 (RNA) so that it and its fp16 copy hold the same significand; with
+        // no fp32 store the fp16 conversion below (RN) is the only rounding (cvt.rna.tf32 is three instructions per value).
+        if (f_round && store_y) x = rn4_tf32(x);
         if (er.valid && store_y) yp[(long)n4 * d.y_cstride] = x;
         if (f_y16) {  // chunks n4 = 2m, 2m + 1 form the 8-channel fp16 chunk m
           const float4 xs = f_gs ? x * y16_sc : x;
@@ -430,15 +448,15 @@ __device__ __forceinline__ void epilogue_tile(const NefConvDesc& d, int g, long 
       }
     }
     if (want_stats) {
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      const int et = tid - 64;  // 0..255
+      asm volatile("bar.sync 1, %0;" ::"n"(EW * 32) : "memory");
+      const int et = tid - 64;  // 0 .. EW * 32 - 1
       const long rec = r0 / 128 + mt;
       if (et < N && rec < n_rec) {
         const long o = rec * ctot + (long)g * N + et;
         d.stat_sum[o] = (s_stat[0 * 128 + et] + s_stat[2 * 128 + et]) + (s_stat[4 * 128 + et] + s_stat[6 * 128 + et]);
         d.stat_sq[o] = (s_stat[1 * 128 + et] + s_stat[3 * 128 + et]) + (s_stat[5 * 128 + et] + s_stat[7 * 128 + et]);
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(EW * 32) : "memory");
     }
   }
 }
@@ -618,8 +636,14 @@ struct PsSmem {
 };
 static_assert(PsSmem::TOTAL <= 227 * 1024, "persistent conv shared memory");
 
+// Epilogue warps of the persistent kernel: 16 (four per scheduler) hide the TMEM-load / global-load latency of the long
+// specialised bodies (dropout, fp16 copies, bit planes) far better than 8; the BatchNorm-statistics and generic bodies
+// need more than the 112 registers that leaves per thread and stay at 8.
 template <int EPI>
-__global__ void __launch_bounds__(FW_THREADS, 1) conv_tc_persist_kernel(const __grid_constant__ NefConvDesc d, int tiles_per_group,
+constexpr int ps_epi_warps() { return (EPI & (EPI_STATS | EPI_GENERIC)) ? 8 : 16; }
+
+template <int EPI>
+__global__ void __launch_bounds__(64 + 32 * ps_epi_warps<EPI>(), 1) conv_tc_persist_kernel(const __grid_constant__ NefConvDesc d, int tiles_per_group,
                                                                         int n_tiles, int use_ws) {
   using S = PsSmem;
   constexpr int MT = S::MT;
@@ -642,7 +666,7 @@ __global__ void __launch_bounds__(FW_THREADS, 1) conv_tc_persist_kernel(const __
   if (tid == 0) {
     for (int i = 0; i < S::XST; ++i) { mbar_init(full_x(i), 1); mbar_init(empty_x(i), 1); }
     for (int i = 0; i < S::WST; ++i) { mbar_init(full_w(i), 1); mbar_init(empty_w(i), 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(acc_full(i), 1); mbar_init(acc_empty(i), FW_THREADS - 64); }
+    for (int i = 0; i < 2; ++i) { mbar_init(acc_full(i), 1); mbar_init(acc_empty(i), 32 * ps_epi_warps<EPI>()); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(smem_u32((const void*)tmem_slot), TM_COLS);
@@ -667,10 +691,11 @@ __global__ void __launch_bounds__(FW_THREADS, 1) conv_tc_persist_kernel(const __
         for (int kb = 0; kb < nkb; ++kb) {
           if (lane == 0) {
             mbar_wait(empty_x(xs), xph ^ 1);
-            mbar_expect_tx(full_x(xs), 8 * xbytes);
+            if (use_ws & 4) mbar_arrive(full_x(xs));   // timing experiment (NEF_TC_WS bit 2): no operand copies at all
+            else mbar_expect_tx(full_x(xs), 8 * xbytes);
           }
           __syncwarp();
-          if (lane < 8) {
+          if (lane < 8 && !(use_ws & 4)) {
             const long chunk = t.x_c4_off + (long)g * t.x_c4_gstride + kb * 8 + lane;
             bulk_g2s(xs0 + xs * S::XBYTES + lane * S::XPITCH, xg + chunk * t.x_cstride, xbytes, full_x(xs));
           }
@@ -678,8 +703,12 @@ __global__ void __launch_bounds__(FW_THREADS, 1) conv_tc_persist_kernel(const __
           if (lane == 0) {
             for (int tp = 0; tp < t.taps; ++tp) {
               mbar_wait(empty_w(wst), wph ^ 1);
-              mbar_expect_tx(full_w(wst), wbytes);
-              bulk_g2s(ws0 + wst * FW_WBYTES, wg + ((((long)g * t.taps + tp) * nkb + kb) * 8) * N, wbytes, full_w(wst));
+              if (use_ws & 4) {
+                mbar_arrive(full_w(wst));
+              } else {
+                mbar_expect_tx(full_w(wst), wbytes);
+                bulk_g2s(ws0 + wst * FW_WBYTES, wg + ((((long)g * t.taps + tp) * nkb + kb) * 8) * N, wbytes, full_w(wst));
+              }
               if (++wst == S::WST) { wst = 0; wph ^= 1; }
             }
           } else {
@@ -691,65 +720,73 @@ __global__ void __launch_bounds__(FW_THREADS, 1) conv_tc_persist_kernel(const __
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
+    // The tensor pipe does not run far ahead of this warp (measured: every cycle between the last MMA of a tap and the
+    // first of the next shows up in the launch time), so the per-tap path is kept as short as possible: operand kind and
+    // tap count are hoisted out of the tap loop, descriptor words advance by adds, the wait accounting (clock reads) only
+    // runs in the timing mode of tools/issuer_waits.py (NEF_TC_WS bit 3).
     const uint32_t idesc = make_idesc(128, N, 0, 0), idesc16 = make_idesc_f16(128, N);
     const uint32_t nb = 2u * (uint32_t)N;
+    const bool timing = (use_ws & 8) != 0;
     int xs = 0, xph = 0, wst = 0, wph = 0, as = 0, aph = 0;
-    long long wt_a = 0, wt_x = 0, wt_w = 0, tq;
+    long long wt_a = 0, wt_x = 0, wt_w = 0, tq = 0;
     const long long t_begin = clock64();
+    const uint32_t xlo0 = desc_lo(xs0, S::XPITCH), wlo0 = desc_lo(ws0, (uint32_t)N * 16);
+    constexpr uint32_t XK = 2 * (S::XPITCH >> 4);   // descriptor units between two K = 16-half (8-float) steps of an activation stage
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      tq = clock64();
+      if (timing) tq = clock64();
       mbar_wait(acc_empty(as), aph ^ 1);
-      wt_a += clock64() - tq;
+      if (timing) wt_a += clock64() - tq;
       tc_fence_after();
       const uint32_t acc0 = tmem + (uint32_t)(as * 256);
       uint32_t accum = 0;
       for (int ti = 0; ti < d.n_terms; ++ti) {
-        const NefConvTerm& t = d.term[ti];
-        const int nkb = t.cin_g >> 5;
+        const int nkb = d.term[ti].cin_g >> 5, taps = d.term[ti].taps;
+        const bool f16 = d.term[ti].x_f16 != 0;
         for (int kb = 0; kb < nkb; ++kb) {
-          tq = clock64();
+          if (timing) tq = clock64();
           mbar_wait(full_x(xs), xph);
-          wt_x += clock64() - tq;
-          for (int tp = 0; tp < t.taps; ++tp) {
-            tq = clock64();
-            mbar_wait(full_w(wst), wph);
-            wt_w += clock64() - tq;
-            tc_fence_after();
-            const uint32_t xa = desc_lo(xs0 + xs * S::XBYTES + tp * 16, S::XPITCH);
-            const uint32_t wa = desc_lo(ws0 + wst * FW_WBYTES, (uint32_t)N * 16);
-            if (elect_one()) {
-              if (t.x_f16) {
-#pragma unroll
-                for (int mt = 0; mt < MT; ++mt) {
-#pragma unroll
-                  for (int k8 = 0; k8 < 4; ++k8)
-                    mma_f16(acc0 + mt * N, desc_of(DESC_HI_SBO128, xa + k8 * 2 * (S::XPITCH >> 4) + mt * 128),
-                            desc_of(DESC_HI_SBO128, wa + k8 * nb), idesc16, accum | (uint32_t)k8);
-                }
-              } else if (use_ws) {  // the weight stage (B) is latched by the first row tile and re-used by the second
-#pragma unroll
-                for (int k8 = 0; k8 < 4; ++k8) {
-                  const uint64_t bd = desc_of(DESC_HI_SBO128, wa + k8 * nb);
-                  mma_tf32_ws<0>(acc0, desc_of(DESC_HI_SBO128, xa + k8 * 2 * (S::XPITCH >> 4)), bd, idesc, accum | (uint32_t)k8);
-                  mma_tf32_ws<2>(acc0 + N, desc_of(DESC_HI_SBO128, xa + k8 * 2 * (S::XPITCH >> 4) + 128), bd, idesc, accum | (uint32_t)k8);
-                }
-              } else {
-#pragma unroll
-                for (int mt = 0; mt < MT; ++mt) {
-#pragma unroll
-                  for (int k8 = 0; k8 < 4; ++k8)
-                    mma_tf32(acc0 + mt * N, desc_of(DESC_HI_SBO128, xa + k8 * 2 * (S::XPITCH >> 4) + mt * 128),
-                             desc_of(DESC_HI_SBO128, wa + k8 * nb), idesc, accum | (uint32_t)k8);
-                }
-              }
-              tc_commit(empty_w(wst));
+          if (timing) wt_x += clock64() - tq;
+          uint32_t xa = xlo0 + (uint32_t)xs * (S::XBYTES >> 4);
+          // All taps of this channel block are issued by the elected lane alone.  Per tap: the 2 x 4 MMAs of the two row
+          // tiles; the wait for the NEXT tap's weight stage sits between the sixth and the seventh, where the issuing
+          // thread is held back by the tensor pipe anyway, so the first MMA of the next tap follows the last of this one.
+          // (No tcgen05 fence here: the operands arrive through the async proxy and their mbarrier; the fence after the
+          // accumulator hand-over above is the one that orders against the epilogue's tcgen05.ld.)
+          if (elect_one()) {
+            int w = wst, ph = wph;
+            if (timing) tq = clock64();
+            mbar_wait(full_w(w), ph);
+            if (timing) wt_w += clock64() - tq;
+#define NEF_PS_TAPS(MMA, IDESC)                                                                                      \
+            for (int tp = 0; tp < taps; ++tp, ++xa) {                                                                \
+              const uint32_t wa = wlo0 + (uint32_t)w * (FW_WBYTES >> 4);                                             \
+              const uint32_t ebar = empty_w(w);                                                                      \
+              if (++w == S::WST) { w = 0; ph ^= 1; }                                                                 \
+              _Pragma("unroll") for (int k8 = 0; k8 < 4; ++k8)                                                       \
+                MMA(acc0, desc_of(DESC_HI_SBO128, xa + k8 * XK), desc_of(DESC_HI_SBO128, wa + k8 * nb), IDESC, accum | (uint32_t)k8); \
+              _Pragma("unroll") for (int k8 = 0; k8 < 2; ++k8)                                                       \
+                MMA(acc0 + N, desc_of(DESC_HI_SBO128, xa + k8 * XK + 128), desc_of(DESC_HI_SBO128, wa + k8 * nb), IDESC, accum | (uint32_t)k8); \
+              if (tp + 1 < taps) {                                                                                   \
+                if (timing) tq = clock64();                                                                          \
+                mbar_wait(full_w(w), ph);                                                                            \
+                if (timing) wt_w += clock64() - tq;                                                                  \
+              }                                                                                                      \
+              _Pragma("unroll") for (int k8 = 2; k8 < 4; ++k8)                                                       \
+                MMA(acc0 + N, desc_of(DESC_HI_SBO128, xa + k8 * XK + 128), desc_of(DESC_HI_SBO128, wa + k8 * nb), IDESC, 1u); \
+              tc_commit(ebar);                                                                                       \
+              accum = 1;                                                                                             \
             }
-            __syncwarp();
-            accum = 1;
-            if (++wst == S::WST) { wst = 0; wph ^= 1; }
+            if (f16) { NEF_PS_TAPS(mma_f16, idesc16) } else { NEF_PS_TAPS(mma_tf32, idesc) }
+#undef NEF_PS_TAPS
+            tc_commit(empty_x(xs));
           }
-          if (elect_one()) tc_commit(empty_x(xs));
           __syncwarp();
+          {  // every lane keeps the stage counters (the elected lane advanced its private copies)
+            const int total = wst + taps;
+            wph ^= (total / S::WST) & 1;
+            wst = total % S::WST;
+            accum = 1;
+          }
           if (++xs == S::XST) { xs = 0; xph ^= 1; }
         }
       }
@@ -771,7 +808,8 @@ __global__ void __launch_bounds__(FW_THREADS, 1) conv_tc_persist_kernel(const __
       const long r0 = (long)(tile - g * tiles_per_group) * (MT * 128);
       mbar_wait(acc_full(as), aph);
       tc_fence_after();
-      epilogue_tile<MT, EPI>(d, g, r0, tmem + (uint32_t)(as * 256), warp, lane, tid, s_stat);
+      if (!(use_ws & 2))   // (NEF_TC_WS bit 1: timing experiment without the epilogue)
+        epilogue_tile<MT, EPI, ps_epi_warps<EPI>()>(d, g, r0, tmem + (uint32_t)(as * 256), warp, lane, tid, s_stat);
       tc_fence_before();
       mbar_arrive(acc_empty(as));
       if (++as == 2) { as = 0; aph ^= 1; }
@@ -1069,7 +1107,8 @@ static int g_tc_mt = 0;  // 0 = automatic; 4 forces four row tiles per CTA, one 
 
 // the specialised epilogues instantiated for the 4-row-tile kernel (everything else takes the generic one)
 #define NEF_TC_EPI_LIST(X) X(0) X(2) X(5) X(32) X(33) X(36) X(37) X(38) X(44) X(48) X(50) X(64) X(294) X(418) X(513) \
-  X(1062) X(1068) X(1318) X(2080) X(2082) X(2338) X(4132) X(4134) X(4390) X(5158) X(5164) X(5414) X(8194) X(14368) X(14370) X(14626) X(21540) X(21796) X(24576) X(30752) X(31008)
+  X(1062) X(1068) X(1318) X(2080) X(2082) X(2338) X(4132) X(4134) X(4390) X(5158) X(5164) X(5414) X(8194) X(14368) X(14370) X(14626) X(21540) X(21796) X(24576) X(30752) X(31008) \
+  X(37932) X(54308) X(54564) X(47136) X(63520) X(63776)   /* the production fp16-only stores: 5164, 21540, 21796, 14368, 30752, 31008 | EPI_NOY */
 
 template <int MT, int EPI>
 static int tc_optin() {
@@ -1136,6 +1175,7 @@ static int epi_code(const NefConvDesc* d) {
   if (d->drop_p > 0.f) e |= tc::EPI_DROP;
   if (d->mask_mode == 1 && !mbits) e |= tc::EPI_MASK1;
   if (d->round_tf32) e |= tc::EPI_ROUND;
+  if (!d->y) e |= tc::EPI_NOY;
   return e;
 }
 
@@ -1171,7 +1211,7 @@ static int launch_conv_persist(const NefConvDesc* d, cudaStream_t s) {
   nef_tc_note_dispatch(0);
   note_persist_epi(specialised ? epi_code(d) : tc::EPI_GENERIC);
   switch (epi_code(d)) {
-#define X(E) case E: tc::conv_tc_persist_kernel<E><<<grid, tc::FW_THREADS, tc::PsSmem::TOTAL, s>>>(*d, tpg, n_tiles, g_tc_ws); break;
+#define X(E) case E: tc::conv_tc_persist_kernel<E><<<grid, 64 + 32 * tc::ps_epi_warps<E>(), tc::PsSmem::TOTAL, s>>>(*d, tpg, n_tiles, g_tc_ws); break;
     NEF_TC_EPI_LIST(X)
 #undef X
     default: tc::conv_tc_persist_kernel<tc::EPI_GENERIC><<<grid, tc::FW_THREADS, tc::PsSmem::TOTAL, s>>>(*d, tpg, n_tiles, g_tc_ws); break;

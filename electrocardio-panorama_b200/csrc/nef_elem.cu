@@ -1,6 +1,7 @@
 // Non-GEMM kernels of the Nef-Net hot path: stem, angular encoding, ROI resampling, latent mixing,
 // BatchNorm passes, the 64->1 output convolution, losses and the optimiser step.
 // Reference lines are cited per kernel (paths relative to the reference's codes/).
+#include <cuda_fp16.h>
 #include "nef_elem.cuh"
 
 namespace nef {
@@ -28,7 +29,7 @@ __device__ __forceinline__ uint32_t f16x2_sat(float lo, float hi) {
 }
 
 __global__ void __launch_bounds__(256) stem_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, T4 y,
-                                                       uint32_t* __restrict__ amax, uint4* __restrict__ y16, int G, int L) {
+                                                       uint32_t* __restrict__ amax, uint4* __restrict__ y16, int G, int L, int store32) {
   __shared__ float xs[4 * STEM_TJ + 24];
   __shared__ float4 ws[15][32];
   const int tid = threadIdx.x;
@@ -96,8 +97,10 @@ __global__ void __launch_bounds__(256) stem_fwd_kernel(const float* __restrict__
     const long off = (long)(g * 32 + c4) * y.cs + y.row(b, j);
     m0 = tf32_rn4(m0);
     m1 = tf32_rn4(m1);
-    y.p[off] = m0;
-    if (has_b) y.p[off + 1] = m1;
+    if (store32) {
+      y.p[off] = m0;
+      if (has_b) y.p[off + 1] = m1;
+    }
     if (y16) {  // fp16 copy for the first encoder convolution: 8 channels (chunks c4, c4 + 1) per 16-byte row
       if ((cc & 1) == 0) {
         h0[0] = f16x2_sat(m0.x, m0.y); h0[1] = f16x2_sat(m0.z, m0.w);
@@ -208,10 +211,10 @@ __global__ void __launch_bounds__(256, 2) stem_bwd_kernel(const float* __restric
   }
 }
 
-int stem_fwd(const float* x, const float* w, T4 y, uint32_t* amax, void* y16, int G, cudaStream_t s) {
+int stem_fwd(const float* x, const float* w, T4 y, uint32_t* amax, void* y16, int G, cudaStream_t s, int store32) {
   const int L = y.L * 4;
   dim3 grid((y.L + STEM_TJ - 1) / STEM_TJ, G, y.B);
-  stem_fwd_kernel<<<grid, 256, 0, s>>>(x, w, y, amax, reinterpret_cast<uint4*>(y16), G, L);
+  stem_fwd_kernel<<<grid, 256, 0, s>>>(x, w, y, amax, reinterpret_cast<uint4*>(y16), G, L, (store32 || !y16) ? 1 : 0);
   NEF_CHECK_LAUNCH("stem_fwd_kernel");
   return 0;
 }
@@ -315,8 +318,8 @@ Window centre_window(int L4) {
   return w;
 }
 
-__global__ void window_extract_kernel(T4 w, T4 xw, int G, Window win) {
-  // xw chunk g*16 + c  <-  w chunk g*32 + 16 + c
+__global__ void window_extract_kernel(T4 w, T4 xw, int G, Window win, const uint4* __restrict__ w16) {
+  // xw chunk g*16 + c  <-  w chunk g*32 + 16 + c  (w16: from the fp16 copy of w, 8 channels per 16-byte row)
   const long total = (long)G * 16 * xw.B * win.Lw;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     const int l = i % win.Lw;
@@ -324,7 +327,15 @@ __global__ void window_extract_kernel(T4 w, T4 xw, int G, Window win) {
     const int b = r % xw.B;
     const int c = r / xw.B;
     const int g = c / 16, cc = c % 16;
-    *xw.at(c, b, l) = *w.at(g * 32 + 16 + cc, b, win.w0 + l);
+    const int c4 = g * 32 + 16 + cc;
+    if (w16) {
+      const uint4 h = __ldg(w16 + (long)(c4 >> 1) * w.cs + w.row(b, win.w0 + l));
+      const uint32_t lo = (c4 & 1) ? h.z : h.x, hi = (c4 & 1) ? h.w : h.y;
+      const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&lo)), e = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+      *xw.at(c, b, l) = make_float4(a.x, a.y, e.x, e.y);
+    } else {
+      *xw.at(c, b, l) = *w.at(c4, b, win.w0 + l);
+    }
   }
 }
 
@@ -357,9 +368,9 @@ __global__ void window_scatter_kernel(T4 gxw, T4 gw, int G, Window win, uint4* _
   }
 }
 
-int window_extract(T4 w, T4 xw, int G, Window win, cudaStream_t s) {
+int window_extract(T4 w, T4 xw, int G, Window win, const void* w16, cudaStream_t s) {
   const long total = (long)G * 16 * xw.B * win.Lw;
-  window_extract_kernel<<<grid_for(total, 256), 256, 0, s>>>(w, xw, G, win);
+  window_extract_kernel<<<grid_for(total, 256), 256, 0, s>>>(w, xw, G, win, reinterpret_cast<const uint4*>(w16));
   NEF_CHECK_LAUNCH("window_extract_kernel");
   return 0;
 }
@@ -470,10 +481,47 @@ __global__ void __launch_bounds__(128) bscale_grad_kernel(T4 gx, T4 ys, const fl
     *reinterpret_cast<float4*>(ds + (long)b * gx.C + c4 * 4) = o;
   }
 }
+// The same from fp16 copies (8 channels per 16-byte row): gx16 carries the loss scale S, inv[0] = 1 / S.
+__global__ void __launch_bounds__(128) bscale_grad_h_kernel(T4 gx, const uint4* __restrict__ gx16, const uint4* __restrict__ ys16,
+                                                            const float* __restrict__ inv, const float* __restrict__ scale,
+                                                            float* __restrict__ ds) {
+  __shared__ float red[4][8];
+  const int c8 = blockIdx.x, b = blockIdx.y;
+  const uint4* gp = gx16 + (long)c8 * gx.cs + gx.row(b, 0);
+  const uint4* yp = ys16 + (long)c8 * gx.cs + gx.row(b, 0);
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int l = threadIdx.x; l < gx.L; l += 128) {
+    const uint4 g = __ldg(gp + l), y = __ldg(yp + l);
+    const uint32_t gw[4] = {g.x, g.y, g.z, g.w}, yw[4] = {y.x, y.y, y.z, y.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&gw[j])), e = __half22float2(*reinterpret_cast<const __half2*>(&yw[j]));
+      acc[2 * j] += a.x * e.x;
+      acc[2 * j + 1] += a.y * e.y;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = warp_sum(acc[j]);
+  if ((threadIdx.x & 31) == 0)
+    for (int j = 0; j < 8; ++j) red[threadIdx.x >> 5][j] = acc[j];
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    const int j = threadIdx.x;
+    const float t = ((red[0][j] + red[1][j]) + (red[2][j] + red[3][j])) * __ldg(inv);
+    const float sc = scale[(long)b * gx.C + c8 * 8 + j];
+    ds[(long)b * gx.C + c8 * 8 + j] = sc != 0.f ? t / (sc * sc) : 0.f;
+  }
+}
 int bscale_grad(T4 gx, T4 ys, const float* scale, float* ds, cudaStream_t s) {
   dim3 grid(gx.C / 4, gx.B);
   bscale_grad_kernel<<<grid, 128, 0, s>>>(gx, ys, scale, ds);
   NEF_CHECK_LAUNCH("bscale_grad_kernel");
+  return 0;
+}
+int bscale_grad_h(T4 gx, const void* gx16, const void* ys16, const float* inv, const float* scale, float* ds, cudaStream_t s) {
+  dim3 grid(gx.C / 8, gx.B);
+  bscale_grad_h_kernel<<<grid, 128, 0, s>>>(gx, reinterpret_cast<const uint4*>(gx16), reinterpret_cast<const uint4*>(ys16), inv, scale, ds);
+  NEF_CHECK_LAUNCH("bscale_grad_h_kernel");
   return 0;
 }
 

@@ -26,7 +26,7 @@ struct BnLayer {          // one BatchNorm1d of the decoder for one decoder call
   double* s2;             // [C] backward: sum g * xhat
 };
 
-int stem_fwd(const float* x, const float* w, T4 y, uint32_t* amax, void* y16, int G, cudaStream_t s);  // y16: optional fp16 copy
+int stem_fwd(const float* x, const float* w, T4 y, uint32_t* amax, void* y16, int G, cudaStream_t s, int store32 = 1);  // y16: optional fp16 copy (store32 = 0: only that copy is written)
 int stem_bwd(const float* x, const uint32_t* amax, T4 dy, float* dw, int G, cudaStream_t s);
 int angular_fwd(const float* theta, const float* w, const float* b, float* out, int n, int D, cudaStream_t s);
 int angular_bwd(const float* theta, const float* dout, float* dw, float* db, int n, int D, cudaStream_t s);
@@ -34,7 +34,7 @@ int angular_bwd(const float* theta, const float* dout, float* dw, float* db, int
 // z2_conv1 only matters at the centre columns (roi_algin samples nothing else)
 struct Window { int w0, Lw, y0; float wy1; };
 Window centre_window(int L4);
-int window_extract(T4 w, T4 xw, int G, Window win, cudaStream_t s);                  // w z2-half -> (64G, Lw)
+int window_extract(T4 w, T4 xw, int G, Window win, const void* w16, cudaStream_t s);   // w16: read the fp16 copy of w instead                  // w z2-half -> (64G, Lw)
 // -> z2 half of g_w, zeros elsewhere; gw16 (optional): fp16 copy of the same rows scaled by s16[0] (device scalar)
 //   store32 = 0: only the fp16 copy is written
 int window_scatter(T4 gxw, T4 gw, int G, Window win, void* gw16, const float* s16, int store32, cudaStream_t s);
@@ -45,7 +45,9 @@ int roi_align_bwd(T4 dra, const int64_t* rois, T4 z2c, T4 gz2c, Window win, int 
 int deinterleave2(T4 src, T4 even, T4 odd, cudaStream_t s);
 // gradient of the angular scale s (model_nefnet.py:120-123): ys = relu(u) * s[b, c]; gx = d ys * s * (ys != 0)  ->
 //   ds[b, c] = sum_l d ys * relu(u) = sum_l gx * ys / s^2      (overwrites ds)
-int bscale_grad(T4 gx, T4 ys, const float* scale, float* ds, cudaStream_t s);                          // (C, 2n) -> 2 x (C, n)
+int bscale_grad(T4 gx, T4 ys, const float* scale, float* ds, cudaStream_t s);
+// the same from fp16 copies of gx (times the loss scale; inv[0] = 1 / S) and ys, both with gx's row geometry
+int bscale_grad_h(T4 gx, const void* gx16, const void* ys16, const float* inv, const float* scale, float* ds, cudaStream_t s);                          // (C, 2n) -> 2 x (C, n)
 
 struct LatentArgs {
   T4 z1, z2o;             // (128G, L4), (896G, 32)

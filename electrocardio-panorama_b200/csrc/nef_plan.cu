@@ -755,7 +755,8 @@ extern "C" int nef_forward(NefPlan* p, const NefForwardArgs* a, nef_stream_t sv)
     RUN(queue_pack(packs, P[P_CT_W] + t, p->ct_f[t], 7 * G, 64, 128, 1, 128LL * 64 * 2, 2, 64 * 2, 0, 0, s));
   RUN(nef_pack_weights_batch(&packs, s));
 
-  RUN(stem_fwd(a->x, P[P_STEM], p->s0, a->save_for_backward ? p->s0_amax : nullptr, p->fwd_f16 ? p->s0_h : nullptr, G, s));
+  RUN(stem_fwd(a->x, P[P_STEM], p->s0, a->save_for_backward ? p->s0_amax : nullptr, p->fwd_f16 ? p->s0_h : nullptr, G, s,
+               p->h_f16_only ? 0 : 1));   // fp16 dataflow: the first block reads only the fp16 copy
   RUN(angular_fwd(a->input_thetas, P[P_MLP1_W], P[P_MLP1_B], p->s_in, B * G, 128, s));
   const float dp = a->drop_p;
   const uint64_t seed = a->drop_seed * 16;
@@ -768,15 +769,16 @@ extern "C" int nef_forward(NefPlan* p, const NefForwardArgs* a, nef_stream_t sv)
       io.h16 = p->eh_h[i];
       io.y16 = p->ey_h[i];
       io.h_f16_only = p->h_f16_only;
-      io.y_f16_only = p->h_f16_only && i < 2;   // ey[2] (bscale_grad) keeps its fp32 storage
+      io.y_f16_only = p->h_f16_only && (i < 2 || !g_k3_tf32);   // every reader takes the fp16 copy / the bit plane
     }
     RUN(block_fwd(io, dp, seed + i, i == 2 ? p->s_in : nullptr, s));
   }
   {
     BlockIO io{p->ey[2], 0, 32, p->hw, p->w, &p->wc[0], &p->wc[1], nullptr, nullptr, G};
     if (a->save_for_backward) { io.hbits = p->b_hw; io.ybits = p->b_w; }
-    if (p->fwd_f16 && !g_k3_tf32) { io.x16 = p->ey_h[2]; io.h16 = p->hw_h; io.y16 = p->w_h; io.h_f16_only = p->h_f16_only; }
-    else if (p->bwd_f16) { io.h16 = p->hw_h; io.y16 = p->w_h; }
+    if (p->fwd_f16 && !g_k3_tf32) {
+      io.x16 = p->ey_h[2]; io.h16 = p->hw_h; io.y16 = p->w_h; io.h_f16_only = p->h_f16_only; io.y_f16_only = p->h_f16_only;
+    } else if (p->bwd_f16) { io.h16 = p->hw_h; io.y16 = p->w_h; }
     RUN(block_fwd(io, dp, seed + 3, nullptr, s));
   }
   {
@@ -786,7 +788,7 @@ extern "C" int nef_forward(NefPlan* p, const NefForwardArgs* a, nef_stream_t sv)
     else if (p->bwd_f16) io.h16 = p->h1_h;
     RUN(block_fwd(io, dp, seed + 4, nullptr, s));
   }
-  RUN(window_extract(p->w, p->xw, G, p->win, s));
+  RUN(window_extract(p->w, p->xw, G, p->win, (p->fwd_f16 && !g_k3_tf32 && p->h_f16_only) ? p->w_h : nullptr, s));
   {
     BlockIO io{p->xw, 0, 16, p->hz, p->z2c, &p->z2c1[0], &p->z2c1[1], &p->z2c1[2], P[P_Z2C1 + 3], G};
     RUN(block_fwd(io, dp, seed + 5, nullptr, s));
@@ -1078,9 +1080,11 @@ extern "C" int nef_backward(NefPlan* p, const NefBackwardArgs* a, nef_stream_t s
     if (f16) {
       bb.io.x16 = p->ey_h[2]; bb.io.h16 = p->hw_h; bb.gy16 = p->GA_h[2]; bb.gh16 = p->GA_h[0]; bb.lscale = ls;
       fin.y16s(p->GA_h[1], ls);
+      fin.d.y = nullptr;   // read as fp16 only: by bscale_grad_h below and by the last encoder block's backward
     }
     RUN(block_bwd(bb, dp, fin, s));
-    RUN(bscale_grad(p->GA[1], p->ey[2], p->s_in, p->ds_in, s));
+    if (f16) RUN(bscale_grad_h(p->GA[1], p->GA_h[1], p->ey_h[2], ls + 1, p->s_in, p->ds_in, s));
+    else RUN(bscale_grad(p->GA[1], p->ey[2], p->s_in, p->ds_in, s));
   }
   if (Gd[P_MLP1_W]) RUN(angular_bwd(p->thetas_in, p->ds_in, Gd[P_MLP1_W], Gd[P_MLP1_B], B * G, 128, s));
   // ---- encoder blocks 2, 1, 0
@@ -1137,15 +1141,18 @@ static bool find_tensor(const NefPlan* p, const char* name, NamedTensor* out) {
     if (n == pre + ".y") { out->t = &y; return true; }
     return false;
   };
-  if (is("stem")) { out->t = &p->s0; return true; }
+  if (is("stem")) { out->t = &p->s0; if (p->h_f16_only) out->h16 = p->s0_h; return true; }
   // hidden activations that the last forward kept as fp16 copies only
   auto h_only = [&](const void* h16) { if (p->h_f16_only && out->t && n.size() > 2 && n.substr(n.size() - 2) == ".h") out->h16 = h16; return true; };
   for (int i = 0; i < 3; ++i)
     if (blk(("W_encoder.layer1." + std::to_string(i)).c_str(), p->eh[i], p->ey[i])) {
-      if (p->h_f16_only && i < 2 && out->t == &p->ey[i]) { out->h16 = p->ey_h[i]; return true; }
+      if (p->h_f16_only && (i < 2 || !g_k3_tf32) && out->t == &p->ey[i]) { out->h16 = p->ey_h[i]; return true; }
       return h_only(p->eh_h[i]);
     }
-  if (blk("w_conv.0", p->hw, p->w)) return h_only(p->hw_h);
+  if (blk("w_conv.0", p->hw, p->w)) {
+    if (p->h_f16_only && p->fwd_f16 && !g_k3_tf32 && out->t == &p->w) { out->h16 = p->w_h; return true; }
+    return h_only(p->hw_h);
+  }
   if (blk("z1_conv.0", p->h1, p->z1)) return h_only(p->h1_h);
   if ( blk("z2_conv1.0", p->hz, p->z2c) ||
       blk("z2_conv2.0", p->h20, p->y20) || blk("z2_conv2.2", p->h22, p->z2o))

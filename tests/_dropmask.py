@@ -1,10 +1,11 @@
-"""Host restatement of the device's counter-based dropout keep-masks (csrc/nef_common.cuh: drop_bits / mix64,
+"""Host restatement of the device's counter-based dropout keep-masks (csrc/nef_common.cuh: drop_bits / hash32,
 csrc/nef_plan.cu: nef_forward's per-block seeds), so that the CPU oracle can be run with dropout ON using exactly the
 masks the CUDA path applied (nefnet_oracle.forward(..., keeps=...)).  Test infrastructure only.
 
 The hidden activation h of every residual block is dropped: element (row, 4-channel chunk c4, lane j) is kept iff the
-j-th 16-bit field of mix64(seed ^ row * K1 ^ (c4 << 40) ^ c4 * K2) is >= floor(p * 65536); row = b * (L + 6) + 3 + l in the
-block's CBL4 row space, c4 = channel / 4 of the (groups * 128)-channel tensor, seed = drop_seed * 16 + block index.
+j-th 16-bit field of (hash32(k), hash32(k ^ K3)), k = hash32(row ^ seedkey) + c4 * K1, is >= floor(p * 65536);
+row = b * (L + 6) + 3 + l in the block's CBL4 row space, c4 = channel / 4 of the (groups * 128)-channel tensor,
+seed = drop_seed * 16 + block index (hash32 = the two-multiply "lowbias32" finaliser).
 """
 import numpy as np
 import torch
@@ -15,23 +16,27 @@ BLOCKS = ("W_encoder.layer1.0", "W_encoder.layer1.1", "W_encoder.layer1.2", "w_c
           "z2_conv2.0", "z2_conv2.2")   # seed index = position (nef_plan.cu: seed + i)
 
 
-def _mix64(z):
-    z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
-    z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
-    return z ^ (z >> np.uint64(31))
+def _hash32(x):
+    x = x.astype(np.uint32) if isinstance(x, np.ndarray) else np.uint32(x)
+    x = (x ^ (x >> np.uint32(16))) * np.uint32(0x7FEB352D)
+    x = (x ^ (x >> np.uint32(15))) * np.uint32(0x846CA68B)
+    return x ^ (x >> np.uint32(16))
 
 
 def keep_mask(seed, B, C, L, p):
     """(B, C, L) bool keep-mask of a CBL4 tensor with C channels, B segments, L samples."""
+    seed &= 0xFFFFFFFFFFFFFFFF
     with np.errstate(over="ignore"):
+        sk = _hash32(np.uint32(seed & 0xFFFFFFFF) ^ _hash32(np.uint32((seed >> 32) & 0xFFFFFFFF) + np.uint32(0x9E3779B9)))
         rows = (np.arange(B, dtype=np.uint64)[:, None] * np.uint64(L + 2 * HALO) + np.uint64(HALO)
                 + np.arange(L, dtype=np.uint64)[None, :]).reshape(-1)                       # (B*L,)
-        c4 = np.arange(C // 4, dtype=np.uint64)
-        key = (np.uint64(seed & 0xFFFFFFFFFFFFFFFF) ^ (rows[None, :] * np.uint64(0x9E3779B97F4A7C15))
-               ^ (c4[:, None] << np.uint64(40)) ^ (c4[:, None] * np.uint64(0xD1B54A32D192ED03)))
-        bits = _mix64(key)                                                                     # (C/4, B*L)
-    thr = np.uint64(int(np.float32(p) * np.float32(65536.0)))
-    lanes = np.stack([((bits >> np.uint64(16 * j)) & np.uint64(0xFFFF)) >= thr for j in range(4)], axis=1)  # (C/4, 4, B*L)
+        rk = _hash32((rows & np.uint64(0xFFFFFFFF)).astype(np.uint32) ^ sk)                   # (B*L,)
+        c4 = np.arange(C // 4, dtype=np.uint32)
+        k = rk[None, :] + c4[:, None] * np.uint32(0x9E3779B1)                                 # (C/4, B*L)
+        lo, hi = _hash32(k), _hash32(k ^ np.uint32(0x85EBCA6B))
+    thr = np.uint32(int(np.float32(p) * np.float32(65536.0)))
+    fields = [lo & np.uint32(0xFFFF), lo >> np.uint32(16), hi & np.uint32(0xFFFF), hi >> np.uint32(16)]
+    lanes = np.stack([f >= thr for f in fields], axis=1)                                      # (C/4, 4, B*L)
     return torch.from_numpy(lanes.reshape(C, B, L).transpose(1, 0, 2).copy())
 
 

@@ -41,7 +41,8 @@ FP32_GRAD_COS = 0.99
 #   5164 first convolutions of the big blocks (dropout, fp16 copy, bit plane), 21540 / 21796 their second convolutions
 #   (residual read from the fp16 copy; angular scale), 37 z1_conv's second convolution, 513 decoder forward with BatchNorm
 #   statistics, 14368 / 30752 / 31008 / 24576 the loss-scaled fp16 data gradients, 0 / 32 decoder data gradients
-BENCH_EPI_DROPOUT = {5164, 21540, 21796, 37, 513, 14368, 30752, 31008, 24576, 0, 32}
+NOY = 32768   # EPI_NOY: no fp32 store, only the fp16 copy / bit plane of the result
+BENCH_EPI_DROPOUT = {5164 | NOY, 21540 | NOY, 21796 | NOY, 37, 513, 14368 | NOY, 30752 | NOY, 31008 | NOY, 24576, 0, 32}
 
 
 BLOCKS = ("W_encoder.layer1.0", "W_encoder.layer1.1", "W_encoder.layer1.2", "w_conv.0", "z1_conv.0", "z2_conv1.0", "z2_conv2.0",
@@ -50,7 +51,7 @@ BLOCKS = ("W_encoder.layer1.0", "W_encoder.layer1.1", "W_encoder.layer1.2", "w_c
 
 # hidden activations of the big blocks: not stored in fp32 by the production dataflow (nothing may read that storage)
 DROPPED_FP32 = ("W_encoder.layer1.0.h", "W_encoder.layer1.1.h", "W_encoder.layer1.2.h", "w_conv.0.h", "z1_conv.0.h",
-                "W_encoder.layer1.0.y", "W_encoder.layer1.1.y")
+                "W_encoder.layer1.0.y", "W_encoder.layer1.1.y", "W_encoder.layer1.2.y", "w_conv.0.y", "stem")
 
 
 def _device_patterns(m, B, G, L):

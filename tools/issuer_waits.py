@@ -17,7 +17,7 @@ for _ in range(3): ops.gconv_fwd(d)
 torch.cuda.synchronize()
 n = 148
 buf = (C.c_ulonglong * (8 * n))()
-lib.nef_tc_debug_dump(buf, n)
+lib.nef_tc_debug_dump(buf, n)  # wait counters need NEF_TC_WS=8 (timing mode)
 t = np.array(buf, dtype=np.int64).reshape(n, 8)
 tot = t[:, 0].astype(float)
 print("taps %d  issuer cycles median %.0f ; waiting: acc_empty %.1f%%  full_x %.1f%%  full_w %.1f%%" % (
