@@ -544,6 +544,46 @@ int deinterleave2(T4 src, T4 even, T4 odd, cudaStream_t s) {
   return 0;
 }
 
+// ROI tiling check (roi_pooling_1d.py:83-98): the reference concatenates, per segment, the 7 reversed ROIs of truncated
+// lengths long(r1 / 4) - long(r0 / 4) and stacks the segments, so every segment's lengths must be positive-or-empty and
+// sum to L / 4 -- otherwise torch.stack / torch.cat raise.  flag[0] = number of offending segments, flag[1] = the first
+// one, flag[2] = its length sum (one block; the caller reads the three ints back whenever it chooses to synchronise).
+__global__ void __launch_bounds__(256) roi_check_kernel(const int64_t* __restrict__ rois, int B, int L4, int* __restrict__ flag) {
+  __shared__ int s_cnt, s_first, s_sum;
+  if (threadIdx.x == 0) { s_cnt = 0; s_first = 0x7fffffff; s_sum = 0; }
+  __syncthreads();
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    long total = 0;
+    bool bad = false;
+    for (int j = 0; j < NEF_NROI; ++j) {
+      const long a0 = (long)((float)rois[((long)b * NEF_NROI + j) * 2 + 0] * 0.25f);
+      const long a1 = (long)((float)rois[((long)b * NEF_NROI + j) * 2 + 1] * 0.25f);
+      if (a1 < a0) bad = true;          // F.interpolate(size < 0) raises in the reference
+      total += a1 > a0 ? a1 - a0 : 0;
+    }
+    if (bad || total != L4) {
+      atomicAdd(&s_cnt, 1);
+      atomicMin(&s_first, b);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && s_cnt > 0) {
+    long total = 0;
+    for (int j = 0; j < NEF_NROI; ++j) {
+      const long a0 = (long)((float)rois[((long)s_first * NEF_NROI + j) * 2 + 0] * 0.25f);
+      const long a1 = (long)((float)rois[((long)s_first * NEF_NROI + j) * 2 + 1] * 0.25f);
+      total += a1 - a0;
+    }
+    s_sum = (int)total;
+  }
+  if (threadIdx.x == 0) { flag[0] = s_cnt; flag[1] = s_cnt ? s_first : -1; flag[2] = s_sum; }
+}
+int roi_check(const int64_t* rois, int B, int L4, int* flag, cudaStream_t s) {
+  roi_check_kernel<<<1, 256, 0, s>>>(rois, B, L4, flag);
+  NEF_CHECK_LAUNCH("roi_check_kernel");
+  return 0;
+}
+
 // ===========================================================================================
 // Latent mixing: roi_pooling_reverse (roi_pooling_1d.py:72-99), lead mean and lead shuffle
 // (model_nefnet.py:143-160), query scaling (:163-166) and the decoder's first Upsample (:102).

@@ -40,6 +40,7 @@ int window_extract(T4 w, T4 xw, int G, Window win, const void* w16, cudaStream_t
 int window_scatter(T4 gxw, T4 gw, int G, Window win, void* gw16, const float* s16, int store32, cudaStream_t s);
 // scale[0] = S, scale[1] = 1 / S, S = 2^k with S * max|d0, d1, d2| in [32, 64) (1 if all zero); scale[2] is scratch
 int grad_loss_scale(const float* d0, const float* d1, const float* d2, long n, float* scale, cudaStream_t s);
+int roi_check(const int64_t* rois, int B, int L4, int* flag, cudaStream_t s);   // flag[3]: bad segments, first one, its length sum
 int roi_align_fwd(T4 z2c, const int64_t* rois, T4 ra, Window win, int L4, cudaStream_t s);
 int roi_align_bwd(T4 dra, const int64_t* rois, T4 z2c, T4 gz2c, Window win, int L4, cudaStream_t s);
 int deinterleave2(T4 src, T4 even, T4 odd, cudaStream_t s);

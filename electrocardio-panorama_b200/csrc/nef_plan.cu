@@ -1212,6 +1212,10 @@ static T4 view_t4(const float* ptr, int C, int B, int L) {
   t.C = C; t.B = B; t.L = L; t.Lp = L + 2 * NEF_HALO; t.cs = (long)B * t.Lp;
   return t;
 }
+extern "C" int nef_roi_check(const int64_t* rois, int B, int L, int32_t* flag, nef_stream_t s) {
+  NEF_REQUIRE(rois && flag && B >= 1 && L % 4 == 0, "nef_roi_check: bad arguments");
+  return roi_check(rois, B, L / 4, flag, (cudaStream_t)s);
+}
 extern "C" int nef_stem_fwd(const float* x, const float* w, float* y, uint32_t* argmax, int B, int G, int L,
                             nef_stream_t s) {
   return stem_fwd(x, w, view_t4(y, 128 * G, B, L / 4), argmax, nullptr, G, (cudaStream_t)s);

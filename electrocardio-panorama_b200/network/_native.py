@@ -97,6 +97,7 @@ SIGNATURES = {
     "nef_backward": (C.c_int, [C.c_void_p, C.POINTER(NefBackwardArgs), C.c_void_p]),
     "nef_gen_ecg": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                               C.c_int, C.c_void_p, C.c_void_p]),
+    "nef_roi_check": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "nef_loss_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int,
                                C.POINTER(C.c_float), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "nef_loss_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int,

@@ -12,6 +12,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 import random
 
 import torch
@@ -104,6 +105,13 @@ class Model_nefnet(nn.Module):
         # the encoder's backward -- so the reference's unmodified solver.py:232-235 (backward(); optim.step()) trains data
         # parallel under torchrun.  Set False to exchange gradients yourself (network.optim.allreduce_gradients).
         self.ddp_allreduce = True
+        # Mis-tiled ROIs: the reference raises (torch.stack / torch.cat size mismatch, roi_pooling_1d.py:96-98) when the
+        # truncated ROI lengths of a segment do not sum to L / 4.  "deferred" (default): a three-int flag written by one small
+        # launch of every forward is read back without stalling the launch queue and the RuntimeError is raised at the
+        # module's next entry point (the same step's backward() in a training loop, else the next forward / gen_ecg /
+        # check_rois()); "sync": raised inside forward (one device synchronisation per call); "off": no check.
+        self.roi_check = os.environ.get("NEF_ROI_CHECK", "deferred")
+        self._roi_pending = None
         self._ddp_ready = False
         self._grads_valid = False
         self._build_parameters()
@@ -287,6 +295,7 @@ class Model_nefnet(nn.Module):
         query_theta = self._f32(query_theta, device)
         rois = rois.detach().to(device=device, dtype=torch.int64).contiguous()
         rest = self._f32(rest_theta, device) if V > 0 else None
+        self._roi_launch_check(rois, B, L, device)
         a = N.NefForwardArgs()
         self._params_arr = self._param_ptr_array()
         a.params = C.cast(self._params_arr, C.POINTER(C.c_void_p))
@@ -320,6 +329,37 @@ class Model_nefnet(nn.Module):
         self._saved = (x, input_thetas, query_theta, rois, plan) if save else None
         return outs
 
+    # ------------------------------------------------------------------ ROI tiling diagnosis
+    def _roi_launch_check(self, rois, B, L, device):
+        self.check_rois()                      # a pending verdict of an earlier call is due now
+        if self.roi_check == "off":
+            return
+        if getattr(self, "_roi_flag_dev", None) is None or self._roi_flag_dev.device != device:
+            self._roi_flag_dev = torch.zeros(3, dtype=torch.int32, device=device)
+            self._roi_flag_host = torch.zeros(3, dtype=torch.int32).pin_memory()
+        N.check(N.load().nef_roi_check(N.ptr(rois), B, L, N.ptr(self._roi_flag_dev), N.stream_ptr()), "nef_roi_check")
+        self._roi_flag_host.copy_(self._roi_flag_dev, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self._roi_pending = (ev, L // 4)
+        if self.roi_check == "sync":
+            self.check_rois()
+
+    def check_rois(self):
+        """Raises the reference's RuntimeError if the ROIs of the last forward / gen_ecg did not tile their segments
+        (waits for that call's first launch only; a no-op when nothing is pending)."""
+        pend, self._roi_pending = self._roi_pending, None
+        if pend is None:
+            return
+        ev, L4 = pend
+        ev.synchronize()
+        bad, first, total = (int(v) for v in self._roi_flag_host)
+        if bad:
+            self._saved = None
+            raise RuntimeError("roi_pooling_reverse: the truncated ROI lengths of %d segment(s) do not tile L/4 = %d (first: segment "
+                               "%d, lengths sum to %d); the reference fails here with a torch.stack / torch.cat size mismatch "
+                               "(network/utils/roi_pooling_1d.py:96-98)" % (bad, L4, first, total))
+
     @staticmethod
     def _rank():
         import torch.distributed as dist
@@ -348,6 +388,7 @@ class Model_nefnet(nn.Module):
     def _run_backward(self, dout, dout_p, dout_l):
         import torch.distributed as dist
         lib = N.load()
+        self.check_rois()
         x, input_thetas, query_theta, rois, plan = self._saved
         device = x.device
         world = self._ddp_world()
@@ -458,6 +499,7 @@ class Model_nefnet(nn.Module):
         z2 = self._f32(z2, device)
         q = self._f32(query_theta, device)
         rois = rois.detach().to(device=device, dtype=torch.int64).contiguous()
+        self._roi_launch_check(rois, B, L, device)
         out = torch.empty((B, V, L), dtype=torch.float32, device=device)
         arr = self._param_ptr_array()
         N.check(lib.nef_gen_ecg(plan.handle, C.cast(arr, C.POINTER(C.c_void_p)), N.ptr(z1), N.ptr(z2), N.ptr(q),

@@ -261,6 +261,15 @@ int nef_gen_ecg(NefPlan* plan, const float* const* params, const float* z1, cons
                 nef_stream_t s);
 
 /* ---- Standin-Learning loss, losses.py:21-50 ------------------------------------------------- */
+/* ROI tiling check -- replaces the shape errors of roi_pooling_reverse (network/utils/roi_pooling_1d.py:83-98: per segment
+ * the 7 reversed ROIs of lengths long(r1 * .25) - long(r0 * .25) are concatenated and the segments stacked, so a segment whose
+ * lengths do not sum to L / 4, or with a negative length, makes torch.stack / torch.cat / F.interpolate raise).  The kernels
+ * themselves clamp; this check lets the host raise the reference's RuntimeError.  rois int64 (B, 7, 2); flag: 3 device ints
+ * written by one small launch -- [0] number of offending segments, [1] the first one (-1: none), [2] its length sum.  The
+ * caller copies them back when it chooses to synchronise (Model_nefnet: at its next entry point, or at once with
+ * roi_check = "sync").                                                                                               */
+int nef_roi_check(const int64_t* rois, int B, int L, int32_t* flag, nef_stream_t s);
+
 /* sums[0..2] = sum|out - out_p|, sum|out - out_l|, sum|out - target| (or squared for mse) ; doubles,
  * zeroed by the call.  losses[0..3] = total, l1*f0, l2*f1, l3*f2 as floats.                      */
 int nef_loss_fwd(const float* out, const float* out_p, const float* out_l, const float* target, int64_t n,
