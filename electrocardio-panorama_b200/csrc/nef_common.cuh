@@ -48,6 +48,7 @@ struct NefPackJob {
   long sg, sn, sk, st;
   int flags;        // bit 0: flip taps, bit 1: TF32 residual, bit 2: fp16 operand packing (8 channels per 16-byte slot)
   int first_block;  // filled by nef_pack_weights_batch
+  int gmod;         // 0: every group has its own source weights; m > 0: group g reads source group g mod m (shared weights)
   const float* nscale;  // optional [groups * N]: the weights of output channel (g, n) are multiplied by nscale[g * N + n]
                         //   before rounding (inference-time BatchNorm folding)
 };

@@ -179,13 +179,13 @@ __global__ void __launch_bounds__(256) wgrad_simt_kernel(const NefWgradDesc d, l
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const long m = cot * 64 + co4 * 4 + i, n = cit * 64 + ci4 * 4 + j;
-          atomicAdd(d.dw + g * d.sg + m * d.sm + n * d.sn + (tap_base + tt) * d.st, acc[tt][i][j]);
+          atomicAdd(d.dw + (long)(d.wg_mod > 0 ? g % d.wg_mod : g) * d.sg + m * d.sm + n * d.sn + (tap_base + tt) * d.st, acc[tt][i][j]);
         }
     }
   }
   if (d.db && cit == 0 && blockIdx.z == 0 && ci4 == 0) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) atomicAdd(d.db + (long)g * d.cout_g + cot * 64 + co4 * 4 + i, f4get(bacc, i));
+    for (int i = 0; i < 4; ++i) atomicAdd(d.db + (long)(d.wg_mod > 0 ? g % d.wg_mod : g) * d.cout_g + cot * 64 + co4 * 4 + i, f4get(bacc, i));
   }
 }
 
@@ -210,8 +210,8 @@ __global__ void __launch_bounds__(256) pack_weights_batch_kernel(const __grid_co
       const int g = (int)r;
       const int k = kb * 64 + c * 8;
       const int ts = (q.flags & 1) ? q.taps - 1 - t : t;
-      const float* sp = q.src + g * q.sg + n * q.sn + k * q.sk + ts * q.st;
-      const float sc = q.nscale ? q.nscale[g * q.N + n] : 1.0f;
+      const float* sp = q.src + (q.gmod > 0 ? g % q.gmod : g) * q.sg + n * q.sn + k * q.sk + ts * q.st;
+      const float sc = q.nscale ? q.nscale[(q.gmod > 0 ? g % q.gmod : g) * q.N + n] : 1.0f;
       uint32_t o[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -240,8 +240,8 @@ __global__ void __launch_bounds__(256) pack_weights_batch_kernel(const __grid_co
     const int g = (int)r;
     const int k = kb * 32 + c * 4;
     const int ts = (q.flags & 1) ? q.taps - 1 - t : t;
-    const float* sp = q.src + g * q.sg + n * q.sn + k * q.sk + ts * q.st;
-    const float sc = q.nscale ? q.nscale[g * q.N + n] : 1.0f;
+    const float* sp = q.src + (q.gmod > 0 ? g % q.gmod : g) * q.sg + n * q.sn + k * q.sk + ts * q.st;
+    const float sc = q.nscale ? q.nscale[(q.gmod > 0 ? g % q.gmod : g) * q.N + n] : 1.0f;
     float o[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -383,7 +383,7 @@ extern "C" int nef_pack_weights(const float* src, float* dst, int groups, int N,
   t.n = 1;
   NefPackJob& q = t.job[0];
   q.src = src; q.dst = dst; q.groups = groups; q.N = N; q.K = K; q.taps = taps;
-  q.sg = sg; q.sn = sn; q.sk = sk; q.st = st; q.flags = flags; q.first_block = 0; q.nscale = nullptr;
+  q.sg = sg; q.sn = sn; q.sk = sk; q.st = st; q.flags = flags; q.first_block = 0; q.nscale = nullptr; q.gmod = 0;
   return nef_pack_weights_batch(&t, (cudaStream_t)s);
 }
 

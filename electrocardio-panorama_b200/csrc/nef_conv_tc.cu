@@ -1044,6 +1044,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
       const int chalf = (warp - 2) >> 2;  // the two warps of a TMEM lane quarter take alternate 32-column groups
       mbar_wait(acc_full, 0);
       tc_fence_after();
+      const int gw = d.wg_mod > 0 ? g % d.wg_mod : g;   // shared weights: group g accumulates into slot g mod wg_mod
       for (int tp = 0; tp < ntap; ++tp) {
         for (int cg = chalf; cg < dcols / 32; cg += 2) {
           uint32_t v[32];
@@ -1051,12 +1052,12 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
           tmem_ld_wait();
           if (!swap) {
             if (lr < d.cout_g) {
-              float* dst = d.dw + (long)g * d.sg + (long)lr * d.sm + (long)(half * dcols + cg * 32) * d.sn + (long)tp * d.st;
+              float* dst = d.dw + (long)gw * d.sg + (long)lr * d.sm + (long)(half * dcols + cg * 32) * d.sn + (long)tp * d.st;
 #pragma unroll
               for (int i = 0; i < 32; ++i) atomicAdd(dst + (long)i * d.sn, __uint_as_float(v[i]));
             }
           } else {
-            float* dst = d.dw + (long)g * d.sg + (long)(cg * 32) * d.sm + (long)(nt * 128 + lr) * d.sn + (long)tp * d.st;
+            float* dst = d.dw + (long)gw * d.sg + (long)(cg * 32) * d.sm + (long)(nt * 128 + lr) * d.sn + (long)tp * d.st;
 #pragma unroll
             for (int i = 0; i < 32; ++i) atomicAdd(dst + (long)i * d.sm, __uint_as_float(v[i]));
           }
@@ -1087,7 +1088,7 @@ __global__ void __launch_bounds__(256) bias_grad_kernel(const NefWgradDesc d, lo
   if (threadIdx.x == 0) {
     float4 t = f4zero();
     for (int w = 0; w < 8; ++w) t = t + red[w];
-    float* o = d.db + (long)g * d.cout_g + c * 4;
+    float* o = d.db + (long)(d.wg_mod > 0 ? g % d.wg_mod : g) * d.cout_g + c * 4;
     atomicAdd(o + 0, t.x); atomicAdd(o + 1, t.y); atomicAdd(o + 2, t.z); atomicAdd(o + 3, t.w);
   }
 }

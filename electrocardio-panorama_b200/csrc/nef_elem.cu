@@ -29,7 +29,7 @@ __device__ __forceinline__ uint32_t f16x2_sat(float lo, float hi) {
 }
 
 __global__ void __launch_bounds__(256) stem_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, T4 y,
-                                                       uint32_t* __restrict__ amax, uint4* __restrict__ y16, int G, int L, int store32) {
+                                                       uint32_t* __restrict__ amax, uint4* __restrict__ y16, int G, int L, int store32, int w_shared) {
   __shared__ float xs[4 * STEM_TJ + 24];
   __shared__ float4 ws[15][32];
   const int tid = threadIdx.x;
@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(256) stem_fwd_kernel(const float* __restrict__
   }
   for (int i = tid; i < 15 * 32; i += 256) {
     int t = i / 32, c4 = i % 32;
-    const float* wp = w + ((long)g * 128 + c4 * 4) * 15 + t;
+    const float* wp = w + ((long)(w_shared ? 0 : g) * 128 + c4 * 4) * 15 + t;
     ws[t][c4] = make_float4(wp[0], wp[15], wp[30], wp[45]);
   }
   __syncthreads();
@@ -125,7 +125,7 @@ constexpr int STEMB_TJ = 256;
 // position costs its 15 taps once:  dW[c][t] += gA * x[4j-9+t] + gB * x[4j-7+t].
 // One warp per 32 consecutive j of one (segment, lead); lane = 4-channel chunk.
 __global__ void __launch_bounds__(256, 2) stem_bwd_kernel(const float* __restrict__ x, const uint32_t* __restrict__ amax,
-                                                          T4 dy, float* __restrict__ dw, int G, int L) {
+                                                          T4 dy, float* __restrict__ dw, int G, int L, int w_shared) {
   __shared__ __align__(16) float xs[4 * STEMB_TJ + 24];
   __shared__ float sdw[15][128];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -207,25 +207,25 @@ __global__ void __launch_bounds__(256, 2) stem_bwd_kernel(const float* __restric
   for (int i = tid; i < 15 * 128; i += 256) {
     const int t = i / 128, c = i % 128;
     const float v = sdw[t][c];
-    if (v != 0.f) atomicAdd(dw + ((long)g * 128 + c) * 15 + t, v);
+    if (v != 0.f) atomicAdd(dw + ((long)(w_shared ? 0 : g) * 128 + c) * 15 + t, v);
   }
 }
 
-int stem_fwd(const float* x, const float* w, T4 y, uint32_t* amax, void* y16, int G, cudaStream_t s, int store32) {
+int stem_fwd(const float* x, const float* w, T4 y, uint32_t* amax, void* y16, int G, cudaStream_t s, int store32, int w_shared) {
   const int L = y.L * 4;
   dim3 grid((y.L + STEM_TJ - 1) / STEM_TJ, G, y.B);
-  stem_fwd_kernel<<<grid, 256, 0, s>>>(x, w, y, amax, reinterpret_cast<uint4*>(y16), G, L, (store32 || !y16) ? 1 : 0);
+  stem_fwd_kernel<<<grid, 256, 0, s>>>(x, w, y, amax, reinterpret_cast<uint4*>(y16), G, L, (store32 || !y16) ? 1 : 0, w_shared);
   NEF_CHECK_LAUNCH("stem_fwd_kernel");
   return 0;
 }
-int stem_bwd(const float* x, const uint32_t* amax, T4 dy, float* dw, int G, cudaStream_t s) {
+int stem_bwd(const float* x, const uint32_t* amax, T4 dy, float* dw, int G, cudaStream_t s, int w_shared) {
   const int L = dy.L * 4;
   const int units = dy.B * ((dy.L + STEMB_TJ - 1) / STEMB_TJ);
   int gx = (2 * 148) / G;               // one wave of two resident blocks per SM over all leads
   if (gx < 1) gx = 1;
   if (gx > units) gx = units;
   dim3 grid(gx, G);
-  stem_bwd_kernel<<<grid, 256, 0, s>>>(x, amax, dy, dw, G, L);
+  stem_bwd_kernel<<<grid, 256, 0, s>>>(x, amax, dy, dw, G, L, w_shared);
   NEF_CHECK_LAUNCH("stem_bwd_kernel");
   return 0;
 }
@@ -700,8 +700,10 @@ __global__ void __launch_bounds__(256) latent_fwd_kernel(const LatentArgs a) {
       const bool use_pick = (k3 == 1 && half == 0) || (k3 == 2 && half == 1);
       const float4* src = use_pick ? pt[h2] : mt[h2];
       if (a.write_lat && ((a.store_mask >> (2 * k3 + half)) & 1)) {
-        for (int i = tid; i < 2 * nl; i += 256) *a.lat[k3].at(latc, b, t0 + (i >> 1)) = src[(i >> 1) + 1];
+        for (int i = tid; i < 2 * nl; i += 256)
+          *a.lat[k3].at(latc, b, t0 + (i >> 1)) = a.round_lat ? tf32_rn4(src[(i >> 1) + 1]) : src[(i >> 1) + 1];
       }
+      if (a.skip_u0) continue;   // Model_nefnet2: two more convolutions sit between the latents and the query scaling
       // 4 * nl is a multiple of 32 only if nl is a multiple of 8: the shuffles below need every lane of a warp, so the loop
       // runs whole warps and the stores are predicated
       for (int i0 = tid & ~31; i0 < 4 * nl; i0 += 256) {
@@ -764,7 +766,7 @@ __global__ void __launch_bounds__(256, 3) latent_bwd_kernel(const LatentBwdArgs 
   // read its sample -- no atomics, fixed summation order
   float accM[4] = {0.f, 0.f, 0.f, 0.f}, accP[4] = {0.f, 0.f, 0.f, 0.f};
   const int latc = half * 32 + cc;
-  const float4 qv = *reinterpret_cast<const float4*>(a.q + (long)b * a.q_stride + latc * 4);
+  const float4 qv = a.direct ? make_float4(1.f, 1.f, 1.f, 1.f) : *reinterpret_cast<const float4*>(a.q + (long)b * a.q_stride + latc * 4);
   const float invG = 1.0f / (float)a.G;
   float4 dq = f4zero();
   const int L2 = 2 * L4;
@@ -775,6 +777,10 @@ __global__ void __launch_bounds__(256, 3) latent_bwd_kernel(const LatentBwdArgs 
     float4 dk[3];
 #pragma unroll
     for (int k3 = 0; k3 < 3; ++k3) {
+      if (a.direct) {   // the latent gradients themselves are given (Model_nefnet2: upq_adjoint and two convolutions ran before)
+        dk[k3] = *a.dlat[k3].at(latc, b, l);
+        continue;
+      }
       const float4* du = a.du0[k3].at(latc, b, 0);
       float4 d = du[2 * l] * 0.75f + du[2 * l + 1] * 0.75f;
       if (l + 1 < L4) d = d + du[2 * l + 2] * 0.25f;
@@ -813,8 +819,10 @@ __global__ void __launch_bounds__(256, 3) latent_bwd_kernel(const LatentBwdArgs 
       dq = dq + (dk[0] + dk[2]) * (msum * invG) + dk[1] * pick;
     } else {
       // lat_0 = lat_1 = mean (this half), lat_2 = lead c2
-      const float4 lm = *a.lat[0].at(latc, b, l), lp = *a.lat[2].at(latc, b, l);
-      dq = dq + (dk[0] + dk[1]) * lm + dk[2] * lp;
+      if (!a.direct) {
+        const float4 lm = *a.lat[0].at(latc, b, l), lp = *a.lat[2].at(latc, b, l);
+        dq = dq + (dk[0] + dk[1]) * lm + dk[2] * lp;
+      }
       sdm[l - t0] = (dk[0] + dk[1]) * qv;
       sdp[l - t0] = dk[2] * qv;
     }
@@ -863,7 +871,7 @@ __global__ void __launch_bounds__(256, 3) latent_bwd_kernel(const LatentBwdArgs 
     if (lane == 0) atomicAdd(&dq_s[k], v);
   }
   __syncthreads();
-  if (tid < 4) a.dq[(long)b * 256 + latc * 4 + tid] = dq_s[tid];
+  if (tid < 4 && !a.direct) a.dq[(long)b * 256 + latc * 4 + tid] = dq_s[tid];
   if (half == 1) {
     // g z2o[(g*128 + 4cc + k)*7 + j][pos] = (Tm/G + [g == c2] Tp) * (z2o > 0)
     for (int i = tid; i < a.G * 7 * 32; i += 256) {
@@ -888,6 +896,56 @@ int latent_bwd(const LatentBwdArgs& a, cudaStream_t s) {
   dim3 grid(2, 32, a.z1.B);
   latent_bwd_kernel<<<grid, 256, smem, s>>>(a);
   NEF_CHECK_LAUNCH("latent_bwd_kernel");
+  return 0;
+}
+
+// Model_nefnet2 only: adjoint of (query scaling, x2 linear upsampling) alone.  d lat'_k = q * up^T(d u0_k) (TF32-rounded: the
+// operand of the single_conv_* data / weight gradients), d q = sum_k sum_l lat'_k * up^T(d u0_k).  One block per (segment,
+// 4-channel chunk of the 256 latent channels).
+__global__ void __launch_bounds__(256) upq_adjoint_kernel(const UpqAdjArgs a) {
+  __shared__ float dq_s[4];
+  const int latc = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
+  const int L4 = a.lat2[0].L, L2 = 2 * L4;
+  if (tid < 4) dq_s[tid] = 0.f;
+  __syncthreads();
+  const float4 qv = *reinterpret_cast<const float4*>(a.q + (long)b * a.q_stride + latc * 4);
+  float4 dq = f4zero();
+  for (int l = tid; l < L4; l += 256) {
+#pragma unroll
+    for (int k3 = 0; k3 < 3; ++k3) {
+      const float4* du = a.du0[k3].at(latc, b, 0);
+      float4 d = du[2 * l] * 0.75f + du[2 * l + 1] * 0.75f;
+      if (l + 1 < L4) d = d + du[2 * l + 2] * 0.25f;
+      if (l >= 1) d = d + du[2 * l - 1] * 0.25f;
+      if (l == 0) d = d + du[0] * 0.25f;
+      if (l == L4 - 1) d = d + du[L2 - 1] * 0.25f;
+      dq = dq + d * *a.lat2[k3].at(latc, b, l);
+      *a.dlat2[k3].at(latc, b, l) = tf32_rn4(d * qv);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float v = warp_sum(f4get(dq, k));
+    if (lane == 0) atomicAdd(&dq_s[k], v);
+  }
+  __syncthreads();
+  if (tid < 4) a.dq[(long)b * 256 + latc * 4 + tid] = dq_s[tid];
+}
+int upq_adjoint(const UpqAdjArgs& a, cudaStream_t s) {
+  dim3 grid(64, a.lat2[0].B);
+  upq_adjoint_kernel<<<grid, 256, 0, s>>>(a);
+  NEF_CHECK_LAUNCH("upq_adjoint_kernel");
+  return 0;
+}
+
+// dst[i] = src[i mod n]: a bias vector shared by the leads, laid out once per lead for the grouped epilogues
+__global__ void replicate_kernel(const float* __restrict__ src, float* __restrict__ dst, int n, int total) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < total) dst[i] = src[i % n];
+}
+int replicate_f32(const float* src, float* dst, int n, int total, cudaStream_t s) {
+  replicate_kernel<<<(total + 255) / 256, 256, 0, s>>>(src, dst, n, total);
+  NEF_CHECK_LAUNCH("replicate_kernel");
   return 0;
 }
 

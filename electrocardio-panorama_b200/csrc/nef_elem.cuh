@@ -26,8 +26,8 @@ struct BnLayer {          // one BatchNorm1d of the decoder for one decoder call
   double* s2;             // [C] backward: sum g * xhat
 };
 
-int stem_fwd(const float* x, const float* w, T4 y, uint32_t* amax, void* y16, int G, cudaStream_t s, int store32 = 1);  // y16: optional fp16 copy (store32 = 0: only that copy is written)
-int stem_bwd(const float* x, const uint32_t* amax, T4 dy, float* dw, int G, cudaStream_t s);
+int stem_fwd(const float* x, const float* w, T4 y, uint32_t* amax, void* y16, int G, cudaStream_t s, int store32 = 1, int w_shared = 0);  // y16: optional fp16 copy (store32 = 0: only that copy is written)
+int stem_bwd(const float* x, const uint32_t* amax, T4 dy, float* dw, int G, cudaStream_t s, int w_shared = 0);
 int angular_fwd(const float* theta, const float* w, const float* b, float* out, int n, int D, cudaStream_t s);
 int angular_bwd(const float* theta, const float* dout, float* dw, float* db, int n, int D, cudaStream_t s);
 
@@ -63,6 +63,8 @@ struct LatentArgs {
   void* u0loh[3];         //   the fp32 residual u0lo is not written (only the fp16 forward convolution reads a residual)
   int n_lat;              // 3 (train) or 1 (extra views: only lat[0] / u0[0])
   int write_lat;          // 0: lat already built, only (re)build u0 from it with another q
+  int skip_u0;            // 1: only build the latents (Model_nefnet2 convolves them before the query scaling)
+  int round_lat;          // 1: the stored latents are TF32-rounded (they feed a tensor-core convolution)
   int store_mask;         // with write_lat: bit (2 k + half) = store half (0: z1 channels, 1: z2 channels) of lat[k].
                           //   training needs only the z2 halves of lat[0] and lat[2] (latent_bwd rebuilds the rest from z1);
                           //   the extra views of the test phase / gen_ecg re-read both halves of lat[0]
@@ -76,8 +78,13 @@ struct LatentBwdArgs {
   const float* s16;
   T4 gz2o;                // out: grad wrt pre-ReLU z2o (896G, 32)
   float* dq;              // out (B, 256), overwritten
+  int direct;             // 1: dlat[k] ARE the latent gradients (no upsample / query adjoint, dq untouched); 0: from du0
+  T4 dlat[3];
 };
 int latent_bwd(const LatentBwdArgs& a, cudaStream_t s);
+struct UpqAdjArgs { T4 du0[3]; T4 lat2[3]; T4 dlat2[3]; const float* q; int q_stride; float* dq; };
+int upq_adjoint(const UpqAdjArgs& a, cudaStream_t s);   // Model_nefnet2: d(q * lat') and dq from the decoder input gradients
+int replicate_f32(const float* src, float* dst, int n, int total, cudaStream_t s);   // dst[i] = src[i mod n]
 
 int bn_finalize(const BnLayer& bn, int C, double count, const float* gamma, const float* beta, float* rmean,
                 float* rvar, int64_t* nbt, int training, cudaStream_t s);

@@ -130,11 +130,15 @@ enum ParamIdx {
   P_DEC1 = 35,    // + {0 c0.w,1 c0.b,2 bn1.w,3 bn1.b,4 rm,5 rv,6 nbt,7 c3.w,8 c3.b,9 bn4.w,10 bn4.b,11 rm,12 rv,13 nbt}
   P_DEC3 = 49,
   P_OUT_W = 63, P_OUT_B = 64,
-  P_COUNT = 65
+  P_COUNT = 65,
+  // Model_nefnet2 (variant 2): the G = 1 table above plus its two plain k3 convolutions (model_nefnet2.py:102-107)
+  P_S1_W = 65, P_S1_B = 66, P_S2_W = 67, P_S2_B = 68,
+  P_COUNT2 = 69
 };
 
 struct ParamInfo { std::string name; int64_t numel; };
-static std::vector<ParamInfo> param_table(int G) {
+static std::vector<ParamInfo> param_table(int G, int variant = 1) {
+  if (variant == 2) G = 1;   // one single-lead trunk shared by all leads
   std::vector<ParamInfo> t;
   auto add = [&](const std::string& n, int64_t e) { t.push_back({n, e}); };
   add("W_encoder.conv1.weight", 128LL * G * 15);
@@ -170,6 +174,10 @@ static std::vector<ParamInfo> param_table(int G) {
     add(p + "4.running_mean", cout[s]); add(p + "4.running_var", cout[s]); add(p + "4.num_batches_tracked", 1);
   }
   add("decoder.4.weight", 64 * 3); add("decoder.4.bias", 1);
+  if (variant == 2) {
+    add("single_conv_z1.0.weight", 128 * 128 * 3); add("single_conv_z1.0.bias", 128);
+    add("single_conv_z2.0.weight", 128 * 128 * 3); add("single_conv_z2.0.bias", 128);
+  }
   return t;
 }
 static thread_local std::string g_name_tmp;
@@ -185,6 +193,19 @@ extern "C" int64_t nef_param_numel(int G, int i) {
   if (i < 0 || i >= (int)t.size()) return -1;
   return t[i].numel;
 }
+// the same for a model variant (1 = Model_nefnet, 2 = Model_nefnet2: the order of the `params` / `grads` arrays)
+extern "C" int nef_param_count_v(int G, int variant) { return (int)param_table(G, variant).size(); }
+extern "C" const char* nef_param_name_v(int G, int variant, int i) {
+  auto t = param_table(G, variant);
+  if (i < 0 || i >= (int)t.size()) return "";
+  g_name_tmp = t[i].name;
+  return g_name_tmp.c_str();
+}
+extern "C" int64_t nef_param_numel_v(int G, int variant, int i) {
+  auto t = param_table(G, variant);
+  if (i < 0 || i >= (int)t.size()) return -1;
+  return t[i].numel;
+}
 
 // ---------------------------------------------------------------------------------------------
 // plan
@@ -196,6 +217,7 @@ struct ConvW {            // one convolution's weights: reference tensor + packe
   float* pk_d;            // data-gradient packing (flipped taps, transposed); N = min(cin_g, 128)
   void* pk_h;             // forward packing in fp16 (encoder convolutions only), or nullptr
   void* pk_dh;            // data-gradient packing in fp16 (layers of the fp16 backward), or nullptr
+  int src_gmod;           // 0: one weight tensor slice per group; m > 0: group g uses (and accumulates into) slice g mod m
 };
 
 struct DecBufs {          // one decoder call
@@ -206,6 +228,7 @@ struct DecBufs {          // one decoder call
 
 struct NefPlan {
   int B, G, L, V, L2, L4, C1;
+  int variant;            // 1 = Model_nefnet, 2 = Model_nefnet2 (the trunk weights are shared by the G leads; two more convolutions)
   Window win;
   size_t ws_bytes;
   char* base;
@@ -239,6 +262,11 @@ struct NefPlan {
   size_t bn_stats_count;
   // weights
   ConvW enc[6], wc[2], z1c[3], z2c1[3], z2a[2], z2b[3], decw[4];
+  // variant 2: single_conv_z1 / single_conv_z2 (applied to the lead means and the picked leads: they are linear, so
+  // conv(mean_i z_i) = mean_i conv(z_i)), convolved latents and their gradients, per-lead copies of the shared biases
+  ConvW s12[2];
+  T4 lat2[3], dlat2[3], dlat[3];
+  float* rb[4];
   float *ct_f[2], *ct_d[2];
   float* dec1_lo;         // TF32 residual of the decoder first conv weights, forward packing
   float *fold_scale[4], *fold_bias[4];  // inference: BatchNorm folded into the decoder convolutions (per output channel)
@@ -272,8 +300,8 @@ struct Carver {
   float* f32(size_t n) { return reinterpret_cast<float*>(take(n * sizeof(float))); }
 };
 
-static void carve_convw(Carver& c, ConvW& w, int pidx, int groups, int cout_g, int cin_g, int taps) {
-  w.pidx = pidx; w.groups = groups; w.cout_g = cout_g; w.cin_g = cin_g; w.taps = taps;
+static void carve_convw(Carver& c, ConvW& w, int pidx, int groups, int cout_g, int cin_g, int taps, int src_gmod = 0) {
+  w.pidx = pidx; w.groups = groups; w.cout_g = cout_g; w.cin_g = cin_g; w.taps = taps; w.src_gmod = src_gmod;
   const size_t n = (size_t)groups * cout_g * cin_g * taps;
   w.pk_f = c.f32(n);
   w.pk_d = c.f32(n);
@@ -285,6 +313,7 @@ static void carve(NefPlan* p, bool dry) {
   Carver c{p, dry, 0};
   c.take(NEF_GUARD_ROWS * sizeof(float4));  // front guard
   const int G = p->G, C1 = p->C1, L4 = p->L4, L2 = p->L2, L = p->L, B = p->B;
+  const int m1 = p->variant == 2 ? 1 : 0, m7 = p->variant == 2 ? 7 : 0;   // shared weights: source slice = group mod m
   p->s0 = c.t4(C1, L4);
   p->s0_amax = reinterpret_cast<uint32_t*>(c.take(((size_t)(C1 / 4) * p->s0.cs + NEF_GUARD_ROWS) * sizeof(uint32_t)));
   for (int i = 0; i < 3; ++i) { p->eh[i] = c.t4(C1, L4); p->ey[i] = c.t4(C1, L4); }
@@ -353,27 +382,27 @@ static void carve(NefPlan* p, bool dry) {
   for (int k = 0; k < 3; ++k) p->du0[k] = c.t4(256, L2);
   // weights
   for (int i = 0; i < 6; ++i) {
-    carve_convw(c, p->enc[i], P_ENC + i, G, 128, 128, 7);
+    carve_convw(c, p->enc[i], P_ENC + i, G, 128, 128, 7, m1);
     p->enc[i].pk_h = c.take((size_t)G * 128 * 128 * 7 * 2);
     p->enc[i].pk_dh = c.take((size_t)G * 128 * 128 * 7 * 2);
   }
-  carve_convw(c, p->wc[0], P_WCONV + 0, G, 128, 128, 3);
-  carve_convw(c, p->wc[1], P_WCONV + 1, G, 128, 128, 3);
-  carve_convw(c, p->z1c[0], P_Z1 + 0, G, 128, 64, 3);
-  carve_convw(c, p->z1c[1], P_Z1 + 1, G, 128, 128, 3);
-  carve_convw(c, p->z1c[2], P_Z1 + 2, G, 128, 64, 1);
+  carve_convw(c, p->wc[0], P_WCONV + 0, G, 128, 128, 3, m1);
+  carve_convw(c, p->wc[1], P_WCONV + 1, G, 128, 128, 3, m1);
+  carve_convw(c, p->z1c[0], P_Z1 + 0, G, 128, 64, 3, m1);
+  carve_convw(c, p->z1c[1], P_Z1 + 1, G, 128, 128, 3, m1);
+  carve_convw(c, p->z1c[2], P_Z1 + 2, G, 128, 64, 1, m1);
   for (ConvW* w : {&p->wc[0], &p->wc[1], &p->z1c[0], &p->z1c[1], &p->z1c[2]}) {
     w->pk_h = c.take((size_t)w->groups * w->cout_g * w->cin_g * w->taps * 2);
     w->pk_dh = c.take((size_t)w->groups * w->cout_g * w->cin_g * w->taps * 2);
   }
-  carve_convw(c, p->z2c1[0], P_Z2C1 + 0, G, 128, 64, 3);
-  carve_convw(c, p->z2c1[1], P_Z2C1 + 1, G, 128, 128, 3);
-  carve_convw(c, p->z2c1[2], P_Z2C1 + 2, G, 128, 64, 1);
-  carve_convw(c, p->z2a[0], P_Z2A + 0, 7 * G, 128, 128, 3);
-  carve_convw(c, p->z2a[1], P_Z2A + 1, 7 * G, 128, 128, 3);
-  carve_convw(c, p->z2b[0], P_Z2B + 0, 7 * G, 128, 64, 3);
-  carve_convw(c, p->z2b[1], P_Z2B + 1, 7 * G, 128, 128, 3);
-  carve_convw(c, p->z2b[2], P_Z2B + 2, 7 * G, 128, 64, 1);
+  carve_convw(c, p->z2c1[0], P_Z2C1 + 0, G, 128, 64, 3, m1);
+  carve_convw(c, p->z2c1[1], P_Z2C1 + 1, G, 128, 128, 3, m1);
+  carve_convw(c, p->z2c1[2], P_Z2C1 + 2, G, 128, 64, 1, m1);
+  carve_convw(c, p->z2a[0], P_Z2A + 0, 7 * G, 128, 128, 3, m7);
+  carve_convw(c, p->z2a[1], P_Z2A + 1, 7 * G, 128, 128, 3, m7);
+  carve_convw(c, p->z2b[0], P_Z2B + 0, 7 * G, 128, 64, 3, m7);
+  carve_convw(c, p->z2b[1], P_Z2B + 1, 7 * G, 128, 128, 3, m7);
+  carve_convw(c, p->z2b[2], P_Z2B + 2, 7 * G, 128, 64, 1, m7);
   carve_convw(c, p->decw[0], P_DEC1 + 0, 1, 128, 256, 3);
   p->decw[0].pk_h = c.take((size_t)128 * 256 * 3 * 2);
   p->dec1_lo_h = c.take((size_t)128 * 256 * 3 * 2);
@@ -387,21 +416,31 @@ static void carve(NefPlan* p, bool dry) {
     p->ct_f[t] = c.f32((size_t)7 * G * 128 * 64);
     p->ct_d[t] = c.f32((size_t)7 * G * 128 * 64);
   }
+  if (p->variant == 2) {
+    carve_convw(c, p->s12[0], P_S1_W, 1, 128, 128, 3);
+    carve_convw(c, p->s12[1], P_S2_W, 1, 128, 128, 3);
+    for (int k = 0; k < 3; ++k) { p->lat2[k] = c.t4(256, L4); p->dlat2[k] = c.t4(256, L4); p->dlat[k] = c.t4(256, L4); }
+    const int nb[4] = {128 * G, 128 * G, 896 * G, 448 * G};
+    for (int i = 0; i < 4; ++i) p->rb[i] = c.f32(nb[i]);
+  }
   c.take(NEF_GUARD_ROWS * sizeof(float4));
   p->ws_bytes = align_up(c.cur, 256);
 }
 
-extern "C" int nef_plan_create(int B, int G, int L, int V, NefPlan** out) {
+extern "C" int nef_plan_create_v(int B, int G, int L, int V, int variant, NefPlan** out) {
   NEF_REQUIRE(B >= 1 && G >= 1 && L >= 16 && L % 4 == 0, "nef_plan_create: need B>=1, G>=1, L>=16, L %% 4 == 0 (B=%d G=%d L=%d)",
               B, G, L);
+  NEF_REQUIRE(variant == 1 || variant == 2, "nef_plan_create_v: variant must be 1 (Model_nefnet) or 2 (Model_nefnet2)");
   NefPlan* p = new NefPlan();
   memset(p, 0, sizeof(NefPlan));
+  p->variant = variant;
   p->B = B; p->G = G; p->L = L; p->V = V; p->L2 = L / 2; p->L4 = L / 4; p->C1 = 128 * G;
   p->win = centre_window(p->L4);
   carve(p, true);
   *out = p;
   return 0;
 }
+extern "C" int nef_plan_create(int B, int G, int L, int V, NefPlan** out) { return nef_plan_create_v(B, G, L, V, 1, out); }
 extern "C" void nef_plan_destroy(NefPlan* p) { delete p; }
 extern "C" size_t nef_plan_workspace_bytes(const NefPlan* p) { return p->ws_bytes; }
 extern "C" int nef_plan_bind(NefPlan* p, void* ws, size_t bytes, nef_stream_t s) {
@@ -478,21 +517,21 @@ struct CD {
 
 static int wgrad(const T4& dy, int dy_off, int dy_gs, int cout_g, const T4& x, int x_off, int x_gs, int cin_g,
                  int groups, int taps, float* dw, int64_t sg, int64_t sm, int64_t sn, int64_t st, float* db,
-                 cudaStream_t s) {
+                 cudaStream_t s, int wg_mod = 0) {
   if (!dw) return 0;
   NefWgradDesc d;
   memset(&d, 0, sizeof(d));
   d.dy = reinterpret_cast<const float*>(dy.p); d.dy_cstride = dy.cs; d.dy_c4_off = dy_off; d.dy_c4_gstride = dy_gs;
   d.x = reinterpret_cast<const float*>(x.p); d.x_cstride = x.cs; d.x_c4_off = x_off; d.x_c4_gstride = x_gs;
   d.cout_g = cout_g; d.cin_g = cin_g; d.groups = groups; d.taps = taps; d.tap_off = -(taps / 2);
-  d.rows = dy.cs; d.dw = dw; d.sg = sg; d.sm = sm; d.sn = sn; d.st = st; d.db = db;
+  d.rows = dy.cs; d.dw = dw; d.sg = sg; d.sm = sm; d.sn = sn; d.st = st; d.db = db; d.wg_mod = wg_mod;
   return nef_gconv_wgrad(&d, (nef_stream_t)s);
 }
 // standard Conv1d weight (groups*cout_g, cin_g, taps)
 static int wgrad_std(const T4& dy, int dy_off, int dy_gs, const T4& x, int x_off, int x_gs, const ConvW& w, float* dw,
                      float* db, cudaStream_t s) {
   return wgrad(dy, dy_off, dy_gs, w.cout_g, x, x_off, x_gs, w.cin_g, w.groups, w.taps, dw,
-               (int64_t)w.cout_g * w.cin_g * w.taps, (int64_t)w.cin_g * w.taps, w.taps, 1, db, s);
+               (int64_t)w.cout_g * w.cin_g * w.taps, (int64_t)w.cin_g * w.taps, w.taps, 1, db, s, w.src_gmod);
 }
 
 #define RUN(x)            \
@@ -503,32 +542,33 @@ static int wgrad_std(const T4& dy, int dy_off, int dy_gs, const T4& x, int x_off
 
 // packing jobs are queued in a table and launched together (nef_pack_weights_batch)
 static int queue_pack(NefPackTable& t, const float* src, float* dst, int groups, int N, int K, int taps, int64_t sg, int64_t sn,
-                      int64_t sk, int64_t st, int flags, cudaStream_t s, const float* nscale = nullptr) {
+                      int64_t sk, int64_t st, int flags, cudaStream_t s, const float* nscale = nullptr, int gmod = 0) {
   if (t.n == NEF_PACK_MAX) RUN(nef_pack_weights_batch(&t, s));
   NefPackJob& q = t.job[t.n++];
+  q.gmod = gmod;
   q.src = src; q.dst = dst; q.groups = groups; q.N = N; q.K = K; q.taps = taps;
   q.sg = sg; q.sn = sn; q.sk = sk; q.st = st; q.flags = flags; q.first_block = 0; q.nscale = nscale;
   return 0;
 }
 static int pack_fwd(NefPackTable& t, const ConvW& w, const float* const* P, cudaStream_t s, const float* nscale = nullptr) {
   return queue_pack(t, P[w.pidx], w.pk_f, w.groups, w.cout_g, w.cin_g, w.taps, (int64_t)w.cout_g * w.cin_g * w.taps,
-                    (int64_t)w.cin_g * w.taps, w.taps, 1, 0, s, nscale);
+                    (int64_t)w.cin_g * w.taps, w.taps, 1, 0, s, nscale, w.src_gmod);
 }
 // dgrad: N' = cin_g (split into sub-groups of 128 when larger; only for groups == 1), K' = cout_g, flipped taps
 static int pack_dgrad(NefPackTable& t, const ConvW& w, const float* const* P, cudaStream_t s) {
   if (w.cin_g > 128) {
     const int sub = w.cin_g / 128;
     return queue_pack(t, P[w.pidx], w.pk_d, sub, 128, w.cout_g, w.taps, (int64_t)128 * w.taps, w.taps,
-                      (int64_t)w.cin_g * w.taps, 1, 1, s);
+                      (int64_t)w.cin_g * w.taps, 1, 1, s);   // (decoder only: one group)
   }
   return queue_pack(t, P[w.pidx], w.pk_d, w.groups, w.cin_g, w.cout_g, w.taps, (int64_t)w.cout_g * w.cin_g * w.taps,
-                    w.taps, (int64_t)w.cin_g * w.taps, 1, 1, s);
+                    w.taps, (int64_t)w.cin_g * w.taps, 1, 1, s, nullptr, w.src_gmod);
 }
 
 // the same in fp16 (layers of the fp16 backward; cin_g <= 128 there)
 static int pack_dgrad_h(NefPackTable& t, const ConvW& w, const float* const* P, cudaStream_t s) {
   return queue_pack(t, P[w.pidx], reinterpret_cast<float*>(w.pk_dh), w.groups, w.cin_g, w.cout_g, w.taps,
-                    (int64_t)w.cout_g * w.cin_g * w.taps, w.taps, (int64_t)w.cin_g * w.taps, 1, 1 | 4, s);
+                    (int64_t)w.cout_g * w.cin_g * w.taps, w.taps, (int64_t)w.cin_g * w.taps, 1, 1 | 4, s, nullptr, w.src_gmod);
 }
 
 static int pack_dec1_lo(NefPackTable& t, NefPlan* p, const float* const* P, cudaStream_t s, const float* nscale = nullptr) {
@@ -572,6 +612,8 @@ static int for_all_convw(NefPlan* p, F f) {
   for (int i = 0; i < 2; ++i) RUN(f(p->z2a[i]));
   for (int i = 0; i < 3; ++i) RUN(f(p->z2b[i]));
   for (int i = 0; i < 4; ++i) RUN(f(p->decw[i]));
+  if (p->variant == 2)
+    for (int i = 0; i < 2; ++i) RUN(f(p->s12[i]));
   return 0;
 }
 
@@ -693,7 +735,8 @@ static int latents_to_decoders(NefPlan* p, const float* const* P, const float* q
                                const int64_t* rois, int phase, int training, int V, float* out, float* out_p,
                                float* out_l, float* rest_out, bool only_views, cudaStream_t s) {
   const int B = p->B;
-  LatentArgs la;
+  const bool v2 = p->variant == 2;
+  LatentArgs la = {};
   la.z1 = p->z1; la.z2o = p->z2o; la.rois = rois; la.G = p->G; la.c1 = p->c1; la.c2 = p->c2;
   for (int k = 0; k < 3; ++k) {
     la.lat[k] = p->lat[k]; la.u0[k] = p->u0[k]; la.u0lo[k] = p->u0lo[k];
@@ -704,7 +747,26 @@ static int latents_to_decoders(NefPlan* p, const float* const* P, const float* q
     RUN(angular_fwd(query_theta, P[P_MLP2_W], P[P_MLP2_B], p->q, B, 256, s));
     la.q = p->q; la.q_stride = 256; la.n_lat = 3; la.write_lat = 1;
     la.store_mask = phase == NEF_PHASE_TEST ? 3 : (2 | 32);
+    if (v2) { la.store_mask = 63; la.skip_u0 = 1; la.round_lat = 1; }   // every half of every latent feeds a convolution
     RUN(latent_fwd(la, s));
+    if (v2) {
+      // single_conv_z1 / single_conv_z2 (model_nefnet2.py:140,148) on the z1 / z2 halves of the three latents -- applied
+      // after the lead mean / pick instead of before (the convolutions are linear) -- then the query scaling + upsampling
+      for (int k = 0; k < 3; ++k)
+        for (int h = 0; h < 2; ++h) {
+          CD c(1, 128, p->lat[k]);
+          c.term(p->lat[k], 32 * h, 0, 128, 3, p->s12[h].pk_f).out(p->lat2[k], 32 * h, 0).bias(P[h ? P_S2_B : P_S1_B]);
+          RUN(c.run(s));
+        }
+      LatentArgs lu = la;
+      lu.write_lat = 0; lu.skip_u0 = 0; lu.n_lat = 1;
+      for (int k = 0; k < 3; ++k) {
+        lu.lat[0] = p->lat2[k]; lu.u0[0] = p->u0[k]; lu.u0lo[0] = p->u0lo[k]; lu.u0h[0] = la.u0h[k]; lu.u0loh[0] = la.u0loh[k];
+        RUN(latent_fwd(lu, s));
+      }
+      la.lat[0] = p->lat2[0];   // the extra views below re-read the convolved mean latent
+      la.skip_u0 = 0;
+    }
     float* outs[3] = {out, out_p, out_l};
     for (int k = 0; k < 3; ++k) RUN(decoder_fwd(p, P, k, k, p->u0[k], p->u0lo[k], training, outs[k], p->L, s));
   } else {
@@ -730,6 +792,7 @@ extern "C" int nef_forward(NefPlan* p, const NefForwardArgs* a, nef_stream_t sv)
   NEF_REQUIRE(p && p->bound, "nef_forward: plan not bound to a workspace");
   const float* const* P = a->params;
   const int G = p->G, B = p->B;
+  const bool v2 = p->variant == 2;
   NEF_REQUIRE(a->lead_choice_z1 >= 0 && a->lead_choice_z1 < G && a->lead_choice_z2 >= 0 && a->lead_choice_z2 < G,
               "nef_forward: lead choice out of range");
   p->have_fwd = false;
@@ -740,6 +803,18 @@ extern "C" int nef_forward(NefPlan* p, const NefForwardArgs* a, nef_stream_t sv)
   packs.n = 0;
   p->fwd_f16 = g_fwd_f16 && g_conv_impl == 1;
   p->bwd_f16 = p->fwd_f16 && g_bwd_f16 && a->save_for_backward;
+  // variant 2: the biases its grouped epilogues index per group are shared by the leads -> one copy per lead
+  const float* b_z1 = P[P_Z1 + 3];
+  const float* b_z2c1 = P[P_Z2C1 + 3];
+  const float* b_z2b = P[P_Z2B + 3];
+  const float* b_ct = P[P_CT_B];
+  if (v2) {
+    RUN(replicate_f32(P[P_Z1 + 3], p->rb[0], 128, 128 * G, s));
+    RUN(replicate_f32(P[P_Z2C1 + 3], p->rb[1], 128, 128 * G, s));
+    RUN(replicate_f32(P[P_Z2B + 3], p->rb[2], 896, 896 * G, s));
+    RUN(replicate_f32(P[P_CT_B], p->rb[3], 448, 448 * G, s));
+    b_z1 = p->rb[0]; b_z2c1 = p->rb[1]; b_z2b = p->rb[2]; b_ct = p->rb[3];
+  }
   // the fp32 hidden activations of the big blocks have a reader only in the TF32 backward (its weight gradients)
   p->h_f16_only = p->fwd_f16 && (p->bwd_f16 || !a->save_for_backward) && !g_keep_h32;
   RUN(for_all_convw(p, [&](const ConvW& w) {
@@ -747,16 +822,16 @@ extern "C" int nef_forward(NefPlan* p, const NefForwardArgs* a, nef_stream_t sv)
     const bool k3 = (&w >= p->wc && &w < p->wc + 2) || (&w >= p->z1c && &w < p->z1c + 3);
     if (p->fwd_f16 && w.pk_h && !(k3 && g_k3_tf32))
       return queue_pack(packs, P[w.pidx], reinterpret_cast<float*>(w.pk_h), w.groups, w.cout_g, w.cin_g, w.taps,
-                        (int64_t)w.cout_g * w.cin_g * w.taps, (int64_t)w.cin_g * w.taps, w.taps, 1, 4, s);
+                        (int64_t)w.cout_g * w.cin_g * w.taps, (int64_t)w.cin_g * w.taps, w.taps, 1, 4, s, nullptr, w.src_gmod);
     return pack_fwd(packs, w, P, s);
   }));
   RUN(queue_decoder_packs(p, packs, P, !a->bn_training && !a->save_for_backward, s));
   for (int t = 0; t < 2; ++t)  // ConvTranspose1d weight (Cin_total, Cout/groups, 2): one 1x1 conv per tap
-    RUN(queue_pack(packs, P[P_CT_W] + t, p->ct_f[t], 7 * G, 64, 128, 1, 128LL * 64 * 2, 2, 64 * 2, 0, 0, s));
+    RUN(queue_pack(packs, P[P_CT_W] + t, p->ct_f[t], 7 * G, 64, 128, 1, 128LL * 64 * 2, 2, 64 * 2, 0, 0, s, nullptr, v2 ? 7 : 0));
   RUN(nef_pack_weights_batch(&packs, s));
 
   RUN(stem_fwd(a->x, P[P_STEM], p->s0, a->save_for_backward ? p->s0_amax : nullptr, p->fwd_f16 ? p->s0_h : nullptr, G, s,
-               p->h_f16_only ? 0 : 1));   // fp16 dataflow: the first block reads only the fp16 copy
+               p->h_f16_only ? 0 : 1, v2 ? 1 : 0));   // fp16 dataflow: the first block reads only the fp16 copy
   RUN(angular_fwd(a->input_thetas, P[P_MLP1_W], P[P_MLP1_B], p->s_in, B * G, 128, s));
   const float dp = a->drop_p;
   const uint64_t seed = a->drop_seed * 16;
@@ -782,7 +857,7 @@ extern "C" int nef_forward(NefPlan* p, const NefForwardArgs* a, nef_stream_t sv)
     RUN(block_fwd(io, dp, seed + 3, nullptr, s));
   }
   {
-    BlockIO io{p->w, 0, 32, p->h1, p->z1, &p->z1c[0], &p->z1c[1], &p->z1c[2], P[P_Z1 + 3], G};
+    BlockIO io{p->w, 0, 32, p->h1, p->z1, &p->z1c[0], &p->z1c[1], &p->z1c[2], b_z1, G};
     if (a->save_for_backward) io.hbits = p->b_h1;
     if (p->fwd_f16 && !g_k3_tf32) { io.x16 = p->w_h; io.h16 = p->h1_h; io.h_f16_only = p->h_f16_only; }
     else if (p->bwd_f16) io.h16 = p->h1_h;
@@ -790,7 +865,7 @@ extern "C" int nef_forward(NefPlan* p, const NefForwardArgs* a, nef_stream_t sv)
   }
   RUN(window_extract(p->w, p->xw, G, p->win, (p->fwd_f16 && !g_k3_tf32 && p->h_f16_only) ? p->w_h : nullptr, s));
   {
-    BlockIO io{p->xw, 0, 16, p->hz, p->z2c, &p->z2c1[0], &p->z2c1[1], &p->z2c1[2], P[P_Z2C1 + 3], G};
+    BlockIO io{p->xw, 0, 16, p->hz, p->z2c, &p->z2c1[0], &p->z2c1[1], &p->z2c1[2], b_z2c1, G};
     RUN(block_fwd(io, dp, seed + 5, nullptr, s));
   }
   RUN(roi_align_fwd(p->z2c, a->rois, p->ra, p->win, p->L4, s));
@@ -800,14 +875,15 @@ extern "C" int nef_forward(NefPlan* p, const NefForwardArgs* a, nef_stream_t sv)
   }
   for (int t = 0; t < 2; ++t) {  // ConvTranspose1d(k2, s2): out[2l + t] = W_t x[l] + b
     CD c(7 * G, 64, p->y20);
-    c.term(p->y20, 0, 32, 128, 1, p->ct_f[t]).out(p->t21, 0, 16, 2, t).bias(P[P_CT_B]).round();
+    c.term(p->y20, 0, 32, 128, 1, p->ct_f[t]).out(p->t21, 0, 16, 2, t).bias(b_ct).round();
     c.d.term[0].tap_off = 0;
     RUN(c.run(s));
   }
   {
-    BlockIO io{p->t21, 0, 16, p->h22, p->z2o, &p->z2b[0], &p->z2b[1], &p->z2b[2], P[P_Z2B + 3], 7 * G};
+    BlockIO io{p->t21, 0, 16, p->h22, p->z2o, &p->z2b[0], &p->z2b[1], &p->z2b[2], b_z2b, 7 * G};
     RUN(block_fwd(io, dp, seed + 7, nullptr, s));
   }
+  NEF_REQUIRE(!(v2 && a->phase == NEF_PHASE_GEN), "nef_forward: phase 'gen' is not built for Model_nefnet2 (its gen_ecg cannot consume it)");
   if (a->phase == NEF_PHASE_GEN) {
     RUN(nef_cbl4_to_ncl(reinterpret_cast<const float*>(p->z1.p), a->out, B, p->C1, p->L4, sv));
     RUN(nef_cbl4_to_ncl(reinterpret_cast<const float*>(p->z2o.p), a->out_p, B, 896 * G, 32, sv));
@@ -824,6 +900,7 @@ extern "C" int nef_gen_ecg(NefPlan* p, const float* const* P, const float* z1, c
   cudaStream_t s = (cudaStream_t)sv;
   NEF_REQUIRE(p && p->bound, "nef_gen_ecg: plan not bound to a workspace");
   NEF_REQUIRE(V >= 1 && V <= p->V, "nef_gen_ecg: V=%d not in [1, plan V=%d]", V, p->V);
+  NEF_REQUIRE(p->variant == 1, "nef_gen_ecg: not built for Model_nefnet2 (the reference's gen_ecg cannot consume its own phase 'gen' output)");
   p->have_fwd = false;
   p->c1 = 0; p->c2 = 0;
   NefPackTable packs;
@@ -863,6 +940,7 @@ static int wgrad_h(const void* dy16, const T4& dy, int dy_off, int dy_gs, const 
   d.cout_g = w.cout_g; d.cin_g = w.cin_g; d.groups = w.groups; d.taps = w.taps; d.tap_off = -(w.taps / 2);
   d.rows = dy.cs; d.dw = dw;
   d.sg = (int64_t)w.cout_g * w.cin_g * w.taps; d.sm = (int64_t)w.cin_g * w.taps; d.sn = w.taps; d.st = 1;
+  d.wg_mod = w.src_gmod;
   return nef_gconv_wgrad_f16(&d, dy16, x16, inv_scale, (nef_stream_t)s);
 }
 extern "C" int nef_bias_grad_tc(const NefWgradDesc* d, nef_stream_t s);
@@ -880,7 +958,7 @@ static int block_bwd(const BlockBwd& b, float drop_p, CD& fin, cudaStream_t s) {
         NefWgradDesc d;
         memset(&d, 0, sizeof(d));
         d.dy = reinterpret_cast<const float*>(b.gy.p); d.dy_cstride = b.gy.cs; d.dy_c4_off = 0; d.dy_c4_gstride = 32;
-        d.cout_g = io.cr->cout_g; d.groups = io.cr->groups; d.rows = b.gy.cs; d.db = b.dbr;
+        d.cout_g = io.cr->cout_g; d.groups = io.cr->groups; d.rows = b.gy.cs; d.db = b.dbr; d.wg_mod = io.cr->src_gmod;
         RUN(nef_bias_grad_tc(&d, (nef_stream_t)s));
       }
     }
@@ -974,6 +1052,7 @@ extern "C" int nef_backward(NefPlan* p, const NefBackwardArgs* a, nef_stream_t s
   const float* const* P = a->params;
   float* const* Gd = a->grads;
   const int G = p->G, B = p->B;
+  const bool v2 = p->variant == 2;
   const float dp = p->drop_p;
   p->have_fwd = false;
 
@@ -985,7 +1064,7 @@ extern "C" int nef_backward(NefPlan* p, const NefBackwardArgs* a, nef_stream_t s
     return pack_dgrad(packs, w, P, s);
   }));
   for (int t = 0; t < 2; ++t)  // ConvTranspose dgrad: dx[l] = sum_t W_t^T dy[2l + t] ; N' = ci (128), K' = co (64)
-    RUN(queue_pack(packs, P[P_CT_W] + t, p->ct_d[t], 7 * G, 128, 64, 1, 128LL * 64 * 2, 64 * 2, 2, 0, 0, s));
+    RUN(queue_pack(packs, P[P_CT_W] + t, p->ct_d[t], 7 * G, 128, 64, 1, 128LL * 64 * 2, 64 * 2, 2, 0, 0, s, nullptr, v2 ? 7 : 0));
   RUN(nef_pack_weights_batch(&packs, s));
   // zero the BatchNorm backward accumulators (s1, s2 of every layer)
   for (int k = 0; k < 3; ++k)
@@ -999,7 +1078,24 @@ extern "C" int nef_backward(NefPlan* p, const NefBackwardArgs* a, nef_stream_t s
     else RUN(zero_t4(p->du0[k], s));
   }
   // latents
-  LatentBwdArgs lb;
+  LatentBwdArgs lb = {};
+  if (v2) {
+    // Model_nefnet2: (query scaling, upsampling) adjoint first, then single_conv_z1 / z2 backward on the latent halves
+    // (weight gradients summed over the three latents, data gradients per latent), then the lead distribution below
+    UpqAdjArgs ua = {};
+    for (int k = 0; k < 3; ++k) { ua.du0[k] = p->du0[k]; ua.lat2[k] = p->lat2[k]; ua.dlat2[k] = p->dlat2[k]; }
+    ua.q = p->q; ua.q_stride = 256; ua.dq = p->dq;
+    RUN(upq_adjoint(ua, s));
+    for (int h = 0; h < 2; ++h)
+      for (int k = 0; k < 3; ++k) {
+        RUN(wgrad_std(p->dlat2[k], 32 * h, 0, p->lat[k], 32 * h, 0, p->s12[h], Gd[h ? P_S2_W : P_S1_W], Gd[h ? P_S2_B : P_S1_B], s));
+        CD c(1, 128, p->dlat2[k]);
+        c.term(p->dlat2[k], 32 * h, 0, 128, 3, p->s12[h].pk_d).out(p->dlat[k], 32 * h, 0);
+        RUN(c.run(s));
+      }
+    lb.direct = 1;
+    for (int k = 0; k < 3; ++k) lb.dlat[k] = p->dlat[k];
+  }
   for (int k = 0; k < 3; ++k) { lb.du0[k] = p->du0[k]; lb.lat[k] = p->lat[k]; }
   lb.z1 = p->z1; lb.z2o = p->z2o; lb.rois = p->rois_in; lb.q = p->q; lb.q_stride = 256; lb.G = G; lb.c1 = p->c1; lb.c2 = p->c2;
   lb.gz1 = p->GA[0]; lb.gz2o = p->gz2o; lb.dq = p->dq;
@@ -1040,7 +1136,7 @@ extern "C" int nef_backward(NefPlan* p, const NefBackwardArgs* a, nef_stream_t s
         d.dy = reinterpret_cast<const float*>(dts[t]->p); d.dy_cstride = dts[t]->cs; d.dy_c4_off = 0; d.dy_c4_gstride = 16;
         d.x = reinterpret_cast<const float*>(p->y20.p); d.x_cstride = p->y20.cs; d.x_c4_off = 0; d.x_c4_gstride = 32;
         d.cout_g = 64; d.cin_g = 128; d.groups = 7 * G; d.taps = 1; d.tap_off = 0; d.rows = p->y20.cs;
-        d.dw = dw; d.sg = 128LL * 64 * 2; d.sm = 2; d.sn = 64 * 2; d.st = 0; d.db = Gd[P_CT_B];
+        d.dw = dw; d.sg = 128LL * 64 * 2; d.sm = 2; d.sn = 64 * 2; d.st = 0; d.db = Gd[P_CT_B]; d.wg_mod = v2 ? 7 : 0;
         RUN(nef_gconv_wgrad(&d, sv));
       }
     }
@@ -1110,7 +1206,7 @@ extern "C" int nef_backward(NefPlan* p, const NefBackwardArgs* a, nef_stream_t s
       RUN(block_bwd(bb, dp, fin, s));
       gy_i = gx_i;
     }
-    if (Gd[P_STEM]) RUN(stem_bwd(p->x_in, p->s0_amax, p->GA[gy_i], Gd[P_STEM], G, s));
+    if (Gd[P_STEM]) RUN(stem_bwd(p->x_in, p->s0_amax, p->GA[gy_i], Gd[P_STEM], G, s, v2 ? 1 : 0));
   }
   return 0;
 }

@@ -238,7 +238,7 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_f16_kernel(const __grid_cons
         uint32_t v[32];
         tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(tp * dcols + cg * 32), v);
         tmem_ld_wait();
-        float* dst = d.dw + (long)g * d.sg + (long)lr * d.sm + (long)(tile * dcols + cg * 32) * d.sn + (long)tp * d.st;
+        float* dst = d.dw + (long)(d.wg_mod > 0 ? g % d.wg_mod : g) * d.sg + (long)lr * d.sm + (long)(tile * dcols + cg * 32) * d.sn + (long)tp * d.st;
 #pragma unroll
         for (int i = 0; i < 32; ++i) atomicAdd(dst + (long)i * d.sn, __uint_as_float(v[i]) * out_scale);
       }
@@ -267,7 +267,7 @@ __global__ void __launch_bounds__(256) wgrad_f16_tail_kernel(const NefWgradDesc 
   float acc = 0.f;
   for (long r = row0; r < d.rows; ++r)
     acc += __half2float(dy16[(yc + r) * 8 + (m & 7)]) * __half2float(x16[(xc + r) * 8 + (n & 7)]);
-  atomicAdd(d.dw + (long)g * d.sg + (long)m * d.sm + (long)n * d.sn + (long)t * d.st, acc * (out_scale_p ? __ldg(out_scale_p) : 1.f));
+  atomicAdd(d.dw + (long)(d.wg_mod > 0 ? g % d.wg_mod : g) * d.sg + (long)m * d.sm + (long)n * d.sn + (long)t * d.st, acc * (out_scale_p ? __ldg(out_scale_p) : 1.f));
 }
 
 }  // namespace wf16

@@ -42,7 +42,7 @@ class NefWgradDesc(C.Structure):
     _fields_ = [("dy", C.c_void_p), ("dy_cstride", C.c_int64), ("dy_c4_off", C.c_int32), ("dy_c4_gstride", C.c_int32),
                 ("x", C.c_void_p), ("x_cstride", C.c_int64), ("x_c4_off", C.c_int32), ("x_c4_gstride", C.c_int32),
                 ("cout_g", C.c_int32), ("cin_g", C.c_int32), ("groups", C.c_int32), ("taps", C.c_int32),
-                ("tap_off", C.c_int32), ("reserved", C.c_int32), ("rows", C.c_int64), ("dw", C.c_void_p),
+                ("tap_off", C.c_int32), ("wg_mod", C.c_int32), ("rows", C.c_int64), ("dw", C.c_void_p),
                 ("sg", C.c_int64), ("sm", C.c_int64), ("sn", C.c_int64), ("st", C.c_int64), ("db", C.c_void_p)]
 
 
@@ -87,6 +87,10 @@ SIGNATURES = {
     "nef_gconv_wgrad": (C.c_int, [C.POINTER(NefWgradDesc), C.c_void_p]),
     "nef_gconv_wgrad_f16": (C.c_int, [C.POINTER(NefWgradDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "nef_plan_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "nef_plan_create_v": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "nef_param_count_v": (C.c_int, [C.c_int, C.c_int]),
+    "nef_param_name_v": (C.c_char_p, [C.c_int, C.c_int, C.c_int]),
+    "nef_param_numel_v": (C.c_int64, [C.c_int, C.c_int, C.c_int]),
     "nef_plan_destroy": (None, [C.c_void_p]),
     "nef_plan_workspace_bytes": (C.c_size_t, [C.c_void_p]),
     "nef_plan_bind": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),

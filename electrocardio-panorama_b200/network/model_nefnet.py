@@ -85,6 +85,12 @@ class _NefFunction(torch.autograd.Function):
 
 
 class Model_nefnet(nn.Module):
+    _variant = 1      # NefPlan variant (include/nefnet_b200.h: nef_plan_create_v)
+
+    def _make_specs(self):
+        specs = _param_specs(self.lead_num)
+        return specs, [s[0] for s in specs]
+
     def __init__(self, theta_encoder_len=1, lead_num=1):
         super().__init__()
         if theta_encoder_len != 1:
@@ -93,8 +99,8 @@ class Model_nefnet(nn.Module):
         self.theta_encoder_len = theta_encoder_len
         self.lead_num = int(lead_num)
         self.dropout_p = 0.2          # nn.Dropout(0.2) of every residual block; active in train() mode
-        self._specs = _param_specs(self.lead_num)
-        self._names = [s[0] for s in self._specs]
+        # _specs: state_dict entries in the reference's registration order; _names: the order of the C ABI's params / grads arrays
+        self._specs, self._names = self._make_specs()
         self._plans = {}
         self._fwd_token = 0
         self._step = 0
@@ -247,10 +253,10 @@ class Model_nefnet(nn.Module):
 
     # ------------------------------------------------------------------ plans / workspace
     class _Plan:
-        def __init__(self, B, G, L, V, device):
+        def __init__(self, B, G, L, V, device, variant=1):
             lib = N.load()
             h = C.c_void_p()
-            N.check(lib.nef_plan_create(B, G, L, V, C.byref(h)), "nef_plan_create")
+            N.check(lib.nef_plan_create_v(B, G, L, V, variant, C.byref(h)), "nef_plan_create_v")
             self.handle = h
             self.B = B
             self.bytes = lib.nef_plan_workspace_bytes(h)
@@ -270,7 +276,7 @@ class Model_nefnet(nn.Module):
             for old in self._plans.values():  # one live workspace at a time (tens of GB at batch 256)
                 old.close()
             self._plans = {}
-            plan = Model_nefnet._Plan(B, self.lead_num, L, V, device)
+            plan = Model_nefnet._Plan(B, self.lead_num, L, V, device, self._variant)
             self._plans[key] = plan
         return plan
 

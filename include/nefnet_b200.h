@@ -169,7 +169,7 @@ int nef_pack_weights(const float* src, float* dst, int groups, int N, int K, int
                      int64_t sk, int64_t st, int flags, nef_stream_t s);
 int nef_gconv_fwd(const NefConvDesc* d, nef_stream_t s);
 
-/* weight gradient: dw[g*sg + m*sm + n*sn + t*st] += sum_rows dy[row][g, m] * x[row + t + tap_off][g, n];
+/* weight gradient (accumulated atomically): dw[g*sg + m*sm + n*sn + t*st] += sum_rows dy[row][g, m] * x[row + t + tap_off][g, n];
  * db[g*cout_g + m] += sum_rows dy[row][g, m]                                                     */
 typedef struct NefWgradDesc {
   const float* dy;
@@ -179,7 +179,9 @@ typedef struct NefWgradDesc {
   int64_t x_cstride;
   int32_t x_c4_off, x_c4_gstride;
   int32_t cout_g, cin_g; /* multiples of 64 */
-  int32_t groups, taps, tap_off, reserved;
+  int32_t groups, taps, tap_off;
+  int32_t wg_mod; /* 0: one weight slot per group; m > 0: group g accumulates into slot g mod m of dw / db (weights shared by
+                   * groups: Model_nefnet2's single-lead trunk applied to every lead) */
   int64_t rows;
   float* dw;
   int64_t sg, sm, sn, st;
@@ -198,6 +200,16 @@ int nef_gconv_wgrad_f16(const NefWgradDesc* d, const void* dy16, const void* x16
 typedef struct NefPlan NefPlan;
 /* V = number of extra views decoded in phase 'test' (0 for training). host call. */
 int nef_plan_create(int B, int G, int L, int V, NefPlan** plan);
+/* The same for a model variant: 1 = Model_nefnet (network/model_nefnet.py), 2 = Model_nefnet2 (network/model_nefnet2.py:63-203):
+ * ONE single-lead trunk whose weights every lead shares (the grouped kernels read weight slice g mod m and accumulate
+ * their weight gradients into it) plus single_conv_z1 / single_conv_z2, which -- being linear -- are applied to the lead
+ * means and the picked leads instead of to every lead.  `params` / `grads` of nef_forward / nef_backward follow
+ * nef_param_name_v(G, 2, i): the G = 1 table of variant 1 followed by single_conv_z1.0.{weight,bias},
+ * single_conv_z2.0.{weight,bias}.  Phase 'gen' and nef_gen_ecg are variant-1 only. */
+int nef_plan_create_v(int B, int G, int L, int V, int variant, NefPlan** plan);
+int nef_param_count_v(int G, int variant);
+const char* nef_param_name_v(int G, int variant, int i);
+int64_t nef_param_numel_v(int G, int variant, int i);
 void nef_plan_destroy(NefPlan* plan);
 size_t nef_plan_workspace_bytes(const NefPlan* plan);
 /* Carves the caller's workspace (must be nef_plan_workspace_bytes) and zero-fills it on `s`. */
