@@ -1126,6 +1126,7 @@ extern "C" int nef_tc_init(void) {
 #undef X
   if (getenv("NEF_TC_MT")) g_tc_mt = atoi(getenv("NEF_TC_MT"));
   if (getenv("NEF_TC_PERSIST")) g_tc_persist = atoi(getenv("NEF_TC_PERSIST"));
+  if (getenv("NEF_TC_PERSIST_MIN")) g_tc_persist_min = atoi(getenv("NEF_TC_PERSIST_MIN"));   // 1: persistent kernel at every size (sanitizer runs)
   if (getenv("NEF_TC_STAGGER")) g_tc_stagger = atoi(getenv("NEF_TC_STAGGER"));
   if (getenv("NEF_TC_WS")) g_tc_ws = atoi(getenv("NEF_TC_WS"));
   { int rc = tc_optin<1, tc::EPI_GENERIC>(); if (rc) return rc; }
