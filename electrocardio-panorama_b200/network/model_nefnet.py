@@ -431,6 +431,10 @@ class Model_nefnet(nn.Module):
             # a side stream behind the event nef_backward recorded; bucket 0 (stem, encoder, mlp, w_conv) follows on the
             # main stream.  ReduceOp.AVG: the mean over ranks, as DataParallel's gradient of the batch-mean loss.
             split = self._ddp_split
+            if os.environ.get("NEF_DDP_OVERLAP", "1") == "0":     # A/B switch: one all-reduce behind the whole backward
+                dist.all_reduce(self._flat_grad, op=dist.ReduceOp.AVG)
+                split = None
+        if world > 1 and split is not None:
             self._ddp_stream.wait_event(self._ddp_event)
             with torch.cuda.stream(self._ddp_stream):
                 w1 = dist.all_reduce(self._flat_grad[split:], op=dist.ReduceOp.AVG, async_op=True)
