@@ -17,6 +17,13 @@ Launcher form -- runs an unmodified reference script with the substitution in pl
 
     cd /path/to/Electrocardio-Panorama/codes
     CUDA_VISIBLE_DEVICES=0 python /path/to/repo/electrocardio-panorama_b200/dropin.py main.py --config-file config/nef_net.yml
+
+Data parallel (one process per GPU; the solver's nn.DataParallel branch, solver.py:32-34, is never taken because each rank
+sees ONE device): launched under torchrun the launcher pins the rank to its GPU (CUDA_VISIBLE_DEVICES = LOCAL_RANK) and
+initialises the NCCL process group before the script starts; the module then averages the gradients inside backward().
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 \
+        /path/to/repo/electrocardio-panorama_b200/dropin.py main.py --config-file config/nef_net.yml
 """
 import importlib.util
 import os
@@ -58,12 +65,31 @@ def install():
     return sys.modules["network"]
 
 
+def _init_data_parallel():
+    """Under torchrun (WORLD_SIZE > 1): one visible device per rank, NCCL process group up before the reference's script runs."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world <= 1:
+        return False
+    local = os.environ.get("LOCAL_RANK", "0")
+    visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+    devs = visible.split(",") if visible else None
+    os.environ["CUDA_VISIBLE_DEVICES"] = devs[int(local)] if devs and int(local) < len(devs) else local
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    import torch
+    import torch.distributed as dist
+    if not dist.is_initialized():
+        torch.cuda.set_device(0)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", 0))
+    return True
+
+
 def main(argv):
     if not argv:
         sys.stderr.write(__doc__)
         return 2
     import runpy
     script = os.path.abspath(argv[0])
+    _init_data_parallel()
     install()
     sys.argv = [script] + list(argv[1:])
     sys.path.insert(0, os.path.dirname(script))   # what `python script.py` does
