@@ -33,7 +33,7 @@ def prepare_segments(raw, rec_off, rec_len, marks, L=512, select_index=None, tar
     if not raw.is_cuda:
         raise RuntimeError("prepare_segments: CUDA tensors required (there is no CPU path)")
     dev = raw.device
-    lib = N.init(dev.index or 0)
+    lib = N.init(N.device_index(dev))
     marks = marks.to(device=dev, dtype=torch.int64).contiguous()
     B = marks.shape[0]
     ori = torch.empty((B, 12, L), dtype=torch.float32, device=dev) if want_ori else None
@@ -51,10 +51,11 @@ def prepare_segments(raw, rec_off, rec_len, marks, L=512, select_index=None, tar
         tgt = torch.empty((B, 1, L), dtype=torch.float32, device=dev)
     rois = torch.empty((B, 7, 2), dtype=torch.int64, device=dev)
     scratch = torch.empty(lib.nef_prepare_scratch_bytes(B) // 8, dtype=torch.float64, device=dev)
-    N.check(lib.nef_prepare_segments(N.ptr(raw), N.ptr(rec_off), N.ptr(rec_len), N.ptr(marks), B, L, N.ptr(sel), G,
-                                     N.ptr(tidx), N.ptr(scratch), N.ptr(ori), N.ptr(data), N.ptr(tgt), N.ptr(rois),
-                                     N.stream_ptr()),
-            "nef_prepare_segments")
+    with N.guard(dev):
+        N.check(lib.nef_prepare_segments(N.ptr(raw), N.ptr(rec_off), N.ptr(rec_len), N.ptr(marks), B, L, N.ptr(sel), G,
+                                         N.ptr(tidx), N.ptr(scratch), N.ptr(ori), N.ptr(data), N.ptr(tgt), N.ptr(rois),
+                                         N.stream_ptr()),
+                "nef_prepare_segments")
     return {"data": data, "target_view": tgt, "ori_data": ori, "rois": rois}
 
 

@@ -3,6 +3,7 @@ parent directory on ``sys.path`` in place of the reference's and ``from network 
 build_loss`` resolves to the B200-native implementation."""
 from .loss import losswrapper
 from .model_nefnet import Model_nefnet
+from .model_nefnet2 import Model_nefnet2  # constructed directly, like the reference's class (build_model never returns it)
 
 
 def build_model(cfg):

@@ -171,6 +171,25 @@ def stream_ptr():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+def guard(device):
+    """Context manager: make `device` (a torch.device or a CUDA tensor) the current CUDA device for the native calls inside,
+    so that stream_ptr() is that device's current stream and nef_init binds the right device -- a module on cuda:1 called
+    while cuda:0 is current launches on cuda:1."""
+    import torch
+    if isinstance(device, torch.Tensor):
+        device = device.device
+    if device.type != "cuda":
+        raise RuntimeError("nefnet_b200: CUDA tensors required (got %s); there is no CPU path" % device)
+    return torch.cuda.device(device)
+
+
+def device_index(device):
+    import torch
+    if isinstance(device, torch.Tensor):
+        device = device.device
+    return device.index if device.index is not None else torch.cuda.current_device()
+
+
 def ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
 

@@ -18,10 +18,20 @@ def _prep(t, like):
 
 class _StandinLoss(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, predict, pred_p, pred_l, target, gt1, gt2, use_mse, factors, mask):
+    def forward(ctx, predict, *rest):
         if predict.device.type != "cuda":
             raise RuntimeError("losswrapper (B200) needs CUDA tensors; there is no CPU path")
-        lib = N.init(predict.device.index if predict.device.index is not None else torch.cuda.current_device())
+        with N.guard(predict):       # launches go to the tensors' device, whatever device is current
+            return _StandinLoss._fwd(ctx, predict, *rest)
+
+    @staticmethod
+    def backward(ctx, dlosses):
+        with N.guard(ctx.saved_tensors[0]):
+            return _StandinLoss._bwd(ctx, dlosses)
+
+    @staticmethod
+    def _fwd(ctx, predict, pred_p, pred_l, target, gt1, gt2, use_mse, factors, mask):
+        lib = N.init(N.device_index(predict))
         o = _prep(predict, predict)
         p, l, t = _prep(pred_p, predict), _prep(pred_l, predict), _prep(target, predict)
         n = o.numel()
@@ -48,7 +58,7 @@ class _StandinLoss(torch.autograd.Function):
         return losses
 
     @staticmethod
-    def backward(ctx, dlosses):
+    def _bwd(ctx, dlosses):
         o, p, l, t = ctx.saved_tensors
         use_mse, factors, mask, fused = ctx.meta
         lib = N.load()
@@ -72,12 +82,13 @@ class _StandinLoss(torch.autograd.Function):
 
 def pair_loss(a, b, use_mse):
     """mean |a - b| (or squared): the unsupervised validation term (losses.py:47-49); no gradient."""
-    lib = N.init(a.device.index if a.device.index is not None else torch.cuda.current_device())
-    a_, b_ = _prep(a, a), _prep(b, a)
-    sums = torch.empty(3, dtype=torch.float64, device=a.device)
-    res = torch.empty(1, dtype=torch.float32, device=a.device)
-    N.check(lib.nef_pair_loss(N.ptr(a_), N.ptr(b_), a_.numel(), int(use_mse), N.ptr(sums), N.ptr(res), N.stream_ptr()),
-            "nef_pair_loss")
+    with N.guard(a):
+        lib = N.init(N.device_index(a))
+        a_, b_ = _prep(a, a), _prep(b, a)
+        sums = torch.empty(3, dtype=torch.float64, device=a.device)
+        res = torch.empty(1, dtype=torch.float32, device=a.device)
+        N.check(lib.nef_pair_loss(N.ptr(a_), N.ptr(b_), a_.numel(), int(use_mse), N.ptr(sums), N.ptr(res), N.stream_ptr()),
+                "nef_pair_loss")
     return res[0]
 
 

@@ -80,7 +80,8 @@ class _NefFunction(torch.autograd.Function):
         # The parameter gradients are written straight into the flat gradient buffer and every p.grad is pointed at its view
         # of it (no per-step copies; a stock torch optimiser, FlatSGD and the data-parallel all-reduce all see one buffer),
         # so autograd itself receives no parameter gradients.
-        model._run_backward(dout, dout_p, dout_l)
+        with N.guard(model._flat):
+            model._run_backward(dout, dout_p, dout_l)
         return (None,) * (7 + ctx.n_live)
 
 
@@ -224,7 +225,7 @@ class Model_nefnet(nn.Module):
         if device.type != "cuda":
             raise RuntimeError("Model_nefnet (B200) runs on an sm_100 CUDA device only; got tensors on %s. "
                                "There is no CPU path." % device)
-        N.init(device.index if device.index is not None else torch.cuda.current_device())
+        N.init(N.device_index(device))
         p0 = next(self.parameters())
         if p0.device != device:
             raise RuntimeError("Model_nefnet: parameters are on %s but inputs on %s" % (p0.device, device))
@@ -480,6 +481,12 @@ class Model_nefnet(nn.Module):
     def forward(self, x, input_thetas, query_theta, rois, rest_theta=None, phase="train"):
         """model_nefnet.py:109-194.  x (B, lead_num, L) fp32, input_thetas (B, lead_num, 2), query_theta
         (B, 2), rois (B, 7, 2) int64, rest_theta (B, V, 2)."""
+        if torch.is_tensor(x) and x.is_cuda:
+            with N.guard(x):      # the native calls run on x's device and its current stream, whatever device is current
+                return self._forward(x, input_thetas, query_theta, rois, rest_theta, phase)
+        return self._forward(x, input_thetas, query_theta, rois, rest_theta, phase)
+
+    def _forward(self, x, input_thetas, query_theta, rois, rest_theta=None, phase="train"):
         if phase == "gen":  # latents before roi reverse (:140-141); no random draws
             with torch.no_grad():
                 return self._run_forward(x, input_thetas, query_theta, rois, None, N.PHASE_GEN, 0, 0, save=False)
@@ -499,6 +506,9 @@ class Model_nefnet(nn.Module):
         """model_nefnet.py:196-218: decode V views from latents; flips the module to eval (:197)."""
         self.eval()
         device = z1.device
+        if device.type == "cuda" and torch.cuda.current_device() != N.device_index(device):
+            with N.guard(device):
+                return self.gen_ecg(z1, z2, query_theta, rois)
         self._ensure_ready(device)
         lib = N.load()
         B = z1.shape[0]

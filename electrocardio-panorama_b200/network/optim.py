@@ -61,8 +61,9 @@ class FlatSGD(torch.optim.Optimizer):
                     grad[o:o + p.numel()].zero_()
                     self._mom[o:o + p.numel()].zero_()
             lib = N.load()
-            N.check(lib.nef_sgd_step(N.ptr(flat), N.ptr(grad), N.ptr(self._mom), flat.numel(), self.lr, self.momentum,
-                                     1.0 / float(world_size), N.stream_ptr()), "nef_sgd_step")
+            with N.guard(flat):
+                N.check(lib.nef_sgd_step(N.ptr(flat), N.ptr(grad), N.ptr(self._mom), flat.numel(), self.lr, self.momentum,
+                                         1.0 / float(world_size), N.stream_ptr()), "nef_sgd_step")
         return loss
 
     # checkpoints (utils/checkpointer.py:28-31 saves optimizer.state_dict()): the momentum lives in one flat buffer

@@ -28,7 +28,7 @@ class PsnrAccumulator:
         """pred, gt (B, V, L) fp32 CUDA tensors; rois (B, 7, 2) int64 or None.  Returns the 0-dim running mean (device)."""
         if not pred.is_cuda:
             raise RuntimeError("PsnrAccumulator: CUDA tensors required (there is no CPU path)")
-        lib = N.init(pred.device.index or 0)
+        lib = N.init(N.device_index(pred))
         pred = pred.detach().to(torch.float32).contiguous()
         gt = gt.detach().to(device=pred.device, dtype=torch.float32).contiguous()
         if pred.shape != gt.shape or pred.dim() != 3:
@@ -38,8 +38,9 @@ class PsnrAccumulator:
             rois = rois.detach().to(device=pred.device, dtype=torch.int64).contiguous()
         if self._rows is None or self._rows.numel() < B * V:
             self._rows = torch.empty(B * V, dtype=torch.float64, device=pred.device)
-        N.check(lib.nef_psnr(N.ptr(pred), N.ptr(gt), N.ptr(rois), B, V, L, N.ptr(self._rows), N.ptr(self.acc),
-                             N.ptr(self.result), N.stream_ptr()), "nef_psnr")
+        with N.guard(pred):
+            N.check(lib.nef_psnr(N.ptr(pred), N.ptr(gt), N.ptr(rois), B, V, L, N.ptr(self._rows), N.ptr(self.acc),
+                                 N.ptr(self.result), N.stream_ptr()), "nef_psnr")
         return self.result[0]
 
     def rows(self, n):
