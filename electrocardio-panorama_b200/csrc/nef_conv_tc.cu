@@ -636,14 +636,19 @@ struct PsSmem {
 };
 static_assert(PsSmem::TOTAL <= 227 * 1024, "persistent conv shared memory");
 
-// Epilogue warps of the persistent kernel: 16 (four per scheduler) hide the TMEM-load / global-load latency of the long
-// specialised bodies (dropout, fp16 copies, bit planes) far better than 8; the BatchNorm-statistics and generic bodies
-// need more than the 112 registers that leaves per thread and stay at 8.
+// Epilogue warps of the persistent kernel: 16 (four per scheduler) hide the TMEM-load / global-load latency of the
+// memory-bound launches (k <= 3: the masked k3 data gradient is 16 % faster than with 8); the BatchNorm-statistics and generic
+// bodies need more than the 112 registers that leaves per thread and stay at 8.  The tensor-bound k7 launches are better off
+// with 8 as well (3-5 %: the MMA-issuing warp shares its scheduler with two busy epilogue warps instead of four), so the
+// epilogues those layers use (NEF_TC_EPI_HEAVY) are also instantiated with 8 and picked per launch by MMAs per tile.
 template <int EPI>
-constexpr int ps_epi_warps() { return (EPI & (EPI_STATS | EPI_GENERIC)) ? 8 : 16; }
+#ifndef NEF_PS_EW
+#define NEF_PS_EW 16
+#endif
+constexpr int ps_epi_warps() { return (EPI & (EPI_STATS | EPI_GENERIC)) ? 8 : NEF_PS_EW; }
 
-template <int EPI>
-__global__ void __launch_bounds__(64 + 32 * ps_epi_warps<EPI>(), 1) conv_tc_persist_kernel(const __grid_constant__ NefConvDesc d, int tiles_per_group,
+template <int EPI, int EW = ps_epi_warps<EPI>()>
+__global__ void __launch_bounds__(64 + 32 * EW, 1) conv_tc_persist_kernel(const __grid_constant__ NefConvDesc d, int tiles_per_group,
                                                                         int n_tiles, int use_ws) {
   using S = PsSmem;
   constexpr int MT = S::MT;
@@ -666,7 +671,7 @@ __global__ void __launch_bounds__(64 + 32 * ps_epi_warps<EPI>(), 1) conv_tc_pers
   if (tid == 0) {
     for (int i = 0; i < S::XST; ++i) { mbar_init(full_x(i), 1); mbar_init(empty_x(i), 1); }
     for (int i = 0; i < S::WST; ++i) { mbar_init(full_w(i), 1); mbar_init(empty_w(i), 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(acc_full(i), 1); mbar_init(acc_empty(i), 32 * ps_epi_warps<EPI>()); }
+    for (int i = 0; i < 2; ++i) { mbar_init(acc_full(i), 1); mbar_init(acc_empty(i), 32 * EW); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(smem_u32((const void*)tmem_slot), TM_COLS);
@@ -809,7 +814,7 @@ __global__ void __launch_bounds__(64 + 32 * ps_epi_warps<EPI>(), 1) conv_tc_pers
       mbar_wait(acc_full(as), aph);
       tc_fence_after();
       if (!(use_ws & 2))   // (NEF_TC_WS bit 1: timing experiment without the epilogue)
-        epilogue_tile<MT, EPI, ps_epi_warps<EPI>()>(d, g, r0, tmem + (uint32_t)(as * 256), warp, lane, tid, s_stat);
+        epilogue_tile<MT, EPI, EW>(d, g, r0, tmem + (uint32_t)(as * 256), warp, lane, tid, s_stat);
       tc_fence_before();
       mbar_arrive(acc_empty(as));
       if (++as == 2) { as = 0; aph ^= 1; }
@@ -1104,12 +1109,17 @@ static int g_tc_ws = 0;   // 1 = weight-stationary MMA form (NEF_TC_WS)
 static int g_tc_persist = 1;  // persistent forward kernel (NEF_TC_PERSIST=0: one CTA per tile)
 static int g_tc_persist_min = 0;  // row-tile x group count from which the persistent kernel is used; 0 = 2 x SM count
 extern "C" int nef_tc_set_persist_min(int tiles) { g_tc_persist_min = tiles; return 0; }  // test hook: 1 = always persistent
+static int g_tc_heavy_mmas = 96;  // MMAs per 256-row tile from which a launch counts as tensor-bound (8 epilogue warps); k7 x 128 ch = 112
 static int g_tc_mt = 0;  // 0 = automatic; 4 forces four row tiles per CTA, one CTA per SM (NEF_TC_MT, for A/B measurements)
 
 // the specialised epilogues instantiated for the 4-row-tile kernel (everything else takes the generic one)
 #define NEF_TC_EPI_LIST(X) X(0) X(2) X(5) X(32) X(33) X(36) X(37) X(38) X(44) X(48) X(50) X(64) X(294) X(418) X(513) \
   X(1062) X(1068) X(1318) X(2080) X(2082) X(2338) X(4132) X(4134) X(4390) X(5158) X(5164) X(5414) X(8194) X(14368) X(14370) X(14626) X(21540) X(21796) X(24576) X(30752) X(31008) \
   X(37932) X(54308) X(54564) X(47136) X(63520) X(63776)   /* the production fp16-only stores: 5164, 21540, 21796, 14368, 30752, 31008 | EPI_NOY */
+
+// the epilogues of the k7 / 128-channel fp16 layers (forward with dropout, second convolutions with the fp16 residual, masked
+// and unmasked loss-scaled data gradients): instantiated with 8 epilogue warps too
+#define NEF_TC_EPI_HEAVY(X) X(37932) X(54308) X(54564) X(47136) X(63520) X(24576)
 
 template <int MT, int EPI>
 static int tc_optin() {
@@ -1124,6 +1134,11 @@ extern "C" int nef_tc_init(void) {
                NEF_REQUIRE(pe == cudaSuccess, "nef_tc_init: conv_tc_persist_kernel<%d> shared-memory opt-in failed: %s", E, cudaGetErrorString(pe)); }
   NEF_TC_EPI_LIST(X)
 #undef X
+#define X(E) { cudaError_t pe = cudaFuncSetAttribute(tc::conv_tc_persist_kernel<E, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::PsSmem::TOTAL); \
+               NEF_REQUIRE(pe == cudaSuccess, "nef_tc_init: conv_tc_persist_kernel<%d, 8> shared-memory opt-in failed: %s", E, cudaGetErrorString(pe)); }
+  NEF_TC_EPI_HEAVY(X)
+#undef X
+  if (getenv("NEF_TC_HEAVY_MMAS")) g_tc_heavy_mmas = atoi(getenv("NEF_TC_HEAVY_MMAS"));
   if (getenv("NEF_TC_MT")) g_tc_mt = atoi(getenv("NEF_TC_MT"));
   if (getenv("NEF_TC_PERSIST")) g_tc_persist = atoi(getenv("NEF_TC_PERSIST"));
   if (getenv("NEF_TC_PERSIST_MIN")) g_tc_persist_min = atoi(getenv("NEF_TC_PERSIST_MIN"));   // 1: persistent kernel at every size (sanitizer runs)
@@ -1212,6 +1227,16 @@ static int launch_conv_persist(const NefConvDesc* d, cudaStream_t s) {
   }
   nef_tc_note_dispatch(0);
   note_persist_epi(specialised ? epi_code(d) : tc::EPI_GENERIC);
+  int mmas = 0;   // MMAs per 256-row tile
+  for (int i = 0; i < d->n_terms; ++i) mmas += (d->term[i].cin_g >> 5) * d->term[i].taps * 8;
+  if (mmas >= g_tc_heavy_mmas) {
+    switch (epi_code(d)) {
+#define X(E) case E: tc::conv_tc_persist_kernel<E, 8><<<grid, 64 + 32 * 8, tc::PsSmem::TOTAL, s>>>(*d, tpg, n_tiles, g_tc_ws); return 0;
+      NEF_TC_EPI_HEAVY(X)
+#undef X
+      default: break;
+    }
+  }
   switch (epi_code(d)) {
 #define X(E) case E: tc::conv_tc_persist_kernel<E><<<grid, 64 + 32 * tc::ps_epi_warps<E>(), tc::PsSmem::TOTAL, s>>>(*d, tpg, n_tiles, g_tc_ws); break;
     NEF_TC_EPI_LIST(X)

@@ -11,7 +11,7 @@ import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _PKG = os.path.dirname(_HERE)
-LIB_PATH = os.path.join(_PKG, "lib", "libnefnet_b200.so")
+LIB_PATH = os.environ.get("NEFNET_B200_LIB") or os.path.join(_PKG, "lib", "libnefnet_b200.so")   # override: A/B builds (tools/)
 
 PHASE_TRAIN, PHASE_TEST, PHASE_GEN = 0, 1, 2
 HALO = 3
