@@ -1209,6 +1209,201 @@ int bnbwd_apply(T4 da, T4 c, const BnLayer& bn, const float* gamma, double count
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// fp16 decoder dataflow (nef_plan.cu dec_f16): the post-BatchNorm activations a1 / u1 / a3 are kept as fp16 operand copies
+// only (half8 rows, 8 channels per 16-byte row, same row indexing as the CBL4 tensor) and the gradients between the decoder
+// layers as loss-scaled fp16 copies.  Same arithmetic as the fp32 kernels above; one thread handles 8 channels of a row.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 h8_pack(float4 a, float4 b) {
+  return make_uint4(f16x2_sat(a.x, a.y), f16x2_sat(a.z, a.w), f16x2_sat(b.x, b.y), f16x2_sat(b.z, b.w));
+}
+__device__ __forceinline__ void h8_unpack(uint4 h, float4& a, float4& b) {
+  const float2 a0 = __half22float2(*reinterpret_cast<const __half2*>(&h.x)), a1 = __half22float2(*reinterpret_cast<const __half2*>(&h.y));
+  const float2 b0 = __half22float2(*reinterpret_cast<const __half2*>(&h.z)), b1 = __half22float2(*reinterpret_cast<const __half2*>(&h.w));
+  a = make_float4(a0.x, a0.y, a1.x, a1.y);
+  b = make_float4(b0.x, b0.y, b1.x, b1.y);
+}
+static inline dim3 ew_grid8(int C, int B, int L) { return dim3((unsigned)((L + EW_TPB * EW_PER - 1) / (EW_TPB * EW_PER)), (unsigned)((C / 8) * B)); }
+
+// out16 = fp16(relu(bn(c))) (with upsample: of the x2 linear upsampling of it); og = geometry of the output tensor
+__global__ void __launch_bounds__(EW_TPB) bn_relu_h_kernel(T4 c, const float* __restrict__ scale, const float* __restrict__ shift,
+                                                           uint4* __restrict__ out16, T4 og, int upsample) {
+  const int c8 = blockIdx.y / c.B, b = blockIdx.y - c8 * c.B;
+  const float4 sc0 = reinterpret_cast<const float4*>(scale)[2 * c8], sc1 = reinterpret_cast<const float4*>(scale)[2 * c8 + 1];
+  const float4 sh0 = reinterpret_cast<const float4*>(shift)[2 * c8], sh1 = reinterpret_cast<const float4*>(shift)[2 * c8 + 1];
+  const float4* cp0 = c.at(2 * c8, b, 0);
+  const float4* cp1 = c.at(2 * c8 + 1, b, 0);
+  uint4* op = out16 + (long)c8 * og.cs + og.row(b, 0);
+  const int l0 = blockIdx.x * (EW_TPB * EW_PER) + threadIdx.x;
+#pragma unroll
+  for (int k = 0; k < EW_PER; ++k) {
+    const int l = l0 + k * EW_TPB;
+    if (l >= og.L) break;
+    float4 v0, v1;
+    if (!upsample) {
+      v0 = bn_relu4(cp0[l], sc0, sh0);
+      v1 = bn_relu4(cp1[l], sc1, sh1);
+    } else {
+      const int li = l >> 1;
+      const int ln = (l & 1) == 0 ? (li > 0 ? li - 1 : li) : (li + 1 < c.L ? li + 1 : li);   // the 0.25-weight neighbour (clamped)
+      const float4 a0 = bn_relu4(cp0[li], sc0, sh0), a1 = bn_relu4(cp1[li], sc1, sh1);
+      const float4 n0 = bn_relu4(cp0[ln], sc0, sh0), n1 = bn_relu4(cp1[ln], sc1, sh1);
+      if ((l & 1) == 0) { v0 = n0 * 0.25f + a0 * 0.75f; v1 = n1 * 0.25f + a1 * 0.75f; }
+      else { v0 = a0 * 0.75f + n0 * 0.25f; v1 = a1 * 0.75f + n1 * 0.25f; }
+    }
+    op[l] = h8_pack(v0, v1);
+  }
+}
+int bn_relu_h(T4 c, const float* scale, const float* shift, void* out16, T4 og, int upsample, cudaStream_t s) {
+  bn_relu_h_kernel<<<ew_grid8(c.C, c.B, og.L), EW_TPB, 0, s>>>(c, scale, shift, reinterpret_cast<uint4*>(out16), og, upsample);
+  NEF_CHECK_LAUNCH("bn_relu_h_kernel");
+  return 0;
+}
+
+// adjoint of the x2 linear upsampling on fp16 gradient copies (both carry the same loss scale): (C, 2n) -> (C, n)
+__global__ void __launch_bounds__(EW_TPB) up_adjoint_h_kernel(const uint4* __restrict__ du16, T4 du, uint4* __restrict__ da16, T4 da) {
+  const int n = da.L;
+  const int c8 = blockIdx.y / da.B, b = blockIdx.y - c8 * da.B;
+  const uint4* p = du16 + (long)c8 * du.cs + du.row(b, 0);
+  uint4* o = da16 + (long)c8 * da.cs + da.row(b, 0);
+  const int l0 = blockIdx.x * (EW_TPB * EW_PER) + threadIdx.x;
+#pragma unroll
+  for (int k = 0; k < EW_PER; ++k) {
+    const int l = l0 + k * EW_TPB;
+    if (l >= n) break;
+    // rows 2l-1 .. 2l+2 ; the halo rows of the tensor are zero, the clamped ends add their own neighbour instead
+    float4 m0, m1, a0, a1, b0, b1, q0, q1;
+    h8_unpack(p[2 * l], a0, a1);
+    h8_unpack(p[2 * l + 1], b0, b1);
+    h8_unpack(l >= 1 ? p[2 * l - 1] : p[0], m0, m1);
+    h8_unpack(l + 1 < n ? p[2 * l + 2] : p[2 * n - 1], q0, q1);
+    const float4 d0 = (a0 + b0) * 0.75f + (m0 + q0) * 0.25f;
+    const float4 d1 = (a1 + b1) * 0.75f + (m1 + q1) * 0.25f;
+    o[l] = h8_pack(d0, d1);
+  }
+}
+int up_adjoint_h(const void* du16, T4 du, void* da16, T4 da, cudaStream_t s) {
+  up_adjoint_h_kernel<<<ew_grid8(da.C, da.B, da.L), EW_TPB, 0, s>>>(reinterpret_cast<const uint4*>(du16), du, reinterpret_cast<uint4*>(da16), da);
+  NEF_CHECK_LAUNCH("up_adjoint_h_kernel");
+  return 0;
+}
+
+// BatchNorm backward pass 1 on an fp16 gradient copy (times the loss scale S): s1, s2 accumulate in the same scaled units
+// grid (segment groups, C/8); block 256
+__global__ void __launch_bounds__(256) bnbwd_stats_h_kernel(const uint4* __restrict__ da16, T4 c, BnLayer bn, int seg_per_block) {
+  __shared__ float red[8][16];
+  const int c8 = blockIdx.y;
+  float sc[8], sh[8], mu[8], is[8], s1[8], s2[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int ch = c8 * 8 + k;
+    sc[k] = bn.scale[ch]; sh[k] = bn.shift[ch]; mu[k] = bn.mean[ch]; is[k] = bn.invstd[ch];
+    s1[k] = 0.f; s2[k] = 0.f;
+  }
+  const int b0 = blockIdx.x * seg_per_block, b1 = min(c.B, b0 + seg_per_block);
+  for (int b = b0; b < b1; ++b) {
+    const float4* cp0 = c.at(2 * c8, b, 0);
+    const float4* cp1 = c.at(2 * c8 + 1, b, 0);
+    const uint4* dp = da16 + (long)c8 * c.cs + c.row(b, 0);
+    for (int l = threadIdx.x; l < c.L; l += 256) {
+      const float4 x0 = cp0[l], x1 = cp1[l];
+      float4 g0, g1;
+      h8_unpack(dp[l], g0, g1);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float x = k < 4 ? f4get(x0, k) : f4get(x1, k - 4);
+        const float gv = k < 4 ? f4get(g0, k) : f4get(g1, k - 4);
+        const float g = (x * sc[k] + sh[k]) > 0.f ? gv : 0.f;
+        s1[k] += g;
+        s2[k] += g * (x - mu[k]) * is[k];
+      }
+    }
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const float a = warp_sum(s1[k]), b2 = warp_sum(s2[k]);
+    if (lane == 0) {
+      red[warp][k] = a;
+      red[warp][8 + k] = b2;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 16) {
+    float v = 0.f;
+    for (int w = 0; w < 8; ++w) v += red[w][threadIdx.x];
+    if (threadIdx.x < 8) atomicAdd(bn.s1 + c8 * 8 + threadIdx.x, (double)v);
+    else atomicAdd(bn.s2 + c8 * 8 + threadIdx.x - 8, (double)v);
+  }
+}
+int bnbwd_stats_h(const void* da16, T4 c, const BnLayer& bn, cudaStream_t s) {
+  int spb = (int)(((long)c.B * (c.C / 8) + 148 * 8 - 1) / (148 * 8));
+  if (spb < 1) spb = 1;
+  dim3 grid((c.B + spb - 1) / spb, c.C / 8);
+  bnbwd_stats_h_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const uint4*>(da16), c, bn, spb);
+  NEF_CHECK_LAUNCH("bnbwd_stats_h_kernel");
+  return 0;
+}
+
+// pass 2 with an fp16 result: dc16 = fp16(S * gamma * invstd * (g - s1/N - xhat * s2/N)).  The incoming gradient is either
+// the fp32 tensor da (unscaled, s1 / s2 unscaled: the result is multiplied by lscale[0] = S) or the fp16 copy da16 (already
+// times S, s1 / s2 in the same units: dgamma / dbeta take them times lscale[1] = 1 / S).  dc16 may alias da16.
+__global__ void __launch_bounds__(EW_TPB) bnbwd_apply_h_kernel(T4 da, const uint4* da16, T4 c, BnLayer bn, const float* __restrict__ gamma,
+                                                               double count, uint4* dc16, float* dgamma, float* dbeta, int training,
+                                                               const float* __restrict__ lscale) {
+  const float invn = training ? (float)(1.0 / count) : 0.f;
+  const float out_sc = da16 ? 1.f : lscale[0];
+  const int c8 = blockIdx.y / c.B, b = blockIdx.y - c8 * c.B;
+  float sc[8], sh[8], mu[8], is[8], gi[8], m1[8], m2[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int ch = c8 * 8 + k;
+    sc[k] = bn.scale[ch]; sh[k] = bn.shift[ch]; mu[k] = bn.mean[ch]; is[k] = bn.invstd[ch];
+    gi[k] = gamma[ch] * is[k] * out_sc;
+    m1[k] = (float)bn.s1[ch] * invn;
+    m2[k] = (float)bn.s2[ch] * invn;
+  }
+  const float4* cp0 = c.at(2 * c8, b, 0);
+  const float4* cp1 = c.at(2 * c8 + 1, b, 0);
+  const long r0 = (long)c8 * c.cs + c.row(b, 0);
+  const int l0 = blockIdx.x * (EW_TPB * EW_PER) + threadIdx.x;
+#pragma unroll
+  for (int j = 0; j < EW_PER; ++j) {
+    const int l = l0 + j * EW_TPB;
+    if (l >= c.L) break;
+    const float4 x0 = cp0[l], x1 = cp1[l];
+    float4 g0, g1, o0, o1;
+    if (da16) h8_unpack(da16[r0 + l], g0, g1);
+    else { g0 = *da.at(2 * c8, b, l); g1 = *da.at(2 * c8 + 1, b, l); }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float x = k < 4 ? f4get(x0, k) : f4get(x1, k - 4);
+      const float gv = k < 4 ? f4get(g0, k) : f4get(g1, k - 4);
+      const float g = (x * sc[k] + sh[k]) > 0.f ? gv : 0.f;
+      const float xhat = (x - mu[k]) * is[k];
+      const float o = gi[k] * (g - m1[k] - xhat * m2[k]);
+      if (k < 4) f4at(o0, k) = o; else f4at(o1, k - 4) = o;
+    }
+    dc16[r0 + l] = h8_pack(o0, o1);
+  }
+  if (blockIdx.x == 0 && blockIdx.y == 0) {
+    const float ps = da16 ? lscale[1] : 1.f;
+    for (int ch = threadIdx.x; ch < c.C; ch += blockDim.x) {
+      if (dgamma) dgamma[ch] += (float)bn.s2[ch] * ps;
+      if (dbeta) dbeta[ch] += (float)bn.s1[ch] * ps;
+    }
+  }
+}
+int bnbwd_apply_h(const T4* da, const void* da16, T4 c, const BnLayer& bn, const float* gamma, double count, void* dc16,
+                  float* dgamma, float* dbeta, int training, const float* lscale, cudaStream_t s) {
+  T4 z = c;
+  z.p = nullptr;
+  bnbwd_apply_h_kernel<<<ew_grid8(c.C, c.B, c.L), EW_TPB, 0, s>>>(da ? *da : z, reinterpret_cast<const uint4*>(da16), c, bn, gamma, count,
+                                                                   reinterpret_cast<uint4*>(dc16), dgamma, dbeta, training, lscale);
+  NEF_CHECK_LAUNCH("bnbwd_apply_h_kernel");
+  return 0;
+}
+
 // ===========================================================================================
 // Output layer: relu(bn4(c4)) -> Conv1d(64 -> 1, k3, p1) -> sigmoid(x / 3)    model_nefnet.py:106,168
 // ===========================================================================================

@@ -97,6 +97,14 @@ int bnbwd_stats(T4 da, T4 c, const BnLayer& bn, cudaStream_t s);
 // training == 0: the forward used running statistics, so the batch-mean terms of the BatchNorm gradient vanish
 int bnbwd_apply(T4 da, T4 c, const BnLayer& bn, const float* gamma, double count, T4 dc, float* dgamma, float* dbeta,
                 int training, cudaStream_t s);
+// fp16 decoder dataflow: the same passes on / into fp16 copies (half8 rows, geometry of the given T4; gradients times the
+// loss scale lscale[0] = S, lscale[1] = 1 / S)
+int bn_relu_h(T4 c, const float* scale, const float* shift, void* out16, T4 og, int upsample, cudaStream_t s);
+int up_adjoint_h(const void* du16, T4 du, void* da16, T4 da, cudaStream_t s);
+int bnbwd_stats_h(const void* da16, T4 c, const BnLayer& bn, cudaStream_t s);
+// da: fp32 incoming gradient (unscaled) or nullptr to read da16 (scaled); dc16 may alias da16
+int bnbwd_apply_h(const T4* da, const void* da16, T4 c, const BnLayer& bn, const float* gamma, double count, void* dc16,
+                  float* dgamma, float* dbeta, int training, const float* lscale, cudaStream_t s);
 int dec_out_fwd(T4 c4, const float* scale, const float* shift, const float* w, const float* b, float* out,
                 int out_bstride, cudaStream_t s);
 int dec_out_bwd(T4 c4, const BnLayer& bn, const float* w, const float* out, const float* dout, T4 g4, float* dw,

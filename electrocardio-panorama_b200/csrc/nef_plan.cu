@@ -70,6 +70,10 @@ extern "C" int nef_set_bwd_f16(int on) { g_bwd_f16 = on; return 0; }
 // A/B switches (environment, read at nef_init): NEF_KEEP_H32=1 also stores the fp32 hidden activations of the big blocks;
 // NEF_K3_TF32=1 runs the forward of w_conv / z1_conv on TF32 operands
 static int g_keep_h32 = 0, g_k3_tf32 = 0;
+// 1 (default) = fp16 decoder dataflow in training: a1 / u1 / a3 kept as fp16 operand copies only, convolutions 2-4 and every
+// decoder data / weight gradient in kind::f16 on loss-scaled fp16 gradient copies (NEF_DEC_F16=0: the TF32 decoder)
+static int g_dec_f16 = 1;
+extern "C" int nef_set_dec_f16(int on) { g_dec_f16 = on; return 0; }
 extern "C" int nef_gconv_wgrad_f16(const NefWgradDesc* d, const void* dy16, const void* x16, const float* out_scale, nef_stream_t s);
 extern "C" int nef_set_dec1_terms(int n) {
   NEF_REQUIRE(n >= 1 && n <= 3, "nef_set_dec1_terms: 1, 2 or 3");
@@ -99,6 +103,7 @@ extern "C" int nef_init(int device) {
   if (getenv("NEF_KEEP_H32")) g_keep_h32 = atoi(getenv("NEF_KEEP_H32"));
   if (getenv("NEF_K3_TF32")) g_k3_tf32 = atoi(getenv("NEF_K3_TF32"));
   if (getenv("NEF_BWD_F16")) g_bwd_f16 = atoi(getenv("NEF_BWD_F16"));
+  if (getenv("NEF_DEC_F16")) g_dec_f16 = atoi(getenv("NEF_DEC_F16"));
   int rc = elem_init();
   if (rc) return rc;
   return nef_tc_init();
@@ -222,6 +227,7 @@ struct ConvW {            // one convolution's weights: reference tensor + packe
 
 struct DecBufs {          // one decoder call
   T4 c1, a1, c2, u1, c3, a3, c4;
+  void *a1_h, *u1_h, *a3_h;   // fp16 copies of a1 / u1 / a3 (dec_f16: the only copies written)
   BnLayer bn[4];
   float* out;             // (B, L) saved sigmoid output
 };
@@ -257,6 +263,8 @@ struct NefPlan {
   T4 GA[3];
   T4 gz2o, gh22, dt21, dte, dto, gy20, gh20, dra, gz2c, ghz, gxw;
   T4 dg4, dg3, du1, dg2, dg1, du0[3];
+  void *dg4_h, *dg3_h, *du1_h, *dg2_h, *dg1_h;   // loss-scaled fp16 gradient copies of the decoder backward (dec_f16)
+  bool dec_f16;                     // this forward / backward pair runs the fp16 decoder dataflow
   float *ds_in, *dq;
   double* bn_stats;       // BatchNorm backward accumulators (s1, s2) of all layers, contiguous
   size_t bn_stats_count;
@@ -343,6 +351,9 @@ static void carve(NefPlan* p, bool dry) {
     DecBufs& d = p->dec[k];
     d.c1 = c.t4(128, L2); d.a1 = c.t4(128, L2); d.c2 = c.t4(128, L2); d.u1 = c.t4(128, L);
     d.c3 = c.t4(64, L); d.a3 = c.t4(64, L); d.c4 = c.t4(64, L);
+    d.a1_h = c.take(((size_t)(128 / 8) * d.a1.cs + NEF_GUARD_ROWS) * 16);
+    d.u1_h = c.take(((size_t)(128 / 8) * d.u1.cs + NEF_GUARD_ROWS) * 16);
+    d.a3_h = c.take(((size_t)(64 / 8) * d.a3.cs + NEF_GUARD_ROWS) * 16);
     d.out = c.f32((size_t)B * L);
     const int ch[4] = {128, 128, 64, 64};
     for (int i = 0; i < 4; ++i) {
@@ -380,6 +391,11 @@ static void carve(NefPlan* p, bool dry) {
   p->gz2c = c.t4(C1, p->win.Lw); p->ghz = c.t4(C1, p->win.Lw); p->gxw = c.t4(64 * G, p->win.Lw);
   p->dg4 = c.t4(64, L); p->dg3 = c.t4(64, L); p->du1 = c.t4(128, L); p->dg2 = c.t4(128, L2); p->dg1 = c.t4(128, L2);
   for (int k = 0; k < 3; ++k) p->du0[k] = c.t4(256, L2);
+  p->dg4_h = c.take(((size_t)(64 / 8) * p->dg4.cs + NEF_GUARD_ROWS) * 16);
+  p->dg3_h = c.take(((size_t)(64 / 8) * p->dg3.cs + NEF_GUARD_ROWS) * 16);
+  p->du1_h = c.take(((size_t)(128 / 8) * p->du1.cs + NEF_GUARD_ROWS) * 16);
+  p->dg2_h = c.take(((size_t)(128 / 8) * p->dg2.cs + NEF_GUARD_ROWS) * 16);
+  p->dg1_h = c.take(((size_t)(128 / 8) * p->dg1.cs + NEF_GUARD_ROWS) * 16);
   // weights
   for (int i = 0; i < 6; ++i) {
     carve_convw(c, p->enc[i], P_ENC + i, G, 128, 128, 7, m1);
@@ -410,6 +426,11 @@ static void carve(NefPlan* p, bool dry) {
   carve_convw(c, p->decw[1], P_DEC1 + 7, 1, 128, 128, 3);
   carve_convw(c, p->decw[2], P_DEC3 + 0, 1, 64, 128, 3);
   carve_convw(c, p->decw[3], P_DEC3 + 7, 1, 64, 64, 3);
+  for (int i = 0; i < 4; ++i) {   // fp16 packings of the decoder (dec_f16): forward of convolutions 2-4, every data gradient
+    ConvW& w = p->decw[i];
+    if (i > 0) w.pk_h = c.take((size_t)w.cout_g * w.cin_g * w.taps * 2);
+    w.pk_dh = c.take((size_t)w.cout_g * w.cin_g * w.taps * 2);
+  }
   for (int i = 0; i < 4; ++i) { p->fold_scale[i] = c.f32(128); p->fold_bias[i] = c.f32(128); }
   p->ident_scale = c.f32(128); p->ident_shift = c.f32(128);
   for (int t = 0; t < 2; ++t) {
@@ -565,8 +586,11 @@ static int pack_dgrad(NefPackTable& t, const ConvW& w, const float* const* P, cu
                     w.taps, (int64_t)w.cin_g * w.taps, 1, 1, s, nullptr, w.src_gmod);
 }
 
-// the same in fp16 (layers of the fp16 backward; cin_g <= 128 there)
+// the same in fp16 (layers of the fp16 backward)
 static int pack_dgrad_h(NefPackTable& t, const ConvW& w, const float* const* P, cudaStream_t s) {
+  if (w.cin_g > 128)   // decoder first convolution: 256 input channels as two sub-groups of 128 (as pack_dgrad)
+    return queue_pack(t, P[w.pidx], reinterpret_cast<float*>(w.pk_dh), w.cin_g / 128, 128, w.cout_g, w.taps, (int64_t)128 * w.taps,
+                      w.taps, (int64_t)w.cin_g * w.taps, 1, 1 | 4, s);
   return queue_pack(t, P[w.pidx], reinterpret_cast<float*>(w.pk_dh), w.groups, w.cin_g, w.cout_g, w.taps,
                     (int64_t)w.cout_g * w.cin_g * w.taps, w.taps, (int64_t)w.cin_g * w.taps, 1, 1 | 4, s, nullptr, w.src_gmod);
 }
@@ -595,6 +619,11 @@ static int queue_decoder_packs(NefPlan* p, NefPackTable& t, const float* const* 
       const ConvW& w = p->decw[0];
       RUN(queue_pack(t, P[w.pidx], reinterpret_cast<float*>(w.pk_h), 1, 128, 256, 3, 0, 256 * 3, 3, 1, 4, s, ns));
       RUN(queue_pack(t, P[w.pidx], reinterpret_cast<float*>(p->dec1_lo_h), 1, 128, 256, 3, 0, 256 * 3, 3, 1, 4 | 2, s, ns));
+      continue;
+    }
+    if (i > 0 && p->dec_f16 && !fold) {
+      const ConvW& w = p->decw[i];
+      RUN(queue_pack(t, P[w.pidx], reinterpret_cast<float*>(w.pk_h), 1, w.cout_g, w.cin_g, 3, 0, (int64_t)w.cin_g * 3, 3, 1, 4, s, ns));
       continue;
     }
     RUN(pack_fwd(t, p->decw[i], P, s, ns));
@@ -704,6 +733,9 @@ static int decoder_fwd(NefPlan* p, const float* const* P, int slot, int lslot, c
       c.term16(u0h, u0.cs, 0, 0, 256, 3, l.w->pk_h);
       if (g_dec1_terms >= 2) c.term16(u0loh, u0.cs, 0, 0, 256, 3, l.w->pk_h);
       if (g_dec1_terms >= 3) c.term16(u0h, u0.cs, 0, 0, 256, 3, p->dec1_lo_h);
+    } else if (p->dec_f16) {     // the post-BatchNorm activations exist as fp16 copies only
+      const void* in16[4] = {nullptr, d.a1_h, d.u1_h, d.a3_h};
+      c.term16(in16[i], l.in.cs, 0, 0, l.w->cin_g, 3, l.w->pk_h);
     } else {
       c.term(l.in, 0, 0, l.w->cin_g, 3, l.w->pk_f);
       if (i == 0) {  // split precision: x_hi w_hi + x_lo w_hi + x_hi w_lo  (this layer dominates the TF32 error budget)
@@ -717,6 +749,12 @@ static int decoder_fwd(NefPlan* p, const float* const* P, int slot, int lslot, c
     RUN(bn_finalize(d.bn[i], l.w->cout_g, l.count, P[l.bnp], P[l.bnp + 1], const_cast<float*>(P[l.bnp + 2]),
                     const_cast<float*>(P[l.bnp + 3]),
                     reinterpret_cast<int64_t*>(const_cast<float*>(P[l.bnp + 4])), training, s));
+    if (p->dec_f16) {
+      if (i == 0) RUN(bn_relu_h(d.c1, d.bn[0].scale, d.bn[0].shift, d.a1_h, d.a1, 0, s));
+      if (i == 1) RUN(bn_relu_h(d.c2, d.bn[1].scale, d.bn[1].shift, d.u1_h, d.u1, 1, s));
+      if (i == 2) RUN(bn_relu_h(d.c3, d.bn[2].scale, d.bn[2].shift, d.a3_h, d.a3, 0, s));
+      continue;
+    }
     if (i == 0) RUN(bn_relu(d.c1, d.bn[0].scale, d.bn[0].shift, d.a1, 0, s));
     if (i == 1) RUN(bn_relu(d.c2, d.bn[1].scale, d.bn[1].shift, d.u1, 1, s));
     if (i == 2) RUN(bn_relu(d.c3, d.bn[2].scale, d.bn[2].shift, d.a3, 0, s));
@@ -803,6 +841,9 @@ extern "C" int nef_forward(NefPlan* p, const NefForwardArgs* a, nef_stream_t sv)
   packs.n = 0;
   p->fwd_f16 = g_fwd_f16 && g_conv_impl == 1;
   p->bwd_f16 = p->fwd_f16 && g_bwd_f16 && a->save_for_backward;
+  // fp16 decoder: training-mode BatchNorm (with running statistics and a backward the conv biases need gradients from the
+  // fp32 tensors; inference without a backward folds the BatchNorm and takes its own path)
+  p->dec_f16 = p->fwd_f16 && g_dec_f16 && a->bn_training && (p->bwd_f16 || !a->save_for_backward);
   // variant 2: the biases its grouped epilogues index per group are shared by the leads -> one copy per lead
   const float* b_z1 = P[P_Z1 + 3];
   const float* b_z2c1 = P[P_Z2C1 + 3];
@@ -906,6 +947,7 @@ extern "C" int nef_gen_ecg(NefPlan* p, const float* const* P, const float* z1, c
   NefPackTable packs;
   packs.n = 0;
   p->fwd_f16 = g_fwd_f16 && g_conv_impl == 1;
+  p->dec_f16 = false;
   RUN(queue_decoder_packs(p, packs, P, true, s));   // gen_ecg runs the module in eval mode (model_nefnet.py:197)
   RUN(nef_pack_weights_batch(&packs, s));
   RUN(nef_ncl_to_cbl4(z1, reinterpret_cast<float*>(p->z1.p), p->B, p->C1, p->L4, 0, sv));
@@ -1040,6 +1082,50 @@ static int decoder_bwd(NefPlan* p, const float* const* P, float* const* Gd, int 
   return 0;
 }
 
+// The same on the fp16 decoder dataflow (dec_f16): the gradients between the layers are loss-scaled fp16 copies only, every
+// data / weight gradient runs in kind::f16 on them and on the fp16 activation copies a1_h / u1_h / a3_h / u0_h.
+static int decoder_bwd_h(NefPlan* p, const float* const* P, float* const* Gd, int slot, const float* dout, cudaStream_t s) {
+  DecBufs& d = p->dec[slot];
+  const int B = p->B;
+  const double n2 = (double)B * p->L2, n1 = (double)B * p->L;
+  const float* ls = p->lscale;
+  const float* inv = ls + 1;
+  auto g = [&](int i) { return Gd[i]; };
+  // data gradient of decoder convolution i from the fp16 gradient copy gin16 (row space `space`) into the fp16 copy gout16
+  auto dgrad = [&](int i, const T4& space, const void* gin16, void* gout16, const T4& outgeom) {
+    const ConvW& w = p->decw[i];
+    CD c(1, w.cin_g, space);
+    c.term16(gin16, space.cs, 0, 0, w.cout_g, 3, w.pk_dh).out(outgeom, 0, 0).y16s(gout16, ls);
+    c.d.acc_scale = inv;
+    c.d.y = nullptr;
+    return c.run(s);
+  };
+  // output layer + bn4 statistics (fp32 g4, unscaled), then bn4's backward into the scaled fp16 copy
+  RUN(dec_out_bwd(d.c4, d.bn[3], P[P_OUT_W], d.out, dout, p->dg4, g(P_OUT_W), g(P_OUT_B), s));
+  RUN(bnbwd_apply_h(&p->dg4, nullptr, d.c4, d.bn[3], P[P_DEC3 + 9], n1, p->dg4_h, g(P_DEC3 + 9), g(P_DEC3 + 10), 1, ls, s));
+  RUN(wgrad_h(p->dg4_h, p->dg4, 0, 0, d.a3_h, d.a3, 0, 0, p->decw[3], g(P_DEC3 + 7), inv, s));
+  RUN(dgrad(3, p->dg4, p->dg4_h, p->dg3_h, p->dg3));
+  RUN(bnbwd_stats_h(p->dg3_h, d.c3, d.bn[2], s));
+  RUN(bnbwd_apply_h(nullptr, p->dg3_h, d.c3, d.bn[2], P[P_DEC3 + 2], n1, p->dg3_h, g(P_DEC3 + 2), g(P_DEC3 + 3), 1, ls, s));
+  RUN(wgrad_h(p->dg3_h, p->dg3, 0, 0, d.u1_h, d.u1, 0, 0, p->decw[2], g(P_DEC3 + 0), inv, s));
+  RUN(dgrad(2, p->dg3, p->dg3_h, p->du1_h, p->du1));
+  RUN(up_adjoint_h(p->du1_h, p->du1, p->dg2_h, p->dg2, s));
+  RUN(bnbwd_stats_h(p->dg2_h, d.c2, d.bn[1], s));
+  RUN(bnbwd_apply_h(nullptr, p->dg2_h, d.c2, d.bn[1], P[P_DEC1 + 9], n2, p->dg2_h, g(P_DEC1 + 9), g(P_DEC1 + 10), 1, ls, s));
+  RUN(wgrad_h(p->dg2_h, p->dg2, 0, 0, d.a1_h, d.a1, 0, 0, p->decw[1], g(P_DEC1 + 7), inv, s));
+  RUN(dgrad(1, p->dg2, p->dg2_h, p->dg1_h, p->dg1));
+  RUN(bnbwd_stats_h(p->dg1_h, d.c1, d.bn[0], s));
+  RUN(bnbwd_apply_h(nullptr, p->dg1_h, d.c1, d.bn[0], P[P_DEC1 + 2], n2, p->dg1_h, g(P_DEC1 + 2), g(P_DEC1 + 3), 1, ls, s));
+  RUN(wgrad_h(p->dg1_h, p->dg1, 0, 0, p->u0_h[slot], p->u0[slot], 0, 0, p->decw[0], g(P_DEC1 + 0), inv, s));
+  {
+    CD c(2, 128, p->dg1);  // 256 output channels as two sub-groups reading the same input; fp32 result for latent_bwd
+    c.term16(p->dg1_h, p->dg1.cs, 0, 0, 128, 3, p->decw[0].pk_dh).out(p->du0[slot], 0, 32).round();
+    c.d.acc_scale = inv;
+    RUN(c.run(s));
+  }
+  return 0;
+}
+
 static int zero_t4(const T4& t, cudaStream_t s) {
   cudaError_t e = cudaMemsetAsync(t.p, 0, (size_t)(t.C / 4) * t.cs * sizeof(float4), s);
   NEF_REQUIRE(e == cudaSuccess, "memset failed: %s", cudaGetErrorString(e));
@@ -1060,7 +1146,8 @@ extern "C" int nef_backward(NefPlan* p, const NefBackwardArgs* a, nef_stream_t s
   packs.n = 0;
   const bool f16 = p->bwd_f16 && g_conv_impl == 1;
   RUN(for_all_convw(p, [&](const ConvW& w) {
-    if (f16 && w.pk_dh) return pack_dgrad_h(packs, w, P, s);   // the TF32 data-gradient packing of these layers is not read
+    const bool dec = &w >= p->decw && &w < p->decw + 4;
+    if (f16 && w.pk_dh && (!dec || p->dec_f16)) return pack_dgrad_h(packs, w, P, s);   // the TF32 data-gradient packing of these layers is not read
     return pack_dgrad(packs, w, P, s);
   }));
   for (int t = 0; t < 2; ++t)  // ConvTranspose dgrad: dx[l] = sum_t W_t^T dy[2l + t] ; N' = ci (128), K' = co (64)
@@ -1074,7 +1161,7 @@ extern "C" int nef_backward(NefPlan* p, const NefBackwardArgs* a, nef_stream_t s
   const float* ls = p->lscale;
   if (f16) RUN(grad_loss_scale(a->dout, a->dout_p, a->dout_l, (long)B * p->L, p->lscale, s));
   for (int k = 0; k < 3; ++k) {
-    if (douts[k]) RUN(decoder_bwd(p, P, Gd, k, douts[k], s));
+    if (douts[k]) RUN((f16 && p->dec_f16) ? decoder_bwd_h(p, P, Gd, k, douts[k], s) : decoder_bwd(p, P, Gd, k, douts[k], s));
     else RUN(zero_t4(p->du0[k], s));
   }
   // latents
@@ -1260,8 +1347,9 @@ static bool find_tensor(const NefPlan* p, const char* name, NamedTensor* out) {
     const std::string pre = "dec" + std::to_string(k) + ".";
     const T4* ts[7] = {&d.c1, &d.a1, &d.c2, &d.u1, &d.c3, &d.a3, &d.c4};
     const char* nm[7] = {"decoder.1.0", "a1", "decoder.1.3", "u1", "decoder.3.0", "a3", "decoder.3.3"};
+    const void* hs[7] = {nullptr, d.a1_h, nullptr, d.u1_h, nullptr, d.a3_h, nullptr};
     for (int i = 0; i < 7; ++i)
-      if (n == pre + nm[i]) { out->t = ts[i]; return true; }
+      if (n == pre + nm[i]) { out->t = ts[i]; if (p->dec_f16) out->h16 = hs[i]; return true; }
     if (n == pre + "u0") { out->t = &p->u0[k]; return true; }
     for (int i = 0; i < 4; ++i) {
       const std::string b = pre + "bn" + std::to_string(i) + ".";

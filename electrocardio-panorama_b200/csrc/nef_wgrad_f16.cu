@@ -142,6 +142,9 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_f16_kernel(const __grid_cons
   const int g = blockIdx.z, tile = blockIdx.x;
   const int ntap = d.taps;
   const int xch = dcols >> 3;   // 8-channel chunks of X staged
+  // 8-channel chunks of dY staged.  cout_g = 64: the MMA still spans M = 128 (an M = 64 MMA runs at the same rate), its upper
+  // 64 rows read the unused half of the staged dY region and their accumulator lanes are never drained
+  const int ych = d.cout_g >> 3;
   const long rbeg = (long)blockIdx.y * rows_per_split;
   const long rend = min(rows_main, rbeg + rows_per_split);
   const int nstage = rend > rbeg ? (int)((rend - rbeg) / ROWS) : 0;
@@ -159,26 +162,26 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_f16_kernel(const __grid_cons
   const uint32_t tmem = *tmem_slot;
 
   if (warp >= 1 && warp <= NPROD) {
-    // ===== copy producers: copy id = pw + NPROD * lane; ids [0, 16) are dY chunks, [16, 16 + xch) are X chunks =====
+    // ===== copy producers: copy id = pw + NPROD * lane; ids [0, ych) are dY chunks, [ych, ych + xch) are X chunks =====
     const int pw = warp - 1;
     const int id = pw + NPROD * lane;
-    const int ncopy = YCH + xch;
+    const int ncopy = ych + xch;
     const uint32_t xbytes = (uint32_t)(ROWS + ntap - 1) * 16;
     uint32_t my_bytes = 0;   // bytes this warp lands per stage (uniform)
     for (int l = 0; l < 32; ++l) {
       const int i = pw + NPROD * l;
-      if (i < YCH) my_bytes += YP;
+      if (i < ych) my_bytes += YP;
       else if (i < ncopy) my_bytes += xbytes;
     }
     const uint4* src = nullptr;
     uint32_t dst_off = 0, bytes = 0;
-    if (id < YCH) {
+    if (id < ych) {
       src = dy16 + (long)((d.dy_c4_off >> 1) + g * (d.dy_c4_gstride >> 1) + id) * d.dy_cstride;
       dst_off = (uint32_t)id * YP;
       bytes = YP;
     } else if (id < ncopy) {
-      src = x16 + (long)((d.x_c4_off >> 1) + g * (d.x_c4_gstride >> 1) + tile * xch + (id - YCH)) * d.x_cstride + d.tap_off;
-      dst_off = YBYTES + (uint32_t)(id - YCH) * XP;
+      src = x16 + (long)((d.x_c4_off >> 1) + g * (d.x_c4_gstride >> 1) + tile * xch + (id - ych)) * d.x_cstride + d.tap_off;
+      dst_off = YBYTES + (uint32_t)(id - ych) * XP;
       bytes = xbytes;
     }
     int st = 0, ph = 0;
@@ -226,7 +229,7 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_f16_kernel(const __grid_cons
       if (elect_one()) tc_commit(acc_full);
       __syncwarp();
     }
-  } else if (nstage > 0) {
+  } else if (nstage > 0 && (warp & 3) * 32 < d.cout_g) {
     // ===== warps 4..7: drain the accumulators (TMEM lane quarter = warp % 4), scaled fp32 RED into the gradient =====
     const int q = warp & 3;
     const int lr = q * 32 + lane;   // output channel
@@ -280,7 +283,7 @@ extern "C" void nef_tc_note_dispatch(int which);
 // dy16 / x16: the fp16 copies, `half8 [C/8][cstride rows]`, addressed from the same row origin as the fp32 tensors.
 extern "C" int nef_gconv_wgrad_f16(const NefWgradDesc* d, const void* dy16, const void* x16, const float* out_scale, nef_stream_t s) {
   NEF_REQUIRE(d && dy16 && x16, "nef_gconv_wgrad_f16: null argument");
-  NEF_REQUIRE(d->cout_g == 128, "nef_gconv_wgrad_f16: cout_g must be 128 (got %d)", d->cout_g);
+  NEF_REQUIRE(d->cout_g == 128 || d->cout_g == 64, "nef_gconv_wgrad_f16: cout_g must be 64 or 128 (got %d)", d->cout_g);
   NEF_REQUIRE(d->cin_g % 64 == 0 && d->taps >= 1 && d->taps <= 7, "nef_gconv_wgrad_f16: cin_g %% 64 == 0 and 1..7 taps required");
   NEF_REQUIRE(((d->dy_c4_off | d->dy_c4_gstride | d->x_c4_off | d->x_c4_gstride) & 1) == 0,
               "nef_gconv_wgrad_f16: chunk offsets and group strides must be even (8-channel fp16 chunks)");

@@ -112,6 +112,7 @@ SIGNATURES = {
                                C.c_void_p]),
     "nef_set_dec1_terms": (C.c_int, [C.c_int]),
     "nef_set_fwd_f16": (C.c_int, [C.c_int]),
+    "nef_set_dec_f16": (C.c_int, [C.c_int]),
     "nef_psnr": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                            C.c_void_p, C.c_void_p]),
     "nef_prepare_scratch_bytes": (C.c_size_t, [C.c_int]),

@@ -45,6 +45,10 @@ int nef_set_dec1_terms(int n);
 /* 1 (default) = the encoder's forward convolutions read fp16 operand copies (NefConvTerm.x_f16); 0 = TF32 operands
  * everywhere.  Measurement hook. */
 int nef_set_fwd_f16(int on);
+/* 1 (default) = fp16 decoder dataflow in training (post-BatchNorm activations kept as fp16 operand copies only, decoder
+ * convolutions 2-4 and all decoder data / weight gradients in kind::f16 on loss-scaled fp16 gradient copies); 0 = the
+ * TF32 decoder.  Measurement hook. */
+int nef_set_dec_f16(int on);
 /* Test hook: 1 = round nothing to TF32 (with conv impl 0 the whole path is then plain fp32 and can be
  * compared tightly with the fp32 oracle); 0 = production behaviour.  Synchronous, call between steps. */
 int nef_set_exact_fp32(int on);
@@ -191,7 +195,7 @@ int nef_gconv_wgrad(const NefWgradDesc* d, nef_stream_t s);
 /* The same weight gradient from fp16 operand copies (`half8 [C/8][rows]`: 8 channels per 16-byte row, the layout of
  * NefConvDesc.y16, addressed from the same row origin as the fp32 tensors), read by the tensor core as the bulk copy lands
  * them (MN-major, no shared-memory re-tile pass).  d gives the geometry, dw and its strides (d->dy, d->x, d->db are not
- * read; chunk offsets / group strides must be even); cout_g must be 128, cin_g a multiple of 64.  The accumulated block is
+ * read; chunk offsets / group strides must be even); cout_g must be 64 or 128, cin_g a multiple of 64.  The accumulated block is
  * multiplied by out_scale[0] (device scalar, NULL = 1: the inverse of the loss scale the dy16 copy carries) before the
  * fp32 accumulation into dw.  tcgen05 kind::f16: 11-bit significands like TF32, twice the rate, half the operand bytes. */
 int nef_gconv_wgrad_f16(const NefWgradDesc* d, const void* dy16, const void* x16, const float* out_scale, nef_stream_t s);

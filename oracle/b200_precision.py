@@ -11,7 +11,7 @@ fp32 oracle the production gradients differ by several percent in L2 whatever th
 
   conv(kind, x, w, b)   operands as the tensor core sees them: 'tf32' -> weights rounded to TF32 (activations arrive rounded
                         from ``store``); 'fp16' -> both operands additionally through fp16 (saturating, RN-even: the encoder
-                        forward); 'fp32' -> untouched (stem and output kernels on CUDA cores; the decoder's first
+                        forward; 'dec' = the same for the decoder's convolutions 2-4 when dec_f16); 'fp32' -> untouched (stem and output kernels on CUDA cores; the decoder's first
                         convolution is evaluated split-precision, x_hi w_hi + x_lo w_hi + x_hi w_lo, i.e. to ~2^-22)
   pattern(name)         optional observed (value != 0) pattern of a ReLU output, see B200Precision
   store(x)              a stored activation: rounded to TF32
@@ -69,8 +69,9 @@ class B200Precision:
     ('<block>.h', '<block>.y', 'dec<k>.<stage>.<bn>'); the oracle then multiplies by it instead of applying ReLU (and the
     dropout keep-mask, which the pattern of a block's h contains).  acts: filled with the named intermediates of a run."""
 
-    def __init__(self, fwd_f16: bool = True, patterns=None, record: bool = False):
+    def __init__(self, fwd_f16: bool = True, patterns=None, record: bool = False, dec_f16: bool = True):
         self.fwd_f16 = fwd_f16
+        self.dec_f16 = dec_f16 and fwd_f16     # decoder convolutions 2-4 on fp16 operand copies (nef_set_dec_f16)
         self.patterns = patterns or {}
         self.acts = {} if record else None
 
@@ -84,7 +85,7 @@ class B200Precision:
     def _ops(self, kind, x, w):
         if kind == "fp32":
             return x, w
-        if kind == "fp16" and self.fwd_f16:
+        if (kind == "fp16" and self.fwd_f16) or (kind == "dec" and self.dec_f16):
             return _STE.apply(x, 1), _f16w(w)
         return x, _STE.apply(w, 0)
 

@@ -216,7 +216,8 @@ def theta_features(theta: torch.Tensor) -> torch.Tensor:
 # ----------------------------------------------------------------------------------------
 def _conv(prec, kind, x, w, b=None, **kw):
     """F.conv1d as the reference evaluates it (fp32), or as `prec` models the device's operand rounding.
-    kind: 'fp16' (encoder k7 convs), 'tf32' (every other grouped / decoder conv), 'fp32' (CUDA-core / split-precision)."""
+    kind: 'fp16' (encoder k7 convs), 'dec' (decoder convolutions 2-4: fp16 operand copies in the fp16 decoder dataflow, else
+    TF32), 'tf32' (every other grouped conv), 'fp32' (CUDA-core / split-precision)."""
     if prec is None:
         return F.conv1d(x, w, b, **kw)
     return prec.conv(kind, x, w, b, **kw)
@@ -361,7 +362,7 @@ def decoder(P, lat, training, stats_out=None, prec=None, name="dec"):
         for conv, bn in (("0", "1"), ("3", "4")):
             pre = f"{stage}.double_conv."
             # the device evaluates the first convolution split-precision (x_hi w_hi + x_lo w_hi + x_hi w_lo): fp32-like
-            h = _pre(prec, _conv(prec, "fp32" if first else "tf32", h, P[pre + conv + ".weight"], P[pre + conv + ".bias"],
+            h = _pre(prec, _conv(prec, "fp32" if first else "dec", h, P[pre + conv + ".weight"], P[pre + conv + ".bias"],
                                  padding=1))
             _obs(prec, f"{name}.{stage}.{conv}", h)
             first = False
