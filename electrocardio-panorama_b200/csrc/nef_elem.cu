@@ -717,7 +717,7 @@ __global__ void __launch_bounds__(256) latent_fwd_kernel(const LatentArgs a) {
         v = v * qv;
         const float4 hi = tf32_rn4(v);
         const float4 lo = make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w);
-        if (ok) *a.u0[k3].at(latc, b, 2 * t0 + u) = hi;
+        if (ok && !a.skip_u032) *a.u0[k3].at(latc, b, 2 * t0 + u) = hi;
         if (a.u0h[k3]) {
           // even lane (channels 0..3 of the row) stores the fp16 row of hi, odd lane (channels 4..7) the row of lo
           const uint32_t hx = f16x2_sat(hi.x, hi.y), hy = f16x2_sat(hi.z, hi.w);
@@ -771,6 +771,7 @@ __global__ void __launch_bounds__(256, 3) latent_bwd_kernel(const LatentBwdArgs 
   float4 dq = f4zero();
   const int L2 = 2 * L4;
   const float s16 = (a.gz1_h && a.s16) ? __ldg(a.s16) : 1.f;
+  const float inv16 = a.s16 ? __ldg(a.s16 + 1) : 1.f;   // 1 / S of the loss-scaled fp16 input gradients du0h
   for (int t0 = 0; t0 < L4; t0 += LB_TL) {
    const int nl = min(LB_TL, L4 - t0);
    for (int l = t0 + tid; l < t0 + nl; l += 256) {
@@ -779,6 +780,20 @@ __global__ void __launch_bounds__(256, 3) latent_bwd_kernel(const LatentBwdArgs 
     for (int k3 = 0; k3 < 3; ++k3) {
       if (a.direct) {   // the latent gradients themselves are given (Model_nefnet2: upq_adjoint and two convolutions ran before)
         dk[k3] = *a.dlat[k3].at(latc, b, l);
+        continue;
+      }
+      if (a.du0h[k3]) {   // loss-scaled fp16 copy: this block's 4 channels are one half of each 16-byte row
+        const uint2* du = reinterpret_cast<const uint2*>(reinterpret_cast<const uint4*>(a.du0h[k3]) + (long)(latc >> 1) * a.du0[k3].cs +
+                                                         a.du0[k3].row(b, 0)) + (latc & 1);
+        auto ld = [&](int r) {
+          const uint2 h = __ldg(du + 2 * r);
+          const float2 x = __half22float2(*reinterpret_cast<const __half2*>(&h.x)), y = __half22float2(*reinterpret_cast<const __half2*>(&h.y));
+          return make_float4(x.x, x.y, y.x, y.y);
+        };
+        float4 d = ld(2 * l) * 0.75f + ld(2 * l + 1) * 0.75f;
+        d = d + ld(l + 1 < L4 ? 2 * l + 2 : L2 - 1) * 0.25f;
+        d = d + ld(l >= 1 ? 2 * l - 1 : 0) * 0.25f;
+        dk[k3] = d * inv16;
         continue;
       }
       const float4* du = a.du0[k3].at(latc, b, 0);
@@ -1288,9 +1303,13 @@ int up_adjoint_h(const void* du16, T4 du, void* da16, T4 da, cudaStream_t s) {
   return 0;
 }
 
-// BatchNorm backward pass 1 on an fp16 gradient copy (times the loss scale S): s1, s2 accumulate in the same scaled units
-// grid (segment groups, C/8); block 256
-__global__ void __launch_bounds__(256) bnbwd_stats_h_kernel(const uint4* __restrict__ da16, T4 c, BnLayer bn, int seg_per_block) {
+// BatchNorm backward pass 1 on an fp16 gradient copy (times the loss scale S): s1, s2 accumulate in the same scaled units.
+// grid (segment groups, C/8); block 256; two rows per thread and iteration (all six loads in flight together).
+// UPADJ: the gradient is not read but built -- the adjoint of the x2 linear upsampling of du16 (C, 2n), stored to da16 on
+// the way (up_adjoint_h fused with this pass: the BatchNorm behind the upsampled tensor).
+template <bool UPADJ>
+__global__ void __launch_bounds__(256) bnbwd_stats_h_kernel(const uint4* __restrict__ da16, T4 c, BnLayer bn, int seg_per_block,
+                                                            const uint4* __restrict__ du16, T4 du, uint4* __restrict__ da_out) {
   __shared__ float red[8][16];
   const int c8 = blockIdx.y;
   float sc[8], sh[8], mu[8], is[8], s1[8], s2[8];
@@ -1300,22 +1319,48 @@ __global__ void __launch_bounds__(256) bnbwd_stats_h_kernel(const uint4* __restr
     sc[k] = bn.scale[ch]; sh[k] = bn.shift[ch]; mu[k] = bn.mean[ch]; is[k] = bn.invstd[ch];
     s1[k] = 0.f; s2[k] = 0.f;
   }
+  const int n = c.L;
   const int b0 = blockIdx.x * seg_per_block, b1 = min(c.B, b0 + seg_per_block);
   for (int b = b0; b < b1; ++b) {
     const float4* cp0 = c.at(2 * c8, b, 0);
     const float4* cp1 = c.at(2 * c8 + 1, b, 0);
-    const uint4* dp = da16 + (long)c8 * c.cs + c.row(b, 0);
-    for (int l = threadIdx.x; l < c.L; l += 256) {
-      const float4 x0 = cp0[l], x1 = cp1[l];
-      float4 g0, g1;
-      h8_unpack(dp[l], g0, g1);
+    const long r0 = (long)c8 * c.cs + c.row(b, 0);
+    const uint4* up = UPADJ ? du16 + (long)c8 * du.cs + du.row(b, 0) : nullptr;
+    for (int l = threadIdx.x; l < n; l += 512) {
+      const int l2 = l + 256;
+      const bool two = l2 < n;
+      float4 x0[2], x1[2], g0[2], g1[2];
+      x0[0] = cp0[l]; x1[0] = cp1[l];
+      x0[1] = two ? cp0[l2] : f4zero(); x1[1] = two ? cp1[l2] : f4zero();
+      if (!UPADJ) {
+        const uint4 ha = da16[r0 + l], hb = two ? da16[r0 + l2] : make_uint4(0u, 0u, 0u, 0u);
+        h8_unpack(ha, g0[0], g1[0]);
+        h8_unpack(hb, g0[1], g1[1]);
+      } else {
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const float x = k < 4 ? f4get(x0, k) : f4get(x1, k - 4);
-        const float gv = k < 4 ? f4get(g0, k) : f4get(g1, k - 4);
-        const float g = (x * sc[k] + sh[k]) > 0.f ? gv : 0.f;
-        s1[k] += g;
-        s2[k] += g * (x - mu[k]) * is[k];
+        for (int j = 0; j < 2; ++j) {
+          const int ll = j ? l2 : l;
+          if (j && !two) { g0[1] = f4zero(); g1[1] = f4zero(); break; }
+          float4 m0, m1, a0, a1, e0, e1, q0, q1;
+          h8_unpack(up[2 * ll], a0, a1);
+          h8_unpack(up[2 * ll + 1], e0, e1);
+          h8_unpack(ll >= 1 ? up[2 * ll - 1] : up[0], m0, m1);
+          h8_unpack(ll + 1 < n ? up[2 * ll + 2] : up[2 * n - 1], q0, q1);
+          const uint4 packed = h8_pack((a0 + e0) * 0.75f + (m0 + q0) * 0.25f, (a1 + e1) * 0.75f + (m1 + q1) * 0.25f);
+          da_out[r0 + ll] = packed;
+          h8_unpack(packed, g0[j], g1[j]);   // the statistics see the stored (rounded) gradient, as the separate pass would
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float x = k < 4 ? f4get(x0[j], k) : f4get(x1[j], k - 4);
+          const float gv = k < 4 ? f4get(g0[j], k) : f4get(g1[j], k - 4);
+          const float g = (x * sc[k] + sh[k]) > 0.f ? gv : 0.f;
+          s1[k] += g;
+          s2[k] += g * (x - mu[k]) * is[k];
+        }
       }
     }
   }
@@ -1336,12 +1381,24 @@ __global__ void __launch_bounds__(256) bnbwd_stats_h_kernel(const uint4* __restr
     else atomicAdd(bn.s2 + c8 * 8 + threadIdx.x - 8, (double)v);
   }
 }
-int bnbwd_stats_h(const void* da16, T4 c, const BnLayer& bn, cudaStream_t s) {
-  int spb = (int)(((long)c.B * (c.C / 8) + 148 * 8 - 1) / (148 * 8));
+static inline dim3 stats_h_grid(const T4& c, int* spb_out) {
+  int spb = (int)(((long)c.B * (c.C / 8) + 148 * 16 - 1) / (148 * 16));
   if (spb < 1) spb = 1;
-  dim3 grid((c.B + spb - 1) / spb, c.C / 8);
-  bnbwd_stats_h_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const uint4*>(da16), c, bn, spb);
+  *spb_out = spb;
+  return dim3((c.B + spb - 1) / spb, c.C / 8);
+}
+int bnbwd_stats_h(const void* da16, T4 c, const BnLayer& bn, cudaStream_t s) {
+  int spb;
+  const dim3 grid = stats_h_grid(c, &spb);
+  bnbwd_stats_h_kernel<false><<<grid, 256, 0, s>>>(reinterpret_cast<const uint4*>(da16), c, bn, spb, nullptr, c, nullptr);
   NEF_CHECK_LAUNCH("bnbwd_stats_h_kernel");
+  return 0;
+}
+int up_adjoint_stats_h(const void* du16, T4 du, void* da16, T4 c, const BnLayer& bn, cudaStream_t s) {
+  int spb;
+  const dim3 grid = stats_h_grid(c, &spb);
+  bnbwd_stats_h_kernel<true><<<grid, 256, 0, s>>>(nullptr, c, bn, spb, reinterpret_cast<const uint4*>(du16), du, reinterpret_cast<uint4*>(da16));
+  NEF_CHECK_LAUNCH("up_adjoint_stats_h_kernel");
   return 0;
 }
 

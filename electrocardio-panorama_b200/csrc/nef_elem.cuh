@@ -65,6 +65,7 @@ struct LatentArgs {
   int write_lat;          // 0: lat already built, only (re)build u0 from it with another q
   int skip_u0;            // 1: only build the latents (Model_nefnet2 convolves them before the query scaling)
   int round_lat;          // 1: the stored latents are TF32-rounded (they feed a tensor-core convolution)
+  int skip_u032;          // 1: the fp32 u0 is not stored (needs u0h: the decoder reads the fp16 copies only)
   int store_mask;         // with write_lat: bit (2 k + half) = store half (0: z1 channels, 1: z2 channels) of lat[k].
                           //   training needs only the z2 halves of lat[0] and lat[2] (latent_bwd rebuilds the rest from z1);
                           //   the extra views of the test phase / gen_ecg re-read both halves of lat[0]
@@ -80,6 +81,7 @@ struct LatentBwdArgs {
   float* dq;              // out (B, 256), overwritten
   int direct;             // 1: dlat[k] ARE the latent gradients (no upsample / query adjoint, dq untouched); 0: from du0
   T4 dlat[3];
+  const void* du0h[3];    // optional: read d u0_k from these loss-scaled fp16 copies (geometry of du0[k], times s16[0]; s16[1] = 1 / S)
 };
 int latent_bwd(const LatentBwdArgs& a, cudaStream_t s);
 struct UpqAdjArgs { T4 du0[3]; T4 lat2[3]; T4 dlat2[3]; const float* q; int q_stride; float* dq; };
@@ -102,6 +104,8 @@ int bnbwd_apply(T4 da, T4 c, const BnLayer& bn, const float* gamma, double count
 int bn_relu_h(T4 c, const float* scale, const float* shift, void* out16, T4 og, int upsample, cudaStream_t s);
 int up_adjoint_h(const void* du16, T4 du, void* da16, T4 da, cudaStream_t s);
 int bnbwd_stats_h(const void* da16, T4 c, const BnLayer& bn, cudaStream_t s);
+// up_adjoint_h and bnbwd_stats_h in one pass: da16 (geometry of c) = adjoint of the upsampling of du16, statistics of da16
+int up_adjoint_stats_h(const void* du16, T4 du, void* da16, T4 c, const BnLayer& bn, cudaStream_t s);
 // da: fp32 incoming gradient (unscaled) or nullptr to read da16 (scaled); dc16 may alias da16
 int bnbwd_apply_h(const T4* da, const void* da16, T4 c, const BnLayer& bn, const float* gamma, double count, void* dc16,
                   float* dgamma, float* dbeta, int training, const float* lscale, cudaStream_t s);

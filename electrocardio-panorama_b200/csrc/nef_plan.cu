@@ -265,6 +265,8 @@ struct NefPlan {
   T4 dg4, dg3, du1, dg2, dg1, du0[3];
   void *dg4_h, *dg3_h, *du1_h, *dg2_h, *dg1_h;   // loss-scaled fp16 gradient copies of the decoder backward (dec_f16)
   bool dec_f16;                     // this forward / backward pair runs the fp16 decoder dataflow
+  bool u0_f16_only;                 // the decoder inputs u0 of this forward exist as fp16 copies (u0_h, u0lo_h) only
+  void* du0_h[3];                   // loss-scaled fp16 gradients of the decoder inputs (dec_f16, variant 1)
   float *ds_in, *dq;
   double* bn_stats;       // BatchNorm backward accumulators (s1, s2) of all layers, contiguous
   size_t bn_stats_count;
@@ -391,6 +393,7 @@ static void carve(NefPlan* p, bool dry) {
   p->gz2c = c.t4(C1, p->win.Lw); p->ghz = c.t4(C1, p->win.Lw); p->gxw = c.t4(64 * G, p->win.Lw);
   p->dg4 = c.t4(64, L); p->dg3 = c.t4(64, L); p->du1 = c.t4(128, L); p->dg2 = c.t4(128, L2); p->dg1 = c.t4(128, L2);
   for (int k = 0; k < 3; ++k) p->du0[k] = c.t4(256, L2);
+  for (int k = 0; k < 3; ++k) p->du0_h[k] = c.take(((size_t)(256 / 8) * p->du0[k].cs + NEF_GUARD_ROWS) * 16);
   p->dg4_h = c.take(((size_t)(64 / 8) * p->dg4.cs + NEF_GUARD_ROWS) * 16);
   p->dg3_h = c.take(((size_t)(64 / 8) * p->dg3.cs + NEF_GUARD_ROWS) * 16);
   p->du1_h = c.take(((size_t)(128 / 8) * p->du1.cs + NEF_GUARD_ROWS) * 16);
@@ -781,6 +784,7 @@ static int latents_to_decoders(NefPlan* p, const float* const* P, const float* q
     la.u0h[k] = p->fwd_f16 ? p->u0_h[k] : nullptr;
     la.u0loh[k] = p->fwd_f16 ? p->u0lo_h[k] : nullptr;
   }
+  la.skip_u032 = p->u0_f16_only ? 1 : 0;
   if (!only_views) {
     RUN(angular_fwd(query_theta, P[P_MLP2_W], P[P_MLP2_B], p->q, B, 256, s));
     la.q = p->q; la.q_stride = 256; la.n_lat = 3; la.write_lat = 1;
@@ -844,6 +848,8 @@ extern "C" int nef_forward(NefPlan* p, const NefForwardArgs* a, nef_stream_t sv)
   // fp16 decoder: training-mode BatchNorm (with running statistics and a backward the conv biases need gradients from the
   // fp32 tensors; inference without a backward folds the BatchNorm and takes its own path)
   p->dec_f16 = p->fwd_f16 && g_dec_f16 && a->bn_training && (p->bwd_f16 || !a->save_for_backward);
+  // the fp32 u0 has readers only without the fp16 forward (first decoder convolution) or in the TF32 decoder backward
+  p->u0_f16_only = p->fwd_f16 && (p->dec_f16 || !a->save_for_backward);
   // variant 2: the biases its grouped epilogues index per group are shared by the leads -> one copy per lead
   const float* b_z1 = P[P_Z1 + 3];
   const float* b_z2c1 = P[P_Z2C1 + 3];
@@ -948,6 +954,7 @@ extern "C" int nef_gen_ecg(NefPlan* p, const float* const* P, const float* z1, c
   packs.n = 0;
   p->fwd_f16 = g_fwd_f16 && g_conv_impl == 1;
   p->dec_f16 = false;
+  p->u0_f16_only = p->fwd_f16;
   RUN(queue_decoder_packs(p, packs, P, true, s));   // gen_ecg runs the module in eval mode (model_nefnet.py:197)
   RUN(nef_pack_weights_batch(&packs, s));
   RUN(nef_ncl_to_cbl4(z1, reinterpret_cast<float*>(p->z1.p), p->B, p->C1, p->L4, 0, sv));
@@ -1109,8 +1116,7 @@ static int decoder_bwd_h(NefPlan* p, const float* const* P, float* const* Gd, in
   RUN(bnbwd_apply_h(nullptr, p->dg3_h, d.c3, d.bn[2], P[P_DEC3 + 2], n1, p->dg3_h, g(P_DEC3 + 2), g(P_DEC3 + 3), 1, ls, s));
   RUN(wgrad_h(p->dg3_h, p->dg3, 0, 0, d.u1_h, d.u1, 0, 0, p->decw[2], g(P_DEC3 + 0), inv, s));
   RUN(dgrad(2, p->dg3, p->dg3_h, p->du1_h, p->du1));
-  RUN(up_adjoint_h(p->du1_h, p->du1, p->dg2_h, p->dg2, s));
-  RUN(bnbwd_stats_h(p->dg2_h, d.c2, d.bn[1], s));
+  RUN(up_adjoint_stats_h(p->du1_h, p->du1, p->dg2_h, d.c2, d.bn[1], s));
   RUN(bnbwd_apply_h(nullptr, p->dg2_h, d.c2, d.bn[1], P[P_DEC1 + 9], n2, p->dg2_h, g(P_DEC1 + 9), g(P_DEC1 + 10), 1, ls, s));
   RUN(wgrad_h(p->dg2_h, p->dg2, 0, 0, d.a1_h, d.a1, 0, 0, p->decw[1], g(P_DEC1 + 7), inv, s));
   RUN(dgrad(1, p->dg2, p->dg2_h, p->dg1_h, p->dg1));
@@ -1118,9 +1124,11 @@ static int decoder_bwd_h(NefPlan* p, const float* const* P, float* const* Gd, in
   RUN(bnbwd_apply_h(nullptr, p->dg1_h, d.c1, d.bn[0], P[P_DEC1 + 2], n2, p->dg1_h, g(P_DEC1 + 2), g(P_DEC1 + 3), 1, ls, s));
   RUN(wgrad_h(p->dg1_h, p->dg1, 0, 0, p->u0_h[slot], p->u0[slot], 0, 0, p->decw[0], g(P_DEC1 + 0), inv, s));
   {
-    CD c(2, 128, p->dg1);  // 256 output channels as two sub-groups reading the same input; fp32 result for latent_bwd
-    c.term16(p->dg1_h, p->dg1.cs, 0, 0, 128, 3, p->decw[0].pk_dh).out(p->du0[slot], 0, 32).round();
+    CD c(2, 128, p->dg1);  // 256 output channels as two sub-groups reading the same input
+    c.term16(p->dg1_h, p->dg1.cs, 0, 0, 128, 3, p->decw[0].pk_dh).out(p->du0[slot], 0, 32);
     c.d.acc_scale = inv;
+    if (p->variant == 1) { c.y16s(p->du0_h[slot], ls); c.d.y = nullptr; }   // latent_bwd reads the loss-scaled fp16 copy
+    else c.round();                                                        // Model_nefnet2: fp32 result for upq_adjoint
     RUN(c.run(s));
   }
   return 0;
@@ -1183,7 +1191,10 @@ extern "C" int nef_backward(NefPlan* p, const NefBackwardArgs* a, nef_stream_t s
     lb.direct = 1;
     for (int k = 0; k < 3; ++k) lb.dlat[k] = p->dlat[k];
   }
-  for (int k = 0; k < 3; ++k) { lb.du0[k] = p->du0[k]; lb.lat[k] = p->lat[k]; }
+  for (int k = 0; k < 3; ++k) {
+    lb.du0[k] = p->du0[k]; lb.lat[k] = p->lat[k];
+    lb.du0h[k] = (f16 && p->dec_f16 && !v2 && douts[k]) ? p->du0_h[k] : nullptr;
+  }
   lb.z1 = p->z1; lb.z2o = p->z2o; lb.rois = p->rois_in; lb.q = p->q; lb.q_stride = 256; lb.G = G; lb.c1 = p->c1; lb.c2 = p->c2;
   lb.gz1 = p->GA[0]; lb.gz2o = p->gz2o; lb.dq = p->dq;
   lb.gz1_h = f16 ? p->GA_h[0] : nullptr; lb.s16 = ls;
@@ -1350,7 +1361,7 @@ static bool find_tensor(const NefPlan* p, const char* name, NamedTensor* out) {
     const void* hs[7] = {nullptr, d.a1_h, nullptr, d.u1_h, nullptr, d.a3_h, nullptr};
     for (int i = 0; i < 7; ++i)
       if (n == pre + nm[i]) { out->t = ts[i]; if (p->dec_f16) out->h16 = hs[i]; return true; }
-    if (n == pre + "u0") { out->t = &p->u0[k]; return true; }
+    if (n == pre + "u0") { out->t = &p->u0[k]; if (p->u0_f16_only) out->h16 = p->u0_h[k]; return true; }
     for (int i = 0; i < 4; ++i) {
       const std::string b = pre + "bn" + std::to_string(i) + ".";
       const int ch = i < 2 ? 128 : 64;
