@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "lib", "libnefnet_b200.so")
 SOURCES = ["nef_conv_simt.cu", "nef_conv_tc.cu", "nef_elem.cu", "nef_plan.cu", "nef_data.cu",
-           "nef_wgrad_f16.cu"]   # the last one is experimental: exported, not called by the path (see its header)
+           "nef_wgrad_f16.cu", "nef_stem_tc.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
          "--expt-relaxed-constexpr", "-Xptxas", "-v"]

@@ -320,9 +320,34 @@ __global__ void bits_to_ncl_kernel(const uint32_t* __restrict__ src, float* __re
   }
 }
 
+// one code byte per channel (a uint32 per 4-channel chunk and row, indexed like a CBL4 tensor) -> floats (B, C, L)
+__global__ void codes_to_ncl_kernel(const uint32_t* __restrict__ src, float* __restrict__ dst, int B, int C, int L) {
+  const int Lp = L + 2 * NEF_HALO;
+  const long total = (long)B * (C / 4) * L;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int l = i % L;
+    long r = i / L;
+    const int b = r % B;
+    const int c4 = r / B;
+    const uint32_t w = src[(long)c4 * B * Lp + (long)b * Lp + NEF_HALO + l];
+    float* o = dst + ((long)b * C + c4 * 4) * L + l;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o[(long)j * L] = (float)((w >> (8 * j)) & 0xffu);
+  }
+}
+
 }  // namespace nef
 
 using namespace nef;
+
+extern "C" int nef_codes_to_ncl(const uint32_t* src, float* dst, int B, int C, int L, nef_stream_t s) {
+  const long total = (long)B * (C / 4) * L;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  codes_to_ncl_kernel<<<blocks, 256, 0, (cudaStream_t)s>>>(src, dst, B, C, L);
+  NEF_CHECK_LAUNCH("codes_to_ncl_kernel");
+  return 0;
+}
 
 extern "C" int nef_bits_to_ncl(const uint32_t* src, float* dst, int B, int C, int L, nef_stream_t s) {
   const long total = (long)B * (C / 32) * L;

@@ -28,6 +28,9 @@ struct BnLayer {          // one BatchNorm1d of the decoder for one decoder call
 
 int stem_fwd(const float* x, const float* w, T4 y, uint32_t* amax, void* y16, int G, cudaStream_t s, int store32 = 1, int w_shared = 0);  // y16: optional fp16 copy (store32 = 0: only that copy is written)
 int stem_bwd(const float* x, const uint32_t* amax, T4 dy, float* dw, int G, cudaStream_t s, int w_shared = 0);
+// the same on the tensor cores (nef_stem_tc.cu): split-precision fp16 MMAs, fp32-accurate; outputs = the fp16 copy y16 and
+// the codes only (geometry of y)
+int stem_tc_fwd(const float* x, const float* w, T4 y, uint32_t* amax, void* y16, int G, cudaStream_t s, int w_shared = 0);
 int angular_fwd(const float* theta, const float* w, const float* b, float* out, int n, int D, cudaStream_t s);
 int angular_bwd(const float* theta, const float* dout, float* dw, float* db, int n, int D, cudaStream_t s);
 

@@ -45,6 +45,7 @@ extern "C" int nef_gconv_wgrad_tc(const NefWgradDesc* d, nef_stream_t s);
 extern "C" int nef_tc_init(void);
 extern "C" int nef_h8_to_ncl(const void* src, float* dst, int B, int C, int L, nef_stream_t s);
 extern "C" int nef_bits_to_ncl(const uint32_t* src, float* dst, int B, int C, int L, nef_stream_t s);
+extern "C" int nef_codes_to_ncl(const uint32_t* src, float* dst, int B, int C, int L, nef_stream_t s);
 
 static int g_conv_impl = 1;
 extern "C" int nef_set_conv_impl(int impl) {
@@ -73,6 +74,8 @@ static int g_keep_h32 = 0, g_k3_tf32 = 0;
 // 1 (default) = fp16 decoder dataflow in training: a1 / u1 / a3 kept as fp16 operand copies only, convolutions 2-4 and every
 // decoder data / weight gradient in kind::f16 on loss-scaled fp16 gradient copies (NEF_DEC_F16=0: the TF32 decoder)
 static int g_dec_f16 = 1;
+// 1 (default) = the stem runs on the tensor cores (nef_stem_tc.cu) whenever only its fp16 copy is kept (NEF_STEM_TC=0: CUDA cores)
+static int g_stem_tc = 1;
 extern "C" int nef_set_dec_f16(int on) { g_dec_f16 = on; return 0; }
 extern "C" int nef_gconv_wgrad_f16(const NefWgradDesc* d, const void* dy16, const void* x16, const float* out_scale, nef_stream_t s);
 extern "C" int nef_set_dec1_terms(int n) {
@@ -104,6 +107,7 @@ extern "C" int nef_init(int device) {
   if (getenv("NEF_K3_TF32")) g_k3_tf32 = atoi(getenv("NEF_K3_TF32"));
   if (getenv("NEF_BWD_F16")) g_bwd_f16 = atoi(getenv("NEF_BWD_F16"));
   if (getenv("NEF_DEC_F16")) g_dec_f16 = atoi(getenv("NEF_DEC_F16"));
+  if (getenv("NEF_STEM_TC")) g_stem_tc = atoi(getenv("NEF_STEM_TC"));
   int rc = elem_init();
   if (rc) return rc;
   return nef_tc_init();
@@ -877,8 +881,11 @@ extern "C" int nef_forward(NefPlan* p, const NefForwardArgs* a, nef_stream_t sv)
     RUN(queue_pack(packs, P[P_CT_W] + t, p->ct_f[t], 7 * G, 64, 128, 1, 128LL * 64 * 2, 2, 64 * 2, 0, 0, s, nullptr, v2 ? 7 : 0));
   RUN(nef_pack_weights_batch(&packs, s));
 
-  RUN(stem_fwd(a->x, P[P_STEM], p->s0, a->save_for_backward ? p->s0_amax : nullptr, p->fwd_f16 ? p->s0_h : nullptr, G, s,
-               p->h_f16_only ? 0 : 1, v2 ? 1 : 0));   // fp16 dataflow: the first block reads only the fp16 copy
+  if (p->fwd_f16 && p->h_f16_only && g_stem_tc)   // fp16 dataflow: the first block reads only the fp16 copy
+    RUN(stem_tc_fwd(a->x, P[P_STEM], p->s0, a->save_for_backward ? p->s0_amax : nullptr, p->s0_h, G, s, v2 ? 1 : 0));
+  else
+    RUN(stem_fwd(a->x, P[P_STEM], p->s0, a->save_for_backward ? p->s0_amax : nullptr, p->fwd_f16 ? p->s0_h : nullptr, G, s,
+                 p->h_f16_only ? 0 : 1, v2 ? 1 : 0));
   RUN(angular_fwd(a->input_thetas, P[P_MLP1_W], P[P_MLP1_B], p->s_in, B * G, 128, s));
   const float dp = a->drop_p;
   const uint64_t seed = a->drop_seed * 16;
@@ -1312,10 +1319,12 @@ extern "C" int nef_backward(NefPlan* p, const NefBackwardArgs* a, nef_stream_t s
 // ---------------------------------------------------------------------------------------------
 // workspace inspection (test hook): named internal tensors of the last forward
 // ---------------------------------------------------------------------------------------------
-struct NamedTensor { const T4* t; const float* v; int n; const void* h16; const uint32_t* bits; };
+struct NamedTensor { const T4* t; const float* v; int n; const void* h16; const uint32_t* bits; const uint32_t* codes; };
 static bool find_tensor(const NefPlan* p, const char* name, NamedTensor* out) {
-  out->t = nullptr; out->v = nullptr; out->n = 0; out->h16 = nullptr; out->bits = nullptr;
+  out->t = nullptr; out->v = nullptr; out->n = 0; out->h16 = nullptr; out->bits = nullptr; out->codes = nullptr;
   std::string n(name);
+  // the stem's max-pool selections: 0..2 = which conv position of the window (2j-1, 2j, 2j+1) won, 3 = clipped by the ReLU
+  if (n == "stem.argmax") { out->t = &p->s0; out->codes = p->s0_amax; return true; }
   // "<block>.h.mask" / "<block>.y.mask": the one-bit (value != 0) plane the masked data-gradient epilogues read, as 0 / 1 floats
   if (n.size() > 5 && n.substr(n.size() - 5) == ".mask") {
     n = n.substr(0, n.size() - 5);
@@ -1382,7 +1391,7 @@ extern "C" int nef_plan_tensor_info(const NefPlan* p, const char* name, int* C, 
 // NaN, so that a test can prove that nothing reads a tensor the dataflow claims to have dropped.
 extern "C" int nef_plan_poison(NefPlan* p, const char* name, float* scratch, nef_stream_t s) {
   NamedTensor t;
-  NEF_REQUIRE(p && p->bound && name && scratch && find_tensor(p, name, &t) && t.t && !t.bits,
+  NEF_REQUIRE(p && p->bound && name && scratch && find_tensor(p, name, &t) && t.t && !t.bits && !t.codes,
               "nef_plan_poison: unknown tensor '%s'", name ? name : "");
   cudaMemsetAsync(scratch, 0xFF, (size_t)p->B * t.t->C * t.t->L * sizeof(float), (cudaStream_t)s);   // all-ones bits = NaN
   return nef_ncl_to_cbl4(scratch, reinterpret_cast<float*>(t.t->p), p->B, t.t->C, t.t->L, 0, s);
@@ -1390,6 +1399,7 @@ extern "C" int nef_plan_poison(NefPlan* p, const char* name, float* scratch, nef
 extern "C" int nef_plan_export(NefPlan* p, const char* name, float* dst, nef_stream_t s) {
   NamedTensor t;
   NEF_REQUIRE(p && p->bound && name && find_tensor(p, name, &t), "nef_plan_export: unknown tensor '%s'", name ? name : "");
+  if (t.t && t.codes) return nef_codes_to_ncl(t.codes, dst, p->B, t.t->C, t.t->L, s);
   if (t.t && t.bits) return nef_bits_to_ncl(t.bits, dst, p->B, t.t->C, t.t->L, s);
   if (t.t && t.h16) return nef_h8_to_ncl(t.h16, dst, p->B, t.t->C, t.t->L, s);
   if (t.t) return nef_cbl4_to_ncl(reinterpret_cast<const float*>(t.t->p), dst, p->B, t.t->C, t.t->L, s);
@@ -1414,6 +1424,10 @@ extern "C" int nef_roi_check(const int64_t* rois, int B, int L, int32_t* flag, n
 extern "C" int nef_stem_fwd(const float* x, const float* w, float* y, uint32_t* argmax, int B, int G, int L,
                             nef_stream_t s) {
   return stem_fwd(x, w, view_t4(y, 128 * G, B, L / 4), argmax, nullptr, G, (cudaStream_t)s);
+}
+extern "C" int nef_stem_tc_fwd(const float* x, const float* w, void* y16, uint32_t* argmax, int B, int G, int L, nef_stream_t s) {
+  NEF_REQUIRE(x && w && y16 && L % 4 == 0, "nef_stem_tc_fwd: bad arguments");
+  return stem_tc_fwd(x, w, view_t4(nullptr, 128 * G, B, L / 4), argmax, y16, G, (cudaStream_t)s);
 }
 extern "C" int nef_stem_bwd(const float* x, const uint32_t* argmax, const float* dy, float* dw, int B, int G, int L,
                             nef_stream_t s) {

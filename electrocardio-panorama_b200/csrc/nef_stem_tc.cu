@@ -1,0 +1,342 @@
+// Encoder stem on the tensor cores (sm_100a): Conv1d(G -> 128G, k15, s2, p7, groups=G, no bias) -> ReLU -> MaxPool1d(3,2,1),
+// network/encoder/resnet_1d.py:102-105 + network/encoder/encoder.py:35-38, and its weight gradient.  The CUDA-core kernels
+// in nef_elem.cu (stem_fwd_kernel / stem_bwd_kernel) compute the same thing at 30 fp32 FMAs per output element and are bound
+// by the FP32 pipe at a fifth of the HBM roof; they stay as the exact-fp32 tier and as the fallback for the fp32 store.
+//
+// Forward.  Per lead the convolution is a GEMM over the 15 taps (K = 16 with a zero tap): conv[p][c] = sum_t x[2p + t - 7] w[c][t].
+// Three accumulator sets indexed by the POOLED position j hold the three conv positions of its window,
+//     E[j] = conv[2j],   O[j] = conv[2j + 1],   Om[j] = conv[2j - 1] = O[j - 1],
+// so the max-pool is lane-local in the epilogue (TMEM lane = j).  The A operands are im2col tiles built in shared memory from
+// the input window, K-major no-swizzle `[k chunk][row][8 halves]` (rows 16 bytes apart, as the convolution kernels stage
+// their tiles): A_E[j][t] = x[4j + t - 7], A_O[j][t] = x[4j + t - 5]; Om reads the O tile through a start address one row
+// (16 bytes) lower.  fp32 accuracy comes from split precision, x = x_hi + x_lo, w = w_hi + w_lo in fp16:
+//     x_hi w_hi + x_lo w_hi + x_hi w_lo      (three accumulating kind::f16 MMAs per set; the dropped x_lo w_lo term is 2^-22)
+// A CTA owns 32 output channels of one lead (M128 x N32 x K16 MMAs, 96 TMEM columns) and walks (segment, 128-output tile)
+// units; four such CTAs share an SM, so one CTA's epilogue overlaps the others' loads and MMAs without any in-kernel pipeline.
+#include <cuda_fp16.h>
+
+#include "nef_elem.cuh"
+
+namespace nef {
+namespace stc {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// descriptor words (SWIZZLE_NONE, version 1): lo = start address | LBO, hi = SBO
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo_bytes) { return ((saddr >> 4) & 0x3FFF) | ((lbo_bytes >> 4) << 16); }
+__device__ __forceinline__ uint32_t desc_hi(uint32_t sbo_bytes) { return (sbo_bytes >> 4) | (1u << 14); }
+__device__ __forceinline__ uint64_t desc_of(uint32_t hi, uint32_t lo) {
+  uint64_t d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
+  return d;
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+// fp32 accumulate (bit 4), F16 x F16, a_mn / b_mn: operand is MN-major, M x N
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N, int a_mn, int b_mn) {
+  return (1u << 4) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ uint32_t f16x2_sat(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ float tf32_rna(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------------------------
+// phase clocks of CTA (0, 0, 0), tiles 0..7 (profiling aid, nef_stem_tc_debug): start, window stored, tiles built, MMAs
+// committed, accumulators ready, epilogue done
+__device__ long long g_stem_dbg[8][8];
+#define STEM_STAMP(slot)                                                                     \
+  do {                                                                                       \
+    if (tid == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && it < 8) g_stem_dbg[it][slot] = clock64(); \
+  } while (0)
+constexpr int SF_THREADS = 128;
+constexpr int SF_TJ = 128;                 // pooled outputs per tile = MMA M
+constexpr int SF_NC = 32;                  // output channels per CTA = MMA N
+constexpr int SF_XW = 4 * SF_TJ + 24;      // input window of a tile: x[4 j0 - 9 .. 4 j0 + 4 * 128 + 14]
+constexpr int SF_AROWS = SF_TJ + 8;        // rows per k chunk plane of an A tile (the O tile holds rows j = -1 .. 127)
+constexpr int SF_APITCH = SF_AROWS * 16;   // bytes between the two k chunks
+constexpr int SF_ABYTES = 2 * SF_APITCH;   // one A tile (K = 16 halves = 2 chunks)
+constexpr int SF_BBYTES = 2 * SF_NC * 16;  // one B tile: [k chunk][channel][8 halves]
+
+__global__ void __launch_bounds__(SF_THREADS, 4) stem_tc_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, T4 y,
+                                                                    uint32_t* __restrict__ amax, uint4* __restrict__ y16, int G, int L,
+                                                                    int w_shared) {
+  __shared__ __align__(128) uint8_t s_a[4 * SF_ABYTES];   // E_hi, E_lo, O_hi, O_lo
+  __shared__ __align__(128) uint8_t s_b[2 * SF_BBYTES];   // w_hi, w_lo
+  __shared__ __align__(16) __half s_xh[SF_XW + 8], s_xl[SF_XW + 8];
+  __shared__ __align__(8) uint64_t s_bar;
+  __shared__ uint32_t s_tmem;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = blockIdx.y, cq = blockIdx.z;   // lead, 32-channel quarter
+  const int L4 = L / 4;
+  const int ntile = (L4 + SF_TJ - 1) / SF_TJ;
+  const uint32_t bar = smem_u32(&s_bar);
+
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(smem_u32(&s_tmem), 128);
+  // weights of this CTA's 32 channels, split into fp16 hi / lo, K-major: slot [k chunk][n] = taps 8 kc .. 8 kc + 7 (tap 15 = 0)
+  for (int i = tid; i < 2 * SF_NC; i += SF_THREADS) {
+    const int kc = i / SF_NC, n = i % SF_NC;
+    const float* wp = w + ((long)(w_shared ? 0 : g) * 128 + cq * SF_NC + n) * 15;
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float v[2], h[2];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int t = kc * 8 + 2 * q + e;
+        v[e] = t < 15 ? wp[t] : 0.f;
+        h[e] = __half2float(__float2half_rn(v[e]));
+      }
+      hi[q] = f16x2_sat(v[0], v[1]);
+      lo[q] = f16x2_sat(v[0] - h[0], v[1] - h[1]);
+    }
+    *reinterpret_cast<uint4*>(s_b + (kc * SF_NC + n) * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(s_b + SF_BBYTES + (kc * SF_NC + n) * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = s_tmem;
+  const uint32_t idesc = make_idesc_f16(128, SF_NC, 0, 0);
+  const uint32_t a_hi = desc_hi(128), b_hi = desc_hi(128);
+  const uint32_t a0 = smem_u32(s_a), b0 = smem_u32(s_b);
+  uint32_t ph = 0;
+
+  // the input window of a tile (x[4 j0 - 9 + i], i < SF_XW + 8) is fetched into registers one tile ahead, behind the epilogue
+  constexpr int XPT = (SF_XW + 8 + SF_THREADS - 1) / SF_THREADS;
+  float xv[XPT];
+  auto fetch_window = [&](int u) {
+    const int b = u / ntile;
+    const int j0 = (u - b * ntile) * SF_TJ;
+    const float* xb = x + ((long)b * G + g) * L;
+#pragma unroll
+    for (int k = 0; k < XPT; ++k) {
+      const int i = tid + k * SF_THREADS;
+      const int p = 4 * j0 - 9 + i;
+      xv[k] = (i < SF_XW + 8 && p >= 0 && p < L) ? __ldg(xb + p) : 0.f;
+    }
+  };
+  fetch_window(blockIdx.x);
+  int it = -1;
+  for (int u = blockIdx.x; u < y.B * ntile; u += gridDim.x) {
+    ++it;
+    STEM_STAMP(0);
+    const int b = u / ntile;
+    const int j0 = (u - b * ntile) * SF_TJ;
+    // ---- input window as fp16 hi / lo
+#pragma unroll
+    for (int k = 0; k < XPT; ++k) {
+      const int i = tid + k * SF_THREADS;
+      if (i < SF_XW + 8) {
+        const __half h = __float2half_rn(xv[k]);
+        s_xh[i] = h;
+        s_xl[i] = __float2half_rn(xv[k] - __half2float(h));
+      }
+    }
+    __syncthreads();
+    STEM_STAMP(1);
+    // ---- im2col tiles.  E row j (tile-local), chunk kc: x[4j - 7 + 8kc ..] = s_x[4j + 2 + 8kc ..] ; O row r = j + 1:
+    //      x[4j - 5 + 8kc ..] = s_x[4r + 8kc ..]  (rows 0 .. 128).  Thread t builds row t of both tiles (both k chunks are 16
+    //      consecutive halves of the window); threads 0, 1 add the two chunks of row 128 of the O tile.
+    {
+      const uint32_t* eh = reinterpret_cast<const uint32_t*>(s_xh + 4 * tid + 2);   // 4-byte aligned
+      const uint32_t* el = reinterpret_cast<const uint32_t*>(s_xl + 4 * tid + 2);
+      const uint2* oh = reinterpret_cast<const uint2*>(s_xh + 4 * tid);             // 8-byte aligned
+      const uint2* ol = reinterpret_cast<const uint2*>(s_xl + 4 * tid);
+      uint32_t a[8], c[8];
+      uint2 d[4], e[4];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) { a[q] = eh[q]; c[q] = el[q]; }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { d[q] = oh[q]; e[q] = ol[q]; }
+      uint8_t* pe = s_a + tid * 16;
+      *reinterpret_cast<uint4*>(pe) = make_uint4(a[0], a[1], a[2], a[3]);
+      *reinterpret_cast<uint4*>(pe + SF_APITCH) = make_uint4(a[4], a[5], a[6], a[7]);
+      *reinterpret_cast<uint4*>(pe + SF_ABYTES) = make_uint4(c[0], c[1], c[2], c[3]);
+      *reinterpret_cast<uint4*>(pe + SF_ABYTES + SF_APITCH) = make_uint4(c[4], c[5], c[6], c[7]);
+      uint8_t* po = s_a + 2 * SF_ABYTES + tid * 16;
+      *reinterpret_cast<uint4*>(po) = make_uint4(d[0].x, d[0].y, d[1].x, d[1].y);
+      *reinterpret_cast<uint4*>(po + SF_APITCH) = make_uint4(d[2].x, d[2].y, d[3].x, d[3].y);
+      *reinterpret_cast<uint4*>(po + SF_ABYTES) = make_uint4(e[0].x, e[0].y, e[1].x, e[1].y);
+      *reinterpret_cast<uint4*>(po + SF_ABYTES + SF_APITCH) = make_uint4(e[2].x, e[2].y, e[3].x, e[3].y);
+      if (tid < 2) {   // row 128 of the O tile, chunk kc = tid
+        const uint2* qh = reinterpret_cast<const uint2*>(s_xh + 4 * SF_TJ + 8 * tid);
+        const uint2* ql = reinterpret_cast<const uint2*>(s_xl + 4 * SF_TJ + 8 * tid);
+        uint8_t* pr = s_a + 2 * SF_ABYTES + tid * SF_APITCH + SF_TJ * 16;
+        *reinterpret_cast<uint4*>(pr) = make_uint4(qh[0].x, qh[0].y, qh[1].x, qh[1].y);
+        *reinterpret_cast<uint4*>(pr + SF_ABYTES) = make_uint4(ql[0].x, ql[0].y, ql[1].x, ql[1].y);
+      }
+    }
+    fence_proxy_async();
+    __syncthreads();
+    STEM_STAMP(2);
+    if (warp == 0) {
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t bh = desc_of(b_hi, desc_lo(b0, SF_NC * 16)), bl = desc_of(b_hi, desc_lo(b0 + SF_BBYTES, SF_NC * 16));
+        // sets: 0 = E, 1 = O (row 1 of the O tile), 2 = Om (row 0 of the O tile)
+        const uint32_t sa[3] = {a0, a0 + 2 * SF_ABYTES + 16, a0 + 2 * SF_ABYTES};
+#pragma unroll
+        for (int st = 0; st < 3; ++st) {
+          const uint64_t ah = desc_of(a_hi, desc_lo(sa[st], SF_APITCH)), al = desc_of(a_hi, desc_lo(sa[st] + SF_ABYTES, SF_APITCH));
+          mma_f16(tmem + st * SF_NC, ah, bh, idesc, 0u);
+          mma_f16(tmem + st * SF_NC, al, bh, idesc, 1u);
+          mma_f16(tmem + st * SF_NC, ah, bl, idesc, 1u);
+        }
+        tc_commit(bar);
+      }
+      __syncwarp();
+    }
+    STEM_STAMP(3);
+    if (u + (int)gridDim.x < y.B * ntile) fetch_window(u + gridDim.x);   // in flight behind the MMA wait and the epilogue
+    mbar_wait(bar, ph);
+    ph ^= 1;
+    tc_fence_after();
+    STEM_STAMP(4);
+    // ---- epilogue: thread = pooled position j0 + 32 warp + lane; max over (2j-1, 2j, 2j+1), ReLU, code, fp16 row stores
+    {
+      const int j = j0 + warp * 32 + lane;
+      const bool ok = j < L4;
+      const bool va = j > 0;   // conv position 2j - 1 exists
+      const uint32_t tl = tmem + ((uint32_t)(warp * 32) << 16);
+      const long row = y.row(b, ok ? j : 0);
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {   // 16 channels at a time (48 accumulator registers in flight)
+        uint32_t ve[16], vo[16], vm[16];
+        tmem_ld16(tl + 0 * SF_NC + hh * 16, ve);
+        tmem_ld16(tl + 1 * SF_NC + hh * 16, vo);
+        tmem_ld16(tl + 2 * SF_NC + hh * 16, vm);
+        tmem_ld_wait();
+        uint32_t hp[4];
+#pragma unroll
+        for (int c4 = 0; c4 < 4; ++c4) {
+          uint32_t code = 0;
+          float m[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float c0 = __uint_as_float(vm[4 * c4 + k]), c1 = __uint_as_float(ve[4 * c4 + k]), c2 = __uint_as_float(vo[4 * c4 + k]);
+            uint32_t best = 1;
+            float bv = c1;
+            if (va && c0 >= c1) { best = 0; bv = c0; }   // first maximum wins (window order), as MaxPool1d
+            if (c2 > bv) { best = 2; bv = c2; }
+            if (!(bv > 0.f)) { best = 3; bv = 0.f; }
+            m[k] = bv;   // the fp16 conversion below is the only rounding
+            code |= best << (8 * k);
+          }
+          const int ch4 = g * 32 + cq * 8 + hh * 4 + c4;   // 4-channel chunk of the 128 G channel space
+          if (amax && ok) amax[(long)ch4 * y.cs + row] = code;
+          hp[(c4 & 1) * 2 + 0] = f16x2_sat(m[0], m[1]);
+          hp[(c4 & 1) * 2 + 1] = f16x2_sat(m[2], m[3]);
+          if ((c4 & 1) && ok) y16[(long)(ch4 >> 1) * y.cs + row] = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+        }
+      }
+    }
+    tc_fence_before();
+    __syncthreads();
+    STEM_STAMP(5);
+  }
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 128);
+  }
+}
+
+}  // namespace stc
+
+// y16: fp16 copy (half8 rows) -- the only output of this form besides the argmax codes (amax may be nullptr)
+int stem_tc_fwd(const float* x, const float* w, T4 y, uint32_t* amax, void* y16, int G, cudaStream_t s, int w_shared) {
+  const int L = y.L * 4;
+  const int ntile = (y.L + stc::SF_TJ - 1) / stc::SF_TJ;
+  const long units = (long)y.B * ntile;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  long gx = ((long)sms * 4) / ((long)G * 4);   // four CTAs per SM over (lead, channel quarter) pairs
+  if (gx < 1) gx = 1;
+  if (gx > units) gx = units;
+  dim3 grid((unsigned)gx, (unsigned)G, 4);
+  // 25 KB of unused dynamic shared memory keep a fifth CTA off the SM: it would only wait for TMEM columns (4 x 128 = all 512)
+  stc::stem_tc_fwd_kernel<<<grid, stc::SF_THREADS, 25 * 1024, s>>>(x, w, y, amax, reinterpret_cast<uint4*>(y16), G, L, w_shared);
+  NEF_CHECK_LAUNCH("stem_tc_fwd_kernel");
+  return 0;
+}
+
+}  // namespace nef
+
+extern "C" int nef_stem_tc_debug(long long* host_out) {
+  cudaDeviceSynchronize();
+  return cudaMemcpyFromSymbol(host_out, nef::stc::g_stem_dbg, sizeof(long long) * 64) == cudaSuccess ? 0 : 1;
+}

@@ -262,7 +262,8 @@ int nef_backward(NefPlan* plan, const NefBackwardArgs* a, nef_stream_t s);
  * L = 0).  Names: "stem"; "<block>.h" / "<block>.y" for the residual blocks W_encoder.layer1.{0,1,2}, w_conv.0, z1_conv.0,
  * z2_conv1.0 (centre window only), z2_conv2.0, z2_conv2.2; "roi_align"; "z2_conv2.1"; per decoder call k = 0..2:
  * "dec<k>.u0", "dec<k>.decoder.{1,3}.{0,3}" (convolution outputs before BatchNorm), "dec<k>.a1|u1|a3",
- * "dec<k>.bn<i>.scale|shift"; "<block>.h.mask" / "<block>.y.mask" (encoder blocks, w_conv.0, z1_conv.0.h): the one-bit
+ * "dec<k>.bn<i>.scale|shift"; "stem.argmax" (the max-pool selections of the stem as floats: 0..2 = the conv position
+ * 2j-1 / 2j / 2j+1 that won, 3 = clipped by the ReLU); "<block>.h.mask" / "<block>.y.mask" (encoder blocks, w_conv.0, z1_conv.0.h): the one-bit
  * (value != 0) planes the masked data gradients read, as 0 / 1 floats.  The parity tests compare them layer by layer with the oracle and evaluate the oracle's
  * backward pass on the device's own ReLU / dropout patterns. */
 int nef_plan_tensor_info(const NefPlan* plan, const char* name, int* C, int* L);
@@ -330,6 +331,9 @@ int nef_prepare_segments(const double* raw, const int64_t* rec_off, const int32_
  * (0..2, MaxPool1d's first maximum) or 3 where the ReLU clipped; written by fwd (may be NULL), required by bwd. */
 int nef_stem_fwd(const float* x, const float* w, float* y, uint32_t* argmax, int B, int G, int L, nef_stream_t s);
 int nef_stem_bwd(const float* x, const uint32_t* argmax, const float* dy, float* dw, int B, int G, int L, nef_stream_t s);
+/* The stem forward on the tensor cores (split-precision fp16 MMAs, fp32-accurate): writes the fp16 copy y16 (half8 rows,
+ * layout of nef_ncl_to_h8 for (B, 128 G, L / 4)) and the argmax codes (may be NULL) -- the production form of the stem. */
+int nef_stem_tc_fwd(const float* x, const float* w, void* y16, uint32_t* argmax, int B, int G, int L, nef_stream_t s);
 /* Angular encoding + Linear, theta_encoder.py:13-29 + model_nefnet.py:76-77: (n,2) -> (n,D) */
 int nef_angular_fwd(const float* theta, const float* w, const float* b, float* out, int n, int D, nef_stream_t s);
 int nef_angular_bwd(const float* theta, const float* dout, float* dw, float* db, int n, int D, nef_stream_t s);

@@ -288,7 +288,16 @@ def encoder(P, x, G, keeps=None, prec=None, out_scale=None):
     """encoder/encoder.py:28-40 with resnet_1d.py:102-105: grouped stem k15 s2 p7 -> ReLU ->
     MaxPool(3,2,1) -> three k7 residual blocks.  out_scale: see residual_block (last block)."""
     h = _conv(prec, "fp32", x, P["W_encoder.conv1.weight"], stride=2, padding=7, groups=G)
-    h = _obs(prec, "stem", _st(prec, F.max_pool1d(F.relu(h), kernel_size=3, stride=2, padding=1)))
+    sel = None if prec is None else prec.pattern("stem.argmax")
+    if sel is None:
+        h = F.max_pool1d(F.relu(h), kernel_size=3, stride=2, padding=1)
+    else:
+        # the device's own max-pool selections (nef_plan_export "stem.argmax": 0..2 = conv position 2j-1 / 2j / 2j+1, 3 = clipped
+        # by the ReLU): near-ties between two conv positions route the gradient like a flipped ReLU mask would
+        sel = sel.to(torch.int64)
+        idx = (2 * torch.arange(sel.shape[-1]) - 1)[None, None, :] + sel.clamp(max=2)
+        h = torch.gather(h, 2, idx.clamp(min=0)) * (sel < 3).to(h.dtype)
+    h = _obs(prec, "stem", _st(prec, h))
     for i in range(3):
         keep = None if keeps is None else keeps.get(f"W_encoder.layer1.{i}")
         h = residual_block(h, P[f"W_encoder.layer1.{i}.conv1.weight"], P[f"W_encoder.layer1.{i}.conv2.weight"], G,

@@ -61,6 +61,7 @@ def _device_patterns(m, B, G, L):
     L4 = L // 4
     pat, acts = {}, {}
     acts["stem"] = m.export_activation("stem").cpu()
+    pat["stem.argmax"] = m.export_activation("stem.argmax").cpu()   # the max-pool selections are a pattern too
     for blk in BLOCKS:
         for s in ("h", "y"):
             a = m.export_activation("%s.%s" % (blk, s)).cpu()
