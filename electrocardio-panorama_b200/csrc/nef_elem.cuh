@@ -30,6 +30,9 @@ int stem_fwd(const float* x, const float* w, T4 y, uint32_t* amax, void* y16, in
 int stem_bwd(const float* x, const uint32_t* amax, T4 dy, float* dw, int G, cudaStream_t s, int w_shared = 0);
 // the same on the tensor cores (nef_stem_tc.cu): split-precision fp16 MMAs, fp32-accurate; outputs = the fp16 copy y16 and
 // the codes only (geometry of y)
+// weight gradient on the tensor cores from the loss-scaled fp16 copy dy16 of the stem output's gradient (geometry of dy)
+int stem_tc_bwd(const float* x, const uint32_t* amax, const void* dy16, T4 dy, float* dw, const float* inv_scale, int G,
+                cudaStream_t s, int w_shared = 0);
 int stem_tc_fwd(const float* x, const float* w, T4 y, uint32_t* amax, void* y16, int G, cudaStream_t s, int w_shared = 0);
 int angular_fwd(const float* theta, const float* w, const float* b, float* out, int n, int D, cudaStream_t s);
 int angular_bwd(const float* theta, const float* dout, float* dw, float* db, int n, int D, cudaStream_t s);

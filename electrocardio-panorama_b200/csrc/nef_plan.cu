@@ -1303,15 +1303,17 @@ extern "C" int nef_backward(NefPlan* p, const NefBackwardArgs* a, nef_stream_t s
       if (f16) {
         bb.io.x16 = i == 0 ? p->s0_h : p->ey_h[i - 1]; bb.io.h16 = p->eh_h[i];
         bb.gy16 = p->GA_h[gy_i]; bb.gh16 = p->GA_h[0]; bb.lscale = ls;
-        if (i > 0) {
+        if (i > 0 || g_stem_tc) {
           fin.y16s(p->GA_h[gx_i], ls);
-          fin.d.y = nullptr;   // the next block reads this gradient as fp16 only
+          fin.d.y = nullptr;   // the next block (the tensor-core stem gradient) reads this gradient as fp16 only
         }
       }
       RUN(block_bwd(bb, dp, fin, s));
       gy_i = gx_i;
     }
-    if (Gd[P_STEM]) RUN(stem_bwd(p->x_in, p->s0_amax, p->GA[gy_i], Gd[P_STEM], G, s, v2 ? 1 : 0));
+    if (Gd[P_STEM] && f16 && g_stem_tc)
+      RUN(stem_tc_bwd(p->x_in, p->s0_amax, p->GA_h[gy_i], p->GA[gy_i], Gd[P_STEM], ls + 1, G, s, v2 ? 1 : 0));
+    else if (Gd[P_STEM]) RUN(stem_bwd(p->x_in, p->s0_amax, p->GA[gy_i], Gd[P_STEM], G, s, v2 ? 1 : 0));
   }
   return 0;
 }

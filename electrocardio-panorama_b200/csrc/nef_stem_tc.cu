@@ -314,6 +314,183 @@ __global__ void __launch_bounds__(SF_THREADS, 4) stem_tc_fwd_kernel(const float*
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// weight gradient
+// ---------------------------------------------------------------------------------------------
+// dW[c][t] = sum_j  gE[j][c] x[4j + t - 7] + gO[j][c] x[4j + t - 5], with the pooled gradient routed to the conv positions by
+// the argmax codes of the forward:  gE[j] = dy[j] [code(j) == 1]   (position 2j)
+//                                    gO[j] = dy[j] [code(j) == 2] + dy[j + 1] [code(j + 1) == 0]   (position 2j + 1).
+// As a GEMM over the pooled positions (K = rows): D[128 channels x 16 taps] += gE^T . X_E + gO^T . X_O.  Both operands are
+// MN-major exactly as they sit in shared memory: the routed gradients as `[8-channel chunk][row][8 halves]` (the layout of
+// the fp16 gradient copy itself) and the im2col tiles of the forward kernel, `[8-tap chunk][row][8 halves]` -- the same bytes
+// the forward reads K-major.  x is split hi / lo (fp32-accurate), the gradient is the loss-scaled fp16 copy the last
+// data-gradient epilogue wrote.  A CTA accumulates all its (segment, 128-row tile) units of one lead in 16 TMEM columns and
+// drains them once, times 1 / S, with fp32 REDs.
+constexpr int SB_THREADS = 256;
+constexpr int SB_TJ = 128;
+constexpr int SB_GP = SB_TJ * 16;          // bytes between 8-channel chunks of a routed-gradient tile
+constexpr int SB_GBYTES = 16 * SB_GP;      // one routed-gradient tile: 128 channels x 128 rows of fp16
+constexpr int SB_XOFF = 2 * SB_GBYTES;     // the four im2col tiles behind the two gradient tiles
+constexpr int SB_TOTAL = SB_XOFF + 4 * SF_ABYTES + 64;
+
+// per 8-channel row: keep the halves whose code byte equals `want` (codes: one byte per channel, two words per row)
+__device__ __forceinline__ uint4 keep_code(uint4 g, uint32_t c0, uint32_t c1, uint32_t want) {
+  auto m2 = [&](uint32_t c, int k) {   // 16-bit masks of channels k, k + 1 of the word c
+    const uint32_t lo = ((c >> (8 * k)) & 0xffu) == want ? 0x0000ffffu : 0u;
+    const uint32_t hi = ((c >> (8 * k + 8)) & 0xffu) == want ? 0xffff0000u : 0u;
+    return lo | hi;
+  };
+  return make_uint4(g.x & m2(c0, 0), g.y & m2(c0, 2), g.z & m2(c1, 0), g.w & m2(c1, 2));
+}
+__device__ __forceinline__ uint32_t hadd2_u32(uint32_t a, uint32_t b) {
+  const __half2 r = __hadd2(*reinterpret_cast<const __half2*>(&a), *reinterpret_cast<const __half2*>(&b));
+  return *reinterpret_cast<const uint32_t*>(&r);
+}
+
+__global__ void __launch_bounds__(SB_THREADS, 2) stem_tc_bwd_kernel(const float* __restrict__ x, const uint32_t* __restrict__ amax,
+                                                                    const uint4* __restrict__ dy16, T4 dy, float* __restrict__ dw,
+                                                                    const float* __restrict__ inv_scale, int G, int L, int w_shared) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ __align__(16) __half s_xh[SF_XW + 8], s_xl[SF_XW + 8];
+  __shared__ __align__(8) uint64_t s_bar;
+  __shared__ uint32_t s_tmem;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int g = blockIdx.y;
+  const int L4 = L / 4;
+  const int ntile = (L4 + SB_TJ - 1) / SB_TJ;
+  const uint32_t bar = smem_u32(&s_bar);
+  uint8_t* s_ge = smem;
+  uint8_t* s_go = smem + SB_GBYTES;
+  uint8_t* s_x = smem + SB_XOFF;   // E_hi, E_lo, O_hi, O_lo
+
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(smem_u32(&s_tmem), 32);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = s_tmem;
+  const uint32_t idesc = make_idesc_f16(128, 16, 1, 1);
+  const uint32_t hi_g = desc_hi(SB_GP), hi_x = desc_hi(SF_APITCH);
+  const uint32_t ge0 = smem_u32(s_ge), go0 = smem_u32(s_go), x0 = smem_u32(s_x);
+  uint32_t ph = 0;
+  int issued = 0;
+  const int row_l = tid & (SB_TJ - 1), chalf = tid >> 7;   // this thread's tile row, and which 8 of the 16 channel chunks
+
+  for (int u = blockIdx.x; u < dy.B * ntile; u += gridDim.x) {
+    const int b = u / ntile;
+    const int j0 = (u - b * ntile) * SB_TJ;
+    const float* xb = x + ((long)b * G + g) * L;
+    // ---- global loads of this tile (all in flight before the previous tile's MMAs are waited for)
+    float xv[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const int i = tid + k * SB_THREADS;
+      const int p = 4 * j0 - 9 + i;
+      xv[k] = (i < SF_XW + 8 && p >= 0 && p < L) ? __ldg(xb + p) : 0.f;
+    }
+    const int j = j0 + row_l;
+    const bool v0 = j < L4, v1 = j + 1 < L4;
+    const long row = dy.row(b, v0 ? j : 0);
+    uint4 ga[8], gb[8];
+    uint32_t ca[8][2], cb[8][2];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int c8 = g * 16 + chalf * 8 + q;
+      const uint4* gp = dy16 + (long)c8 * dy.cs + row;
+      const uint32_t* cp = amax + (long)(2 * c8) * dy.cs + row;
+      ga[q] = v0 ? __ldg(gp) : make_uint4(0u, 0u, 0u, 0u);
+      gb[q] = v1 ? __ldg(gp + 1) : make_uint4(0u, 0u, 0u, 0u);
+      ca[q][0] = __ldg(cp); ca[q][1] = __ldg(cp + dy.cs);
+      cb[q][0] = __ldg(cp + 1); cb[q][1] = __ldg(cp + dy.cs + 1);
+    }
+    // ---- the previous tile's MMAs must have read the shared-memory tiles before they are overwritten
+    if (issued) {
+      mbar_wait(bar, ph);
+      ph ^= 1;
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const int i = tid + k * SB_THREADS;
+      if (i < SF_XW + 8) {
+        const __half h = __float2half_rn(xv[k]);
+        s_xh[i] = h;
+        s_xl[i] = __float2half_rn(xv[k] - __half2float(h));
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const uint32_t off = (uint32_t)((chalf * 8 + q) * SB_GP + row_l * 16);
+      const uint4 e = keep_code(ga[q], ca[q][0], ca[q][1], 1u);
+      const uint4 o2 = keep_code(ga[q], ca[q][0], ca[q][1], 2u);
+      const uint4 o0 = keep_code(gb[q], cb[q][0], cb[q][1], 0u);   // disjoint supports are not guaranteed: add
+      *reinterpret_cast<uint4*>(s_ge + off) = e;
+      *reinterpret_cast<uint4*>(s_go + off) =
+          make_uint4(hadd2_u32(o2.x, o0.x), hadd2_u32(o2.y, o0.y), hadd2_u32(o2.z, o0.z), hadd2_u32(o2.w, o0.w));
+    }
+    __syncthreads();
+    // ---- im2col tiles (as in the forward): E row r chunk tc = s_x[4r + 2 + 8tc ..], O row r chunk tc = s_x[4r + 4 + 8tc ..]
+    if (tid < SB_TJ) {
+      const uint32_t* eh = reinterpret_cast<const uint32_t*>(s_xh + 4 * tid + 2);
+      const uint32_t* el = reinterpret_cast<const uint32_t*>(s_xl + 4 * tid + 2);
+      const uint2* oh = reinterpret_cast<const uint2*>(s_xh + 4 * tid + 4);
+      const uint2* ol = reinterpret_cast<const uint2*>(s_xl + 4 * tid + 4);
+      uint8_t* pe = s_x + tid * 16;
+      *reinterpret_cast<uint4*>(pe) = make_uint4(eh[0], eh[1], eh[2], eh[3]);
+      *reinterpret_cast<uint4*>(pe + SF_APITCH) = make_uint4(eh[4], eh[5], eh[6], eh[7]);
+      *reinterpret_cast<uint4*>(pe + SF_ABYTES) = make_uint4(el[0], el[1], el[2], el[3]);
+      *reinterpret_cast<uint4*>(pe + SF_ABYTES + SF_APITCH) = make_uint4(el[4], el[5], el[6], el[7]);
+      uint8_t* po = s_x + 2 * SF_ABYTES + tid * 16;
+      *reinterpret_cast<uint4*>(po) = make_uint4(oh[0].x, oh[0].y, oh[1].x, oh[1].y);
+      *reinterpret_cast<uint4*>(po + SF_APITCH) = make_uint4(oh[2].x, oh[2].y, oh[3].x, oh[3].y);
+      *reinterpret_cast<uint4*>(po + SF_ABYTES) = make_uint4(ol[0].x, ol[0].y, ol[1].x, ol[1].y);
+      *reinterpret_cast<uint4*>(po + SF_ABYTES + SF_APITCH) = make_uint4(ol[2].x, ol[2].y, ol[3].x, ol[3].y);
+    }
+    fence_proxy_async();
+    __syncthreads();
+    if (warp == 0) {
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t gel = desc_lo(ge0, 128), gol = desc_lo(go0, 128);
+        const uint32_t xeh = desc_lo(x0, 128), xel = desc_lo(x0 + SF_ABYTES, 128);
+        const uint32_t xoh = desc_lo(x0 + 2 * SF_ABYTES, 128), xol = desc_lo(x0 + 3 * SF_ABYTES, 128);
+#pragma unroll
+        for (int ks = 0; ks < SB_TJ / 16; ++ks) {   // 16 rows = 256 bytes = 16 descriptor units per K step
+          const uint64_t ae = desc_of(hi_g, gel + ks * 16), ao = desc_of(hi_g, gol + ks * 16);
+          mma_f16(tmem, ae, desc_of(hi_x, xeh + ks * 16), idesc, (uint32_t)(issued | ks));
+          mma_f16(tmem, ae, desc_of(hi_x, xel + ks * 16), idesc, 1u);
+          mma_f16(tmem, ao, desc_of(hi_x, xoh + ks * 16), idesc, 1u);
+          mma_f16(tmem, ao, desc_of(hi_x, xol + ks * 16), idesc, 1u);
+        }
+        tc_commit(bar);
+      }
+      __syncwarp();
+    }
+    issued = 1;
+  }
+  if (issued) {
+    mbar_wait(bar, ph);
+    tc_fence_after();
+    if (warp < 4) {   // TMEM lane = channel, column = tap
+      uint32_t v[16];
+      tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16), v);
+      tmem_ld_wait();
+      const float sc = inv_scale ? __ldg(inv_scale) : 1.f;
+      float* dst = dw + ((long)(w_shared ? 0 : g) * 128 + tid) * 15;
+#pragma unroll
+      for (int t = 0; t < 15; ++t) atomicAdd(dst + t, __uint_as_float(v[t]) * sc);
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 32);
+  }
+}
+
 }  // namespace stc
 
 // y16: fp16 copy (half8 rows) -- the only output of this form besides the argmax codes (amax may be nullptr)
@@ -331,6 +508,27 @@ int stem_tc_fwd(const float* x, const float* w, T4 y, uint32_t* amax, void* y16,
   // 25 KB of unused dynamic shared memory keep a fifth CTA off the SM: it would only wait for TMEM columns (4 x 128 = all 512)
   stc::stem_tc_fwd_kernel<<<grid, stc::SF_THREADS, 25 * 1024, s>>>(x, w, y, amax, reinterpret_cast<uint4*>(y16), G, L, w_shared);
   NEF_CHECK_LAUNCH("stem_tc_fwd_kernel");
+  return 0;
+}
+
+// dy16: loss-scaled fp16 copy of the gradient of the stem output (half8 rows, geometry of dy); inv_scale[0] = 1 / S (device)
+int stem_tc_bwd(const float* x, const uint32_t* amax, const void* dy16, T4 dy, float* dw, const float* inv_scale, int G,
+                cudaStream_t s, int w_shared) {
+  const int L = dy.L * 4;
+  const int ntile = (dy.L + stc::SB_TJ - 1) / stc::SB_TJ;
+  const long units = (long)dy.B * ntile;
+  cudaError_t e = cudaFuncSetAttribute(stc::stem_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, stc::SB_TOTAL);
+  NEF_REQUIRE(e == cudaSuccess, "stem_tc_bwd: shared-memory opt-in failed: %s", cudaGetErrorString(e));
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  long gx = ((long)sms * 2) / G;   // two CTAs per SM over the leads
+  if (gx < 1) gx = 1;
+  if (gx > units) gx = units;
+  dim3 grid((unsigned)gx, (unsigned)G);
+  stc::stem_tc_bwd_kernel<<<grid, stc::SB_THREADS, stc::SB_TOTAL, s>>>(x, amax, reinterpret_cast<const uint4*>(dy16), dy, dw, inv_scale, G, L,
+                                                                        w_shared);
+  NEF_CHECK_LAUNCH("stem_tc_bwd_kernel");
   return 0;
 }
 

@@ -40,10 +40,10 @@ FP32_GRAD_COS = 0.99
 # epilogue codes of conv_tc_persist_kernel the 256 x 12 x 5000 training step launches (profiles/r02_step_b256_per_kernel_*):
 #   5164 first convolutions of the big blocks (dropout, fp16 copy, bit plane), 21540 / 21796 their second convolutions
 #   (residual read from the fp16 copy; angular scale), 37 z1_conv's second convolution, 513 decoder forward with BatchNorm
-#   statistics, 14368 / 30752 / 31008 / 24576 the loss-scaled fp16 data gradients, 12288 | NOY the decoder's data gradients
+#   statistics, 14368 / 30752 / 31008 / 28672 the loss-scaled fp16 data gradients (the last one feeds the tensor-core stem gradient), 12288 | NOY the decoder's data gradients
 #   (fp16 in, loss-scaled fp16 out), 32 the z2 branch's
 NOY = 32768   # EPI_NOY: no fp32 store, only the fp16 copy / bit plane of the result
-BENCH_EPI_DROPOUT = {5164 | NOY, 21540 | NOY, 21796 | NOY, 37, 513, 14368 | NOY, 30752 | NOY, 31008 | NOY, 24576, 12288 | NOY, 32}
+BENCH_EPI_DROPOUT = {5164 | NOY, 21540 | NOY, 21796 | NOY, 37, 513, 14368 | NOY, 30752 | NOY, 31008 | NOY, 28672 | NOY, 12288 | NOY, 32}
 
 
 BLOCKS = ("W_encoder.layer1.0", "W_encoder.layer1.1", "W_encoder.layer1.2", "w_conv.0", "z1_conv.0", "z2_conv1.0", "z2_conv2.0",
