@@ -1098,6 +1098,35 @@ __global__ void __launch_bounds__(256) bias_grad_kernel(const NefWgradDesc d, lo
   }
 }
 
+// the same from an fp16 gradient copy (half8 rows: 8 channels per 16-byte row, times a loss scale): db += scale[0] * sum
+__global__ void __launch_bounds__(256) bias_grad_h_kernel(const NefWgradDesc d, const uint4* __restrict__ dy16, const float* __restrict__ scale,
+                                                          long rows_per_split) {
+  __shared__ float red[8][8];
+  const int ch8 = blockIdx.y;  // chunk among groups * cout_g / 8
+  const int g = ch8 / (d.cout_g >> 3), c = ch8 % (d.cout_g >> 3);
+  const uint4* yg = dy16 + (long)((d.dy_c4_off >> 1) + g * (d.dy_c4_gstride >> 1) + c) * d.dy_cstride;
+  const long rbeg = (long)blockIdx.x * rows_per_split, rend = min(d.rows, rbeg + rows_per_split);
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (long r = rbeg + threadIdx.x; r < rend; r += 256) {
+    const uint4 h = __ldg(yg + r);
+    const float2 a0 = __half22float2(*reinterpret_cast<const __half2*>(&h.x)), a1 = __half22float2(*reinterpret_cast<const __half2*>(&h.y));
+    const float2 b0 = __half22float2(*reinterpret_cast<const __half2*>(&h.z)), b1 = __half22float2(*reinterpret_cast<const __half2*>(&h.w));
+    acc[0] += a0.x; acc[1] += a0.y; acc[2] += a1.x; acc[3] += a1.y;
+    acc[4] += b0.x; acc[5] += b0.y; acc[6] += b1.x; acc[7] += b1.y;
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const float v = warp_sum(acc[k]);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][k] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x];
+    atomicAdd(d.db + (long)(d.wg_mod > 0 ? g % d.wg_mod : g) * d.cout_g + c * 8 + threadIdx.x, t * (scale ? __ldg(scale) : 1.f));
+  }
+}
+
 }  // namespace tc
 }  // namespace nef
 
@@ -1334,6 +1363,17 @@ extern "C" int nef_bias_grad_tc(const NefWgradDesc* d, nef_stream_t s) {
   dim3 grid((unsigned)((d->rows + rps - 1) / rps), (unsigned)(d->groups * (d->cout_g / 4)));
   tc::bias_grad_kernel<<<grid, 256, 0, (cudaStream_t)s>>>(*d, rps);
   NEF_CHECK_LAUNCH("bias_grad_kernel");
+  return 0;
+}
+
+// the same from the loss-scaled fp16 copy dy16 of the gradient (geometry of d; d->dy is not read); scale[0] = 1 / S (device)
+extern "C" int nef_bias_grad_h(const NefWgradDesc* d, const void* dy16, const float* scale, nef_stream_t s) {
+  long splits = (d->rows + 4095) / 4096;
+  if (splits > 64) splits = 64;
+  const long rps = (d->rows + splits - 1) / splits;
+  dim3 grid((unsigned)((d->rows + rps - 1) / rps), (unsigned)(d->groups * (d->cout_g / 8)));
+  tc::bias_grad_h_kernel<<<grid, 256, 0, (cudaStream_t)s>>>(*d, reinterpret_cast<const uint4*>(dy16), scale, rps);
+  NEF_CHECK_LAUNCH("bias_grad_h_kernel");
   return 0;
 }
 

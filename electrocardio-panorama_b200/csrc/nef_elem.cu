@@ -823,7 +823,7 @@ __global__ void __launch_bounds__(256, 3) latent_bwd_kernel(const LatentBwdArgs 
             gsum = make_float4(z[k].x > 0.f ? gsum.x : 0.f, z[k].y > 0.f ? gsum.y : 0.f, z[k].z > 0.f ? gsum.z : 0.f,
                                z[k].w > 0.f ? gsum.w : 0.f);
             gsum = tf32_rn4(gsum);
-            *a.gz1.at(g * 32 + cc, b, l) = gsum;
+            if (!a.skip_gz1_32) *a.gz1.at(g * 32 + cc, b, l) = gsum;
             if (a.gz1_h) {   // this block's 4 channels are one half of the 16-byte fp16 row (the block of chunk cc ^ 1 writes the other)
               uint2* hp = reinterpret_cast<uint2*>(reinterpret_cast<uint4*>(a.gz1_h) + (long)((g * 32 + cc) >> 1) * a.gz1.cs + a.gz1.row(b, l));
               hp[cc & 1] = make_uint2(f16x2_sat(gsum.x * s16, gsum.y * s16), f16x2_sat(gsum.z * s16, gsum.w * s16));

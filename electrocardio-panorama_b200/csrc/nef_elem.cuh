@@ -83,6 +83,7 @@ struct LatentBwdArgs {
   T4 gz1;                 // out: grad wrt pre-ReLU z1 (128G, L4)
   void* gz1_h;            // optional: fp16 copy of gz1 (8 channels per 16-byte row) multiplied by s16[0] (device scalar)
   const float* s16;
+  int skip_gz1_32;        // 1: only the fp16 copy gz1_h is written
   T4 gz2o;                // out: grad wrt pre-ReLU z2o (896G, 32)
   float* dq;              // out (B, 256), overwritten
   int direct;             // 1: dlat[k] ARE the latent gradients (no upsample / query adjoint, dq untouched); 0: from du0

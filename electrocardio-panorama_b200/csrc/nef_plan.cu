@@ -1000,6 +1000,7 @@ static int wgrad_h(const void* dy16, const T4& dy, int dy_off, int dy_gs, const 
   return nef_gconv_wgrad_f16(&d, dy16, x16, inv_scale, (nef_stream_t)s);
 }
 extern "C" int nef_bias_grad_tc(const NefWgradDesc* d, nef_stream_t s);
+extern "C" int nef_bias_grad_h(const NefWgradDesc* d, const void* dy16, const float* scale, nef_stream_t s);
 static int block_bwd(const BlockBwd& b, float drop_p, CD& fin, cudaStream_t s) {
   const BlockIO& io = b.io;
   // Full fp16 backward of the block: every operand of its convolutions' data and weight gradients is an fp16 copy (the
@@ -1013,9 +1014,9 @@ static int block_bwd(const BlockBwd& b, float drop_p, CD& fin, cudaStream_t s) {
       if (b.dbr) {
         NefWgradDesc d;
         memset(&d, 0, sizeof(d));
-        d.dy = reinterpret_cast<const float*>(b.gy.p); d.dy_cstride = b.gy.cs; d.dy_c4_off = 0; d.dy_c4_gstride = 32;
+        d.dy_cstride = b.gy.cs; d.dy_c4_off = 0; d.dy_c4_gstride = 32;
         d.cout_g = io.cr->cout_g; d.groups = io.cr->groups; d.rows = b.gy.cs; d.db = b.dbr; d.wg_mod = io.cr->src_gmod;
-        RUN(nef_bias_grad_tc(&d, (nef_stream_t)s));
+        RUN(nef_bias_grad_h(&d, b.gy16, inv, (nef_stream_t)s));   // the fp32 gy of such a block is not stored
       }
     }
     CD a(io.groups, 128, io.x);
@@ -1205,6 +1206,7 @@ extern "C" int nef_backward(NefPlan* p, const NefBackwardArgs* a, nef_stream_t s
   lb.z1 = p->z1; lb.z2o = p->z2o; lb.rois = p->rois_in; lb.q = p->q; lb.q_stride = 256; lb.G = G; lb.c1 = p->c1; lb.c2 = p->c2;
   lb.gz1 = p->GA[0]; lb.gz2o = p->gz2o; lb.dq = p->dq;
   lb.gz1_h = f16 ? p->GA_h[0] : nullptr; lb.s16 = ls;
+  lb.skip_gz1_32 = f16 ? 1 : 0;   // the fp16 backward of z1_conv reads the fp16 copy only
   RUN(latent_bwd(lb, s));
   if (Gd[P_MLP2_W]) RUN(angular_bwd(p->query_in, p->dq, Gd[P_MLP2_W], Gd[P_MLP2_B], B, 256, s));
 
@@ -1430,6 +1432,11 @@ extern "C" int nef_stem_fwd(const float* x, const float* w, float* y, uint32_t* 
 extern "C" int nef_stem_tc_fwd(const float* x, const float* w, void* y16, uint32_t* argmax, int B, int G, int L, nef_stream_t s) {
   NEF_REQUIRE(x && w && y16 && L % 4 == 0, "nef_stem_tc_fwd: bad arguments");
   return stem_tc_fwd(x, w, view_t4(nullptr, 128 * G, B, L / 4), argmax, y16, G, (cudaStream_t)s);
+}
+extern "C" int nef_stem_tc_bwd(const float* x, const uint32_t* argmax, const void* dy16, float* dw, const float* inv_scale, int B, int G,
+                               int L, nef_stream_t s) {
+  NEF_REQUIRE(x && argmax && dy16 && dw && L % 4 == 0, "nef_stem_tc_bwd: bad arguments");
+  return stem_tc_bwd(x, argmax, dy16, view_t4(nullptr, 128 * G, B, L / 4), dw, inv_scale, G, (cudaStream_t)s);
 }
 extern "C" int nef_stem_bwd(const float* x, const uint32_t* argmax, const float* dy, float* dw, int B, int G, int L,
                             nef_stream_t s) {

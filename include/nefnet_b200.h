@@ -334,6 +334,10 @@ int nef_stem_bwd(const float* x, const uint32_t* argmax, const float* dy, float*
 /* The stem forward on the tensor cores (split-precision fp16 MMAs, fp32-accurate): writes the fp16 copy y16 (half8 rows,
  * layout of nef_ncl_to_h8 for (B, 128 G, L / 4)) and the argmax codes (may be NULL) -- the production form of the stem. */
 int nef_stem_tc_fwd(const float* x, const float* w, void* y16, uint32_t* argmax, int B, int G, int L, nef_stream_t s);
+/* The stem weight gradient on the tensor cores: dy16 = fp16 copy (layout of y16 above) of the gradient of the stem output,
+ * multiplied by a loss scale S; inv_scale = device pointer to 1 / S (NULL = 1); dw (128 G, 1, 15) accumulates (+=). */
+int nef_stem_tc_bwd(const float* x, const uint32_t* argmax, const void* dy16, float* dw, const float* inv_scale, int B, int G,
+                    int L, nef_stream_t s);
 /* Angular encoding + Linear, theta_encoder.py:13-29 + model_nefnet.py:76-77: (n,2) -> (n,D) */
 int nef_angular_fwd(const float* theta, const float* w, const float* b, float* out, int n, int D, nef_stream_t s);
 int nef_angular_bwd(const float* theta, const float* dout, float* dw, float* db, int n, int D, nef_stream_t s);
