@@ -13,6 +13,7 @@
 //     x_hi w_hi + x_lo w_hi + x_hi w_lo      (three accumulating kind::f16 MMAs per set; the dropped x_lo w_lo term is 2^-22)
 // A CTA owns 32 output channels of one lead (M128 x N32 x K16 MMAs, 96 TMEM columns) and walks (segment, 128-output tile)
 // units; four such CTAs share an SM, so one CTA's epilogue overlaps the others' loads and MMAs without any in-kernel pipeline.
+#include <cstdlib>
 #include <cuda_fp16.h>
 
 #include "nef_elem.cuh"
@@ -120,16 +121,18 @@ __device__ long long g_stem_dbg[8][8];
   } while (0)
 constexpr int SF_THREADS = 128;
 constexpr int SF_TJ = 128;                 // pooled outputs per tile = MMA M
-constexpr int SF_NC = 32;                  // output channels per CTA = MMA N
 constexpr int SF_XW = 4 * SF_TJ + 24;      // input window of a tile: x[4 j0 - 9 .. 4 j0 + 4 * 128 + 14]
 constexpr int SF_AROWS = SF_TJ + 8;        // rows per k chunk plane of an A tile (the O tile holds rows j = -1 .. 127)
 constexpr int SF_APITCH = SF_AROWS * 16;   // bytes between the two k chunks
 constexpr int SF_ABYTES = 2 * SF_APITCH;   // one A tile (K = 16 halves = 2 chunks)
-constexpr int SF_BBYTES = 2 * SF_NC * 16;  // one B tile: [k chunk][channel][8 halves]
 
-__global__ void __launch_bounds__(SF_THREADS, 4) stem_tc_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, T4 y,
+// SF_NC = output channels per CTA = MMA N (32: 96 TMEM columns, four CTAs per SM; 16: 48 columns, eight CTAs per SM)
+template <int SF_NC>
+__global__ void __launch_bounds__(SF_THREADS, 512 / (SF_NC == 32 ? 128 : 64)) stem_tc_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, T4 y,
                                                                     uint32_t* __restrict__ amax, uint4* __restrict__ y16, int G, int L,
                                                                     int w_shared) {
+  constexpr int SF_BBYTES = 2 * SF_NC * 16;   // one B tile: [k chunk][channel][8 halves]
+  constexpr uint32_t TM_COLS = SF_NC == 32 ? 128 : 64;
   __shared__ __align__(128) uint8_t s_a[4 * SF_ABYTES];   // E_hi, E_lo, O_hi, O_lo
   __shared__ __align__(128) uint8_t s_b[2 * SF_BBYTES];   // w_hi, w_lo
   __shared__ __align__(16) __half s_xh[SF_XW + 8], s_xl[SF_XW + 8];
@@ -145,7 +148,7 @@ __global__ void __launch_bounds__(SF_THREADS, 4) stem_tc_fwd_kernel(const float*
     mbar_init(bar, 1);
     fence_barrier_init();
   }
-  if (warp == 0) tmem_alloc(smem_u32(&s_tmem), 128);
+  if (warp == 0) tmem_alloc(smem_u32(&s_tmem), TM_COLS);
   // weights of this CTA's 32 channels, split into fp16 hi / lo, K-major: slot [k chunk][n] = taps 8 kc .. 8 kc + 7 (tap 15 = 0)
   for (int i = tid; i < 2 * SF_NC; i += SF_THREADS) {
     const int kc = i / SF_NC, n = i % SF_NC;
@@ -273,35 +276,39 @@ __global__ void __launch_bounds__(SF_THREADS, 4) stem_tc_fwd_kernel(const float*
       const bool va = j > 0;   // conv position 2j - 1 exists
       const uint32_t tl = tmem + ((uint32_t)(warp * 32) << 16);
       const long row = y.row(b, ok ? j : 0);
+      // all accumulator columns of this thread's row in one round trip (3 x SF_NC registers), then one pass over them
+      uint32_t ve[SF_NC], vo[SF_NC], vm[SF_NC];
+      if constexpr (SF_NC == 32) {
+        tmem_ld32(tl + 0 * SF_NC, ve);
+        tmem_ld32(tl + 1 * SF_NC, vo);
+        tmem_ld32(tl + 2 * SF_NC, vm);
+      } else {
+        tmem_ld16(tl + 0 * SF_NC, ve);
+        tmem_ld16(tl + 1 * SF_NC, vo);
+        tmem_ld16(tl + 2 * SF_NC, vm);
+      }
+      tmem_ld_wait();
+      uint32_t hp[4];
 #pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {   // 16 channels at a time (48 accumulator registers in flight)
-        uint32_t ve[16], vo[16], vm[16];
-        tmem_ld16(tl + 0 * SF_NC + hh * 16, ve);
-        tmem_ld16(tl + 1 * SF_NC + hh * 16, vo);
-        tmem_ld16(tl + 2 * SF_NC + hh * 16, vm);
-        tmem_ld_wait();
-        uint32_t hp[4];
+      for (int c4 = 0; c4 < SF_NC / 4; ++c4) {
+        uint32_t code = 0;
+        float m[4];
 #pragma unroll
-        for (int c4 = 0; c4 < 4; ++c4) {
-          uint32_t code = 0;
-          float m[4];
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const float c0 = __uint_as_float(vm[4 * c4 + k]), c1 = __uint_as_float(ve[4 * c4 + k]), c2 = __uint_as_float(vo[4 * c4 + k]);
-            uint32_t best = 1;
-            float bv = c1;
-            if (va && c0 >= c1) { best = 0; bv = c0; }   // first maximum wins (window order), as MaxPool1d
-            if (c2 > bv) { best = 2; bv = c2; }
-            if (!(bv > 0.f)) { best = 3; bv = 0.f; }
-            m[k] = bv;   // the fp16 conversion below is the only rounding
-            code |= best << (8 * k);
-          }
-          const int ch4 = g * 32 + cq * 8 + hh * 4 + c4;   // 4-channel chunk of the 128 G channel space
-          if (amax && ok) amax[(long)ch4 * y.cs + row] = code;
-          hp[(c4 & 1) * 2 + 0] = f16x2_sat(m[0], m[1]);
-          hp[(c4 & 1) * 2 + 1] = f16x2_sat(m[2], m[3]);
-          if ((c4 & 1) && ok) y16[(long)(ch4 >> 1) * y.cs + row] = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+        for (int k = 0; k < 4; ++k) {
+          const float c0 = __uint_as_float(vm[4 * c4 + k]), c1 = __uint_as_float(ve[4 * c4 + k]), c2 = __uint_as_float(vo[4 * c4 + k]);
+          uint32_t best = 1;
+          float bv = c1;
+          if (va && c0 >= c1) { best = 0; bv = c0; }   // first maximum wins (window order), as MaxPool1d
+          if (c2 > bv) { best = 2; bv = c2; }
+          if (!(bv > 0.f)) { best = 3; bv = 0.f; }
+          m[k] = bv;   // the fp16 conversion below is the only rounding
+          code |= best << (8 * k);
         }
+        const int ch4 = g * 32 + cq * (SF_NC / 4) + c4;   // 4-channel chunk of the 128 G channel space
+        if (amax && ok) amax[(long)ch4 * y.cs + row] = code;
+        hp[(c4 & 1) * 2 + 0] = f16x2_sat(m[0], m[1]);
+        hp[(c4 & 1) * 2 + 1] = f16x2_sat(m[2], m[3]);
+        if ((c4 & 1) && ok) y16[(long)(ch4 >> 1) * y.cs + row] = make_uint4(hp[0], hp[1], hp[2], hp[3]);
       }
     }
     tc_fence_before();
@@ -310,7 +317,7 @@ __global__ void __launch_bounds__(SF_THREADS, 4) stem_tc_fwd_kernel(const float*
   }
   if (warp == 0) {
     tc_fence_after();
-    tmem_dealloc(tmem, 128);
+    tmem_dealloc(tmem, TM_COLS);
   }
 }
 
@@ -501,12 +508,17 @@ int stem_tc_fwd(const float* x, const float* w, T4 y, uint32_t* amax, void* y16,
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  long gx = ((long)sms * 4) / ((long)G * 4);   // four CTAs per SM over (lead, channel quarter) pairs
+  static int nc = getenv("NEF_STEM_NC") ? atoi(getenv("NEF_STEM_NC")) : 32;   // A/B: 16 = eight CTAs of 16 channels per SM
+  const int per_sm = nc == 16 ? 8 : 4, nz = 128 / (nc == 16 ? 16 : 32);
+  long gx = ((long)sms * per_sm) / ((long)G * nz);   // per_sm CTAs per SM over (lead, channel slice) pairs
   if (gx < 1) gx = 1;
   if (gx > units) gx = units;
-  dim3 grid((unsigned)gx, (unsigned)G, 4);
-  // 25 KB of unused dynamic shared memory keep a fifth CTA off the SM: it would only wait for TMEM columns (4 x 128 = all 512)
-  stc::stem_tc_fwd_kernel<<<grid, stc::SF_THREADS, 25 * 1024, s>>>(x, w, y, amax, reinterpret_cast<uint4*>(y16), G, L, w_shared);
+  dim3 grid((unsigned)gx, (unsigned)G, (unsigned)nz);
+  // unused dynamic shared memory keeps one CTA too many off the SM: it would only wait for TMEM columns (all 512 are taken)
+  if (nc == 16)
+    stc::stem_tc_fwd_kernel<16><<<grid, stc::SF_THREADS, 6 * 1024, s>>>(x, w, y, amax, reinterpret_cast<uint4*>(y16), G, L, w_shared);
+  else
+    stc::stem_tc_fwd_kernel<32><<<grid, stc::SF_THREADS, 25 * 1024, s>>>(x, w, y, amax, reinterpret_cast<uint4*>(y16), G, L, w_shared);
   NEF_CHECK_LAUNCH("stem_tc_fwd_kernel");
   return 0;
 }
