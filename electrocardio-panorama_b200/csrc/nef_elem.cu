@@ -447,7 +447,36 @@ __global__ void roi_align_bwd_kernel(T4 dra, const int64_t* __restrict__ rois, T
   }
 }
 
-int roi_align_fwd(T4 z2c, const int64_t* rois, T4 ra, Window win, int L4, cudaStream_t s) {
+// the same into the fp16 operand copy of ra only (half8 rows, geometry of ra): one thread per 8 channels
+__global__ void roi_align_fwd_h_kernel(T4 z2c, const int64_t* __restrict__ rois, T4 ra, uint4* __restrict__ ra16, Window win, int L4) {
+  const long total = (long)(ra.C / 8) * ra.B * NEF_ROI_SIZE;
+  const int c0 = win.y0 - win.w0;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int s = i % NEF_ROI_SIZE;
+    long r = i / NEF_ROI_SIZE;
+    const int b = r % ra.B;
+    const int ch8 = r / ra.B;
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int ch = ch8 * 8 + k;
+      const int c = ch / NEF_NROI, j = ch % NEF_NROI;
+      const float4* zp = z2c.at(c >> 2, b, c0);
+      float centre = f4get(zp[0], c & 3) * (1.0f - win.wy1);
+      if (win.wy1 > 0.f && c0 + 1 < win.Lw) centre += f4get(zp[1], c & 3) * win.wy1;
+      v[k] = centre * roi_wx(rois, b, j, s, L4);
+    }
+    ra16[(long)ch8 * ra.cs + ra.row(b, s)] = make_uint4(f16x2_sat(v[0], v[1]), f16x2_sat(v[2], v[3]), f16x2_sat(v[4], v[5]), f16x2_sat(v[6], v[7]));
+  }
+}
+
+int roi_align_fwd(T4 z2c, const int64_t* rois, T4 ra, Window win, int L4, cudaStream_t s, void* ra16) {
+  if (ra16) {
+    const long total = (long)(ra.C / 8) * ra.B * NEF_ROI_SIZE;
+    roi_align_fwd_h_kernel<<<grid_for(total, 256), 256, 0, s>>>(z2c, rois, ra, reinterpret_cast<uint4*>(ra16), win, L4);
+    NEF_CHECK_LAUNCH("roi_align_fwd_h_kernel");
+    return 0;
+  }
   const long total = (long)(ra.C / 4) * ra.B * NEF_ROI_SIZE;
   roi_align_fwd_kernel<<<grid_for(total, 256), 256, 0, s>>>(z2c, rois, ra, win, L4);
   NEF_CHECK_LAUNCH("roi_align_fwd_kernel");
@@ -536,6 +565,27 @@ __global__ void deinterleave2_kernel(T4 src, T4 even, T4 odd) {
     *even.at(c4, b, l) = sp[0];
     *odd.at(c4, b, l) = sp[1];
   }
+}
+// the same on fp16 copies (half8 rows; geometries of src / even)
+__global__ void deinterleave2_h_kernel(const uint4* __restrict__ src16, T4 src, uint4* __restrict__ even16, uint4* __restrict__ odd16, T4 even) {
+  const long total = (long)(src.C / 8) * src.B * even.L;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int l = i % even.L;
+    long r = i / even.L;
+    const int b = r % src.B;
+    const int c8 = r / src.B;
+    const uint4* sp = src16 + (long)c8 * src.cs + src.row(b, 2 * l);
+    const long o = (long)c8 * even.cs + even.row(b, l);
+    even16[o] = sp[0];
+    odd16[o] = sp[1];
+  }
+}
+int deinterleave2_h(const void* src16, T4 src, void* even16, void* odd16, T4 even, cudaStream_t s) {
+  const long total = (long)(src.C / 8) * src.B * even.L;
+  deinterleave2_h_kernel<<<grid_for(total, 256), 256, 0, s>>>(reinterpret_cast<const uint4*>(src16), src, reinterpret_cast<uint4*>(even16),
+                                                               reinterpret_cast<uint4*>(odd16), even);
+  NEF_CHECK_LAUNCH("deinterleave2_h_kernel");
+  return 0;
 }
 int deinterleave2(T4 src, T4 even, T4 odd, cudaStream_t s) {
   const long total = (long)(src.C / 4) * src.B * even.L;
@@ -772,6 +822,7 @@ __global__ void __launch_bounds__(256, 3) latent_bwd_kernel(const LatentBwdArgs 
   const int L2 = 2 * L4;
   const float s16 = (a.gz1_h && a.s16) ? __ldg(a.s16) : 1.f;
   const float inv16 = a.s16 ? __ldg(a.s16 + 1) : 1.f;   // 1 / S of the loss-scaled fp16 input gradients du0h
+  const float s16z = (a.gz2o_h && a.s16) ? __ldg(a.s16) : 1.f;
   for (int t0 = 0; t0 < L4; t0 += LB_TL) {
    const int nl = min(LB_TL, L4 - t0);
    for (int l = t0 + tid; l < t0 + nl; l += 256) {
@@ -901,7 +952,13 @@ __global__ void __launch_bounds__(256, 3) latent_bwd_kernel(const LatentBwdArgs 
         if (g == a.c2) v += Tp[chl * 32 + pos];
         f4at(o, e) = f4get(z, e) > 0.f ? v : 0.f;
       }
-      *a.gz2o.at(g * 224 + cc * 7 + m, b, pos) = tf32_rn4(o);
+      if (a.gz2o_h) {   // loss-scaled fp16 copy only: this chunk's 4 channels are one half of a 16-byte row
+        const int c4 = g * 224 + cc * 7 + m;
+        uint2* hp = reinterpret_cast<uint2*>(reinterpret_cast<uint4*>(a.gz2o_h) + (long)(c4 >> 1) * a.gz2o.cs + a.gz2o.row(b, pos));
+        hp[c4 & 1] = make_uint2(f16x2_sat(o.x * s16z, o.y * s16z), f16x2_sat(o.z * s16z, o.w * s16z));
+      } else {
+        *a.gz2o.at(g * 224 + cc * 7 + m, b, pos) = tf32_rn4(o);
+      }
     }
   }
 }

@@ -47,9 +47,10 @@ int window_scatter(T4 gxw, T4 gw, int G, Window win, void* gw16, const float* s1
 // scale[0] = S, scale[1] = 1 / S, S = 2^k with S * max|d0, d1, d2| in [32, 64) (1 if all zero); scale[2] is scratch
 int grad_loss_scale(const float* d0, const float* d1, const float* d2, long n, float* scale, cudaStream_t s);
 int roi_check(const int64_t* rois, int B, int L4, int* flag, cudaStream_t s);   // flag[3]: bad segments, first one, its length sum
-int roi_align_fwd(T4 z2c, const int64_t* rois, T4 ra, Window win, int L4, cudaStream_t s);
+int roi_align_fwd(T4 z2c, const int64_t* rois, T4 ra, Window win, int L4, cudaStream_t s, void* ra16 = nullptr);   // ra16: write only the fp16 copy
 int roi_align_bwd(T4 dra, const int64_t* rois, T4 z2c, T4 gz2c, Window win, int L4, cudaStream_t s);
 int deinterleave2(T4 src, T4 even, T4 odd, cudaStream_t s);
+int deinterleave2_h(const void* src16, T4 src, void* even16, void* odd16, T4 even, cudaStream_t s);   // fp16 copies (half8 rows)
 // gradient of the angular scale s (model_nefnet.py:120-123): ys = relu(u) * s[b, c]; gx = d ys * s * (ys != 0)  ->
 //   ds[b, c] = sum_l d ys * relu(u) = sum_l gx * ys / s^2      (overwrites ds)
 int bscale_grad(T4 gx, T4 ys, const float* scale, float* ds, cudaStream_t s);
@@ -84,6 +85,7 @@ struct LatentBwdArgs {
   void* gz1_h;            // optional: fp16 copy of gz1 (8 channels per 16-byte row) multiplied by s16[0] (device scalar)
   const float* s16;
   int skip_gz1_32;        // 1: only the fp16 copy gz1_h is written
+  void* gz2o_h;           // optional: gz2o is written ONLY as this fp16 copy (times s16[0])
   T4 gz2o;                // out: grad wrt pre-ReLU z2o (896G, 32)
   float* dq;              // out (B, 256), overwritten
   int direct;             // 1: dlat[k] ARE the latent gradients (no upsample / query adjoint, dq untouched); 0: from du0

@@ -76,6 +76,9 @@ static int g_keep_h32 = 0, g_k3_tf32 = 0;
 static int g_dec_f16 = 1;
 // 1 (default) = the stem runs on the tensor cores (nef_stem_tc.cu) whenever only its fp16 copy is kept (NEF_STEM_TC=0: CUDA cores)
 static int g_stem_tc = 1;
+// 1 (default) = the z2 deflection branch (z2_conv2: residual block, ConvTranspose, residual block on 7 G groups) runs on fp16
+// operand copies forward and backward like the big blocks (NEF_Z2_F16=0: TF32 operands, fp32 tensors)
+static int g_z2_f16 = 1;
 extern "C" int nef_set_dec_f16(int on) { g_dec_f16 = on; return 0; }
 extern "C" int nef_gconv_wgrad_f16(const NefWgradDesc* d, const void* dy16, const void* x16, const float* out_scale, nef_stream_t s);
 extern "C" int nef_set_dec1_terms(int n) {
@@ -108,6 +111,7 @@ extern "C" int nef_init(int device) {
   if (getenv("NEF_BWD_F16")) g_bwd_f16 = atoi(getenv("NEF_BWD_F16"));
   if (getenv("NEF_DEC_F16")) g_dec_f16 = atoi(getenv("NEF_DEC_F16"));
   if (getenv("NEF_STEM_TC")) g_stem_tc = atoi(getenv("NEF_STEM_TC"));
+  if (getenv("NEF_Z2_F16")) g_z2_f16 = atoi(getenv("NEF_Z2_F16"));
   int rc = elem_init();
   if (rc) return rc;
   return nef_tc_init();
@@ -269,6 +273,13 @@ struct NefPlan {
   T4 dg4, dg3, du1, dg2, dg1, du0[3];
   void *dg4_h, *dg3_h, *du1_h, *dg2_h, *dg1_h;   // loss-scaled fp16 gradient copies of the decoder backward (dec_f16)
   bool dec_f16;                     // this forward / backward pair runs the fp16 decoder dataflow
+  // z2 deflection branch on fp16 copies (z2_f16): activations ra, h20, y20, t21, h22 and the gradients between the layers exist
+  // as fp16 copies (+ one-bit planes of h20, y20, h22) only
+  void *ra_h, *h20_h, *y20_h, *t21_h, *h22_h;
+  uint32_t *b_h20, *b_y20, *b_h22;
+  void *gz2o_h, *gh22_h, *dt21_h, *dte_h, *dto_h, *gy20_h, *gh20_h;
+  void *ct_h[2], *ct_dh[2];         // fp16 packings of the ConvTranspose weights (forward / data gradient, per tap)
+  bool z2_f16;
   bool u0_f16_only;                 // the decoder inputs u0 of this forward exist as fp16 copies (u0_h, u0lo_h) only
   void* du0_h[3];                   // loss-scaled fp16 gradients of the decoder inputs (dec_f16, variant 1)
   float *ds_in, *dq;
@@ -347,6 +358,12 @@ static void carve(NefPlan* p, bool dry) {
   p->xw = c.t4(64 * G, p->win.Lw); p->hz = c.t4(C1, p->win.Lw); p->z2c = c.t4(C1, p->win.Lw);
   p->ra = c.t4(896 * G, 16); p->h20 = c.t4(896 * G, 16); p->y20 = c.t4(896 * G, 16);
   p->t21 = c.t4(448 * G, 32); p->h22 = c.t4(896 * G, 32); p->z2o = c.t4(896 * G, 32);
+  {
+    auto h8 = [&](const T4& t) { return c.take(((size_t)(t.C / 8) * t.cs + NEF_GUARD_ROWS) * 16); };
+    auto bits = [&](const T4& t) { return reinterpret_cast<uint32_t*>(c.take(((size_t)(t.C / 32) * t.cs + NEF_GUARD_ROWS) * sizeof(uint32_t))); };
+    p->ra_h = h8(p->ra); p->h20_h = h8(p->h20); p->y20_h = h8(p->y20); p->t21_h = h8(p->t21); p->h22_h = h8(p->h22);
+    p->b_h20 = bits(p->h20); p->b_y20 = bits(p->y20); p->b_h22 = bits(p->h22);
+  }
   for (int k = 0; k < 3; ++k) { p->lat[k] = c.t4(256, L4); p->u0[k] = c.t4(256, L2); p->u0lo[k] = c.t4(256, L2); }
   for (int k = 0; k < 3; ++k) {
     const size_t bytes = ((size_t)(256 / 8) * p->u0[k].cs + NEF_GUARD_ROWS) * 16;
@@ -395,6 +412,11 @@ static void carve(NefPlan* p, bool dry) {
   p->dte = c.t4(448 * G, 16); p->dto = c.t4(448 * G, 16);
   p->gy20 = c.t4(896 * G, 16); p->gh20 = c.t4(896 * G, 16); p->dra = c.t4(896 * G, 16);
   p->gz2c = c.t4(C1, p->win.Lw); p->ghz = c.t4(C1, p->win.Lw); p->gxw = c.t4(64 * G, p->win.Lw);
+  {
+    auto h8 = [&](const T4& t) { return c.take(((size_t)(t.C / 8) * t.cs + NEF_GUARD_ROWS) * 16); };
+    p->gz2o_h = h8(p->gz2o); p->gh22_h = h8(p->gh22); p->dt21_h = h8(p->dt21); p->dte_h = h8(p->dte); p->dto_h = h8(p->dto);
+    p->gy20_h = h8(p->gy20); p->gh20_h = h8(p->gh20);
+  }
   p->dg4 = c.t4(64, L); p->dg3 = c.t4(64, L); p->du1 = c.t4(128, L); p->dg2 = c.t4(128, L2); p->dg1 = c.t4(128, L2);
   for (int k = 0; k < 3; ++k) p->du0[k] = c.t4(256, L2);
   for (int k = 0; k < 3; ++k) p->du0_h[k] = c.take(((size_t)(256 / 8) * p->du0[k].cs + NEF_GUARD_ROWS) * 16);
@@ -426,6 +448,10 @@ static void carve(NefPlan* p, bool dry) {
   carve_convw(c, p->z2b[0], P_Z2B + 0, 7 * G, 128, 64, 3, m7);
   carve_convw(c, p->z2b[1], P_Z2B + 1, 7 * G, 128, 128, 3, m7);
   carve_convw(c, p->z2b[2], P_Z2B + 2, 7 * G, 128, 64, 1, m7);
+  for (ConvW* w : {&p->z2a[0], &p->z2a[1], &p->z2b[0], &p->z2b[1], &p->z2b[2]}) {
+    w->pk_h = c.take((size_t)w->groups * w->cout_g * w->cin_g * w->taps * 2);
+    w->pk_dh = c.take((size_t)w->groups * w->cout_g * w->cin_g * w->taps * 2);
+  }
   carve_convw(c, p->decw[0], P_DEC1 + 0, 1, 128, 256, 3);
   p->decw[0].pk_h = c.take((size_t)128 * 256 * 3 * 2);
   p->dec1_lo_h = c.take((size_t)128 * 256 * 3 * 2);
@@ -443,6 +469,8 @@ static void carve(NefPlan* p, bool dry) {
   for (int t = 0; t < 2; ++t) {
     p->ct_f[t] = c.f32((size_t)7 * G * 128 * 64);
     p->ct_d[t] = c.f32((size_t)7 * G * 128 * 64);
+    p->ct_h[t] = c.take((size_t)7 * G * 128 * 64 * 2);
+    p->ct_dh[t] = c.take((size_t)7 * G * 128 * 64 * 2);
   }
   if (p->variant == 2) {
     carve_convw(c, p->s12[0], P_S1_W, 1, 128, 128, 3);
@@ -868,17 +896,20 @@ extern "C" int nef_forward(NefPlan* p, const NefForwardArgs* a, nef_stream_t sv)
   }
   // the fp32 hidden activations of the big blocks have a reader only in the TF32 backward (its weight gradients)
   p->h_f16_only = p->fwd_f16 && (p->bwd_f16 || !a->save_for_backward) && !g_keep_h32;
+  p->z2_f16 = p->h_f16_only && g_z2_f16;
   RUN(for_all_convw(p, [&](const ConvW& w) {
     if (&w >= p->decw && &w < p->decw + 4) return 0;
     const bool k3 = (&w >= p->wc && &w < p->wc + 2) || (&w >= p->z1c && &w < p->z1c + 3);
-    if (p->fwd_f16 && w.pk_h && !(k3 && g_k3_tf32))
+    const bool z2 = (&w >= p->z2a && &w < p->z2a + 2) || (&w >= p->z2b && &w < p->z2b + 3);
+    if (p->fwd_f16 && w.pk_h && !(k3 && g_k3_tf32) && !(z2 && !p->z2_f16))
       return queue_pack(packs, P[w.pidx], reinterpret_cast<float*>(w.pk_h), w.groups, w.cout_g, w.cin_g, w.taps,
                         (int64_t)w.cout_g * w.cin_g * w.taps, (int64_t)w.cin_g * w.taps, w.taps, 1, 4, s, nullptr, w.src_gmod);
     return pack_fwd(packs, w, P, s);
   }));
   RUN(queue_decoder_packs(p, packs, P, !a->bn_training && !a->save_for_backward, s));
   for (int t = 0; t < 2; ++t)  // ConvTranspose1d weight (Cin_total, Cout/groups, 2): one 1x1 conv per tap
-    RUN(queue_pack(packs, P[P_CT_W] + t, p->ct_f[t], 7 * G, 64, 128, 1, 128LL * 64 * 2, 2, 64 * 2, 0, 0, s, nullptr, v2 ? 7 : 0));
+    RUN(queue_pack(packs, P[P_CT_W] + t, p->z2_f16 ? reinterpret_cast<float*>(p->ct_h[t]) : p->ct_f[t], 7 * G, 64, 128, 1, 128LL * 64 * 2, 2,
+                   64 * 2, 0, p->z2_f16 ? 4 : 0, s, nullptr, v2 ? 7 : 0));
   RUN(nef_pack_weights_batch(&packs, s));
 
   if (p->fwd_f16 && p->h_f16_only && g_stem_tc)   // fp16 dataflow: the first block reads only the fp16 copy
@@ -922,19 +953,32 @@ extern "C" int nef_forward(NefPlan* p, const NefForwardArgs* a, nef_stream_t sv)
     BlockIO io{p->xw, 0, 16, p->hz, p->z2c, &p->z2c1[0], &p->z2c1[1], &p->z2c1[2], b_z2c1, G};
     RUN(block_fwd(io, dp, seed + 5, nullptr, s));
   }
-  RUN(roi_align_fwd(p->z2c, a->rois, p->ra, p->win, p->L4, s));
+  RUN(roi_align_fwd(p->z2c, a->rois, p->ra, p->win, p->L4, s, p->z2_f16 ? p->ra_h : nullptr));
   {
     BlockIO io{p->ra, 0, 32, p->h20, p->y20, &p->z2a[0], &p->z2a[1], nullptr, nullptr, 7 * G};
+    if (p->z2_f16) {   // fp16 copies (+ bit planes for the backward) only
+      io.x16 = p->ra_h; io.h16 = p->h20_h; io.y16 = p->y20_h; io.h_f16_only = true; io.y_f16_only = true;
+      if (a->save_for_backward) { io.hbits = p->b_h20; io.ybits = p->b_y20; }
+    }
     RUN(block_fwd(io, dp, seed + 6, nullptr, s));
   }
   for (int t = 0; t < 2; ++t) {  // ConvTranspose1d(k2, s2): out[2l + t] = W_t x[l] + b
     CD c(7 * G, 64, p->y20);
-    c.term(p->y20, 0, 32, 128, 1, p->ct_f[t]).out(p->t21, 0, 16, 2, t).bias(b_ct).round();
+    if (p->z2_f16) {
+      c.term16(p->y20_h, p->y20.cs, 0, 16, 128, 1, p->ct_h[t]).out(p->t21, 0, 16, 2, t).bias(b_ct).y16(p->t21_h);
+      c.d.y = nullptr;
+    } else {
+      c.term(p->y20, 0, 32, 128, 1, p->ct_f[t]).out(p->t21, 0, 16, 2, t).bias(b_ct).round();
+    }
     c.d.term[0].tap_off = 0;
     RUN(c.run(s));
   }
   {
     BlockIO io{p->t21, 0, 16, p->h22, p->z2o, &p->z2b[0], &p->z2b[1], &p->z2b[2], b_z2b, 7 * G};
+    if (p->z2_f16) {   // the block output z2o stays fp32 (latent mixing reads it)
+      io.x16 = p->t21_h; io.h16 = p->h22_h; io.h_f16_only = true;
+      if (a->save_for_backward) io.hbits = p->b_h22;
+    }
     RUN(block_fwd(io, dp, seed + 7, nullptr, s));
   }
   NEF_REQUIRE(!(v2 && a->phase == NEF_PHASE_GEN), "nef_forward: phase 'gen' is not built for Model_nefnet2 (its gen_ecg cannot consume it)");
@@ -961,6 +1005,7 @@ extern "C" int nef_gen_ecg(NefPlan* p, const float* const* P, const float* z1, c
   packs.n = 0;
   p->fwd_f16 = g_fwd_f16 && g_conv_impl == 1;
   p->dec_f16 = false;
+  p->z2_f16 = false;
   p->u0_f16_only = p->fwd_f16;
   RUN(queue_decoder_packs(p, packs, P, true, s));   // gen_ecg runs the module in eval mode (model_nefnet.py:197)
   RUN(nef_pack_weights_batch(&packs, s));
@@ -1163,11 +1208,13 @@ extern "C" int nef_backward(NefPlan* p, const NefBackwardArgs* a, nef_stream_t s
   const bool f16 = p->bwd_f16 && g_conv_impl == 1;
   RUN(for_all_convw(p, [&](const ConvW& w) {
     const bool dec = &w >= p->decw && &w < p->decw + 4;
-    if (f16 && w.pk_dh && (!dec || p->dec_f16)) return pack_dgrad_h(packs, w, P, s);   // the TF32 data-gradient packing of these layers is not read
+    const bool z2 = (&w >= p->z2a && &w < p->z2a + 2) || (&w >= p->z2b && &w < p->z2b + 3);
+    if (f16 && w.pk_dh && (!dec || p->dec_f16) && (!z2 || p->z2_f16)) return pack_dgrad_h(packs, w, P, s);   // the TF32 data-gradient packing of these layers is not read
     return pack_dgrad(packs, w, P, s);
   }));
   for (int t = 0; t < 2; ++t)  // ConvTranspose dgrad: dx[l] = sum_t W_t^T dy[2l + t] ; N' = ci (128), K' = co (64)
-    RUN(queue_pack(packs, P[P_CT_W] + t, p->ct_d[t], 7 * G, 128, 64, 1, 128LL * 64 * 2, 64 * 2, 2, 0, 0, s, nullptr, v2 ? 7 : 0));
+    RUN(queue_pack(packs, P[P_CT_W] + t, (f16 && p->z2_f16) ? reinterpret_cast<float*>(p->ct_dh[t]) : p->ct_d[t], 7 * G, 128, 64, 1, 128LL * 64 * 2,
+                   64 * 2, 2, 0, (f16 && p->z2_f16) ? 4 : 0, s, nullptr, v2 ? 7 : 0));
   RUN(nef_pack_weights_batch(&packs, s));
   // zero the BatchNorm backward accumulators (s1, s2 of every layer)
   for (int k = 0; k < 3; ++k)
@@ -1207,6 +1254,8 @@ extern "C" int nef_backward(NefPlan* p, const NefBackwardArgs* a, nef_stream_t s
   lb.gz1 = p->GA[0]; lb.gz2o = p->gz2o; lb.dq = p->dq;
   lb.gz1_h = f16 ? p->GA_h[0] : nullptr; lb.s16 = ls;
   lb.skip_gz1_32 = f16 ? 1 : 0;   // the fp16 backward of z1_conv reads the fp16 copy only
+  const bool z2h = f16 && p->z2_f16;
+  lb.gz2o_h = z2h ? p->gz2o_h : nullptr;
   RUN(latent_bwd(lb, s));
   if (Gd[P_MLP2_W]) RUN(angular_bwd(p->query_in, p->dq, Gd[P_MLP2_W], Gd[P_MLP2_B], B, 256, s));
 
@@ -1230,11 +1279,20 @@ extern "C" int nef_backward(NefPlan* p, const NefBackwardArgs* a, nef_stream_t s
                 Gd[P_Z2B + 0], Gd[P_Z2B + 1], Gd[P_Z2B + 2], Gd[P_Z2B + 3]};
     CD fin(7 * G, 64, p->t21);
     fin.out(p->dt21, 0, 16).round();
+    if (z2h) {
+      bb.io.x16 = p->t21_h; bb.io.h16 = p->h22_h; bb.io.hbits = p->b_h22;
+      bb.gy16 = p->gz2o_h; bb.gh16 = p->gh22_h; bb.lscale = ls;
+      fin.d.round_tf32 = 0;
+      fin.y16s(p->dt21_h, ls);
+      fin.d.y = nullptr;
+    }
     RUN(block_bwd(bb, dp, fin, s));
   }
-  RUN(deinterleave2(p->dt21, p->dte, p->dto, s));
+  if (z2h) RUN(deinterleave2_h(p->dt21_h, p->dt21, p->dte_h, p->dto_h, p->dte, s));
+  else RUN(deinterleave2(p->dt21, p->dte, p->dto, s));
   {
     const T4* dts[2] = {&p->dte, &p->dto};
+    const void* dts16[2] = {p->dte_h, p->dto_h};
     for (int t = 0; t < 2; ++t) {
       float* dw = Gd[P_CT_W] ? Gd[P_CT_W] + t : nullptr;
       if (dw) {
@@ -1244,13 +1302,27 @@ extern "C" int nef_backward(NefPlan* p, const NefBackwardArgs* a, nef_stream_t s
         d.x = reinterpret_cast<const float*>(p->y20.p); d.x_cstride = p->y20.cs; d.x_c4_off = 0; d.x_c4_gstride = 32;
         d.cout_g = 64; d.cin_g = 128; d.groups = 7 * G; d.taps = 1; d.tap_off = 0; d.rows = p->y20.cs;
         d.dw = dw; d.sg = 128LL * 64 * 2; d.sm = 2; d.sn = 64 * 2; d.st = 0; d.db = Gd[P_CT_B]; d.wg_mod = v2 ? 7 : 0;
-        RUN(nef_gconv_wgrad(&d, sv));
+        if (z2h) {
+          RUN(nef_gconv_wgrad_f16(&d, dts16[t], p->y20_h, ls + 1, sv));
+          if (d.db) RUN(nef_bias_grad_h(&d, dts16[t], ls + 1, sv));
+        } else {
+          RUN(nef_gconv_wgrad(&d, sv));
+        }
       }
     }
     CD c(7 * G, 128, p->y20);
-    c.term(p->dte, 0, 16, 64, 1, p->ct_d[0]).term(p->dto, 0, 16, 64, 1, p->ct_d[1]);
+    if (z2h) {
+      c.term16(p->dte_h, p->dte.cs, 0, 8, 64, 1, p->ct_dh[0]).term16(p->dto_h, p->dto.cs, 0, 8, 64, 1, p->ct_dh[1]);
+      c.d.acc_scale = ls + 1;
+    } else {
+      c.term(p->dte, 0, 16, 64, 1, p->ct_d[0]).term(p->dto, 0, 16, 64, 1, p->ct_d[1]);
+    }
     c.d.term[0].tap_off = 0; c.d.term[1].tap_off = 0;
     c.out(p->gy20, 0, 32).mask(p->y20, 0, 32, 1, 1.f).round();
+    if (z2h) {
+      c.mbits(p->b_y20).y16s(p->gy20_h, ls);
+      c.d.y = nullptr;
+    }
     RUN(c.run(s));
   }
   {
@@ -1258,6 +1330,10 @@ extern "C" int nef_backward(NefPlan* p, const NefBackwardArgs* a, nef_stream_t s
                 Gd[P_Z2A + 0], Gd[P_Z2A + 1], nullptr, nullptr};
     CD fin(7 * G, 128, p->ra);
     fin.out(p->dra, 0, 32);
+    if (z2h) {
+      bb.io.x16 = p->ra_h; bb.io.h16 = p->h20_h; bb.io.hbits = p->b_h20;
+      bb.gy16 = p->gy20_h; bb.gh16 = p->gh20_h; bb.lscale = ls;
+    }
     RUN(block_bwd(bb, dp, fin, s));
   }
   RUN(roi_align_bwd(p->dra, p->rois_in, p->z2c, p->gz2c, p->win, p->L4, s));
@@ -1336,7 +1412,8 @@ static bool find_tensor(const NefPlan* p, const char* name, NamedTensor* out) {
         {"W_encoder.layer1.0.h", &p->eh[0], p->b_eh[0]}, {"W_encoder.layer1.1.h", &p->eh[1], p->b_eh[1]},
         {"W_encoder.layer1.2.h", &p->eh[2], p->b_eh[2]}, {"W_encoder.layer1.0.y", &p->ey[0], p->b_ey[0]},
         {"W_encoder.layer1.1.y", &p->ey[1], p->b_ey[1]}, {"W_encoder.layer1.2.y", &p->ey[2], p->b_ey[2]},
-        {"w_conv.0.h", &p->hw, p->b_hw}, {"w_conv.0.y", &p->w, p->b_w}, {"z1_conv.0.h", &p->h1, p->b_h1}};
+        {"w_conv.0.h", &p->hw, p->b_hw}, {"w_conv.0.y", &p->w, p->b_w}, {"z1_conv.0.h", &p->h1, p->b_h1},
+        {"z2_conv2.0.h", &p->h20, p->b_h20}, {"z2_conv2.0.y", &p->y20, p->b_y20}, {"z2_conv2.2.h", &p->h22, p->b_h22}};
     for (auto& q : planes)
       if (n == q.name) { out->t = q.t; out->bits = q.b; return true; }
     return false;
@@ -1361,11 +1438,11 @@ static bool find_tensor(const NefPlan* p, const char* name, NamedTensor* out) {
     return h_only(p->hw_h);
   }
   if (blk("z1_conv.0", p->h1, p->z1)) return h_only(p->h1_h);
-  if ( blk("z2_conv1.0", p->hz, p->z2c) ||
-      blk("z2_conv2.0", p->h20, p->y20) || blk("z2_conv2.2", p->h22, p->z2o))
-    return true;
-  if (is("roi_align")) { out->t = &p->ra; return true; }
-  if (is("z2_conv2.1")) { out->t = &p->t21; return true; }
+  if (blk("z2_conv1.0", p->hz, p->z2c)) return true;
+  if (blk("z2_conv2.0", p->h20, p->y20)) { if (p->z2_f16) out->h16 = out->t == &p->h20 ? p->h20_h : p->y20_h; return true; }
+  if (blk("z2_conv2.2", p->h22, p->z2o)) { if (p->z2_f16 && out->t == &p->h22) out->h16 = p->h22_h; return true; }
+  if (is("roi_align")) { out->t = &p->ra; if (p->z2_f16) out->h16 = p->ra_h; return true; }
+  if (is("z2_conv2.1")) { out->t = &p->t21; if (p->z2_f16) out->h16 = p->t21_h; return true; }
   for (int k = 0; k < 3; ++k) {
     const DecBufs& d = p->dec[k];
     const std::string pre = "dec" + std::to_string(k) + ".";

@@ -69,9 +69,10 @@ class B200Precision:
     ('<block>.h', '<block>.y', 'dec<k>.<stage>.<bn>'); the oracle then multiplies by it instead of applying ReLU (and the
     dropout keep-mask, which the pattern of a block's h contains).  acts: filled with the named intermediates of a run."""
 
-    def __init__(self, fwd_f16: bool = True, patterns=None, record: bool = False, dec_f16: bool = True):
+    def __init__(self, fwd_f16: bool = True, patterns=None, record: bool = False, dec_f16: bool = True, z2_f16: bool = True):
         self.fwd_f16 = fwd_f16
         self.dec_f16 = dec_f16 and fwd_f16     # decoder convolutions 2-4 on fp16 operand copies (nef_set_dec_f16)
+        self.z2_f16 = z2_f16 and fwd_f16       # the z2_conv2 chain on fp16 operand copies (NEF_Z2_F16)
         self.patterns = patterns or {}
         self.acts = {} if record else None
 
@@ -85,7 +86,7 @@ class B200Precision:
     def _ops(self, kind, x, w):
         if kind == "fp32":
             return x, w
-        if (kind == "fp16" and self.fwd_f16) or (kind == "dec" and self.dec_f16):
+        if (kind == "fp16" and self.fwd_f16) or (kind == "dec" and self.dec_f16) or (kind == "z2" and self.z2_f16):
             return _STE.apply(x, 1), _f16w(w)
         return x, _STE.apply(w, 0)
 
@@ -94,6 +95,8 @@ class B200Precision:
         return F.conv1d(x, w, b, **kw)
 
     def conv_transpose(self, x, w, b=None, **kw):
+        if self.z2_f16:
+            return F.conv_transpose1d(_STE.apply(x, 1), _f16w(w), b, **kw)
         return F.conv_transpose1d(x, _STE.apply(w, 0), b, **kw)
 
     def store(self, x):

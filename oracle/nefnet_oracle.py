@@ -217,7 +217,7 @@ def theta_features(theta: torch.Tensor) -> torch.Tensor:
 def _conv(prec, kind, x, w, b=None, **kw):
     """F.conv1d as the reference evaluates it (fp32), or as `prec` models the device's operand rounding.
     kind: 'fp16' (encoder k7 convs), 'dec' (decoder convolutions 2-4: fp16 operand copies in the fp16 decoder dataflow, else
-    TF32), 'tf32' (every other grouped conv), 'fp32' (CUDA-core / split-precision)."""
+    TF32), 'z2' (the z2_conv2 chain: the same under z2_f16), 'tf32' (every other grouped conv), 'fp32' (CUDA-core / split-precision)."""
     if prec is None:
         return F.conv1d(x, w, b, **kw)
     return prec.conv(kind, x, w, b, **kw)
@@ -275,7 +275,7 @@ def residual_block(x, w1, w2, groups, res_w=None, res_b=None, keep=None, p=0.2, 
     h = _obs(prec, name + ".h", _st(prec, h))
     y = _conv(prec, kind, h, w2, padding=pad, groups=groups)
     if y.shape[1] != x.shape[1]:
-        r = _conv(prec, "tf32", x, res_w, res_b, groups=groups)
+        r = _conv(prec, "z2" if kind == "z2" else "tf32", x, res_w, res_b, groups=groups)
     else:
         r = x
     y = _relu(prec, name + ".y", _pre(prec, y + r))
@@ -411,7 +411,7 @@ def latents(P, x, input_thetas, rois, G, keeps=None, stop_before_reverse=False, 
     z2 = _obs(prec, "roi_align", _st(prec, roi_align_center(z2, rois)))  # (B,128G,7,16) :136
     z2 = z2.reshape(B, 128 * G * N_ROI, ROI_SIZE)  # :137
     z2 = residual_block(z2, P["z2_conv2.0.conv1.weight"], P["z2_conv2.0.conv2.weight"], 7 * G, keep=kp("z2_conv2.0"),
-                        prec=prec, name="z2_conv2.0")
+                        prec=prec, kind="z2", name="z2_conv2.0")
     if prec is None:
         z2 = F.conv_transpose1d(z2, P["z2_conv2.1.weight"], P["z2_conv2.1.bias"], stride=2, groups=7 * G)
     else:
@@ -419,7 +419,7 @@ def latents(P, x, input_thetas, rois, G, keeps=None, stop_before_reverse=False, 
                                                       groups=7 * G)))
     z2 = residual_block(z2, P["z2_conv2.2.conv1.weight"], P["z2_conv2.2.conv2.weight"], 7 * G,
                         P["z2_conv2.2.residual_conv.weight"], P["z2_conv2.2.residual_conv.bias"],
-                        keep=kp("z2_conv2.2"), prec=prec, name="z2_conv2.2")
+                        keep=kp("z2_conv2.2"), prec=prec, kind="z2", name="z2_conv2.2")
     z2 = z2.view(B, 128 * G, N_ROI, 2 * ROI_SIZE)  # :138
     if stop_before_reverse:
         return z1, z2

@@ -41,9 +41,9 @@ FP32_GRAD_COS = 0.99
 #   5164 first convolutions of the big blocks (dropout, fp16 copy, bit plane), 21540 / 21796 their second convolutions
 #   (residual read from the fp16 copy; angular scale), 37 z1_conv's second convolution, 513 decoder forward with BatchNorm
 #   statistics, 14368 / 30752 / 31008 / 28672 the loss-scaled fp16 data gradients (the last one feeds the tensor-core stem gradient), 12288 | NOY the decoder's data gradients
-#   (fp16 in, loss-scaled fp16 out), 32 the z2 branch's
+#   and the z2 branch's (fp16 in, loss-scaled fp16 out)
 NOY = 32768   # EPI_NOY: no fp32 store, only the fp16 copy / bit plane of the result
-BENCH_EPI_DROPOUT = {5164 | NOY, 21540 | NOY, 21796 | NOY, 37, 513, 14368 | NOY, 30752 | NOY, 31008 | NOY, 28672 | NOY, 12288 | NOY, 32}
+BENCH_EPI_DROPOUT = {5164 | NOY, 21540 | NOY, 21796 | NOY, 37, 513, 14368 | NOY, 30752 | NOY, 31008 | NOY, 28672 | NOY, 12288 | NOY}
 
 
 BLOCKS = ("W_encoder.layer1.0", "W_encoder.layer1.1", "W_encoder.layer1.2", "w_conv.0", "z1_conv.0", "z2_conv1.0", "z2_conv2.0",
@@ -71,7 +71,8 @@ def _device_patterns(m, B, G, L):
                 full = torch.ones(B, a.shape[1], L4, dtype=torch.bool)
                 full[:, :, w0:w0 + Lw] = a != 0
                 pat["%s.%s" % (blk, s)] = full
-            elif (blk.startswith("W_encoder") or blk == "w_conv.0" or (blk == "z1_conv.0" and s == "h")):
+            elif (blk.startswith("W_encoder") or blk == "w_conv.0" or (blk == "z1_conv.0" and s == "h") or blk == "z2_conv2.0"
+                  or (blk == "z2_conv2.2" and s == "h")):
                 # the backward pass of these reads one-bit planes recorded from the fp32 value (the fp16 copy of a tiny
                 # positive activation may flush to zero): take the pattern the device actually applies
                 pat["%s.%s" % (blk, s)] = m.export_activation("%s.%s.mask" % (blk, s)).cpu() != 0

@@ -31,7 +31,8 @@ for d in launch.values():
     ms = d.get("gpu__time_duration.sum", 0.0)
     a["n"] += 1; a["ms"] += ms
     a["bytes"] += d.get("dram__bytes_read.sum", 0.0) + d.get("dram__bytes_write.sum", 0.0)
-    a["tc"] += ms * d.get("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", 0.0)
+    a["tc"] += ms * d.get("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
+                          d.get("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", 0.0))
 tot = sum(a["ms"] for a in agg.values())
 print("%-58s %4s %9s %6s %9s %9s %6s %7s" % ("kernel", "n", "ms", "%step", "DRAM GB", "GB/s", "%HBM", "tensor%"))
 for n, a in sorted(agg.items(), key=lambda kv: -kv[1]["ms"]):
