@@ -1144,7 +1144,7 @@ static int g_tc_mt = 0;  // 0 = automatic; 4 forces four row tiles per CTA, one 
 // the specialised epilogues instantiated for the 4-row-tile kernel (everything else takes the generic one)
 #define NEF_TC_EPI_LIST(X) X(0) X(2) X(5) X(32) X(33) X(36) X(37) X(38) X(44) X(48) X(50) X(64) X(294) X(418) X(513) \
   X(1062) X(1068) X(1318) X(2080) X(2082) X(2338) X(4132) X(4134) X(4390) X(5158) X(5164) X(5414) X(8194) X(14368) X(14370) X(14626) X(21540) X(21796) X(24576) X(30752) X(31008) \
-  X(37932) X(54308) X(54564) X(47136) X(63520) X(63776) X(45056) X(8224) X(61440) X(36865)   /* the production fp16-only stores: 5164, 21540, 21796, 14368, 30752, 31008 | EPI_NOY */
+  X(37932) X(54308) X(54564) X(47136) X(63520) X(63776) X(45056) X(8224) X(61440) X(36865) X(36869)   /* the production fp16-only stores: 5164, 21540, 21796, 14368, 30752, 31008 | EPI_NOY */
 
 // the epilogues of the k7 / 128-channel fp16 layers (forward with dropout, second convolutions with the fp16 residual, masked
 // and unmasked loss-scaled data gradients): instantiated with 8 epilogue warps too

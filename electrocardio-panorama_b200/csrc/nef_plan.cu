@@ -656,7 +656,7 @@ static int queue_decoder_packs(NefPlan* p, NefPackTable& t, const float* const* 
       RUN(queue_pack(t, P[w.pidx], reinterpret_cast<float*>(p->dec1_lo_h), 1, 128, 256, 3, 0, 256 * 3, 3, 1, 4 | 2, s, ns));
       continue;
     }
-    if (i > 0 && p->dec_f16 && !fold) {
+    if (i > 0 && (p->dec_f16 || (fold && p->fwd_f16 && g_dec_f16))) {   // fp16 operand packing (with the folded scales in inference)
       const ConvW& w = p->decw[i];
       RUN(queue_pack(t, P[w.pidx], reinterpret_cast<float*>(w.pk_h), 1, w.cout_g, w.cin_g, 3, 0, (int64_t)w.cin_g * 3, 3, 1, 4, s, ns));
       continue;
@@ -735,6 +735,9 @@ static int decoder_fwd(NefPlan* p, const float* const* P, int slot, int lslot, c
   if (p->folded) {  // inference: conv (BatchNorm folded into weights and bias) + ReLU epilogues, one upsample pass
     const T4 ins[4] = {u0, d.a1, d.u1, d.a3};
     const T4 outs[4] = {d.a1, d.c2, d.a3, d.c4};
+    const bool h = p->fwd_f16 && g_dec_f16;   // a1 / u1 / a3 as fp16 operand copies only (c2 and c4 stay fp32)
+    const void* in16[4] = {nullptr, d.a1_h, d.u1_h, d.a3_h};
+    void* out16[4] = {d.a1_h, nullptr, d.a3_h, nullptr};
     for (int i = 0; i < 4; ++i) {
       const ConvW& w = p->decw[i];
       CD c(1, w.cout_g, ins[i]);
@@ -742,6 +745,8 @@ static int decoder_fwd(NefPlan* p, const float* const* P, int slot, int lslot, c
         c.term16(u0h, u0.cs, 0, 0, 256, 3, w.pk_h);
         if (g_dec1_terms >= 2) c.term16(u0loh, u0.cs, 0, 0, 256, 3, w.pk_h);
         if (g_dec1_terms >= 3) c.term16(u0h, u0.cs, 0, 0, 256, 3, p->dec1_lo_h);
+      } else if (h) {
+        c.term16(in16[i], ins[i].cs, 0, 0, w.cin_g, 3, w.pk_h);
       } else {
         c.term(ins[i], 0, 0, w.cin_g, 3, w.pk_f);
         if (i == 0) {
@@ -750,9 +755,11 @@ static int decoder_fwd(NefPlan* p, const float* const* P, int slot, int lslot, c
         }
       }
       c.out(outs[i], 0, 0).bias(p->fold_bias[i]).relu();
-      if (i == 0 || i == 2) c.round();  // a1, a3 feed the next tensor-core convolution directly
+      if (h && out16[i]) { c.y16(out16[i]); c.d.y = nullptr; }
+      else if (i == 0 || i == 2) c.round();  // a1, a3 feed the next tensor-core convolution directly
       RUN(c.run(s));
-      if (i == 1) RUN(bn_relu(d.c2, p->ident_scale, p->ident_shift, d.u1, 1, s));
+      if (i == 1 && h) RUN(bn_relu_h(d.c2, p->ident_scale, p->ident_shift, d.u1_h, d.u1, 1, s));
+      else if (i == 1) RUN(bn_relu(d.c2, p->ident_scale, p->ident_shift, d.u1, 1, s));
     }
     RUN(dec_out_fwd(d.c4, p->ident_scale, p->ident_shift, P[P_OUT_W], P[P_OUT_B], d.out, p->L, s));
   } else {
@@ -1450,7 +1457,7 @@ static bool find_tensor(const NefPlan* p, const char* name, NamedTensor* out) {
     const char* nm[7] = {"decoder.1.0", "a1", "decoder.1.3", "u1", "decoder.3.0", "a3", "decoder.3.3"};
     const void* hs[7] = {nullptr, d.a1_h, nullptr, d.u1_h, nullptr, d.a3_h, nullptr};
     for (int i = 0; i < 7; ++i)
-      if (n == pre + nm[i]) { out->t = ts[i]; if (p->dec_f16) out->h16 = hs[i]; return true; }
+      if (n == pre + nm[i]) { out->t = ts[i]; if (p->dec_f16 || (p->folded && p->fwd_f16 && g_dec_f16)) out->h16 = hs[i]; return true; }
     if (n == pre + "u0") { out->t = &p->u0[k]; if (p->u0_f16_only) out->h16 = p->u0_h[k]; return true; }
     for (int i = 0; i < 4; ++i) {
       const std::string b = pre + "bn" + std::to_string(i) + ".";
