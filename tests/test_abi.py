@@ -117,7 +117,7 @@ def test_product_never_touches_the_oracle():
 
 def test_plan_sizing_is_host_only_and_fits_the_part(lib):
     """nef_plan_create / nef_plan_workspace_bytes make no CUDA call: the caller-owned workspace of every BASELINE
-    configuration is known before a device exists, and fits the 180 GB of HBM3e (57.6 GB at C2)."""
+    configuration is known before a device exists, and fits the 180 GB of HBM3e (70.1 GB at C2)."""
     import ctypes as C
     sizes = {}
     for name, (B, G, L, V) in {"C2": (256, 12, 5000, 0), "C4": (64, 12, 20000, 0), "C5": (64, 12, 5000, 24),
@@ -126,7 +126,7 @@ def test_plan_sizing_is_host_only_and_fits_the_part(lib):
         assert lib.nef_plan_create(B, G, L, V, C.byref(h)) == 0, lib.nef_last_error()
         sizes[name] = lib.nef_plan_workspace_bytes(h)
         lib.nef_plan_destroy(h)
-    assert 50.0 < sizes["C2"] / 1e9 < 70.0, sizes["C2"]   # 63.5 GB with the fp16 operand / gradient copies of round 2
+    assert 50.0 < sizes["C2"] / 1e9 < 75.0, sizes["C2"]   # 70.1 GB with the fp16 operand / gradient copies of every block
     assert all(v < 180e9 * 0.9 for v in sizes.values()) and sizes["tiny"] < 64e6
     assert sizes["C5"] < sizes["C2"] / 3      # nothing is saved for backward per view: the 24 views reuse one decoder slot
     for bad in ((0, 1, 16, 0), (1, 0, 16, 0), (1, 1, 18, 0), (1, 1, 8, 0)):
