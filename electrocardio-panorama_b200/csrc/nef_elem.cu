@@ -1365,7 +1365,7 @@ int up_adjoint_h(const void* du16, T4 du, void* da16, T4 da, cudaStream_t s) {
 // UPADJ: the gradient is not read but built -- the adjoint of the x2 linear upsampling of du16 (C, 2n), stored to da16 on
 // the way (up_adjoint_h fused with this pass: the BatchNorm behind the upsampled tensor).
 template <bool UPADJ>
-__global__ void __launch_bounds__(256) bnbwd_stats_h_kernel(const uint4* __restrict__ da16, T4 c, BnLayer bn, int seg_per_block,
+__global__ void __launch_bounds__(256, 3) bnbwd_stats_h_kernel(const uint4* __restrict__ da16, T4 c, BnLayer bn, int seg_per_block,
                                                             const uint4* __restrict__ du16, T4 du, uint4* __restrict__ da_out) {
   __shared__ float red[8][16];
   const int c8 = blockIdx.y;
@@ -1568,7 +1568,7 @@ int dec_out_fwd(T4 c4, const float* scale, const float* shift, const float* w, c
 // registers over all its positions; one block reduction at the end.
 constexpr int DOB_R = 4;               // consecutive samples per thread
 constexpr int DOB_SPAN = 256 * DOB_R;  // samples per block unit
-__global__ void __launch_bounds__(256) dec_out_bwd_kernel(T4 c4t, BnLayer bn, const float* __restrict__ w,
+__global__ void __launch_bounds__(256, 3) dec_out_bwd_kernel(T4 c4t, BnLayer bn, const float* __restrict__ w,
                                                           const float* __restrict__ out, const float* __restrict__ dout,
                                                           T4 g4, float* __restrict__ dw, float* __restrict__ db) {
   __shared__ float red[8][21];
