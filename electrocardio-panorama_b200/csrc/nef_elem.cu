@@ -1656,6 +1656,117 @@ int dec_out_bwd(T4 c4, const BnLayer& bn, const float* w, const float* out, cons
   return 0;
 }
 
+// The same with g4 leaving as the loss-scaled fp16 copy ONLY (fp16 decoder dataflow): g4h = fp16(S * g4), s1 / s2 in the same
+// scaled units taken over the stored (rounded) values, which is what bnbwd_apply_h's fp16-input form expects; dw / db are
+// multiplied back by 1 / S.  Adjacent lanes take the two 4-channel chunks of an 8-channel fp16 row and exchange halves by
+// shuffle, so every lane stores two whole 16-byte rows (one 32-byte sector).  grid: x = position blocks, y = the 8 rows' chunks.
+constexpr int DOH_R = 2;               // consecutive samples per lane pair (4 spills at three blocks per SM)
+constexpr int DOH_SPAN = 128 * DOH_R;  // samples per block unit
+__global__ void __launch_bounds__(256, 3) dec_out_bwd_h_kernel(T4 c4t, BnLayer bn, const float* __restrict__ w,
+                                                            const float* __restrict__ out, const float* __restrict__ dout,
+                                                            T4 g4, uint4* __restrict__ g4h, const float* __restrict__ lscale,
+                                                            float* __restrict__ dw, float* __restrict__ db) {
+  __shared__ float red[8][2][21];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int h2 = tid & 1, pg = tid >> 1;
+  const int c8 = blockIdx.y, c = 2 * c8 + h2;
+  const float4 w0 = make_float4(w[(c * 4 + 0) * 3 + 0], w[(c * 4 + 1) * 3 + 0], w[(c * 4 + 2) * 3 + 0], w[(c * 4 + 3) * 3 + 0]);
+  const float4 w1 = make_float4(w[(c * 4 + 0) * 3 + 1], w[(c * 4 + 1) * 3 + 1], w[(c * 4 + 2) * 3 + 1], w[(c * 4 + 3) * 3 + 1]);
+  const float4 w2 = make_float4(w[(c * 4 + 0) * 3 + 2], w[(c * 4 + 1) * 3 + 2], w[(c * 4 + 2) * 3 + 2], w[(c * 4 + 3) * 3 + 2]);
+  const float4 sc = reinterpret_cast<const float4*>(bn.scale)[c], sh = reinterpret_cast<const float4*>(bn.shift)[c];
+  const float4 mu = reinterpret_cast<const float4*>(bn.mean)[c], is = reinterpret_cast<const float4*>(bn.invstd)[c];
+  const float S = __ldg(lscale) * (1.0f / 3.0f), invS = __ldg(lscale + 1);
+  const int L = c4t.L;
+  float4 s1 = f4zero(), s2 = f4zero(), a_m = f4zero(), a_0 = f4zero(), a_p = f4zero();
+  float dbl = 0.f;
+  const int spans = (L + DOH_SPAN - 1) / DOH_SPAN;
+  for (long u = blockIdx.x; u < (long)c4t.B * spans; u += gridDim.x) {
+    const int b = (int)(u / spans);
+    const int l0 = (int)(u - (long)b * spans) * DOH_SPAN;
+    const int l = l0 + pg * DOH_R;
+    const bool act = l < L;   // (whole warps stay in the loop: the shuffles below need every lane)
+    const float* op = out + (long)b * L;
+    const float* dp = dout + (long)b * L;
+    const float4* p = c4t.at(c, b, 0);
+    // Only dy needs the neighbouring samples: the tap sums are taken per ACTIVATION row (dw[.,0] = sum_l a4[l] dy[l+1],
+    // dw[.,2] = sum_l a4[l] dy[l-1]; a4 and dy vanish outside [0, L)), so each conv-output row is loaded once.
+    float dy[DOH_R + 2];
+    float4 cv[DOH_R];
+#pragma unroll
+    for (int i = 0; i < DOH_R + 2; ++i) {
+      const int li = l - 1 + i;
+      const bool ok = act && li >= 0 && li < L;
+      const float o = ok ? op[li] : 0.f, d = ok ? dp[li] : 0.f;
+      dy[i] = d * o * (1.0f - o) * S;
+    }
+#pragma unroll
+    for (int i = 0; i < DOH_R; ++i) cv[i] = (act && l + i < L) ? p[l + i] : f4zero();
+    uint32_t hx[DOH_R], hy[DOH_R];
+#pragma unroll
+    for (int i = 0; i < DOH_R; ++i) {
+      // da4[l] = dy[l+1] w[.,0] + dy[l] w[.,1] + dy[l-1] w[.,2]
+      const float4 dd = w0 * dy[i + 2] + w1 * dy[i + 1] + w2 * dy[i];
+      const float4 cc = cv[i];
+      const float4 a0 = (act && l + i < L) ? bn_relu4(cc, sc, sh) : f4zero();
+      hx[i] = f16x2_sat(a0.x > 0.f ? dd.x : 0.f, a0.y > 0.f ? dd.y : 0.f);
+      hy[i] = f16x2_sat(a0.z > 0.f ? dd.z : 0.f, a0.w > 0.f ? dd.w : 0.f);
+      const float2 gx = __half22float2(*reinterpret_cast<const __half2*>(&hx[i]));
+      const float2 gy = __half22float2(*reinterpret_cast<const __half2*>(&hy[i]));
+      const float4 gv = make_float4(gx.x, gx.y, gy.x, gy.y);
+      const float4 xh = make_float4((cc.x - mu.x) * is.x, (cc.y - mu.y) * is.y, (cc.z - mu.z) * is.z, (cc.w - mu.w) * is.w);
+      s1 = s1 + gv;
+      s2 = s2 + gv * xh;
+      a_m = a_m + a0 * dy[i + 2];
+      a_0 = a_0 + a0 * dy[i + 1];
+      a_p = a_p + a0 * dy[i];
+      dbl += dy[i + 1];
+    }
+    // the even lane (channels 0..3) keeps the first DOH_R / 2 rows and needs the odd lane's halves of them; the odd lane keeps
+    // the rest: every lane stores DOH_R / 2 whole 16-byte rows
+    constexpr int HR = DOH_R / 2;
+    const int k0 = h2 ? HR : 0;
+#pragma unroll
+    for (int j = 0; j < HR; ++j) {
+      const uint32_t rx = __shfl_xor_sync(0xffffffffu, h2 ? hx[j] : hx[HR + j], 1), ry = __shfl_xor_sync(0xffffffffu, h2 ? hy[j] : hy[HR + j], 1);
+      const uint32_t ox = h2 ? hx[HR + j] : hx[j], oy = h2 ? hy[HR + j] : hy[j];
+      if (act && l + k0 + j < L)
+        g4h[(long)c8 * g4.cs + g4.row(b, l + k0 + j)] = h2 ? make_uint4(rx, ry, ox, oy) : make_uint4(ox, oy, rx, ry);
+    }
+  }
+  float v[21] = {s1.x, s1.y, s1.z, s1.w, s2.x, s2.y, s2.z, s2.w, a_m.x, a_m.y, a_m.z, a_m.w,
+                 a_0.x, a_0.y, a_0.z, a_0.w, a_p.x, a_p.y, a_p.z, a_p.w, dbl};
+#pragma unroll
+  for (int k = 0; k < 21; ++k) {   // lanes of one parity hold one chunk: lanes 0 and 1 end up with the two totals
+    float r = v[k];
+#pragma unroll
+    for (int off = 16; off >= 2; off >>= 1) r += __shfl_xor_sync(0xffffffffu, r, off);
+    if (lane < 2) red[warp][lane][k] = r;
+  }
+  __syncthreads();
+  if (tid < 42) {
+    const int hh = tid / 21, k = tid - hh * 21, ch4 = 2 * c8 + hh;
+    float r = 0.f;
+    for (int wp = 0; wp < 8; ++wp) r += red[wp][hh][k];
+    if (k < 4) atomicAdd(bn.s1 + ch4 * 4 + k, (double)r);
+    else if (k < 8) atomicAdd(bn.s2 + ch4 * 4 + k - 4, (double)r);
+    else if (k < 20) {
+      const int t = (k - 8) / 4, kk = (k - 8) % 4;
+      atomicAdd(dw + (ch4 * 4 + kk) * 3 + t, r * invS);
+    } else if (ch4 == 0) atomicAdd(db, r * invS);
+  }
+}
+int dec_out_bwd_h(T4 c4, const BnLayer& bn, const float* w, const float* out, const float* dout, T4 g4, void* g4h,
+                  const float* lscale, float* dw, float* db, cudaStream_t s) {
+  const long units = (long)c4.B * ((c4.L + DOH_SPAN - 1) / DOH_SPAN);
+  const long per = (units + 148 * 4 - 1) / (148 * 4);   // units per block: equal shares instead of a ragged last round
+  int gx = (int)((units + per - 1) / (per > 0 ? per : 1));
+  if (gx < 1) gx = 1;
+  dim3 grid(gx, 8);
+  dec_out_bwd_h_kernel<<<grid, 256, 0, s>>>(c4, bn, w, out, dout, g4, reinterpret_cast<uint4*>(g4h), lscale, dw, db);
+  NEF_CHECK_LAUNCH("dec_out_bwd_h_kernel");
+  return 0;
+}
+
 // ===========================================================================================
 // Standin-Learning loss, network/loss/losses.py:21-50 ; SGD, solver/optim_scheduler.py:10
 // ===========================================================================================

@@ -122,5 +122,8 @@ int dec_out_fwd(T4 c4, const float* scale, const float* shift, const float* w, c
                 int out_bstride, cudaStream_t s);
 int dec_out_bwd(T4 c4, const BnLayer& bn, const float* w, const float* out, const float* dout, T4 g4, float* dw,
                 float* db, cudaStream_t s);
+// fp16 decoder dataflow: g4 leaves as the loss-scaled fp16 copy g4h only (geometry of g4), s1 / s2 in scaled units
+int dec_out_bwd_h(T4 c4, const BnLayer& bn, const float* w, const float* out, const float* dout, T4 g4, void* g4h,
+                  const float* lscale, float* dw, float* db, cudaStream_t s);
 
 }  // namespace nef

@@ -1168,8 +1168,14 @@ static int decoder_bwd_h(NefPlan* p, const float* const* P, float* const* Gd, in
     return c.run(s);
   };
   // output layer + bn4 statistics (fp32 g4, unscaled), then bn4's backward into the scaled fp16 copy
-  RUN(dec_out_bwd(d.c4, d.bn[3], P[P_OUT_W], d.out, dout, p->dg4, g(P_OUT_W), g(P_OUT_B), s));
-  RUN(bnbwd_apply_h(&p->dg4, nullptr, d.c4, d.bn[3], P[P_DEC3 + 9], n1, p->dg4_h, g(P_DEC3 + 9), g(P_DEC3 + 10), 1, ls, s));
+  static const bool out_h = !getenv("NEF_DEC_OUT_H") || atoi(getenv("NEF_DEC_OUT_H")) != 0;   // A/B switch: 0 = fp32 g4
+  if (out_h) {   // g4 as the loss-scaled fp16 copy only, bn4's backward in place on it
+    RUN(dec_out_bwd_h(d.c4, d.bn[3], P[P_OUT_W], d.out, dout, p->dg4, p->dg4_h, ls, g(P_OUT_W), g(P_OUT_B), s));
+    RUN(bnbwd_apply_h(nullptr, p->dg4_h, d.c4, d.bn[3], P[P_DEC3 + 9], n1, p->dg4_h, g(P_DEC3 + 9), g(P_DEC3 + 10), 1, ls, s));
+  } else {
+    RUN(dec_out_bwd(d.c4, d.bn[3], P[P_OUT_W], d.out, dout, p->dg4, g(P_OUT_W), g(P_OUT_B), s));
+    RUN(bnbwd_apply_h(&p->dg4, nullptr, d.c4, d.bn[3], P[P_DEC3 + 9], n1, p->dg4_h, g(P_DEC3 + 9), g(P_DEC3 + 10), 1, ls, s));
+  }
   RUN(wgrad_h(p->dg4_h, p->dg4, 0, 0, d.a3_h, d.a3, 0, 0, p->decw[3], g(P_DEC3 + 7), inv, s));
   RUN(dgrad(3, p->dg4, p->dg4_h, p->dg3_h, p->dg3));
   RUN(bnbwd_stats_h(p->dg3_h, d.c3, d.bn[2], s));

@@ -129,7 +129,7 @@ static_assert(STAGE % 128 == 0 && YBYTES % 128 == 0, "stage alignment");
 // grid: x = input-channel tile (dcols channels), y = row split, z = group
 __global__ void __launch_bounds__(THREADS, 1) wgrad_f16_kernel(const __grid_constant__ NefWgradDesc d, const uint4* __restrict__ dy16,
                                                                const uint4* __restrict__ x16, const float* __restrict__ out_scale_p, int dcols,
-                                                               long rows_per_split, long rows_main) {
+                                                               long rows_per_split, long rows_main, int coalesced_drain) {
   extern __shared__ __align__(128) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
   const uint32_t bar0 = sbase + BAR_OFF;
@@ -236,6 +236,30 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_f16_kernel(const __grid_cons
     const float out_scale = out_scale_p ? __ldg(out_scale_p) : 1.f;
     mbar_wait(acc_full, 0);
     tc_fence_after();
+    float* const dwg = d.dw + (long)(d.wg_mod > 0 ? g % d.wg_mod : g) * d.sg;
+    if (coalesced_drain) {
+      // Conv1d weight layout [cout][cin][k]: for one output channel the (cin, tap) plane is one contiguous run.  A TMEM lane
+      // is an output channel, so a thread-per-lane RED touches 32 different lines per instruction (the drain of a k7 block
+      // was 114 k such sector requests per CTA).  Each drain warp transposes its 32 channels x (32 cin x taps) slab through
+      // the pipeline's shared memory (free once acc_full has fired; odd pitch = conflict-free both ways) and issues REDs whose
+      // 32 lanes cover 128 contiguous bytes.
+      const int run = 32 * ntap, pitch = run + 1;
+      float* slab = reinterpret_cast<float*>(smem) + q * (32 * 225);
+      for (int cg = 0; cg < dcols / 32; ++cg) {
+        for (int tp = 0; tp < ntap; ++tp) {
+          uint32_t v[32];
+          tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(tp * dcols + cg * 32), v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) slab[lane * pitch + i * ntap + tp] = __uint_as_float(v[i]) * out_scale;
+        }
+        __syncwarp();
+        float* dst = dwg + (long)(q * 32) * d.sm + (long)(tile * dcols + cg * 32) * ntap;
+        for (int r = 0; r < 32; ++r)
+          for (int c = lane; c < run; c += 32) atomicAdd(dst + (long)r * d.sm + c, slab[r * pitch + c]);
+        __syncwarp();
+      }
+    } else
     for (int tp = 0; tp < ntap; ++tp) {
       for (int cg = 0; cg < dcols / 32; ++cg) {
         uint32_t v[32];
@@ -311,9 +335,12 @@ extern "C" int nef_gconv_wgrad_f16(const NefWgradDesc* d, const void* dy16, cons
     const long st_per_split = (nst_total + best - 1) / best;
     const long splits = (nst_total + st_per_split - 1) / st_per_split;
     dim3 grid((unsigned)(d->cin_g / dcols), (unsigned)splits, (unsigned)d->groups);
+    // NEF_WGRAD_DRAIN=0: the thread-per-channel RED drain for every layout (A/B switch)
+    static const int drain_mode = getenv("NEF_WGRAD_DRAIN") ? atoi(getenv("NEF_WGRAD_DRAIN")) : 1;
+    const int coalesced = drain_mode && d->st == 1 && d->sn == d->taps;
     wf16::wgrad_f16_kernel<<<grid, wf16::THREADS, wf16::TOTAL, (cudaStream_t)s>>>(
         *d, reinterpret_cast<const uint4*>(dy16), reinterpret_cast<const uint4*>(x16), out_scale, dcols,
-        st_per_split * wf16::ROWS, rows_main);
+        st_per_split * wf16::ROWS, rows_main, coalesced);
     NEF_CHECK_LAUNCH("wgrad_f16_kernel");
     nef_tc_note_dispatch(5);
   }
