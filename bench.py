@@ -493,6 +493,34 @@ def main():
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
+    # N > 1: what the step pays for the exchange.  (a) the gradient all-reduce of the flat buffer alone; (b) the same step
+    # with the exchange switched off, per rank -- the ranks then run independently, so the spread between the fastest and the
+    # slowest GPU of the box (power cap) shows, which a synchronised step hides behind its max.
+    breakdown = None
+    if world > 1 and not sweep:
+        fg = model._flat_grad
+        dist.all_reduce(fg, op=dist.ReduceOp.AVG)
+        ms_ar = timed(lambda: dist.all_reduce(fg, op=dist.ReduceOp.AVG), args.steps) / args.steps
+        model.ddp_allreduce = False
+        step(resident)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        dist.barrier()
+        e0.record()
+        for _ in range(args.steps):
+            step(resident)
+        e1.record()
+        torch.cuda.synchronize()
+        mine = torch.tensor([e0.elapsed_time(e1) / args.steps], device=dev)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        model.ddp_allreduce = True
+        per_rank = [round(float(t), 3) for t in allr]
+        breakdown = {"allreduce_ms": ms_ar, "allreduce_bytes": int(fg.numel()) * 4,
+                     "step_ms_without_exchange_per_rank": per_rank,
+                     "step_ms_without_exchange_min": min(per_rank), "step_ms_without_exchange_max": max(per_rank),
+                     "overlap": os.environ.get("NEF_DDP_OVERLAP", "1" if world <= 2 else "0") != "0"}
+
     ms_step = ms / args.steps
     units = B * (V if sweep else 1)
     value = world * units / (ms_step / 1000.0)
@@ -549,6 +577,8 @@ def main():
                 }
         if ms_fwd is not None:
             line["forward"] = forward_report(ms_fwd, world, B, G, L, hbm_peak)
+        if breakdown is not None:
+            line["scaling_breakdown"] = breakdown
     if world > 1:
         dist.barrier()
     if rank == 0:

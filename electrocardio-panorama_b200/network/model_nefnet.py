@@ -431,8 +431,12 @@ class Model_nefnet(nn.Module):
             # bucket 1 (z1_conv .. decoder, 2/3 of the bytes) is final long before the encoder's backward ends: reduce it on
             # a side stream behind the event nef_backward recorded; bucket 0 (stem, encoder, mlp, w_conv) follows on the
             # main stream.  ReduceOp.AVG: the mean over ranks, as DataParallel's gradient of the batch-mean loss.
+            # Overlap policy (NEF_DDP_OVERLAP=0 / 1 forces it): measured on one box each, the overlapped form wins at 2 ranks
+            # (35.35 vs 35.47 ms) and loses at 8 (35.01 vs 34.79 ms) -- the NCCL kernel's CTAs keep a few SMs from taking
+            # their CTA of every persistent conv launch it runs beside (static tile walk), and at 8 ranks it runs longer.
             split = self._ddp_split
-            if os.environ.get("NEF_DDP_OVERLAP", "1") == "0":     # A/B switch: one all-reduce behind the whole backward
+            overlap = os.environ.get("NEF_DDP_OVERLAP", "1" if world <= 2 else "0") != "0"
+            if not overlap:     # one all-reduce behind the whole backward
                 dist.all_reduce(self._flat_grad, op=dist.ReduceOp.AVG)
                 split = None
         if world > 1 and split is not None:
