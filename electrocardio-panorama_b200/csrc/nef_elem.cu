@@ -417,24 +417,28 @@ __global__ void roi_align_fwd_kernel(T4 z2c, const int64_t* __restrict__ rois, T
   }
 }
 
+// One thread per (4-channel chunk, segment), adjacent threads on adjacent segments (a per-segment block with the weights in
+// shared memory measured 65 % SLOWER: its threads stride over chunk planes).  The tent weight of a (roi, sample) is evaluated
+// once for the thread's four channels; per channel the (roi, sample) summation order is unchanged.
 __global__ void roi_align_bwd_kernel(T4 dra, const int64_t* __restrict__ rois, T4 z2c, T4 gz2c, Window win, int L4) {
   const long total = (long)(z2c.C / 4) * z2c.B;
   const int c0 = win.y0 - win.w0;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     const int b = i % z2c.B;
     const int c4 = i / z2c.B;
-    float4 dc = f4zero();
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int j = 0; j < NEF_NROI; ++j) {
+      const float4* dp[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int c = c4 * 4 + k;
-      float acc = 0.f;
-      for (int j = 0; j < NEF_NROI; ++j) {
-        const int ch = c * NEF_NROI + j;
-        const float4* dp = dra.at(ch >> 2, b, 0);
-        for (int s = 0; s < NEF_ROI_SIZE; ++s) acc += f4get(dp[s], ch & 3) * roi_wx(rois, b, j, s, L4);
+      for (int k = 0; k < 4; ++k) dp[k] = dra.at(((c4 * 4 + k) * NEF_NROI + j) >> 2, b, 0);
+#pragma unroll 4
+      for (int s = 0; s < NEF_ROI_SIZE; ++s) {
+        const float wgt = roi_wx(rois, b, j, s, L4);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc[k] += f4get(dp[k][s], ((c4 * 4 + k) * NEF_NROI + j) & 3) * wgt;
       }
-      f4at(dc, k) = acc;
     }
+    const float4 dc = make_float4(acc[0], acc[1], acc[2], acc[3]);
     for (int l = 0; l < win.Lw; ++l) {
       float wgt = 0.f;
       if (l == c0) wgt = 1.0f - win.wy1;
@@ -447,32 +451,47 @@ __global__ void roi_align_bwd_kernel(T4 dra, const int64_t* __restrict__ rois, T
   }
 }
 
-// the same into the fp16 operand copy of ra only (half8 rows, geometry of ra): one thread per 8 channels
-__global__ void roi_align_fwd_h_kernel(T4 z2c, const int64_t* __restrict__ rois, T4 ra, uint4* __restrict__ ra16, Window win, int L4) {
-  const long total = (long)(ra.C / 8) * ra.B * NEF_ROI_SIZE;
+// the same into the fp16 operand copy of ra only (half8 rows, geometry of ra).  One thread per (8 z2c channels = 56 ra channels
+// = 7 fp16 rows, segment, sample): the seven tent weights of the sample are evaluated once per thread (they were re-evaluated
+// for every one of a thread's 8 channels: the kernel was instruction-bound at 12 % of HBM).
+__global__ void __launch_bounds__(256) roi_align_fwd_h_kernel(T4 z2c, const int64_t* __restrict__ rois, T4 ra, uint4* __restrict__ ra16, Window win, int L4) {
+  const int total = (z2c.C / 8) * ra.B * NEF_ROI_SIZE;
   const int c0 = win.y0 - win.w0;
-  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+  const bool two = win.wy1 > 0.f && c0 + 1 < win.Lw;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int s = i % NEF_ROI_SIZE;
-    long r = i / NEF_ROI_SIZE;
+    const int r = i / NEF_ROI_SIZE;
     const int b = r % ra.B;
-    const int ch8 = r / ra.B;
-    float v[8];
+    const int q = r / ra.B;
+    float cen[8], wx[NEF_NROI];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const int ch = ch8 * 8 + k;
-      const int c = ch / NEF_NROI, j = ch % NEF_NROI;
-      const float4* zp = z2c.at(c >> 2, b, c0);
-      float centre = f4get(zp[0], c & 3) * (1.0f - win.wy1);
-      if (win.wy1 > 0.f && c0 + 1 < win.Lw) centre += f4get(zp[1], c & 3) * win.wy1;
-      v[k] = centre * roi_wx(rois, b, j, s, L4);
+    for (int hh = 0; hh < 2; ++hh) {
+      const float4* zp = z2c.at(2 * q + hh, b, c0);
+      const float4 z0 = zp[0];
+      const float4 z1 = two ? zp[1] : f4zero();
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float centre = f4get(z0, k) * (1.0f - win.wy1);
+        if (two) centre += f4get(z1, k) * win.wy1;
+        cen[hh * 4 + k] = centre;
+      }
     }
-    ra16[(long)ch8 * ra.cs + ra.row(b, s)] = make_uint4(f16x2_sat(v[0], v[1]), f16x2_sat(v[2], v[3]), f16x2_sat(v[4], v[5]), f16x2_sat(v[6], v[7]));
+#pragma unroll
+    for (int j = 0; j < NEF_NROI; ++j) wx[j] = roi_wx(rois, b, j, s, L4);
+    const long row = ra.row(b, s);
+#pragma unroll
+    for (int m = 0; m < NEF_NROI; ++m) {   // ra channel 56 q + n, n = (local channel) * 7 + roi: fp16 row 7 q + m holds n = 8 m .. 8 m + 7
+      float v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = cen[(8 * m + k) / NEF_NROI] * wx[(8 * m + k) % NEF_NROI];
+      ra16[(long)(NEF_NROI * q + m) * ra.cs + row] = make_uint4(f16x2_sat(v[0], v[1]), f16x2_sat(v[2], v[3]), f16x2_sat(v[4], v[5]), f16x2_sat(v[6], v[7]));
+    }
   }
 }
 
 int roi_align_fwd(T4 z2c, const int64_t* rois, T4 ra, Window win, int L4, cudaStream_t s, void* ra16) {
   if (ra16) {
-    const long total = (long)(ra.C / 8) * ra.B * NEF_ROI_SIZE;
+    const long total = (long)(z2c.C / 8) * ra.B * NEF_ROI_SIZE;
     roi_align_fwd_h_kernel<<<grid_for(total, 256), 256, 0, s>>>(z2c, rois, ra, reinterpret_cast<uint4*>(ra16), win, L4);
     NEF_CHECK_LAUNCH("roi_align_fwd_h_kernel");
     return 0;
@@ -667,7 +686,7 @@ __device__ __forceinline__ void interp_src(int i, int n, int& i0, int& i1, float
 }
 
 constexpr int LAT_TL = 256;  // latent positions per inner tile
-constexpr int LB_TL = 1024;  // latent positions per tile of the backward kernel
+constexpr int LB_TL = 1280;  // latent positions per tile of the backward kernel (L4 = 1250 in one tile; 47 KB of shared memory)
 constexpr int LAT_GB = 12;   // leads whose loads are batched in the backward kernel
 
 // One block per (segment b, PAIR of 4-channel chunks of the 128 latent channels of a half, half: z1 | z2).  Adjacent lanes
@@ -714,7 +733,7 @@ __global__ void __launch_bounds__(256) latent_fwd_kernel(const LatentArgs a) {
       } else if (half == 0) {
         m = f4zero();
         p = f4zero();
-        for (int g0 = 0; g0 < a.G; g0 += 4) {  // four leads at a time: their loads are in flight together
+        for (int g0 = 0; g0 < a.G; g0 += 4) {  // four leads at a time: their loads are in flight together (6 / 12 measured the same)
           float4 v[4];
 #pragma unroll
           for (int k = 0; k < 4; ++k) v[k] = (g0 + k < a.G) ? __ldg(a.z1.at((g0 + k) * 32 + cc0 + h2, b, l)) : f4zero();
@@ -797,11 +816,91 @@ int latent_fwd(const LatentArgs& a, cudaStream_t s) {
   return 0;
 }
 
+// z1 half of latent_bwd on the production dataflow (loss-scaled fp16 du0 copies in, loss-scaled fp16 gz1 copy out only) as a
+// kernel of its own.  The general kernel below pays four dependent memory latencies per position (three groups of four 8-byte
+// gradient loads behind run-time branches, then the leads) at 37 % occupancy: latency-bound at 56 % of HBM.  Here a thread
+// requests the z1 rows of up to twelve leads AND all twelve gradient half-rows of its position together (24 loads, 288 bytes
+// in flight per thread; 128 registers, two blocks per SM = 98 KB in flight per SM), so one latency is exposed per position.
+// grid (32 chunks, B); the z2 half keeps the general kernel (only_half = 1).
+__device__ __forceinline__ float4 lb_h4(uint2 h) {
+  const float2 x = __half22float2(*reinterpret_cast<const __half2*>(&h.x)), y = __half22float2(*reinterpret_cast<const __half2*>(&h.y));
+  return make_float4(x.x, x.y, y.x, y.y);
+}
+__global__ void __launch_bounds__(256, 2) latent_bwd_z1_kernel(const LatentBwdArgs a) {
+  __shared__ float dq_s[4];
+  const int cc = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
+  if (tid < 4) dq_s[tid] = 0.f;
+  __syncthreads();
+  const int L4 = a.z1.L, L2 = 2 * L4, G = a.G;
+  const float4 qv = *reinterpret_cast<const float4*>(a.q + (long)b * a.q_stride + cc * 4);
+  const float invG = 1.0f / (float)G;
+  const float s16 = __ldg(a.s16), inv16 = __ldg(a.s16 + 1);
+  const uint2* du[3];
+#pragma unroll
+  for (int k3 = 0; k3 < 3; ++k3)
+    du[k3] = reinterpret_cast<const uint2*>(reinterpret_cast<const uint4*>(a.du0h[k3]) + (long)(cc >> 1) * a.du0[k3].cs + a.du0[k3].row(b, 0)) + (cc & 1);
+  const long zs = 32 * a.z1.cs, hs = 32 * a.gz1.cs;   // per-lead strides in float4 / uint2 units (16 cs uint4 = 32 cs uint2)
+  float4 dq = f4zero();
+  constexpr int GB = 12;
+  for (int l = tid; l < L4; l += 256) {
+    const float4* zp = a.z1.p + (long)cc * a.z1.cs + a.z1.row(b, l);
+    uint2* hp = reinterpret_cast<uint2*>(reinterpret_cast<uint4*>(a.gz1_h) + (long)(cc >> 1) * a.gz1.cs + a.gz1.row(b, l)) + (cc & 1);
+    float4 z[GB];
+#pragma unroll
+    for (int k = 0; k < GB; ++k) z[k] = k < G ? __ldg(zp + k * zs) : f4zero();
+    const int i2 = l + 1 < L4 ? 2 * l + 2 : L2 - 1, i3 = l >= 1 ? 2 * l - 1 : 0;
+    uint2 h[3][4];
+#pragma unroll
+    for (int k3 = 0; k3 < 3; ++k3) {
+      h[k3][0] = __ldg(du[k3] + 2 * (2 * l));
+      h[k3][1] = __ldg(du[k3] + 2 * (2 * l + 1));
+      h[k3][2] = __ldg(du[k3] + 2 * i2);
+      h[k3][3] = __ldg(du[k3] + 2 * i3);
+    }
+    float4 dk[3];
+#pragma unroll
+    for (int k3 = 0; k3 < 3; ++k3) {   // same order of operations as the general kernel
+      float4 d = lb_h4(h[k3][0]) * 0.75f + lb_h4(h[k3][1]) * 0.75f;
+      d = d + lb_h4(h[k3][2]) * 0.25f;
+      d = d + lb_h4(h[k3][3]) * 0.25f;
+      dk[k3] = d * inv16;
+    }
+    const float4 dmg = (dk[0] + dk[2]) * qv * invG, dp = dk[1] * qv;
+    float4 msum = f4zero(), pick = f4zero();
+    for (int g0 = 0; g0 < G; g0 += GB) {
+      if (g0 > 0) {
+#pragma unroll
+        for (int k = 0; k < GB; ++k) z[k] = g0 + k < G ? __ldg(zp + (g0 + k) * zs) : f4zero();
+      }
+#pragma unroll
+      for (int k = 0; k < GB; ++k) {
+        const int g = g0 + k;
+        if (g < G) {   // same summation order over the leads as latent_fwd
+          msum = msum + z[k];
+          float4 gsum = dmg;
+          if (g == a.c1) { gsum = gsum + dp; pick = z[k]; }
+          gsum = make_float4(z[k].x > 0.f ? gsum.x : 0.f, z[k].y > 0.f ? gsum.y : 0.f, z[k].z > 0.f ? gsum.z : 0.f, z[k].w > 0.f ? gsum.w : 0.f);
+          gsum = tf32_rn4(gsum);
+          hp[(long)g * hs] = make_uint2(f16x2_sat(gsum.x * s16, gsum.y * s16), f16x2_sat(gsum.z * s16, gsum.w * s16));
+        }
+      }
+    }
+    dq = dq + (dk[0] + dk[2]) * (msum * invG) + dk[1] * pick;
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float v = warp_sum(f4get(dq, k));
+    if (lane == 0) atomicAdd(&dq_s[k], v);
+  }
+  __syncthreads();
+  if (tid < 4) a.dq[(long)b * 256 + cc * 4 + tid] = dq_s[tid];
+}
+
 // Backward of the above.  d lat_k = q * up^T(d u0_k);  d q += sum lat_k * up^T(d u0_k)
 __global__ void __launch_bounds__(256, 3) latent_bwd_kernel(const LatentBwdArgs a) {
   extern __shared__ float4 sm[];
   const int L4 = a.z1.L;
-  const int half = blockIdx.x, cc = blockIdx.y, b = blockIdx.z;  // memory-bound z1 blocks next to atomics-bound z2 blocks
+  const int half = a.only_half >= 0 ? a.only_half : blockIdx.x, cc = blockIdx.y, b = blockIdx.z;  // memory-bound z1 blocks next to atomics-bound z2 blocks
   const int tid = threadIdx.x, lane = tid & 31;
   float* Tm = reinterpret_cast<float*>(sm);  // [4][7][32] adjoint-resampled d(mean) / d(pick)   (z2 half)
   float* Tp = Tm + 4 * 7 * 32;
@@ -823,12 +922,38 @@ __global__ void __launch_bounds__(256, 3) latent_bwd_kernel(const LatentBwdArgs 
   const float s16 = (a.gz1_h && a.s16) ? __ldg(a.s16) : 1.f;
   const float inv16 = a.s16 ? __ldg(a.s16 + 1) : 1.f;   // 1 / S of the loss-scaled fp16 input gradients du0h
   const float s16z = (a.gz2o_h && a.s16) ? __ldg(a.s16) : 1.f;
+  const bool all_h = !a.direct && a.du0h[0] && a.du0h[1] && a.du0h[2];   // (block-uniform)
   for (int t0 = 0; t0 < L4; t0 += LB_TL) {
    const int nl = min(LB_TL, L4 - t0);
    for (int l = t0 + tid; l < t0 + nl; l += 256) {
     float4 dk[3];
+    float4 lm = f4zero(), lp = f4zero();   // z2 half: the stored latents of this position (for dq)
+    if (all_h) {
+      // production dataflow: the twelve gradient half-rows (and the two latent rows) of the position are requested together --
+      // behind the run-time branches of the general form below they were three dependent groups of four (+ one)
+      uint2 h[3][4];
+      const int i2 = l + 1 < L4 ? 2 * l + 2 : L2 - 1, i3 = l >= 1 ? 2 * l - 1 : 0;
 #pragma unroll
-    for (int k3 = 0; k3 < 3; ++k3) {
+      for (int k3 = 0; k3 < 3; ++k3) {
+        const uint2* du = reinterpret_cast<const uint2*>(reinterpret_cast<const uint4*>(a.du0h[k3]) + (long)(latc >> 1) * a.du0[k3].cs +
+                                                         a.du0[k3].row(b, 0)) + (latc & 1);
+        h[k3][0] = __ldg(du + 2 * (2 * l));
+        h[k3][1] = __ldg(du + 2 * (2 * l + 1));
+        h[k3][2] = __ldg(du + 2 * i2);
+        h[k3][3] = __ldg(du + 2 * i3);
+      }
+      if (half == 1) { lm = *a.lat[0].at(latc, b, l); lp = *a.lat[2].at(latc, b, l); }
+#pragma unroll
+      for (int k3 = 0; k3 < 3; ++k3) {
+        float4 d = lb_h4(h[k3][0]) * 0.75f + lb_h4(h[k3][1]) * 0.75f;
+        d = d + lb_h4(h[k3][2]) * 0.25f;
+        d = d + lb_h4(h[k3][3]) * 0.25f;
+        dk[k3] = d * inv16;
+      }
+    } else {
+     if (half == 1 && !a.direct) { lm = *a.lat[0].at(latc, b, l); lp = *a.lat[2].at(latc, b, l); }
+#pragma unroll
+     for (int k3 = 0; k3 < 3; ++k3) {
       if (a.direct) {   // the latent gradients themselves are given (Model_nefnet2: upq_adjoint and two convolutions ran before)
         dk[k3] = *a.dlat[k3].at(latc, b, l);
         continue;
@@ -854,6 +979,7 @@ __global__ void __launch_bounds__(256, 3) latent_bwd_kernel(const LatentBwdArgs 
       if (l == 0) d = d + du[0] * 0.25f;
       if (l == L4 - 1) d = d + du[L2 - 1] * 0.25f;
       dk[k3] = d;
+     }
     }
     if (half == 0) {
       // lat_0 = lat_2 = mean over leads, lat_1 = lead c1 (this half): both are rebuilt from the z1 loads the ReLU mask
@@ -885,10 +1011,7 @@ __global__ void __launch_bounds__(256, 3) latent_bwd_kernel(const LatentBwdArgs 
       dq = dq + (dk[0] + dk[2]) * (msum * invG) + dk[1] * pick;
     } else {
       // lat_0 = lat_1 = mean (this half), lat_2 = lead c2
-      if (!a.direct) {
-        const float4 lm = *a.lat[0].at(latc, b, l), lp = *a.lat[2].at(latc, b, l);
-        dq = dq + (dk[0] + dk[1]) * lm + dk[2] * lp;
-      }
+      if (!a.direct) dq = dq + (dk[0] + dk[1]) * lm + dk[2] * lp;
       sdm[l - t0] = (dk[0] + dk[1]) * qv;
       sdp[l - t0] = dk[2] * qv;
     }
@@ -940,10 +1063,21 @@ __global__ void __launch_bounds__(256, 3) latent_bwd_kernel(const LatentBwdArgs 
   if (tid < 4 && !a.direct) a.dq[(long)b * 256 + latc * 4 + tid] = dq_s[tid];
   if (half == 1) {
     // g z2o[(g*128 + 4cc + k)*7 + j][pos] = (Tm/G + [g == c2] Tp) * (z2o > 0)
-    for (int i = tid; i < a.G * 7 * 32; i += 256) {
+    constexpr int ZB = 4;   // rows per batch: their loads are in flight together
+    for (int i0 = tid; i0 < a.G * 7 * 32; i0 += 256 * ZB) {
+     float4 zv[ZB];
+#pragma unroll
+     for (int u = 0; u < ZB; ++u) {
+       const int i = i0 + u * 256;
+       zv[u] = i < a.G * 7 * 32 ? *a.z2o.at((i >> 5) / 7 * 224 + cc * 7 + (i >> 5) % 7, b, i & 31) : f4zero();
+     }
+#pragma unroll
+     for (int u = 0; u < ZB; ++u) {
+      const int i = i0 + u * 256;
+      if (i >= a.G * 7 * 32) break;
       const int pos = i & 31, r = i >> 5;
       const int g = r / 7, m = r % 7;
-      const float4 z = *a.z2o.at(g * 224 + cc * 7 + m, b, pos);
+      const float4 z = zv[u];
       float4 o;
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
@@ -959,13 +1093,23 @@ __global__ void __launch_bounds__(256, 3) latent_bwd_kernel(const LatentBwdArgs 
       } else {
         *a.gz2o.at(g * 224 + cc * 7 + m, b, pos) = tf32_rn4(o);
       }
+     }
     }
   }
 }
 
-int latent_bwd(const LatentBwdArgs& a, cudaStream_t s) {
+int latent_bwd(const LatentBwdArgs& a_in, cudaStream_t s) {
+  static const int fast_env = getenv("NEF_LATENT_FAST") ? atoi(getenv("NEF_LATENT_FAST")) : 1;   // A/B switch: 0 = general kernel only
+  LatentBwdArgs a = a_in;
   const size_t smem = (size_t)2 * 4 * 7 * 32 * sizeof(float) + (size_t)2 * LB_TL * sizeof(float4);
-  dim3 grid(2, 32, a.z1.B);
+  // production dataflow of the z1 half (fp16 gradient copies in, fp16 gz1 copy out only): its own batched-load kernel
+  const bool z1_fast = fast_env && !a.direct && a.du0h[0] && a.du0h[1] && a.du0h[2] && a.gz1_h && a.skip_gz1_32 && a.s16;
+  a.only_half = z1_fast ? 1 : -1;
+  if (z1_fast) {
+    latent_bwd_z1_kernel<<<dim3(32, a.z1.B), 256, 0, s>>>(a);
+    NEF_CHECK_LAUNCH("latent_bwd_z1_kernel");
+  }
+  dim3 grid(z1_fast ? 1 : 2, 32, a.z1.B);
   latent_bwd_kernel<<<grid, 256, smem, s>>>(a);
   NEF_CHECK_LAUNCH("latent_bwd_kernel");
   return 0;
@@ -1027,7 +1171,7 @@ int replicate_f32(const float* src, float* dst, int n, int total, cudaStream_t s
 // One block per channel: the per-tile partial sums are reduced in a fixed order (thread-strided double
 // accumulation, then a fixed shared-memory tree), so equal conv outputs give bit-equal statistics.
 // (A coalesced variant -- 8 channels x 32 record lanes per block -- was 6x slower: 157 dependent-latency steps per thread.)
-constexpr int BNF_T = 512;  // the reduction is latency-bound (one strided load per record): many short per-thread chains
+constexpr int BNF_T = 512;  // the reduction is latency-bound (one strided load per record): many short per-thread chains (1024 threads x 4 records per step measured 10 % slower)
 __global__ void __launch_bounds__(BNF_T) bn_finalize_kernel(BnLayer bn, int C, double count, const float* __restrict__ gamma,
                                                             const float* __restrict__ beta, float* rmean, float* rvar,
                                                             int64_t* nbt, int training) {
@@ -1521,11 +1665,16 @@ int bnbwd_apply_h(const T4* da, const void* da16, T4 c, const BnLayer& bn, const
 // ===========================================================================================
 // Output layer: relu(bn4(c4)) -> Conv1d(64 -> 1, k3, p1) -> sigmoid(x / 3)    model_nefnet.py:106,168
 // ===========================================================================================
-__global__ void __launch_bounds__(128) dec_out_fwd_kernel(T4 c4t, const float* __restrict__ scale,
-                                                          const float* __restrict__ shift, const float* __restrict__ w,
-                                                          const float* __restrict__ bias, float* __restrict__ out,
-                                                          int out_bstride) {
+// Each thread loads ONE row (all 16 chunks in flight together), forms the three tap products T_t[l] = sum_c w[c][t] a4[l][c] of
+// its own position and takes T_0[l-1] / T_2[l+1] from its neighbours through shared memory: out[l] = b + T_0[l-1] + T_1[l] + T_2[l+1].
+// A block covers DOF_OUT consecutive outputs of a segment with one halo thread either side.
+constexpr int DOF_T = 128, DOF_OUT = DOF_T - 2;
+__global__ void __launch_bounds__(DOF_T) dec_out_fwd_kernel(T4 c4t, const float* __restrict__ scale,
+                                                            const float* __restrict__ shift, const float* __restrict__ w,
+                                                            const float* __restrict__ bias, float* __restrict__ out,
+                                                            int out_bstride, int spans) {
   __shared__ float4 ws[3][16], scs[16], shs[16];
+  __shared__ float t0s[DOF_T], t2s[DOF_T];
   const int tid = threadIdx.x;
   if (tid < 48) {
     const int t = tid / 16, c = tid % 16;
@@ -1536,27 +1685,34 @@ __global__ void __launch_bounds__(128) dec_out_fwd_kernel(T4 c4t, const float* _
   }
   __syncthreads();
   const int L = c4t.L;
-  const long total = (long)c4t.B * L;
-  for (long i = blockIdx.x * (long)blockDim.x + tid; i < total; i += (long)gridDim.x * blockDim.x) {
-    const int l = i % L;
-    const int b = i / L;
-    float acc = bias[0];
-#pragma unroll 4
-    for (int c = 0; c < 16; ++c) {
-      const float4* p = c4t.at(c, b, l);
-      const float4 a1 = bn_relu4(p[0], scs[c], shs[c]);
-      float4 s = a1 * ws[1][c];
-      if (l > 0) s = s + bn_relu4(p[-1], scs[c], shs[c]) * ws[0][c];
-      if (l + 1 < L) s = s + bn_relu4(p[1], scs[c], shs[c]) * ws[2][c];
-      acc += (s.x + s.y) + (s.z + s.w);
-    }
+  const int b = blockIdx.x / spans;
+  const int l = (blockIdx.x - b * spans) * DOF_OUT - 1 + tid;   // this thread's row (a halo row at both ends of the block)
+  const bool in = l >= 0 && l < L;
+  float4 v[16];
+  const float4* p = c4t.at(0, b, in ? l : 0);
+#pragma unroll
+  for (int c = 0; c < 16; ++c) v[c] = __ldg(p + (long)c * c4t.cs);
+  float T0 = 0.f, T1 = 0.f, T2 = 0.f;
+#pragma unroll
+  for (int c = 0; c < 16; ++c) {
+    const float4 a1 = bn_relu4(v[c], scs[c], shs[c]);
+    const float4 s0 = a1 * ws[0][c], s1 = a1 * ws[1][c], s2 = a1 * ws[2][c];
+    T0 += (s0.x + s0.y) + (s0.z + s0.w);
+    T1 += (s1.x + s1.y) + (s1.z + s1.w);
+    T2 += (s2.x + s2.y) + (s2.z + s2.w);
+  }
+  t0s[tid] = in ? T0 : 0.f;   // rows outside the segment are the convolution's zero padding
+  t2s[tid] = in ? T2 : 0.f;
+  __syncthreads();
+  if (tid >= 1 && tid <= DOF_OUT && in) {
+    const float acc = bias[0] + t0s[tid - 1] + T1 + t2s[tid + 1];
     out[(long)b * out_bstride + l] = 1.0f / (1.0f + expf(-acc * (1.0f / 3.0f)));
   }
 }
 int dec_out_fwd(T4 c4, const float* scale, const float* shift, const float* w, const float* b, float* out,
                 int out_bstride, cudaStream_t s) {
-  const long total = (long)c4.B * c4.L;
-  dec_out_fwd_kernel<<<grid_for(total, 128), 128, 0, s>>>(c4, scale, shift, w, b, out, out_bstride);
+  const int spans = (c4.L + DOF_OUT - 1) / DOF_OUT;
+  dec_out_fwd_kernel<<<(unsigned)((long)c4.B * spans), DOF_T, 0, s>>>(c4, scale, shift, w, b, out, out_bstride, spans);
   NEF_CHECK_LAUNCH("dec_out_fwd_kernel");
   return 0;
 }
@@ -1680,7 +1836,7 @@ __global__ void __launch_bounds__(256, 3) dec_out_bwd_h_kernel(T4 c4t, BnLayer b
   float4 s1 = f4zero(), s2 = f4zero(), a_m = f4zero(), a_0 = f4zero(), a_p = f4zero();
   float dbl = 0.f;
   const int spans = (L + DOH_SPAN - 1) / DOH_SPAN;
-  for (long u = blockIdx.x; u < (long)c4t.B * spans; u += gridDim.x) {
+  for (long u = blockIdx.x; u < (long)c4t.B * spans; u += gridDim.x) {   // (32-bit unit arithmetic measured 12 % SLOWER)
     const int b = (int)(u / spans);
     const int l0 = (int)(u - (long)b * spans) * DOH_SPAN;
     const int l = l0 + pg * DOH_R;

@@ -91,6 +91,7 @@ struct LatentBwdArgs {
   int direct;             // 1: dlat[k] ARE the latent gradients (no upsample / query adjoint, dq untouched); 0: from du0
   T4 dlat[3];
   const void* du0h[3];    // optional: read d u0_k from these loss-scaled fp16 copies (geometry of du0[k], times s16[0]; s16[1] = 1 / S)
+  int only_half;          // set by latent_bwd(): -1 = the general kernel does both halves, 1 = the z2 half only (the z1 half ran in latent_bwd_z1_kernel)
 };
 int latent_bwd(const LatentBwdArgs& a, cudaStream_t s);
 struct UpqAdjArgs { T4 du0[3]; T4 lat2[3]; T4 dlat2[3]; const float* q; int q_stride; float* dq; };
