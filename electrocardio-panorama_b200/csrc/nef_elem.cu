@@ -417,28 +417,26 @@ __global__ void roi_align_fwd_kernel(T4 z2c, const int64_t* __restrict__ rois, T
   }
 }
 
-// One thread per (4-channel chunk, segment), adjacent threads on adjacent segments (a per-segment block with the weights in
-// shared memory measured 65 % SLOWER: its threads stride over chunk planes).  The tent weight of a (roi, sample) is evaluated
-// once for the thread's four channels; per channel the (roi, sample) summation order is unchanged.
+// (Tried: a per-segment block with the 7 x 16 tent weights in shared memory -- 65 % slower, its threads stride over chunk planes;
+// one weight evaluation per (roi, sample) for the thread's four channels -- 60 % slower, the four interleaved planes thrash L1.)
 __global__ void roi_align_bwd_kernel(T4 dra, const int64_t* __restrict__ rois, T4 z2c, T4 gz2c, Window win, int L4) {
   const long total = (long)(z2c.C / 4) * z2c.B;
   const int c0 = win.y0 - win.w0;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     const int b = i % z2c.B;
     const int c4 = i / z2c.B;
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int j = 0; j < NEF_NROI; ++j) {
-      const float4* dp[4];
+    float4 dc = f4zero();
 #pragma unroll
-      for (int k = 0; k < 4; ++k) dp[k] = dra.at(((c4 * 4 + k) * NEF_NROI + j) >> 2, b, 0);
-#pragma unroll 4
-      for (int s = 0; s < NEF_ROI_SIZE; ++s) {
-        const float wgt = roi_wx(rois, b, j, s, L4);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) acc[k] += f4get(dp[k][s], ((c4 * 4 + k) * NEF_NROI + j) & 3) * wgt;
+    for (int k = 0; k < 4; ++k) {
+      const int c = c4 * 4 + k;
+      float acc = 0.f;
+      for (int j = 0; j < NEF_NROI; ++j) {
+        const int ch = c * NEF_NROI + j;
+        const float4* dp = dra.at(ch >> 2, b, 0);
+        for (int s = 0; s < NEF_ROI_SIZE; ++s) acc += f4get(dp[s], ch & 3) * roi_wx(rois, b, j, s, L4);
       }
+      f4at(dc, k) = acc;
     }
-    const float4 dc = make_float4(acc[0], acc[1], acc[2], acc[3]);
     for (int l = 0; l < win.Lw; ++l) {
       float wgt = 0.f;
       if (l == c0) wgt = 1.0f - win.wy1;
