@@ -399,8 +399,8 @@ def main():
         def step(inp):
             outs = model(inp["x"], inp["input_thetas"], inp["query_theta"], inp["rois"], phase="train")
             loss = loss_fn(outs[0], outs[1], outs[2], inp["target"], Cfg)[0]
-            loss.backward()      # world > 1: backward() itself averages the gradients over the ranks (two bucketed NCCL
-            opt.step()           # all-reduces of the flat buffer, the first overlapped with the encoder's backward)
+            loss.backward()      # world > 1: backward() itself averages the gradients over the ranks (one NCCL all-reduce of
+            opt.step()           # the flat buffer; NEF_DDP_OVERLAP=1: two buckets, the first beside the encoder's backward)
             opt.zero_grad()
             return loss
 
@@ -519,7 +519,7 @@ def main():
         breakdown = {"allreduce_ms": ms_ar, "allreduce_bytes": int(fg.numel()) * 4,
                      "step_ms_without_exchange_per_rank": per_rank,
                      "step_ms_without_exchange_min": min(per_rank), "step_ms_without_exchange_max": max(per_rank),
-                     "overlap": os.environ.get("NEF_DDP_OVERLAP", "1" if world <= 2 else "0") != "0"}
+                     "overlap": os.environ.get("NEF_DDP_OVERLAP", "0") != "0"}
 
     ms_step = ms / args.steps
     units = B * (V if sweep else 1)

@@ -895,11 +895,15 @@ __global__ void __launch_bounds__(256, 2) latent_bwd_z1_kernel(const LatentBwdAr
 }
 
 // Backward of the above.  d lat_k = q * up^T(d u0_k);  d q += sum lat_k * up^T(d u0_k)
-__global__ void __launch_bounds__(256, 3) latent_bwd_kernel(const LatentBwdArgs a) {
+// MODE 0: the general kernel (both halves, every dataflow).  MODE 1: the z2 half alone on the production dataflow (fp16 gradient
+// copies in; the z1 half ran in latent_bwd_z1_kernel) -- the other paths compile away, which leaves room for four blocks per SM.
+template <int MODE>
+__global__ void __launch_bounds__(256, MODE == 1 ? 4 : 3) latent_bwd_kernel(const LatentBwdArgs a) {
   extern __shared__ float4 sm[];
   const int L4 = a.z1.L;
-  const int half = a.only_half >= 0 ? a.only_half : blockIdx.x, cc = blockIdx.y, b = blockIdx.z;  // memory-bound z1 blocks next to atomics-bound z2 blocks
+  const int half = MODE == 1 ? 1 : (a.only_half >= 0 ? a.only_half : blockIdx.x), cc = blockIdx.y, b = blockIdx.z;  // memory-bound z1 blocks next to atomics-bound z2 blocks
   const int tid = threadIdx.x, lane = tid & 31;
+  const bool direct = MODE == 1 ? false : a.direct != 0;
   float* Tm = reinterpret_cast<float*>(sm);  // [4][7][32] adjoint-resampled d(mean) / d(pick)   (z2 half)
   float* Tp = Tm + 4 * 7 * 32;
   float4* sdm = sm + 2 * 7 * 32;             // [LB_TL] d(mean latent), d(picked latent) of the current tile (z2 half)
@@ -913,14 +917,14 @@ __global__ void __launch_bounds__(256, 3) latent_bwd_kernel(const LatentBwdArgs 
   // read its sample -- no atomics, fixed summation order
   float accM[4] = {0.f, 0.f, 0.f, 0.f}, accP[4] = {0.f, 0.f, 0.f, 0.f};
   const int latc = half * 32 + cc;
-  const float4 qv = a.direct ? make_float4(1.f, 1.f, 1.f, 1.f) : *reinterpret_cast<const float4*>(a.q + (long)b * a.q_stride + latc * 4);
+  const float4 qv = direct ? make_float4(1.f, 1.f, 1.f, 1.f) : *reinterpret_cast<const float4*>(a.q + (long)b * a.q_stride + latc * 4);
   const float invG = 1.0f / (float)a.G;
   float4 dq = f4zero();
   const int L2 = 2 * L4;
   const float s16 = (a.gz1_h && a.s16) ? __ldg(a.s16) : 1.f;
   const float inv16 = a.s16 ? __ldg(a.s16 + 1) : 1.f;   // 1 / S of the loss-scaled fp16 input gradients du0h
   const float s16z = (a.gz2o_h && a.s16) ? __ldg(a.s16) : 1.f;
-  const bool all_h = !a.direct && a.du0h[0] && a.du0h[1] && a.du0h[2];   // (block-uniform)
+  const bool all_h = MODE == 1 || (!direct && a.du0h[0] && a.du0h[1] && a.du0h[2]);   // (block-uniform)
   for (int t0 = 0; t0 < L4; t0 += LB_TL) {
    const int nl = min(LB_TL, L4 - t0);
    for (int l = t0 + tid; l < t0 + nl; l += 256) {
@@ -949,10 +953,10 @@ __global__ void __launch_bounds__(256, 3) latent_bwd_kernel(const LatentBwdArgs 
         dk[k3] = d * inv16;
       }
     } else {
-     if (half == 1 && !a.direct) { lm = *a.lat[0].at(latc, b, l); lp = *a.lat[2].at(latc, b, l); }
+     if (half == 1 && !direct) { lm = *a.lat[0].at(latc, b, l); lp = *a.lat[2].at(latc, b, l); }
 #pragma unroll
      for (int k3 = 0; k3 < 3; ++k3) {
-      if (a.direct) {   // the latent gradients themselves are given (Model_nefnet2: upq_adjoint and two convolutions ran before)
+      if (direct) {   // the latent gradients themselves are given (Model_nefnet2: upq_adjoint and two convolutions ran before)
         dk[k3] = *a.dlat[k3].at(latc, b, l);
         continue;
       }
@@ -1009,7 +1013,7 @@ __global__ void __launch_bounds__(256, 3) latent_bwd_kernel(const LatentBwdArgs 
       dq = dq + (dk[0] + dk[2]) * (msum * invG) + dk[1] * pick;
     } else {
       // lat_0 = lat_1 = mean (this half), lat_2 = lead c2
-      if (!a.direct) dq = dq + (dk[0] + dk[1]) * lm + dk[2] * lp;
+      if (!direct) dq = dq + (dk[0] + dk[1]) * lm + dk[2] * lp;
       sdm[l - t0] = (dk[0] + dk[1]) * qv;
       sdp[l - t0] = dk[2] * qv;
     }
@@ -1058,7 +1062,7 @@ __global__ void __launch_bounds__(256, 3) latent_bwd_kernel(const LatentBwdArgs 
     if (lane == 0) atomicAdd(&dq_s[k], v);
   }
   __syncthreads();
-  if (tid < 4 && !a.direct) a.dq[(long)b * 256 + latc * 4 + tid] = dq_s[tid];
+  if (tid < 4 && !direct) a.dq[(long)b * 256 + latc * 4 + tid] = dq_s[tid];
   if (half == 1) {
     // g z2o[(g*128 + 4cc + k)*7 + j][pos] = (Tm/G + [g == c2] Tp) * (z2o > 0)
     constexpr int ZB = 4;   // rows per batch: their loads are in flight together
@@ -1108,7 +1112,8 @@ int latent_bwd(const LatentBwdArgs& a_in, cudaStream_t s) {
     NEF_CHECK_LAUNCH("latent_bwd_z1_kernel");
   }
   dim3 grid(z1_fast ? 1 : 2, 32, a.z1.B);
-  latent_bwd_kernel<<<grid, 256, smem, s>>>(a);
+  if (z1_fast) latent_bwd_kernel<1><<<grid, 256, smem, s>>>(a);
+  else latent_bwd_kernel<0><<<grid, 256, smem, s>>>(a);
   NEF_CHECK_LAUNCH("latent_bwd_kernel");
   return 0;
 }

@@ -108,8 +108,9 @@ class Model_nefnet(nn.Module):
         self._flat = None
         self._flat_grad = None
         # data parallel (one process per GPU): when a torch.distributed process group with more than one rank is initialised,
-        # backward() itself averages the gradients over the ranks -- two bucketed all-reduces, the first overlapped with
-        # the encoder's backward -- so the reference's unmodified solver.py:232-235 (backward(); optim.step()) trains data
+        # backward() itself averages the gradients over the ranks -- one all-reduce of the flat gradient buffer (or, with
+        # NEF_DDP_OVERLAP=1, two buckets, the first overlapped with the encoder's backward) -- so the reference's unmodified
+        # solver.py:232-235 (backward(); optim.step()) trains data
         # parallel under torchrun.  Set False to exchange gradients yourself (network.optim.allreduce_gradients).
         self.ddp_allreduce = True
         # Mis-tiled ROIs: the reference raises (torch.stack / torch.cat size mismatch, roi_pooling_1d.py:96-98) when the
@@ -431,11 +432,12 @@ class Model_nefnet(nn.Module):
             # bucket 1 (z1_conv .. decoder, 2/3 of the bytes) is final long before the encoder's backward ends: reduce it on
             # a side stream behind the event nef_backward recorded; bucket 0 (stem, encoder, mlp, w_conv) follows on the
             # main stream.  ReduceOp.AVG: the mean over ranks, as DataParallel's gradient of the batch-mean loss.
-            # Overlap policy (NEF_DDP_OVERLAP=0 / 1 forces it): measured on one box each, the overlapped form wins at 2 ranks
-            # (35.35 vs 35.47 ms) and loses at 8 (35.01 vs 34.79 ms) -- the NCCL kernel's CTAs keep a few SMs from taking
-            # their CTA of every persistent conv launch it runs beside (static tile walk), and at 8 ranks it runs longer.
+            # Default: ONE all-reduce behind the whole backward; NEF_DDP_OVERLAP=1 selects the bucketed, overlapped form.
+            # Measured on one box each: at 2 ranks the two forms tie (35.35 vs 35.47 ms; 35.30 vs 35.22 / 35.34 ms), at 8 the
+            # overlapped one loses (35.01 vs 34.79 ms) -- the NCCL kernel's CTAs keep a few SMs from taking their CTA of every
+            # persistent conv launch it runs beside (static tile walk), and at 8 ranks it runs longer.
             split = self._ddp_split
-            overlap = os.environ.get("NEF_DDP_OVERLAP", "1" if world <= 2 else "0") != "0"
+            overlap = os.environ.get("NEF_DDP_OVERLAP", "0") != "0"
             if not overlap:     # one all-reduce behind the whole backward
                 dist.all_reduce(self._flat_grad, op=dist.ReduceOp.AVG)
                 split = None

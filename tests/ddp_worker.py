@@ -1,8 +1,8 @@
 """Worker of tests/test_gpu_ddp.py (one process per GPU under torchrun): the module's built-in data-parallel exchange.
 
 Every rank builds the model from a DIFFERENT seed (the first forward must broadcast rank 0's parameters), runs one training
-step on its shard with the built-in all-reduce (backward() averages the gradients over the ranks, bucket 1 overlapped on a
-side stream), then re-runs EVERY shard locally with the exchange off and checks
+step on its shard with the built-in all-reduce (backward() averages the gradients over the ranks: one all-reduce, or with
+NEF_DDP_OVERLAP=1 two buckets, the first overlapped on a side stream), then re-runs EVERY shard locally with the exchange off and checks
     gradients after backward()  ==  mean over shards of the local gradients
 to fp32 summation noise.  Dropout is off (per-rank dropout seeds differ by design); BatchNorm statistics are per replica, as
 under nn.DataParallel (solver.py:32-34)."""

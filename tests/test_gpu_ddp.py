@@ -20,11 +20,12 @@ def _free_port():
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-def test_builtin_allreduce_equals_mean_of_shard_gradients():
+@pytest.mark.parametrize("overlap", ["0", "1"])   # one all-reduce behind the backward (default) / two buckets, the first overlapped
+def test_builtin_allreduce_equals_mean_of_shard_gradients(overlap):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
            "--master-port", str(_free_port()), os.path.join(root, "tests", "ddp_worker.py")]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root, env=dict(os.environ, NEF_DDP_OVERLAP=overlap))
     print(r.stdout[-3000:])
     print(r.stderr[-3000:])
     assert r.returncode == 0 and "DDP_OK" in r.stdout
