@@ -657,8 +657,14 @@ struct PsSmem {
   static constexpr int XROWS = MT * 128 + 8;
   static constexpr int XPITCH = XROWS * 16;
   static constexpr int XBYTES = 8 * XPITCH;
-  static constexpr int XST = 3;
-  static constexpr int WST = 6;
+#ifndef NEF_PS_XST
+#define NEF_PS_XST 3
+#endif
+#ifndef NEF_PS_WST
+#define NEF_PS_WST 6
+#endif
+  static constexpr int XST = NEF_PS_XST;   // activation stages (33 KB each) and weight stages (16 KB each) of the operand pipeline
+  static constexpr int WST = NEF_PS_WST;   // (-DNEF_PS_XST / -DNEF_PS_WST: A/B builds, loaded through NEFNET_B200_LIB)
   static constexpr int BAR_OFF = XST * XBYTES + WST * FW_WBYTES;
   static constexpr int STAT_OFF = BAR_OFF + 256;
   static constexpr int TOTAL = STAT_OFF + 4 * 2 * 128 * 4 + 128;
