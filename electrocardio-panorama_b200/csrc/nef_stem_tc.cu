@@ -181,9 +181,7 @@ __global__ void __launch_bounds__(SF_THREADS, 512 / (SF_NC == 32 ? 128 : 64)) st
   // the input window of a tile (x[4 j0 - 9 + i], i < SF_XW + 8) is fetched into registers one tile ahead, behind the epilogue
   constexpr int XPT = (SF_XW + 8 + SF_THREADS - 1) / SF_THREADS;
   float xv[XPT];
-  auto fetch_window = [&](int u) {
-    const int b = u / ntile;
-    const int j0 = (u - b * ntile) * SF_TJ;
+  auto fetch_window = [&](int b, int j0) {
     const float* xb = x + ((long)b * G + g) * L;
 #pragma unroll
     for (int k = 0; k < XPT; ++k) {
@@ -192,13 +190,20 @@ __global__ void __launch_bounds__(SF_THREADS, 512 / (SF_NC == 32 ? 128 : 64)) st
       xv[k] = (i < SF_XW + 8 && p >= 0 && p < L) ? __ldg(xb + p) : 0.f;
     }
   };
-  fetch_window(blockIdx.x);
+  // (segment, tile) of unit u advance incrementally: one division pair per kernel instead of two per tile
+  const int step_b = (int)gridDim.x / ntile, step_t = (int)gridDim.x % ntile;
+  int b = (int)blockIdx.x / ntile, tl_i = (int)blockIdx.x % ntile;
+  // per-CTA output bases: 4-channel chunk g * 32 + cq * (SF_NC / 4) of the codes, 8-channel chunk of the fp16 copy; the chunk
+  // stride fits 32 bits (rows per chunk plane), so a chunk offset is one 32 x 32 -> 64-bit multiply
+  const uint32_t cs32 = (uint32_t)y.cs;
+  uint32_t* const amax_c = amax ? amax + (size_t)(g * 32 + cq * (SF_NC / 4)) * cs32 : nullptr;
+  uint4* const y16_c = y16 + (size_t)((g * 32 + cq * (SF_NC / 4)) >> 1) * cs32;
+  fetch_window(b, tl_i * SF_TJ);
   int it = -1;
   for (int u = blockIdx.x; u < y.B * ntile; u += gridDim.x) {
     ++it;
     STEM_STAMP(0);
-    const int b = u / ntile;
-    const int j0 = (u - b * ntile) * SF_TJ;
+    const int j0 = tl_i * SF_TJ;
     // ---- input window as fp16 hi / lo
 #pragma unroll
     for (int k = 0; k < XPT; ++k) {
@@ -264,7 +269,9 @@ __global__ void __launch_bounds__(SF_THREADS, 512 / (SF_NC == 32 ? 128 : 64)) st
       __syncwarp();
     }
     STEM_STAMP(3);
-    if (u + (int)gridDim.x < y.B * ntile) fetch_window(u + gridDim.x);   // in flight behind the MMA wait and the epilogue
+    int nb = b + step_b, nt = tl_i + step_t;   // the next unit of this CTA
+    if (nt >= ntile) { nt -= ntile; ++nb; }
+    if (u + (int)gridDim.x < y.B * ntile) fetch_window(nb, nt * SF_TJ);   // in flight behind the MMA wait and the epilogue
     mbar_wait(bar, ph);
     ph ^= 1;
     tc_fence_after();
@@ -304,16 +311,18 @@ __global__ void __launch_bounds__(SF_THREADS, 512 / (SF_NC == 32 ? 128 : 64)) st
           m[k] = bv;   // the fp16 conversion below is the only rounding
           code |= best << (8 * k);
         }
-        const int ch4 = g * 32 + cq * (SF_NC / 4) + c4;   // 4-channel chunk of the 128 G channel space
-        if (amax && ok) amax[(long)ch4 * y.cs + row] = code;
+        // 4-channel chunk g * 32 + cq * (SF_NC / 4) + c4 of the 128 G channel space
+        if (amax_c && ok) amax_c[(size_t)c4 * cs32 + row] = code;
         hp[(c4 & 1) * 2 + 0] = f16x2_sat(m[0], m[1]);
         hp[(c4 & 1) * 2 + 1] = f16x2_sat(m[2], m[3]);
-        if ((c4 & 1) && ok) y16[(long)(ch4 >> 1) * y.cs + row] = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+        if ((c4 & 1) && ok) y16_c[(size_t)(c4 >> 1) * cs32 + row] = make_uint4(hp[0], hp[1], hp[2], hp[3]);
       }
     }
     tc_fence_before();
     __syncthreads();
     STEM_STAMP(5);
+    b = nb;
+    tl_i = nt;
   }
   if (warp == 0) {
     tc_fence_after();
@@ -386,9 +395,15 @@ __global__ void __launch_bounds__(SB_THREADS, 2) stem_tc_bwd_kernel(const float*
   int issued = 0;
   const int row_l = tid & (SB_TJ - 1), chalf = tid >> 7;   // this thread's tile row, and which 8 of the 16 channel chunks
 
+  // (segment, tile) of unit u advance incrementally; per-thread bases of the gradient rows and codes (the chunk stride fits 32
+  // bits: a chunk offset is one 32 x 32 -> 64-bit multiply instead of a 64 x 64 one per load)
+  const int step_b = (int)gridDim.x / ntile, step_t = (int)gridDim.x % ntile;
+  int b = (int)blockIdx.x / ntile, tl_i = (int)blockIdx.x % ntile;
+  const uint32_t cs32 = (uint32_t)dy.cs;
+  const uint4* const gp_c = dy16 + (size_t)(g * 16 + chalf * 8) * cs32;
+  const uint32_t* const cp_c = amax + (size_t)(2 * (g * 16 + chalf * 8)) * cs32;
   for (int u = blockIdx.x; u < dy.B * ntile; u += gridDim.x) {
-    const int b = u / ntile;
-    const int j0 = (u - b * ntile) * SB_TJ;
+    const int j0 = tl_i * SB_TJ;
     const float* xb = x + ((long)b * G + g) * L;
     // ---- global loads of this tile (all in flight before the previous tile's MMAs are waited for)
     float xv[3];
@@ -405,13 +420,12 @@ __global__ void __launch_bounds__(SB_THREADS, 2) stem_tc_bwd_kernel(const float*
     uint32_t ca[8][2], cb[8][2];
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
-      const int c8 = g * 16 + chalf * 8 + q;
-      const uint4* gp = dy16 + (long)c8 * dy.cs + row;
-      const uint32_t* cp = amax + (long)(2 * c8) * dy.cs + row;
+      const uint4* gp = gp_c + (size_t)q * cs32 + row;              // 8-channel chunk g * 16 + chalf * 8 + q
+      const uint32_t* cp = cp_c + (size_t)(2 * q) * cs32 + row;
       ga[q] = v0 ? __ldg(gp) : make_uint4(0u, 0u, 0u, 0u);
       gb[q] = v1 ? __ldg(gp + 1) : make_uint4(0u, 0u, 0u, 0u);
-      ca[q][0] = __ldg(cp); ca[q][1] = __ldg(cp + dy.cs);
-      cb[q][0] = __ldg(cp + 1); cb[q][1] = __ldg(cp + dy.cs + 1);
+      ca[q][0] = __ldg(cp); ca[q][1] = __ldg(cp + cs32);
+      cb[q][0] = __ldg(cp + 1); cb[q][1] = __ldg(cp + cs32 + 1);
     }
     // ---- the previous tile's MMAs must have read the shared-memory tiles before they are overwritten
     if (issued) {
@@ -476,6 +490,9 @@ __global__ void __launch_bounds__(SB_THREADS, 2) stem_tc_bwd_kernel(const float*
       __syncwarp();
     }
     issued = 1;
+    b += step_b;
+    tl_i += step_t;
+    if (tl_i >= ntile) { tl_i -= ntile; ++b; }
   }
   if (issued) {
     mbar_wait(bar, ph);
