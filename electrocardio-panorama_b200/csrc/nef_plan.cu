@@ -487,6 +487,7 @@ extern "C" int nef_plan_create_v(int B, int G, int L, int V, int variant, NefPla
   NEF_REQUIRE(B >= 1 && G >= 1 && L >= 16 && L % 4 == 0, "nef_plan_create: need B>=1, G>=1, L>=16, L %% 4 == 0 (B=%d G=%d L=%d)",
               B, G, L);
   NEF_REQUIRE(variant == 1 || variant == 2, "nef_plan_create_v: variant must be 1 (Model_nefnet) or 2 (Model_nefnet2)");
+  NEF_REQUIRE((long)B * (L + 2 * NEF_HALO) < (1L << 31), "nef_plan_create: B * (L + halo) must stay below 2^31 rows per chunk plane (the stem kernels multiply chunk strides in 32 bits; B=%d L=%d)", B, L);
   NefPlan* p = new NefPlan();
   memset(p, 0, sizeof(NefPlan));
   p->variant = variant;
